@@ -1,0 +1,234 @@
+/* include/vxl.h -- C ABI of the B200-native voxel-lighting pass (libvxl.so).
+ *
+ * Drop-in boundary for ONE path of carloshgsilva/VoxelEngine: the world occupancy volume built by
+ * ShadowVoxSystem and the four light passes that ray-march it (sun shadow + ambient occlusion,
+ * point-light shadows, spot-light shadows, specular occlusion).  Each entry point names the
+ * reference interface it replaces; paths are relative to the reference tree.
+ *
+ *   reference (Vulkan, fragment shaders)                         this library (CUDA, sm_100a)
+ *   ------------------------------------------------------------ -------------------------------
+ *   ShadowVoxSystem::ShadowVoxSystem()                           vxl_volume_create
+ *     Sources/World/Systems/ShadowVoxSystem.cpp:55-79
+ *   CmdBuffer::copy(buffer, image, regions)                      vxl_volume_upload_regions
+ *     Vendor/evk/evk.cpp:759-780 (called at ShadowVoxSystem.cpp:196)
+ *   ShadowVoxSystem::OnUpdate / OnVoxDestroyed                   vxl_volume_voxelize
+ *     ShadowVoxSystem.cpp:116-201, :7-53
+ *   VoxAsset::Upload (model voxels -> GPU image)                 vxl_model_create
+ *     Sources/Asset/VoxAsset.cpp:3-14
+ *   LightAmbientPipeline::Use                                    vxl_pass_ambient
+ *     Sources/Graphics/Pipelines/LightAmbientPipeline.h:35-52  -> Shaders/LightAmbient.frag:134-175
+ *   LightPointPipeline::Use + DrawLight                          vxl_pass_point
+ *     Pipelines/LightPointPipeline.h:58-100                    -> Shaders/LightPoint.frag:85-129
+ *   LightSpotPipeline::Use + DrawLight                           vxl_pass_spot
+ *     Pipelines/LightSpotPipeline.h:60-104                     -> Shaders/LightSpot.frag:73-117
+ *   LightReflectionPipeline::Use                                 vxl_pass_reflection
+ *     Pipelines/LightReflectionPipeline.h:34-51                -> Shaders/LightReflection.frag:60-113
+ *   raycastShadowVolume{,Sparse,SuperSparse}                     vxl_trace_rays  (ray-level entry)
+ *     Sources/Shaders/lib/Light.frag:29-81,131-173,175-217
+ *   Graphics::Frame / Graphics::Transfer  (record, submit, WAIT) vxl_sync
+ *     Sources/Graphics/Graphics.h:23-32
+ *   whole "Lights" + "Reflection" timestamp blocks, host buffers vxl_lighting_host
+ *     Sources/Graphics/Renderer/WorldRenderer.cpp:239-260,269-274
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative vxl_status otherwise; nothing throws;
+ *     vxl_last_error_string() describes the last failure on the calling thread.
+ *   - unless a parameter is documented as HOST, data pointers are DEVICE pointers on the context's
+ *     GPU and the call is asynchronous on the context's stream (stream-ordered); vxl_sync blocks.
+ *   - one context per GPU, used from one host thread at a time.
+ *   - there is no CPU fallback: without a CUDA device vxl_ctx_create fails with VXL_ERR_CUDA.
+ *   - the new pass contract writes separate float planes where the reference folds shader locals
+ *     into one RGBA16F light target:
+ *        shadow   1 = lit, 0 = occluded                 (LightAmbient.frag:167-169 etc.)
+ *        ao       mean_i((d_i/128)^2) * 0.05            (LightAmbient.frag:121-125)
+ *        spec_t   reflection-ray distance t, 256 = miss (LightReflection.frag:113)
+ *     pixels that generate no ray (sky, range-culled light) hold shadow = 1, ao = 0, spec_t = 256.
+ */
+#ifndef VXL_H
+#define VXL_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VXL_ABI_VERSION 1
+#define VXL_MAX_LIGHTS 64   /* LightPointPipeline.h:15, LightSpotPipeline.h:14 */
+
+typedef enum vxl_status {
+    VXL_OK = 0,
+    VXL_ERR_INVALID = -1,   /* bad argument */
+    VXL_ERR_CUDA = -2,      /* CUDA runtime / launch failure (incl. no device) */
+    VXL_ERR_OOM = -3,
+    VXL_ERR_LIMIT = -4      /* more than VXL_MAX_LIGHTS, etc. */
+} vxl_status;
+
+typedef struct vxl_ctx vxl_ctx;         /* one GPU + one stream */
+typedef struct vxl_volume vxl_volume;   /* packed world occupancy volume + derived occupancy levels */
+
+/* Sources/Graphics/Renderer/View.h:16-30 == GLSL ViewBuffer (lib/Common.frag:45-61). 380 bytes. */
+typedef struct vxl_view {
+    float LastViewMatrix[16], ViewMatrix[16], InverseViewMatrix[16];
+    float ProjectionMatrix[16], InverseProjectionMatrix[16];   /* column-major (glm) */
+    float Res[2], iRes[2];
+    float CameraPosition[3]; int32_t _pad0;
+    float Jitter[2];
+    int32_t Frame;
+    int32_t ColorTextureRID, DepthTextureRID, PalleteColorRID, PalleteMaterialRID;
+} vxl_view;
+
+/* LightPointPipeline.h:20-25 (32 B) and LightSpotPipeline.h:19-28 (64 B) */
+typedef struct vxl_point_light { float Position[3], Range, Color[3], Attenuation; } vxl_point_light;
+typedef struct vxl_spot_light {
+    float Position[3], Range, Color[3], Attenuation, Direction[3], Angle, AngleAttenuation, _pad[3];
+} vxl_spot_light;
+
+/* evk ImageRegion as pushed by ShadowVoxSystem.cpp:189 (texel units) */
+typedef struct vxl_region { int32_t x, y, z; uint32_t w, h, d; int32_t mip; } vxl_region;
+
+/* One visited entity of ShadowVoxSystem::OnUpdate (flags = 0: clear at prev, set at cur, both
+ * translated by -pivot) or one OnVoxDestroyed callback (VXL_ENT_DESTROY: clear at cur, pivot
+ * ignored -- sic, ShadowVoxSystem.cpp:22-25).  Commands apply in array order, last writer wins. */
+typedef struct vxl_entity {
+    int32_t model;      /* id from vxl_model_create */
+    int32_t flags;
+    float   prev[16];   /* Transform::PreviousWorldMatrix (identity on an entity's first frame) */
+    float   cur[16];    /* Transform::WorldMatrix */
+    float   pivot[3];   /* VoxRenderer::Pivot */
+    int32_t _pad;
+} vxl_entity;
+enum { VXL_ENT_DESTROY = 1 };
+
+/* G-buffer + noise inputs of a (shard of a) frame.  Planes are "tile-compact": local tile i
+ * (i < n_tiles) is global tile tile_first + i*tile_stride of the tile_w x tile_h grid laid
+ * row-major over the width x height frame, stored as [n_tiles][tile_h][tile_w].  A whole frame on
+ * one GPU is the single tile tile_w = width, tile_h = height (plain row-major, row 0 = top).
+ *   depth24  D24 unorm in the low 24 bits, linear (w-NEAR)/(FAR-NEAR); sky = 0xFFFFFF
+ *            (Graphics.h:59; GeometryVoxel.frag:169; GeometrySky.frag:30)
+ *   normal   R8G8B8A8_SNORM world-space normal (Graphics.h:56; GeometryVoxel.frag:156)
+ *   material UNORM8 .r roughness .g metallic .b emit (Graphics.h:57); only the spec pass reads it
+ *   noise    512 x 512 RGBA8 blue noise (Assets/.../LDR_RGBA_0.png), NOT tiled                  */
+typedef struct vxl_frame {
+    int32_t width, height;
+    int32_t tile_w, tile_h;
+    int32_t tile_first, tile_stride, n_tiles;
+    int32_t _pad;
+    const uint32_t* depth24;
+    const uint32_t* normal;
+    const uint32_t* material;
+    const uint32_t* noise;
+} vxl_frame;
+
+/* rays generated / occupancy probes performed by the reference algorithm / ray-generating pixels */
+typedef struct vxl_stats { uint64_t rays, steps, pixels; } vxl_stats;
+
+/* ray-level interface (level-1 parity): 32-byte rays in, 48-byte records out */
+typedef struct vxl_ray { float ox, oy, oz, dx, dy, dz, dist, pad; } vxl_ray;
+typedef struct vxl_hit {
+    float t; int32_t steps; int32_t vx, vy, vz; int32_t status;
+    float px, py, pz; float nx, ny, nz;
+} vxl_hit;
+enum { VXL_TRACE_SPARSE = 0, VXL_TRACE_SUPERSPARSE = 1, VXL_TRACE_DDA = 2 };
+
+/* ---- library / context ------------------------------------------------------------------------ */
+int         vxl_abi_version(void);
+const char* vxl_last_error_string(void);
+int vxl_ctx_create(int device, vxl_ctx** out);
+int vxl_ctx_destroy(vxl_ctx* ctx);
+/* use an existing cudaStream_t (e.g. torch's current stream) instead of the context's own */
+int vxl_ctx_set_stream(vxl_ctx* ctx, void* cuda_stream);
+int vxl_sync(vxl_ctx* ctx);
+/* device counters accumulated by every pass since the last reset (vxl_stats_read synchronises) */
+int vxl_stats_reset(vxl_ctx* ctx);
+int vxl_stats_read(vxl_ctx* ctx, vxl_stats* out /* HOST */);
+/* number of kernels this library launched on the context since creation (bench gpu_launches) */
+int vxl_launch_count(vxl_ctx* ctx, uint64_t* out /* HOST */);
+
+/* raw memory helpers so a C caller needs no CUDA headers */
+int vxl_malloc(vxl_ctx* ctx, size_t bytes, void** out_dev);
+int vxl_free(vxl_ctx* ctx, void* dev);
+int vxl_host_alloc(size_t bytes, void** out_pinned);
+int vxl_host_free(void* pinned);
+int vxl_memcpy_h2d(vxl_ctx* ctx, void* dev, const void* host, size_t bytes);   /* async on stream */
+int vxl_memcpy_d2h(vxl_ctx* ctx, void* host, const void* dev, size_t bytes);   /* async on stream */
+int vxl_memset(vxl_ctx* ctx, void* dev, int value, size_t bytes);
+
+/* ---- world occupancy volume (ShadowVoxSystem) -------------------------------------------------- */
+/* sx,sy,sz in TEXELS (bytes); each byte packs 2x2x2 voxels, bit = (x&1)|(y&1)<<1|(z&1)<<2
+ * (ShadowVoxSystem.cpp:82-94).  Created zero-filled like the reference constructor. */
+int vxl_volume_create(vxl_ctx* ctx, int sx, int sy, int sz, vxl_volume** out);
+int vxl_volume_destroy(vxl_volume* vol);
+int vxl_volume_dims(const vxl_volume* vol, int* sx, int* sy, int* sz);
+/* copy `n` regions from a HOST staging buffer of the full volume size, with the addressing of
+ * CmdBuffer::copy: byte (x,y,z) at x + y*sx + z*sx*sy in both buffers */
+int vxl_volume_upload_regions(vxl_volume* vol, const uint8_t* host_staging, const vxl_region* regions /* HOST */, int n);
+int vxl_volume_upload(vxl_volume* vol, const uint8_t* host_bytes);   /* whole volume */
+int vxl_volume_download(vxl_volume* vol, uint8_t* host_bytes);       /* synchronises */
+int vxl_volume_clear(vxl_volume* vol);
+/* device pointer of the canonical packed bytes (x fastest); writing through it requires a
+ * following vxl_volume_mark_dirty */
+int vxl_volume_device_ptr(vxl_volume* vol, uint8_t** out_dev);
+int vxl_volume_mark_dirty(vxl_volume* vol);
+/* (re)build the derived occupancy levels used to skip empty space.  Pure acceleration: never
+ * changes a result.  Called implicitly by the passes when the volume is dirty. */
+int vxl_volume_build_occupancy(vxl_volume* vol);
+
+/* register a model: palette indices, x fastest (VoxAsset.h:52-56); 0 empty, 1..15 glass (not an
+ * occluder), >= 16 solid (ShadowVoxSystem.cpp:145).  voxels is a HOST pointer. */
+int vxl_model_create(vxl_ctx* ctx, const uint8_t* voxels, int sx, int sy, int sz, int* out_id);
+/* apply `n` commands with the reference's sequential semantics.  ents, out_regions (n entries)
+ * and out_valid (n entries; 0 = the reference would push no region) are HOST pointers; the two
+ * outputs may be NULL.  Synchronises only when an output is requested. */
+int vxl_volume_voxelize(vxl_volume* vol, const vxl_entity* ents, int n, vxl_region* out_regions, int32_t* out_valid);
+
+/* ---- light passes ------------------------------------------------------------------------------ */
+/* view/lights are HOST pointers (copied at call time); frame planes and outputs are DEVICE
+ * pointers in the frame's tile-compact layout; outputs may be NULL to skip a plane.
+ * n_ao = AO rays per pixel: 1 reproduces the reference; ray 0 uses getNoise(), ray i >= 1 uses
+ * getNoise(i) (LightAmbient.frag:44-47). */
+int vxl_pass_ambient(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, const vxl_frame* frame,
+                     int n_ao, float* out_shadow, float* out_ao);
+/* out_shadow: n_lights consecutive planes */
+int vxl_pass_point(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, const vxl_frame* frame,
+                   const vxl_point_light* lights, int n_lights, float* out_shadow);
+int vxl_pass_spot(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, const vxl_frame* frame,
+                  const vxl_spot_light* lights, int n_lights, float* out_shadow);
+int vxl_pass_reflection(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, const vxl_frame* frame,
+                        float* out_spec_t);
+/* rays/out are DEVICE pointers */
+int vxl_trace_rays(vxl_ctx* ctx, vxl_volume* vol, const vxl_ray* rays, int64_t n, int variant, vxl_hit* out);
+
+/* ---- whole-frame drop-in with HOST buffers ----------------------------------------------------- */
+/* What a renderer that keeps its G-buffer on the host side of the boundary calls once per frame:
+ * H2D of the frame shard, ambient + point + spot + reflection passes, D2H of the output planes.
+ * All pointers HOST (pinned memory recommended: vxl_host_alloc).  Planes use the frame's
+ * tile-compact layout.  Any output pointer may be NULL (that pass is skipped when all of its
+ * outputs are NULL).  Blocks until the outputs are in host memory. */
+typedef struct vxl_lighting_host_args {
+    vxl_frame frame;                 /* plane pointers are HOST pointers here */
+    const vxl_view* view;
+    int32_t n_ao;
+    int32_t n_point, n_spot;
+    const vxl_point_light* point;
+    const vxl_spot_light* spot;
+    float* out_shadow;               /* [tiles] */
+    float* out_ao;                   /* [tiles] */
+    float* out_point_shadow;         /* [n_point][tiles] */
+    float* out_spot_shadow;          /* [n_spot][tiles] */
+    float* out_spec_t;               /* [tiles] */
+} vxl_lighting_host_args;
+int vxl_lighting_host(vxl_ctx* ctx, vxl_volume* vol, const vxl_lighting_host_args* args);
+
+/* ---- synthetic inputs (not reference passes) ------------------------------------- */
+/* FastNoise-Perlin terrain: voxel solid iff GetTerrainNoise(x,y,z) > (y/NY - 0.5)*2
+ * (Sources/Util/Noise.cpp:131-135, FastNoise seed 1337 freq 0.01). Overwrites the volume. */
+int vxl_volume_gen_terrain(vxl_volume* vol);
+/* primary-visibility G-buffer through the packed volume (A4 DDA arithmetic, reference encodings).
+ * Writes the frame's depth24/normal/material planes (cast away const: DEVICE, writable). */
+int vxl_gbuffer_primary(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, const vxl_frame* frame);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VXL_H */

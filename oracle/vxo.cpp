@@ -1,0 +1,823 @@
+// oracle/vxo.cpp -- CPU ORACLE (test infrastructure only; see the header of vxo.h).
+//
+// Build: g++ -O2 -ffp-contract=off -fno-fast-math -fopenmp   (oracle/Makefile)
+// Every `a*b+c` below is two roundings -- no FMA contraction -- on purpose: the CUDA product is
+// compiled with --fmad=false and must agree with this file bit-for-bit.
+//
+// Pinned choices for GLSL-undefined behaviour:
+//   * out-of-range texelFetch            -> 0
+//   * ivec3(float)                       -> truncation toward zero, saturating to INT_MIN/MAX,
+//                                           NaN -> 0 (the semantics of PTX cvt.rzi.s32.f32)
+//   * integer / 2 on negatives           -> C truncation
+//   * min(NaN, x)                        -> x (fminf)
+//   * sign(0) = 0, 1/0 = inf, 0*inf = NaN propagate per IEEE-754
+// Operation orders follow glm 0.9.9.9:
+//   dot(a,b) = (a.x*b.x + a.y*b.y) + a.z*b.z         Vendor/glm/detail/func_geometric.inl:48-55
+//   normalize(v) = v * (1/sqrt(dot(v,v)))            func_geometric.inl:82-90
+//   mix(x,y,a) = x*(1-a) + y*a                       func_common.inl:81-89
+//   mod(x,y) = x - y*floor(x/y)                      func_common.inl:212-219
+//   M*v = (M0*v0 + M1*v1) + (M2*v2 + M3*v3)          type_mat4x4.inl:561-572
+#include "vxo.h"
+
+#include <cmath>
+#include <cstring>
+#include <climits>
+#include <random>
+#include <vector>
+#include <algorithm>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+struct V3 { float x, y, z; };
+struct V4 { float x, y, z, w; };
+struct I3 { int x, y, z; };
+
+inline V3 v3(float x, float y, float z) { return V3{x, y, z}; }
+inline V3 operator+(V3 a, V3 b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V3 operator-(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 operator*(V3 a, float s) { return V3{a.x * s, a.y * s, a.z * s}; }
+inline V3 operator*(V3 a, V3 b) { return V3{a.x * b.x, a.y * b.y, a.z * b.z}; }
+inline V3 operator/(V3 a, V3 b) { return V3{a.x / b.x, a.y / b.y, a.z / b.z}; }
+
+inline float dot3(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+inline V3 normalize3(V3 v) { float inv = 1.0f / sqrtf(dot3(v, v)); return v * inv; }
+inline float length3(V3 v) { return sqrtf(dot3(v, v)); }
+inline V3 mix3(V3 x, V3 y, float a) { float ia = 1.0f - a; return x * ia + y * a; }
+inline V3 cross3(V3 a, V3 b) {  // func_geometric.inl:61-72
+    return V3{a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y};
+}
+inline float gmod(float x, float y) { return x - y * floorf(x / y); }
+inline float gsign(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
+inline float gstep(float edge, float x) { return x < edge ? 0.0f : 1.0f; }
+inline float gclamp(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+inline float gsmoothstep(float e0, float e1, float x) {
+    float t = gclamp((x - e0) / (e1 - e0), 0.0f, 1.0f);
+    return t * t * (3.0f - 2.0f * t);
+}
+// cvt.rzi.s32.f32 semantics
+inline int f2i(float x) {
+    if (x != x) return 0;
+    if (x >= 2147483648.0f) return INT_MAX;
+    if (x <= -2147483648.0f) return INT_MIN;
+    return (int)x;
+}
+// column-major mat4 (glm) times vec4
+inline V4 mat_mul(const float* m, V4 v) {
+    V4 r;
+    r.x = (m[0] * v.x + m[4] * v.y) + (m[8] * v.z + m[12] * v.w);
+    r.y = (m[1] * v.x + m[5] * v.y) + (m[9] * v.z + m[13] * v.w);
+    r.z = (m[2] * v.x + m[6] * v.y) + (m[10] * v.z + m[14] * v.w);
+    r.w = (m[3] * v.x + m[7] * v.y) + (m[11] * v.z + m[15] * v.w);
+    return r;
+}
+inline V3 xyz(V4 v) { return V3{v.x, v.y, v.z}; }
+
+const float NEAR_ = 0.1f;      // Sources/Shaders/lib/Common.frag:12
+const float FAR_ = 4096.0f;    // Common.frag:13
+const float GOLDEN_RATIO = 2.118033988749895f;  // Common.frag:9 (sic)
+
+// ---------------------------------------------------------------------------------------------
+// A1  texelFetch(SHADOW_VOX_TEXTURE, p, 0).r  with out-of-range -> 0
+// ---------------------------------------------------------------------------------------------
+inline unsigned fetch(const vxo_volume& v, int x, int y, int z) {
+    if ((unsigned)x >= (unsigned)v.sx || (unsigned)y >= (unsigned)v.sy || (unsigned)z >= (unsigned)v.sz) return 0u;
+    return v.data[(size_t)x + (size_t)y * (size_t)v.sx + (size_t)z * (size_t)v.sx * (size_t)v.sy];
+}
+
+// Sources/Shaders/lib/Light.frag:14-27  getVolumeAt(pos, mip)   (image has one level: realMip==0)
+inline bool get_volume_at(const vxo_volume& v, I3 p, int mip) {
+    int bit = (p.x & 1) | ((p.y & 1) << 1) | ((p.z & 1) << 2);
+    int mask = 1 << bit;
+    p.x /= 2; p.y /= 2; p.z /= 2;
+    unsigned voxel = fetch(v, p.x, p.y, p.z);
+    if (mip % 2 == 1) return voxel != 0u;
+    return (voxel & (unsigned)mask) != 0u;
+}
+
+// ---------------------------------------------------------------------------------------------
+// A2/A3  Light.frag:131-173 raycastShadowVolumeSparse (step0 = 0.5)
+//        Light.frag:175-217 raycastShadowVolumeSuperSparse (step0 = 2.5)
+// The two functions differ only in the initial stepFactor.
+// ---------------------------------------------------------------------------------------------
+float march(const vxo_volume& vol, V3 origin, V3 dir, float dist, float step0, uint64_t& nsteps, vxo_hit* rec) {
+    float stepFactor = step0;
+    V3 stepDir = dir * stepFactor;
+    V3 pos = origin;
+    float d = stepFactor;
+    int steps = 0;
+
+    while (d < 16.0f) {
+        I3 t{f2i(pos.x / 2.0f), f2i(pos.y / 2.0f), f2i(pos.z / 2.0f)};
+        unsigned v = fetch(vol, t.x, t.y, t.z);
+        unsigned bit = 0u;
+        bit += gmod(pos.x, 0.5f) > 0.25f ? 1u : 0u;
+        bit += gmod(pos.y, 0.5f) > 0.25f ? 2u : 0u;
+        bit += gmod(pos.z, 0.5f) > 0.25f ? 4u : 0u;
+        unsigned mask = 1u << bit;
+        ++steps;
+        if ((mask & v) != 0u) {
+            nsteps += (uint64_t)steps;
+            if (rec) {
+                rec->t = d; rec->steps = steps; rec->status = 1;
+                rec->vx = t.x * 2 + (int)(bit & 1u); rec->vy = t.y * 2 + (int)((bit >> 1) & 1u); rec->vz = t.z * 2 + (int)((bit >> 2) & 1u);
+                rec->px = pos.x; rec->py = pos.y; rec->pz = pos.z;
+            }
+            return d;
+        }
+        pos = pos + stepDir;
+        d += stepFactor;
+    }
+
+    stepFactor *= 2.0f;
+    stepDir = stepDir * 2.0f;
+    float lod1MaxT = fminf(dist, 164.0f);
+    while (d < lod1MaxT) {
+        I3 p{f2i(pos.x), f2i(pos.y), f2i(pos.z)};
+        ++steps;
+        if (get_volume_at(vol, p, 1)) {
+            nsteps += (uint64_t)steps;
+            if (rec) {
+                rec->t = d; rec->steps = steps; rec->status = 2;
+                rec->vx = p.x; rec->vy = p.y; rec->vz = p.z;
+                rec->px = pos.x; rec->py = pos.y; rec->pz = pos.z;
+            }
+            return d;
+        }
+        pos = pos + stepDir;
+        d += stepFactor;
+    }
+    nsteps += (uint64_t)steps;
+    if (rec) { rec->t = dist; rec->steps = steps; rec->status = 0; }
+    return dist;
+}
+
+// ---------------------------------------------------------------------------------------------
+// A4  Light.frag:29-81 raycastShadowVolume -- Amanatides-Woo DDA at mip 0.
+// `mip` starts at 0 and can only decrement on a hit at mip>0, so mipSize == 1 throughout and the
+// outer do/while restarts the same walk from the same origin up to 4 times.
+// ---------------------------------------------------------------------------------------------
+bool dda(const vxo_volume& vol, V3 origin, V3 direction, float maxt, vxo_hit* rec, uint64_t& nsteps) {
+    I3 dim{vol.sx, vol.sy, vol.sz};
+    V3 stepSign{gsign(direction.x), gsign(direction.y), gsign(direction.z)};
+    V3 t_delta = v3(1.0f, 1.0f, 1.0f) / (direction * stepSign);
+    int mip = 0;
+    int i = 0, nt = 0, probes = 0;
+    float totalt = 0.0f;
+    float best_t = 0.0f;
+    do {
+        float mipSize = (float)(1 << mip);
+        origin = origin / v3(mipSize, mipSize, mipSize);
+        I3 cur{f2i(floorf(origin.x)), f2i(floorf(origin.y)), f2i(floorf(origin.z))};
+        V3 next_bounds = v3((float)cur.x, (float)cur.y, (float)cur.z) + (stepSign * 0.5f + v3(0.5f, 0.5f, 0.5f));
+        V3 t_max = (next_bounds - origin) / direction;
+        int n = 0;
+        do {
+            V3 select{gstep(t_max.x, t_max.z) * gstep(t_max.x, t_max.y),
+                      gstep(t_max.y, t_max.x) * gstep(t_max.y, t_max.z),
+                      gstep(t_max.z, t_max.y) * gstep(t_max.z, t_max.x)};
+            // clamp(current_voxel, ivec3(0), ivec3(dim/mipSize)*2+1) != current_voxel -> miss
+            I3 hi{f2i((float)dim.x / mipSize) * 2 + 1, f2i((float)dim.y / mipSize) * 2 + 1, f2i((float)dim.z / mipSize) * 2 + 1};
+            if (cur.x < 0 || cur.y < 0 || cur.z < 0 || cur.x > hi.x || cur.y > hi.y || cur.z > hi.z) {
+                nsteps += (uint64_t)probes;
+                if (rec) { rec->t = best_t; rec->steps = nt; rec->status = 3; rec->vx = cur.x; rec->vy = cur.y; rec->vz = cur.z; }
+                return false;
+            }
+            bool voxel = get_volume_at(vol, cur, mip);
+            ++probes;
+            best_t = dot3(t_max, select);
+            if (voxel) {
+                // mip == 0 always
+                nsteps += (uint64_t)probes;
+                if (rec) {
+                    V3 nrm = (stepSign * -1.0f) * select;
+                    V3 hit = (origin + direction * best_t) * mipSize;
+                    rec->t = best_t; rec->steps = nt; rec->status = 1;
+                    rec->vx = cur.x; rec->vy = cur.y; rec->vz = cur.z;
+                    rec->px = hit.x; rec->py = hit.y; rec->pz = hit.z;
+                    rec->nx = nrm.x; rec->ny = nrm.y; rec->nz = nrm.z;
+                }
+                return true;
+            }
+            V3 adv = select * stepSign;
+            cur.x += f2i(adv.x); cur.y += f2i(adv.y); cur.z += f2i(adv.z);
+            t_max = t_max + t_delta * select;
+            totalt = best_t;
+            nt++;
+        } while (++n < 256 && totalt < maxt);
+        origin = origin * mipSize;
+    } while (++i < 4);
+    nsteps += (uint64_t)probes;
+    if (rec) { rec->t = best_t; rec->steps = nt; rec->status = 0; }
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// G-buffer decoders (Vulkan fixed-point conversion rules; formats from Sources/Graphics/Graphics.h:53-60)
+// ---------------------------------------------------------------------------------------------
+inline float unorm24(uint32_t d) { return (float)(d & 0xFFFFFFu) / 16777215.0f; }
+inline float unorm8(uint32_t c) { return (float)(c & 0xFFu) / 255.0f; }
+inline float snorm8(uint32_t c) { return fmaxf((float)(int8_t)(c & 0xFFu) / 127.0f, -1.0f); }
+
+struct Luts { float cosT[256], sinT[256]; };
+// SURVEY hard part 1: cos/sin of theta = 6.283*v (v = k/255) evaluated in double, rounded once.
+const Luts& luts() {
+    static Luts L;
+    static bool init = false;
+    if (!init) {
+        for (int k = 0; k < 256; ++k) {
+            float v = (float)k / 255.0f;
+            float theta = 6.283f * v;
+            L.cosT[k] = (float)cos((double)theta);
+            L.sinT[k] = (float)sin((double)theta);
+        }
+        init = true;
+    }
+    return L;
+}
+
+// LightAmbient.frag:81-87 cosineSampleHemisphere(rand) with rand = noise.xy (bytes nx, ny)
+inline V3 cosine_sample_hemisphere(const Luts& L, uint32_t nx, uint32_t ny) {
+    float u = unorm8(nx);
+    float r = sqrtf(u);
+    float x = r * L.cosT[ny & 0xFFu];
+    float y = r * L.sinT[ny & 0xFFu];
+    return V3{x, y, sqrtf(fmaxf(0.0f, 1.0f - u))};
+}
+
+struct Pixel {
+    V3 farvec;   // LightAmbient.vert:32-36 evaluated per pixel
+    float u, v;  // In.UV
+};
+
+inline Pixel pixel_setup(const vxo_view& view, int W, int H, int px, int py) {
+    Pixel p;
+    p.u = ((float)px + 0.5f) / (float)W;
+    p.v = ((float)py + 0.5f) / (float)H;
+    float ndcx = 2.0f * p.u - 1.0f;
+    float ndcy = 1.0f - 2.0f * p.v;
+    V4 f = mat_mul(view.InverseProjectionMatrix, V4{ndcx, ndcy, 1.0f, 1.0f});
+    p.farvec = V3{f.x / f.w, f.y / f.w, f.z / f.w};
+    return p;
+}
+
+// LightAmbient.frag:44-52 getNoise() / getNoise(int s); s < 0 selects the argument-less overload.
+inline uint32_t get_noise(const vxo_gbuffer& gb, const vxo_view& view, const Pixel& p, int s) {
+    float fx, fy;
+    if (s < 0) {
+        fx = GOLDEN_RATIO * gmod((float)view.Frame, 16.0f);
+        fy = GOLDEN_RATIO * gmod((float)(view.Frame + 1), 16.0f);
+    } else {
+        fx = GOLDEN_RATIO * gmod((float)(view.Frame + s * 5), 64.0f);
+        fy = GOLDEN_RATIO * gmod((float)(view.Frame + s * 7 + 1), 64.0f);
+    }
+    float resx = (float)gb.width, resy = (float)gb.height;
+    int cx = f2i((p.u + fx) * resx) % 512;
+    int cy = f2i((p.v + fy) * resy) % 512;
+    return gb.noise[cy * 512 + cx];
+}
+
+inline V3 decode_normal(uint32_t n) { return V3{snorm8(n), snorm8(n >> 8), snorm8(n >> 16)}; }
+
+inline V3 sun_dir() { return normalize3(v3(0.3f, 0.4f, 0.5f)); }  // LightAmbient.frag:15
+
+inline int nthreads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+struct Acc { uint64_t rays = 0, steps = 0, pixels = 0; };
+
+}  // namespace
+
+extern "C" {
+
+int vxo_num_threads(void) { return nthreads(); }
+void vxo_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+void vxo_trace_rays(const vxo_volume* vol, const vxo_ray* rays, int64_t n, int variant, vxo_hit* out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        const vxo_ray& r = rays[i];
+        vxo_hit h;
+        memset(&h, 0, sizeof h);
+        uint64_t s = 0;
+        V3 o{r.ox, r.oy, r.oz}, d{r.dx, r.dy, r.dz};
+        if (variant == VXO_SPARSE) march(*vol, o, d, r.dist, 0.5f, s, &h);
+        else if (variant == VXO_SUPERSPARSE) march(*vol, o, d, r.dist, 2.5f, s, &h);
+        else dda(*vol, o, d, r.dist, &h, s);
+        out[i] = h;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// A5  LightAmbient.frag:134-175 (main, shadow block) + :111-126 calculateAmbientIrradiance.
+// Outputs of the new pass contract: shadow in {0,1}, ao = mean_i((d_i/128)^2) * 0.05.
+// Sky pixels (depth >= 0.999) generate no rays: shadow = 1, ao = 0.
+// n_ao > 1 is the build's multi-sample extension: ray 0 uses getNoise(), ray i >= 1
+// uses getNoise(i).
+// ---------------------------------------------------------------------------------------------
+void vxo_pass_ambient(const vxo_volume* vol, const vxo_view* view, const vxo_gbuffer* gb, int n_ao,
+                      vxo_rows rows, float* out_shadow, float* out_ao, vxo_stats* stats) {
+    const Luts& L = luts();
+    const int W = gb->width, H = gb->height;
+    const V3 SUN = sun_dir();
+    uint64_t trays = 0, tsteps = 0, tpix = 0;
+    if (rows.step < 1) rows.step = 1;
+    const int nrows = rows.end > rows.begin ? (rows.end - rows.begin + rows.step - 1) / rows.step : 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : trays, tsteps, tpix)
+    for (int ri = 0; ri < nrows; ++ri) {
+        const int py = rows.begin + ri * rows.step;
+        if (py < 0 || py >= H) continue;
+        for (int px = 0; px < W; ++px) {
+            const size_t idx = (size_t)py * W + px;
+            float depth = unorm24(gb->depth24[idx]);
+            if (!(depth < 0.999f)) { out_shadow[idx] = 1.0f; out_ao[idx] = 0.0f; continue; }
+            Pixel p = pixel_setup(*view, W, H, px, py);
+            V3 pos = p.farvec * (depth * (1.0f + 1.0f / FAR_));       // :141
+            V3 normal = decode_normal(gb->normal[idx]);               // :142
+            V3 wd = SUN;                                              // :149
+            V3 wcp = xyz(mat_mul(view->InverseViewMatrix, V4{pos.x, pos.y, pos.z, 1.0f})) * 10.0f;  // :150
+            uint32_t n = get_noise(*gb, *view, p, -1);
+            V3 randomVec = cosine_sample_hemisphere(L, n, n >> 8) * 0.1f;   // :151
+            randomVec.z *= gsign(unorm8(n >> 16) - 0.5f);                  // :152
+            wd = mix3(wd, randomVec, 0.5f);                                // :153
+            wd = normalize3(wd);                                           // :154
+            wcp = wcp + wd * (unorm8(n >> 24) * 1.0f);                     // :155
+            wcp = wcp + randomVec * 2.5f;                                  // :156
+            float bias = gsmoothstep(0.0f, 0.2f, depth) * 50.0f + 1.5f;    // :158
+            V3 origin = wcp + normal * bias;
+            uint64_t s = 0;
+            float shadow = 1.0f;
+            if (march(*vol, origin, wd, 128.0f, 0.5f, s, nullptr) != 128.0f) shadow = 0.0f;  // :167-169
+            // calculateAmbientIrradiance(origin, normal)  :111-126
+            V3 tangent = fabsf(normal.z) > 0.5f ? v3(0.0f, -normal.z, normal.y) : v3(-normal.y, normal.x, 0.0f);
+            V3 bitangent = cross3(normal, tangent);
+            float acc = 0.0f;
+            for (int i = 0; i < n_ao; ++i) {
+                uint32_t ni = (i == 0) ? n : get_noise(*gb, *view, p, i);
+                V3 rv = cosine_sample_hemisphere(L, ni, ni >> 8);
+                V3 dir = tangent * rv.x + bitangent * rv.y + normal * rv.z;
+                float d = march(*vol, origin, dir, 128.0f, 2.5f, s, nullptr) / 128.0f;
+                acc += d * d;
+            }
+            float ao = n_ao > 0 ? (acc / (float)n_ao) * 0.05f : 0.0f;   // AMBIENT_LIGHT_FACTOR :17
+            out_shadow[idx] = shadow;
+            out_ao[idx] = ao;
+            trays += 1 + (uint64_t)n_ao; tsteps += s; tpix += 1;
+        }
+    }
+    if (stats) { stats->rays = trays; stats->steps = tsteps; stats->pixels = tpix; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// A6  LightPoint.frag:85-129.  One plane per light; range-culled pixels (discard) -> shadow = 1.
+// Note the reference applies no sky test in this pass.
+// ---------------------------------------------------------------------------------------------
+}  // extern "C"
+namespace {
+template <bool SPOT>
+void pass_local_light(const vxo_volume* vol, const vxo_view* view, const vxo_gbuffer* gb,
+                      const float* light_base, int stride_floats, int n_lights, vxo_rows rows,
+                      float* out_shadow, vxo_stats* stats) {
+    const Luts& L = luts();
+    const int W = gb->width, H = gb->height;
+    uint64_t trays = 0, tsteps = 0, tpix = 0;
+    if (rows.step < 1) rows.step = 1;
+    const int nrows = rows.end > rows.begin ? (rows.end - rows.begin + rows.step - 1) / rows.step : 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : trays, tsteps, tpix)
+    for (int ri = 0; ri < nrows; ++ri) {
+        const int py = rows.begin + ri * rows.step;
+        if (py < 0 || py >= H) continue;
+        for (int px = 0; px < W; ++px) {
+            const size_t idx = (size_t)py * W + px;
+            float depth = unorm24(gb->depth24[idx]);
+            Pixel p = pixel_setup(*view, W, H, px, py);
+            V3 pos = p.farvec * (depth * (1.0f + 1.0f / FAR_));          // LightPoint.frag:89
+            V3 normal = decode_normal(gb->normal[idx]);                  // :90
+            V3 worldPos = xyz(mat_mul(view->InverseViewMatrix, V4{pos.x, pos.y, pos.z, 1.0f}));  // :95
+            uint32_t n = get_noise(*gb, *view, p, -1);
+            V3 rv0 = cosine_sample_hemisphere(L, n, n >> 8) * 0.1f;      // :111
+            rv0.z *= gsign(unorm8(n >> 16) - 0.5f);                      // :112
+            bool any = false;
+            for (int li = 0; li < n_lights; ++li) {
+                const float* lt = light_base + (size_t)li * stride_floats;
+                V3 lpos{lt[0], lt[1], lt[2]};
+                float range = lt[3];
+                V3 lightDir = lpos - worldPos;                           // :97
+                float lightDistance = length3(lightDir);                 // :98
+                float* outp = out_shadow + (size_t)li * W * H + idx;
+                if (lightDistance > range) { *outp = 1.0f; continue; }   // :100-103 discard
+                V3 wd; float hitDist; float step0;
+                if (!SPOT) { wd = lightDir; hitDist = lightDistance * 10.5f; step0 = 0.5f; }              // :108-109
+                else { wd = normalize3(lightDir) * 10.0f; hitDist = lightDistance * 10.0f; step0 = 2.5f; } // LightSpot.frag:96-97
+                V3 wcp = worldPos * 10.0f;                               // :110
+                wd = mix3(wd, rv0, 0.5f);                                // :113
+                wd = normalize3(wd);                                     // :114
+                wcp = wcp + wd * (unorm8(n >> 24) * 1.0f);               // :115
+                wcp = wcp + rv0 * 2.5f;                                  // :116
+                uint64_t s = 0;
+                float shadow = 1.0f;
+                if (march(*vol, wcp + normal * 0.5f, wd, hitDist, step0, s, nullptr) < hitDist) shadow = 0.0f;  // :125
+                *outp = shadow;
+                trays += 1; tsteps += s; any = true;
+            }
+            if (any) tpix += 1;
+        }
+    }
+    if (stats) { stats->rays = trays; stats->steps = tsteps; stats->pixels = tpix; }
+}
+}  // namespace
+extern "C" {
+
+void vxo_pass_point(const vxo_volume* vol, const vxo_view* view, const vxo_gbuffer* gb,
+                    const vxo_point_light* lights, int n_lights, vxo_rows rows, float* out_shadow, vxo_stats* stats) {
+    pass_local_light<false>(vol, view, gb, (const float*)lights, (int)(sizeof(vxo_point_light) / 4), n_lights, rows, out_shadow, stats);
+}
+// LightSpot.frag:73-117 (same ray-gen; SuperSparse march, hitDist = 10*|L|)
+void vxo_pass_spot(const vxo_volume* vol, const vxo_view* view, const vxo_gbuffer* gb,
+                   const vxo_spot_light* lights, int n_lights, vxo_rows rows, float* out_shadow, vxo_stats* stats) {
+    pass_local_light<true>(vol, view, gb, (const float*)lights, (int)(sizeof(vxo_spot_light) / 4), n_lights, rows, out_shadow, stats);
+}
+
+// ---------------------------------------------------------------------------------------------
+// A6  LightReflection.frag:60-113.  Output: t (256 on a miss / sky pixel).
+// ---------------------------------------------------------------------------------------------
+void vxo_pass_reflection(const vxo_volume* vol, const vxo_view* view, const vxo_gbuffer* gb,
+                         vxo_rows rows, float* out_t, vxo_stats* stats) {
+    const Luts& L = luts();
+    const int W = gb->width, H = gb->height;
+    uint64_t trays = 0, tsteps = 0, tpix = 0;
+    if (rows.step < 1) rows.step = 1;
+    const int nrows = rows.end > rows.begin ? (rows.end - rows.begin + rows.step - 1) / rows.step : 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : trays, tsteps, tpix)
+    for (int ri = 0; ri < nrows; ++ri) {
+        const int py = rows.begin + ri * rows.step;
+        if (py < 0 || py >= H) continue;
+        for (int px = 0; px < W; ++px) {
+            const size_t idx = (size_t)py * W + px;
+            float depth = unorm24(gb->depth24[idx]);
+            if (!(depth < 0.999f)) { out_t[idx] = 256.0f; continue; }    // :88
+            Pixel p = pixel_setup(*view, W, H, px, py);
+            V3 pos = p.farvec * (depth * (1.0f + 1.0f / FAR_));          // :64
+            V3 normal = decode_normal(gb->normal[idx]);                  // :65
+            float roughness = unorm8(gb->material[idx]);                 // :68
+            V3 V = normalize3(pos) * -1.0f;                              // :79
+            V4 n4 = mat_mul(view->ViewMatrix, V4{normal.x, normal.y, normal.z, 0.0f});
+            V3 N = xyz(n4);                                              // :80
+            V3 I = V * -1.0f;
+            V3 R = I - N * dot3(N, I) * 2.0f;                            // :81 reflect(-V, N)
+            V3 wd = normalize3(xyz(mat_mul(view->InverseViewMatrix, V4{R.x, R.y, R.z, 0.0f})));   // :92
+            V3 wcp = xyz(mat_mul(view->InverseViewMatrix, V4{pos.x, pos.y, pos.z, 1.0f})) * 10.0f; // :93
+            uint32_t n = get_noise(*gb, *view, p, -1);
+            V3 rv = cosine_sample_hemisphere(L, n, n >> 8);              // :94
+            rv.z *= gsign(unorm8(n >> 16) - 0.5f);                       // :95
+            wd = mix3(wd, rv, roughness * 0.1f);                         // :96
+            float nw = unorm8(n >> 24);
+            wcp = wcp + normal * nw;                                     // :97
+            wd = wd * (1.0f + nw * 0.5f);                                // :98
+            uint64_t s = 0;
+            float t = march(*vol, wcp + normal, wd, 256.0f, 0.5f, s, nullptr);   // :113
+            out_t[idx] = t;
+            trays += 1; tsteps += s; tpix += 1;
+        }
+    }
+    if (stats) { stats->rays = trays; stats->steps = tsteps; stats->pixels = tpix; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// A7  Sources/World/Systems/ShadowVoxSystem.cpp
+// ---------------------------------------------------------------------------------------------
+// :82-94 SetVolumeAt
+void vxo_set_volume_at(uint8_t* data, int sx, int sy, int sz, int x, int y, int z, int value) {
+    if (x < 0 || y < 0 || z < 0 || x >= sx * 2 || y >= sy * 2 || z >= sz * 2) return;
+    int bit = (x & 1) | ((y & 1) << 1) | ((z & 1) << 2);
+    int mask = 1 << bit;
+    x /= 2; y /= 2; z /= 2;
+    uint8_t* p = data + ((size_t)x + (size_t)y * (size_t)sx + (size_t)z * (size_t)sx * (size_t)sy);
+    *p = (uint8_t)((*p & ~mask) | (value << bit));
+}
+
+int vxo_get_volume_at(const vxo_volume* vol, int x, int y, int z, int mip) {
+    return get_volume_at(*vol, I3{x, y, z}, mip) ? 1 : 0;
+}
+
+namespace {
+struct Basis { V3 o, dx, dy, dz; };
+// glm::translate(m, -pivot) (Vendor/glm/ext/matrix_transform.inl:10-15) then the o/dx/dy/dz
+// extraction of ShadowVoxSystem.cpp:134-140.
+inline Basis basis_from(const float* m, const float* pivot, bool use_pivot) {
+    Basis b;
+    if (use_pivot) {
+        float v0 = -pivot[0], v1 = -pivot[1], v2 = -pivot[2];
+        b.o.x = ((m[0] * v0 + m[4] * v1) + m[8] * v2) + m[12];
+        b.o.y = ((m[1] * v0 + m[5] * v1) + m[9] * v2) + m[13];
+        b.o.z = ((m[2] * v0 + m[6] * v1) + m[10] * v2) + m[14];
+    } else {
+        b.o = V3{m[12], m[13], m[14]};
+    }
+    b.dx = V3{m[0] * 0.1f, m[1] * 0.1f, m[2] * 0.1f};
+    b.dy = V3{m[4] * 0.1f, m[5] * 0.1f, m[6] * 0.1f};
+    b.dz = V3{m[8] * 0.1f, m[9] * 0.1f, m[10] * 0.1f};
+    return b;
+}
+inline void stamp(uint8_t* data, int sx, int sy, int sz, const vxo_model& mdl, const Basis& b, int value, I3& mn, I3& mx) {
+    for (int z = 0; z < mdl.sz; z++)
+        for (int y = 0; y < mdl.sy; y++)
+            for (int x = 0; x < mdl.sx; x++) {
+                if (mdl.voxels[(size_t)x + (size_t)y * mdl.sx + (size_t)z * mdl.sx * mdl.sy] >= 16) {   // :145
+                    V3 wp = b.o + b.dx * (float)x + b.dy * (float)y + b.dz * (float)z;                  // :146
+                    I3 f{f2i(wp.x * 10.0f), f2i(wp.y * 10.0f), f2i(wp.z * 10.0f)};                      // :147
+                    mn.x = std::min(mn.x, f.x); mn.y = std::min(mn.y, f.y); mn.z = std::min(mn.z, f.z);
+                    mx.x = std::max(mx.x, f.x); mx.y = std::max(mx.y, f.y); mx.z = std::max(mx.z, f.z);
+                    vxo_set_volume_at(data, sx, sy, sz, f.x, f.y, f.z, value);
+                }
+            }
+}
+}  // namespace
+
+// :116-191 OnUpdate (per visited entity) and :7-53 OnVoxDestroyed, sequential, in array order.
+void vxo_voxelize(uint8_t* data, int sx, int sy, int sz, const vxo_model* models,
+                  const vxo_entity* ents, int n, vxo_region* out_regions, int32_t* out_valid) {
+    for (int e = 0; e < n; ++e) {
+        const vxo_entity& en = ents[e];
+        const vxo_model& mdl = models[en.model];
+        I3 startmin{sx - 1, sy - 1, sz - 1};   // :128 (texel units, mixed with voxel units below: sic)
+        I3 startmax{0, 0, 0};
+        I3 mn = startmin, mx = startmax;
+        if (en.flags & VXO_ENT_DESTROY) {
+            Basis b = basis_from(en.cur, en.pivot, false);   // :22-25 pivot ignored
+            stamp(data, sx, sy, sz, mdl, b, 0, mn, mx);
+        } else {
+            Basis bp = basis_from(en.prev, en.pivot, true);
+            stamp(data, sx, sy, sz, mdl, bp, 0, mn, mx);
+            Basis bc = basis_from(en.cur, en.pivot, true);
+            stamp(data, sx, sy, sz, mdl, bc, 1, mn, mx);
+        }
+        int valid = 0;
+        vxo_region r;
+        memset(&r, 0, sizeof r);
+        if (mx.x != startmax.x || mx.y != startmax.y || mx.z != startmax.z) {   // :181
+            mn.x /= 2; mn.y /= 2; mn.z /= 2;
+            mx.x /= 2; mx.y /= 2; mx.z /= 2;
+            mn.x = std::max(mn.x, 0); mn.y = std::max(mn.y, 0); mn.z = std::max(mn.z, 0);
+            mx.x = std::min(mx.x, startmin.x); mx.y = std::min(mx.y, startmin.y); mx.z = std::min(mx.z, startmin.z);
+            r.x = mn.x; r.y = mn.y; r.z = mn.z;
+            r.w = (uint32_t)(mx.x - mn.x + 1); r.h = (uint32_t)(mx.y - mn.y + 1); r.d = (uint32_t)(mx.z - mn.z + 1);
+            r.mip = 0;
+            valid = 1;
+        }
+        if (out_regions) out_regions[e] = r;
+        if (out_valid) out_valid[e] = valid;
+    }
+}
+
+// Vendor/evk/evk.cpp:759-780: bufferOffset = x + y*W + z*W*H, row length W, image height H.
+void vxo_upload_regions(uint8_t* image, const uint8_t* staging, int sx, int sy, int sz,
+                        const vxo_region* regions, int n) {
+    for (int i = 0; i < n; ++i) {
+        const vxo_region& r = regions[i];
+        for (uint32_t z = 0; z < r.d; ++z)
+            for (uint32_t y = 0; y < r.h; ++y) {
+                int zz = r.z + (int)z, yy = r.y + (int)y;
+                if (zz < 0 || zz >= sz || yy < 0 || yy >= sy) continue;
+                int x0 = std::max(r.x, 0), x1 = std::min(r.x + (int)r.w, sx);
+                if (x1 <= x0) continue;
+                size_t off = (size_t)x0 + (size_t)yy * sx + (size_t)zz * sx * sy;
+                memcpy(image + off, staging + off, (size_t)(x1 - x0));
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Synthetic inputs.  Gradient noise after the published FastNoise 0.4 "Perlin"
+// algorithm (Vendor/FastNoise/FastNoise.cpp:197-215 seed table, :826-880 3-D, :950-985 2-D),
+// combined as Noise::GetTerrainNoise (Sources/Util/Noise.cpp:93-135).  Restated, not copied;
+// cross-checked against the vendored library by oracle/refcheck (oracle/_ref).
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct Perm { uint8_t p[512], p12[512]; bool init = false; };
+Perm g_perm;
+const float GX[12] = {1, -1, 1, -1, 1, -1, 1, -1, 0, 0, 0, 0};
+const float GY[12] = {1, 1, -1, -1, 0, 0, 0, 0, 1, -1, 1, -1};
+const float GZ[12] = {0, 0, 0, 0, 1, 1, -1, -1, 1, 1, -1, -1};
+
+void build_perm(int seed, uint8_t* p, uint8_t* p12) {
+    std::mt19937_64 gen((unsigned long long)seed);
+    for (int i = 0; i < 256; i++) p[i] = (uint8_t)i;
+    for (int j = 0; j < 256; j++) {
+        int rng = (int)(gen() % (uint64_t)(256 - j));
+        int k = rng + j;
+        uint8_t l = p[j];
+        p[j] = p[j + 256] = p[k];
+        p[k] = l;
+        p12[j] = p12[j + 256] = (uint8_t)(p[j] % 12);
+    }
+}
+inline const Perm& perm() {
+    if (!g_perm.init) { build_perm(1337, g_perm.p, g_perm.p12); g_perm.init = true; }
+    return g_perm;
+}
+inline int fast_floor(float f) { return f >= 0 ? (int)f : (int)f - 1; }
+inline float quintic(float t) { return t * t * t * (t * (t * 6.0f - 15.0f) + 10.0f); }
+inline float lerp(float a, float b, float t) { return a + t * (b - a); }
+inline float grad2(const Perm& P, int x, int y, float xd, float yd) {
+    uint8_t i = P.p12[(x & 0xff) + P.p[(y & 0xff) + 0]];
+    return xd * GX[i] + yd * GY[i];
+}
+inline float grad3(const Perm& P, int x, int y, int z, float xd, float yd, float zd) {
+    uint8_t i = P.p12[(x & 0xff) + P.p[(y & 0xff) + P.p[(z & 0xff) + 0]]];
+    return xd * GX[i] + yd * GY[i] + zd * GZ[i];
+}
+float perlin2(const Perm& P, float x, float y) {
+    int x0 = fast_floor(x), y0 = fast_floor(y);
+    int x1 = x0 + 1, y1 = y0 + 1;
+    float xs = quintic(x - (float)x0), ys = quintic(y - (float)y0);
+    float xd0 = x - (float)x0, yd0 = y - (float)y0;
+    float xd1 = xd0 - 1.0f, yd1 = yd0 - 1.0f;
+    float xf0 = lerp(grad2(P, x0, y0, xd0, yd0), grad2(P, x1, y0, xd1, yd0), xs);
+    float xf1 = lerp(grad2(P, x0, y1, xd0, yd1), grad2(P, x1, y1, xd1, yd1), xs);
+    return lerp(xf0, xf1, ys);
+}
+float perlin3(const Perm& P, float x, float y, float z) {
+    int x0 = fast_floor(x), y0 = fast_floor(y), z0 = fast_floor(z);
+    int x1 = x0 + 1, y1 = y0 + 1, z1 = z0 + 1;
+    float xs = quintic(x - (float)x0), ys = quintic(y - (float)y0), zs = quintic(z - (float)z0);
+    float xd0 = x - (float)x0, yd0 = y - (float)y0, zd0 = z - (float)z0;
+    float xd1 = xd0 - 1.0f, yd1 = yd0 - 1.0f, zd1 = zd0 - 1.0f;
+    float xf00 = lerp(grad3(P, x0, y0, z0, xd0, yd0, zd0), grad3(P, x1, y0, z0, xd1, yd0, zd0), xs);
+    float xf10 = lerp(grad3(P, x0, y1, z0, xd0, yd1, zd0), grad3(P, x1, y1, z0, xd1, yd1, zd0), xs);
+    float xf01 = lerp(grad3(P, x0, y0, z1, xd0, yd0, zd1), grad3(P, x1, y0, z1, xd1, yd0, zd1), xs);
+    float xf11 = lerp(grad3(P, x0, y1, z1, xd0, yd1, zd1), grad3(P, x1, y1, z1, xd1, yd1, zd1), xs);
+    float yf0 = lerp(xf00, xf10, ys);
+    float yf1 = lerp(xf01, xf11, ys);
+    return lerp(yf0, yf1, zs);
+}
+const float FREQ = 0.01f;   // FastNoise.h:221
+// Noise.cpp:93-121 GetOctave
+float octave2(const Perm& P, float x, float y, int octaves) {
+    float total = 0.0f, frequency = 1.0f, amplitude = 1.0f, maxValue = 0.0f;
+    for (int i = 0; i < octaves; i++) {
+        total += perlin2(P, (x * frequency) * FREQ, (y * frequency) * FREQ) * amplitude;
+        maxValue += amplitude; amplitude *= 0.5f; frequency *= 2.0f;
+    }
+    return total / maxValue;
+}
+float octave3(const Perm& P, float x, float y, float z, int octaves) {
+    float total = 0.0f, frequency = 1.0f, amplitude = 1.0f, maxValue = 0.0f;
+    for (int i = 0; i < octaves; i++) {
+        total += perlin3(P, (x * frequency) * FREQ, (y * frequency) * FREQ, (z * frequency) * FREQ) * amplitude;
+        maxValue += amplitude; amplitude *= 0.5f; frequency *= 2.0f;
+    }
+    return total / maxValue;
+}
+// Noise.cpp:131-135 with info = {Bias2D 0, Frequency2D 1, Octaves2D 4, Bias3D 0, Frequency3D 2, Octaves3D 3}
+inline float terrain2d(const Perm& P, float x, float z) { return octave2(P, x * 1.0f, z * 1.0f, 4) + 0.0f; }
+inline float terrain3d(const Perm& P, float x, float y, float z) { return octave3(P, x * 2.0f, y * 2.0f, z * 2.0f, 3) + 0.0f; }
+}  // namespace
+
+void vxo_perm_table(int seed, uint8_t* perm512, uint8_t* perm12_512) { build_perm(seed, perm512, perm12_512); }
+
+float vxo_terrain_noise(float x, float y, float z) {
+    const Perm& P = perm();
+    float v = terrain2d(P, x, z);
+    v += terrain3d(P, x, y, z);
+    return v;
+}
+
+// voxel (x,y,z) solid iff GetTerrainNoise(x,y,z) > (y/NY - 0.5)*2, NY = 2*sy voxels.
+void vxo_gen_terrain(uint8_t* data, int sx, int sy, int sz) {
+    const Perm& P = perm();
+    const float NY = (float)(2 * sy);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int tz = 0; tz < sz; ++tz) {
+        std::vector<float> col2((size_t)4 * sx);   // 2-D term for the 2x2 voxel columns of each texel
+        for (int tx = 0; tx < sx; ++tx)
+            for (int b = 0; b < 4; ++b)
+                col2[(size_t)tx * 4 + b] = terrain2d(P, (float)(2 * tx + (b & 1)), (float)(2 * tz + (b >> 1)));
+        for (int ty = 0; ty < sy; ++ty)
+            for (int tx = 0; tx < sx; ++tx) {
+                unsigned byte = 0;
+                for (int bit = 0; bit < 8; ++bit) {
+                    int vx = 2 * tx + (bit & 1), vy = 2 * ty + ((bit >> 1) & 1), vz = 2 * tz + (bit >> 2);
+                    float v = col2[(size_t)tx * 4 + ((bit & 1) | ((bit >> 2) << 1))];
+                    v += terrain3d(P, (float)vx, (float)vy, (float)vz);
+                    float thr = ((float)vy / NY - 0.5f) * 2.0f;
+                    if (v > thr) byte |= 1u << bit;
+                }
+                data[(size_t)tx + (size_t)ty * sx + (size_t)tz * sx * sy] = (uint8_t)byte;
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Synthetic G-buffer (SURVEY 8d "G-buffer"): primary rays through the packed volume with the A4
+// DDA arithmetic (unbounded step count, clipped to the volume box first).  Input synthesis, not a
+// reference pass; the encodings are the reference's (GeometryVoxel.frag:156,169; GeometrySky.frag:30).
+// ---------------------------------------------------------------------------------------------
+void vxo_gbuffer_primary(const vxo_volume* vol, const vxo_view* view, int W, int H,
+                         uint32_t* depth24, uint32_t* normal, uint32_t* material) {
+    const V3 box{(float)(vol->sx * 2), (float)(vol->sy * 2), (float)(vol->sz * 2)};
+    const int max_steps = 2 * (vol->sx + vol->sy + vol->sz) * 2 + 8;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int py = 0; py < H; ++py)
+        for (int px = 0; px < W; ++px) {
+            const size_t idx = (size_t)py * W + px;
+            Pixel p = pixel_setup(*view, W, H, px, py);
+            V3 dir = normalize3(xyz(mat_mul(view->InverseViewMatrix, V4{p.farvec.x, p.farvec.y, p.farvec.z, 0.0f})));
+            V3 org = v3(view->InverseViewMatrix[12], view->InverseViewMatrix[13], view->InverseViewMatrix[14]) * 10.0f;
+            uint32_t od = 0xFFFFFFu, on = 0u, om = 0u;
+            // slab clip when the eye is outside the box
+            float t0 = 0.0f;
+            bool inside = org.x >= 0.0f && org.y >= 0.0f && org.z >= 0.0f && org.x < box.x && org.y < box.y && org.z < box.z;
+            bool ok = true;
+            if (!inside) {
+                float tmin = 0.0f, tmax = 3.0e38f;
+                const float o[3] = {org.x, org.y, org.z}, d[3] = {dir.x, dir.y, dir.z}, b[3] = {box.x, box.y, box.z};
+                for (int a = 0; a < 3; ++a) {
+                    if (d[a] == 0.0f) { if (o[a] < 0.0f || o[a] >= b[a]) ok = false; continue; }
+                    float ta = (0.0f - o[a]) / d[a], tb = (b[a] - o[a]) / d[a];
+                    float lo = fminf(ta, tb), hi = fmaxf(ta, tb);
+                    tmin = fmaxf(tmin, lo); tmax = fminf(tmax, hi);
+                }
+                if (!(tmin <= tmax)) ok = false;
+                t0 = tmin + 0.001f;
+            }
+            if (ok) {
+                V3 o = org + dir * t0;
+                V3 stepSign{gsign(dir.x), gsign(dir.y), gsign(dir.z)};
+                V3 t_delta = v3(1.0f, 1.0f, 1.0f) / (dir * stepSign);
+                I3 cur{f2i(floorf(o.x)), f2i(floorf(o.y)), f2i(floorf(o.z))};
+                V3 nb = v3((float)cur.x, (float)cur.y, (float)cur.z) + (stepSign * 0.5f + v3(0.5f, 0.5f, 0.5f));
+                V3 t_max = (nb - o) / dir;
+                float t_enter = 0.0f;
+                V3 nrm{0.0f, 1.0f, 0.0f};
+                for (int n = 0; n < max_steps; ++n) {
+                    if (cur.x < 0 || cur.y < 0 || cur.z < 0 || cur.x >= vol->sx * 2 || cur.y >= vol->sy * 2 || cur.z >= vol->sz * 2) break;
+                    if (get_volume_at(*vol, cur, 0)) {
+                        V3 hit = o + dir * t_enter;                 // voxel units
+                        V3 hw = hit * 0.1f;                         // world units
+                        V4 pv = mat_mul(view->ViewMatrix, V4{hw.x, hw.y, hw.z, 1.0f});
+                        float w = -pv.z;                            // GL perspective: w_clip = -z_view
+                        float dlin = (w - NEAR_) / (FAR_ - NEAR_);  // GeometryVoxel.frag:169
+                        dlin = gclamp(dlin, 0.0f, 1.0f);
+                        od = (uint32_t)f2i(floorf(dlin * 16777215.0f + 0.5f));
+                        int qx = f2i(floorf(nrm.x * 127.0f + 0.5f)), qy = f2i(floorf(nrm.y * 127.0f + 0.5f)), qz = f2i(floorf(nrm.z * 127.0f + 0.5f));
+                        on = ((uint32_t)(uint8_t)(int8_t)qx) | ((uint32_t)(uint8_t)(int8_t)qy << 8) | ((uint32_t)(uint8_t)(int8_t)qz << 16);
+                        uint32_t rough = (uint32_t)((cur.x * 7 + cur.y * 13 + cur.z * 29) & 255);
+                        om = rough | (0u << 8) | (0u << 16) | (255u << 24);
+                        break;
+                    }
+                    V3 select{gstep(t_max.x, t_max.z) * gstep(t_max.x, t_max.y),
+                              gstep(t_max.y, t_max.x) * gstep(t_max.y, t_max.z),
+                              gstep(t_max.z, t_max.y) * gstep(t_max.z, t_max.x)};
+                    t_enter = dot3(t_max, select);
+                    if (t_enter != t_enter) break;   // NaN: axis-parallel ray (0*inf); treat as a miss
+                    nrm = (stepSign * -1.0f) * select;
+                    V3 adv = select * stepSign;
+                    cur.x += f2i(adv.x); cur.y += f2i(adv.y); cur.z += f2i(adv.z);
+                    t_max = t_max + t_delta * select;
+                }
+            }
+            depth24[idx] = od; normal[idx] = on; material[idx] = om;
+        }
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Debug exports so tests can compare the pinned operation orders with glm (oracle/refcheck).
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+void vxo_dbg_normalize(const float* v, float* out) { V3 r = normalize3(V3{v[0], v[1], v[2]}); out[0] = r.x; out[1] = r.y; out[2] = r.z; }
+void vxo_dbg_mix(const float* a, const float* b, float t, float* out) { V3 r = mix3(V3{a[0], a[1], a[2]}, V3{b[0], b[1], b[2]}, t); out[0] = r.x; out[1] = r.y; out[2] = r.z; }
+void vxo_dbg_cross(const float* a, const float* b, float* out) { V3 r = cross3(V3{a[0], a[1], a[2]}, V3{b[0], b[1], b[2]}); out[0] = r.x; out[1] = r.y; out[2] = r.z; }
+float vxo_dbg_dot(const float* a, const float* b) { return dot3(V3{a[0], a[1], a[2]}, V3{b[0], b[1], b[2]}); }
+void vxo_dbg_matvec(const float* m, const float* v, float* out) { V4 r = mat_mul(m, V4{v[0], v[1], v[2], v[3]}); out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w; }
+void vxo_dbg_reflect(const float* i, const float* n, float* out) {
+    V3 I{i[0], i[1], i[2]}, N{n[0], n[1], n[2]};
+    V3 r = I - N * dot3(N, I) * 2.0f;
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+float vxo_dbg_mod(float x, float y) { return gmod(x, y); }
+float vxo_dbg_smoothstep(float e0, float e1, float x) { return gsmoothstep(e0, e1, x); }
+// o, dx, dy, dz of ShadowVoxSystem.cpp:134-140 -> out[12]
+void vxo_dbg_basis(const float* m, const float* pivot, float* out) {
+    Basis b = basis_from(m, pivot, true);
+    const V3 v[4] = {b.o, b.dx, b.dy, b.dz};
+    for (int i = 0; i < 4; ++i) { out[i * 3] = v[i].x; out[i * 3 + 1] = v[i].y; out[i * 3 + 2] = v[i].z; }
+}
+void vxo_dbg_hemisphere(uint32_t nx, uint32_t ny, float* out) { V3 r = cosine_sample_hemisphere(luts(), nx, ny); out[0] = r.x; out[1] = r.y; out[2] = r.z; }
+void vxo_dbg_luts(float* cos256, float* sin256) { memcpy(cos256, luts().cosT, 1024); memcpy(sin256, luts().sinT, 1024); }
+}

@@ -1,0 +1,262 @@
+"""ctypes front-end of the CPU oracle (oracle/liboracle.so).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, bench.py's cpu_baseline / --impl reference legs and __graft_entry__.smoke() import
+this module.  The product package (voxelengine_b200) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "liboracle.so")
+_REF = os.path.join(_HERE, "_ref", "libvxref.so")
+
+HIT_DTYPE = np.dtype([("t", "<f4"), ("steps", "<i4"), ("vx", "<i4"), ("vy", "<i4"), ("vz", "<i4"),
+                      ("status", "<i4"), ("px", "<f4"), ("py", "<f4"), ("pz", "<f4"),
+                      ("nx", "<f4"), ("ny", "<f4"), ("nz", "<f4")])
+RAY_DTYPE = np.dtype([("ox", "<f4"), ("oy", "<f4"), ("oz", "<f4"), ("dx", "<f4"), ("dy", "<f4"),
+                      ("dz", "<f4"), ("dist", "<f4"), ("pad", "<f4")])
+REGION_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("z", "<i4"), ("w", "<u4"), ("h", "<u4"),
+                         ("d", "<u4"), ("mip", "<i4")])
+ENTITY_DTYPE = np.dtype([("model", "<i4"), ("flags", "<i4"), ("prev", "<f4", (16,)),
+                         ("cur", "<f4", (16,)), ("pivot", "<f4", (3,)), ("_pad", "<i4")])
+VIEW_DTYPE = np.dtype([("LastViewMatrix", "<f4", (16,)), ("ViewMatrix", "<f4", (16,)),
+                       ("InverseViewMatrix", "<f4", (16,)), ("ProjectionMatrix", "<f4", (16,)),
+                       ("InverseProjectionMatrix", "<f4", (16,)), ("Res", "<f4", (2,)),
+                       ("iRes", "<f4", (2,)), ("CameraPosition", "<f4", (3,)), ("_pad0", "<i4"),
+                       ("Jitter", "<f4", (2,)), ("Frame", "<i4"), ("ColorTextureRID", "<i4"),
+                       ("DepthTextureRID", "<i4"), ("PalleteColorRID", "<i4"),
+                       ("PalleteMaterialRID", "<i4")])
+POINT_LIGHT_DTYPE = np.dtype([("Position", "<f4", (3,)), ("Range", "<f4"), ("Color", "<f4", (3,)),
+                              ("Attenuation", "<f4")])
+SPOT_LIGHT_DTYPE = np.dtype([("Position", "<f4", (3,)), ("Range", "<f4"), ("Color", "<f4", (3,)),
+                             ("Attenuation", "<f4"), ("Direction", "<f4", (3,)), ("Angle", "<f4"),
+                             ("AngleAttenuation", "<f4"), ("_pad", "<f4", (3,))])
+assert HIT_DTYPE.itemsize == 48 and RAY_DTYPE.itemsize == 32 and VIEW_DTYPE.itemsize == 380
+assert POINT_LIGHT_DTYPE.itemsize == 32 and SPOT_LIGHT_DTYPE.itemsize == 64
+assert ENTITY_DTYPE.itemsize == 152 and REGION_DTYPE.itemsize == 28
+
+SPARSE, SUPERSPARSE, DDA = 0, 1, 2
+ENT_DESTROY = 1
+
+
+class _Vol(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("sx", C.c_int32), ("sy", C.c_int32), ("sz", C.c_int32)]
+
+
+class _GB(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("depth24", C.c_void_p),
+                ("normal", C.c_void_p), ("material", C.c_void_p), ("noise", C.c_void_p)]
+
+
+class _Rows(C.Structure):
+    _fields_ = [("begin", C.c_int32), ("end", C.c_int32), ("step", C.c_int32)]
+
+
+class _Stats(C.Structure):
+    _fields_ = [("rays", C.c_uint64), ("steps", C.c_uint64), ("pixels", C.c_uint64)]
+
+
+class _Model(C.Structure):
+    _fields_ = [("voxels", C.c_void_p), ("sx", C.c_int32), ("sy", C.c_int32), ("sz", C.c_int32)]
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/liboracle.so (and oracle/_ref when /root/reference is mounted)."""
+    src = [os.path.join(_HERE, f) for f in ("vxo.cpp", "vxo.h", "Makefile")]
+    stale = force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in src)
+    if stale:
+        subprocess.run(["make", "-C", _HERE, "all"], check=True, capture_output=True)
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB)
+        _lib.vxo_terrain_noise.restype = C.c_float
+        _lib.vxo_terrain_noise.argtypes = [C.c_float] * 3
+        _lib.vxo_dbg_dot.restype = C.c_float
+        _lib.vxo_dbg_mod.restype = C.c_float
+        _lib.vxo_dbg_mod.argtypes = [C.c_float, C.c_float]
+        _lib.vxo_dbg_smoothstep.restype = C.c_float
+        _lib.vxo_dbg_smoothstep.argtypes = [C.c_float] * 3
+        _lib.vxo_dbg_mix.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+        _lib.vxo_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+    return _lib
+
+
+def ref_lib():
+    """The cross-check library built from the reference's vendored sources, or None."""
+    if not os.path.exists(_REF):
+        return None
+    r = C.CDLL(_REF)
+    for name in ("ref_dot", "ref_mod", "ref_smoothstep", "ref_terrain_noise", "ref_perlin3", "ref_perlin2"):
+        getattr(r, name).restype = C.c_float
+    r.ref_mod.argtypes = [C.c_float, C.c_float]
+    r.ref_smoothstep.argtypes = [C.c_float] * 3
+    r.ref_terrain_noise.argtypes = [C.c_float] * 3
+    r.ref_perlin3.argtypes = [C.c_float] * 3
+    r.ref_perlin2.argtypes = [C.c_float] * 2
+    r.ref_mix.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+    r.ref_perspective.argtypes = [C.c_float] * 4 + [C.c_void_p]
+    r.ref_camera.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+    return r
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _vol(volume: np.ndarray) -> _Vol:
+    """volume: uint8 array of shape (sz, sy, sx), C-contiguous (x fastest)."""
+    assert volume.dtype == np.uint8 and volume.ndim == 3 and volume.flags.c_contiguous
+    sz, sy, sx = volume.shape
+    return _Vol(volume.ctypes.data, sx, sy, sz)
+
+
+def _gb(gb: dict) -> _GB:
+    h, w = gb["depth24"].shape
+    for k in ("depth24", "normal", "material"):
+        assert gb[k].dtype == np.uint32 and gb[k].shape == (h, w) and gb[k].flags.c_contiguous
+    assert gb["noise"].dtype == np.uint32 and gb["noise"].shape == (512, 512)
+    return _GB(w, h, gb["depth24"].ctypes.data, gb["normal"].ctypes.data, gb["material"].ctypes.data,
+               gb["noise"].ctypes.data)
+
+
+def _rows(rows, h):
+    if rows is None:
+        return _Rows(0, h, 1)
+    return _Rows(*rows)
+
+
+def num_threads() -> int:
+    return lib().vxo_num_threads()
+
+
+def set_num_threads(n: int) -> None:
+    lib().vxo_set_num_threads(int(n))
+
+
+def trace_rays(volume, rays, variant):
+    rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+    out = np.zeros(rays.shape[0], dtype=HIT_DTYPE)
+    v = _vol(volume)
+    lib().vxo_trace_rays(C.byref(v), _p(rays), rays.shape[0], variant, _p(out))
+    return out
+
+
+def _view(view):
+    view = np.ascontiguousarray(view, dtype=VIEW_DTYPE).reshape(())
+    return view
+
+
+def pass_ambient(volume, view, gb, n_ao=1, rows=None):
+    h, w = gb["depth24"].shape
+    shadow = np.ones((h, w), np.float32)
+    ao = np.zeros((h, w), np.float32)
+    st = _Stats()
+    v, g, vw = _vol(volume), _gb(gb), _view(view)
+    lib().vxo_pass_ambient(C.byref(v), _p(vw), C.byref(g), int(n_ao), _rows(rows, h), _p(shadow), _p(ao), C.byref(st))
+    return shadow, ao, dict(rays=st.rays, steps=st.steps, pixels=st.pixels)
+
+
+def pass_point(volume, view, gb, lights, rows=None):
+    h, w = gb["depth24"].shape
+    lights = np.ascontiguousarray(lights, dtype=POINT_LIGHT_DTYPE)
+    out = np.ones((len(lights), h, w), np.float32)
+    st = _Stats()
+    v, g, vw = _vol(volume), _gb(gb), _view(view)
+    lib().vxo_pass_point(C.byref(v), _p(vw), C.byref(g), _p(lights), len(lights), _rows(rows, h), _p(out), C.byref(st))
+    return out, dict(rays=st.rays, steps=st.steps, pixels=st.pixels)
+
+
+def pass_spot(volume, view, gb, lights, rows=None):
+    h, w = gb["depth24"].shape
+    lights = np.ascontiguousarray(lights, dtype=SPOT_LIGHT_DTYPE)
+    out = np.ones((len(lights), h, w), np.float32)
+    st = _Stats()
+    v, g, vw = _vol(volume), _gb(gb), _view(view)
+    lib().vxo_pass_spot(C.byref(v), _p(vw), C.byref(g), _p(lights), len(lights), _rows(rows, h), _p(out), C.byref(st))
+    return out, dict(rays=st.rays, steps=st.steps, pixels=st.pixels)
+
+
+def pass_reflection(volume, view, gb, rows=None):
+    h, w = gb["depth24"].shape
+    out = np.full((h, w), 256.0, np.float32)
+    st = _Stats()
+    v, g, vw = _vol(volume), _gb(gb), _view(view)
+    lib().vxo_pass_reflection(C.byref(v), _p(vw), C.byref(g), _rows(rows, h), _p(out), C.byref(st))
+    return out, dict(rays=st.rays, steps=st.steps, pixels=st.pixels)
+
+
+def set_volume_at(volume, x, y, z, value):
+    sz, sy, sx = volume.shape
+    lib().vxo_set_volume_at(_p(volume), sx, sy, sz, int(x), int(y), int(z), int(value))
+
+
+def get_volume_at(volume, x, y, z, mip=0):
+    v = _vol(volume)
+    return bool(lib().vxo_get_volume_at(C.byref(v), int(x), int(y), int(z), int(mip)))
+
+
+def voxelize(volume, models, entities):
+    """In-place sequential voxelisation; returns (regions, valid)."""
+    sz, sy, sx = volume.shape
+    entities = np.ascontiguousarray(entities, dtype=ENTITY_DTYPE)
+    keep = [np.ascontiguousarray(m, dtype=np.uint8) for m in models]
+    arr = (_Model * len(keep))()
+    for i, m in enumerate(keep):
+        msz, msy, msx = m.shape
+        arr[i] = _Model(m.ctypes.data, msx, msy, msz)
+    regions = np.zeros(len(entities), dtype=REGION_DTYPE)
+    valid = np.zeros(len(entities), dtype=np.int32)
+    lib().vxo_voxelize(_p(volume), sx, sy, sz, arr, _p(entities), len(entities), _p(regions), _p(valid))
+    return regions, valid
+
+
+def upload_regions(image, staging, regions):
+    sz, sy, sx = image.shape
+    regions = np.ascontiguousarray(regions, dtype=REGION_DTYPE)
+    lib().vxo_upload_regions(_p(image), _p(staging), sx, sy, sz, _p(regions), len(regions))
+
+
+def gen_terrain(sx, sy, sz):
+    vol = np.zeros((sz, sy, sx), np.uint8)
+    lib().vxo_gen_terrain(_p(vol), sx, sy, sz)
+    return vol
+
+
+def terrain_noise(x, y, z):
+    return lib().vxo_terrain_noise(x, y, z)
+
+
+def perm_table(seed=1337):
+    p = np.zeros(512, np.uint8)
+    p12 = np.zeros(512, np.uint8)
+    lib().vxo_perm_table(int(seed), _p(p), _p(p12))
+    return p, p12
+
+
+def gbuffer_primary(volume, view, width, height):
+    d = np.zeros((height, width), np.uint32)
+    n = np.zeros((height, width), np.uint32)
+    m = np.zeros((height, width), np.uint32)
+    v, vw = _vol(volume), _view(view)
+    lib().vxo_gbuffer_primary(C.byref(v), _p(vw), int(width), int(height), _p(d), _p(n), _p(m))
+    return d, n, m
+
+
+def luts():
+    c = np.zeros(256, np.float32)
+    s = np.zeros(256, np.float32)
+    lib().vxo_dbg_luts(_p(c), _p(s))
+    return c, s

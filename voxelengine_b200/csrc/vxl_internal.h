@@ -1,0 +1,94 @@
+// vxl_internal.h -- private definitions shared by the .cu files of libvxl.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/vxl.h"
+
+namespace vxl {
+
+// Device-side view of the occupancy volume handed to kernels by value.
+struct VolView {
+    const uint8_t* __restrict__ bytes;   // canonical packed bytes, x fastest (reference layout)
+    int sx, sy, sz;                      // texels
+    // derived, acceleration only (never changes a result); see vxl_occupancy.cu
+    const uint32_t* __restrict__ occ8;   // 1 bit per 8x8x8-texel brick ... reserved for the skipper
+    int bx, by, bz;
+};
+
+struct FrameView {
+    int width, height, tile_w, tile_h, tile_first, tile_stride, n_tiles, tiles_x;
+    const uint32_t* __restrict__ depth24;
+    const uint32_t* __restrict__ normal;
+    const uint32_t* __restrict__ material;
+    const uint32_t* __restrict__ noise;
+};
+
+struct ModelDev { const uint8_t* voxels; int sx, sy, sz; unsigned solid; };
+
+constexpr int STAT_SLOTS = 64;   // striped counters: slot = blockIdx & 63, 4 x u64 each
+
+}  // namespace vxl
+
+struct vxl_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint64_t launches = 0;
+    unsigned long long* d_stats = nullptr;   // [STAT_SLOTS][4]
+    float* d_luts = nullptr;                 // cos[256] sin[256]
+    void* d_lights = nullptr;                // VXL_MAX_LIGHTS * 64 B
+    uint8_t* d_perm = nullptr;               // perm[512] perm12[512] (terrain generator)
+    std::vector<vxl::ModelDev> models;
+    vxl::ModelDev* d_models = nullptr;
+    int d_models_cap = 0;
+    // voxeliser scratch
+    unsigned long long* d_hkeys = nullptr;
+    unsigned* d_hvals = nullptr;
+    size_t hcap = 0;
+    vxl_entity* d_ents = nullptr;
+    int* d_aabb = nullptr;                   // [n][6]
+    int ents_cap = 0;
+    // host drop-in scratch
+    uint32_t* h_planes = nullptr;            // device buffers for vxl_lighting_host
+    size_t h_planes_bytes = 0;
+    float* h_out = nullptr;
+    size_t h_out_bytes = 0;
+    uint32_t* h_noise = nullptr;
+};
+
+struct vxl_volume {
+    vxl_ctx* ctx = nullptr;
+    int sx = 0, sy = 0, sz = 0;
+    uint8_t* d_bytes = nullptr;
+    bool dirty = true;
+    uint32_t* d_occ8 = nullptr;
+    int bx = 0, by = 0, bz = 0;
+};
+
+namespace vxl {
+void set_error(const std::string& s);
+int cuda_fail(cudaError_t e, const char* what);
+#define VXL_CUDA(call)                                             \
+    do {                                                           \
+        cudaError_t _e = (call);                                   \
+        if (_e != cudaSuccess) return vxl::cuda_fail(_e, #call);   \
+    } while (0)
+#define VXL_LAUNCH_CHECK(ctx)                                                  \
+    do {                                                                       \
+        (ctx)->launches++;                                                     \
+        cudaError_t _e = cudaGetLastError();                                   \
+        if (_e != cudaSuccess) return vxl::cuda_fail(_e, "kernel launch");     \
+    } while (0)
+
+inline VolView vol_view(const vxl_volume* v) {
+    VolView r;
+    r.bytes = v->d_bytes; r.sx = v->sx; r.sy = v->sy; r.sz = v->sz;
+    r.occ8 = v->d_occ8; r.bx = v->bx; r.by = v->by; r.bz = v->bz;
+    return r;
+}
+int frame_view(const vxl_frame* f, FrameView* out);
+size_t frame_pixels(const vxl_frame* f);   // n_tiles * tile_w * tile_h
+}  // namespace vxl

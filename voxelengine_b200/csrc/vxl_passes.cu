@@ -1,0 +1,354 @@
+// vxl_passes.cu -- the four light passes and the ray-level entry as sm_100a kernels.
+//
+// One thread per pixel of a tile-compact frame shard.  A warp covers an 8x4 pixel block so that
+// neighbouring rays (which start close together and, for shadows, point the same way) touch the
+// same cache lines of the volume.  Ray generation follows the reference fragment shaders line by
+// line (citations inline); the traversal is vxl_trace.cuh.
+#include "vxl_internal.h"
+#include "vxl_math.cuh"
+#include "vxl_trace.cuh"
+
+namespace vxl {
+
+constexpr float FAR_ = 4096.0f;                     // Sources/Shaders/lib/Common.frag:13
+constexpr float GOLDEN_RATIO = 2.118033988749895f;  // Common.frag:9 (sic)
+
+constexpr int BLOCK_W = 32, BLOCK_H = 8;            // pixels per thread block (8 warps of 8x4)
+
+struct ViewK { float InvView[16], View[16], InvProj[16]; int Frame; };
+
+struct PixelCtx {
+    bool valid;
+    int px, py;       // frame coordinates
+    size_t idx;       // index into the tile-compact planes
+    float u, v;       // In.UV
+    float3 farvec;    // LightAmbient.vert:32-36, evaluated per pixel
+};
+
+// thread -> pixel of the shard.  blockIdx.x enumerates (tile, block-in-tile).
+VXL_DI PixelCtx pixel_ctx(const FrameView& F, const ViewK& K) {
+    PixelCtx p;
+    const int bpt_x = (F.tile_w + BLOCK_W - 1) / BLOCK_W, bpt_y = (F.tile_h + BLOCK_H - 1) / BLOCK_H;
+    const int bpt = bpt_x * bpt_y;
+    const int lt = blockIdx.x / bpt, b = blockIdx.x - lt * bpt;
+    const int by = b / bpt_x, bx = b - by * bpt_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // 8 warps as 4 (x) by 2 (y); each warp 8 (x) by 4 (y)
+    const int lx = bx * BLOCK_W + (warp & 3) * 8 + (lane & 7);
+    const int ly = by * BLOCK_H + (warp >> 2) * 4 + (lane >> 3);
+    const int gt = F.tile_first + lt * F.tile_stride;
+    const int ty = gt / F.tiles_x, tx = gt - ty * F.tiles_x;
+    p.px = tx * F.tile_w + lx;
+    p.py = ty * F.tile_h + ly;
+    p.valid = lx < F.tile_w && ly < F.tile_h && p.px < F.width && p.py < F.height && lt < F.n_tiles;
+    p.idx = ((size_t)lt * F.tile_h + ly) * F.tile_w + lx;
+    p.u = ((float)p.px + 0.5f) / (float)F.width;
+    p.v = ((float)p.py + 0.5f) / (float)F.height;
+    const float ndcx = 2.0f * p.u - 1.0f, ndcy = 1.0f - 2.0f * p.v;
+    const float4 f = mat_mul(K.InvProj, make_float4(ndcx, ndcy, 1.0f, 1.0f));
+    p.farvec = make_float3(f.x / f.w, f.y / f.w, f.z / f.w);
+    return p;
+}
+
+// LightAmbient.frag:44-52 getNoise() (s < 0) / getNoise(int s)
+VXL_DI uint32_t get_noise(const FrameView& F, const ViewK& K, const PixelCtx& p, int s) {
+    float fx, fy;
+    if (s < 0) {
+        fx = GOLDEN_RATIO * gmod((float)K.Frame, 16.0f);
+        fy = GOLDEN_RATIO * gmod((float)(K.Frame + 1), 16.0f);
+    } else {
+        fx = GOLDEN_RATIO * gmod((float)(K.Frame + s * 5), 64.0f);
+        fy = GOLDEN_RATIO * gmod((float)(K.Frame + s * 7 + 1), 64.0f);
+    }
+    const int cx = f2i((p.u + fx) * (float)F.width) % 512;
+    const int cy = f2i((p.v + fy) * (float)F.height) % 512;
+    return __ldg(F.noise + cy * 512 + cx);
+}
+
+// LightAmbient.frag:81-87 with the cos/sin of theta = 6.283*(k/255) tabulated (host, double, rounded once)
+VXL_DI float3 cosine_sample_hemisphere(const float* __restrict__ lut, uint32_t nx, uint32_t ny) {
+    const float u = unorm8(nx);
+    const float r = sqrtf(u);
+    const float x = r * lut[ny & 0xFFu];
+    const float y = r * lut[256 + (ny & 0xFFu)];
+    return make_float3(x, y, sqrtf(fmaxf(0.0f, 1.0f - u)));
+}
+
+VXL_DI void load_luts(float* s_lut, const float* __restrict__ g_lut) {
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_lut[i] = g_lut[i];
+    __syncthreads();
+}
+
+// block-level accumulation of (rays, steps, pixels) into striped global counters
+VXL_DI void flush_stats(unsigned long long* __restrict__ g_stats, unsigned rays, unsigned steps, unsigned pixels) {
+    __shared__ unsigned s_acc[3];
+    if (threadIdx.x < 3) s_acc[threadIdx.x] = 0u;
+    __syncthreads();
+    rays = __reduce_add_sync(0xFFFFFFFFu, rays);
+    steps = __reduce_add_sync(0xFFFFFFFFu, steps);
+    pixels = __reduce_add_sync(0xFFFFFFFFu, pixels);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_acc[0], rays); atomicAdd(&s_acc[1], steps); atomicAdd(&s_acc[2], pixels); }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        unsigned v = s_acc[threadIdx.x];
+        if (v) atomicAdd(&g_stats[(blockIdx.x & (STAT_SLOTS - 1)) * 4 + threadIdx.x], (unsigned long long)v);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// LightAmbient.frag:134-175 + calculateAmbientIrradiance :111-126
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ambient(VolView V, FrameView F, ViewK K, const float* __restrict__ g_lut, int n_ao,
+                                                 float* __restrict__ out_shadow, float* __restrict__ out_ao,
+                                                 unsigned long long* __restrict__ g_stats) {
+    __shared__ float s_lut[512];
+    load_luts(s_lut, g_lut);
+    const PixelCtx p = pixel_ctx(F, K);
+    unsigned rays = 0, pixels = 0;
+    int steps = 0;
+    if (p.valid) {
+        const float depth = unorm24(__ldg(F.depth24 + p.idx));
+        float shadow = 1.0f, ao = 0.0f;
+        if (depth < 0.999f) {                                                     // :138
+            const float3 pos = p.farvec * (depth * (1.0f + 1.0f / FAR_));          // :141
+            const float3 normal = decode_normal(__ldg(F.normal + p.idx));          // :142
+            float3 wd = normalize3(make_float3(0.3f, 0.4f, 0.5f));                 // SUN_DIR :15,:149
+            float3 wcp = xyz(mat_mul(K.InvView, make_float4(pos.x, pos.y, pos.z, 1.0f))) * 10.0f;  // :150
+            const uint32_t n = get_noise(F, K, p, -1);
+            float3 randomVec = cosine_sample_hemisphere(s_lut, n, n >> 8) * 0.1f;  // :151
+            randomVec.z *= gsign(unorm8(n >> 16) - 0.5f);                         // :152
+            wd = mix3(wd, randomVec, 0.5f);                                        // :153
+            wd = normalize3(wd);                                                   // :154
+            wcp = wcp + wd * (unorm8(n >> 24) * 1.0f);                             // :155
+            wcp = wcp + randomVec * 2.5f;                                          // :156
+            const float bias = gsmoothstep(0.0f, 0.2f, depth) * 50.0f + 1.5f;      // :158
+            const float3 origin = wcp + normal * bias;
+            if (out_shadow) {
+                if (march<false>(V, origin, wd, 128.0f, 0.5f, steps, nullptr) != 128.0f) shadow = 0.0f;   // :167-169
+                rays += 1;
+            }
+            if (out_ao && n_ao > 0) {
+                const float3 tangent = fabsf(normal.z) > 0.5f ? make_float3(0.0f, -normal.z, normal.y)
+                                                             : make_float3(-normal.y, normal.x, 0.0f);    // :112
+                const float3 bitangent = cross3(normal, tangent);                                         // :113
+                float acc = 0.0f;
+                for (int i = 0; i < n_ao; ++i) {
+                    const uint32_t ni = (i == 0) ? n : get_noise(F, K, p, i);
+                    const float3 rv = cosine_sample_hemisphere(s_lut, ni, ni >> 8);                       // :118
+                    const float3 dir = tangent * rv.x + bitangent * rv.y + normal * rv.z;                 // :119
+                    const float d = march<false>(V, origin, dir, 128.0f, 2.5f, steps, nullptr) / 128.0f;  // :121
+                    acc += d * d;
+                }
+                ao = (acc / (float)n_ao) * 0.05f;                                                         // :125
+                rays += (unsigned)n_ao;
+            }
+            pixels = 1;
+        }
+        if (out_shadow) out_shadow[p.idx] = shadow;
+        if (out_ao) out_ao[p.idx] = ao;
+    }
+    flush_stats(g_stats, rays, (unsigned)steps, pixels);
+}
+
+// -------------------------------------------------------------------------------------------------
+// LightPoint.frag:85-129 / LightSpot.frag:73-117 -- all lights of the list in one launch; the
+// G-buffer, noise and world position are read / derived once per pixel instead of once per light.
+// -------------------------------------------------------------------------------------------------
+template <bool SPOT>
+__global__ void __launch_bounds__(256) k_local_lights(VolView V, FrameView F, ViewK K, const float* __restrict__ g_lut,
+                                                      const float* __restrict__ lights, int n_lights,
+                                                      float* __restrict__ out_shadow, size_t plane_stride,
+                                                      unsigned long long* __restrict__ g_stats) {
+    __shared__ float s_lut[512];
+    __shared__ float s_light[VXL_MAX_LIGHTS * 4];   // position.xyz, range
+    load_luts(s_lut, g_lut);
+    constexpr int STRIDE = SPOT ? 16 : 8;
+    for (int i = threadIdx.x; i < n_lights * 4; i += blockDim.x) s_light[i] = lights[(i >> 2) * STRIDE + (i & 3)];
+    __syncthreads();
+    const PixelCtx p = pixel_ctx(F, K);
+    unsigned rays = 0, pixels = 0;
+    int steps = 0;
+    if (p.valid) {
+        const float depth = unorm24(__ldg(F.depth24 + p.idx));
+        const float3 pos = p.farvec * (depth * (1.0f + 1.0f / FAR_));                        // LightPoint.frag:89
+        const float3 normal = decode_normal(__ldg(F.normal + p.idx));                        // :90
+        const float3 worldPos = xyz(mat_mul(K.InvView, make_float4(pos.x, pos.y, pos.z, 1.0f)));   // :95
+        const uint32_t n = get_noise(F, K, p, -1);
+        float3 rv0 = cosine_sample_hemisphere(s_lut, n, n >> 8) * 0.1f;                      // :111
+        rv0.z *= gsign(unorm8(n >> 16) - 0.5f);                                             // :112
+        const float nw = unorm8(n >> 24) * 1.0f;
+        for (int li = 0; li < n_lights; ++li) {
+            const float3 lpos = make_float3(s_light[li * 4], s_light[li * 4 + 1], s_light[li * 4 + 2]);
+            const float range = s_light[li * 4 + 3];
+            const float3 lightDir = lpos - worldPos;                                         // :97
+            const float lightDistance = length3(lightDir);                                   // :98
+            float shadow = 1.0f;
+            if (!(lightDistance > range)) {                                                  // :100-103
+                float3 wd; float hitDist; float step0;
+                if (!SPOT) { wd = lightDir; hitDist = lightDistance * 10.5f; step0 = 0.5f; }                 // :108-109
+                else { wd = normalize3(lightDir) * 10.0f; hitDist = lightDistance * 10.0f; step0 = 2.5f; }   // LightSpot.frag:96-97
+                float3 wcp = worldPos * 10.0f;                                               // :110
+                wd = mix3(wd, rv0, 0.5f);                                                    // :113
+                wd = normalize3(wd);                                                         // :114
+                wcp = wcp + wd * nw;                                                         // :115
+                wcp = wcp + rv0 * 2.5f;                                                      // :116
+                if (march<false>(V, wcp + normal * 0.5f, wd, hitDist, step0, steps, nullptr) < hitDist) shadow = 0.0f;   // :125
+                rays += 1;
+                pixels = 1;
+            }
+            out_shadow[(size_t)li * plane_stride + p.idx] = shadow;
+        }
+    }
+    flush_stats(g_stats, rays, (unsigned)steps, pixels);
+}
+
+// -------------------------------------------------------------------------------------------------
+// LightReflection.frag:60-113
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_reflection(VolView V, FrameView F, ViewK K, const float* __restrict__ g_lut,
+                                                    float* __restrict__ out_t, unsigned long long* __restrict__ g_stats) {
+    __shared__ float s_lut[512];
+    load_luts(s_lut, g_lut);
+    const PixelCtx p = pixel_ctx(F, K);
+    unsigned rays = 0, pixels = 0;
+    int steps = 0;
+    if (p.valid) {
+        const float depth = unorm24(__ldg(F.depth24 + p.idx));
+        float t = 256.0f;
+        if (depth < 0.999f) {                                                               // :88
+            const float3 pos = p.farvec * (depth * (1.0f + 1.0f / FAR_));                    // :64
+            const float3 normal = decode_normal(__ldg(F.normal + p.idx));                    // :65
+            const float roughness = unorm8(__ldg(F.material + p.idx));                       // :68
+            const float3 Vv = normalize3(pos) * -1.0f;                                       // :79
+            const float3 N = xyz(mat_mul(K.View, make_float4(normal.x, normal.y, normal.z, 0.0f)));   // :80
+            const float3 I = Vv * -1.0f;
+            const float3 R = I - N * dot3(N, I) * 2.0f;                                      // :81
+            float3 wd = normalize3(xyz(mat_mul(K.InvView, make_float4(R.x, R.y, R.z, 0.0f))));        // :92
+            float3 wcp = xyz(mat_mul(K.InvView, make_float4(pos.x, pos.y, pos.z, 1.0f))) * 10.0f;     // :93
+            const uint32_t n = get_noise(F, K, p, -1);
+            float3 rv = cosine_sample_hemisphere(s_lut, n, n >> 8);                          // :94
+            rv.z *= gsign(unorm8(n >> 16) - 0.5f);                                          // :95
+            wd = mix3(wd, rv, roughness * 0.1f);                                             // :96
+            const float nw = unorm8(n >> 24);
+            wcp = wcp + normal * nw;                                                         // :97
+            wd = wd * (1.0f + nw * 0.5f);                                                    // :98
+            t = march<false>(V, wcp + normal, wd, 256.0f, 0.5f, steps, nullptr);             // :113
+            rays = 1; pixels = 1;
+        }
+        out_t[p.idx] = t;
+    }
+    flush_stats(g_stats, rays, (unsigned)steps, pixels);
+}
+
+// -------------------------------------------------------------------------------------------------
+// Ray-level entry (level-1 parity): explicit rays in, 48-byte records out.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_trace_rays(VolView V, const vxl_ray* __restrict__ rays, long long n, int variant,
+                                                    vxl_hit* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const vxl_ray r = rays[i];
+    vxl_hit h;
+    h.t = 0.f; h.steps = 0; h.vx = h.vy = h.vz = 0; h.status = 0; h.px = h.py = h.pz = 0.f; h.nx = h.ny = h.nz = 0.f;
+    const float3 o = make_float3(r.ox, r.oy, r.oz), d = make_float3(r.dx, r.dy, r.dz);
+    if (variant == VXL_TRACE_DDA) {
+        DdaResult R;
+        dda(V, o, d, r.dist, R);
+        h.t = R.t; h.steps = R.nt; h.status = R.status; h.vx = R.vx; h.vy = R.vy; h.vz = R.vz;
+        if (R.status == 1) { h.px = R.hit.x; h.py = R.hit.y; h.pz = R.hit.z; h.nx = R.normal.x; h.ny = R.normal.y; h.nz = R.normal.z; }
+    } else {
+        MarchResult M;
+        int steps = 0;
+        march<true>(V, o, d, r.dist, variant == VXL_TRACE_SPARSE ? 0.5f : 2.5f, steps, &M);
+        h.t = M.d; h.steps = M.steps; h.status = M.status; h.vx = M.vx; h.vy = M.vy; h.vz = M.vz;
+        h.px = M.pos.x; h.py = M.pos.y; h.pz = M.pos.z;
+    }
+    out[i] = h;
+}
+
+static ViewK make_viewk(const vxl_view* v) {
+    ViewK k;
+    for (int i = 0; i < 16; ++i) { k.InvView[i] = v->InverseViewMatrix[i]; k.View[i] = v->ViewMatrix[i]; k.InvProj[i] = v->InverseProjectionMatrix[i]; }
+    k.Frame = v->Frame;
+    return k;
+}
+
+static unsigned grid_for(const FrameView& F) {
+    const int bpt_x = (F.tile_w + BLOCK_W - 1) / BLOCK_W, bpt_y = (F.tile_h + BLOCK_H - 1) / BLOCK_H;
+    return (unsigned)(bpt_x * bpt_y * F.n_tiles);
+}
+
+}  // namespace vxl
+
+using namespace vxl;
+
+extern "C" {
+
+int vxl_pass_ambient(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, const vxl_frame* frame, int n_ao,
+                     float* out_shadow, float* out_ao) {
+    if (!ctx || !vol || !view || !frame || n_ao < 0) { set_error("vxl_pass_ambient: bad argument"); return VXL_ERR_INVALID; }
+    FrameView F;
+    if (int e = frame_view(frame, &F)) return e;
+    if (!out_shadow && !out_ao) return VXL_OK;
+    if (F.n_tiles == 0) return VXL_OK;
+    if (vol->dirty) { if (int e = vxl_volume_build_occupancy(vol)) return e; }
+    k_ambient<<<grid_for(F), 256, 0, ctx->stream>>>(vol_view(vol), F, make_viewk(view), ctx->d_luts, n_ao, out_shadow, out_ao, ctx->d_stats);
+    VXL_LAUNCH_CHECK(ctx);
+    return VXL_OK;
+}
+
+static int local_lights(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, const vxl_frame* frame, const void* lights,
+                        int n_lights, size_t light_bytes, bool spot, float* out_shadow) {
+    if (!ctx || !vol || !view || !frame || n_lights < 0 || (n_lights > 0 && (!lights || !out_shadow))) {
+        set_error("vxl_pass_point/spot: bad argument");
+        return VXL_ERR_INVALID;
+    }
+    if (n_lights > VXL_MAX_LIGHTS) { set_error("more than VXL_MAX_LIGHTS lights"); return VXL_ERR_LIMIT; }
+    FrameView F;
+    if (int e = frame_view(frame, &F)) return e;
+    if (n_lights == 0 || F.n_tiles == 0) return VXL_OK;
+    if (vol->dirty) { if (int e = vxl_volume_build_occupancy(vol)) return e; }
+    VXL_CUDA(cudaMemcpyAsync(ctx->d_lights, lights, (size_t)n_lights * light_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t plane = frame_pixels(frame);
+    if (spot)
+        k_local_lights<true><<<grid_for(F), 256, 0, ctx->stream>>>(vol_view(vol), F, make_viewk(view), ctx->d_luts, (const float*)ctx->d_lights, n_lights, out_shadow, plane, ctx->d_stats);
+    else
+        k_local_lights<false><<<grid_for(F), 256, 0, ctx->stream>>>(vol_view(vol), F, make_viewk(view), ctx->d_luts, (const float*)ctx->d_lights, n_lights, out_shadow, plane, ctx->d_stats);
+    VXL_LAUNCH_CHECK(ctx);
+    return VXL_OK;
+}
+
+int vxl_pass_point(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, const vxl_frame* frame,
+                   const vxl_point_light* lights, int n_lights, float* out_shadow) {
+    return local_lights(ctx, vol, view, frame, lights, n_lights, sizeof(vxl_point_light), false, out_shadow);
+}
+
+int vxl_pass_spot(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, const vxl_frame* frame,
+                  const vxl_spot_light* lights, int n_lights, float* out_shadow) {
+    return local_lights(ctx, vol, view, frame, lights, n_lights, sizeof(vxl_spot_light), true, out_shadow);
+}
+
+int vxl_pass_reflection(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, const vxl_frame* frame, float* out_spec_t) {
+    if (!ctx || !vol || !view || !frame) { set_error("vxl_pass_reflection: bad argument"); return VXL_ERR_INVALID; }
+    if (!out_spec_t) return VXL_OK;
+    FrameView F;
+    if (int e = frame_view(frame, &F)) return e;
+    if (!F.material) { set_error("vxl_pass_reflection: frame.material is NULL"); return VXL_ERR_INVALID; }
+    if (F.n_tiles == 0) return VXL_OK;
+    if (vol->dirty) { if (int e = vxl_volume_build_occupancy(vol)) return e; }
+    k_reflection<<<grid_for(F), 256, 0, ctx->stream>>>(vol_view(vol), F, make_viewk(view), ctx->d_luts, out_spec_t, ctx->d_stats);
+    VXL_LAUNCH_CHECK(ctx);
+    return VXL_OK;
+}
+
+int vxl_trace_rays(vxl_ctx* ctx, vxl_volume* vol, const vxl_ray* rays, int64_t n, int variant, vxl_hit* out) {
+    if (!ctx || !vol || n < 0 || (n > 0 && (!rays || !out)) || variant < 0 || variant > 2) { set_error("vxl_trace_rays: bad argument"); return VXL_ERR_INVALID; }
+    if (n == 0) return VXL_OK;
+    if (vol->dirty) { if (int e = vxl_volume_build_occupancy(vol)) return e; }
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    k_trace_rays<<<grid, 256, 0, ctx->stream>>>(vol_view(vol), rays, (long long)n, variant, out);
+    VXL_LAUNCH_CHECK(ctx);
+    return VXL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,391 @@
+"""Host-side mirror of the reference's operator interface for the voxel-lighting path, over the
+C ABI of include/vxl.h.
+
+Names and argument meaning follow the reference (paths relative to /root/reference):
+    ShadowVoxSystem            Sources/World/Systems/ShadowVoxSystem.h:9-38
+    LightAmbientPipeline.Use   Sources/Graphics/Pipelines/LightAmbientPipeline.h:35-52
+    LightPointPipeline.Use     Sources/Graphics/Pipelines/LightPointPipeline.h:58-100   (+ DrawLight)
+    LightSpotPipeline.Use      Sources/Graphics/Pipelines/LightSpotPipeline.h:60-104    (+ DrawLight)
+    LightReflectionPipeline.Use Sources/Graphics/Pipelines/LightReflectionPipeline.h:34-51
+PyTorch supplies device memory, the stream and (in bench.py) torch.distributed; all arithmetic is
+in libvxl.so.  There is no fallback: constructing a Context without the library or a GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import check
+from .scenes import (ENTITY_DTYPE, HIT_DTYPE, POINT_LIGHT_DTYPE, RAY_DTYPE, REGION_DTYPE, SPOT_LIGHT_DTYPE,
+                     VIEW_DTYPE)
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _np_ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _dev_ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class Context:
+    """One GPU + one stream (vxl_ctx).  By default it launches on torch's current stream of that
+    device so torch.cuda.Event timing and torch tensors are ordered with the kernels."""
+
+    def __init__(self, device: int = 0, use_torch_stream: bool = True):
+        self.lib = capi.load()
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise capi.VxlError("no CUDA device: voxelengine_b200 has no CPU fallback")
+        self.device = int(device)
+        h = C.c_void_p()
+        check(self.lib.vxl_ctx_create(self.device, C.byref(h)), "vxl_ctx_create")
+        self.h = h
+        self.torch_device = torch.device("cuda", self.device)
+        if use_torch_stream:
+            s = torch.cuda.current_stream(self.torch_device).cuda_stream
+            check(self.lib.vxl_ctx_set_stream(self.h, C.c_void_p(s)), "vxl_ctx_set_stream")
+
+    def sync(self):
+        check(self.lib.vxl_sync(self.h), "vxl_sync")
+
+    def stats_reset(self):
+        check(self.lib.vxl_stats_reset(self.h), "vxl_stats_reset")
+
+    def stats(self) -> dict:
+        s = capi.Stats()
+        check(self.lib.vxl_stats_read(self.h, C.byref(s)), "vxl_stats_read")
+        return dict(rays=int(s.rays), steps=int(s.steps), pixels=int(s.pixels))
+
+    def launch_count(self) -> int:
+        n = C.c_uint64()
+        check(self.lib.vxl_launch_count(self.h, C.byref(n)), "vxl_launch_count")
+        return int(n.value)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vxl_ctx_destroy(self.h)
+            self.h = None
+
+    def empty(self, shape, dtype):
+        return _torch().empty(shape, dtype=dtype, device=self.torch_device)
+
+
+class ShadowVoxSystem:
+    """World occupancy volume.  Default size is the reference's 524 x 188 x 524 texels
+    (ShadowVoxSystem.cpp:56-58); here it is a runtime parameter."""
+
+    def __init__(self, ctx: Context, size=(524, 188, 524)):
+        self.ctx, self.lib = ctx, ctx.lib
+        self.sx, self.sy, self.sz = (int(v) for v in size)
+        h = C.c_void_p()
+        check(self.lib.vxl_volume_create(ctx.h, self.sx, self.sy, self.sz, C.byref(h)), "vxl_volume_create")
+        self.h = h
+        self._models = []
+
+    # --- reference-named surface -------------------------------------------------------------
+    def GetVolumeImage(self):
+        return self
+
+    def OnUpdate(self, entities: np.ndarray, want_regions: bool = True):
+        """ShadowVoxSystem::OnUpdate for the given visited entities (array of scenes.ENTITY_DTYPE,
+        in view order).  Returns (regions, valid) like the reference's _UpdateRegions pushes."""
+        entities = np.ascontiguousarray(entities, dtype=ENTITY_DTYPE)
+        n = len(entities)
+        if want_regions:
+            regions = np.zeros(n, dtype=REGION_DTYPE)
+            valid = np.zeros(n, dtype=np.int32)
+            check(self.lib.vxl_volume_voxelize(self.h, _np_ptr(entities), n, _np_ptr(regions), _np_ptr(valid)),
+                  "vxl_volume_voxelize")
+            return regions, valid
+        check(self.lib.vxl_volume_voxelize(self.h, _np_ptr(entities), n, None, None), "vxl_volume_voxelize")
+        return None, None
+
+    # --- data movement -----------------------------------------------------------------------
+    def add_model(self, voxels: np.ndarray) -> int:
+        """voxels: uint8 (sz, sy, sx) palette indices (x fastest), VoxAsset layout."""
+        voxels = np.ascontiguousarray(voxels, dtype=np.uint8)
+        msz, msy, msx = voxels.shape
+        mid = C.c_int()
+        check(self.lib.vxl_model_create(self.ctx.h, _np_ptr(voxels), msx, msy, msz, C.byref(mid)), "vxl_model_create")
+        return int(mid.value)
+
+    def upload(self, host: np.ndarray):
+        host = np.ascontiguousarray(host, dtype=np.uint8)
+        assert host.shape == (self.sz, self.sy, self.sx)
+        check(self.lib.vxl_volume_upload(self.h, _np_ptr(host)), "vxl_volume_upload")
+        self.ctx.sync()
+
+    def upload_regions(self, staging: np.ndarray, regions: np.ndarray):
+        """CmdBuffer::copy(_Buffer, _Volume, _UpdateRegions) (ShadowVoxSystem.cpp:196)."""
+        staging = np.ascontiguousarray(staging, dtype=np.uint8)
+        assert staging.shape == (self.sz, self.sy, self.sx)
+        regions = np.ascontiguousarray(regions, dtype=REGION_DTYPE)
+        check(self.lib.vxl_volume_upload_regions(self.h, _np_ptr(staging), _np_ptr(regions), len(regions)),
+              "vxl_volume_upload_regions")
+        self.ctx.sync()
+
+    def download(self) -> np.ndarray:
+        out = np.empty((self.sz, self.sy, self.sx), np.uint8)
+        check(self.lib.vxl_volume_download(self.h, _np_ptr(out)), "vxl_volume_download")
+        return out
+
+    def clear(self):
+        check(self.lib.vxl_volume_clear(self.h), "vxl_volume_clear")
+
+    def gen_terrain(self):
+        check(self.lib.vxl_volume_gen_terrain(self.h), "vxl_volume_gen_terrain")
+
+    def build_occupancy(self):
+        check(self.lib.vxl_volume_build_occupancy(self.h), "vxl_volume_build_occupancy")
+
+    def trace_rays(self, rays: np.ndarray, variant: int) -> np.ndarray:
+        """Ray-level entry: host rays in, host hit records out (copies through device buffers)."""
+        torch = _torch()
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        n = len(rays)
+        out = np.zeros(n, dtype=HIT_DTYPE)
+        if n == 0:
+            return out
+        d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1)).to(self.ctx.torch_device)
+        d_out = torch.empty(n * HIT_DTYPE.itemsize, dtype=torch.uint8, device=self.ctx.torch_device)
+        check(self.lib.vxl_trace_rays(self.ctx.h, self.h, _dev_ptr(d_rays), n, int(variant), _dev_ptr(d_out)), "vxl_trace_rays")
+        self.ctx.sync()
+        return d_out.cpu().numpy().view(HIT_DTYPE).copy()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vxl_volume_destroy(self.h)
+            self.h = None
+
+
+class GeometryBuffer:
+    """The G-buffer attachments the light passes read (Sources/Graphics/Graphics.h:51-60) plus the
+    blue-noise image, resident in HBM as torch int32 tensors in tile-compact layout.
+
+    A whole frame on one GPU is one tile (tile_w, tile_h = width, height).  For screen-tile
+    sharding, rank r of n holds tiles r, r+n, r+2n, ... of the tile grid."""
+
+    def __init__(self, ctx: Context, width: int, height: int, tile_w: int | None = None, tile_h: int | None = None,
+                 rank: int = 0, world: int = 1):
+        torch = _torch()
+        self.ctx = ctx
+        self.width, self.height = int(width), int(height)
+        self.tile_w = int(tile_w or width)
+        self.tile_h = int(tile_h or height)
+        self.tiles_x = -(-self.width // self.tile_w)
+        self.tiles_y = -(-self.height // self.tile_h)
+        total = self.tiles_x * self.tiles_y
+        self.tile_first, self.tile_stride = int(rank), int(world)
+        self.n_tiles = len(range(self.tile_first, total, self.tile_stride))
+        shape = (self.n_tiles, self.tile_h, self.tile_w)
+        self.depth24 = torch.full(shape, 0xFFFFFF, dtype=torch.int32, device=ctx.torch_device)
+        self.normal = torch.zeros(shape, dtype=torch.int32, device=ctx.torch_device)
+        self.material = torch.zeros(shape, dtype=torch.int32, device=ctx.torch_device)
+        self.noise = torch.zeros((512, 512), dtype=torch.int32, device=ctx.torch_device)
+
+    @property
+    def shape(self):
+        return (self.n_tiles, self.tile_h, self.tile_w)
+
+    def tile_ids(self):
+        return list(range(self.tile_first, self.tiles_x * self.tiles_y, self.tile_stride))
+
+    def frame(self) -> capi.Frame:
+        return capi.Frame(self.width, self.height, self.tile_w, self.tile_h, self.tile_first, self.tile_stride,
+                          self.n_tiles, 0, self.depth24.data_ptr(), self.normal.data_ptr(), self.material.data_ptr(),
+                          self.noise.data_ptr())
+
+    def set_noise(self, noise: np.ndarray):
+        torch = _torch()
+        self.noise.copy_(torch.from_numpy(np.ascontiguousarray(noise, dtype=np.uint32).view(np.int32)))
+
+    def set_planes(self, depth24: np.ndarray, normal: np.ndarray, material: np.ndarray):
+        """Upload full-frame (H, W) uint32 planes, extracting this shard's tiles."""
+        torch = _torch()
+        for name, a in (("depth24", depth24), ("normal", normal), ("material", material)):
+            t = self.to_tiles(np.ascontiguousarray(a, dtype=np.uint32))
+            getattr(self, name).copy_(torch.from_numpy(t.view(np.int32)))
+
+    def to_tiles(self, plane: np.ndarray) -> np.ndarray:
+        """(H, W) -> this shard's (n_tiles, tile_h, tile_w), zero padded at the frame edge."""
+        out = np.zeros(self.shape, dtype=plane.dtype)
+        for i, gt in enumerate(self.tile_ids()):
+            ty, tx = divmod(gt, self.tiles_x)
+            y0, x0 = ty * self.tile_h, tx * self.tile_w
+            blk = plane[y0:y0 + self.tile_h, x0:x0 + self.tile_w]
+            out[i, :blk.shape[0], :blk.shape[1]] = blk
+        return out
+
+    def from_tiles(self, tiles: np.ndarray, out: np.ndarray):
+        """Scatter this shard's (n_tiles, tile_h, tile_w) back into a full (H, W) plane."""
+        for i, gt in enumerate(self.tile_ids()):
+            ty, tx = divmod(gt, self.tiles_x)
+            y0, x0 = ty * self.tile_h, tx * self.tile_w
+            h, w = min(self.tile_h, self.height - y0), min(self.tile_w, self.width - x0)
+            out[y0:y0 + h, x0:x0 + w] = tiles[i, :h, :w]
+        return out
+
+    def synthesize(self, volume: ShadowVoxSystem, view: np.ndarray):
+        """Fill depth/normal/material with the synthetic primary-visibility G-buffer."""
+        f = self.frame()
+        v = np.ascontiguousarray(view, dtype=VIEW_DTYPE).reshape(())
+        check(self.ctx.lib.vxl_gbuffer_primary(self.ctx.h, volume.h, _np_ptr(v), C.byref(f)), "vxl_gbuffer_primary")
+
+
+def _view_ptr(view):
+    v = np.ascontiguousarray(view, dtype=VIEW_DTYPE).reshape(())
+    return v, _np_ptr(v)
+
+
+class LightAmbientPipeline:
+    """Sun shadow + ambient occlusion.  Use() keeps the reference argument order minus the Vulkan
+    command buffer and the sky box (only sampled for sky pixels' colour)."""
+    _inst = None
+
+    @classmethod
+    def Get(cls):
+        cls._inst = cls._inst or cls()
+        return cls._inst
+
+    def Use(self, viewBuffer, geometryFB: GeometryBuffer, shadowVox: ShadowVoxSystem, n_ao: int = 1,
+            out_shadow=None, out_ao=None):
+        torch = _torch()
+        ctx = geometryFB.ctx
+        if out_shadow is None:
+            out_shadow = ctx.empty(geometryFB.shape, torch.float32)
+        if out_ao is None:
+            out_ao = ctx.empty(geometryFB.shape, torch.float32)
+        v, vp = _view_ptr(viewBuffer)
+        f = geometryFB.frame()
+        check(ctx.lib.vxl_pass_ambient(ctx.h, shadowVox.h, vp, C.byref(f), int(n_ao), _dev_ptr(out_shadow), _dev_ptr(out_ao)),
+              "vxl_pass_ambient")
+        return out_shadow, out_ao
+
+
+class _LocalLightPipeline:
+    MAX_LIGHTS = capi.VXL_MAX_LIGHTS
+    _dtype = None
+    _fn = None
+
+    def __init__(self):
+        self._data = np.zeros(self.MAX_LIGHTS, dtype=self._dtype)
+        self._current = 0
+        self.warnings = 0
+
+    def _reset(self):
+        self._current = 0
+
+    def _use(self, viewBuffer, geometryFB, shadowVox, cb, out_shadow):
+        torch = _torch()
+        ctx = geometryFB.ctx
+        self._reset()                       # _CurrentLightIndex = 0
+        if cb is not None:
+            cb(self)
+        n = self._current
+        if out_shadow is None:
+            out_shadow = ctx.empty((n,) + geometryFB.shape, torch.float32)
+        if n == 0:
+            return out_shadow
+        v, vp = _view_ptr(viewBuffer)
+        f = geometryFB.frame()
+        fn = getattr(ctx.lib, self._fn)
+        check(fn(ctx.h, shadowVox.h, vp, C.byref(f), _np_ptr(self._data), n, _dev_ptr(out_shadow)), self._fn)
+        return out_shadow
+
+
+class LightPointPipeline(_LocalLightPipeline):
+    _dtype = POINT_LIGHT_DTYPE
+    _fn = "vxl_pass_point"
+    _inst = None
+
+    @classmethod
+    def Get(cls):
+        cls._inst = cls._inst or cls()
+        return cls._inst
+
+    def DrawLight(self, position, range_, color, attenuation):
+        # LightPointPipeline.h:58-72: beyond 64 lights the reference warns and drops the light
+        if self._current >= self.MAX_LIGHTS:
+            self.warnings += 1
+            return
+        l = self._data[self._current]
+        l["Position"], l["Range"], l["Color"], l["Attenuation"] = position, range_, color, attenuation
+        self._current += 1
+
+    def Use(self, viewBuffer, geometryFB, shadowVox, cb, out_shadow=None):
+        return self._use(viewBuffer, geometryFB, shadowVox, cb, out_shadow)
+
+
+class LightSpotPipeline(_LocalLightPipeline):
+    _dtype = SPOT_LIGHT_DTYPE
+    _fn = "vxl_pass_spot"
+    _inst = None
+
+    @classmethod
+    def Get(cls):
+        cls._inst = cls._inst or cls()
+        return cls._inst
+
+    def DrawLight(self, position, range_, color, attenuation, direction, angle, angleAttenuation):
+        if self._current >= self.MAX_LIGHTS:
+            self.warnings += 1
+            return
+        l = self._data[self._current]
+        l["Position"], l["Range"], l["Color"], l["Attenuation"] = position, range_, color, attenuation
+        l["Direction"], l["Angle"], l["AngleAttenuation"] = direction, angle, angleAttenuation
+        self._current += 1
+
+    def Use(self, viewBuffer, geometryFB, shadowVox, cb, out_shadow=None):
+        return self._use(viewBuffer, geometryFB, shadowVox, cb, out_shadow)
+
+
+class LightReflectionPipeline:
+    _inst = None
+
+    @classmethod
+    def Get(cls):
+        cls._inst = cls._inst or cls()
+        return cls._inst
+
+    def Use(self, viewBuffer, geometryFB: GeometryBuffer, shadowVox: ShadowVoxSystem, out_spec_t=None):
+        torch = _torch()
+        ctx = geometryFB.ctx
+        if out_spec_t is None:
+            out_spec_t = ctx.empty(geometryFB.shape, torch.float32)
+        v, vp = _view_ptr(viewBuffer)
+        f = geometryFB.frame()
+        check(ctx.lib.vxl_pass_reflection(ctx.h, shadowVox.h, vp, C.byref(f), _dev_ptr(out_spec_t)), "vxl_pass_reflection")
+        return out_spec_t
+
+
+def lighting_host(ctx: Context, shadowVox: ShadowVoxSystem, view, frame_desc: dict, planes: dict, outs: dict,
+                  n_ao: int = 1, point=None, spot=None):
+    """vxl_lighting_host: HOST (pinned torch / numpy) G-buffer planes in, HOST output planes out.
+    frame_desc: width,height,tile_w,tile_h,tile_first,tile_stride,n_tiles.  planes: depth24, normal,
+    material, noise (host arrays with .ctypes or torch CPU tensors).  outs: any of shadow, ao,
+    point_shadow, spot_shadow, spec_t."""
+    def hp(x):
+        if x is None:
+            return None
+        if hasattr(x, "data_ptr"):
+            return x.data_ptr()
+        return x.ctypes.data
+    v, vp = _view_ptr(view)
+    fr = capi.Frame(frame_desc["width"], frame_desc["height"], frame_desc["tile_w"], frame_desc["tile_h"],
+                    frame_desc["tile_first"], frame_desc["tile_stride"], frame_desc["n_tiles"], 0,
+                    hp(planes["depth24"]), hp(planes["normal"]), hp(planes.get("material")), hp(planes["noise"]))
+    pt = np.ascontiguousarray(point, dtype=POINT_LIGHT_DTYPE) if point is not None else None
+    sp = np.ascontiguousarray(spot, dtype=SPOT_LIGHT_DTYPE) if spot is not None else None
+    a = capi.LightingHostArgs(fr, vp, int(n_ao), 0 if pt is None else len(pt), 0 if sp is None else len(sp),
+                              None if pt is None else pt.ctypes.data, None if sp is None else sp.ctypes.data,
+                              hp(outs.get("shadow")), hp(outs.get("ao")), hp(outs.get("point_shadow")),
+                              hp(outs.get("spot_shadow")), hp(outs.get("spec_t")))
+    check(ctx.lib.vxl_lighting_host(ctx.h, shadowVox.h, C.byref(a)), "vxl_lighting_host")
