@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py -- shadow + AO + specular-occlusion throughput of the voxel-lighting pass.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 3] [--impl ours|reference]
+
+A "step" is one frame of the light passes over the workload BASELINE.json's metric is quoted on:
+config 3 = 1024^3-voxel FastNoise terrain + 200 props, 3840x2160, per lit pixel 1 sun-shadow ray +
+16 AO rays + up to 4 point-light shadow rays + 1 specular-occlusion ray (synthetic, seeded).
+N > 1 (torchrun, one rank per GPU): the same frame partitioned into 128x128 screen tiles dealt
+round-robin to the ranks, volume replicated, one NCCL all-gather of the output tiles per step.
+
+Prints ONE JSON line (rank 0).  `value` = rays actually generated per second with inputs resident
+in HBM; `e2e` = the same through the host-buffer C-ABI call (H2D + passes + D2H per step);
+`roofline` = algorithmic bytes of the dominant kernel / its CUDA-event time / measured HBM peak;
+`cpu_baseline` = the CPU oracle (oracle/liboracle.so) timed on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "shadow+AO+spec-occlusion Mrays/s"
+UNIT = "Mrays/s"
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(pass_name: str, st: dict, n_ao: int) -> int:
+    """sum_rays steps*1 B + sum_lit_pixels (in_px + out_px).  in_px = depth 4 + normal 4 + 4 per
+    distinct blue-noise texel (+ material 4 for the spec pass); out_px = 4 B per output scalar."""
+    if pass_name == "ambient":
+        return st["steps"] + st["pixels"] * (4 + 4 + 4 * max(n_ao, 1) + 8)
+    if pass_name == "point":
+        return st["steps"] + st["pixels"] * (4 + 4 + 4) + st["rays"] * 4
+    return st["steps"] + st["pixels"] * (4 + 4 + 4 + 4 + 4)
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm: the CPU oracle (a port of the reference shaders; the reference itself is Vulkan/Windows
+# only and cannot run here) on all host cores, inputs generated on the CPU as well.
+# ------------------------------------------------------------------------------------------------------
+def cpu_frame(O, vol, view, gb, lights, cfg, rows):
+    t0 = time.perf_counter()
+    rays = steps = 0
+    _, _, st = O.pass_ambient(vol, view, gb, cfg["n_ao"], rows=rows)
+    rays += st["rays"]; steps += st["steps"]
+    if cfg["n_point"]:
+        _, st = O.pass_point(vol, view, gb, lights, rows=rows)
+        rays += st["rays"]; steps += st["steps"]
+    if cfg["spec"]:
+        _, st = O.pass_reflection(vol, view, gb, rows=rows)
+        rays += st["rays"]; steps += st["steps"]
+    return rays, steps, time.perf_counter() - t0
+
+
+def pick_rows(O, vol, view, gb, lights, cfg, H, target_s=12.0):
+    """Bounded sample: every k-th row, k chosen from a 1/64 probe so that one pass over the sample takes ~target_s."""
+    r, s, dt = cpu_frame(O, vol, view, gb, lights, cfg, (0, H, 64))
+    est_full = dt * 64
+    k = int(max(1, min(64, np.ceil(est_full / target_s))))
+    return (0, H, k)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import vxo_py as O
+    from voxelengine_b200 import scenes as S
+    from voxelengine_b200.workloads import CONFIGS
+    cfg = CONFIGS[args.config]
+    sx, sy, sz = cfg["texels"]
+    W, H = cfg["res"]
+    if cfg["scene"] == "house":
+        vol = np.zeros((sz, sy, sx), np.uint8)
+        e = S.entities(1)
+        off = (2 * sx - 40) // 2
+        e[0]["cur"] = S.transform_matrix((off * 0.1, 0.2, off * 0.1))
+        O.voxelize(vol, [S.house_model(40, 1)], e)
+        ext = 2 * sx * 0.1
+        view = S.make_view((-ext * 0.2, ext * 0.9, -ext * 0.25), 3.927, -0.5, W, H, 0)
+    else:
+        vol = O.gen_terrain(sx, sy, sz)
+        if cfg["scene"] == "terrain+props":
+            O.voxelize(vol, [S.house_model(40, 1)], S.prop_entities(vol, n=cfg["n_props"], model_size=40, seed=2))
+        view = S.default_camera(cfg["texels"], W, H, 0)
+    d, n, m = O.gbuffer_primary(vol, view, W, H)
+    gb = dict(depth24=d, normal=n, material=m, noise=S.blue_noise(4))
+    lights = S.quarter_point_lights(vol, cfg["n_point"]) if cfg["n_point"] else None
+    rows = pick_rows(O, vol, view, gb, lights, cfg, H, target_s=max(2.0, 150.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_frame(O, vol, view, gb, lights, cfg, rows)
+    tot_r = tot_t = 0.0
+    for _ in range(args.steps):
+        r, s, dt = cpu_frame(O, vol, view, gb, lights, cfg, rows)
+        tot_r += r; tot_t += dt
+    val = tot_r / tot_t / 1e6
+    sample = f"rows {rows[0]}:{rows[1]}:{rows[2]} of the {W}x{H} frame per step ({int(tot_r / max(args.steps, 1))} rays)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32+u8", "data": "synthetic", "config": {"workload": cfg["name"], "volume_texels": list(cfg["texels"]), "resolution": [W, H]},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": O.num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from voxelengine_b200.build import build
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if local == 0:
+        build()
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    from voxelengine_b200 import engine as E
+    from voxelengine_b200.workloads import Workload
+
+    wl = Workload(args.config, rank=rank, world=world, device=local)
+    cfg = wl.cfg
+    W, H = wl.res
+    dev = wl.ctx.torch_device
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def flush():
+        flush_buf.fill_(rank & 0xFF)
+
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        return float(t.item())
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # per-frame accounting, counted by the kernels themselves (deterministic per frame)
+    st_local = wl.count()
+    rays = allsum(float(st_local["rays"]))
+    probes = allsum(float(st_local["steps"]))
+    lit = allsum(float(st_local["pixels"]))
+
+    for _ in range(max(args.warmup, 3)):
+        wl.step()
+    torch.cuda.synchronize()
+
+    # ---- timed region: K steps, CUDA events on the launching stream, L2 flushed between steps ----
+    launches0 = wl.ctx.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    with ClockSampler(local) as clk:
+        for a, b in ev:
+            flush()
+            a.record()
+            wl.step()
+            b.record()
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = wl.ctx.launch_count() - launches0
+    t_ms = allmax(sum(a.elapsed_time(b) for a, b in ev))
+    ms_per_step = t_ms / args.steps
+    value = rays / (ms_per_step * 1e-3) / 1e6
+
+    # warm-L2 variant (no flush), reported beside the flushed figure
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in ev2:
+        a.record(); wl.step(); b.record()
+    torch.cuda.synchronize()
+    ms_warm = allmax(sum(a.elapsed_time(b) for a, b in ev2)) / args.steps
+
+    # ---- per-kernel times (rank 0's shard) for the roofline of the dominant kernel ----
+    per = wl.per_pass_counts()
+    n = wl.gb.n_tiles
+    o = wl.out
+    tmp_pt = wl.ctx.empty((max(wl.n_point, 1), n, wl.gb.tile_h, wl.gb.tile_w), torch.float32)
+    calls = {"ambient": lambda: E.LightAmbientPipeline.Get().Use(wl.view, wl.gb, wl.vol, n_ao=wl.n_ao, out_shadow=o[0, :n], out_ao=o[1, :n])}
+    if wl.n_point:
+        calls["point"] = lambda: wl._point(tmp_pt)
+    if wl.spec:
+        calls["reflection"] = lambda: E.LightReflectionPipeline.Get().Use(wl.view, wl.gb, wl.vol, out_spec_t=o[2, :n])
+    ktime = {}
+    for name, fn in calls.items():
+        tt = 0.0
+        for _ in range(args.steps):
+            flush()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            tt += a.elapsed_time(b)
+        ktime[name] = tt / args.steps
+    dom = max(ktime, key=ktime.get)
+    peak, peak_src = hbm_peak()
+    abytes = algorithmic_bytes(dom, per[dom], wl.n_ao)
+    achieved = abytes / (ktime[dom] * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get({"ambient": "k_ambient", "point": "k_local_lights", "reflection": "k_reflection"}[dom])
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": {"ambient": "k_ambient", "point": "k_local_lights<false>", "reflection": "k_reflection"}[dom],
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes, "kernel_ms": ktime[dom],
+                "all_kernels_ms": ktime, "probes_per_s": per[dom]["steps"] / (ktime[dom] * 1e-3)}
+
+    # ---- end to end: host buffers in, host buffers out, every step ----
+    e2e = run_e2e(args, wl, torch, dist, world, rank, rays)
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample of the same frame ----
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        from oracle import vxo_py as O
+        vol_h = wl.host_volume if wl.host_volume is not None else wl.vol.download()
+        gbh = {k: getattr(wl.gb, k).cpu().numpy().view(np.uint32)[0] for k in ("depth24", "normal", "material")}
+        gbh["noise"] = wl.gb.noise.cpu().numpy().view(np.uint32)
+        rows = pick_rows(O, vol_h, wl.view, gbh, wl.lights, cfg, H, target_s=15.0)
+        r, s, dt = cpu_frame(O, vol_h, wl.view, gbh, wl.lights, cfg, rows)
+        cpu = {"value": r / dt / 1e6, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
+               "sample": f"rows {rows[0]}:{rows[1]}:{rows[2]} of the {W}x{H} frame ({r} rays, {dt:.1f} s)"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+u8",
+            "data": "synthetic",
+            "config": {"workload": cfg["name"], "volume_texels": list(wl.texels), "resolution": [W, H],
+                       "rays_per_step": int(rays), "probes_per_step": int(probes), "lit_pixels": int(lit),
+                       "parallelism": "1 GPU, whole frame" if world == 1 else f"{world} GPUs, 128x128 screen tiles round-robin, volume replicated, NCCL all-gather of output tiles",
+                       "l2": "flushed between timed steps (256 MiB fill outside the event pairs); per-step working set 128 MiB volume + 100 MB G-buffer + 232 MB outputs",
+                       "ms_per_step_warm_l2": ms_warm},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(),
+        }))
+    wl.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, wl, torch, dist, world, rank, rays):
+    """Same metric through the host-facing call.  N=1: vxl_lighting_host (pinned host G-buffer in, pinned host planes
+    out).  N>1: each rank uploads its tile shard from pinned memory, runs the passes, all-gathers on the device, and
+    rank 0 reads the assembled tiles back."""
+    from voxelengine_b200 import engine as E
+    steps = max(3, min(args.steps, 10))
+    n = wl.gb.n_tiles
+    shape = (n, wl.gb.tile_h, wl.gb.tile_w)
+    planes = {k: getattr(wl.gb, k).cpu().pin_memory() for k in ("depth24", "normal", "material")}
+    planes["noise"] = wl.gb.noise.cpu().pin_memory()
+    px = int(np.prod(shape))
+    h2d = 3 * px * 4 + 512 * 512 * 4
+    if world == 1:
+        outs = dict(shadow=torch.empty(shape, dtype=torch.float32).pin_memory(), ao=torch.empty(shape, dtype=torch.float32).pin_memory())
+        if wl.spec:
+            outs["spec_t"] = torch.empty(shape, dtype=torch.float32).pin_memory()
+        if wl.n_point:
+            outs["point_shadow"] = torch.empty((wl.n_point,) + shape, dtype=torch.float32).pin_memory()
+        d2h = sum(int(t.numel()) * 4 for t in outs.values())
+        desc = dict(width=wl.gb.width, height=wl.gb.height, tile_w=wl.gb.tile_w, tile_h=wl.gb.tile_h, tile_first=wl.gb.tile_first,
+                    tile_stride=wl.gb.tile_stride, n_tiles=n)
+
+        def one():
+            E.lighting_host(wl.ctx, wl.vol, wl.view, desc, planes, outs, n_ao=wl.n_ao, point=wl.lights)
+        for _ in range(2):
+            one()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            one()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / steps
+        # the device planes must equal the resident path's
+        ref = wl.step(gather=False).cpu()
+        assert torch.equal(outs["shadow"], ref[0, :n]) and torch.equal(outs["ao"], ref[1, :n]), "e2e planes differ from the resident path"
+        return {"value": rays / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3,
+                "api": "vxl_lighting_host (pinned host buffers)"}
+    host_full = torch.empty((world,) + tuple(wl.out.shape), dtype=torch.float32).pin_memory() if rank == 0 else None
+    d2h = int(host_full.numel()) * 4 if rank == 0 else 0
+
+    def one():
+        for k in ("depth24", "normal", "material"):
+            getattr(wl.gb, k).copy_(planes[k], non_blocking=True)
+        wl.gb.noise.copy_(planes["noise"], non_blocking=True)
+        wl.step(gather=True)
+        if rank == 0:
+            host_full.copy_(wl.gathered, non_blocking=True)
+        torch.cuda.synchronize()
+    for _ in range(2):
+        one()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dist.barrier()
+    dt = (time.perf_counter() - t0) / steps
+    t = torch.tensor([dt, float(h2d)], dtype=torch.float64, device=wl.ctx.torch_device)
+    tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    tsum = t.clone(); dist.all_reduce(tsum)
+    dt = float(tmax[0].item())
+    return {"value": rays / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(tsum[1].item()), "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3,
+            "api": "pinned shard upload + passes + NCCL all-gather + rank-0 readback"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

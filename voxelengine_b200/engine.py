@@ -18,6 +18,7 @@ import numpy as np
 
 from . import capi
 from .capi import check
+from .tiles import TileLayout
 from .scenes import (ENTITY_DTYPE, HIT_DTYPE, POINT_LIGHT_DTYPE, RAY_DTYPE, REGION_DTYPE, SPOT_LIGHT_DTYPE,
                      VIEW_DTYPE)
 
@@ -177,14 +178,10 @@ class GeometryBuffer:
                  rank: int = 0, world: int = 1):
         torch = _torch()
         self.ctx = ctx
-        self.width, self.height = int(width), int(height)
-        self.tile_w = int(tile_w or width)
-        self.tile_h = int(tile_h or height)
-        self.tiles_x = -(-self.width // self.tile_w)
-        self.tiles_y = -(-self.height // self.tile_h)
-        total = self.tiles_x * self.tiles_y
-        self.tile_first, self.tile_stride = int(rank), int(world)
-        self.n_tiles = len(range(self.tile_first, total, self.tile_stride))
+        self.layout = L = TileLayout(width, height, tile_w, tile_h, rank, world)
+        self.width, self.height, self.tile_w, self.tile_h = L.width, L.height, L.tile_w, L.tile_h
+        self.tiles_x, self.tiles_y = L.tiles_x, L.tiles_y
+        self.tile_first, self.tile_stride, self.n_tiles = L.tile_first, L.tile_stride, L.n_tiles
         shape = (self.n_tiles, self.tile_h, self.tile_w)
         self.depth24 = torch.full(shape, 0xFFFFFF, dtype=torch.int32, device=ctx.torch_device)
         self.normal = torch.zeros(shape, dtype=torch.int32, device=ctx.torch_device)
@@ -196,7 +193,7 @@ class GeometryBuffer:
         return (self.n_tiles, self.tile_h, self.tile_w)
 
     def tile_ids(self):
-        return list(range(self.tile_first, self.tiles_x * self.tiles_y, self.tile_stride))
+        return self.layout.ids()
 
     def frame(self) -> capi.Frame:
         return capi.Frame(self.width, self.height, self.tile_w, self.tile_h, self.tile_first, self.tile_stride,
@@ -216,22 +213,11 @@ class GeometryBuffer:
 
     def to_tiles(self, plane: np.ndarray) -> np.ndarray:
         """(H, W) -> this shard's (n_tiles, tile_h, tile_w), zero padded at the frame edge."""
-        out = np.zeros(self.shape, dtype=plane.dtype)
-        for i, gt in enumerate(self.tile_ids()):
-            ty, tx = divmod(gt, self.tiles_x)
-            y0, x0 = ty * self.tile_h, tx * self.tile_w
-            blk = plane[y0:y0 + self.tile_h, x0:x0 + self.tile_w]
-            out[i, :blk.shape[0], :blk.shape[1]] = blk
-        return out
+        return self.layout.to_tiles(plane)
 
     def from_tiles(self, tiles: np.ndarray, out: np.ndarray):
         """Scatter this shard's (n_tiles, tile_h, tile_w) back into a full (H, W) plane."""
-        for i, gt in enumerate(self.tile_ids()):
-            ty, tx = divmod(gt, self.tiles_x)
-            y0, x0 = ty * self.tile_h, tx * self.tile_w
-            h, w = min(self.tile_h, self.height - y0), min(self.tile_w, self.width - x0)
-            out[y0:y0 + h, x0:x0 + w] = tiles[i, :h, :w]
-        return out
+        return self.layout.from_tiles(tiles, out)
 
     def synthesize(self, volume: ShadowVoxSystem, view: np.ndarray):
         """Fill depth/normal/material with the synthetic primary-visibility G-buffer."""

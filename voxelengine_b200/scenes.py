@@ -2,7 +2,7 @@
 light lists, .vox-style models, entity transforms and blue noise.
 
 Everything here produces *inputs* (plain numpy arrays with the reference's byte layouts); the same
-bytes are handed to the CUDA path and, in tests, to the CPU oracle.  Nothing in this module is path
+bytes are handed to the CUDA path and, in tests, to the CPU checker.  Nothing in this module is path
 arithmetic.  Layouts cite /root/reference paths.
 """
 from __future__ import annotations

@@ -1,0 +1,68 @@
+"""Screen-tile partitioning of a frame across ranks: the tile grid is laid row-major
+over the frame, tile g goes to rank g % world ("round-robin" for load balance between sky and dense
+regions), each rank stores its tiles compactly as [n_local][tile_h][tile_w] (zero padded at the frame
+edge) and, for the gather, pads its tile count to ceil(total / world).  Pure host logic (numpy /
+torch.distributed); the kernels consume the same description through vxl_frame."""
+from __future__ import annotations
+
+import numpy as np
+
+
+class TileLayout:
+    def __init__(self, width, height, tile_w=None, tile_h=None, rank=0, world=1):
+        self.width, self.height = int(width), int(height)
+        self.tile_w, self.tile_h = int(tile_w or width), int(tile_h or height)
+        self.tiles_x = -(-self.width // self.tile_w)
+        self.tiles_y = -(-self.height // self.tile_h)
+        self.total = self.tiles_x * self.tiles_y
+        self.rank, self.world = int(rank), int(world)
+        if not (0 <= self.rank < self.world):
+            raise ValueError("rank out of range")
+        self.tile_first, self.tile_stride = self.rank, self.world
+        self.n_tiles = len(range(self.tile_first, self.total, self.tile_stride))
+        self.tiles_padded = -(-self.total // self.world)
+
+    def ids(self, rank=None):
+        r = self.rank if rank is None else rank
+        return list(range(r, self.total, self.world))
+
+    def rect(self, g):
+        ty, tx = divmod(g, self.tiles_x)
+        y0, x0 = ty * self.tile_h, tx * self.tile_w
+        return y0, x0, min(self.tile_h, self.height - y0), min(self.tile_w, self.width - x0)
+
+    def to_tiles(self, plane: np.ndarray, rank=None) -> np.ndarray:
+        """(..., H, W) -> (..., n_local, tile_h, tile_w) for `rank` (default: own), zero padded."""
+        ids = self.ids(rank)
+        out = np.zeros(plane.shape[:-2] + (len(ids), self.tile_h, self.tile_w), dtype=plane.dtype)
+        for i, g in enumerate(ids):
+            y0, x0, h, w = self.rect(g)
+            out[..., i, :h, :w] = plane[..., y0:y0 + h, x0:x0 + w]
+        return out
+
+    def from_tiles(self, tiles: np.ndarray, out: np.ndarray, rank=None) -> np.ndarray:
+        """Scatter (..., >=n_local, tile_h, tile_w) of `rank` into the full (..., H, W) plane `out`."""
+        for i, g in enumerate(self.ids(rank)):
+            y0, x0, h, w = self.rect(g)
+            out[..., y0:y0 + h, x0:x0 + w] = tiles[..., i, :h, :w]
+        return out
+
+    def assemble(self, gathered: np.ndarray) -> np.ndarray:
+        """gathered: (world, planes, tiles_padded, tile_h, tile_w) as produced by all_gather of every
+        rank's padded tile stack -> (planes, H, W)."""
+        full = np.zeros((gathered.shape[1], self.height, self.width), gathered.dtype)
+        for r in range(self.world):
+            self.from_tiles(gathered[r], full, rank=r)
+        return full
+
+
+def gather_tiles(local, group=None, out=None):
+    """all-gather every rank's padded tile stack (torch tensor, same shape on all ranks) ->
+    (world, *local.shape).  Works with NCCL (device tensors) and gloo (CPU tensors)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if out is None:
+        out = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out.view(-1), local.contiguous().view(-1), group=group)
+    return out

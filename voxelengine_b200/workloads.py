@@ -1,0 +1,170 @@
+"""The BASELINE.json configs as concrete device-resident workloads.
+
+"N^3 volume" = N^3 voxels = (N/2)^3 bytes in the reference's 2x2x2-bits-per-byte layout.
+A workload owns the volume, the (tile-sharded) G-buffer, the packed output tensor and runs one
+"step" = one frame of the light passes over this rank's tiles.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import engine as E
+from . import scenes as S
+
+CONFIGS = {
+    1: dict(name="cfg1: 64^3 .vox-style model, 256x256, 1 sun shadow + 4 AO", texels=(32, 32, 32), res=(256, 256),
+            scene="house", n_ao=4, n_point=0, spec=False),
+    2: dict(name="cfg2: 512^3 FastNoise terrain, 1080p, 1 sun shadow + 8 AO", texels=(256, 256, 256), res=(1920, 1080),
+            scene="terrain", n_ao=8, n_point=0, spec=False),
+    3: dict(name="cfg3: 1024^3 terrain + 200 props, 4K, sun shadow + 16 AO + 4 point-light shadows + spec occlusion",
+            texels=(512, 512, 512), res=(3840, 2160), scene="terrain+props", n_props=200, n_ao=16, n_point=4, spec=True),
+    4: dict(name="cfg4: 1024^3, 1000 moving 16^3 entities re-voxelised per frame, 1080p sun shadow + 1 AO",
+            texels=(512, 512, 512), res=(1920, 1080), scene="dynamic", n_entities=1000, n_ao=1, n_point=0, spec=False),
+    5: dict(name="cfg5: 2048^3 terrain + 200 props, 8K, sun shadow + 16 AO + 4 point-light shadows + spec occlusion",
+            texels=(1024, 1024, 1024), res=(7680, 4320), scene="terrain+props", n_props=200, n_ao=16, n_point=4, spec=True),
+}
+
+
+class Workload:
+    def __init__(self, config: int, rank: int = 0, world: int = 1, device: int | None = None, tile=(128, 128),
+                 scale: float = 1.0, frame_index: int = 0):
+        """scale < 1 shrinks volume and resolution proportionally (tests only; the bench uses 1.0)."""
+        import torch
+        self.torch = torch
+        cfg = dict(CONFIGS[config])
+        self.cfg, self.config, self.rank, self.world = cfg, config, rank, world
+        tex = tuple(max(16, int(round(t * scale))) for t in cfg["texels"])
+        res = tuple(max(32, int(round(r * scale))) for r in cfg["res"])
+        self.texels, self.res = tex, res
+        self.ctx = E.Context(rank if device is None else device)
+        self.vol = E.ShadowVoxSystem(self.ctx, tex)
+        W, H = res
+        if world == 1:
+            self.gb = E.GeometryBuffer(self.ctx, W, H)
+        else:
+            self.gb = E.GeometryBuffer(self.ctx, W, H, tile[0], tile[1], rank=rank, world=world)
+        self.host_volume = None
+        self.entities = None
+        self._build_scene(scale)
+        self.view = S.default_camera(tex, W, H, frame_index) if cfg["scene"] != "house" else self._house_view(W, H, frame_index)
+        self.gb.set_noise(S.blue_noise(4))
+        self.gb.synthesize(self.vol, self.view)
+        self.n_ao, self.n_point, self.spec = cfg["n_ao"], cfg["n_point"], cfg["spec"]
+        self.lights = S.quarter_point_lights(self.host_volume, self.n_point) if self.n_point else None
+        # packed outputs: planes [shadow, ao, spec_t, point_0..point_{n-1}], every rank padded to the same tile count
+        total_tiles = self.gb.tiles_x * self.gb.tiles_y
+        self.tiles_padded = -(-total_tiles // world)
+        self.n_planes = 3 + self.n_point
+        self.out = torch.zeros((self.n_planes, self.tiles_padded, self.gb.tile_h, self.gb.tile_w), dtype=torch.float32,
+                               device=self.ctx.torch_device)
+        self.gathered = None
+        self.ctx.sync()
+
+    # -- scene -------------------------------------------------------------------------------------
+    def _house_view(self, W, H, frame):
+        ext = 2 * self.texels[0] * 0.1
+        return S.make_view((-ext * 0.2, ext * 0.9, -ext * 0.25), 3.927, -0.5, W, H, frame)
+
+    def _build_scene(self, scale):
+        cfg, vol = self.cfg, self.vol
+        sx, sy, sz = self.texels
+        if cfg["scene"] == "house":
+            msz = max(8, int(round(40 * scale)))
+            mid = vol.add_model(S.house_model(msz, seed=1))
+            e = S.entities(1)
+            off = (2 * sx - msz) // 2
+            e[0]["model"] = mid
+            e[0]["cur"] = S.transform_matrix((off * 0.1, 0.2, off * 0.1))
+            vol.OnUpdate(e, want_regions=False)
+            self.host_volume = vol.download()
+            return
+        vol.gen_terrain()
+        self.host_volume = vol.download()
+        if cfg["scene"] == "terrain+props":
+            msz = max(8, int(round(40 * scale)))
+            mid = vol.add_model(S.house_model(msz, seed=1))
+            e = S.prop_entities(self.host_volume, n=cfg["n_props"], model_size=msz, seed=2, model=mid)
+            vol.OnUpdate(e, want_regions=False)
+            self.host_volume = vol.download()
+        elif cfg["scene"] == "dynamic":
+            mid = vol.add_model(S.shell_cube_model(16))
+            self.entities, self._pos, self._yaw = S.dynamic_entities(self.texels, cfg["n_entities"], seed=3, model=mid)
+            vol.OnUpdate(self.entities, want_regions=False)     # first frame: prev = identity (reference quirk)
+            self.host_volume = None                              # changes every frame; download on demand
+
+    # -- one frame ---------------------------------------------------------------------------------
+    def planes(self):
+        n = self.gb.n_tiles
+        o = self.out
+        return dict(shadow=o[0, :n], ao=o[1, :n], spec_t=o[2, :n], point=o[3:, :n])
+
+    def step(self, gather: bool = True):
+        """One frame over this rank's tiles; with world > 1, all-gather the packed output tiles."""
+        if self.cfg["scene"] == "dynamic":
+            self.entities, self._pos, self._yaw = S.advance_entities(self.entities, self._pos, self._yaw)
+            self.vol.OnUpdate(self.entities, want_regions=False)
+            self.vol.build_occupancy()
+        n = self.gb.n_tiles
+        o = self.out
+        E.LightAmbientPipeline.Get().Use(self.view, self.gb, self.vol, n_ao=self.n_ao, out_shadow=o[0, :n], out_ao=o[1, :n])
+        if self.n_point:
+            # point planes are [n_point][tiles_padded] inside `out`; the C ABI wants consecutive planes of the
+            # shard's own size, which holds when tiles_padded == n_tiles; otherwise stage through a view copy
+            if n == self.tiles_padded:
+                self._point(o[3:])
+            else:
+                tmp = self.ctx.empty((self.n_point, n, self.gb.tile_h, self.gb.tile_w), self.torch.float32)
+                self._point(tmp)
+                o[3:, :n].copy_(tmp)
+        if self.spec:
+            E.LightReflectionPipeline.Get().Use(self.view, self.gb, self.vol, out_spec_t=o[2, :n])
+        if gather and self.world > 1:
+            from .tiles import gather_tiles
+            self.gathered = gather_tiles(self.out, out=self.gathered)   # the one collective of the path
+        return self.out
+
+    def _point(self, out):
+        L = self.lights
+        E.LightPointPipeline.Get().Use(self.view, self.gb, self.vol,
+                                       lambda p: [p.DrawLight(l["Position"], l["Range"], l["Color"], l["Attenuation"]) for l in L],
+                                       out_shadow=out)
+
+    # -- accounting --------------------------------------------------------------------------------
+    def count(self):
+        """(rays, probes, lit pixels) of one frame on this rank, counted by the kernels themselves."""
+        self.ctx.stats_reset()
+        self.step(gather=False)
+        return self.ctx.stats()
+
+    def per_pass_counts(self):
+        """stats per pass (ambient, point, reflection) of one frame on this rank."""
+        n = self.gb.n_tiles
+        o = self.out
+        res = {}
+        self.ctx.stats_reset()
+        E.LightAmbientPipeline.Get().Use(self.view, self.gb, self.vol, n_ao=self.n_ao, out_shadow=o[0, :n], out_ao=o[1, :n])
+        res["ambient"] = self.ctx.stats()
+        if self.n_point:
+            self.ctx.stats_reset()
+            tmp = self.ctx.empty((self.n_point, n, self.gb.tile_h, self.gb.tile_w), self.torch.float32)
+            self._point(tmp)
+            res["point"] = self.ctx.stats()
+        if self.spec:
+            self.ctx.stats_reset()
+            E.LightReflectionPipeline.Get().Use(self.view, self.gb, self.vol, out_spec_t=o[2, :n])
+            res["reflection"] = self.ctx.stats()
+        return res
+
+    def assemble(self, gathered: np.ndarray | None = None):
+        """Full-frame float planes (n_planes, H, W) from the gathered tile-compact tensor (or, world == 1, from out)."""
+        W, H = self.res
+        full = np.zeros((self.n_planes, H, W), np.float32)
+        if self.world == 1:
+            full[:] = self.out.cpu().numpy()[:, 0, :H, :W]
+            return full
+        g = self.gathered.cpu().numpy() if gathered is None else gathered
+        return self.gb.layout.assemble(g)
+
+    def close(self):
+        self.vol.close()
+        self.ctx.close()
