@@ -248,6 +248,18 @@ def run_ours(args):
     torch.cuda.synchronize()
     ms_warm = allmax(sum(a.elapsed_time(b) for a, b in ev2)) / args.steps
 
+    # plain per-probe march (kernel variant 0) on the same frame, for the record: same results, no culling
+    wl.ctx.set_variant(0)
+    wl.step(); torch.cuda.synchronize()
+    ev3 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
+    for a, b in ev3:
+        flush(); a.record(); wl.step(); b.record()
+    torch.cuda.synchronize()
+    ms_plain = allmax(sum(a.elapsed_time(b) for a, b in ev3)) / 3
+    wl.ctx.set_variant(1)
+    wl.ctx.stats_reset(); wl.step(gather=False)
+    exact_probes = allsum(float(wl.ctx.exact_probes()))
+
     # ---- per-kernel times (rank 0's shard) for the roofline of the dominant kernel ----
     per = wl.per_pass_counts()
     n = wl.gb.n_tiles
@@ -285,7 +297,7 @@ def run_ours(args):
                 "all_kernels_ms": ktime, "probes_per_s": per[dom]["steps"] / (ktime[dom] * 1e-3)}
 
     # ---- end to end: host buffers in, host buffers out, every step ----
-    e2e = run_e2e(args, wl, torch, dist, world, rank, rays)
+    e2e = None if args.no_e2e else run_e2e(args, wl, torch, dist, world, rank, rays)
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample of the same frame ----
     cpu = None
@@ -308,7 +320,8 @@ def run_ours(args):
                        "rays_per_step": int(rays), "probes_per_step": int(probes), "lit_pixels": int(lit),
                        "parallelism": "1 GPU, whole frame" if world == 1 else f"{world} GPUs, 128x128 screen tiles round-robin, volume replicated, NCCL all-gather of output tiles",
                        "l2": "flushed between timed steps (256 MiB fill outside the event pairs); per-step working set 128 MiB volume + 100 MB G-buffer + 232 MB outputs",
-                       "ms_per_step_warm_l2": ms_warm},
+                       "ms_per_step_warm_l2": ms_warm, "ms_per_step_plain_march_variant0": ms_plain,
+                       "probes_executed_exactly": int(exact_probes)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(),
         }))
     wl.close()
@@ -388,6 +401,7 @@ def main():
     ap.add_argument("--config", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,0 +1,126 @@
+"""The accelerated march (clearance-map culling + exact replay, vxl_fastmarch.cuh) compiled for the HOST
+must reproduce the oracle's plain march bit-for-bit: distance, probe count, hit voxel, hit position.
+Runs without a GPU; the same header is what the CUDA kernels instantiate."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(__file__))
+import scene_util as U  # noqa: E402
+from emul import emul_py  # noqa: E402
+from voxelengine_b200 import scenes as S  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def terrain(oracle):
+    return U.terrain_scene(oracle)
+
+
+@pytest.fixture(scope="module")
+def emul(terrain):
+    e = emul_py.Emul(terrain["volume"])
+    yield e
+    e.close()
+
+
+def _compare(got, want):
+    for f in ("steps", "vx", "vy", "vz", "status"):
+        assert np.array_equal(got[f], want[f]), f"{f}: {(got[f] != want[f]).sum()} rays differ"
+    for f in ("t", "px", "py", "pz"):
+        a, b = got[f].view(np.uint32), want[f].view(np.uint32)
+        nan_both = np.isnan(got[f]) & np.isnan(want[f])
+        assert np.array_equal(a[~nan_both], b[~nan_both]), f"{f}: {(a != b).sum()} rays differ bitwise"
+
+
+def _surface_rays(rs, vol, n, center, spread, dist_choices):
+    """Rays shaped like the light passes': origins clustered within `spread` voxels of `center`, unit-ish directions."""
+    r = np.zeros(n, dtype=S.RAY_DTYPE)
+    o = np.asarray(center, np.float32) + rs.uniform(-spread, spread, size=(n, 3)).astype(np.float32)
+    d = rs.normal(size=(n, 3)).astype(np.float32)
+    d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-6).astype(np.float32)
+    d *= rs.choice([1.0, 1.0, 1.0, 0.7, 1.5], size=(n, 1)).astype(np.float32)
+    r["ox"], r["oy"], r["oz"] = o[:, 0], o[:, 1], o[:, 2]
+    r["dx"], r["dy"], r["dz"] = d[:, 0], d[:, 1], d[:, 2]
+    r["dist"] = rs.choice(dist_choices, size=n).astype(np.float32)
+    return r
+
+
+def _surface_points(vol, k, rs):
+    """k voxel positions just above solid terrain."""
+    sz, sy, sx = vol.shape
+    pts = []
+    while len(pts) < k:
+        x, z = rs.randint(4, 2 * sx - 4), rs.randint(4, 2 * sz - 4)
+        col = vol[z // 2, :, x // 2]
+        ys = np.nonzero(col)[0]
+        if len(ys):
+            pts.append((x, 2 * int(ys.max()) + 3, z))
+    return pts
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_emulated_fast_march_matches_oracle_on_pass_like_rays(oracle, terrain, emul, variant):
+    vol = terrain["volume"]
+    rs = np.random.RandomState(100 + variant)
+    total_exact = total_steps = 0
+    for center in _surface_points(vol, 12, rs):
+        rays = _surface_rays(rs, vol, 20_000, center, 6.0, [128.0, 256.0, 40.0, 73.3, 17.0, 10.0, 164.0, 500.0])
+        want = oracle.trace_rays(vol, rays, variant)
+        got, exact, steps = emul.trace(rays, variant, center)
+        _compare(got, want)
+        assert steps == int(want["steps"].sum())
+        total_exact += exact
+        total_steps += steps
+    # the acceleration really engages: most probes are proven empty, not executed
+    assert total_exact < 0.6 * total_steps, (total_exact, total_steps)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_emulated_fast_march_matches_oracle_on_arbitrary_rays(oracle, terrain, emul, variant):
+    """Rays that start outside the volume, at negative coordinates, axis-parallel, on voxel boundaries, far from
+    the tile centre, with NaN / inf / zero directions: eligibility must route them correctly."""
+    vol = terrain["volume"]
+    sz, sy, sx = vol.shape
+    rs = np.random.RandomState(7 + variant)
+    rays = U.random_rays(rs, 100_000, (2 * sx, 2 * sy, 2 * sz), dist_lo=5.0)
+    k = 64
+    rays["dx"][:k] = np.nan
+    rays["oy"][k:2 * k] = np.inf
+    rays["dx"][2 * k:3 * k] = 0.0; rays["dy"][2 * k:3 * k] = 0.0; rays["dz"][2 * k:3 * k] = 0.0
+    rays["dist"][3 * k:4 * k] = np.nan
+    rays["dist"][4 * k:5 * k] = np.inf
+    rays["dist"][5 * k:6 * k] = -3.0
+    want = oracle.trace_rays(vol, rays, variant)
+    for center in [(sx, sy, sz), (10, 2 * sy - 5, 2 * sz - 3), (-40, 50, 300)]:
+        got, _, steps = emul.trace(rays, variant, center)
+        _compare(got, want)
+
+
+def test_emulated_plain_march_is_the_oracle(oracle, terrain, emul):
+    vol = terrain["volume"]
+    sz, sy, sx = vol.shape
+    rays = U.random_rays(np.random.RandomState(3), 50_000, (2 * sx, 2 * sy, 2 * sz))
+    for variant in (0, 1):
+        got, exact, _ = emul.trace(rays, variant, (sx, sy, sz), fast=False)
+        _compare(got, oracle.trace_rays(vol, rays, variant))
+        assert exact == 0
+
+
+def test_bruteforce_clearance_is_a_chebyshev_distance(terrain, emul):
+    """emul's brute-force maps (the reference for the GPU build test) against scipy's chessboard transform."""
+    from scipy import ndimage
+    vol = terrain["volume"]
+    for level, tpc, cap in ((2, 2, 8), (4, 8, 15)):
+        r, border = emul.level(level)
+        assert border == cap
+        sz, sy, sx = vol.shape
+        n = [-(-s // tpc) for s in (sz, sy, sx)]
+        pad = np.zeros([-(-s // tpc) * tpc for s in (sz, sy, sx)], np.uint8)
+        pad[:sz, :sy, :sx] = vol
+        occ = pad.reshape(n[0], tpc, n[1], tpc, n[2], tpc).max(axis=(1, 3, 5)) != 0
+        occp = np.pad(occ, cap)
+        dist = ndimage.distance_transform_cdt(~occp, metric="chessboard")
+        want = np.minimum(dist, cap).astype(np.uint8)
+        assert np.array_equal(r, want)

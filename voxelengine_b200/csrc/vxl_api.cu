@@ -2,6 +2,7 @@
 // drop-in of libvxl.so.  No CPU fallback anywhere: every entry point needs a CUDA device.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 
@@ -73,6 +74,7 @@ int vxl_ctx_create(int device, vxl_ctx** out) {
     VXL_CUDA(cudaSetDevice(device));
     vxl_ctx* c = new vxl_ctx();
     c->device = device;
+    if (const char* ev = getenv("VXL_VARIANT")) c->variant = atoi(ev);
     VXL_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
     VXL_CUDA(cudaMalloc(&c->d_stats, STAT_SLOTS * 4 * sizeof(unsigned long long)));
@@ -136,6 +138,22 @@ int vxl_stats_read(vxl_ctx* c, vxl_stats* out) {
     VXL_CUDA(cudaStreamSynchronize(c->stream));
     out->rays = out->steps = out->pixels = 0;
     for (int i = 0; i < STAT_SLOTS; ++i) { out->rays += h[i * 4]; out->steps += h[i * 4 + 1]; out->pixels += h[i * 4 + 2]; }
+    return VXL_OK;
+}
+
+int vxl_debug_set_variant(vxl_ctx* c, int variant) {
+    if (!c || variant < 0 || variant > 1) { set_error("vxl_debug_set_variant: bad argument"); return VXL_ERR_INVALID; }
+    c->variant = variant;
+    return VXL_OK;
+}
+
+int vxl_debug_exact_probes(vxl_ctx* c, uint64_t* out) {
+    if (!c || !out) { set_error("vxl_debug_exact_probes: bad argument"); return VXL_ERR_INVALID; }
+    unsigned long long h[STAT_SLOTS * 4];
+    VXL_CUDA(cudaMemcpyAsync(h, c->d_stats, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    VXL_CUDA(cudaStreamSynchronize(c->stream));
+    *out = 0;
+    for (int i = 0; i < STAT_SLOTS; ++i) *out += h[i * 4 + 3];
     return VXL_OK;
 }
 

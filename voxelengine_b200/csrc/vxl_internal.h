@@ -9,13 +9,24 @@
 
 namespace vxl {
 
+// One clearance map (vxl_occupancy.cu): nibbles, 8 cells per word along x, cell = 2^shift voxels.
+// The array is padded by `border` (= cap) cells on every side so that out-of-volume cells carry their true
+// clearance; array index = cell index + border.  Everything beyond the padded array has clearance >= cap.
+struct ClearLevel {
+    uint32_t* d_words = nullptr;
+    int cx = 0, cy = 0, cz = 0;          // padded array dims, cells
+    int pitch = 0;                       // words per row (>= ceil(cx/8) + 1)
+    int shift = 0;                       // log2(voxels per cell)
+    int cap = 0;                         // largest stored distance == border
+};
+struct ClearView { const uint32_t* __restrict__ words; int cx, cy, cz, pitch, border; };
+
 // Device-side view of the occupancy volume handed to kernels by value.
 struct VolView {
     const uint8_t* __restrict__ bytes;   // canonical packed bytes, x fastest (reference layout)
     int sx, sy, sz;                      // texels
     // derived, acceleration only (never changes a result); see vxl_occupancy.cu
-    const uint32_t* __restrict__ occ8;   // 1 bit per 8x8x8-texel brick ... reserved for the skipper
-    int bx, by, bz;
+    ClearView cm4, cm16;
 };
 
 struct FrameView {
@@ -37,6 +48,7 @@ struct vxl_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     uint64_t launches = 0;
+    int variant = 1;                         // 0: plain per-probe march; 1: clearance-map accelerated (default)
     unsigned long long* d_stats = nullptr;   // [STAT_SLOTS][4]
     float* d_luts = nullptr;                 // cos[256] sin[256]
     void* d_lights = nullptr;                // VXL_MAX_LIGHTS * 64 B
@@ -64,8 +76,8 @@ struct vxl_volume {
     int sx = 0, sy = 0, sz = 0;
     uint8_t* d_bytes = nullptr;
     bool dirty = true;
-    uint32_t* d_occ8 = nullptr;
-    int bx = 0, by = 0, bz = 0;
+    vxl::ClearLevel cm4, cm16;           // clearance maps at 4- and 16-voxel cells
+    uint8_t* d_scratch = nullptr;        // distance-transform ping-pong
 };
 
 namespace vxl {
@@ -86,7 +98,8 @@ int cuda_fail(cudaError_t e, const char* what);
 inline VolView vol_view(const vxl_volume* v) {
     VolView r;
     r.bytes = v->d_bytes; r.sx = v->sx; r.sy = v->sy; r.sz = v->sz;
-    r.occ8 = v->d_occ8; r.bx = v->bx; r.by = v->by; r.bz = v->bz;
+    r.cm4 = ClearView{v->cm4.d_words, v->cm4.cx, v->cm4.cy, v->cm4.cz, v->cm4.pitch, v->cm4.cap};
+    r.cm16 = ClearView{v->cm16.d_words, v->cm16.cx, v->cm16.cy, v->cm16.cz, v->cm16.pitch, v->cm16.cap};
     return r;
 }
 int frame_view(const vxl_frame* f, FrameView* out);

@@ -16,7 +16,9 @@
 
 namespace vxl {
 
-#define VXL_DI __device__ __forceinline__
+// __host__ too: tests/emul compiles the traversal for the host so its logic can be checked
+// without a GPU (test infrastructure; the product only ever runs the device instantiation).
+#define VXL_DI __host__ __device__ __forceinline__
 
 VXL_DI float3 operator+(float3 a, float3 b) { return make_float3(a.x + b.x, a.y + b.y, a.z + b.z); }
 VXL_DI float3 operator-(float3 a, float3 b) { return make_float3(a.x - b.x, a.y - b.y, a.z - b.z); }
@@ -39,7 +41,23 @@ VXL_DI float gsmoothstep(float e0, float e1, float x) {
     float t = gclamp((x - e0) / (e1 - e0), 0.0f, 1.0f);
     return t * t * (3.0f - 2.0f * t);
 }
-VXL_DI int f2i(float x) { return __float2int_rz(x); }
+VXL_DI int f2i(float x) {
+#ifdef __CUDA_ARCH__
+    return __float2int_rz(x);
+#else   // cvt.rzi.s32.f32 semantics on the host
+    if (x != x) return 0;
+    if (x >= 2147483648.0f) return 2147483647;
+    if (x <= -2147483648.0f) return -2147483647 - 1;
+    return (int)x;
+#endif
+}
+template <typename T> VXL_DI T ldg(const T* p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
 
 // column-major mat4 * vec4
 VXL_DI float4 mat_mul(const float* __restrict__ m, float4 v) {

@@ -7,6 +7,7 @@
 #include "vxl_internal.h"
 #include "vxl_math.cuh"
 #include "vxl_trace.cuh"
+#include "vxl_fastmarch.cuh"
 
 namespace vxl {
 
@@ -26,7 +27,7 @@ struct PixelCtx {
 };
 
 // thread -> pixel of the shard.  blockIdx.x enumerates (tile, block-in-tile).
-VXL_DI PixelCtx pixel_ctx(const FrameView& F, const ViewK& K) {
+__device__ __forceinline__ PixelCtx pixel_ctx(const FrameView& F, const ViewK& K) {
     PixelCtx p;
     const int bpt_x = (F.tile_w + BLOCK_W - 1) / BLOCK_W, bpt_y = (F.tile_h + BLOCK_H - 1) / BLOCK_H;
     const int bpt = bpt_x * bpt_y;
@@ -51,7 +52,7 @@ VXL_DI PixelCtx pixel_ctx(const FrameView& F, const ViewK& K) {
 }
 
 // LightAmbient.frag:44-52 getNoise() (s < 0) / getNoise(int s)
-VXL_DI uint32_t get_noise(const FrameView& F, const ViewK& K, const PixelCtx& p, int s) {
+__device__ __forceinline__ uint32_t get_noise(const FrameView& F, const ViewK& K, const PixelCtx& p, int s) {
     float fx, fy;
     if (s < 0) {
         fx = GOLDEN_RATIO * gmod((float)K.Frame, 16.0f);
@@ -66,31 +67,88 @@ VXL_DI uint32_t get_noise(const FrameView& F, const ViewK& K, const PixelCtx& p,
 }
 
 // LightAmbient.frag:81-87 with the cos/sin of theta = 6.283*(k/255) tabulated (host, double, rounded once)
-VXL_DI float3 cosine_sample_hemisphere(const float* __restrict__ lut, uint32_t nx, uint32_t ny) {
-    const float u = unorm8(nx);
-    const float r = sqrtf(u);
+// and r = sqrt(u), z = sqrt(max(0, 1-u)) tabulated per block over the 256 possible u = k/255 (same
+// device sqrtf on the same input as the per-ray evaluation, so the values are identical).
+constexpr int LUT_FLOATS = 1024;   // cos[256] sin[256] r[256] z[256]
+__device__ __forceinline__ float3 cosine_sample_hemisphere(const float* __restrict__ lut, uint32_t nx, uint32_t ny) {
+    const float r = lut[512 + (nx & 0xFFu)];
     const float x = r * lut[ny & 0xFFu];
     const float y = r * lut[256 + (ny & 0xFFu)];
-    return make_float3(x, y, sqrtf(fmaxf(0.0f, 1.0f - u)));
+    return make_float3(x, y, lut[768 + (nx & 0xFFu)]);
 }
 
-VXL_DI void load_luts(float* s_lut, const float* __restrict__ g_lut) {
+// (no barrier: the caller's block prologue synchronises before the first use)
+__device__ __forceinline__ void load_luts(float* s_lut, const float* __restrict__ g_lut) {
     for (int i = threadIdx.x; i < 512; i += blockDim.x) s_lut[i] = g_lut[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        const float u = unorm8((uint32_t)i);
+        s_lut[512 + i] = sqrtf(u);
+        s_lut[768 + i] = sqrtf(fmaxf(0.0f, 1.0f - u));
+    }
+}
+
+// Shared-memory state of the accelerated march for one thread block.
+struct BlockShared {
+    uint32_t t4[CT_WORDS];
+    uint32_t t16[CT_WORDS];
+    float lut[LUT_FLOATS];
+    int bb[6];
+    unsigned acc[4];
+};
+
+// Bounding box of the block's ray origins -> tile placement -> stage both clearance tiles.
+// `hint` is (close to) the thread's ray origin in voxel units; threads without rays pass valid = false.
+// Ends with a block barrier (which also publishes the LUTs).
+template <bool FAST>
+__device__ __forceinline__ FastCtx block_prologue(const VolView& V, BlockShared& S, bool valid, float3 hint) {
+    FastCtx C;
+    C.t4.w = S.t4; C.t16.w = S.t16;
+    C.t4.ox = C.t4.oy = C.t4.oz = 0; C.t16.ox = C.t16.oy = C.t16.oz = 0;
+    C.enabled = false;
+    if (threadIdx.x < 3) { S.bb[threadIdx.x] = 0x7fffffff; S.bb[3 + threadIdx.x] = -0x7fffffff - 1; }
+    if (threadIdx.x < 4) S.acc[threadIdx.x] = 0u;
     __syncthreads();
+    if (!FAST) return C;
+    const int big = 1 << 24;
+    int ix = valid ? max(-big, min(big, f2i(hint.x))) : 0x7fffffff, iy = valid ? max(-big, min(big, f2i(hint.y))) : 0x7fffffff,
+        iz = valid ? max(-big, min(big, f2i(hint.z))) : 0x7fffffff;
+    const int mnx = __reduce_min_sync(0xFFFFFFFFu, ix), mny = __reduce_min_sync(0xFFFFFFFFu, iy), mnz = __reduce_min_sync(0xFFFFFFFFu, iz);
+    if (!valid) { ix = iy = iz = -0x7fffffff - 1; }
+    const int mxx = __reduce_max_sync(0xFFFFFFFFu, ix), mxy = __reduce_max_sync(0xFFFFFFFFu, iy), mxz = __reduce_max_sync(0xFFFFFFFFu, iz);
+    if ((threadIdx.x & 31) == 0 && mnx != 0x7fffffff) {
+        atomicMin(&S.bb[0], mnx); atomicMin(&S.bb[1], mny); atomicMin(&S.bb[2], mnz);
+        atomicMax(&S.bb[3], mxx); atomicMax(&S.bb[4], mxy); atomicMax(&S.bb[5], mxz);
+    }
+    __syncthreads();
+    if (S.bb[0] == 0x7fffffff) return C;                    // no ray in this block (uniform)
+    const int cx = (S.bb[0] + S.bb[3]) >> 1, cy = (S.bb[1] + S.bb[4]) >> 1, cz = (S.bb[2] + S.bb[5]) >> 1;
+    C.t4.ox = (cx >> 2) - CT / 2; C.t4.oy = (cy >> 2) - CT / 2; C.t4.oz = (cz >> 2) - CT / 2;
+    C.t16.ox = (cx >> 4) - CT / 2; C.t16.oy = (cy >> 4) - CT / 2; C.t16.oz = (cz >> 4) - CT / 2;
+    stage_tile(S.t4, V.cm4, C.t4.ox, C.t4.oy, C.t4.oz);
+    stage_tile(S.t16, V.cm16, C.t16.ox, C.t16.oy, C.t16.oz);
+    __syncthreads();
+    C.enabled = true;
+    return C;
+}
+
+template <bool FAST, bool SUPER>
+__device__ __forceinline__ float ray_march(const VolView& V, const FastCtx& C, float3 origin, float3 dir, float dist, int& steps, unsigned& exact) {
+    if (FAST) return march_fast<SUPER, false>(V, C, origin, dir, dist, steps, nullptr, exact);
+    return march<false>(V, origin, dir, dist, SUPER ? 2.5f : 0.5f, steps, nullptr);
 }
 
 // block-level accumulation of (rays, steps, pixels) into striped global counters
-VXL_DI void flush_stats(unsigned long long* __restrict__ g_stats, unsigned rays, unsigned steps, unsigned pixels) {
-    __shared__ unsigned s_acc[3];
-    if (threadIdx.x < 3) s_acc[threadIdx.x] = 0u;
-    __syncthreads();
+// (slot 3: probes executed exactly by the accelerated march -- diagnostics).  S.acc is zeroed by block_prologue.
+__device__ __forceinline__ void flush_stats(BlockShared& S, unsigned long long* __restrict__ g_stats, unsigned rays, unsigned steps,
+                                            unsigned pixels, unsigned exact) {
     rays = __reduce_add_sync(0xFFFFFFFFu, rays);
     steps = __reduce_add_sync(0xFFFFFFFFu, steps);
     pixels = __reduce_add_sync(0xFFFFFFFFu, pixels);
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_acc[0], rays); atomicAdd(&s_acc[1], steps); atomicAdd(&s_acc[2], pixels); }
+    exact = __reduce_add_sync(0xFFFFFFFFu, exact);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&S.acc[0], rays); atomicAdd(&S.acc[1], steps); atomicAdd(&S.acc[2], pixels); atomicAdd(&S.acc[3], exact); }
     __syncthreads();
-    if (threadIdx.x < 3) {
-        unsigned v = s_acc[threadIdx.x];
+    if (threadIdx.x < 4) {
+        unsigned v = S.acc[threadIdx.x];
         if (v) atomicAdd(&g_stats[(blockIdx.x & (STAT_SLOTS - 1)) * 4 + threadIdx.x], (unsigned long long)v);
     }
 }
@@ -98,33 +156,45 @@ VXL_DI void flush_stats(unsigned long long* __restrict__ g_stats, unsigned rays,
 // -------------------------------------------------------------------------------------------------
 // LightAmbient.frag:134-175 + calculateAmbientIrradiance :111-126
 // -------------------------------------------------------------------------------------------------
+template <bool FAST>
 __global__ void __launch_bounds__(256) k_ambient(VolView V, FrameView F, ViewK K, const float* __restrict__ g_lut, int n_ao,
                                                  float* __restrict__ out_shadow, float* __restrict__ out_ao,
                                                  unsigned long long* __restrict__ g_stats) {
-    __shared__ float s_lut[512];
-    load_luts(s_lut, g_lut);
+    __shared__ BlockShared S;
+    load_luts(S.lut, g_lut);
     const PixelCtx p = pixel_ctx(F, K);
-    unsigned rays = 0, pixels = 0;
+    float depth = 1.0f;
+    float3 normal = make_float3(0.f, 0.f, 0.f), wcp0 = make_float3(0.f, 0.f, 0.f);
+    float bias = 0.0f;
+    bool lit = false;
+    if (p.valid) {
+        depth = unorm24(__ldg(F.depth24 + p.idx));
+        if (depth < 0.999f) {                                                         // :138
+            lit = true;
+            const float3 pos = p.farvec * (depth * (1.0f + 1.0f / FAR_));              // :141
+            normal = decode_normal(__ldg(F.normal + p.idx));                           // :142
+            wcp0 = xyz(mat_mul(K.InvView, make_float4(pos.x, pos.y, pos.z, 1.0f))) * 10.0f;   // :150
+            bias = gsmoothstep(0.0f, 0.2f, depth) * 50.0f + 1.5f;                      // :158
+        }
+    }
+    const FastCtx C = block_prologue<FAST>(V, S, lit, wcp0 + normal * bias);
+    unsigned rays = 0, pixels = 0, exact = 0;
     int steps = 0;
     if (p.valid) {
-        const float depth = unorm24(__ldg(F.depth24 + p.idx));
         float shadow = 1.0f, ao = 0.0f;
-        if (depth < 0.999f) {                                                     // :138
-            const float3 pos = p.farvec * (depth * (1.0f + 1.0f / FAR_));          // :141
-            const float3 normal = decode_normal(__ldg(F.normal + p.idx));          // :142
-            float3 wd = normalize3(make_float3(0.3f, 0.4f, 0.5f));                 // SUN_DIR :15,:149
-            float3 wcp = xyz(mat_mul(K.InvView, make_float4(pos.x, pos.y, pos.z, 1.0f))) * 10.0f;  // :150
+        if (lit) {
+            float3 wd = normalize3(make_float3(0.3f, 0.4f, 0.5f));                     // SUN_DIR :15,:149
+            float3 wcp = wcp0;
             const uint32_t n = get_noise(F, K, p, -1);
-            float3 randomVec = cosine_sample_hemisphere(s_lut, n, n >> 8) * 0.1f;  // :151
-            randomVec.z *= gsign(unorm8(n >> 16) - 0.5f);                         // :152
-            wd = mix3(wd, randomVec, 0.5f);                                        // :153
-            wd = normalize3(wd);                                                   // :154
-            wcp = wcp + wd * (unorm8(n >> 24) * 1.0f);                             // :155
-            wcp = wcp + randomVec * 2.5f;                                          // :156
-            const float bias = gsmoothstep(0.0f, 0.2f, depth) * 50.0f + 1.5f;      // :158
+            float3 randomVec = cosine_sample_hemisphere(S.lut, n, n >> 8) * 0.1f;      // :151
+            randomVec.z *= gsign(unorm8(n >> 16) - 0.5f);                             // :152
+            wd = mix3(wd, randomVec, 0.5f);                                            // :153
+            wd = normalize3(wd);                                                       // :154
+            wcp = wcp + wd * (unorm8(n >> 24) * 1.0f);                                 // :155
+            wcp = wcp + randomVec * 2.5f;                                              // :156
             const float3 origin = wcp + normal * bias;
             if (out_shadow) {
-                if (march<false>(V, origin, wd, 128.0f, 0.5f, steps, nullptr) != 128.0f) shadow = 0.0f;   // :167-169
+                if (ray_march<FAST, false>(V, C, origin, wd, 128.0f, steps, exact) != 128.0f) shadow = 0.0f;   // :167-169
                 rays += 1;
             }
             if (out_ao && n_ao > 0) {
@@ -134,9 +204,9 @@ __global__ void __launch_bounds__(256) k_ambient(VolView V, FrameView F, ViewK K
                 float acc = 0.0f;
                 for (int i = 0; i < n_ao; ++i) {
                     const uint32_t ni = (i == 0) ? n : get_noise(F, K, p, i);
-                    const float3 rv = cosine_sample_hemisphere(s_lut, ni, ni >> 8);                       // :118
+                    const float3 rv = cosine_sample_hemisphere(S.lut, ni, ni >> 8);                       // :118
                     const float3 dir = tangent * rv.x + bitangent * rv.y + normal * rv.z;                 // :119
-                    const float d = march<false>(V, origin, dir, 128.0f, 2.5f, steps, nullptr) / 128.0f;  // :121
+                    const float d = ray_march<FAST, true>(V, C, origin, dir, 128.0f, steps, exact) / 128.0f;   // :121
                     acc += d * d;
                 }
                 ao = (acc / (float)n_ao) * 0.05f;                                                         // :125
@@ -147,34 +217,39 @@ __global__ void __launch_bounds__(256) k_ambient(VolView V, FrameView F, ViewK K
         if (out_shadow) out_shadow[p.idx] = shadow;
         if (out_ao) out_ao[p.idx] = ao;
     }
-    flush_stats(g_stats, rays, (unsigned)steps, pixels);
+    flush_stats(S, g_stats, rays, (unsigned)steps, pixels, exact);
 }
 
 // -------------------------------------------------------------------------------------------------
 // LightPoint.frag:85-129 / LightSpot.frag:73-117 -- all lights of the list in one launch; the
 // G-buffer, noise and world position are read / derived once per pixel instead of once per light.
 // -------------------------------------------------------------------------------------------------
-template <bool SPOT>
+template <bool SPOT, bool FAST>
 __global__ void __launch_bounds__(256) k_local_lights(VolView V, FrameView F, ViewK K, const float* __restrict__ g_lut,
                                                       const float* __restrict__ lights, int n_lights,
                                                       float* __restrict__ out_shadow, size_t plane_stride,
                                                       unsigned long long* __restrict__ g_stats) {
-    __shared__ float s_lut[512];
+    __shared__ BlockShared S;
     __shared__ float s_light[VXL_MAX_LIGHTS * 4];   // position.xyz, range
-    load_luts(s_lut, g_lut);
+    load_luts(S.lut, g_lut);
     constexpr int STRIDE = SPOT ? 16 : 8;
     for (int i = threadIdx.x; i < n_lights * 4; i += blockDim.x) s_light[i] = lights[(i >> 2) * STRIDE + (i & 3)];
-    __syncthreads();
     const PixelCtx p = pixel_ctx(F, K);
-    unsigned rays = 0, pixels = 0;
-    int steps = 0;
+    float3 normal = make_float3(0.f, 0.f, 0.f), worldPos = make_float3(0.f, 0.f, 0.f);
+    bool hint_ok = false;   // sky pixels are shaded like any other (no depth test here) but must not stretch the tile placement
     if (p.valid) {
         const float depth = unorm24(__ldg(F.depth24 + p.idx));
+        hint_ok = depth < 0.999f;
         const float3 pos = p.farvec * (depth * (1.0f + 1.0f / FAR_));                        // LightPoint.frag:89
-        const float3 normal = decode_normal(__ldg(F.normal + p.idx));                        // :90
-        const float3 worldPos = xyz(mat_mul(K.InvView, make_float4(pos.x, pos.y, pos.z, 1.0f)));   // :95
+        normal = decode_normal(__ldg(F.normal + p.idx));                                     // :90
+        worldPos = xyz(mat_mul(K.InvView, make_float4(pos.x, pos.y, pos.z, 1.0f)));          // :95
+    }
+    const FastCtx C = block_prologue<FAST>(V, S, hint_ok, worldPos * 10.0f);
+    unsigned rays = 0, pixels = 0, exact = 0;
+    int steps = 0;
+    if (p.valid) {
         const uint32_t n = get_noise(F, K, p, -1);
-        float3 rv0 = cosine_sample_hemisphere(s_lut, n, n >> 8) * 0.1f;                      // :111
+        float3 rv0 = cosine_sample_hemisphere(S.lut, n, n >> 8) * 0.1f;                      // :111
         rv0.z *= gsign(unorm8(n >> 16) - 0.5f);                                             // :112
         const float nw = unorm8(n >> 24) * 1.0f;
         for (int li = 0; li < n_lights; ++li) {
@@ -184,60 +259,71 @@ __global__ void __launch_bounds__(256) k_local_lights(VolView V, FrameView F, Vi
             const float lightDistance = length3(lightDir);                                   // :98
             float shadow = 1.0f;
             if (!(lightDistance > range)) {                                                  // :100-103
-                float3 wd; float hitDist; float step0;
-                if (!SPOT) { wd = lightDir; hitDist = lightDistance * 10.5f; step0 = 0.5f; }                 // :108-109
-                else { wd = normalize3(lightDir) * 10.0f; hitDist = lightDistance * 10.0f; step0 = 2.5f; }   // LightSpot.frag:96-97
+                float3 wd; float hitDist;
+                if (!SPOT) { wd = lightDir; hitDist = lightDistance * 10.5f; }               // :108-109
+                else { wd = normalize3(lightDir) * 10.0f; hitDist = lightDistance * 10.0f; } // LightSpot.frag:96-97
                 float3 wcp = worldPos * 10.0f;                                               // :110
                 wd = mix3(wd, rv0, 0.5f);                                                    // :113
                 wd = normalize3(wd);                                                         // :114
                 wcp = wcp + wd * nw;                                                         // :115
                 wcp = wcp + rv0 * 2.5f;                                                      // :116
-                if (march<false>(V, wcp + normal * 0.5f, wd, hitDist, step0, steps, nullptr) < hitDist) shadow = 0.0f;   // :125
+                if (ray_march<FAST, SPOT>(V, C, wcp + normal * 0.5f, wd, hitDist, steps, exact) < hitDist) shadow = 0.0f;   // :125
                 rays += 1;
                 pixels = 1;
             }
             out_shadow[(size_t)li * plane_stride + p.idx] = shadow;
         }
     }
-    flush_stats(g_stats, rays, (unsigned)steps, pixels);
+    flush_stats(S, g_stats, rays, (unsigned)steps, pixels, exact);
 }
 
 // -------------------------------------------------------------------------------------------------
 // LightReflection.frag:60-113
 // -------------------------------------------------------------------------------------------------
+template <bool FAST>
 __global__ void __launch_bounds__(256) k_reflection(VolView V, FrameView F, ViewK K, const float* __restrict__ g_lut,
                                                     float* __restrict__ out_t, unsigned long long* __restrict__ g_stats) {
-    __shared__ float s_lut[512];
-    load_luts(s_lut, g_lut);
+    __shared__ BlockShared S;
+    load_luts(S.lut, g_lut);
     const PixelCtx p = pixel_ctx(F, K);
-    unsigned rays = 0, pixels = 0;
+    float depth = 1.0f;
+    float3 pos = make_float3(0.f, 0.f, 0.f), normal = make_float3(0.f, 0.f, 0.f), wcp0 = make_float3(0.f, 0.f, 0.f);
+    bool lit = false;
+    if (p.valid) {
+        depth = unorm24(__ldg(F.depth24 + p.idx));
+        if (depth < 0.999f) {                                                               // :88
+            lit = true;
+            pos = p.farvec * (depth * (1.0f + 1.0f / FAR_));                                 // :64
+            normal = decode_normal(__ldg(F.normal + p.idx));                                 // :65
+            wcp0 = xyz(mat_mul(K.InvView, make_float4(pos.x, pos.y, pos.z, 1.0f))) * 10.0f;  // :93
+        }
+    }
+    const FastCtx C = block_prologue<FAST>(V, S, lit, wcp0 + normal);
+    unsigned rays = 0, pixels = 0, exact = 0;
     int steps = 0;
     if (p.valid) {
-        const float depth = unorm24(__ldg(F.depth24 + p.idx));
         float t = 256.0f;
-        if (depth < 0.999f) {                                                               // :88
-            const float3 pos = p.farvec * (depth * (1.0f + 1.0f / FAR_));                    // :64
-            const float3 normal = decode_normal(__ldg(F.normal + p.idx));                    // :65
+        if (lit) {
             const float roughness = unorm8(__ldg(F.material + p.idx));                       // :68
             const float3 Vv = normalize3(pos) * -1.0f;                                       // :79
             const float3 N = xyz(mat_mul(K.View, make_float4(normal.x, normal.y, normal.z, 0.0f)));   // :80
             const float3 I = Vv * -1.0f;
             const float3 R = I - N * dot3(N, I) * 2.0f;                                      // :81
             float3 wd = normalize3(xyz(mat_mul(K.InvView, make_float4(R.x, R.y, R.z, 0.0f))));        // :92
-            float3 wcp = xyz(mat_mul(K.InvView, make_float4(pos.x, pos.y, pos.z, 1.0f))) * 10.0f;     // :93
+            float3 wcp = wcp0;
             const uint32_t n = get_noise(F, K, p, -1);
-            float3 rv = cosine_sample_hemisphere(s_lut, n, n >> 8);                          // :94
+            float3 rv = cosine_sample_hemisphere(S.lut, n, n >> 8);                          // :94
             rv.z *= gsign(unorm8(n >> 16) - 0.5f);                                          // :95
             wd = mix3(wd, rv, roughness * 0.1f);                                             // :96
             const float nw = unorm8(n >> 24);
             wcp = wcp + normal * nw;                                                         // :97
             wd = wd * (1.0f + nw * 0.5f);                                                    // :98
-            t = march<false>(V, wcp + normal, wd, 256.0f, 0.5f, steps, nullptr);             // :113
+            t = ray_march<FAST, false>(V, C, wcp + normal, wd, 256.0f, steps, exact);        // :113
             rays = 1; pixels = 1;
         }
         out_t[p.idx] = t;
     }
-    flush_stats(g_stats, rays, (unsigned)steps, pixels);
+    flush_stats(S, g_stats, rays, (unsigned)steps, pixels, exact);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -292,7 +378,10 @@ int vxl_pass_ambient(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, const 
     if (!out_shadow && !out_ao) return VXL_OK;
     if (F.n_tiles == 0) return VXL_OK;
     if (vol->dirty) { if (int e = vxl_volume_build_occupancy(vol)) return e; }
-    k_ambient<<<grid_for(F), 256, 0, ctx->stream>>>(vol_view(vol), F, make_viewk(view), ctx->d_luts, n_ao, out_shadow, out_ao, ctx->d_stats);
+    if (ctx->variant == 0)
+        k_ambient<false><<<grid_for(F), 256, 0, ctx->stream>>>(vol_view(vol), F, make_viewk(view), ctx->d_luts, n_ao, out_shadow, out_ao, ctx->d_stats);
+    else
+        k_ambient<true><<<grid_for(F), 256, 0, ctx->stream>>>(vol_view(vol), F, make_viewk(view), ctx->d_luts, n_ao, out_shadow, out_ao, ctx->d_stats);
     VXL_LAUNCH_CHECK(ctx);
     return VXL_OK;
 }
@@ -310,10 +399,10 @@ static int local_lights(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, con
     if (vol->dirty) { if (int e = vxl_volume_build_occupancy(vol)) return e; }
     VXL_CUDA(cudaMemcpyAsync(ctx->d_lights, lights, (size_t)n_lights * light_bytes, cudaMemcpyHostToDevice, ctx->stream));
     const size_t plane = frame_pixels(frame);
-    if (spot)
-        k_local_lights<true><<<grid_for(F), 256, 0, ctx->stream>>>(vol_view(vol), F, make_viewk(view), ctx->d_luts, (const float*)ctx->d_lights, n_lights, out_shadow, plane, ctx->d_stats);
-    else
-        k_local_lights<false><<<grid_for(F), 256, 0, ctx->stream>>>(vol_view(vol), F, make_viewk(view), ctx->d_luts, (const float*)ctx->d_lights, n_lights, out_shadow, plane, ctx->d_stats);
+#define VXL_LL(SPOT_, FAST_) k_local_lights<SPOT_, FAST_><<<grid_for(F), 256, 0, ctx->stream>>>(vol_view(vol), F, make_viewk(view), ctx->d_luts, (const float*)ctx->d_lights, n_lights, out_shadow, plane, ctx->d_stats)
+    if (spot) { if (ctx->variant == 0) VXL_LL(true, false); else VXL_LL(true, true); }
+    else { if (ctx->variant == 0) VXL_LL(false, false); else VXL_LL(false, true); }
+#undef VXL_LL
     VXL_LAUNCH_CHECK(ctx);
     return VXL_OK;
 }
@@ -336,7 +425,10 @@ int vxl_pass_reflection(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, con
     if (!F.material) { set_error("vxl_pass_reflection: frame.material is NULL"); return VXL_ERR_INVALID; }
     if (F.n_tiles == 0) return VXL_OK;
     if (vol->dirty) { if (int e = vxl_volume_build_occupancy(vol)) return e; }
-    k_reflection<<<grid_for(F), 256, 0, ctx->stream>>>(vol_view(vol), F, make_viewk(view), ctx->d_luts, out_spec_t, ctx->d_stats);
+    if (ctx->variant == 0)
+        k_reflection<false><<<grid_for(F), 256, 0, ctx->stream>>>(vol_view(vol), F, make_viewk(view), ctx->d_luts, out_spec_t, ctx->d_stats);
+    else
+        k_reflection<true><<<grid_for(F), 256, 0, ctx->stream>>>(vol_view(vol), F, make_viewk(view), ctx->d_luts, out_spec_t, ctx->d_stats);
     VXL_LAUNCH_CHECK(ctx);
     return VXL_OK;
 }

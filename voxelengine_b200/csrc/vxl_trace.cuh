@@ -17,7 +17,7 @@ namespace vxl {
 VXL_DI unsigned fetch_texel(const VolView& V, int x, int y, int z) {
     if ((unsigned)x >= (unsigned)V.sx || (unsigned)y >= (unsigned)V.sy || (unsigned)z >= (unsigned)V.sz) return 0u;
     size_t off = (size_t)x + (size_t)y * (size_t)V.sx + (size_t)z * ((size_t)V.sx * (size_t)V.sy);
-    return (unsigned)__ldg(V.bytes + off);
+    return (unsigned)ldg(V.bytes + off);
 }
 
 // Light.frag:14-27

@@ -322,7 +322,7 @@ int vxl_volume_create(vxl_ctx* ctx, int sx, int sy, int sz, vxl_volume** out) {
 int vxl_volume_destroy(vxl_volume* v) {
     if (!v) return VXL_OK;
     cudaStreamSynchronize(v->ctx->stream);
-    cudaFree(v->d_bytes); cudaFree(v->d_occ8);
+    cudaFree(v->d_bytes); cudaFree(v->cm4.d_words); cudaFree(v->cm16.d_words); cudaFree(v->d_scratch);
     delete v;
     return VXL_OK;
 }
@@ -386,13 +386,6 @@ int vxl_volume_device_ptr(vxl_volume* v, uint8_t** out) {
 int vxl_volume_mark_dirty(vxl_volume* v) {
     if (!v) { set_error("vxl_volume_mark_dirty: vol is NULL"); return VXL_ERR_INVALID; }
     v->dirty = true;
-    return VXL_OK;
-}
-
-int vxl_volume_build_occupancy(vxl_volume* v) {
-    if (!v) { set_error("vxl_volume_build_occupancy: vol is NULL"); return VXL_ERR_INVALID; }
-    // Round 1: the passes march the canonical bytes directly; no derived level is consumed yet.
-    v->dirty = false;
     return VXL_OK;
 }
 

@@ -65,6 +65,15 @@ class Context:
         check(self.lib.vxl_stats_read(self.h, C.byref(s)), "vxl_stats_read")
         return dict(rays=int(s.rays), steps=int(s.steps), pixels=int(s.pixels))
 
+    def set_variant(self, variant: int):
+        """Diagnostics: 0 = plain per-probe march, 1 = clearance-map accelerated march (default). Same results."""
+        check(self.lib.vxl_debug_set_variant(self.h, int(variant)), "vxl_debug_set_variant")
+
+    def exact_probes(self) -> int:
+        n = C.c_uint64()
+        check(self.lib.vxl_debug_exact_probes(self.h, C.byref(n)), "vxl_debug_exact_probes")
+        return int(n.value)
+
     def launch_count(self) -> int:
         n = C.c_uint64()
         check(self.lib.vxl_launch_count(self.h, C.byref(n)), "vxl_launch_count")
@@ -146,6 +155,14 @@ class ShadowVoxSystem:
 
     def build_occupancy(self):
         check(self.lib.vxl_volume_build_occupancy(self.h), "vxl_volume_build_occupancy")
+
+    def clearance(self, level: int):
+        """Diagnostics: (clearance map of `level` incl. border as uint8 [cz][cy][cx], border)."""
+        dims = np.zeros(4, np.int32)
+        check(self.lib.vxl_volume_debug_clearance(self.h, int(level), None, _np_ptr(dims)), "vxl_volume_debug_clearance")
+        out = np.zeros((dims[2], dims[1], dims[0]), np.uint8)
+        check(self.lib.vxl_volume_debug_clearance(self.h, int(level), _np_ptr(out), _np_ptr(dims)), "vxl_volume_debug_clearance")
+        return out, int(dims[3])
 
     def trace_rays(self, rays: np.ndarray, variant: int) -> np.ndarray:
         """Ray-level entry: host rays in, host hit records out (copies through device buffers)."""
