@@ -145,15 +145,15 @@ int vxl_stats_read(vxl_ctx* ctx, vxl_stats* out /* HOST */);
 /* number of kernels this library launched on the context since creation (bench gpu_launches) */
 int vxl_launch_count(vxl_ctx* ctx, uint64_t* out /* HOST */);
 
-/* diagnostics (no reference counterpart): kernel variant 0 = plain per-probe march, 1 = clearance-map
- * accelerated march (default; also env VXL_VARIANT); both produce identical results.
- * vxl_debug_exact_probes: probes the accelerated march had to execute exactly since the last
- * vxl_stats_reset (the rest were proven empty from the clearance maps). */
+/* diagnostics (no reference counterpart): kernel variant 0 = plain march on the volume bytes, 1 = march
+ * against the per-block occupancy-bit tile in shared memory (default; also env VXL_VARIANT); both
+ * produce identical results.  vxl_debug_fetched_probes: probes of variant 1 that had to read the volume
+ * since the last vxl_stats_reset (the others were answered by a clear occupancy bit). */
 int vxl_debug_set_variant(vxl_ctx* ctx, int variant);
-int vxl_debug_exact_probes(vxl_ctx* ctx, uint64_t* out /* HOST */);
-/* download one clearance map (level 2: 4-voxel cells, level 4: 16-voxel cells) unpacked to bytes
- * [cz][cy][cx] including its border; out_dims = {cx, cy, cz, border}; host_out may be NULL */
-int vxl_volume_debug_clearance(vxl_volume* vol, int level, uint8_t* host_out /* HOST */, int* out_dims /* HOST[4] */);
+int vxl_debug_fetched_probes(vxl_ctx* ctx, uint64_t* out /* HOST */);
+/* download one occupancy level (shift 2: 4-voxel cells, 3: 8-voxel cells) unpacked to 0/1 bytes
+ * [cz][cy][cx]; out_dims = {cx, cy, cz}; host_out may be NULL */
+int vxl_volume_debug_occupancy(vxl_volume* vol, int shift, uint8_t* host_out /* HOST */, int* out_dims /* HOST[3] */);
 
 /* raw memory helpers so a C caller needs no CUDA headers */
 int vxl_malloc(vxl_ctx* ctx, size_t bytes, void** out_dev);

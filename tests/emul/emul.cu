@@ -1,82 +1,89 @@
 // tests/emul/emul.cu -- TEST INFRASTRUCTURE: host instantiation of the device traversal code.
 //
-// The accelerated march (voxelengine_b200/csrc/vxl_fastmarch.cuh) is __host__ __device__; this file
-// compiles it for the host (nvcc, no GPU needed) so that its logic -- clearance lookups, skip
-// counts, exact replay, eligibility -- can be checked bit-for-bit against the CPU oracle in the
-// `-m "not gpu"` suite.  The clearance maps and tiles are rebuilt here by an independent brute-force
-// method (iterated 3x3x3 dilation), not by the product's kernels.  Nothing in the product loads this.
+// The tile march (voxelengine_b200/csrc/vxl_bitmarch.cuh) is __host__ __device__; this file compiles
+// it for the host (nvcc, no GPU needed) so that its logic -- eligibility, folded tile addressing,
+// scan loops, fall-through to the reference test -- can be checked bit-for-bit against the CPU
+// oracle in the `-m "not gpu"` suite.  The occupancy levels and tiles are rebuilt here by an
+// independent straightforward method, not by the product's kernels.  Nothing in the product loads this.
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <vector>
 
-#include "../../voxelengine_b200/csrc/vxl_fastmarch.cuh"
+#include "../../voxelengine_b200/csrc/vxl_bitmarch.cuh"
 
 using namespace vxl;
 
 namespace {
 
-struct HostLevel {
-    int shift, cap, border;
-    int cx, cy, cz;              // padded dims
-    std::vector<uint8_t> r;      // clearance per padded cell
+struct HostOcc {
+    int shift = 0, cx = 0, cy = 0, cz = 0;
+    std::vector<uint8_t> occ;    // 0/1 per cell
+    bool at(int x, int y, int z) const {
+        if (x < 0 || y < 0 || z < 0 || x >= cx || y >= cy || z >= cz) return false;
+        return occ[(size_t)x + (size_t)y * cx + (size_t)z * cx * cy] != 0;
+    }
 };
 
-// brute force: base occupancy then `cap` rounds of 3x3x3 dilation
-HostLevel build_level(const uint8_t* vol, int sx, int sy, int sz, int shift, int cap) {
-    HostLevel L;
-    L.shift = shift; L.cap = cap; L.border = cap;
+HostOcc build_occ(const uint8_t* vol, int sx, int sy, int sz, int shift) {
+    HostOcc L;
+    L.shift = shift;
     const int tpc = 1 << (shift - 1);                        // texels per cell edge
-    const int nx = (sx + tpc - 1) / tpc, ny = (sy + tpc - 1) / tpc, nz = (sz + tpc - 1) / tpc;
-    L.cx = nx + 2 * cap; L.cy = ny + 2 * cap; L.cz = nz + 2 * cap;
-    const size_t n = (size_t)L.cx * L.cy * L.cz;
-    std::vector<uint8_t> occ(n, 0);
+    L.cx = (sx + tpc - 1) / tpc; L.cy = (sy + tpc - 1) / tpc; L.cz = (sz + tpc - 1) / tpc;
+    L.occ.assign((size_t)L.cx * L.cy * L.cz, 0);
     for (int z = 0; z < sz; ++z)
         for (int y = 0; y < sy; ++y)
             for (int x = 0; x < sx; ++x)
                 if (vol[(size_t)x + (size_t)y * sx + (size_t)z * sx * sy])
-                    occ[(size_t)(x / tpc + cap) + (size_t)(y / tpc + cap) * L.cx + (size_t)(z / tpc + cap) * L.cx * L.cy] = 1;
-    L.r.assign(n, (uint8_t)cap);
-    std::vector<uint8_t> cur = occ, nxt(n);
-    for (size_t i = 0; i < n; ++i) if (occ[i]) L.r[i] = 0;
-    for (int round = 1; round < cap; ++round) {
-        for (int z = 0; z < L.cz; ++z)
-            for (int y = 0; y < L.cy; ++y)
-                for (int x = 0; x < L.cx; ++x) {
-                    uint8_t v = 0;
-                    for (int dz = -1; dz <= 1 && !v; ++dz)
-                        for (int dy = -1; dy <= 1 && !v; ++dy)
-                            for (int dx = -1; dx <= 1; ++dx) {
-                                const int ax = x + dx, ay = y + dy, az = z + dz;
-                                if (ax < 0 || ay < 0 || az < 0 || ax >= L.cx || ay >= L.cy || az >= L.cz) continue;
-                                if (cur[(size_t)ax + (size_t)ay * L.cx + (size_t)az * L.cx * L.cy]) { v = 1; break; }
-                            }
-                    nxt[(size_t)x + (size_t)y * L.cx + (size_t)z * L.cx * L.cy] = v;
-                }
-        for (size_t i = 0; i < n; ++i) if (nxt[i] && !cur[i]) L.r[i] = (uint8_t)round;
-        cur.swap(nxt);
-    }
+                    L.occ[(size_t)(x / tpc) + (size_t)(y / tpc) * L.cx + (size_t)(z / tpc) * L.cx * L.cy] = 1;
     return L;
 }
 
-void build_tile(const HostLevel& L, int ox, int oy, int oz, std::vector<uint32_t>& w) {
-    w.assign(CT_WORDS, 0);
-    const int fill = std::min(15, L.border + 1);
-    for (int z = 0; z < CT; ++z)
-        for (int y = 0; y < CT; ++y)
-            for (int x = 0; x < CT; ++x) {
-                const int ax = ox + x + L.border, ay = oy + y + L.border, az = oz + z + L.border;
-                int r = fill;
-                if (ax >= 0 && ay >= 0 && az >= 0 && ax < L.cx && ay < L.cy && az < L.cz) r = L.r[(size_t)ax + (size_t)ay * L.cx + (size_t)az * L.cx * L.cy];
-                w[(z * CT + y) * CTW + (x >> 3)] |= (uint32_t)r << (4 * (x & 7));
-            }
+template <int TY, int TW>
+void build_tile(const HostOcc& L, int ox, int oy, int oz, std::vector<uint32_t>& w) {
+    w.assign((size_t)TY * TY * TW, 0);
+    for (int z = 0; z < TY; ++z)
+        for (int y = 0; y < TY; ++y)
+            for (int x = 0; x < TW * 32; ++x)
+                if (L.at(ox + x, oy + y, oz + z)) w[(size_t)(z * TY + y) * TW + (x >> 5)] |= 1u << (x & 31);
 }
 
 struct Emul {
     std::vector<uint8_t> vol;
     int sx, sy, sz;
-    HostLevel l2, l4;
+    HostOcc lv[5];               // index = shift (1..4)
 };
+
+template <int SHIFT, int TY, int TW>
+void trace_geom(Emul* e, const float* rays, long long n, int variant, const int* center, int fast, vxl_hit* out,
+                unsigned long long* counters) {
+    VolView V;
+    V.bytes = e->vol.data(); V.sx = e->sx; V.sy = e->sy; V.sz = e->sz;
+    std::vector<uint32_t> w;
+    BitTile T;
+    // same placement as block_prologue (vxl_passes.cu)
+    T.ox = (center[0] >> SHIFT) - TW * 16; T.oy = (center[1] >> SHIFT) - TY / 2; T.oz = (center[2] >> SHIFT) - TY / 2;
+    build_tile<TY, TW>(e->lv[SHIFT], T.ox, T.oy, T.oz, w);
+    T.w = w.data();
+    T.enabled = fast != 0;
+    unsigned long long fetched_total = 0, steps_total = 0;
+    for (long long i = 0; i < n; ++i) {
+        const float* r = rays + i * 8;
+        MarchResult M;
+        int steps = 0;
+        unsigned fetched = 0;
+        const float3 o = make_float3(r[0], r[1], r[2]), d = make_float3(r[3], r[4], r[5]);
+        if (variant == 0) march_bits<false, true, SHIFT, TY, TW>(V, T, o, d, r[6], steps, &M, fetched);
+        else march_bits<true, true, SHIFT, TY, TW>(V, T, o, d, r[6], steps, &M, fetched);
+        vxl_hit hh;
+        memset(&hh, 0, sizeof hh);
+        hh.t = M.d; hh.steps = M.steps; hh.status = M.status; hh.vx = M.vx; hh.vy = M.vy; hh.vz = M.vz;
+        hh.px = M.pos.x; hh.py = M.pos.y; hh.pz = M.pos.z;
+        out[i] = hh;
+        fetched_total += fetched; steps_total += (unsigned long long)steps;
+    }
+    if (counters) { counters[0] = fetched_total; counters[1] = steps_total; }
+}
 
 }  // namespace
 
@@ -86,54 +93,73 @@ void* emul_create(const uint8_t* vol, int sx, int sy, int sz) {
     Emul* e = new Emul();
     e->vol.assign(vol, vol + (size_t)sx * sy * sz);
     e->sx = sx; e->sy = sy; e->sz = sz;
-    e->l2 = build_level(vol, sx, sy, sz, 2, 8);
-    e->l4 = build_level(vol, sx, sy, sz, 4, 15);
+    for (int sh = 1; sh <= 4; ++sh) e->lv[sh] = build_occ(vol, sx, sy, sz, sh);
     return e;
 }
 void emul_destroy(void* h) { delete (Emul*)h; }
 
-// clearance arrays (padded) for comparison with vxl_volume_debug_clearance / numpy
-void emul_level(void* h, int level, uint8_t* out, int* dims) {
+// occupancy level as 0/1 bytes [cz][cy][cx] for comparison with vxl_volume_debug_occupancy / numpy
+void emul_level(void* h, int shift, uint8_t* out, int* dims) {
     Emul* e = (Emul*)h;
-    const HostLevel& L = level == 2 ? e->l2 : e->l4;
-    dims[0] = L.cx; dims[1] = L.cy; dims[2] = L.cz; dims[3] = L.border;
-    if (out) memcpy(out, L.r.data(), L.r.size());
+    const HostOcc& L = e->lv[shift];
+    dims[0] = L.cx; dims[1] = L.cy; dims[2] = L.cz;
+    if (out) memcpy(out, L.occ.data(), L.occ.size());
 }
 
-// rays: 8 floats each (origin, dir, dist, pad); variant 0 Sparse / 1 SuperSparse; the clearance tiles are
-// placed around `center` (voxels) exactly as block_prologue does.  fast = 0 runs the plain march.
-void emul_trace(void* h, const float* rays, long long n, int variant, const int* center, int fast, vxl_hit* out,
-                unsigned long long* exact_total, unsigned long long* steps_total) {
+// rays: 8 floats each (origin, dir, dist, pad); variant 0 Sparse / 1 SuperSparse; geom 0 ambient, 1 local lights,
+// 2 reflection (the tile geometries of vxl_passes.cu); the tile is placed around `center` (voxels) exactly as
+// block_prologue does.  fast = 0 runs the plain march.  counters: probes that read the volume, total probes.
+void emul_trace(void* h, const float* rays, long long n, int variant, const int* center, int fast, int geom, vxl_hit* out,
+                unsigned long long* counters) {
     Emul* e = (Emul*)h;
-    VolView V;
-    V.bytes = e->vol.data(); V.sx = e->sx; V.sy = e->sy; V.sz = e->sz;
-    V.cm4 = ClearView{nullptr, 0, 0, 0, 0, 0}; V.cm16 = V.cm4;
-    std::vector<uint32_t> w4, w16;
-    FastCtx C;
-    C.t4.ox = (center[0] >> 2) - CT / 2; C.t4.oy = (center[1] >> 2) - CT / 2; C.t4.oz = (center[2] >> 2) - CT / 2;
-    C.t16.ox = (center[0] >> 4) - CT / 2; C.t16.oy = (center[1] >> 4) - CT / 2; C.t16.oz = (center[2] >> 4) - CT / 2;
-    build_tile(e->l2, C.t4.ox, C.t4.oy, C.t4.oz, w4);
-    build_tile(e->l4, C.t16.ox, C.t16.oy, C.t16.oz, w16);
-    C.t4.w = w4.data(); C.t16.w = w16.data();
-    C.enabled = fast != 0;
-    unsigned long long ex = 0, st = 0;
+    if (geom == 0) trace_geom<2, 72, 3>(e, rays, n, variant, center, fast, out, counters);
+    else if (geom == 1) trace_geom<2, 84, 3>(e, rays, n, variant, center, fast, out, counters);
+    else trace_geom<3, 72, 3>(e, rays, n, variant, center, fast, out, counters);
+}
+
+// experiment helper: classify every probe of the plain march by what a bit-occupancy hierarchy would know.
+// out[phase(2)][near(2)][8]: [0]=probes, [1]=texel byte zero, [2]=4-voxel cell empty, [3]=8-voxel cell empty, [4]=16-voxel cell empty
+void emul_classify(void* h, const float* rays, long long n, int variant, const int* center, float near_half, unsigned long long* out) {
+    Emul* e = (Emul*)h;
+    memset(out, 0, sizeof(unsigned long long) * 2 * 2 * 8);
+    const float step0 = variant ? 2.5f : 0.5f;
+    auto occ = [&](int shift, float3 p) -> bool {
+        const float c = (float)(1 << shift);
+        return e->lv[shift].at((int)floorf(p.x / c), (int)floorf(p.y / c), (int)floorf(p.z / c));
+    };
+    VolView V; V.bytes = e->vol.data(); V.sx = e->sx; V.sy = e->sy; V.sz = e->sz;
     for (long long i = 0; i < n; ++i) {
         const float* r = rays + i * 8;
-        MarchResult M;
-        int steps = 0;
-        unsigned exact = 0;
-        const float3 o = make_float3(r[0], r[1], r[2]), d = make_float3(r[3], r[4], r[5]);
-        if (variant == 0) march_fast<false, true>(V, C, o, d, r[6], steps, &M, exact);
-        else march_fast<true, true>(V, C, o, d, r[6], steps, &M, exact);
-        vxl_hit hh;
-        memset(&hh, 0, sizeof hh);
-        hh.t = M.d; hh.steps = M.steps; hh.status = M.status; hh.vx = M.vx; hh.vy = M.vy; hh.vz = M.vz;
-        hh.px = M.pos.x; hh.py = M.pos.y; hh.pz = M.pos.z;
-        out[i] = hh;
-        ex += exact; st += (unsigned long long)steps;
+        float3 pos = make_float3(r[0], r[1], r[2]);
+        float3 sd = make_float3(r[3], r[4], r[5]) * step0;
+        float d = step0, sf = step0;
+        auto tally = [&](int phase) {
+            const bool nearp = fabsf(pos.x - center[0]) < near_half && fabsf(pos.y - center[1]) < near_half && fabsf(pos.z - center[2]) < near_half;
+            unsigned long long* o = out + (phase * 2 + (nearp ? 1 : 0)) * 8;
+            o[0]++;
+            for (int sh = 1; sh <= 4; ++sh) if (!occ(sh, pos)) o[sh]++;
+        };
+        bool hit = false;
+        while (d < 16.0f) {
+            tally(0);
+            const int tx = f2i(pos.x / 2.0f), ty = f2i(pos.y / 2.0f), tz = f2i(pos.z / 2.0f);
+            const unsigned v = fetch_texel(V, tx, ty, tz);
+            unsigned bit = 0u;
+            bit += gmod(pos.x, 0.5f) > 0.25f ? 1u : 0u;
+            bit += gmod(pos.y, 0.5f) > 0.25f ? 2u : 0u;
+            bit += gmod(pos.z, 0.5f) > 0.25f ? 4u : 0u;
+            if ((v >> bit) & 1u) { hit = true; break; }
+            pos = pos + sd; d += sf;
+        }
+        if (hit) continue;
+        sf *= 2.0f; sd = sd * 2.0f;
+        const float lim = fminf(r[6], 164.0f);
+        while (d < lim) {
+            tally(1);
+            if (fetch_texel(V, f2i(pos.x) / 2, f2i(pos.y) / 2, f2i(pos.z) / 2) != 0u) break;
+            pos = pos + sd; d += sf;
+        }
     }
-    if (exact_total) *exact_total = ex;
-    if (steps_total) *steps_total = st;
 }
 
 }  // extern "C"

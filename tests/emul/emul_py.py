@@ -43,7 +43,8 @@ def lib():
         L.emul_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.emul_destroy.argtypes = [C.c_void_p]
         L.emul_level.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
-        L.emul_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.emul_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.emul_classify.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_float, C.c_void_p]
         _lib = L
     return _lib
 
@@ -54,21 +55,25 @@ class Emul:
         sz, sy, sx = self.volume.shape
         self.h = lib().emul_create(self.volume.ctypes.data, sx, sy, sz)
 
-    def level(self, level: int):
-        dims = np.zeros(4, np.int32)
-        lib().emul_level(self.h, level, None, dims.ctypes.data)
+    def level(self, shift: int) -> np.ndarray:
+        """occupancy level (cell = 2^shift voxels) as 0/1 uint8 [cz][cy][cx], built by straightforward host code"""
+        dims = np.zeros(3, np.int32)
+        lib().emul_level(self.h, shift, None, dims.ctypes.data)
         out = np.zeros((dims[2], dims[1], dims[0]), np.uint8)
-        lib().emul_level(self.h, level, out.ctypes.data, dims.ctypes.data)
-        return out, int(dims[3])
+        lib().emul_level(self.h, shift, out.ctypes.data, dims.ctypes.data)
+        return out
 
-    def trace(self, rays: np.ndarray, variant: int, center, fast: bool = True):
+    GEOMS = {"ambient": 0, "local": 1, "reflection": 2}
+
+    def trace(self, rays: np.ndarray, variant: int, center, fast: bool = True, geom: str = "ambient"):
+        """-> (hit records, probes that read the volume, total probe count)"""
         rays = np.ascontiguousarray(rays)
         n = len(rays)
         out = np.zeros(n, HIT_DTYPE)
         c = np.asarray(center, np.int32)
-        ex, st = C.c_ulonglong(0), C.c_ulonglong(0)
-        lib().emul_trace(self.h, rays.ctypes.data, n, int(variant), c.ctypes.data, int(fast), out.ctypes.data, C.byref(ex), C.byref(st))
-        return out, int(ex.value), int(st.value)
+        cnt = np.zeros(2, np.uint64)
+        lib().emul_trace(self.h, rays.ctypes.data, n, int(variant), c.ctypes.data, int(fast), self.GEOMS[geom], out.ctypes.data, cnt.ctypes.data)
+        return out, int(cnt[0]), int(cnt[1])
 
     def close(self):
         if self.h:

@@ -36,7 +36,7 @@ def main():
     hits = [O.trace_rays(sc["volume"], rays, v) for v in (0, 1, 2)]
     np.savez_compressed(
         os.path.join(HERE, "house64.npz"),
-        volume=np.packbits(sc["volume"]), depth24=sc["gb"]["depth24"], normal=sc["gb"]["normal"], material=sc["gb"]["material"],
+        volume=sc["volume"], depth24=sc["gb"]["depth24"], normal=sc["gb"]["normal"], material=sc["gb"]["material"],
         shadow=sh.astype(np.uint8), ao=ao, point=pt.astype(np.uint8), spot=sp.astype(np.uint8), spec_t=t,
         stats=np.array([[s["rays"], s["steps"], s["pixels"]] for s in (st_a, st_p, st_s, st_r)], np.uint64),
         hits_sparse=hits[0], hits_supersparse=hits[1], hits_dda=hits[2])

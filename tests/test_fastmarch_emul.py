@@ -1,5 +1,5 @@
-"""The accelerated march (clearance-map culling + exact replay, vxl_fastmarch.cuh) compiled for the HOST
-must reproduce the oracle's plain march bit-for-bit: distance, probe count, hit voxel, hit position.
+"""The tile march (occupancy-bit tile in front of the reference's texel test, vxl_bitmarch.cuh) compiled for the
+HOST must reproduce the oracle's plain march bit-for-bit: distance, probe count, hit voxel, hit position.
 Runs without a GPU; the same header is what the CUDA kernels instantiate."""
 import os
 import sys
@@ -61,20 +61,21 @@ def _surface_points(vol, k, rs):
 
 
 @pytest.mark.parametrize("variant", [0, 1])
-def test_emulated_fast_march_matches_oracle_on_pass_like_rays(oracle, terrain, emul, variant):
+@pytest.mark.parametrize("geom", ["ambient", "local", "reflection"])
+def test_emulated_tile_march_matches_oracle_on_pass_like_rays(oracle, terrain, emul, variant, geom):
     vol = terrain["volume"]
     rs = np.random.RandomState(100 + variant)
-    total_exact = total_steps = 0
-    for center in _surface_points(vol, 12, rs):
+    total_fetched = total_steps = 0
+    for center in _surface_points(vol, 8, rs):
         rays = _surface_rays(rs, vol, 20_000, center, 6.0, [128.0, 256.0, 40.0, 73.3, 17.0, 10.0, 164.0, 500.0])
         want = oracle.trace_rays(vol, rays, variant)
-        got, exact, steps = emul.trace(rays, variant, center)
+        got, fetched, steps = emul.trace(rays, variant, center, geom=geom)
         _compare(got, want)
         assert steps == int(want["steps"].sum())
-        total_exact += exact
+        total_fetched += fetched
         total_steps += steps
-    # the acceleration really engages: most probes are proven empty, not executed
-    assert total_exact < 0.6 * total_steps, (total_exact, total_steps)
+    # the tile really engages: most probes are answered by a clear occupancy bit
+    assert 0 < total_fetched < 0.5 * total_steps, (total_fetched, total_steps)
 
 
 @pytest.mark.parametrize("variant", [0, 1])
@@ -93,8 +94,9 @@ def test_emulated_fast_march_matches_oracle_on_arbitrary_rays(oracle, terrain, e
     rays["dist"][4 * k:5 * k] = np.inf
     rays["dist"][5 * k:6 * k] = -3.0
     want = oracle.trace_rays(vol, rays, variant)
-    for center in [(sx, sy, sz), (10, 2 * sy - 5, 2 * sz - 3), (-40, 50, 300)]:
-        got, _, steps = emul.trace(rays, variant, center)
+    for geom, center in [("ambient", (sx, sy, sz)), ("local", (10, 2 * sy - 5, 2 * sz - 3)), ("reflection", (-40, 50, 300)),
+                         ("ambient", (3, 3, 3))]:
+        got, _, steps = emul.trace(rays, variant, center, geom=geom)
         _compare(got, want)
 
 
@@ -103,24 +105,18 @@ def test_emulated_plain_march_is_the_oracle(oracle, terrain, emul):
     sz, sy, sx = vol.shape
     rays = U.random_rays(np.random.RandomState(3), 50_000, (2 * sx, 2 * sy, 2 * sz))
     for variant in (0, 1):
-        got, exact, _ = emul.trace(rays, variant, (sx, sy, sz), fast=False)
+        got, fetched, _ = emul.trace(rays, variant, (sx, sy, sz), fast=False)
         _compare(got, oracle.trace_rays(vol, rays, variant))
-        assert exact == 0
+        assert fetched == 0
 
 
-def test_bruteforce_clearance_is_a_chebyshev_distance(terrain, emul):
-    """emul's brute-force maps (the reference for the GPU build test) against scipy's chessboard transform."""
-    from scipy import ndimage
+def test_host_occupancy_levels_are_block_maxima(terrain, emul):
+    """emul's occupancy levels (the reference for the GPU build test) against a numpy block reduction."""
     vol = terrain["volume"]
-    for level, tpc, cap in ((2, 2, 8), (4, 8, 15)):
-        r, border = emul.level(level)
-        assert border == cap
-        sz, sy, sx = vol.shape
+    sz, sy, sx = vol.shape
+    for shift, tpc in ((1, 1), (2, 2), (3, 4), (4, 8)):
         n = [-(-s // tpc) for s in (sz, sy, sx)]
-        pad = np.zeros([-(-s // tpc) * tpc for s in (sz, sy, sx)], np.uint8)
+        pad = np.zeros([k * tpc for k in n], np.uint8)
         pad[:sz, :sy, :sx] = vol
-        occ = pad.reshape(n[0], tpc, n[1], tpc, n[2], tpc).max(axis=(1, 3, 5)) != 0
-        occp = np.pad(occ, cap)
-        dist = ndimage.distance_transform_cdt(~occp, metric="chessboard")
-        want = np.minimum(dist, cap).astype(np.uint8)
-        assert np.array_equal(r, want)
+        want = (pad.reshape(n[0], tpc, n[1], tpc, n[2], tpc).max(axis=(1, 3, 5)) != 0).astype(np.uint8)
+        assert np.array_equal(emul.level(shift), want)

@@ -18,7 +18,7 @@ SYMBOLS = [
     "vxl_volume_mark_dirty", "vxl_volume_build_occupancy", "vxl_model_create", "vxl_volume_voxelize",
     "vxl_pass_ambient", "vxl_pass_point", "vxl_pass_spot", "vxl_pass_reflection", "vxl_trace_rays",
     "vxl_lighting_host", "vxl_volume_gen_terrain", "vxl_gbuffer_primary",
-    "vxl_debug_set_variant", "vxl_debug_exact_probes", "vxl_volume_debug_clearance",
+    "vxl_debug_set_variant", "vxl_debug_fetched_probes", "vxl_volume_debug_occupancy",
 ]
 
 VXL_MAX_LIGHTS = 64
@@ -81,8 +81,8 @@ def load():
         "vxl_trace_rays": [vp, vp, vp, i64, i32, vp],
         "vxl_lighting_host": [vp, vp, P(LightingHostArgs)],
         "vxl_volume_gen_terrain": [vp], "vxl_gbuffer_primary": [vp, vp, vp, P(Frame)],
-        "vxl_debug_set_variant": [vp, i32], "vxl_debug_exact_probes": [vp, P(C.c_uint64)],
-        "vxl_volume_debug_clearance": [vp, i32, vp, vp],
+        "vxl_debug_set_variant": [vp, i32], "vxl_debug_fetched_probes": [vp, P(C.c_uint64)],
+        "vxl_volume_debug_occupancy": [vp, i32, vp, vp],
     }
     for name, argtypes in protos.items():
         fn = getattr(lib, name)

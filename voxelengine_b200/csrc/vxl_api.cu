@@ -147,8 +147,8 @@ int vxl_debug_set_variant(vxl_ctx* c, int variant) {
     return VXL_OK;
 }
 
-int vxl_debug_exact_probes(vxl_ctx* c, uint64_t* out) {
-    if (!c || !out) { set_error("vxl_debug_exact_probes: bad argument"); return VXL_ERR_INVALID; }
+int vxl_debug_fetched_probes(vxl_ctx* c, uint64_t* out) {
+    if (!c || !out) { set_error("vxl_debug_fetched_probes: bad argument"); return VXL_ERR_INVALID; }
     unsigned long long h[STAT_SLOTS * 4];
     VXL_CUDA(cudaMemcpyAsync(h, c->d_stats, sizeof h, cudaMemcpyDeviceToHost, c->stream));
     VXL_CUDA(cudaStreamSynchronize(c->stream));

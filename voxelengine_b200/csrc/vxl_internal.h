@@ -9,24 +9,21 @@
 
 namespace vxl {
 
-// One clearance map (vxl_occupancy.cu): nibbles, 8 cells per word along x, cell = 2^shift voxels.
-// The array is padded by `border` (= cap) cells on every side so that out-of-volume cells carry their true
-// clearance; array index = cell index + border.  Everything beyond the padded array has clearance >= cap.
-struct ClearLevel {
+// One occupancy bitmask level (vxl_occupancy.cu): bit (x & 31) of word x >> 5, cell = 2^shift voxels.
+struct BitLevel {
     uint32_t* d_words = nullptr;
-    int cx = 0, cy = 0, cz = 0;          // padded array dims, cells
-    int pitch = 0;                       // words per row (>= ceil(cx/8) + 1)
-    int shift = 0;                       // log2(voxels per cell)
-    int cap = 0;                         // largest stored distance == border
+    int cx = 0, cy = 0, cz = 0;          // cells
+    int pitch = 0;                       // words per row (ceil(cx/32) + 1 spare zero word)
+    int shift = 0;                       // log2(voxels per cell edge)
 };
-struct ClearView { const uint32_t* __restrict__ words; int cx, cy, cz, pitch, border; };
+struct BitView { const uint32_t* __restrict__ words; int cx, cy, cz, pitch; };
 
 // Device-side view of the occupancy volume handed to kernels by value.
 struct VolView {
     const uint8_t* __restrict__ bytes;   // canonical packed bytes, x fastest (reference layout)
     int sx, sy, sz;                      // texels
     // derived, acceleration only (never changes a result); see vxl_occupancy.cu
-    ClearView cm4, cm16;
+    BitView occ[2];                      // 4-voxel and 8-voxel cells
 };
 
 struct FrameView {
@@ -48,7 +45,7 @@ struct vxl_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     uint64_t launches = 0;
-    int variant = 1;                         // 0: plain per-probe march; 1: clearance-map accelerated (default)
+    int variant = 1;                         // 0: plain march on the volume bytes; 1: occupancy-bit tile in shared memory (default)
     unsigned long long* d_stats = nullptr;   // [STAT_SLOTS][4]
     float* d_luts = nullptr;                 // cos[256] sin[256]
     void* d_lights = nullptr;                // VXL_MAX_LIGHTS * 64 B
@@ -76,8 +73,7 @@ struct vxl_volume {
     int sx = 0, sy = 0, sz = 0;
     uint8_t* d_bytes = nullptr;
     bool dirty = true;
-    vxl::ClearLevel cm4, cm16;           // clearance maps at 4- and 16-voxel cells
-    uint8_t* d_scratch = nullptr;        // distance-transform ping-pong
+    vxl::BitLevel occ[2];                // occupancy bitmasks at 4- and 8-voxel cells
 };
 
 namespace vxl {
@@ -98,8 +94,7 @@ int cuda_fail(cudaError_t e, const char* what);
 inline VolView vol_view(const vxl_volume* v) {
     VolView r;
     r.bytes = v->d_bytes; r.sx = v->sx; r.sy = v->sy; r.sz = v->sz;
-    r.cm4 = ClearView{v->cm4.d_words, v->cm4.cx, v->cm4.cy, v->cm4.cz, v->cm4.pitch, v->cm4.cap};
-    r.cm16 = ClearView{v->cm16.d_words, v->cm16.cx, v->cm16.cy, v->cm16.cz, v->cm16.pitch, v->cm16.cap};
+    for (int i = 0; i < 2; ++i) r.occ[i] = BitView{v->occ[i].d_words, v->occ[i].cx, v->occ[i].cy, v->occ[i].cz, v->occ[i].pitch};
     return r;
 }
 int frame_view(const vxl_frame* f, FrameView* out);

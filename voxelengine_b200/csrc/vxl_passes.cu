@@ -1,20 +1,24 @@
 // vxl_passes.cu -- the four light passes and the ray-level entry as sm_100a kernels.
 //
-// One thread per pixel of a tile-compact frame shard.  A warp covers an 8x4 pixel block so that
-// neighbouring rays (which start close together and, for shadows, point the same way) touch the
-// same cache lines of the volume.  Ray generation follows the reference fragment shaders line by
-// line (citations inline); the traversal is vxl_trace.cuh.
+// One thread per pixel of a tile-compact frame shard; a thread block covers 32x16 pixels (a warp 8x4).
+// Ray generation follows the reference fragment shaders line by line (citations inline).  The
+// rays of a block start within a few voxels of each other, so the block stages the occupancy-bit
+// tile around them in shared memory once and every probe tests that tile before touching the
+// volume (vxl_bitmarch.cuh); kernel variant 0 is the plain march on the bytes (vxl_trace.cuh).
 #include "vxl_internal.h"
 #include "vxl_math.cuh"
 #include "vxl_trace.cuh"
-#include "vxl_fastmarch.cuh"
+#include "vxl_bitmarch.cuh"
+
+#include <cstddef>
 
 namespace vxl {
 
 constexpr float FAR_ = 4096.0f;                     // Sources/Shaders/lib/Common.frag:13
 constexpr float GOLDEN_RATIO = 2.118033988749895f;  // Common.frag:9 (sic)
 
-constexpr int BLOCK_W = 32, BLOCK_H = 8;            // pixels per thread block (8 warps of 8x4)
+constexpr int BLOCK_W = 32, BLOCK_H = 16;           // pixels per thread block (16 warps of 8x4)
+constexpr int BLOCK_THREADS = BLOCK_W * BLOCK_H;
 
 struct ViewK { float InvView[16], View[16], InvProj[16]; int Frame; };
 
@@ -34,7 +38,7 @@ __device__ __forceinline__ PixelCtx pixel_ctx(const FrameView& F, const ViewK& K
     const int lt = blockIdx.x / bpt, b = blockIdx.x - lt * bpt;
     const int by = b / bpt_x, bx = b - by * bpt_x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // 8 warps as 4 (x) by 2 (y); each warp 8 (x) by 4 (y)
+    // 16 warps as 4 (x) by 4 (y); each warp 8 (x) by 4 (y)
     const int lx = bx * BLOCK_W + (warp & 3) * 8 + (lane & 7);
     const int ly = by * BLOCK_H + (warp >> 2) * 4 + (lane >> 3);
     const int gt = F.tile_first + lt * F.tile_stride;
@@ -87,28 +91,35 @@ __device__ __forceinline__ void load_luts(float* s_lut, const float* __restrict_
     }
 }
 
-// Shared-memory state of the accelerated march for one thread block.
+// Shared-memory state of one thread block (dynamic: the tile exceeds the 48 KB static limit).
+template <int TY, int TW>
 struct BlockShared {
-    uint32_t t4[CT_WORDS];
-    uint32_t t16[CT_WORDS];
     float lut[LUT_FLOATS];
     int bb[6];
     unsigned acc[4];
+    uint32_t tile[TY * TY * TW];     // last: kernel variant 0 allocates only the header
 };
+template <typename G, bool FAST>
+constexpr size_t smem_bytes() {
+    typedef BlockShared<G::TY, G::TW> BS;
+    return FAST ? sizeof(BS) : sizeof(BS) - sizeof(uint32_t) * G::TY * G::TY * G::TW;
+}
+// tile geometry per pass: cells of 2^SHIFT voxels, TW*32 x TY x TY cells
+struct AmbientGeom { static constexpr int SHIFT = 2, TY = 72, TW = 3; };     // +-144 voxels (AO 128, sun 128)
+struct LocalGeom   { static constexpr int SHIFT = 2, TY = 84, TW = 3; };     // +-168 voxels (<= 164 + spread)
+struct ReflGeom    { static constexpr int SHIFT = 3, TY = 72, TW = 3; };     // +-288 voxels (164 steps * |wd| <= 1.5)
 
-// Bounding box of the block's ray origins -> tile placement -> stage both clearance tiles.
+// Bounding box of the block's ray origins -> tile placement -> stage the occupancy tile.
 // `hint` is (close to) the thread's ray origin in voxel units; threads without rays pass valid = false.
 // Ends with a block barrier (which also publishes the LUTs).
-template <bool FAST>
-__device__ __forceinline__ FastCtx block_prologue(const VolView& V, BlockShared& S, bool valid, float3 hint) {
-    FastCtx C;
-    C.t4.w = S.t4; C.t16.w = S.t16;
-    C.t4.ox = C.t4.oy = C.t4.oz = 0; C.t16.ox = C.t16.oy = C.t16.oz = 0;
-    C.enabled = false;
+template <bool FAST, typename G>
+__device__ __forceinline__ BitTile block_prologue(const VolView& V, BlockShared<G::TY, G::TW>& S, bool valid, float3 hint) {
+    BitTile T;
+    T.w = S.tile; T.ox = T.oy = T.oz = 0; T.enabled = false;
     if (threadIdx.x < 3) { S.bb[threadIdx.x] = 0x7fffffff; S.bb[3 + threadIdx.x] = -0x7fffffff - 1; }
     if (threadIdx.x < 4) S.acc[threadIdx.x] = 0u;
     __syncthreads();
-    if (!FAST) return C;
+    if (!FAST) return T;
     const int big = 1 << 24;
     int ix = valid ? max(-big, min(big, f2i(hint.x))) : 0x7fffffff, iy = valid ? max(-big, min(big, f2i(hint.y))) : 0x7fffffff,
         iz = valid ? max(-big, min(big, f2i(hint.z))) : 0x7fffffff;
@@ -120,26 +131,25 @@ __device__ __forceinline__ FastCtx block_prologue(const VolView& V, BlockShared&
         atomicMax(&S.bb[3], mxx); atomicMax(&S.bb[4], mxy); atomicMax(&S.bb[5], mxz);
     }
     __syncthreads();
-    if (S.bb[0] == 0x7fffffff) return C;                    // no ray in this block (uniform)
+    if (S.bb[0] == 0x7fffffff) return T;                    // no ray in this block (uniform)
     const int cx = (S.bb[0] + S.bb[3]) >> 1, cy = (S.bb[1] + S.bb[4]) >> 1, cz = (S.bb[2] + S.bb[5]) >> 1;
-    C.t4.ox = (cx >> 2) - CT / 2; C.t4.oy = (cy >> 2) - CT / 2; C.t4.oz = (cz >> 2) - CT / 2;
-    C.t16.ox = (cx >> 4) - CT / 2; C.t16.oy = (cy >> 4) - CT / 2; C.t16.oz = (cz >> 4) - CT / 2;
-    stage_tile(S.t4, V.cm4, C.t4.ox, C.t4.oy, C.t4.oz);
-    stage_tile(S.t16, V.cm16, C.t16.ox, C.t16.oy, C.t16.oz);
+    T.ox = (cx >> G::SHIFT) - G::TW * 16; T.oy = (cy >> G::SHIFT) - G::TY / 2; T.oz = (cz >> G::SHIFT) - G::TY / 2;
+    stage_bits<G::TY, G::TW>(S.tile, V.occ[G::SHIFT - 2], T.ox, T.oy, T.oz);
     __syncthreads();
-    C.enabled = true;
-    return C;
+    T.enabled = true;
+    return T;
 }
 
-template <bool FAST, bool SUPER>
-__device__ __forceinline__ float ray_march(const VolView& V, const FastCtx& C, float3 origin, float3 dir, float dist, int& steps, unsigned& exact) {
-    if (FAST) return march_fast<SUPER, false>(V, C, origin, dir, dist, steps, nullptr, exact);
+template <bool FAST, bool SUPER, typename G>
+__device__ __forceinline__ float ray_march(const VolView& V, const BitTile& T, float3 origin, float3 dir, float dist, int& steps, unsigned& fetched) {
+    if (FAST) return march_bits<SUPER, false, G::SHIFT, G::TY, G::TW>(V, T, origin, dir, dist, steps, nullptr, fetched);
     return march<false>(V, origin, dir, dist, SUPER ? 2.5f : 0.5f, steps, nullptr);
 }
 
 // block-level accumulation of (rays, steps, pixels) into striped global counters
-// (slot 3: probes executed exactly by the accelerated march -- diagnostics).  S.acc is zeroed by block_prologue.
-__device__ __forceinline__ void flush_stats(BlockShared& S, unsigned long long* __restrict__ g_stats, unsigned rays, unsigned steps,
+// (slot 3: probes that read the volume in the tile march -- diagnostics).  S.acc is zeroed by block_prologue.
+template <typename BS>
+__device__ __forceinline__ void flush_stats(BS& S, unsigned long long* __restrict__ g_stats, unsigned rays, unsigned steps,
                                             unsigned pixels, unsigned exact) {
     rays = __reduce_add_sync(0xFFFFFFFFu, rays);
     steps = __reduce_add_sync(0xFFFFFFFFu, steps);
@@ -157,10 +167,12 @@ __device__ __forceinline__ void flush_stats(BlockShared& S, unsigned long long* 
 // LightAmbient.frag:134-175 + calculateAmbientIrradiance :111-126
 // -------------------------------------------------------------------------------------------------
 template <bool FAST>
-__global__ void __launch_bounds__(256) k_ambient(VolView V, FrameView F, ViewK K, const float* __restrict__ g_lut, int n_ao,
+__global__ void __launch_bounds__(BLOCK_THREADS, 2) k_ambient(VolView V, FrameView F, ViewK K, const float* __restrict__ g_lut, int n_ao,
                                                  float* __restrict__ out_shadow, float* __restrict__ out_ao,
                                                  unsigned long long* __restrict__ g_stats) {
-    __shared__ BlockShared S;
+    typedef AmbientGeom G;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BlockShared<G::TY, G::TW>& S = *reinterpret_cast<BlockShared<G::TY, G::TW>*>(smem_raw);
     load_luts(S.lut, g_lut);
     const PixelCtx p = pixel_ctx(F, K);
     float depth = 1.0f;
@@ -177,7 +189,7 @@ __global__ void __launch_bounds__(256) k_ambient(VolView V, FrameView F, ViewK K
             bias = gsmoothstep(0.0f, 0.2f, depth) * 50.0f + 1.5f;                      // :158
         }
     }
-    const FastCtx C = block_prologue<FAST>(V, S, lit, wcp0 + normal * bias);
+    const BitTile C = block_prologue<FAST, G>(V, S, lit, wcp0 + normal * bias);
     unsigned rays = 0, pixels = 0, exact = 0;
     int steps = 0;
     if (p.valid) {
@@ -194,7 +206,7 @@ __global__ void __launch_bounds__(256) k_ambient(VolView V, FrameView F, ViewK K
             wcp = wcp + randomVec * 2.5f;                                              // :156
             const float3 origin = wcp + normal * bias;
             if (out_shadow) {
-                if (ray_march<FAST, false>(V, C, origin, wd, 128.0f, steps, exact) != 128.0f) shadow = 0.0f;   // :167-169
+                if (ray_march<FAST, false, G>(V, C, origin, wd, 128.0f, steps, exact) != 128.0f) shadow = 0.0f;   // :167-169
                 rays += 1;
             }
             if (out_ao && n_ao > 0) {
@@ -206,7 +218,7 @@ __global__ void __launch_bounds__(256) k_ambient(VolView V, FrameView F, ViewK K
                     const uint32_t ni = (i == 0) ? n : get_noise(F, K, p, i);
                     const float3 rv = cosine_sample_hemisphere(S.lut, ni, ni >> 8);                       // :118
                     const float3 dir = tangent * rv.x + bitangent * rv.y + normal * rv.z;                 // :119
-                    const float d = ray_march<FAST, true>(V, C, origin, dir, 128.0f, steps, exact) / 128.0f;   // :121
+                    const float d = ray_march<FAST, true, G>(V, C, origin, dir, 128.0f, steps, exact) / 128.0f;   // :121
                     acc += d * d;
                 }
                 ao = (acc / (float)n_ao) * 0.05f;                                                         // :125
@@ -225,11 +237,13 @@ __global__ void __launch_bounds__(256) k_ambient(VolView V, FrameView F, ViewK K
 // G-buffer, noise and world position are read / derived once per pixel instead of once per light.
 // -------------------------------------------------------------------------------------------------
 template <bool SPOT, bool FAST>
-__global__ void __launch_bounds__(256) k_local_lights(VolView V, FrameView F, ViewK K, const float* __restrict__ g_lut,
+__global__ void __launch_bounds__(BLOCK_THREADS, 2) k_local_lights(VolView V, FrameView F, ViewK K, const float* __restrict__ g_lut,
                                                       const float* __restrict__ lights, int n_lights,
                                                       float* __restrict__ out_shadow, size_t plane_stride,
                                                       unsigned long long* __restrict__ g_stats) {
-    __shared__ BlockShared S;
+    typedef LocalGeom G;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BlockShared<G::TY, G::TW>& S = *reinterpret_cast<BlockShared<G::TY, G::TW>*>(smem_raw);
     __shared__ float s_light[VXL_MAX_LIGHTS * 4];   // position.xyz, range
     load_luts(S.lut, g_lut);
     constexpr int STRIDE = SPOT ? 16 : 8;
@@ -244,7 +258,7 @@ __global__ void __launch_bounds__(256) k_local_lights(VolView V, FrameView F, Vi
         normal = decode_normal(__ldg(F.normal + p.idx));                                     // :90
         worldPos = xyz(mat_mul(K.InvView, make_float4(pos.x, pos.y, pos.z, 1.0f)));          // :95
     }
-    const FastCtx C = block_prologue<FAST>(V, S, hint_ok, worldPos * 10.0f);
+    const BitTile C = block_prologue<FAST, G>(V, S, hint_ok, worldPos * 10.0f);
     unsigned rays = 0, pixels = 0, exact = 0;
     int steps = 0;
     if (p.valid) {
@@ -267,7 +281,7 @@ __global__ void __launch_bounds__(256) k_local_lights(VolView V, FrameView F, Vi
                 wd = normalize3(wd);                                                         // :114
                 wcp = wcp + wd * nw;                                                         // :115
                 wcp = wcp + rv0 * 2.5f;                                                      // :116
-                if (ray_march<FAST, SPOT>(V, C, wcp + normal * 0.5f, wd, hitDist, steps, exact) < hitDist) shadow = 0.0f;   // :125
+                if (ray_march<FAST, SPOT, G>(V, C, wcp + normal * 0.5f, wd, hitDist, steps, exact) < hitDist) shadow = 0.0f;   // :125
                 rays += 1;
                 pixels = 1;
             }
@@ -281,9 +295,11 @@ __global__ void __launch_bounds__(256) k_local_lights(VolView V, FrameView F, Vi
 // LightReflection.frag:60-113
 // -------------------------------------------------------------------------------------------------
 template <bool FAST>
-__global__ void __launch_bounds__(256) k_reflection(VolView V, FrameView F, ViewK K, const float* __restrict__ g_lut,
+__global__ void __launch_bounds__(BLOCK_THREADS, 2) k_reflection(VolView V, FrameView F, ViewK K, const float* __restrict__ g_lut,
                                                     float* __restrict__ out_t, unsigned long long* __restrict__ g_stats) {
-    __shared__ BlockShared S;
+    typedef ReflGeom G;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BlockShared<G::TY, G::TW>& S = *reinterpret_cast<BlockShared<G::TY, G::TW>*>(smem_raw);
     load_luts(S.lut, g_lut);
     const PixelCtx p = pixel_ctx(F, K);
     float depth = 1.0f;
@@ -298,7 +314,7 @@ __global__ void __launch_bounds__(256) k_reflection(VolView V, FrameView F, View
             wcp0 = xyz(mat_mul(K.InvView, make_float4(pos.x, pos.y, pos.z, 1.0f))) * 10.0f;  // :93
         }
     }
-    const FastCtx C = block_prologue<FAST>(V, S, lit, wcp0 + normal);
+    const BitTile C = block_prologue<FAST, G>(V, S, lit, wcp0 + normal);
     unsigned rays = 0, pixels = 0, exact = 0;
     int steps = 0;
     if (p.valid) {
@@ -318,7 +334,7 @@ __global__ void __launch_bounds__(256) k_reflection(VolView V, FrameView F, View
             const float nw = unorm8(n >> 24);
             wcp = wcp + normal * nw;                                                         // :97
             wd = wd * (1.0f + nw * 0.5f);                                                    // :98
-            t = ray_march<FAST, false>(V, C, wcp + normal, wd, 256.0f, steps, exact);        // :113
+            t = ray_march<FAST, false, G>(V, C, wcp + normal, wd, 256.0f, steps, exact);        // :113
             rays = 1; pixels = 1;
         }
         out_t[p.idx] = t;
@@ -378,10 +394,12 @@ int vxl_pass_ambient(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, const 
     if (!out_shadow && !out_ao) return VXL_OK;
     if (F.n_tiles == 0) return VXL_OK;
     if (vol->dirty) { if (int e = vxl_volume_build_occupancy(vol)) return e; }
-    if (ctx->variant == 0)
-        k_ambient<false><<<grid_for(F), 256, 0, ctx->stream>>>(vol_view(vol), F, make_viewk(view), ctx->d_luts, n_ao, out_shadow, out_ao, ctx->d_stats);
-    else
-        k_ambient<true><<<grid_for(F), 256, 0, ctx->stream>>>(vol_view(vol), F, make_viewk(view), ctx->d_luts, n_ao, out_shadow, out_ao, ctx->d_stats);
+    if (ctx->variant == 0) {
+        k_ambient<false><<<grid_for(F), BLOCK_THREADS, smem_bytes<AmbientGeom, false>(), ctx->stream>>>(vol_view(vol), F, make_viewk(view), ctx->d_luts, n_ao, out_shadow, out_ao, ctx->d_stats);
+    } else {
+        VXL_CUDA(cudaFuncSetAttribute(k_ambient<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<AmbientGeom, true>()));
+        k_ambient<true><<<grid_for(F), BLOCK_THREADS, smem_bytes<AmbientGeom, true>(), ctx->stream>>>(vol_view(vol), F, make_viewk(view), ctx->d_luts, n_ao, out_shadow, out_ao, ctx->d_stats);
+    }
     VXL_LAUNCH_CHECK(ctx);
     return VXL_OK;
 }
@@ -399,7 +417,12 @@ static int local_lights(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, con
     if (vol->dirty) { if (int e = vxl_volume_build_occupancy(vol)) return e; }
     VXL_CUDA(cudaMemcpyAsync(ctx->d_lights, lights, (size_t)n_lights * light_bytes, cudaMemcpyHostToDevice, ctx->stream));
     const size_t plane = frame_pixels(frame);
-#define VXL_LL(SPOT_, FAST_) k_local_lights<SPOT_, FAST_><<<grid_for(F), 256, 0, ctx->stream>>>(vol_view(vol), F, make_viewk(view), ctx->d_luts, (const float*)ctx->d_lights, n_lights, out_shadow, plane, ctx->d_stats)
+#define VXL_LL(SPOT_, FAST_)                                                                                                              \
+    do {                                                                                                                              \
+        if (FAST_) VXL_CUDA(cudaFuncSetAttribute(k_local_lights<SPOT_, FAST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<LocalGeom, FAST_>())); \
+        k_local_lights<SPOT_, FAST_><<<grid_for(F), BLOCK_THREADS, smem_bytes<LocalGeom, FAST_>(), ctx->stream>>>(                    \
+            vol_view(vol), F, make_viewk(view), ctx->d_luts, (const float*)ctx->d_lights, n_lights, out_shadow, plane, ctx->d_stats); \
+    } while (0)
     if (spot) { if (ctx->variant == 0) VXL_LL(true, false); else VXL_LL(true, true); }
     else { if (ctx->variant == 0) VXL_LL(false, false); else VXL_LL(false, true); }
 #undef VXL_LL
@@ -425,10 +448,12 @@ int vxl_pass_reflection(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, con
     if (!F.material) { set_error("vxl_pass_reflection: frame.material is NULL"); return VXL_ERR_INVALID; }
     if (F.n_tiles == 0) return VXL_OK;
     if (vol->dirty) { if (int e = vxl_volume_build_occupancy(vol)) return e; }
-    if (ctx->variant == 0)
-        k_reflection<false><<<grid_for(F), 256, 0, ctx->stream>>>(vol_view(vol), F, make_viewk(view), ctx->d_luts, out_spec_t, ctx->d_stats);
-    else
-        k_reflection<true><<<grid_for(F), 256, 0, ctx->stream>>>(vol_view(vol), F, make_viewk(view), ctx->d_luts, out_spec_t, ctx->d_stats);
+    if (ctx->variant == 0) {
+        k_reflection<false><<<grid_for(F), BLOCK_THREADS, smem_bytes<ReflGeom, false>(), ctx->stream>>>(vol_view(vol), F, make_viewk(view), ctx->d_luts, out_spec_t, ctx->d_stats);
+    } else {
+        VXL_CUDA(cudaFuncSetAttribute(k_reflection<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<ReflGeom, true>()));
+        k_reflection<true><<<grid_for(F), BLOCK_THREADS, smem_bytes<ReflGeom, true>(), ctx->stream>>>(vol_view(vol), F, make_viewk(view), ctx->d_luts, out_spec_t, ctx->d_stats);
+    }
     VXL_LAUNCH_CHECK(ctx);
     return VXL_OK;
 }

@@ -66,12 +66,12 @@ class Context:
         return dict(rays=int(s.rays), steps=int(s.steps), pixels=int(s.pixels))
 
     def set_variant(self, variant: int):
-        """Diagnostics: 0 = plain per-probe march, 1 = clearance-map accelerated march (default). Same results."""
+        """Diagnostics: 0 = plain march on the volume bytes, 1 = occupancy-bit tile march (default). Same results."""
         check(self.lib.vxl_debug_set_variant(self.h, int(variant)), "vxl_debug_set_variant")
 
-    def exact_probes(self) -> int:
+    def fetched_probes(self) -> int:
         n = C.c_uint64()
-        check(self.lib.vxl_debug_exact_probes(self.h, C.byref(n)), "vxl_debug_exact_probes")
+        check(self.lib.vxl_debug_fetched_probes(self.h, C.byref(n)), "vxl_debug_fetched_probes")
         return int(n.value)
 
     def launch_count(self) -> int:
@@ -156,13 +156,13 @@ class ShadowVoxSystem:
     def build_occupancy(self):
         check(self.lib.vxl_volume_build_occupancy(self.h), "vxl_volume_build_occupancy")
 
-    def clearance(self, level: int):
-        """Diagnostics: (clearance map of `level` incl. border as uint8 [cz][cy][cx], border)."""
-        dims = np.zeros(4, np.int32)
-        check(self.lib.vxl_volume_debug_clearance(self.h, int(level), None, _np_ptr(dims)), "vxl_volume_debug_clearance")
+    def occupancy(self, shift: int) -> np.ndarray:
+        """Diagnostics: occupancy level `shift` (2: 4-voxel cells, 3: 8-voxel cells) as 0/1 uint8 [cz][cy][cx]."""
+        dims = np.zeros(3, np.int32)
+        check(self.lib.vxl_volume_debug_occupancy(self.h, int(shift), None, _np_ptr(dims)), "vxl_volume_debug_occupancy")
         out = np.zeros((dims[2], dims[1], dims[0]), np.uint8)
-        check(self.lib.vxl_volume_debug_clearance(self.h, int(level), _np_ptr(out), _np_ptr(dims)), "vxl_volume_debug_clearance")
-        return out, int(dims[3])
+        check(self.lib.vxl_volume_debug_occupancy(self.h, int(shift), _np_ptr(out), _np_ptr(dims)), "vxl_volume_debug_occupancy")
+        return out
 
     def trace_rays(self, rays: np.ndarray, variant: int) -> np.ndarray:
         """Ray-level entry: host rays in, host hit records out (copies through device buffers)."""
