@@ -55,7 +55,7 @@ struct Emul {
 };
 
 template <int SHIFT, int TY, int TW>
-void trace_geom(Emul* e, const float* rays, long long n, int variant, const int* center, int fast, vxl_hit* out,
+void trace_geom(Emul* e, const float* rays, long long n, int variant, const int* center, int fast, int direct, int lockstep, vxl_hit* out,
                 unsigned long long* counters) {
     VolView V;
     V.bytes = e->vol.data(); V.sx = e->sx; V.sy = e->sy; V.sz = e->sz;
@@ -66,6 +66,9 @@ void trace_geom(Emul* e, const float* rays, long long n, int variant, const int*
     build_tile<TY, TW>(e->lv[SHIFT], T.ox, T.oy, T.oz, w);
     T.w = w.data();
     T.enabled = fast != 0;
+    constexpr int TPC = 1 << (SHIFT - 1);
+    T.direct = direct != 0 && (V.sx % TPC == 0) && (V.sy % TPC == 0) && (V.sz % TPC == 0);
+    T.koff = TileAddr<SHIFT, TY, TW>::texel_koff(V);
     unsigned long long fetched_total = 0, steps_total = 0;
     for (long long i = 0; i < n; ++i) {
         const float* r = rays + i * 8;
@@ -73,8 +76,13 @@ void trace_geom(Emul* e, const float* rays, long long n, int variant, const int*
         int steps = 0;
         unsigned fetched = 0;
         const float3 o = make_float3(r[0], r[1], r[2]), d = make_float3(r[3], r[4], r[5]);
-        if (variant == 0) march_bits<false, true, SHIFT, TY, TW>(V, T, o, d, r[6], steps, &M, fetched);
-        else march_bits<true, true, SHIFT, TY, TW>(V, T, o, d, r[6], steps, &M, fetched);
+        if (lockstep) {
+            if (variant == 0) march_bits<false, true, true, SHIFT, TY, TW>(V, T, o, d, r[6], steps, &M, fetched);
+            else march_bits<true, true, true, SHIFT, TY, TW>(V, T, o, d, r[6], steps, &M, fetched);
+        } else {
+            if (variant == 0) march_bits<false, true, false, SHIFT, TY, TW>(V, T, o, d, r[6], steps, &M, fetched);
+            else march_bits<true, true, false, SHIFT, TY, TW>(V, T, o, d, r[6], steps, &M, fetched);
+        }
         vxl_hit hh;
         memset(&hh, 0, sizeof hh);
         hh.t = M.d; hh.steps = M.steps; hh.status = M.status; hh.vx = M.vx; hh.vy = M.vy; hh.vz = M.vz;
@@ -108,13 +116,13 @@ void emul_level(void* h, int shift, uint8_t* out, int* dims) {
 
 // rays: 8 floats each (origin, dir, dist, pad); variant 0 Sparse / 1 SuperSparse; geom 0 ambient, 1 local lights,
 // 2 reflection (the tile geometries of vxl_passes.cu); the tile is placed around `center` (voxels) exactly as
-// block_prologue does.  fast = 0 runs the plain march.  counters: probes that read the volume, total probes.
-void emul_trace(void* h, const float* rays, long long n, int variant, const int* center, int fast, int geom, vxl_hit* out,
-                unsigned long long* counters) {
+// block_prologue does.  fast = 0 runs the plain march; direct = 0 forces the bounds-checked fetch.  counters: probes that read the volume, total probes.
+void emul_trace(void* h, const float* rays, long long n, int variant, const int* center, int fast, int geom, int direct, int lockstep,
+                vxl_hit* out, unsigned long long* counters) {
     Emul* e = (Emul*)h;
-    if (geom == 0) trace_geom<2, 72, 3>(e, rays, n, variant, center, fast, out, counters);
-    else if (geom == 1) trace_geom<2, 84, 3>(e, rays, n, variant, center, fast, out, counters);
-    else trace_geom<3, 72, 3>(e, rays, n, variant, center, fast, out, counters);
+    if (geom == 0) trace_geom<2, 72, 3>(e, rays, n, variant, center, fast, direct, lockstep, out, counters);
+    else if (geom == 1) trace_geom<2, 84, 3>(e, rays, n, variant, center, fast, direct, lockstep, out, counters);
+    else trace_geom<3, 72, 3>(e, rays, n, variant, center, fast, direct, lockstep, out, counters);
 }
 
 // experiment helper: classify every probe of the plain march by what a bit-occupancy hierarchy would know.

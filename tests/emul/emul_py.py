@@ -43,7 +43,7 @@ def lib():
         L.emul_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.emul_destroy.argtypes = [C.c_void_p]
         L.emul_level.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
-        L.emul_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.emul_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.emul_classify.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_float, C.c_void_p]
         _lib = L
     return _lib
@@ -65,14 +65,14 @@ class Emul:
 
     GEOMS = {"ambient": 0, "local": 1, "reflection": 2}
 
-    def trace(self, rays: np.ndarray, variant: int, center, fast: bool = True, geom: str = "ambient"):
+    def trace(self, rays: np.ndarray, variant: int, center, fast: bool = True, geom: str = "ambient", direct: bool = True, lockstep: bool = True):
         """-> (hit records, probes that read the volume, total probe count)"""
         rays = np.ascontiguousarray(rays)
         n = len(rays)
         out = np.zeros(n, HIT_DTYPE)
         c = np.asarray(center, np.int32)
         cnt = np.zeros(2, np.uint64)
-        lib().emul_trace(self.h, rays.ctypes.data, n, int(variant), c.ctypes.data, int(fast), self.GEOMS[geom], out.ctypes.data, cnt.ctypes.data)
+        lib().emul_trace(self.h, rays.ctypes.data, n, int(variant), c.ctypes.data, int(fast), self.GEOMS[geom], int(direct), int(lockstep), out.ctypes.data, cnt.ctypes.data)
         return out, int(cnt[0]), int(cnt[1])
 
     def close(self):

@@ -72,6 +72,9 @@ def test_emulated_tile_march_matches_oracle_on_pass_like_rays(oracle, terrain, e
         got, fetched, steps = emul.trace(rays, variant, center, geom=geom)
         _compare(got, want)
         assert steps == int(want["steps"].sum())
+        got2, fetched2, _ = emul.trace(rays, variant, center, geom=geom, direct=False, lockstep=False)   # bounds-checked fetch, per-lane exit
+        _compare(got2, want)
+        assert fetched2 == fetched
         total_fetched += fetched
         total_steps += steps
     # the tile really engages: most probes are answered by a clear occupancy bit

@@ -30,19 +30,10 @@ struct BitTile {
     const uint32_t* w;     // [TY][TY][TW] words; bit (x & 31) of word x >> 5
     int ox, oy, oz;        // tile origin, cells
     bool enabled;
+    bool direct;           // texels of occupied cells can be fetched without bounds checks and with 32-bit offsets:
+                           // volume dims are multiples of the cell's texel edge and the volume is < 4 GiB
+    unsigned koff;         // folded constant of the direct texel offset (see TileAddr::texel_offset)
 };
-
-// floor(p / 2^SHIFT) for 0 <= p < 2^(23+SHIFT)
-template <int SHIFT>
-VXL_DI int cell_floor(float p) {
-#ifdef __CUDA_ARCH__
-    // p + 2^(23+SHIFT), rounded toward zero, lies on the grid of spacing 2^SHIFT: its mantissa is the quotient
-    constexpr int MB = 0x4B000000 + (SHIFT << 23);
-    return __float_as_int(__fadd_rz(p, __int_as_float(MB))) - MB;
-#else
-    return (int)floorf(p * (1.0f / (float)(1 << SHIFT)));
-#endif
-}
 
 VXL_DI float3 fma3(float3 s, float k, float3 o) {
 #ifdef __CUDA_ARCH__
@@ -52,34 +43,64 @@ VXL_DI float3 fma3(float3 s, float k, float3 o) {
 #endif
 }
 
-// Tile lookup with the constant parts of the address folded once per ray:
-//   raw_a = bits of (p_a + 2^(23+SHIFT)) rounded toward zero = MB + floor(p_a / cell)
-//   word  = ((raw_z - MB - oz) * TY + (raw_y - MB - oy)) * TW + ((raw_x - MB - ox) >> 5)
-//         = raw_z * (TY*TW) + raw_y * TW + ((raw_x - kx) >> 5) + c0          (32-bit wrap-around arithmetic)
+// bits of (p + m) rounded toward zero.  With m = 2^(23+S) - o*2^S (exactly representable) and
+// o*2^S <= p < (o + 2^23) * 2^S the exact sum lies in [2^(23+S), 2^(24+S)), whose floats are spaced 2^S apart,
+// so the result is 2^(23+S) + 2^S * (floor(p / 2^S) - o): the mantissa field holds the cell index relative to o.
+VXL_DI unsigned magic_floor_bits(float p, float m, int S, int o) {
+#ifdef __CUDA_ARCH__
+    (void)S; (void)o;
+    return __float_as_uint(__fadd_rz(p, m));
+#else
+    (void)m;
+    return (unsigned)(0x4B000000 + (S << 23)) + (unsigned)((int)floorf(p * (1.0f / (float)(1 << S))) - o);
+#endif
+}
+
+// Tile lookup with everything constant folded once per ray:
+//   b_a  = MB + rel_a                      (MB = 0x4B000000 + (SHIFT << 23), a multiple of 32)
+//   word = rel_z * (TY*TW) + rel_y * TW + (rel_x >> 5) = b_z * (TY*TW) + b_y * TW + (b_x >> 5) - CC      (mod 2^32)
+//   bit  = rel_x & 31 = b_x & 31
 template <int SHIFT, int TY, int TW>
 struct TileAddr {
+    static constexpr unsigned MB = 0x4B000000u + ((unsigned)SHIFT << 23);
+    static constexpr unsigned CC = MB * (unsigned)(TY * TW) + MB * (unsigned)TW + (MB >> 5);
+    static constexpr unsigned MB1 = 0x4B000000u + (1u << 23);       // texel grid (2 voxels)
     const uint32_t* w;
-    int kx, c0;
+    unsigned sbase;        // device: shared-window byte address of w[-CC] (wraps mod 2^32)
+    float mx, my, mz;      // 2^(23+SHIFT) - o_a * 2^SHIFT
+    int ox, oy, oz;
     VXL_DI TileAddr(const BitTile& T) {
-        constexpr int MB = 0x4B000000 + (SHIFT << 23);
-        w = T.w;
-        kx = MB + T.ox;
-        c0 = (int)(0u - (unsigned)(MB + T.oz) * (unsigned)(TY * TW) - (unsigned)(MB + T.oy) * (unsigned)TW);
-    }
-    // non-zero iff the occupancy bit of the cell containing p is set
-    VXL_DI unsigned test(float3 p) const {
+        const float M = (float)(1 << 23) * (float)(1 << SHIFT), cell = (float)(1 << SHIFT);
+        w = T.w; ox = T.ox; oy = T.oy; oz = T.oz;
+        mx = M - (float)T.ox * cell; my = M - (float)T.oy * cell; mz = M - (float)T.oz * cell;
 #ifdef __CUDA_ARCH__
-        constexpr float M = (float)(1 << 23) * (float)(1 << SHIFT);
-        const int bx = __float_as_int(__fadd_rz(p.x, M)), by = __float_as_int(__fadd_rz(p.y, M)), bz = __float_as_int(__fadd_rz(p.z, M));
+        sbase = (unsigned)__cvta_generic_to_shared(T.w) - 4u * CC;
+        asm volatile("" : "+r"(sbase));      // keep the folded base in one register (one LEA per lookup)
 #else
-        constexpr int MB = 0x4B000000 + (SHIFT << 23);
-        const int bx = MB + (int)floorf(p.x * (1.0f / (float)(1 << SHIFT))), by = MB + (int)floorf(p.y * (1.0f / (float)(1 << SHIFT))),
-                  bz = MB + (int)floorf(p.z * (1.0f / (float)(1 << SHIFT)));
+        sbase = 0;
 #endif
-        const int rx = bx - kx;
-        const unsigned idx = (unsigned)bz * (unsigned)(TY * TW) + (unsigned)by * (unsigned)TW + (unsigned)(rx >> 5) + (unsigned)c0;
-        return w[idx] & (1u << (rx & 31));
     }
+    // non-zero iff the occupancy bit of the cell containing p is set (p inside the tile)
+    VXL_DI unsigned test(float3 p) const {
+        const unsigned bx = magic_floor_bits(p.x, mx, SHIFT, ox), by = magic_floor_bits(p.y, my, SHIFT, oy), bz = magic_floor_bits(p.z, mz, SHIFT, oz);
+#ifdef __CUDA_ARCH__
+        const unsigned idx = bz * (unsigned)(TY * TW) + by * (unsigned)TW + (bx >> 5);
+        unsigned word, mask;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(sbase + 4u * idx));
+        asm("shf.l.wrap.b32 %0, 0, 1, %1;" : "=r"(mask) : "r"(bx));       // high word of {1:0} << (bx & 31) = 1 << (bx & 31); opaque so it stays a mask test
+        return word & mask;
+#else
+        const unsigned idx = bz * (unsigned)(TY * TW) + by * (unsigned)TW + (bx >> 5) - CC;
+        return w[idx] & (1u << (bx & 31));
+#endif
+    }
+    // byte offset of the texel containing p (p >= 0, inside the volume): floor(p/2) per axis, x fastest
+    static VXL_DI unsigned texel_offset(const VolView& V, unsigned koff, float3 p) {
+        const float M1 = 16777216.0f;                               // 2^24: grid of 2 voxels
+        const unsigned tx = magic_floor_bits(p.x, M1, 1, 0), ty = magic_floor_bits(p.y, M1, 1, 0), tz = magic_floor_bits(p.z, M1, 1, 0);
+        return tz * (unsigned)(V.sx * V.sy) + ty * (unsigned)V.sx + tx - koff;
+    }
+    static VXL_DI unsigned texel_koff(const VolView& V) { return MB1 * (unsigned)(V.sx * V.sy) + MB1 * (unsigned)V.sx + MB1; }
 };
 
 template <bool SUPER>
@@ -93,9 +114,21 @@ VXL_DI int phase2_count(float lim) {
     return n;
 }
 
+VXL_DI bool warp_any(bool p) {
+#ifdef __CUDA_ARCH__
+    return __any_sync(__activemask(), p);
+#else
+    return p;
+#endif
+}
+
 // SUPER = false: raycastShadowVolumeSparse (step 0.5 then 1); true: ...SuperSparse (step 2.5 then 5).
 // `fetched` counts probes that had to read the volume (diagnostics).
-template <bool SUPER, bool RECORD, int SHIFT, int TY, int TW>
+// LOCKSTEP: a lane whose ray has hit keeps walking with its tests masked off (live = 0) instead of leaving the
+// loop, so the loop has one trip count for the whole warp (a compile-time constant when `dist` is a literal) and
+// no data-dependent exit; the other lanes of the warp would have kept the issue slots busy anyway.  Every 8
+// probes the warp leaves early if no lane is live.  Use it when `dist` is warp-uniform.
+template <bool SUPER, bool RECORD, bool LOCKSTEP, int SHIFT, int TY, int TW>
 VXL_DI float march_bits(const VolView& V, const BitTile& T, float3 origin, float3 dir, float dist, int& steps_out,
                         MarchResult* rec, unsigned& fetched) {
     constexpr float step0 = SUPER ? 2.5f : 0.5f;
@@ -123,56 +156,76 @@ VXL_DI float march_bits(const VolView& V, const BitTile& T, float3 origin, float
     float3 stepDir = dir * step0;
     float3 pos = origin;
 
+    // A set occupancy bit drops into the reference's fetch + test right there, which is short when the texel can
+    // be addressed directly.  The loops only record the hit index; everything derived from it comes after the loop.
+    unsigned live = 0xFFFFFFFFu;
+    float3 hpos = pos;
     // ---- phase 1 (:138-154): fine steps, position-hashed bit of the texel ----
-    int k = 0;
-    while (true) {
-        // tight scan: advance while the cell's occupancy bit is clear
-        while (k < n1 && !A.test(pos)) { pos = pos + stepDir; ++k; }
-        if (k >= n1) break;
-        {
+    int hit1 = -1;
+    unsigned hbit = 0u;
+#pragma unroll 2
+    for (int k = 0; k < n1; ++k) {
+        if (A.test(pos) & live) {
             ++fetched;
-            const int tx = f2i(pos.x / 2.0f), ty = f2i(pos.y / 2.0f), tz = f2i(pos.z / 2.0f);
-            const unsigned v = fetch_texel(V, tx, ty, tz);
-            unsigned bit = 0u;
-            bit += gmod(pos.x, 0.5f) > 0.25f ? 1u : 0u;
-            bit += gmod(pos.y, 0.5f) > 0.25f ? 2u : 0u;
-            bit += gmod(pos.z, 0.5f) > 0.25f ? 4u : 0u;
-            if ((v >> bit) & 1u) {
-                steps_out += k + 1;
-                const float d = step0 * (float)(k + 1);
-                if (RECORD) {
-                    rec->d = d; rec->steps = k + 1; rec->status = 1;
-                    rec->vx = tx * 2 + (int)(bit & 1u); rec->vy = ty * 2 + (int)((bit >> 1) & 1u); rec->vz = tz * 2 + (int)((bit >> 2) & 1u);
-                    rec->pos = pos;
+            unsigned v;
+            if (T.direct) v = V.bytes[TileAddr<SHIFT, TY, TW>::texel_offset(V, T.koff, pos)];
+            else v = fetch_texel(V, f2i(pos.x / 2.0f), f2i(pos.y / 2.0f), f2i(pos.z / 2.0f));
+            if (v != 0u) {
+                unsigned bit = 0u;
+                bit += gmod(pos.x, 0.5f) > 0.25f ? 1u : 0u;
+                bit += gmod(pos.y, 0.5f) > 0.25f ? 2u : 0u;
+                bit += gmod(pos.z, 0.5f) > 0.25f ? 4u : 0u;
+                if ((v >> bit) & 1u) {
+                    hit1 = k; hbit = bit;
+                    if (RECORD) hpos = pos;
+                    if (LOCKSTEP) live = 0u; else break;
                 }
-                return d;
             }
         }
-        pos = pos + stepDir; ++k;
+        pos = pos + stepDir;
+        if (LOCKSTEP && !SUPER && (k & 7) == 7 && !warp_any(live != 0u)) break;
+    }
+    if (hit1 >= 0) {
+        steps_out += hit1 + 1;
+        const float d = step0 * (float)(hit1 + 1);
+        if (RECORD) {
+            const int tx = f2i(hpos.x / 2.0f), ty = f2i(hpos.y / 2.0f), tz = f2i(hpos.z / 2.0f);
+            rec->d = d; rec->steps = hit1 + 1; rec->status = 1;
+            rec->vx = tx * 2 + (int)(hbit & 1u); rec->vy = ty * 2 + (int)((hbit >> 1) & 1u); rec->vz = tz * 2 + (int)((hbit >> 2) & 1u);
+            rec->pos = hpos;
+        }
+        return d;
     }
 
     // ---- phase 2 (:156-170): doubled steps, byte != 0 ----
     stepDir = stepDir * 2.0f;
     const int n2 = phase2_count<SUPER>(lim);
-    int j = 0;
-    while (true) {
-        while (j < n2 && !A.test(pos)) { pos = pos + stepDir; ++j; }
-        if (j >= n2) break;
-        {
+    int hit2 = -1;
+#pragma unroll 2
+    for (int j = 0; j < n2; ++j) {
+        if (A.test(pos) & live) {
             ++fetched;
-            const int px = f2i(pos.x), py = f2i(pos.y), pz = f2i(pos.z);
-            if (fetch_texel(V, px / 2, py / 2, pz / 2) != 0u) {   // getVolumeAt(ivec3(pos), 1)
-                steps_out += n1 + j + 1;
-                const float d = d0 + step2 * (float)j;
-                if (RECORD) {
-                    rec->d = d; rec->steps = n1 + j + 1; rec->status = 2;
-                    rec->vx = px; rec->vy = py; rec->vz = pz;
-                    rec->pos = pos;
-                }
-                return d;
+            unsigned v;
+            if (T.direct) v = V.bytes[TileAddr<SHIFT, TY, TW>::texel_offset(V, T.koff, pos)];
+            else { const int px = f2i(pos.x), py = f2i(pos.y), pz = f2i(pos.z); v = fetch_texel(V, px / 2, py / 2, pz / 2); }   // getVolumeAt(ivec3(pos), 1)
+            if (v != 0u) {
+                hit2 = j;
+                if (RECORD) hpos = pos;
+                if (LOCKSTEP) live = 0u; else break;
             }
         }
-        pos = pos + stepDir; ++j;
+        pos = pos + stepDir;
+        if (LOCKSTEP && (j & 7) == 7 && !warp_any(live != 0u)) break;
+    }
+    if (hit2 >= 0) {
+        steps_out += n1 + hit2 + 1;
+        const float d = d0 + step2 * (float)hit2;
+        if (RECORD) {
+            rec->d = d; rec->steps = n1 + hit2 + 1; rec->status = 2;
+            rec->vx = f2i(hpos.x); rec->vy = f2i(hpos.y); rec->vz = f2i(hpos.z);
+            rec->pos = hpos;
+        }
+        return d;
     }
     steps_out += n1 + n2;
     if (RECORD) { rec->d = dist; rec->steps = n1 + n2; rec->status = 0; rec->vx = rec->vy = rec->vz = 0; rec->pos = make_float3(0.f, 0.f, 0.f); }
@@ -187,17 +240,20 @@ __device__ __forceinline__ void stage_bits(uint32_t* __restrict__ dst, const Bit
     const int w0 = ox >> 5;                                 // arithmetic shift: floor for negatives
     const int sh = ox & 31;
     const int words_x = M.pitch - 1;                        // the spare word of each row is zero
-    for (int i = threadIdx.x; i < TY * TY * TW; i += blockDim.x) {
-        const int xw = i % TW, y = (i / TW) % TY, z = i / (TW * TY);
+    for (int r = threadIdx.x; r < TY * TY; r += blockDim.x) {   // one tile row (TW words) per iteration
+        const int z = r / TY, y = r - z * TY;
         const int ay = oy + y, az = oz + z;
-        uint32_t a = 0u, b = 0u;
+        uint32_t g[TW + 1];
+#pragma unroll
+        for (int k = 0; k <= TW; ++k) g[k] = 0u;
         if ((unsigned)ay < (unsigned)M.cy && (unsigned)az < (unsigned)M.cz) {
             const uint32_t* row = M.words + ((size_t)az * M.cy + ay) * M.pitch;
-            const int wa = w0 + xw, wb = wa + 1;
-            if ((unsigned)wa < (unsigned)words_x) a = __ldg(row + wa);
-            if ((unsigned)wb < (unsigned)words_x) b = __ldg(row + wb);
+#pragma unroll
+            for (int k = 0; k <= TW; ++k)
+                if ((unsigned)(w0 + k) < (unsigned)words_x) g[k] = __ldg(row + w0 + k);
         }
-        dst[i] = __funnelshift_r(a, b, sh);                 // sh == 0 returns a
+#pragma unroll
+        for (int k = 0; k < TW; ++k) dst[r * TW + k] = __funnelshift_r(g[k], g[k + 1], sh);   // sh == 0 returns g[k]
     }
 }
 #endif

@@ -116,6 +116,9 @@ template <bool FAST, typename G>
 __device__ __forceinline__ BitTile block_prologue(const VolView& V, BlockShared<G::TY, G::TW>& S, bool valid, float3 hint) {
     BitTile T;
     T.w = S.tile; T.ox = T.oy = T.oz = 0; T.enabled = false;
+    constexpr int TPC = 1 << (G::SHIFT - 1);                // texels per cell edge
+    T.direct = (V.sx % TPC == 0) && (V.sy % TPC == 0) && (V.sz % TPC == 0) && ((unsigned long long)V.sx * V.sy * V.sz < (1ull << 32));
+    T.koff = TileAddr<G::SHIFT, G::TY, G::TW>::texel_koff(V);
     if (threadIdx.x < 3) { S.bb[threadIdx.x] = 0x7fffffff; S.bb[3 + threadIdx.x] = -0x7fffffff - 1; }
     if (threadIdx.x < 4) S.acc[threadIdx.x] = 0u;
     __syncthreads();
@@ -140,9 +143,11 @@ __device__ __forceinline__ BitTile block_prologue(const VolView& V, BlockShared<
     return T;
 }
 
-template <bool FAST, bool SUPER, typename G>
+// UNIFORM: `dist` is the same for every lane of the warp, which allows the masked-lane lockstep loops of
+// march_bits.  Measured slower than per-lane exits on config 3 (profiles/r1e vs r1d), so the passes use false.
+template <bool FAST, bool SUPER, bool UNIFORM, typename G>
 __device__ __forceinline__ float ray_march(const VolView& V, const BitTile& T, float3 origin, float3 dir, float dist, int& steps, unsigned& fetched) {
-    if (FAST) return march_bits<SUPER, false, G::SHIFT, G::TY, G::TW>(V, T, origin, dir, dist, steps, nullptr, fetched);
+    if (FAST) return march_bits<SUPER, false, UNIFORM, G::SHIFT, G::TY, G::TW>(V, T, origin, dir, dist, steps, nullptr, fetched);
     return march<false>(V, origin, dir, dist, SUPER ? 2.5f : 0.5f, steps, nullptr);
 }
 
@@ -206,7 +211,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_ambient(VolView V, FrameVi
             wcp = wcp + randomVec * 2.5f;                                              // :156
             const float3 origin = wcp + normal * bias;
             if (out_shadow) {
-                if (ray_march<FAST, false, G>(V, C, origin, wd, 128.0f, steps, exact) != 128.0f) shadow = 0.0f;   // :167-169
+                if (ray_march<FAST, false, false, G>(V, C, origin, wd, 128.0f, steps, exact) != 128.0f) shadow = 0.0f;   // :167-169
                 rays += 1;
             }
             if (out_ao && n_ao > 0) {
@@ -218,7 +223,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_ambient(VolView V, FrameVi
                     const uint32_t ni = (i == 0) ? n : get_noise(F, K, p, i);
                     const float3 rv = cosine_sample_hemisphere(S.lut, ni, ni >> 8);                       // :118
                     const float3 dir = tangent * rv.x + bitangent * rv.y + normal * rv.z;                 // :119
-                    const float d = ray_march<FAST, true, G>(V, C, origin, dir, 128.0f, steps, exact) / 128.0f;   // :121
+                    const float d = ray_march<FAST, true, false, G>(V, C, origin, dir, 128.0f, steps, exact) / 128.0f;   // :121
                     acc += d * d;
                 }
                 ao = (acc / (float)n_ao) * 0.05f;                                                         // :125
@@ -248,15 +253,23 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_local_lights(VolView V, Fr
     load_luts(S.lut, g_lut);
     constexpr int STRIDE = SPOT ? 16 : 8;
     for (int i = threadIdx.x; i < n_lights * 4; i += blockDim.x) s_light[i] = lights[(i >> 2) * STRIDE + (i & 3)];
+    __syncthreads();
     const PixelCtx p = pixel_ctx(F, K);
     float3 normal = make_float3(0.f, 0.f, 0.f), worldPos = make_float3(0.f, 0.f, 0.f);
-    bool hint_ok = false;   // sky pixels are shaded like any other (no depth test here) but must not stretch the tile placement
+    // Tile placement considers the pixels that will cast a ray from the scene: not sky (which the reference shades
+    // like any other pixel -- no depth test here -- but whose world position is ~40000 voxels away) and inside
+    // some light's range.  A block without such pixels stages nothing.
+    bool hint_ok = false;
     if (p.valid) {
         const float depth = unorm24(__ldg(F.depth24 + p.idx));
-        hint_ok = depth < 0.999f;
         const float3 pos = p.farvec * (depth * (1.0f + 1.0f / FAR_));                        // LightPoint.frag:89
         normal = decode_normal(__ldg(F.normal + p.idx));                                     // :90
         worldPos = xyz(mat_mul(K.InvView, make_float4(pos.x, pos.y, pos.z, 1.0f)));          // :95
+        if (depth < 0.999f)
+            for (int li = 0; li < n_lights && !hint_ok; ++li) {
+                const float3 L = make_float3(s_light[li * 4], s_light[li * 4 + 1], s_light[li * 4 + 2]) - worldPos;
+                hint_ok = !(length3(L) > s_light[li * 4 + 3]);
+            }
     }
     const BitTile C = block_prologue<FAST, G>(V, S, hint_ok, worldPos * 10.0f);
     unsigned rays = 0, pixels = 0, exact = 0;
@@ -281,7 +294,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_local_lights(VolView V, Fr
                 wd = normalize3(wd);                                                         // :114
                 wcp = wcp + wd * nw;                                                         // :115
                 wcp = wcp + rv0 * 2.5f;                                                      // :116
-                if (ray_march<FAST, SPOT, G>(V, C, wcp + normal * 0.5f, wd, hitDist, steps, exact) < hitDist) shadow = 0.0f;   // :125
+                if (ray_march<FAST, SPOT, false, G>(V, C, wcp + normal * 0.5f, wd, hitDist, steps, exact) < hitDist) shadow = 0.0f;   // :125
                 rays += 1;
                 pixels = 1;
             }
@@ -334,7 +347,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_reflection(VolView V, Fram
             const float nw = unorm8(n >> 24);
             wcp = wcp + normal * nw;                                                         // :97
             wd = wd * (1.0f + nw * 0.5f);                                                    // :98
-            t = ray_march<FAST, false, G>(V, C, wcp + normal, wd, 256.0f, steps, exact);        // :113
+            t = ray_march<FAST, false, false, G>(V, C, wcp + normal, wd, 256.0f, steps, exact);        // :113
             rays = 1; pixels = 1;
         }
         out_t[p.idx] = t;
