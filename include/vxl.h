@@ -146,9 +146,10 @@ int vxl_stats_read(vxl_ctx* ctx, vxl_stats* out /* HOST */);
 int vxl_launch_count(vxl_ctx* ctx, uint64_t* out /* HOST */);
 
 /* diagnostics (no reference counterpart): kernel variant 0 = plain march on the volume bytes, 1 = march
- * against the per-block occupancy-bit tile in shared memory (default; also env VXL_VARIANT); both
- * produce identical results.  vxl_debug_fetched_probes: probes of variant 1 that had to read the volume
- * since the last vxl_stats_reset (the others were answered by a clear occupancy bit). */
+ * against the per-block occupancy-bit tile in shared memory (default; also env VXL_VARIANT), 2 = variant 1
+ * that also counts the probes that had to read the volume; all produce identical results.
+ * vxl_debug_fetched_probes: that count since the last vxl_stats_reset (variant 2 only; the other probes
+ * were answered by a clear occupancy bit). */
 int vxl_debug_set_variant(vxl_ctx* ctx, int variant);
 int vxl_debug_fetched_probes(vxl_ctx* ctx, uint64_t* out /* HOST */);
 /* download one occupancy level (shift 2: 4-voxel cells, 3: 8-voxel cells) unpacked to 0/1 bytes

@@ -77,11 +77,11 @@ void trace_geom(Emul* e, const float* rays, long long n, int variant, const int*
         unsigned fetched = 0;
         const float3 o = make_float3(r[0], r[1], r[2]), d = make_float3(r[3], r[4], r[5]);
         if (lockstep) {
-            if (variant == 0) march_bits<false, true, true, SHIFT, TY, TW>(V, T, o, d, r[6], steps, &M, fetched);
-            else march_bits<true, true, true, SHIFT, TY, TW>(V, T, o, d, r[6], steps, &M, fetched);
+            if (variant == 0) march_bits<false, true, true, true, SHIFT, TY, TW>(V, T, o, d, r[6], steps, &M, fetched);
+            else march_bits<true, true, true, true, SHIFT, TY, TW>(V, T, o, d, r[6], steps, &M, fetched);
         } else {
-            if (variant == 0) march_bits<false, true, false, SHIFT, TY, TW>(V, T, o, d, r[6], steps, &M, fetched);
-            else march_bits<true, true, false, SHIFT, TY, TW>(V, T, o, d, r[6], steps, &M, fetched);
+            if (variant == 0) march_bits<false, true, false, true, SHIFT, TY, TW>(V, T, o, d, r[6], steps, &M, fetched);
+            else march_bits<true, true, false, true, SHIFT, TY, TW>(V, T, o, d, r[6], steps, &M, fetched);
         }
         vxl_hit hh;
         memset(&hh, 0, sizeof hh);

@@ -355,12 +355,12 @@ def test_occupancy_levels_match_block_maxima(gpu_ctx, oracle, texels):
 
 
 def test_plain_and_tile_kernels_agree_and_the_tile_engages(gpu_ctx, oracle, terrain):
-    """Variant 0 (plain march on the bytes) and variant 1 (occupancy-bit tile, default) give the same bits and the
-    same probe counts; variant 1 reads the volume for only a fraction of the probes."""
+    """Variant 0 (plain march on the bytes), 1 (occupancy-bit tile, default) and 2 (tile + read counter) give the
+    same bits and the same probe counts; the tile march reads the volume for only a fraction of the probes."""
     E = _eng()
     vol, gb = _upload_scene(gpu_ctx, terrain)
     res = {}
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         gpu_ctx.set_variant(variant)
         gpu_ctx.stats_reset()
         sh, ao = E.LightAmbientPipeline.Get().Use(terrain["view"], gb, vol, n_ao=8)
@@ -371,8 +371,9 @@ def test_plain_and_tile_kernels_agree_and_the_tile_engages(gpu_ctx, oracle, terr
         st = gpu_ctx.stats()
         res[variant] = (sh.cpu().numpy(), ao.cpu().numpy(), t.cpu().numpy(), pt.cpu().numpy(), st, gpu_ctx.fetched_probes())
     gpu_ctx.set_variant(1)
-    for a, b in zip(res[0][:4], res[1][:4]):
-        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
-    assert res[0][4] == res[1][4]
-    assert res[0][5] == 0 and 0 < res[1][5] < 0.5 * res[1][4]["steps"], (res[1][5], res[1][4])
+    for v in (1, 2):
+        for a, b in zip(res[0][:4], res[v][:4]):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        assert res[0][4] == res[v][4]
+    assert res[0][5] == 0 and res[1][5] == 0 and 0 < res[2][5] < 0.5 * res[2][4]["steps"], (res[2][5], res[2][4])
     vol.close()

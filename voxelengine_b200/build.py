@@ -49,7 +49,8 @@ def nvcc_path() -> str:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return OUT
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + sources()
+    extra = os.environ.get("VXL_NVCC_EXTRA", "").split()      # experiments only, e.g. -DVXL_AMBIENT_BLOCKS=3
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + sources()
     env = dict(os.environ)
     if os.path.exists("/usr/bin/g++"):
         cmd[1:1] = ["-ccbin", "/usr/bin/g++"]

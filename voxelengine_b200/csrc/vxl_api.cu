@@ -142,7 +142,7 @@ int vxl_stats_read(vxl_ctx* c, vxl_stats* out) {
 }
 
 int vxl_debug_set_variant(vxl_ctx* c, int variant) {
-    if (!c || variant < 0 || variant > 1) { set_error("vxl_debug_set_variant: bad argument"); return VXL_ERR_INVALID; }
+    if (!c || variant < 0 || variant > 2) { set_error("vxl_debug_set_variant: bad argument"); return VXL_ERR_INVALID; }
     c->variant = variant;
     return VXL_OK;
 }

@@ -128,7 +128,8 @@ VXL_DI bool warp_any(bool p) {
 // loop, so the loop has one trip count for the whole warp (a compile-time constant when `dist` is a literal) and
 // no data-dependent exit; the other lanes of the warp would have kept the issue slots busy anyway.  Every 8
 // probes the warp leaves early if no lane is live.  Use it when `dist` is warp-uniform.
-template <bool SUPER, bool RECORD, bool LOCKSTEP, int SHIFT, int TY, int TW>
+// COUNT: maintain `fetched` (diagnostic kernels only).
+template <bool SUPER, bool RECORD, bool LOCKSTEP, bool COUNT, int SHIFT, int TY, int TW>
 VXL_DI float march_bits(const VolView& V, const BitTile& T, float3 origin, float3 dir, float dist, int& steps_out,
                         MarchResult* rec, unsigned& fetched) {
     constexpr float step0 = SUPER ? 2.5f : 0.5f;
@@ -166,7 +167,7 @@ VXL_DI float march_bits(const VolView& V, const BitTile& T, float3 origin, float
 #pragma unroll 2
     for (int k = 0; k < n1; ++k) {
         if (A.test(pos) & live) {
-            ++fetched;
+            if (COUNT) ++fetched;
             unsigned v;
             if (T.direct) v = V.bytes[TileAddr<SHIFT, TY, TW>::texel_offset(V, T.koff, pos)];
             else v = fetch_texel(V, f2i(pos.x / 2.0f), f2i(pos.y / 2.0f), f2i(pos.z / 2.0f));
@@ -204,7 +205,7 @@ VXL_DI float march_bits(const VolView& V, const BitTile& T, float3 origin, float
 #pragma unroll 2
     for (int j = 0; j < n2; ++j) {
         if (A.test(pos) & live) {
-            ++fetched;
+            if (COUNT) ++fetched;
             unsigned v;
             if (T.direct) v = V.bytes[TileAddr<SHIFT, TY, TW>::texel_offset(V, T.koff, pos)];
             else { const int px = f2i(pos.x), py = f2i(pos.y), pz = f2i(pos.z); v = fetch_texel(V, px / 2, py / 2, pz / 2); }   // getVolumeAt(ivec3(pos), 1)
@@ -217,19 +218,17 @@ VXL_DI float march_bits(const VolView& V, const BitTile& T, float3 origin, float
         pos = pos + stepDir;
         if (LOCKSTEP && (j & 7) == 7 && !warp_any(live != 0u)) break;
     }
-    if (hit2 >= 0) {
-        steps_out += n1 + hit2 + 1;
-        const float d = d0 + step2 * (float)hit2;
-        if (RECORD) {
-            rec->d = d; rec->steps = n1 + hit2 + 1; rec->status = 2;
-            rec->vx = f2i(hpos.x); rec->vy = f2i(hpos.y); rec->vz = f2i(hpos.z);
-            rec->pos = hpos;
-        }
-        return d;
+    // single exit: everything below is arithmetic on the recorded hit index
+    const bool h2 = hit2 >= 0;
+    const int nsteps = h2 ? n1 + hit2 + 1 : n1 + n2;
+    const float d = h2 ? d0 + step2 * (float)hit2 : dist;
+    steps_out += nsteps;
+    if (RECORD) {
+        rec->d = d; rec->steps = nsteps; rec->status = h2 ? 2 : 0;
+        rec->vx = h2 ? f2i(hpos.x) : 0; rec->vy = h2 ? f2i(hpos.y) : 0; rec->vz = h2 ? f2i(hpos.z) : 0;
+        rec->pos = h2 ? hpos : make_float3(0.f, 0.f, 0.f);
     }
-    steps_out += n1 + n2;
-    if (RECORD) { rec->d = dist; rec->steps = n1 + n2; rec->status = 0; rec->vx = rec->vy = rec->vz = 0; rec->pos = make_float3(0.f, 0.f, 0.f); }
-    return dist;
+    return d;
 }
 
 // Stage the TW*32 x TY x TY-cell window of an occupancy level whose origin cell is (ox, oy, oz).

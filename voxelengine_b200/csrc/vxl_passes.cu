@@ -19,6 +19,9 @@ constexpr float GOLDEN_RATIO = 2.118033988749895f;  // Common.frag:9 (sic)
 
 constexpr int BLOCK_W = 32, BLOCK_H = 16;           // pixels per thread block (16 warps of 8x4)
 constexpr int BLOCK_THREADS = BLOCK_W * BLOCK_H;
+#ifndef VXL_AMBIENT_BLOCKS
+#define VXL_AMBIENT_BLOCKS 2      // resident blocks per SM the register allocation of k_ambient is capped for
+#endif
 
 struct ViewK { float InvView[16], View[16], InvProj[16]; int Frame; };
 
@@ -145,9 +148,10 @@ __device__ __forceinline__ BitTile block_prologue(const VolView& V, BlockShared<
 
 // UNIFORM: `dist` is the same for every lane of the warp, which allows the masked-lane lockstep loops of
 // march_bits.  Measured slower than per-lane exits on config 3 (profiles/r1e vs r1d), so the passes use false.
-template <bool FAST, bool SUPER, bool UNIFORM, typename G>
+// MODE: 0 plain march on the bytes, 1 tile march, 2 tile march that also counts the probes that read the volume
+template <int MODE, bool SUPER, bool UNIFORM, typename G>
 __device__ __forceinline__ float ray_march(const VolView& V, const BitTile& T, float3 origin, float3 dir, float dist, int& steps, unsigned& fetched) {
-    if (FAST) return march_bits<SUPER, false, UNIFORM, G::SHIFT, G::TY, G::TW>(V, T, origin, dir, dist, steps, nullptr, fetched);
+    if (MODE > 0) return march_bits<SUPER, false, UNIFORM, MODE == 2, G::SHIFT, G::TY, G::TW>(V, T, origin, dir, dist, steps, nullptr, fetched);
     return march<false>(V, origin, dir, dist, SUPER ? 2.5f : 0.5f, steps, nullptr);
 }
 
@@ -171,8 +175,8 @@ __device__ __forceinline__ void flush_stats(BS& S, unsigned long long* __restric
 // -------------------------------------------------------------------------------------------------
 // LightAmbient.frag:134-175 + calculateAmbientIrradiance :111-126
 // -------------------------------------------------------------------------------------------------
-template <bool FAST>
-__global__ void __launch_bounds__(BLOCK_THREADS, 2) k_ambient(VolView V, FrameView F, ViewK K, const float* __restrict__ g_lut, int n_ao,
+template <int MODE>
+__global__ void __launch_bounds__(BLOCK_THREADS, VXL_AMBIENT_BLOCKS) k_ambient(VolView V, FrameView F, ViewK K, const float* __restrict__ g_lut, int n_ao,
                                                  float* __restrict__ out_shadow, float* __restrict__ out_ao,
                                                  unsigned long long* __restrict__ g_stats) {
     typedef AmbientGeom G;
@@ -194,7 +198,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_ambient(VolView V, FrameVi
             bias = gsmoothstep(0.0f, 0.2f, depth) * 50.0f + 1.5f;                      // :158
         }
     }
-    const BitTile C = block_prologue<FAST, G>(V, S, lit, wcp0 + normal * bias);
+    const BitTile C = block_prologue<(MODE > 0), G>(V, S, lit, wcp0 + normal * bias);
     unsigned rays = 0, pixels = 0, exact = 0;
     int steps = 0;
     if (p.valid) {
@@ -211,7 +215,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_ambient(VolView V, FrameVi
             wcp = wcp + randomVec * 2.5f;                                              // :156
             const float3 origin = wcp + normal * bias;
             if (out_shadow) {
-                if (ray_march<FAST, false, false, G>(V, C, origin, wd, 128.0f, steps, exact) != 128.0f) shadow = 0.0f;   // :167-169
+                if (ray_march<MODE, false, false, G>(V, C, origin, wd, 128.0f, steps, exact) != 128.0f) shadow = 0.0f;   // :167-169
                 rays += 1;
             }
             if (out_ao && n_ao > 0) {
@@ -223,7 +227,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_ambient(VolView V, FrameVi
                     const uint32_t ni = (i == 0) ? n : get_noise(F, K, p, i);
                     const float3 rv = cosine_sample_hemisphere(S.lut, ni, ni >> 8);                       // :118
                     const float3 dir = tangent * rv.x + bitangent * rv.y + normal * rv.z;                 // :119
-                    const float d = ray_march<FAST, true, false, G>(V, C, origin, dir, 128.0f, steps, exact) / 128.0f;   // :121
+                    const float d = ray_march<MODE, true, false, G>(V, C, origin, dir, 128.0f, steps, exact) / 128.0f;   // :121
                     acc += d * d;
                 }
                 ao = (acc / (float)n_ao) * 0.05f;                                                         // :125
@@ -241,7 +245,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_ambient(VolView V, FrameVi
 // LightPoint.frag:85-129 / LightSpot.frag:73-117 -- all lights of the list in one launch; the
 // G-buffer, noise and world position are read / derived once per pixel instead of once per light.
 // -------------------------------------------------------------------------------------------------
-template <bool SPOT, bool FAST>
+template <bool SPOT, int MODE>
 __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_local_lights(VolView V, FrameView F, ViewK K, const float* __restrict__ g_lut,
                                                       const float* __restrict__ lights, int n_lights,
                                                       float* __restrict__ out_shadow, size_t plane_stride,
@@ -271,7 +275,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_local_lights(VolView V, Fr
                 hint_ok = !(length3(L) > s_light[li * 4 + 3]);
             }
     }
-    const BitTile C = block_prologue<FAST, G>(V, S, hint_ok, worldPos * 10.0f);
+    const BitTile C = block_prologue<(MODE > 0), G>(V, S, hint_ok, worldPos * 10.0f);
     unsigned rays = 0, pixels = 0, exact = 0;
     int steps = 0;
     if (p.valid) {
@@ -294,7 +298,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_local_lights(VolView V, Fr
                 wd = normalize3(wd);                                                         // :114
                 wcp = wcp + wd * nw;                                                         // :115
                 wcp = wcp + rv0 * 2.5f;                                                      // :116
-                if (ray_march<FAST, SPOT, false, G>(V, C, wcp + normal * 0.5f, wd, hitDist, steps, exact) < hitDist) shadow = 0.0f;   // :125
+                if (ray_march<MODE, SPOT, false, G>(V, C, wcp + normal * 0.5f, wd, hitDist, steps, exact) < hitDist) shadow = 0.0f;   // :125
                 rays += 1;
                 pixels = 1;
             }
@@ -307,7 +311,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_local_lights(VolView V, Fr
 // -------------------------------------------------------------------------------------------------
 // LightReflection.frag:60-113
 // -------------------------------------------------------------------------------------------------
-template <bool FAST>
+template <int MODE>
 __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_reflection(VolView V, FrameView F, ViewK K, const float* __restrict__ g_lut,
                                                     float* __restrict__ out_t, unsigned long long* __restrict__ g_stats) {
     typedef ReflGeom G;
@@ -327,7 +331,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_reflection(VolView V, Fram
             wcp0 = xyz(mat_mul(K.InvView, make_float4(pos.x, pos.y, pos.z, 1.0f))) * 10.0f;  // :93
         }
     }
-    const BitTile C = block_prologue<FAST, G>(V, S, lit, wcp0 + normal);
+    const BitTile C = block_prologue<(MODE > 0), G>(V, S, lit, wcp0 + normal);
     unsigned rays = 0, pixels = 0, exact = 0;
     int steps = 0;
     if (p.valid) {
@@ -347,7 +351,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_reflection(VolView V, Fram
             const float nw = unorm8(n >> 24);
             wcp = wcp + normal * nw;                                                         // :97
             wd = wd * (1.0f + nw * 0.5f);                                                    // :98
-            t = ray_march<FAST, false, false, G>(V, C, wcp + normal, wd, 256.0f, steps, exact);        // :113
+            t = ray_march<MODE, false, false, G>(V, C, wcp + normal, wd, 256.0f, steps, exact);        // :113
             rays = 1; pixels = 1;
         }
         out_t[p.idx] = t;
@@ -407,12 +411,14 @@ int vxl_pass_ambient(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, const 
     if (!out_shadow && !out_ao) return VXL_OK;
     if (F.n_tiles == 0) return VXL_OK;
     if (vol->dirty) { if (int e = vxl_volume_build_occupancy(vol)) return e; }
-    if (ctx->variant == 0) {
-        k_ambient<false><<<grid_for(F), BLOCK_THREADS, smem_bytes<AmbientGeom, false>(), ctx->stream>>>(vol_view(vol), F, make_viewk(view), ctx->d_luts, n_ao, out_shadow, out_ao, ctx->d_stats);
-    } else {
-        VXL_CUDA(cudaFuncSetAttribute(k_ambient<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<AmbientGeom, true>()));
-        k_ambient<true><<<grid_for(F), BLOCK_THREADS, smem_bytes<AmbientGeom, true>(), ctx->stream>>>(vol_view(vol), F, make_viewk(view), ctx->d_luts, n_ao, out_shadow, out_ao, ctx->d_stats);
-    }
+#define VXL_AMB(MODE_)                                                                                                                  \
+    do {                                                                                                                            \
+        if (MODE_) VXL_CUDA(cudaFuncSetAttribute(k_ambient<MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<AmbientGeom, (MODE_ > 0)>())); \
+        k_ambient<MODE_><<<grid_for(F), BLOCK_THREADS, smem_bytes<AmbientGeom, (MODE_ > 0)>(), ctx->stream>>>(                       \
+            vol_view(vol), F, make_viewk(view), ctx->d_luts, n_ao, out_shadow, out_ao, ctx->d_stats);                               \
+    } while (0)
+    if (ctx->variant == 0) VXL_AMB(0); else if (ctx->variant == 1) VXL_AMB(1); else VXL_AMB(2);
+#undef VXL_AMB
     VXL_LAUNCH_CHECK(ctx);
     return VXL_OK;
 }
@@ -430,14 +436,14 @@ static int local_lights(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, con
     if (vol->dirty) { if (int e = vxl_volume_build_occupancy(vol)) return e; }
     VXL_CUDA(cudaMemcpyAsync(ctx->d_lights, lights, (size_t)n_lights * light_bytes, cudaMemcpyHostToDevice, ctx->stream));
     const size_t plane = frame_pixels(frame);
-#define VXL_LL(SPOT_, FAST_)                                                                                                              \
+#define VXL_LL(SPOT_, MODE_)                                                                                                              \
     do {                                                                                                                              \
-        if (FAST_) VXL_CUDA(cudaFuncSetAttribute(k_local_lights<SPOT_, FAST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<LocalGeom, FAST_>())); \
-        k_local_lights<SPOT_, FAST_><<<grid_for(F), BLOCK_THREADS, smem_bytes<LocalGeom, FAST_>(), ctx->stream>>>(                    \
+        if (MODE_) VXL_CUDA(cudaFuncSetAttribute(k_local_lights<SPOT_, MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<LocalGeom, (MODE_ > 0)>())); \
+        k_local_lights<SPOT_, MODE_><<<grid_for(F), BLOCK_THREADS, smem_bytes<LocalGeom, (MODE_ > 0)>(), ctx->stream>>>(              \
             vol_view(vol), F, make_viewk(view), ctx->d_luts, (const float*)ctx->d_lights, n_lights, out_shadow, plane, ctx->d_stats); \
     } while (0)
-    if (spot) { if (ctx->variant == 0) VXL_LL(true, false); else VXL_LL(true, true); }
-    else { if (ctx->variant == 0) VXL_LL(false, false); else VXL_LL(false, true); }
+    if (spot) { if (ctx->variant == 0) VXL_LL(true, 0); else if (ctx->variant == 1) VXL_LL(true, 1); else VXL_LL(true, 2); }
+    else { if (ctx->variant == 0) VXL_LL(false, 0); else if (ctx->variant == 1) VXL_LL(false, 1); else VXL_LL(false, 2); }
 #undef VXL_LL
     VXL_LAUNCH_CHECK(ctx);
     return VXL_OK;
@@ -461,12 +467,14 @@ int vxl_pass_reflection(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, con
     if (!F.material) { set_error("vxl_pass_reflection: frame.material is NULL"); return VXL_ERR_INVALID; }
     if (F.n_tiles == 0) return VXL_OK;
     if (vol->dirty) { if (int e = vxl_volume_build_occupancy(vol)) return e; }
-    if (ctx->variant == 0) {
-        k_reflection<false><<<grid_for(F), BLOCK_THREADS, smem_bytes<ReflGeom, false>(), ctx->stream>>>(vol_view(vol), F, make_viewk(view), ctx->d_luts, out_spec_t, ctx->d_stats);
-    } else {
-        VXL_CUDA(cudaFuncSetAttribute(k_reflection<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<ReflGeom, true>()));
-        k_reflection<true><<<grid_for(F), BLOCK_THREADS, smem_bytes<ReflGeom, true>(), ctx->stream>>>(vol_view(vol), F, make_viewk(view), ctx->d_luts, out_spec_t, ctx->d_stats);
-    }
+#define VXL_RF(MODE_)                                                                                                                   \
+    do {                                                                                                                            \
+        if (MODE_) VXL_CUDA(cudaFuncSetAttribute(k_reflection<MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<ReflGeom, (MODE_ > 0)>())); \
+        k_reflection<MODE_><<<grid_for(F), BLOCK_THREADS, smem_bytes<ReflGeom, (MODE_ > 0)>(), ctx->stream>>>(                       \
+            vol_view(vol), F, make_viewk(view), ctx->d_luts, out_spec_t, ctx->d_stats);                                             \
+    } while (0)
+    if (ctx->variant == 0) VXL_RF(0); else if (ctx->variant == 1) VXL_RF(1); else VXL_RF(2);
+#undef VXL_RF
     VXL_LAUNCH_CHECK(ctx);
     return VXL_OK;
 }

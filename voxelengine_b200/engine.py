@@ -66,7 +66,8 @@ class Context:
         return dict(rays=int(s.rays), steps=int(s.steps), pixels=int(s.pixels))
 
     def set_variant(self, variant: int):
-        """Diagnostics: 0 = plain march on the volume bytes, 1 = occupancy-bit tile march (default). Same results."""
+        """Diagnostics: 0 = plain march on the volume bytes, 1 = occupancy-bit tile march (default), 2 = tile march
+        that also counts volume reads (fetched_probes). Same results."""
         check(self.lib.vxl_debug_set_variant(self.h, int(variant)), "vxl_debug_set_variant")
 
     def fetched_probes(self) -> int:
