@@ -152,9 +152,10 @@ int vxl_launch_count(vxl_ctx* ctx, uint64_t* out /* HOST */);
  * were answered by a clear occupancy bit). */
 int vxl_debug_set_variant(vxl_ctx* ctx, int variant);
 int vxl_debug_fetched_probes(vxl_ctx* ctx, uint64_t* out /* HOST */);
-/* download one occupancy level (shift 2: 4-voxel cells, 3: 8-voxel cells) unpacked to 0/1 bytes
- * [cz][cy][cx]; out_dims = {cx, cy, cz}; host_out may be NULL */
-int vxl_volume_debug_occupancy(vxl_volume* vol, int shift, uint8_t* host_out /* HOST */, int* out_dims /* HOST[3] */);
+/* download one occupancy level unpacked to 0/1 bytes [cz][cy][cx]: level 2, 3, 4 = plain (cell = 2^level
+ * voxels), 13, 14 = the 3x3x3-dilated levels 3, 4 including their 1-cell border; out_dims = {cx, cy, cz};
+ * host_out may be NULL */
+int vxl_volume_debug_occupancy(vxl_volume* vol, int level, uint8_t* host_out /* HOST */, int* out_dims /* HOST[3] */);
 
 /* raw memory helpers so a C caller needs no CUDA headers */
 int vxl_malloc(vxl_ctx* ctx, size_t bytes, void** out_dev);

@@ -39,32 +39,42 @@ HostOcc build_occ(const uint8_t* vol, int sx, int sy, int sz, int shift) {
     return L;
 }
 
+// dilated = true: OR over the 3x3x3 neighbourhood (computed per tile cell straight from the plain level)
 template <int TY, int TW>
-void build_tile(const HostOcc& L, int ox, int oy, int oz, std::vector<uint32_t>& w) {
+void build_tile(const HostOcc& L, int ox, int oy, int oz, bool dilated, std::vector<uint32_t>& w) {
     w.assign((size_t)TY * TY * TW, 0);
     for (int z = 0; z < TY; ++z)
         for (int y = 0; y < TY; ++y)
-            for (int x = 0; x < TW * 32; ++x)
-                if (L.at(ox + x, oy + y, oz + z)) w[(size_t)(z * TY + y) * TW + (x >> 5)] |= 1u << (x & 31);
+            for (int x = 0; x < TW * 32; ++x) {
+                bool b = false;
+                if (!dilated) b = L.at(ox + x, oy + y, oz + z);
+                else
+                    for (int dz = -1; dz <= 1 && !b; ++dz)
+                        for (int dy = -1; dy <= 1 && !b; ++dy)
+                            for (int dx = -1; dx <= 1 && !b; ++dx) b = L.at(ox + x + dx, oy + y + dy, oz + z + dz);
+                if (b) w[(size_t)(z * TY + y) * TW + (x >> 5)] |= 1u << (x & 31);
+            }
 }
 
 struct Emul {
     std::vector<uint8_t> vol;
     int sx, sy, sz;
-    HostOcc lv[5];               // index = shift (1..4)
+    HostOcc lv[6];               // index = shift (1..5)
 };
 
-template <int SHIFT, int TY, int TW>
+template <int SHIFT, int TY, int TW, int DT, int DW, int GH>
 void trace_geom(Emul* e, const float* rays, long long n, int variant, const int* center, int fast, int direct, int lockstep, vxl_hit* out,
                 unsigned long long* counters) {
     VolView V;
     V.bytes = e->vol.data(); V.sx = e->sx; V.sy = e->sy; V.sz = e->sz;
-    std::vector<uint32_t> w;
+    std::vector<uint32_t> w, wd;
     BitTile T;
     // same placement as block_prologue (vxl_passes.cu)
     T.ox = (center[0] >> SHIFT) - TW * 16; T.oy = (center[1] >> SHIFT) - TY / 2; T.oz = (center[2] >> SHIFT) - TY / 2;
-    build_tile<TY, TW>(e->lv[SHIFT], T.ox, T.oy, T.oz, w);
-    T.w = w.data();
+    T.dx = T.ox >> 1; T.dy = T.oy >> 1; T.dz = T.oz >> 1;
+    build_tile<TY, TW>(e->lv[SHIFT], T.ox, T.oy, T.oz, false, w);
+    build_tile<DT, DW>(e->lv[SHIFT + 1], T.dx, T.dy, T.dz, true, wd);
+    T.w = w.data(); T.wd = wd.data();
     T.enabled = fast != 0;
     constexpr int TPC = 1 << (SHIFT - 1);
     T.direct = direct != 0 && (V.sx % TPC == 0) && (V.sy % TPC == 0) && (V.sz % TPC == 0);
@@ -77,11 +87,11 @@ void trace_geom(Emul* e, const float* rays, long long n, int variant, const int*
         unsigned fetched = 0;
         const float3 o = make_float3(r[0], r[1], r[2]), d = make_float3(r[3], r[4], r[5]);
         if (lockstep) {
-            if (variant == 0) march_bits<false, true, true, true, SHIFT, TY, TW>(V, T, o, d, r[6], steps, &M, fetched);
-            else march_bits<true, true, true, true, SHIFT, TY, TW>(V, T, o, d, r[6], steps, &M, fetched);
+            if (variant == 0) march_bits<false, true, true, true, SHIFT, TY, TW, DT, DW, GH>(V, T, o, d, r[6], steps, &M, fetched);
+            else march_bits<true, true, true, true, SHIFT, TY, TW, DT, DW, GH>(V, T, o, d, r[6], steps, &M, fetched);
         } else {
-            if (variant == 0) march_bits<false, true, false, true, SHIFT, TY, TW>(V, T, o, d, r[6], steps, &M, fetched);
-            else march_bits<true, true, false, true, SHIFT, TY, TW>(V, T, o, d, r[6], steps, &M, fetched);
+            if (variant == 0) march_bits<false, true, false, true, SHIFT, TY, TW, DT, DW, GH>(V, T, o, d, r[6], steps, &M, fetched);
+            else march_bits<true, true, false, true, SHIFT, TY, TW, DT, DW, GH>(V, T, o, d, r[6], steps, &M, fetched);
         }
         vxl_hit hh;
         memset(&hh, 0, sizeof hh);
@@ -101,7 +111,7 @@ void* emul_create(const uint8_t* vol, int sx, int sy, int sz) {
     Emul* e = new Emul();
     e->vol.assign(vol, vol + (size_t)sx * sy * sz);
     e->sx = sx; e->sy = sy; e->sz = sz;
-    for (int sh = 1; sh <= 4; ++sh) e->lv[sh] = build_occ(vol, sx, sy, sz, sh);
+    for (int sh = 1; sh <= 5; ++sh) e->lv[sh] = build_occ(vol, sx, sy, sz, sh);
     return e;
 }
 void emul_destroy(void* h) { delete (Emul*)h; }
@@ -114,15 +124,16 @@ void emul_level(void* h, int shift, uint8_t* out, int* dims) {
     if (out) memcpy(out, L.occ.data(), L.occ.size());
 }
 
-// rays: 8 floats each (origin, dir, dist, pad); variant 0 Sparse / 1 SuperSparse; geom 0 ambient, 1 local lights,
-// 2 reflection (the tile geometries of vxl_passes.cu); the tile is placed around `center` (voxels) exactly as
+// rays: 8 floats each (origin, dir, dist, pad); variant 0 Sparse / 1 SuperSparse; geom 0 ambient / local lights,
+// 1 the same without probe groups, 2 reflection (the tile geometries of vxl_passes.cu); the tile is placed around `center` (voxels) exactly as
 // block_prologue does.  fast = 0 runs the plain march; direct = 0 forces the bounds-checked fetch.  counters: probes that read the volume, total probes.
 void emul_trace(void* h, const float* rays, long long n, int variant, const int* center, int fast, int geom, int direct, int lockstep,
                 vxl_hit* out, unsigned long long* counters) {
     Emul* e = (Emul*)h;
-    if (geom == 0) trace_geom<2, 72, 3>(e, rays, n, variant, center, fast, direct, lockstep, out, counters);
-    else if (geom == 1) trace_geom<2, 84, 3>(e, rays, n, variant, center, fast, direct, lockstep, out, counters);
-    else trace_geom<3, 72, 3>(e, rays, n, variant, center, fast, direct, lockstep, out, counters);
+    // the geometries of vxl_passes.cu (AmbientGeom == LocalGeom, ReflGeom) and a GH = 0 twin without probe groups
+    if (geom == 0) trace_geom<2, 70, 3, 36, 2, 7>(e, rays, n, variant, center, fast, direct, lockstep, out, counters);
+    else if (geom == 1) trace_geom<2, 70, 3, 36, 2, 0>(e, rays, n, variant, center, fast, direct, lockstep, out, counters);
+    else trace_geom<3, 70, 3, 36, 2, 10>(e, rays, n, variant, center, fast, direct, lockstep, out, counters);
 }
 
 // experiment helper: classify every probe of the plain march by what a bit-occupancy hierarchy would know.

@@ -61,7 +61,7 @@ def _surface_points(vol, k, rs):
 
 
 @pytest.mark.parametrize("variant", [0, 1])
-@pytest.mark.parametrize("geom", ["ambient", "local", "reflection"])
+@pytest.mark.parametrize("geom", ["ambient", "nogroup", "reflection"])
 def test_emulated_tile_march_matches_oracle_on_pass_like_rays(oracle, terrain, emul, variant, geom):
     vol = terrain["volume"]
     rs = np.random.RandomState(100 + variant)
@@ -97,7 +97,7 @@ def test_emulated_fast_march_matches_oracle_on_arbitrary_rays(oracle, terrain, e
     rays["dist"][4 * k:5 * k] = np.inf
     rays["dist"][5 * k:6 * k] = -3.0
     want = oracle.trace_rays(vol, rays, variant)
-    for geom, center in [("ambient", (sx, sy, sz)), ("local", (10, 2 * sy - 5, 2 * sz - 3)), ("reflection", (-40, 50, 300)),
+    for geom, center in [("ambient", (sx, sy, sz)), ("nogroup", (10, 2 * sy - 5, 2 * sz - 3)), ("reflection", (-40, 50, 300)),
                          ("ambient", (3, 3, 3))]:
         got, _, steps = emul.trace(rays, variant, center, geom=geom)
         _compare(got, want)
@@ -117,7 +117,7 @@ def test_host_occupancy_levels_are_block_maxima(terrain, emul):
     """emul's occupancy levels (the reference for the GPU build test) against a numpy block reduction."""
     vol = terrain["volume"]
     sz, sy, sx = vol.shape
-    for shift, tpc in ((1, 1), (2, 2), (3, 4), (4, 8)):
+    for shift, tpc in ((1, 1), (2, 2), (3, 4), (4, 8), (5, 16)):
         n = [-(-s // tpc) for s in (sz, sy, sx)]
         pad = np.zeros([k * tpc for k in n], np.uint8)
         pad[:sz, :sy, :sx] = vol

@@ -342,13 +342,18 @@ def test_occupancy_levels_match_block_maxima(gpu_ctx, oracle, texels):
     host[rs.randint(0, sz, 20), rs.randint(0, sy, 20), rs.randint(0, sx, 20)] = 1    # isolated specks
     vol = E.ShadowVoxSystem(gpu_ctx, texels)
     vol.upload(host)
-    for shift, tpc in ((2, 2), (3, 4)):
+    from scipy import ndimage
+    for shift, tpc in ((2, 2), (3, 4), (4, 8)):
         n = [-(-s // tpc) for s in (sz, sy, sx)]
         pad = np.zeros([k * tpc for k in n], np.uint8)
         pad[:sz, :sy, :sx] = host
         want = (pad.reshape(n[0], tpc, n[1], tpc, n[2], tpc).max(axis=(1, 3, 5)) != 0).astype(np.uint8)
         got = vol.occupancy(shift)
         assert got.shape == want.shape and np.array_equal(got, want), f"shift {shift}: {(got != want).sum()} cells differ"
+        if shift >= 3:      # dilated twin: 3x3x3 maximum of the plain level, with a 1-cell border
+            wd = ndimage.maximum_filter(np.pad(want, 1), size=3, mode="constant", cval=0)
+            gd = vol.occupancy(10 + shift)
+            assert gd.shape == wd.shape and np.array_equal(gd, wd), f"dilated {shift}: {(gd != wd).sum()} cells differ"
     vol.clear()                      # an update must be picked up (dirty flag)
     assert vol.occupancy(2).max() == 0
     vol.close()

@@ -33,6 +33,8 @@ struct BitTile {
     bool direct;           // texels of occupied cells can be fetched without bounds checks and with 32-bit offsets:
                            // volume dims are multiples of the cell's texel edge and the volume is < 4 GiB
     unsigned koff;         // folded constant of the direct texel offset (see TileAddr::texel_offset)
+    const uint32_t* wd;    // dilated level (cell = 2^(SHIFT+1) voxels): [DT][DT][DW] words
+    int dx, dy, dz;        // its origin, cells
 };
 
 VXL_DI float3 fma3(float3 s, float k, float3 o) {
@@ -69,12 +71,14 @@ struct TileAddr {
     unsigned sbase;        // device: shared-window byte address of w[-CC] (wraps mod 2^32)
     float mx, my, mz;      // 2^(23+SHIFT) - o_a * 2^SHIFT
     int ox, oy, oz;
-    VXL_DI TileAddr(const BitTile& T) {
+    VXL_DI TileAddr(const BitTile& T) { init(T.w, T.ox, T.oy, T.oz); }
+    VXL_DI TileAddr(const uint32_t* words, int ox_, int oy_, int oz_) { init(words, ox_, oy_, oz_); }
+    VXL_DI void init(const uint32_t* words, int ox_, int oy_, int oz_) {
         const float M = (float)(1 << 23) * (float)(1 << SHIFT), cell = (float)(1 << SHIFT);
-        w = T.w; ox = T.ox; oy = T.oy; oz = T.oz;
-        mx = M - (float)T.ox * cell; my = M - (float)T.oy * cell; mz = M - (float)T.oz * cell;
+        w = words; ox = ox_; oy = oy_; oz = oz_;
+        mx = M - (float)ox_ * cell; my = M - (float)oy_ * cell; mz = M - (float)oz_ * cell;
 #ifdef __CUDA_ARCH__
-        sbase = (unsigned)__cvta_generic_to_shared(T.w) - 4u * CC;
+        sbase = (unsigned)__cvta_generic_to_shared(words) - 4u * CC;
         asm volatile("" : "+r"(sbase));      // keep the folded base in one register (one LEA per lookup)
 #else
         sbase = 0;
@@ -129,7 +133,12 @@ VXL_DI bool warp_any(bool p) {
 // no data-dependent exit; the other lanes of the warp would have kept the issue slots busy anyway.  Every 8
 // probes the warp leaves early if no lane is live.  Use it when `dist` is warp-uniform.
 // COUNT: maintain `fetched` (diagnostic kernels only).
-template <bool SUPER, bool RECORD, bool LOCKSTEP, bool COUNT, int SHIFT, int TY, int TW>
+// GH > 0 (Sparse only): phase 2 runs in groups of 2*GH+1 probes; one test of the dilated level (cell = 2^(SHIFT+1)
+// voxels, tile [DT][DT][DW]) at the group's middle probe clears the whole group when it reads 0, because every probe
+// of the group is then within one dilated cell of the middle one (GH * max|stepDir_a| <= cell, checked per ray).
+// Skipped probes only advance the float recurrence.  Pays off for rays that are coherent across a warp (sun,
+// reflection, point-light shadows); a group that is not clear runs the per-probe loop.
+template <bool SUPER, bool RECORD, bool LOCKSTEP, bool COUNT, int SHIFT, int TY, int TW, int DT = 1, int DW = 1, int GH = 0>
 VXL_DI float march_bits(const VolView& V, const BitTile& T, float3 origin, float3 dir, float dist, int& steps_out,
                         MarchResult* rec, unsigned& fetched) {
     constexpr float step0 = SUPER ? 2.5f : 0.5f;
@@ -202,19 +211,51 @@ VXL_DI float march_bits(const VolView& V, const BitTile& T, float3 origin, float
     stepDir = stepDir * 2.0f;
     const int n2 = phase2_count<SUPER>(lim);
     int hit2 = -1;
-#pragma unroll 2
-    for (int j = 0; j < n2; ++j) {
+    int j = 0;
+    // one per-probe test of phase 2; returns true when the ray ends at probe jj
+    auto probe2 = [&](int jj) -> bool {
         if (A.test(pos) & live) {
             if (COUNT) ++fetched;
             unsigned v;
             if (T.direct) v = V.bytes[TileAddr<SHIFT, TY, TW>::texel_offset(V, T.koff, pos)];
             else { const int px = f2i(pos.x), py = f2i(pos.y), pz = f2i(pos.z); v = fetch_texel(V, px / 2, py / 2, pz / 2); }   // getVolumeAt(ivec3(pos), 1)
             if (v != 0u) {
-                hit2 = j;
+                hit2 = jj;
                 if (RECORD) hpos = pos;
-                if (LOCKSTEP) live = 0u; else break;
+                return true;
             }
         }
+        return false;
+    };
+    if (!SUPER && GH > 0) {
+        constexpr int G = 2 * GH + 1;
+        const TileAddr<SHIFT + 1, DT, DW> D(T.wd, T.dx, T.dy, T.dz);
+        const float m2 = fmaxf(fmaxf(fabsf(stepDir.x), fabsf(stepDir.y)), fabsf(stepDir.z));
+        const bool can_group = (float)GH * m2 <= (float)(2 << SHIFT) - 2.0f * BM_MARGIN;
+        bool done = false;
+        while (!done && j + G <= n2) {
+            const float3 p0 = pos;
+#pragma unroll
+            for (int i = 0; i < GH; ++i) pos = pos + stepDir;            // middle probe of the group
+            if (can_group && !D.test(pos)) {
+#pragma unroll
+                for (int i = 0; i < GH + 1; ++i) pos = pos + stepDir;    // first probe of the next group
+                j += G;
+                continue;
+            }
+            pos = p0;
+#pragma unroll 1
+            for (int i = 0; i < G; ++i) {
+                if (probe2(j + i)) { done = true; break; }
+                pos = pos + stepDir;
+            }
+            j += G;
+        }
+        if (done) j = n2;
+    }
+#pragma unroll 2
+    for (; j < n2; ++j) {
+        if (probe2(j)) { if (LOCKSTEP) live = 0u; else break; }
         pos = pos + stepDir;
         if (LOCKSTEP && (j & 7) == 7 && !warp_any(live != 0u)) break;
     }
@@ -236,12 +277,13 @@ VXL_DI float march_bits(const VolView& V, const BitTile& T, float3 origin, float
 #ifdef __CUDACC__
 template <int TY, int TW>
 __device__ __forceinline__ void stage_bits(uint32_t* __restrict__ dst, const BitView& M, int ox, int oy, int oz) {
-    const int w0 = ox >> 5;                                 // arithmetic shift: floor for negatives
-    const int sh = ox & 31;
+    const int ax0 = ox + M.border;                          // array index = cell index + border
+    const int w0 = ax0 >> 5;                                // arithmetic shift: floor for negatives
+    const int sh = ax0 & 31;
     const int words_x = M.pitch - 1;                        // the spare word of each row is zero
     for (int r = threadIdx.x; r < TY * TY; r += blockDim.x) {   // one tile row (TW words) per iteration
         const int z = r / TY, y = r - z * TY;
-        const int ay = oy + y, az = oz + z;
+        const int ay = oy + y + M.border, az = oz + z + M.border;
         uint32_t g[TW + 1];
 #pragma unroll
         for (int k = 0; k <= TW; ++k) g[k] = 0u;

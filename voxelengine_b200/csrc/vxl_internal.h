@@ -15,15 +15,17 @@ struct BitLevel {
     int cx = 0, cy = 0, cz = 0;          // cells
     int pitch = 0;                       // words per row (ceil(cx/32) + 1 spare zero word)
     int shift = 0;                       // log2(voxels per cell edge)
+    int border = 0;                      // array index = cell index + border (dilated levels: 1)
 };
-struct BitView { const uint32_t* __restrict__ words; int cx, cy, cz, pitch; };
+struct BitView { const uint32_t* __restrict__ words; int cx, cy, cz, pitch, border; };
 
 // Device-side view of the occupancy volume handed to kernels by value.
 struct VolView {
     const uint8_t* __restrict__ bytes;   // canonical packed bytes, x fastest (reference layout)
     int sx, sy, sz;                      // texels
     // derived, acceleration only (never changes a result); see vxl_occupancy.cu
-    BitView occ[2];                      // 4-voxel and 8-voxel cells
+    BitView occ[3];                      // plain levels: 4-, 8-, 16-voxel cells
+    BitView dil[2];                      // dilated levels: 8-, 16-voxel cells
 };
 
 struct FrameView {
@@ -73,7 +75,8 @@ struct vxl_volume {
     int sx = 0, sy = 0, sz = 0;
     uint8_t* d_bytes = nullptr;
     bool dirty = true;
-    vxl::BitLevel occ[2];                // occupancy bitmasks at 4- and 8-voxel cells
+    vxl::BitLevel occ[3];                // occupancy bitmasks at 4-, 8-, 16-voxel cells
+    vxl::BitLevel dil[2];                // 3x3x3-dilated bitmasks at 8-, 16-voxel cells
 };
 
 namespace vxl {
@@ -94,7 +97,8 @@ int cuda_fail(cudaError_t e, const char* what);
 inline VolView vol_view(const vxl_volume* v) {
     VolView r;
     r.bytes = v->d_bytes; r.sx = v->sx; r.sy = v->sy; r.sz = v->sz;
-    for (int i = 0; i < 2; ++i) r.occ[i] = BitView{v->occ[i].d_words, v->occ[i].cx, v->occ[i].cy, v->occ[i].cz, v->occ[i].pitch};
+    for (int i = 0; i < 3; ++i) r.occ[i] = BitView{v->occ[i].d_words, v->occ[i].cx, v->occ[i].cy, v->occ[i].cz, v->occ[i].pitch, v->occ[i].border};
+    for (int i = 0; i < 2; ++i) r.dil[i] = BitView{v->dil[i].d_words, v->dil[i].cx, v->dil[i].cy, v->dil[i].cz, v->dil[i].pitch, v->dil[i].border};
     return r;
 }
 int frame_view(const vxl_frame* f, FrameView* out);

@@ -19,9 +19,9 @@ constexpr float GOLDEN_RATIO = 2.118033988749895f;  // Common.frag:9 (sic)
 
 constexpr int BLOCK_W = 32, BLOCK_H = 16;           // pixels per thread block (16 warps of 8x4)
 constexpr int BLOCK_THREADS = BLOCK_W * BLOCK_H;
-#ifndef VXL_AMBIENT_BLOCKS
-#define VXL_AMBIENT_BLOCKS 2      // resident blocks per SM the register allocation of k_ambient is capped for
-#endif
+#ifndef VXL_PASS_BLOCKS
+#define VXL_PASS_BLOCKS 3         // resident 512-thread blocks per SM the pass kernels' registers are capped for (<= 42 regs);
+#endif                            // measured: 3 blocks 5.91 ms vs 2 blocks 6.51 ms for k_ambient on config 3 (profiles/r1f)
 
 struct ViewK { float InvView[16], View[16], InvProj[16]; int Frame; };
 
@@ -95,30 +95,35 @@ __device__ __forceinline__ void load_luts(float* s_lut, const float* __restrict_
 }
 
 // Shared-memory state of one thread block (dynamic: the tile exceeds the 48 KB static limit).
-template <int TY, int TW>
+template <typename G>
 struct BlockShared {
     float lut[LUT_FLOATS];
     int bb[6];
     unsigned acc[4];
-    uint32_t tile[TY * TY * TW];     // last: kernel variant 0 allocates only the header
+    uint32_t tile[G::TY * G::TY * G::TW];     // from here on: kernel variant 0 allocates only the header
+    uint32_t dtile[G::DT * G::DT * G::DW];
 };
 template <typename G, bool FAST>
 constexpr size_t smem_bytes() {
-    typedef BlockShared<G::TY, G::TW> BS;
-    return FAST ? sizeof(BS) : sizeof(BS) - sizeof(uint32_t) * G::TY * G::TY * G::TW;
+    typedef BlockShared<G> BS;
+    return FAST ? sizeof(BS) : sizeof(BS) - sizeof(uint32_t) * (G::TY * G::TY * G::TW + G::DT * G::DT * G::DW);
 }
-// tile geometry per pass: cells of 2^SHIFT voxels, TW*32 x TY x TY cells
-struct AmbientGeom { static constexpr int SHIFT = 2, TY = 72, TW = 3; };     // +-144 voxels (AO 128, sun 128)
-struct LocalGeom   { static constexpr int SHIFT = 2, TY = 84, TW = 3; };     // +-168 voxels (<= 164 + spread)
-struct ReflGeom    { static constexpr int SHIFT = 3, TY = 72, TW = 3; };     // +-288 voxels (164 steps * |wd| <= 1.5)
+// Tile geometry per pass.  Plain tile: cells of 2^SHIFT voxels, TW*32 x TY x TY cells.  Dilated tile: cells of
+// 2^(SHIFT+1) voxels, DW*32 x DT x DT cells, covering at least the plain tile.  GH: half width of a probe group of the
+// Sparse march (GH * max|stepDir_a| must stay <= the dilated cell: 7 * 1.0 <= 8, 10 * 1.5 <= 16).
+// 58.8 KB + 10.4 KB + 4 KB per block: three 512-thread blocks per SM.
+struct AmbientGeom { static constexpr int SHIFT = 2, TY = 70, TW = 3, DT = 36, DW = 2, GH = 7; };    // +-140 voxels (AO 128, sun 128)
+struct LocalGeom   { static constexpr int SHIFT = 2, TY = 70, TW = 3, DT = 36, DW = 2, GH = 7; };    // point/spot rays beyond +-140 voxels take the plain march
+struct ReflGeom    { static constexpr int SHIFT = 3, TY = 70, TW = 3, DT = 36, DW = 2, GH = 10; };   // +-280 voxels (164 steps * |wd| <= 1.5)
 
 // Bounding box of the block's ray origins -> tile placement -> stage the occupancy tile.
 // `hint` is (close to) the thread's ray origin in voxel units; threads without rays pass valid = false.
 // Ends with a block barrier (which also publishes the LUTs).
 template <bool FAST, typename G>
-__device__ __forceinline__ BitTile block_prologue(const VolView& V, BlockShared<G::TY, G::TW>& S, bool valid, float3 hint) {
+__device__ __forceinline__ BitTile block_prologue(const VolView& V, BlockShared<G>& S, bool valid, float3 hint) {
     BitTile T;
     T.w = S.tile; T.ox = T.oy = T.oz = 0; T.enabled = false;
+    T.wd = S.dtile; T.dx = T.dy = T.dz = 0;
     constexpr int TPC = 1 << (G::SHIFT - 1);                // texels per cell edge
     T.direct = (V.sx % TPC == 0) && (V.sy % TPC == 0) && (V.sz % TPC == 0) && ((unsigned long long)V.sx * V.sy * V.sz < (1ull << 32));
     T.koff = TileAddr<G::SHIFT, G::TY, G::TW>::texel_koff(V);
@@ -140,7 +145,9 @@ __device__ __forceinline__ BitTile block_prologue(const VolView& V, BlockShared<
     if (S.bb[0] == 0x7fffffff) return T;                    // no ray in this block (uniform)
     const int cx = (S.bb[0] + S.bb[3]) >> 1, cy = (S.bb[1] + S.bb[4]) >> 1, cz = (S.bb[2] + S.bb[5]) >> 1;
     T.ox = (cx >> G::SHIFT) - G::TW * 16; T.oy = (cy >> G::SHIFT) - G::TY / 2; T.oz = (cz >> G::SHIFT) - G::TY / 2;
+    T.dx = T.ox >> 1; T.dy = T.oy >> 1; T.dz = T.oz >> 1;   // floor: the dilated tile starts at or before the plain one
     stage_bits<G::TY, G::TW>(S.tile, V.occ[G::SHIFT - 2], T.ox, T.oy, T.oz);
+    stage_bits<G::DT, G::DW>(S.dtile, V.dil[G::SHIFT - 2], T.dx, T.dy, T.dz);
     __syncthreads();
     T.enabled = true;
     return T;
@@ -151,7 +158,7 @@ __device__ __forceinline__ BitTile block_prologue(const VolView& V, BlockShared<
 // MODE: 0 plain march on the bytes, 1 tile march, 2 tile march that also counts the probes that read the volume
 template <int MODE, bool SUPER, bool UNIFORM, typename G>
 __device__ __forceinline__ float ray_march(const VolView& V, const BitTile& T, float3 origin, float3 dir, float dist, int& steps, unsigned& fetched) {
-    if (MODE > 0) return march_bits<SUPER, false, UNIFORM, MODE == 2, G::SHIFT, G::TY, G::TW>(V, T, origin, dir, dist, steps, nullptr, fetched);
+    if (MODE > 0) return march_bits<SUPER, false, UNIFORM, MODE == 2, G::SHIFT, G::TY, G::TW, G::DT, G::DW, G::GH>(V, T, origin, dir, dist, steps, nullptr, fetched);
     return march<false>(V, origin, dir, dist, SUPER ? 2.5f : 0.5f, steps, nullptr);
 }
 
@@ -176,12 +183,12 @@ __device__ __forceinline__ void flush_stats(BS& S, unsigned long long* __restric
 // LightAmbient.frag:134-175 + calculateAmbientIrradiance :111-126
 // -------------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(BLOCK_THREADS, VXL_AMBIENT_BLOCKS) k_ambient(VolView V, FrameView F, ViewK K, const float* __restrict__ g_lut, int n_ao,
+__global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_ambient(VolView V, FrameView F, ViewK K, const float* __restrict__ g_lut, int n_ao,
                                                  float* __restrict__ out_shadow, float* __restrict__ out_ao,
                                                  unsigned long long* __restrict__ g_stats) {
     typedef AmbientGeom G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    BlockShared<G::TY, G::TW>& S = *reinterpret_cast<BlockShared<G::TY, G::TW>*>(smem_raw);
+    BlockShared<G>& S = *reinterpret_cast<BlockShared<G>*>(smem_raw);
     load_luts(S.lut, g_lut);
     const PixelCtx p = pixel_ctx(F, K);
     float depth = 1.0f;
@@ -246,13 +253,13 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_AMBIENT_BLOCKS) k_ambient(V
 // G-buffer, noise and world position are read / derived once per pixel instead of once per light.
 // -------------------------------------------------------------------------------------------------
 template <bool SPOT, int MODE>
-__global__ void __launch_bounds__(BLOCK_THREADS, 2) k_local_lights(VolView V, FrameView F, ViewK K, const float* __restrict__ g_lut,
+__global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_local_lights(VolView V, FrameView F, ViewK K, const float* __restrict__ g_lut,
                                                       const float* __restrict__ lights, int n_lights,
                                                       float* __restrict__ out_shadow, size_t plane_stride,
                                                       unsigned long long* __restrict__ g_stats) {
     typedef LocalGeom G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    BlockShared<G::TY, G::TW>& S = *reinterpret_cast<BlockShared<G::TY, G::TW>*>(smem_raw);
+    BlockShared<G>& S = *reinterpret_cast<BlockShared<G>*>(smem_raw);
     __shared__ float s_light[VXL_MAX_LIGHTS * 4];   // position.xyz, range
     load_luts(S.lut, g_lut);
     constexpr int STRIDE = SPOT ? 16 : 8;
@@ -312,11 +319,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_local_lights(VolView V, Fr
 // LightReflection.frag:60-113
 // -------------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(BLOCK_THREADS, 2) k_reflection(VolView V, FrameView F, ViewK K, const float* __restrict__ g_lut,
+__global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_reflection(VolView V, FrameView F, ViewK K, const float* __restrict__ g_lut,
                                                     float* __restrict__ out_t, unsigned long long* __restrict__ g_stats) {
     typedef ReflGeom G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    BlockShared<G::TY, G::TW>& S = *reinterpret_cast<BlockShared<G::TY, G::TW>*>(smem_raw);
+    BlockShared<G>& S = *reinterpret_cast<BlockShared<G>*>(smem_raw);
     load_luts(S.lut, g_lut);
     const PixelCtx p = pixel_ctx(F, K);
     float depth = 1.0f;

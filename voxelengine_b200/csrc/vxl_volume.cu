@@ -322,7 +322,9 @@ int vxl_volume_create(vxl_ctx* ctx, int sx, int sy, int sz, vxl_volume** out) {
 int vxl_volume_destroy(vxl_volume* v) {
     if (!v) return VXL_OK;
     cudaStreamSynchronize(v->ctx->stream);
-    cudaFree(v->d_bytes); cudaFree(v->occ[0].d_words); cudaFree(v->occ[1].d_words);
+    cudaFree(v->d_bytes);
+    for (auto& L : v->occ) cudaFree(L.d_words);
+    for (auto& L : v->dil) cudaFree(L.d_words);
     delete v;
     return VXL_OK;
 }

@@ -158,7 +158,8 @@ class ShadowVoxSystem:
         check(self.lib.vxl_volume_build_occupancy(self.h), "vxl_volume_build_occupancy")
 
     def occupancy(self, shift: int) -> np.ndarray:
-        """Diagnostics: occupancy level `shift` (2: 4-voxel cells, 3: 8-voxel cells) as 0/1 uint8 [cz][cy][cx]."""
+        """Diagnostics: occupancy level as 0/1 uint8 [cz][cy][cx]; 2, 3, 4 = plain (cell = 2^level voxels),
+        13, 14 = 3x3x3-dilated levels 3, 4 including their 1-cell border."""
         dims = np.zeros(3, np.int32)
         check(self.lib.vxl_volume_debug_occupancy(self.h, int(shift), None, _np_ptr(dims)), "vxl_volume_debug_occupancy")
         out = np.zeros((dims[2], dims[1], dims[0]), np.uint8)
