@@ -14,6 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "liboracle.so")
 _REF = os.path.join(_HERE, "_ref", "libvxref.so")
+_SHADER = os.path.join(_HERE, "_ref", "libvxshader.so")
 
 HIT_DTYPE = np.dtype([("t", "<f4"), ("steps", "<i4"), ("vx", "<i4"), ("vy", "<i4"), ("vz", "<i4"),
                       ("status", "<i4"), ("px", "<f4"), ("py", "<f4"), ("pz", "<f4"),
@@ -71,6 +72,8 @@ def build(force: bool = False) -> str:
     stale = force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in src)
     if stale:
         subprocess.run(["make", "-C", _HERE, "all"], check=True, capture_output=True)
+    from .refcheck import build_shaders
+    build_shaders.build()          # oracle/_ref/libvxshader.so, only when the reference tree is mounted
     return _LIB
 
 
@@ -110,6 +113,64 @@ def ref_lib():
     r.ref_perspective.argtypes = [C.c_float] * 4 + [C.c_void_p]
     r.ref_camera.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p]
     return r
+
+
+# ---- the reference's own shaders compiled for the host (oracle/refcheck/build_shaders.py) ---------------
+SHADER_RAYREC_DTYPE = np.dtype([("o", "<f4", (3,)), ("d", "<f4", (3,)), ("dist", "<f4"), ("result", "<f4"), ("variant", "<i4"),
+                                ("fetches", "<i4"), ("lx", "<i4"), ("ly", "<i4"), ("lz", "<i4"), ("pad", "<i4")])
+SHADER_PIXREC_DTYPE = np.dtype([("n", "<i4"), ("discarded", "<i4"), ("color", "<f4", (4,)), ("ray", SHADER_RAYREC_DTYPE, (2,))])
+assert SHADER_RAYREC_DTYPE.itemsize == 56 and SHADER_PIXREC_DTYPE.itemsize == 136
+PASS_AMBIENT, PASS_POINT, PASS_SPOT, PASS_REFLECTION = 0, 1, 2, 3
+
+_shader = None
+
+
+def shader_lib():
+    """libvxshader.so (Light.frag, LightAmbient/Point/Spot/Reflection.frag of the reference compiled as C++), or None."""
+    global _shader
+    if _shader is None:
+        if not os.path.exists(_SHADER):
+            return None
+        _shader = C.CDLL(_SHADER)
+        _shader.vxshader_set_volume.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        _shader.vxshader_trace.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]
+        _shader.vxshader_pass.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int] * 5 + [C.c_void_p]
+    return _shader
+
+
+def shader_trace(volume, rays, variant):
+    """The reference's raycastShadowVolume{Sparse,SuperSparse,} on `rays`.  Records use HIT_DTYPE with
+    steps = texelFetch calls on the volume and (vx, vy, vz) = the last fetched TEXEL."""
+    L = shader_lib()
+    volume = np.ascontiguousarray(volume, np.uint8)
+    sz, sy, sx = volume.shape
+    rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+    out = np.zeros(len(rays), dtype=HIT_DTYPE)
+    L.vxshader_set_volume(_p(volume), sx, sy, sz)
+    L.vxshader_trace(_p(rays), len(rays), int(variant), _p(out))
+    return out
+
+
+def shader_pass(which, volume, view, gb, lights=None, light_index=0, rect=None):
+    """Run the reference fragment shader `which` over the pixel rectangle (x0, y0, x1, y1); one SHADER_PIXREC per pixel."""
+    L = shader_lib()
+    volume = np.ascontiguousarray(volume, np.uint8)
+    sz, sy, sx = volume.shape
+    h, w = gb["depth24"].shape
+    x0, y0, x1, y1 = rect if rect is not None else (0, 0, w, h)
+    out = np.zeros((y1 - y0, x1 - x0), dtype=SHADER_PIXREC_DTYPE)
+    L.vxshader_set_volume(_p(volume), sx, sy, sz)
+    keep = [np.ascontiguousarray(gb[k], np.uint32) for k in ("depth24", "normal", "material", "noise")]
+    lp = None
+    if lights is not None:
+        dt = POINT_LIGHT_DTYPE if which == PASS_POINT else SPOT_LIGHT_DTYPE
+        buf = np.zeros(64, dtype=dt)
+        buf[:len(lights)] = np.ascontiguousarray(lights, dtype=dt)
+        lp = _p(buf)
+    vw = _view(view)
+    L.vxshader_pass(int(which), _p(vw), w, h, _p(keep[0]), _p(keep[1]), _p(keep[2]), _p(keep[3]), lp, int(light_index),
+                    int(x0), int(y0), int(x1), int(y1), _p(out))
+    return out
 
 
 def _p(a):
