@@ -6,12 +6,21 @@
  * cpu_baseline / --impl reference legs and __graft_entry__.smoke() may load it.  The product
  * never links, includes or calls anything in this directory.
  *
- * PARITY UNPINNED: the reference has no tests, golden vectors or fixtures for this path and its
- * GPU half (GLSL/Vulkan, Windows-only) cannot run in this image (no Vulkan loader / lavapipe /
- * glslang).  Fidelity rests on line-by-line transliteration (each function cites file:line),
- * on the hand-derivable invariants in tests/test_oracle_invariants.py, and on the glm /
- * FastNoise cross-checks built from the reference's vendored sources by oracle/Makefile
- * (oracle/_ref, only when /root/reference is mounted).
+ * PARITY PINNED AGAINST THE REFERENCE ITSELF, RUN HERE.  The reference has no tests, golden vectors
+ * or fixtures for this path and its Vulkan build cannot run in this image, but its sources for the
+ * path compile on the host from where they lie under /root/reference (recipes under oracle/refcheck,
+ * outputs only under oracle/_ref/):
+ *   - Sources/Shaders/lib/Light.frag and Light{Ambient,Point,Spot,Reflection}.frag as C++ on the
+ *     reference's vendored glm (refcheck/build_shaders.py -> _ref/libvxshader.so);
+ *   - Sources/World/Systems/ShadowVoxSystem.cpp with the reference's vendored entt + glm
+ *     (refcheck/shadowvox_wrap.cpp -> _ref/libvxshadowvox.so);
+ *   - glm / FastNoise / Sources/Util/Noise.cpp (refcheck/ref_wrap.cpp -> _ref/libvxref.so).
+ * tests/test_oracle_shaders.py and tests/test_oracle_refcheck.py check this oracle against them bit for
+ * bit (distance, probe count, hit texel, DDA hit/normal, every plane of the four passes, voxelised bytes,
+ * dirty regions), and tests/golden/ref_shaders.npz carries their outputs to machines without the
+ * reference tree.  What stays a declared definition (no reference source exists for it): the
+ * hardware's fixed-point texel decode, In.FarVec evaluated per pixel instead of interpolated, and
+ * cos/sin as correctly rounded values.
  *
  * All paths cited are relative to /root/reference/.
  */

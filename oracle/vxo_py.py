@@ -173,6 +173,32 @@ def shader_pass(which, volume, view, gb, lights=None, light_index=0, rect=None):
     return out
 
 
+_SHADOWVOX = os.path.join(_HERE, "_ref", "libvxshadowvox.so")
+
+
+def ref_shadowvox(models, entities, destroy=None):
+    """The reference's own ShadowVoxSystem (constructor, OnCreate, OnUpdate, OnVoxDestroyed) on a fresh 524x188x524
+    volume -> (staging bytes [sz][sy][sx], regions copied, entt visiting order), or None when the library is absent."""
+    if not os.path.exists(_SHADOWVOX):
+        return None
+    L = C.CDLL(_SHADOWVOX)
+    entities = np.ascontiguousarray(entities, dtype=ENTITY_DTYPE)
+    n = len(entities)
+    keep = [np.ascontiguousarray(m, dtype=np.uint8) for m in models]
+    ptrs = (C.c_void_p * len(keep))(*[m.ctypes.data for m in keep])
+    dims = np.array([[m.shape[2], m.shape[1], m.shape[0]] for m in keep], np.int32)
+    out = np.zeros((524, 188, 524), np.uint8)
+    odims = np.zeros(3, np.int32)
+    regions = np.zeros(2 * n + 4, dtype=REGION_DTYPE)
+    order = np.zeros(n, np.int32)
+    d = None if destroy is None else np.ascontiguousarray(destroy, np.int32)
+    L.vxref_shadowvox_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    nr = L.vxref_shadowvox_run(ptrs, _p(dims), len(keep), _p(entities), n, None if d is None else _p(d), _p(out), _p(odims), _p(regions),
+                               len(regions), _p(order))
+    assert odims.tolist() == [524, 188, 524]
+    return out, regions[:nr], order
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 

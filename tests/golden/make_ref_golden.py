@@ -68,6 +68,14 @@ def main():
     rays = U.random_rays(np.random.RandomState(42), 4096, (64, 64, 64))
     for v, name in ((0, "sparse"), (1, "supersparse"), (2, "dda")):
         out["hits_" + name] = O.shader_trace(volume, rays, v)
+    # the reference's ShadowVoxSystem (oracle/_ref/libvxshadowvox.so) on tests/scene_util.voxeliser_case()
+    models, ents, destroy = U.voxeliser_case()
+    vbytes, vregions, vorder = O.ref_shadowvox(models, ents, destroy)
+    nz = np.flatnonzero(vbytes.ravel())
+    out["vox_nonzero_index"] = nz.astype(np.uint32)           # sparse form of the 524x188x524 staging buffer
+    out["vox_nonzero_value"] = vbytes.ravel()[nz]
+    out["vox_regions"] = vregions
+    out["vox_order"] = vorder
     # drop the per-ray origin/dir of the local-light passes (large, and implied by result + fetches)
     for k in list(out):
         if (k.startswith("point") or k.startswith("spot")) and (k.endswith("_origin") or k.endswith("_dir") or k.endswith("_texel")):

@@ -55,3 +55,28 @@ def random_rays(rs, n, extent, dist_lo=20.0, dist_hi=300.0):
     r["dx"], r["dy"], r["dz"] = d[:, 0], d[:, 1], d[:, 2]
     r["dist"] = rs.uniform(dist_lo, dist_hi, size=n).astype(np.float32)
     return r
+
+
+def voxeliser_case(n=14, seed=5):
+    """Entities for the voxeliser checks against the reference's ShadowVoxSystem: moving / rotated / scaled / overlapping /
+    glass / partly and entirely out-of-volume entities and a destroy list -> (models, entities, destroy flags)."""
+    rs = np.random.RandomState(seed)
+    models = [S.house_model(24, seed=1), S.shell_cube_model(16)]
+    glass = np.zeros((8, 8, 8), np.uint8); glass[:] = 7; glass[2:6, 2:6, 2:6] = 99      # palette < 16 is not voxelised
+    models.append(glass)
+    e = S.entities(n)
+    for i in range(n):
+        pos = rs.uniform(2.0, 16.0, size=3)
+        if i == 3:
+            pos = np.array([-0.7, 3.0, 5.0])            # partly outside (negative coordinates truncate toward zero)
+        if i == 4:
+            pos = np.array([200.0, 3.0, 5.0])           # entirely outside: no region
+        if i in (6, 7):
+            pos = np.array([8.0, 6.0, 8.0]) + 0.3 * i   # overlapping pair: last writer wins per bit
+        rot = (0.0, float(rs.uniform(0, 6.28)), 0.0) if i % 3 else (float(rs.uniform(-0.5, 0.5)), float(rs.uniform(0, 6.28)), 0.3)
+        e[i]["model"] = i % 3
+        e[i]["cur"] = S.transform_matrix(tuple(pos), rot, (1.0, 1.0, 1.0) if i % 4 else (1.5, 0.75, 1.25))
+        e[i]["prev"] = S.transform_matrix(tuple(pos + rs.uniform(-0.4, 0.4, size=3)), rot) if i % 2 else e[i]["prev"]
+        e[i]["pivot"] = (1.2, 0.0, 1.2) if i % 2 else (0.0, 0.0, 0.0)
+    destroy = np.zeros(n, np.int32); destroy[[1, 6, 9]] = 1
+    return models, e, destroy

@@ -94,3 +94,30 @@ def test_host_camera_matrices_match_glm(oracle, ref):
     pos = np.array([26, 15, 25], np.float32)
     ref.ref_camera(_p(pos), 0.81, -0.43, _p(Cm))
     assert np.abs(Cm - S.cm(S.camera_matrix((26, 15, 25), 0.81, -0.43))).max() < 1e-6
+
+
+def test_voxeliser_matches_reference_shadowvoxsystem(oracle):
+    """vxo_voxelize against the REFERENCE's own ShadowVoxSystem.cpp (+ vendored entt, glm) compiled from where it
+    lies (oracle/_ref/libvxshadowvox.so): staging bytes and dirty regions, moving / rotated / overlapping / glass /
+    out-of-volume / destroyed entities, commands given to the oracle in entt's visiting order."""
+    import scene_util as U
+    models, e, destroy = U.voxeliser_case()
+    n = len(e)
+    got = oracle.ref_shadowvox(models, e, destroy)
+    if got is None:
+        pytest.skip("oracle/_ref/libvxshadowvox.so not built (reference tree not mounted)")
+    want_bytes, want_regions, order = got
+    assert sorted(order.tolist()) == list(range(n))
+    cmds = np.concatenate([e[order], e[np.flatnonzero(destroy)]])
+    cmds["flags"][n:] = oracle.ENT_DESTROY
+    vol = np.zeros((524, 188, 524), np.uint8)
+    regions, valid = oracle.voxelize(vol, models, cmds)
+    assert int(vol.sum()) > 0
+    assert np.array_equal(vol, want_bytes)
+    mine = regions[valid != 0]
+    # the constructor queues one whole-volume region (ShadowVoxSystem.cpp:78) that the first OnUpdate uploads first
+    assert tuple(want_regions[0]) == (0, 0, 0, 524, 188, 524, 0)
+    want_regions = want_regions[1:]
+    assert len(mine) == len(want_regions)
+    for a in ("x", "y", "z", "w", "h", "d", "mip"):
+        assert np.array_equal(mine[a], want_regions[a]), a

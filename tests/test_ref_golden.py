@@ -102,6 +102,41 @@ def test_oracle_reproduces_reference_shader_golden(oracle):
         assert np.array_equal(_bits(h["t"]), _bits(g["ambient_result"][lit][:, k])) and np.array_equal(h["steps"], g["ambient_fetches"][lit][:, k])
 
 
+def _vox_case(g):
+    models, e, destroy = U.voxeliser_case()
+    order = g["vox_order"]
+    cmds = np.concatenate([e[order], e[np.flatnonzero(destroy)]])
+    cmds["flags"][len(e):] = 1                      # VXO_ENT_DESTROY / VXL_ENT_DESTROY
+    want = np.zeros(524 * 188 * 524, np.uint8)
+    want[g["vox_nonzero_index"]] = g["vox_nonzero_value"]
+    return models, cmds, want.reshape(524, 188, 524), g["vox_regions"][1:]   # [0] = the constructor's whole-volume region
+
+
+def test_oracle_reproduces_reference_voxeliser_golden(oracle):
+    g = np.load(os.path.join(HERE, "golden", "ref_shaders.npz"))
+    models, cmds, want, want_regions = _vox_case(g)
+    vol = np.zeros((524, 188, 524), np.uint8)
+    regions, valid = oracle.voxelize(vol, models, cmds)
+    assert np.array_equal(vol, want)
+    assert regions[valid != 0].tobytes() == np.ascontiguousarray(want_regions).tobytes()
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_reference_voxeliser_golden(gpu_ctx):
+    """Device voxeliser (vxl_volume_voxelize through the C ABI) against the reference ShadowVoxSystem's own output."""
+    from voxelengine_b200 import engine as E
+    g = np.load(os.path.join(HERE, "golden", "ref_shaders.npz"))
+    models, cmds, want, want_regions = _vox_case(g)
+    vol = E.ShadowVoxSystem(gpu_ctx)                # the reference's 524 x 188 x 524 texels
+    ids = [vol.add_model(m) for m in models]
+    cmds = cmds.copy()
+    cmds["model"] = np.asarray(ids, np.int32)[cmds["model"]]
+    regions, valid = vol.OnUpdate(cmds)
+    assert np.array_equal(vol.download(), want)
+    assert np.ascontiguousarray(regions[valid != 0]).tobytes() == np.ascontiguousarray(want_regions).tobytes()
+    vol.close()
+
+
 @pytest.mark.gpu
 def test_cuda_reproduces_reference_shader_golden(gpu_ctx):
     """CUDA path (through the C ABI) against the reference's own outputs; no oracle call on this test's path."""
