@@ -62,9 +62,9 @@ struct Emul {
     HostOcc lv[6];               // index = shift (1..5)
 };
 
-template <int SHIFT, int TY, int TW, int DT, int DW, int GH>
+template <int SHIFT, int TY, int TW, int DT, int DW, int GH, bool SCAN = false>
 void trace_geom(Emul* e, const float* rays, long long n, int variant, const int* center, int fast, int direct, int lockstep, vxl_hit* out,
-                unsigned long long* counters) {
+                unsigned long long* counters, bool near = true) {
     VolView V;
     V.bytes = e->vol.data(); V.sx = e->sx; V.sy = e->sy; V.sz = e->sz;
     std::vector<uint32_t> w, wd;
@@ -75,6 +75,9 @@ void trace_geom(Emul* e, const float* rays, long long n, int variant, const int*
     build_tile<TY, TW>(e->lv[SHIFT], T.ox, T.oy, T.oz, false, w);
     build_tile<DT, DW>(e->lv[SHIFT + 1], T.dx, T.dy, T.dz, true, wd);
     T.w = w.data(); T.wd = wd.data();
+    std::vector<uint32_t> wn;
+    T.wn = nullptr; T.nx = (center[0] >> 1) - NEAR_T / 2; T.ny = (center[1] >> 1) - NEAR_T / 2; T.nz = (center[2] >> 1) - NEAR_T / 2;
+    if (SCAN) { build_tile<NEAR_T, 1>(e->lv[1], T.nx, T.ny, T.nz, false, wn); T.wn = wn.data(); }
     T.enabled = fast != 0;
     constexpr int TPC = 1 << (SHIFT - 1);
     T.direct = direct != 0 && (V.sx % TPC == 0) && (V.sy % TPC == 0) && (V.sz % TPC == 0);
@@ -86,7 +89,10 @@ void trace_geom(Emul* e, const float* rays, long long n, int variant, const int*
         int steps = 0;
         unsigned fetched = 0;
         const float3 o = make_float3(r[0], r[1], r[2]), d = make_float3(r[3], r[4], r[5]);
-        if (lockstep) {
+        if (SCAN && variant == 1 && r[6] == 128.0f) {
+            if (near) march_scan_super<true, true, true, SHIFT, TY, TW, 23>(V, T, o, d, r[6], steps, &M, fetched);
+            else march_scan_super<true, true, false, SHIFT, TY, TW, 23>(V, T, o, d, r[6], steps, &M, fetched);
+        } else if (lockstep) {
             if (variant == 0) march_bits<false, true, true, true, SHIFT, TY, TW, DT, DW, GH>(V, T, o, d, r[6], steps, &M, fetched);
             else march_bits<true, true, true, true, SHIFT, TY, TW, DT, DW, GH>(V, T, o, d, r[6], steps, &M, fetched);
         } else {
@@ -131,7 +137,9 @@ void emul_trace(void* h, const float* rays, long long n, int variant, const int*
                 vxl_hit* out, unsigned long long* counters) {
     Emul* e = (Emul*)h;
     // the geometries of vxl_passes.cu (AmbientGeom == LocalGeom, ReflGeom) and a GH = 0 twin without probe groups
-    if (geom == 0) trace_geom<2, 70, 3, 36, 2, 7>(e, rays, n, variant, center, fast, direct, lockstep, out, counters);
+    if (geom == 0) trace_geom<2, 69, 3, 36, 2, 7>(e, rays, n, variant, center, fast, direct, lockstep, out, counters);
+    else if (geom == 3) trace_geom<2, 69, 3, 36, 2, 7, true>(e, rays, n, variant, center, fast, direct, lockstep, out, counters);   // AO rays (SuperSparse, dist 128) by scan + resolve, near tile
+    else if (geom == 4) trace_geom<2, 69, 3, 36, 2, 7, true>(e, rays, n, variant, center, fast, direct, lockstep, out, counters, false);   // the same without the near tile
     else if (geom == 1) trace_geom<2, 70, 3, 36, 2, 0>(e, rays, n, variant, center, fast, direct, lockstep, out, counters);
     else trace_geom<3, 70, 3, 36, 2, 10>(e, rays, n, variant, center, fast, direct, lockstep, out, counters);
 }

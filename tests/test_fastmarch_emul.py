@@ -81,6 +81,32 @@ def test_emulated_tile_march_matches_oracle_on_pass_like_rays(oracle, terrain, e
     assert 0 < total_fetched < 0.5 * total_steps, (total_fetched, total_steps)
 
 
+def test_emulated_scan_march_matches_oracle_on_ao_like_rays(oracle, terrain, emul):
+    """AO rays (SuperSparse, dist 128) through the scan + resolve march: candidate mask, approximate-position texel
+    lookup with its exact-replay fallback, hit index arithmetic.  Large coordinates make eps large enough that the
+    fallback runs; tiny origins spread exercises the phase-1 replay."""
+    vol = terrain["volume"]
+    rs = np.random.RandomState(321)
+    total_fetched = total_steps = 0
+    for center in _surface_points(vol, 10, rs):
+        rays = _surface_rays(rs, vol, 30_000, center, 5.0, [128.0])
+        rays["oy"] -= rs.uniform(0.0, 3.0, size=len(rays)).astype(np.float32)        # some origins inside the terrain
+        want = oracle.trace_rays(vol, rays, 1)
+        got, fetched, steps = emul.trace(rays, 1, center, geom="scan")
+        _compare(got, want)
+        assert steps == int(want["steps"].sum())
+        got, fetched_far, _ = emul.trace(rays, 1, center, geom="scan_far")       # without the near (texel-level) tile
+        _compare(got, want)
+        assert fetched < fetched_far
+        total_fetched += fetched
+        total_steps += steps
+    assert 0 < total_fetched < 0.5 * total_steps, (total_fetched, total_steps)
+    # other distances take the per-probe march, ineligible rays the plain one
+    rays = _surface_rays(rs, vol, 20_000, center, 200.0, [128.0, 40.0, 164.0])
+    got, _, _ = emul.trace(rays, 1, center, geom="scan")
+    _compare(got, oracle.trace_rays(vol, rays, 1))
+
+
 @pytest.mark.parametrize("variant", [0, 1])
 def test_emulated_fast_march_matches_oracle_on_arbitrary_rays(oracle, terrain, emul, variant):
     """Rays that start outside the volume, at negative coordinates, axis-parallel, on voxel boundaries, far from
@@ -97,8 +123,10 @@ def test_emulated_fast_march_matches_oracle_on_arbitrary_rays(oracle, terrain, e
     rays["dist"][4 * k:5 * k] = np.inf
     rays["dist"][5 * k:6 * k] = -3.0
     want = oracle.trace_rays(vol, rays, variant)
+    rays["dist"][6 * k:] = np.where(rs.uniform(size=len(rays) - 6 * k) < 0.5, np.float32(128.0), rays["dist"][6 * k:])
+    want = oracle.trace_rays(vol, rays, variant)
     for geom, center in [("ambient", (sx, sy, sz)), ("nogroup", (10, 2 * sy - 5, 2 * sz - 3)), ("reflection", (-40, 50, 300)),
-                         ("ambient", (3, 3, 3))]:
+                         ("ambient", (3, 3, 3)), ("scan", (sx, sy, sz)), ("scan", (3, 3, 3))]:
         got, _, steps = emul.trace(rays, variant, center, geom=geom)
         _compare(got, want)
 

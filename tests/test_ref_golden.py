@@ -67,7 +67,10 @@ def _check_hits(got, want, variant):
         ok = got["status"] == 1
         assert np.array_equal(ok, want["status"] == 1)
         for a in ("px", "py", "pz", "nx", "ny", "nz"):
-            assert np.array_equal(_bits(got[a][ok]), _bits(want[a][ok])), a
+            # a NaN is a NaN: its sign / payload bits are not defined by GLSL (x86 produces 0xFFC00000, sm_100 0x7FFFFFFF)
+            x, y = got[a][ok], want[a][ok]
+            both_nan = np.isnan(x) & np.isnan(y)
+            assert np.array_equal(_bits(x)[~both_nan], _bits(y)[~both_nan]), a
         assert np.array_equal(got["steps"] + ok.astype(np.int32), want["steps"]), "DDA probe count"
         for a in ("vx", "vy", "vz"):
             assert np.array_equal(_trunc_half(got[a])[ok], want[a][ok].astype(np.int64)), a

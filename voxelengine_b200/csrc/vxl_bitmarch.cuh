@@ -35,6 +35,8 @@ struct BitTile {
     unsigned koff;         // folded constant of the direct texel offset (see TileAddr::texel_offset)
     const uint32_t* wd;    // dilated level (cell = 2^(SHIFT+1) voxels): [DT][DT][DW] words
     int dx, dy, dz;        // its origin, cells
+    const uint32_t* wn;    // near tile: texel level (cell = 2 voxels), [NEAR_T][NEAR_T] words of 32 texels; nullptr = none
+    int nx, ny, nz;        // its origin, texels
 };
 
 VXL_DI float3 fma3(float3 s, float k, float3 o) {
@@ -58,6 +60,39 @@ VXL_DI unsigned magic_floor_bits(float p, float m, int S, int o) {
 #endif
 }
 
+constexpr int NEAR_T = 32;                   // near tile: 32^3 texels = 64^3 voxels = 4 KB
+
+// Lookup in the near tile: word = z * 32 + y, bit = x, all relative to the tile origin.
+struct NearAddr {
+    static constexpr unsigned MB = 0x4B000000u + (1u << 23);
+    const uint32_t* w;
+    unsigned sbase;
+    float mx, my, mz;
+    int ox, oy, oz;
+    VXL_DI NearAddr(const BitTile& T) {
+        const float M = 16777216.0f;
+        w = T.wn; ox = T.nx; oy = T.ny; oz = T.nz;
+        mx = M - (float)ox * 2.0f; my = M - (float)oy * 2.0f; mz = M - (float)oz * 2.0f;
+#ifdef __CUDA_ARCH__
+        sbase = (unsigned)__cvta_generic_to_shared(T.wn);
+#else
+        sbase = 0;
+#endif
+    }
+    // the texel bit of the texel containing p, in bit 0 (p inside the near window)
+    VXL_DI unsigned bit(float3 p) const {
+        const unsigned bx = magic_floor_bits(p.x, mx, 1, ox), by = magic_floor_bits(p.y, my, 1, oy), bz = magic_floor_bits(p.z, mz, 1, oz);
+        const unsigned idx = (bz * (unsigned)NEAR_T + by) & (unsigned)(NEAR_T * NEAR_T - 1);      // MB * 33 = 0 (mod 1024)
+#ifdef __CUDA_ARCH__
+        unsigned word;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(sbase + 4u * idx));
+        return __funnelshift_r(word, 0u, bx);
+#else
+        return w[idx] >> (bx & 31);
+#endif
+    }
+};
+
 // Tile lookup with everything constant folded once per ray:
 //   b_a  = MB + rel_a                      (MB = 0x4B000000 + (SHIFT << 23), a multiple of 32)
 //   word = rel_z * (TY*TW) + rel_y * TW + (rel_x >> 5) = b_z * (TY*TW) + b_y * TW + (b_x >> 5) - CC      (mod 2^32)
@@ -65,21 +100,31 @@ VXL_DI unsigned magic_floor_bits(float p, float m, int S, int o) {
 template <int SHIFT, int TY, int TW>
 struct TileAddr {
     static constexpr unsigned MB = 0x4B000000u + ((unsigned)SHIFT << 23);
-    static constexpr unsigned CC = MB * (unsigned)(TY * TW) + MB * (unsigned)TW + (MB >> 5);
+    static constexpr unsigned CC0 = MB * (unsigned)(TY * TW) + MB * (unsigned)TW + (MB >> 5);
+    // Bias the per-axis origins by (32 JX, KY, KZ) cells so that the folded constant vanishes mod 2^30 (word index ->
+    // byte address drops two more bits): (MB + KZ) TY TW + (MB + KY) TW + (MB >> 5) + JX = 0, which saves the add of
+    // the constant per lookup.  The biased index must stay inside the binade of the magic sum (KZ + TY < 2^23); the
+    // narrow dilated tiles do not admit a solution and keep the constant.
+    static constexpr unsigned RR = (0u - CC0) & 0x3FFFFFFFu;
+    static constexpr bool FOLD0 = RR / (unsigned)(TY * TW) < (1u << 23) - 4096u;
+    static constexpr int KZ = FOLD0 ? (int)(RR / (unsigned)(TY * TW)) : 0;
+    static constexpr int KY = FOLD0 ? (int)((RR % (unsigned)(TY * TW)) / (unsigned)TW) : 0;
+    static constexpr int JX = FOLD0 ? (int)(RR % (unsigned)TW) : 0;
+    static constexpr unsigned CC = CC0 + (unsigned)KZ * (unsigned)(TY * TW) + (unsigned)KY * (unsigned)TW + (unsigned)JX;   // 4 * CC == 0 (mod 2^32) when FOLD0
     static constexpr unsigned MB1 = 0x4B000000u + (1u << 23);       // texel grid (2 voxels)
     const uint32_t* w;
     unsigned sbase;        // device: shared-window byte address of w[-CC] (wraps mod 2^32)
     float mx, my, mz;      // 2^(23+SHIFT) - o_a * 2^SHIFT
-    int ox, oy, oz;
+    int ox, oy, oz;        // biased origin, cells
     VXL_DI TileAddr(const BitTile& T) { init(T.w, T.ox, T.oy, T.oz); }
     VXL_DI TileAddr(const uint32_t* words, int ox_, int oy_, int oz_) { init(words, ox_, oy_, oz_); }
     VXL_DI void init(const uint32_t* words, int ox_, int oy_, int oz_) {
         const float M = (float)(1 << 23) * (float)(1 << SHIFT), cell = (float)(1 << SHIFT);
-        w = words; ox = ox_; oy = oy_; oz = oz_;
-        mx = M - (float)ox_ * cell; my = M - (float)oy_ * cell; mz = M - (float)oz_ * cell;
+        w = words; ox = ox_ - 32 * JX; oy = oy_ - KY; oz = oz_ - KZ;
+        mx = M - (float)ox * cell; my = M - (float)oy * cell; mz = M - (float)oz * cell;
 #ifdef __CUDA_ARCH__
         sbase = (unsigned)__cvta_generic_to_shared(words) - 4u * CC;
-        asm volatile("" : "+r"(sbase));      // keep the folded base in one register (one LEA per lookup)
+        if (!FOLD0) asm volatile("" : "+r"(sbase));      // keep the folded base in one register (one LEA per lookup)
 #else
         sbase = 0;
 #endif
@@ -94,8 +139,21 @@ struct TileAddr {
         asm("shf.l.wrap.b32 %0, 0, 1, %1;" : "=r"(mask) : "r"(bx));       // high word of {1:0} << (bx & 31) = 1 << (bx & 31); opaque so it stays a mask test
         return word & mask;
 #else
-        const unsigned idx = bz * (unsigned)(TY * TW) + by * (unsigned)TW + (bx >> 5) - CC;
+        const unsigned idx = (bz * (unsigned)(TY * TW) + by * (unsigned)TW + (bx >> 5) - CC) & 0x3FFFFFFFu;
         return w[idx] & (1u << (bx & 31));
+#endif
+    }
+    // the occupancy bit of the cell containing p, in bit 0 (upper bits: the neighbouring cells of the word)
+    VXL_DI unsigned bit(float3 p) const {
+        const unsigned bx = magic_floor_bits(p.x, mx, SHIFT, ox), by = magic_floor_bits(p.y, my, SHIFT, oy), bz = magic_floor_bits(p.z, mz, SHIFT, oz);
+#ifdef __CUDA_ARCH__
+        const unsigned idx = bz * (unsigned)(TY * TW) + by * (unsigned)TW + (bx >> 5);
+        unsigned word;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(sbase + 4u * idx));
+        return __funnelshift_r(word, 0u, bx);                             // word >> (bx & 31)
+#else
+        const unsigned idx = (bz * (unsigned)(TY * TW) + by * (unsigned)TW + (bx >> 5) - CC) & 0x3FFFFFFFu;
+        return w[idx] >> (bx & 31);
 #endif
     }
     // byte offset of the texel containing p (p >= 0, inside the volume): floor(p/2) per axis, x fastest
@@ -268,6 +326,158 @@ VXL_DI float march_bits(const VolView& V, const BitTile& T, float3 origin, float
         rec->d = d; rec->steps = nsteps; rec->status = h2 ? 2 : 0;
         rec->vx = h2 ? f2i(hpos.x) : 0; rec->vy = h2 ? f2i(hpos.y) : 0; rec->vz = h2 ? f2i(hpos.z) : 0;
         rec->pos = h2 ? hpos : make_float3(0.f, 0.f, 0.f);
+    }
+    return d;
+}
+
+// ---- scan + resolve march (SuperSparse with a compile-time probe count: the AO rays) --------------------------
+// The per-probe loop above leaves the warp whenever ONE lane meets a set occupancy bit (8 % of the probes, i.e. 80 %
+// of the warp iterations at 19 live lanes), and every such excursion is a dependent L2 round trip.  Here a ray first
+// SCANS all N = 6 + N2 probe positions with the reference's float recurrence, branch-free and fully unrolled, packing
+// the occupancy bits of its probes into one word (13 instructions per probe: 3 FADD, 3 FADD.RZ, 4 address, LDS, 2
+// funnel shifts).  Then it RESOLVES the set bits in probe order with the reference's own texel test, stopping at the
+// first hit.  The probes after a hit are wasted scan work, bounded by N.
+//
+// Resolve needs the probe position.  Phase-1 candidates (k < 6) replay the recurrence (<= 5 additions).  A phase-2
+// candidate only needs its TEXEL, floor(pos / 2): q = fma(stepDir, 2k - 6, origin) differs from the recurrence's pos_k
+// by at most (k + 2) roundings of values below hi + 1 (<= 31 * 2^-24 * (hi + 1) < eps = (hi + 1) * 2^-18, origin + (2k - 6) stepDir
+// being what the recurrence sums without rounding: stepDir * 2 is exact); when q - eps and q + eps fall in the same
+// texel on every axis, so does pos_k.  Otherwise (about 1 % of candidates) the recurrence is replayed.
+template <int SHIFT, int TY, int TW>
+VXL_DI bool tile_eligible(const BitTile& T, float3 origin, float3 dir, float reach, float& hi_max) {
+    const float3 end = fma3(dir, reach, origin);
+    const float3 lo = make_float3(fminf(origin.x, end.x), fminf(origin.y, end.y), fminf(origin.z, end.z));
+    const float3 hi = make_float3(fmaxf(origin.x, end.x), fmaxf(origin.y, end.y), fmaxf(origin.z, end.z));
+    const float cell = (float)(1 << SHIFT);
+    const float3 tlo = make_float3((float)T.ox * cell, (float)T.oy * cell, (float)T.oz * cell);
+    bool fast = T.enabled;
+    fast = fast && (lo.x >= fmaxf(tlo.x, 0.0f) + BM_MARGIN) && (lo.y >= fmaxf(tlo.y, 0.0f) + BM_MARGIN) && (lo.z >= fmaxf(tlo.z, 0.0f) + BM_MARGIN);
+    fast = fast && (hi.x <= fminf(tlo.x + (float)(TW * 32) * cell, BM_MAXCOORD) - BM_MARGIN) &&
+           (hi.y <= fminf(tlo.y + (float)TY * cell, BM_MAXCOORD) - BM_MARGIN) && (hi.z <= fminf(tlo.z + (float)TY * cell, BM_MAXCOORD) - BM_MARGIN);
+    fast = fast && (origin.x == origin.x) && (origin.y == origin.y) && (origin.z == origin.z) && (end.x == end.x) && (end.y == end.y) && (end.z == end.z);
+    hi_max = fmaxf(fmaxf(hi.x, hi.y), hi.z);
+    return fast;
+}
+
+VXL_DI unsigned funnel_r(unsigned lo, unsigned hi, unsigned sh) {
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(lo, hi, sh);
+#else
+    sh &= 31u;
+    return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
+#endif
+}
+
+// N2 = phase2_count<true>(min(dist, 164)), known at compile time (23 for the AO rays' dist = 128); 6 + N2 <= 32.
+// NEAR: the block also staged the near tile (texel bits of the 64^3 voxels around the ray origins).  A ray whose first
+// KN = 8 probes (d <= 25) stay inside it tests those probes against the texel bits instead of the 4-voxel cells: a
+// phase-2 probe is then answered exactly (the bit IS getVolumeAt(pos, 1)), and a phase-1 probe is a candidate only when
+// its texel is non-zero (a quarter of the cell-level candidates, measured on config 3).
+template <bool RECORD, bool COUNT, bool NEAR, int SHIFT, int TY, int TW, int N2>
+VXL_DI float march_scan_super(const VolView& V, const BitTile& T, float3 origin, float3 dir, float dist, int& steps_out,
+                              MarchResult* rec, unsigned& fetched) {
+    constexpr int N1 = 6, N = N1 + N2, KN = 8;
+    static_assert(N <= 32 && KN <= N, "candidate mask is one word");
+    const float lim = fminf(dist, 164.0f);
+    float hi_max;
+    if (!T.direct || !tile_eligible<SHIFT, TY, TW>(T, origin, dir, fmaxf(lim, 16.0f) + 1.0f, hi_max))
+        return march<RECORD>(V, origin, dir, dist, 2.5f, steps_out, rec);
+
+    typedef TileAddr<SHIFT, TY, TW> TA;
+    const TA A(T);
+    const float3 s1 = dir * 2.5f;
+    const float3 s2 = s1 * 2.0f;
+    // ---- scan: probe k ends up in bit k ----
+    unsigned cand = 0u;
+    float3 pos = origin;
+    bool near_ok = false;
+    if (NEAR) {
+        const float3 e = fma3(s1, (float)(2 * (KN - 1) - N1), origin);       // probe KN - 1, up to rounding (<< margin)
+        const float lx = (float)T.nx * 2.0f + BM_MARGIN, ly = (float)T.ny * 2.0f + BM_MARGIN, lz = (float)T.nz * 2.0f + BM_MARGIN;
+        const float w = (float)(2 * NEAR_T) - 2.0f * BM_MARGIN;
+        near_ok = T.wn != nullptr && fminf(origin.x, e.x) >= lx && fmaxf(origin.x, e.x) <= lx + w && fminf(origin.y, e.y) >= ly &&
+                  fmaxf(origin.y, e.y) <= ly + w && fminf(origin.z, e.z) >= lz && fmaxf(origin.z, e.z) <= lz + w;
+    }
+    if (NEAR && near_ok) {
+        const NearAddr B(T);
+#pragma unroll
+        for (int k = 0; k < KN; ++k) {
+            cand = funnel_r(cand, B.bit(pos), 1u);
+            pos = pos + (k + 1 <= N1 ? s1 : s2);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < KN; ++k) {
+            cand = funnel_r(cand, A.bit(pos), 1u);
+            pos = pos + (k + 1 <= N1 ? s1 : s2);                            // the addition after probe 5 still uses s1 (:151)
+        }
+    }
+#pragma unroll
+    for (int k = KN; k < N; ++k) {
+        cand = funnel_r(cand, A.bit(pos), 1u);
+        if (k + 1 < N) pos = pos + s2;
+    }
+    cand >>= (32 - N);
+    // ---- resolve ----
+    const float eps = (hi_max + 1.0f) * (1.0f / 262144.0f);
+    int hit = -1;
+    unsigned hbit = 0u;
+    while (cand) {
+#ifdef __CUDA_ARCH__
+        const int k = __ffs((int)cand) - 1;
+#else
+        const int k = __builtin_ctz(cand);
+#endif
+        cand &= cand - 1u;
+        if (k < N1) {
+            if (COUNT) ++fetched;
+            float3 p = origin;
+#pragma unroll
+            for (int i = 0; i < N1 - 1; ++i)
+                if (i < k) p = p + s1;
+            const unsigned v = V.bytes[TA::texel_offset(V, T.koff, p)];
+            if (v != 0u) {
+                unsigned bit = 0u;
+                bit += gmod(p.x, 0.5f) > 0.25f ? 1u : 0u;
+                bit += gmod(p.y, 0.5f) > 0.25f ? 2u : 0u;
+                bit += gmod(p.z, 0.5f) > 0.25f ? 4u : 0u;
+                if ((v >> bit) & 1u) { hit = k; hbit = bit; break; }
+            }
+        } else if (NEAR && near_ok && k < KN) {
+            hit = k;                                                      // texel bit set = byte != 0 = the reference's test
+            break;
+        } else {
+            if (COUNT) ++fetched;
+            const float3 q = fma3(s1, (float)(2 * k - N1), origin);
+            const float M1 = 16777216.0f;
+            const unsigned ax = magic_floor_bits(q.x - eps, M1, 1, 0), bx = magic_floor_bits(q.x + eps, M1, 1, 0);
+            const unsigned ay = magic_floor_bits(q.y - eps, M1, 1, 0), by = magic_floor_bits(q.y + eps, M1, 1, 0);
+            const unsigned az = magic_floor_bits(q.z - eps, M1, 1, 0), bz = magic_floor_bits(q.z + eps, M1, 1, 0);
+            unsigned off = bz * (unsigned)(V.sx * V.sy) + by * (unsigned)V.sx + bx - T.koff;
+            if ((ax ^ bx) | (ay ^ by) | (az ^ bz)) {                     // within eps of a texel face: exact position
+                float3 p = origin;
+                for (int i = 0; i < N1; ++i) p = p + s1;
+                for (int i = N1; i < k; ++i) p = p + s2;
+                off = TA::texel_offset(V, T.koff, p);
+            }
+            if (V.bytes[off] != 0u) { hit = k; break; }
+        }
+    }
+    const bool h = hit >= 0;
+    const int nsteps = h ? hit + 1 : N;
+    const float d = !h ? dist : (hit < N1 ? 2.5f * (float)(hit + 1) : 17.5f + 5.0f * (float)(hit - N1));
+    steps_out += nsteps;
+    if (RECORD) {
+        float3 p = origin;
+        for (int i = 0; i < hit; ++i) p = p + (i < N1 ? s1 : s2);
+        rec->d = d; rec->steps = nsteps; rec->status = !h ? 0 : (hit < N1 ? 1 : 2);
+        if (h && hit < N1) {
+            const int tx = f2i(p.x / 2.0f), ty = f2i(p.y / 2.0f), tz = f2i(p.z / 2.0f);
+            rec->vx = tx * 2 + (int)(hbit & 1u); rec->vy = ty * 2 + (int)((hbit >> 1) & 1u); rec->vz = tz * 2 + (int)((hbit >> 2) & 1u);
+        } else {
+            rec->vx = h ? f2i(p.x) : 0; rec->vy = h ? f2i(p.y) : 0; rec->vz = h ? f2i(p.z) : 0;
+        }
+        rec->pos = h ? p : make_float3(0.f, 0.f, 0.f);
     }
     return d;
 }

@@ -24,6 +24,7 @@ struct VolView {
     const uint8_t* __restrict__ bytes;   // canonical packed bytes, x fastest (reference layout)
     int sx, sy, sz;                      // texels
     // derived, acceleration only (never changes a result); see vxl_occupancy.cu
+    BitView tex;                         // texel level: 1 bit per packed byte (2-voxel cells); bit = (byte != 0)
     BitView occ[3];                      // plain levels: 4-, 8-, 16-voxel cells
     BitView dil[2];                      // dilated levels: 8-, 16-voxel cells
 };
@@ -75,6 +76,7 @@ struct vxl_volume {
     int sx = 0, sy = 0, sz = 0;
     uint8_t* d_bytes = nullptr;
     bool dirty = true;
+    vxl::BitLevel tex;                   // occupancy bitmask at texel (2-voxel) cells
     vxl::BitLevel occ[3];                // occupancy bitmasks at 4-, 8-, 16-voxel cells
     vxl::BitLevel dil[2];                // 3x3x3-dilated bitmasks at 8-, 16-voxel cells
 };
@@ -97,6 +99,7 @@ int cuda_fail(cudaError_t e, const char* what);
 inline VolView vol_view(const vxl_volume* v) {
     VolView r;
     r.bytes = v->d_bytes; r.sx = v->sx; r.sy = v->sy; r.sz = v->sz;
+    r.tex = BitView{v->tex.d_words, v->tex.cx, v->tex.cy, v->tex.cz, v->tex.pitch, v->tex.border};
     for (int i = 0; i < 3; ++i) r.occ[i] = BitView{v->occ[i].d_words, v->occ[i].cx, v->occ[i].cy, v->occ[i].cz, v->occ[i].pitch, v->occ[i].border};
     for (int i = 0; i < 2; ++i) r.dil[i] = BitView{v->dil[i].d_words, v->dil[i].cx, v->dil[i].cy, v->dil[i].cz, v->dil[i].pitch, v->dil[i].border};
     return r;

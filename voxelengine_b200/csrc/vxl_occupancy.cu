@@ -3,6 +3,9 @@
 // Pure acceleration (SURVEY.md 7 step 5 "k_occupancy_mips"): nothing here exists in the reference
 // (its volume has one mip level, ShadowVoxSystem.cpp:61) and nothing here may change a result.
 //
+// Texel level (L = 1, cell = one packed byte = 2 voxels per axis): bit = (byte != 0).  This is the reference's own
+//   coarse test (Light.frag:163 getVolumeAt(pos, 1)), so inside a staged window of this level a phase-2 probe is
+//   answered exactly, and a phase-1 probe whose bit is clear cannot hit.
 // Plain level L (cell = 2^L voxels per axis; L = 2, 3, 4):
 //   occ_L[c] = 1 iff any packed byte of the canonical volume inside cell c is non-zero.
 //   A march probe (Light.frag:140 fine bit test, :163 coarse byte test) whose cell bit is 0 reads a zero
@@ -18,29 +21,29 @@
 
 namespace vxl {
 
-// one thread per output word: 32 cells along x, each TPC^3 texels
-template <int TPC>
-__global__ void __launch_bounds__(256) k_occ_bits(const uint8_t* __restrict__ bytes, int sx, int sy, int sz,
-                                                  int cy, int cz, int pitch, uint32_t* __restrict__ out) {
+// texel level: one thread per output word = 32 consecutive bytes of a volume row; HBM-bound (reads the volume once)
+__device__ __forceinline__ uint32_t nonzero_bytes4(uint32_t v) {        // bit i = (byte i of v != 0)
+    const uint32_t m = (v | ((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu)) & 0x80808080u;
+    return ((m >> 7) & 1u) | ((m >> 14) & 2u) | ((m >> 21) & 4u) | ((m >> 28) & 8u);
+}
+__global__ void __launch_bounds__(256) k_occ_texels(const uint8_t* __restrict__ bytes, int sx, int sy, int sz,
+                                                    int pitch, uint32_t* __restrict__ out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)pitch * cy * cz;
+    const long long total = (long long)pitch * sy * sz;
     if (i >= total) return;
-    const int w = (int)(i % pitch), y = (int)((i / pitch) % cy), z = (int)(i / ((long long)pitch * cy));
+    const int w = (int)(i % pitch), y = (int)((i / pitch) % sy), z = (int)(i / ((long long)pitch * sy));
     uint32_t word = 0;
-    const int x0 = w * 32 * TPC;
+    const int x0 = w * 32;
     if (x0 < sx) {
-        for (int dz = 0; dz < TPC; ++dz) {
-            const int tz = z * TPC + dz;
-            if (tz >= sz) break;
-            for (int dy = 0; dy < TPC; ++dy) {
-                const int ty = y * TPC + dy;
-                if (ty >= sy) break;
-                const uint8_t* row = bytes + (size_t)ty * sx + (size_t)tz * ((size_t)sx * sy);
-                const int n = min(32 * TPC, sx - x0);
-#pragma unroll 4
-                for (int k = 0; k < n; ++k)
-                    if (row[x0 + k]) word |= 1u << (k / TPC);
-            }
+        const uint8_t* row = bytes + (size_t)y * sx + (size_t)z * ((size_t)sx * sy) + x0;
+        if (x0 + 32 <= sx && (reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(row)), b = __ldg(reinterpret_cast<const uint4*>(row) + 1);
+            word = nonzero_bytes4(a.x) | (nonzero_bytes4(a.y) << 4) | (nonzero_bytes4(a.z) << 8) | (nonzero_bytes4(a.w) << 12) |
+                   (nonzero_bytes4(b.x) << 16) | (nonzero_bytes4(b.y) << 20) | (nonzero_bytes4(b.z) << 24) | (nonzero_bytes4(b.w) << 28);
+        } else {
+            const int n = min(32, sx - x0);
+            for (int k = 0; k < n; ++k)
+                if (row[k]) word |= 1u << k;
         }
     }
     out[i] = word;
@@ -114,6 +117,7 @@ int vxl_volume_build_occupancy(vxl_volume* v) {
     vxl_ctx* c = v->ctx;
     VXL_CUDA(cudaSetDevice(c->device));
     if (!v->occ[0].d_words) {
+        if (int e = alloc_level(v->tex, 1, v->sx, v->sy, v->sz, 0)) return e;
         for (int li = 0; li < 3; ++li) {
             const int tpc = 2 << li;                          // texels per cell edge: 2, 4, 8
             if (int e = alloc_level(v->occ[li], 2 + li, (v->sx + tpc - 1) / tpc, (v->sy + tpc - 1) / tpc, (v->sz + tpc - 1) / tpc, 0)) return e;
@@ -124,11 +128,11 @@ int vxl_volume_build_occupancy(vxl_volume* v) {
         }
     }
     auto grid_of = [](const BitLevel& L) { return (unsigned)(((long long)L.pitch * L.cy * L.cz + 255) / 256); };
-    BitLevel& L2 = v->occ[0];
-    k_occ_bits<2><<<grid_of(L2), 256, 0, c->stream>>>(v->d_bytes, v->sx, v->sy, v->sz, L2.cy, L2.cz, L2.pitch, L2.d_words);
+    BitLevel& L1 = v->tex;
+    k_occ_texels<<<grid_of(L1), 256, 0, c->stream>>>(v->d_bytes, v->sx, v->sy, v->sz, L1.pitch, L1.d_words);
     VXL_LAUNCH_CHECK(c);
-    for (int li = 1; li < 3; ++li) {
-        const BitLevel& F = v->occ[li - 1];
+    for (int li = 0; li < 3; ++li) {
+        const BitLevel& F = li ? v->occ[li - 1] : v->tex;
         BitLevel& L = v->occ[li];
         k_occ_coarsen<<<grid_of(L), 256, 0, c->stream>>>(F.d_words, F.cy, F.cz, F.pitch, L.cy, L.cz, L.pitch, L.d_words);
         VXL_LAUNCH_CHECK(c);
@@ -143,12 +147,12 @@ int vxl_volume_build_occupancy(vxl_volume* v) {
     return VXL_OK;
 }
 
-/* diagnostics: download one occupancy level unpacked to 0/1 bytes [cz][cy][cx]; level = 2, 3, 4 (plain, cell =
+/* diagnostics: download one occupancy level unpacked to 0/1 bytes [cz][cy][cx]; level = 1, 2, 3, 4 (plain, cell =
  * 2^level voxels) or 13, 14 (dilated levels 3, 4, including their 1-cell border); out_dims = {cx, cy, cz} */
 int vxl_volume_debug_occupancy(vxl_volume* v, int level, uint8_t* host_out, int* out_dims) {
-    if (!v || !((level >= 2 && level <= 4) || level == 13 || level == 14)) { set_error("vxl_volume_debug_occupancy: bad argument"); return VXL_ERR_INVALID; }
+    if (!v || !((level >= 1 && level <= 4) || level == 13 || level == 14)) { set_error("vxl_volume_debug_occupancy: bad argument"); return VXL_ERR_INVALID; }
     if (v->dirty || !v->occ[0].d_words) { if (int e = vxl_volume_build_occupancy(v)) return e; }
-    const BitLevel& L = level < 10 ? v->occ[level - 2] : v->dil[level - 13];
+    const BitLevel& L = level == 1 ? v->tex : (level < 10 ? v->occ[level - 2] : v->dil[level - 13]);
     if (out_dims) { out_dims[0] = L.cx; out_dims[1] = L.cy; out_dims[2] = L.cz; }
     if (!host_out) return VXL_OK;
     const size_t words = (size_t)L.pitch * L.cy * L.cz;

@@ -102,19 +102,21 @@ struct BlockShared {
     unsigned acc[4];
     uint32_t tile[G::TY * G::TY * G::TW];     // from here on: kernel variant 0 allocates only the header
     uint32_t dtile[G::DT * G::DT * G::DW];
+    uint32_t ntile[G::NEAR ? NEAR_T * NEAR_T : 1];
 };
 template <typename G, bool FAST>
 constexpr size_t smem_bytes() {
     typedef BlockShared<G> BS;
-    return FAST ? sizeof(BS) : sizeof(BS) - sizeof(uint32_t) * (G::TY * G::TY * G::TW + G::DT * G::DT * G::DW);
+    return FAST ? sizeof(BS) : sizeof(BS) - sizeof(uint32_t) * (G::TY * G::TY * G::TW + G::DT * G::DT * G::DW + (G::NEAR ? NEAR_T * NEAR_T : 1));
 }
 // Tile geometry per pass.  Plain tile: cells of 2^SHIFT voxels, TW*32 x TY x TY cells.  Dilated tile: cells of
 // 2^(SHIFT+1) voxels, DW*32 x DT x DT cells, covering at least the plain tile.  GH: half width of a probe group of the
 // Sparse march (GH * max|stepDir_a| must stay <= the dilated cell: 7 * 1.0 <= 8, 10 * 1.5 <= 16).
-// 58.8 KB + 10.4 KB + 4 KB per block: three 512-thread blocks per SM.
-struct AmbientGeom { static constexpr int SHIFT = 2, TY = 70, TW = 3, DT = 36, DW = 2, GH = 7; };    // +-140 voxels (AO 128, sun 128)
-struct LocalGeom   { static constexpr int SHIFT = 2, TY = 70, TW = 3, DT = 36, DW = 2, GH = 7; };    // point/spot rays beyond +-140 voxels take the plain march
-struct ReflGeom    { static constexpr int SHIFT = 3, TY = 70, TW = 3, DT = 36, DW = 2, GH = 10; };   // +-280 voxels (164 steps * |wd| <= 1.5)
+// NEAR: also stage the near tile (texel bits of the 64^3 voxels around the ray origins, 4 KB; vxl_bitmarch.cuh).
+// 57.1 / 58.8 KB + 10.4 KB + 4 KB LUTs (+ 4 KB near tile) per block: three 512-thread blocks per SM (<= 75 KB each).
+struct AmbientGeom { static constexpr int SHIFT = 2, TY = 69, TW = 3, DT = 36, DW = 2, GH = 7; static constexpr bool NEAR = true; };     // +-138 voxels (AO 128, sun 128)
+struct LocalGeom   { static constexpr int SHIFT = 2, TY = 70, TW = 3, DT = 36, DW = 2, GH = 7; static constexpr bool NEAR = false; };    // point/spot rays beyond +-140 voxels take the plain march
+struct ReflGeom    { static constexpr int SHIFT = 3, TY = 70, TW = 3, DT = 36, DW = 2, GH = 10; static constexpr bool NEAR = false; };   // +-280 voxels (164 steps * |wd| <= 1.5)
 
 // Bounding box of the block's ray origins -> tile placement -> stage the occupancy tile.
 // `hint` is (close to) the thread's ray origin in voxel units; threads without rays pass valid = false.
@@ -124,6 +126,7 @@ __device__ __forceinline__ BitTile block_prologue(const VolView& V, BlockShared<
     BitTile T;
     T.w = S.tile; T.ox = T.oy = T.oz = 0; T.enabled = false;
     T.wd = S.dtile; T.dx = T.dy = T.dz = 0;
+    T.wn = nullptr; T.nx = T.ny = T.nz = 0;
     constexpr int TPC = 1 << (G::SHIFT - 1);                // texels per cell edge
     T.direct = (V.sx % TPC == 0) && (V.sy % TPC == 0) && (V.sz % TPC == 0) && ((unsigned long long)V.sx * V.sy * V.sz < (1ull << 32));
     T.koff = TileAddr<G::SHIFT, G::TY, G::TW>::texel_koff(V);
@@ -148,6 +151,11 @@ __device__ __forceinline__ BitTile block_prologue(const VolView& V, BlockShared<
     T.dx = T.ox >> 1; T.dy = T.oy >> 1; T.dz = T.oz >> 1;   // floor: the dilated tile starts at or before the plain one
     stage_bits<G::TY, G::TW>(S.tile, V.occ[G::SHIFT - 2], T.ox, T.oy, T.oz);
     stage_bits<G::DT, G::DW>(S.dtile, V.dil[G::SHIFT - 2], T.dx, T.dy, T.dz);
+    if (G::NEAR) {
+        T.nx = (cx >> 1) - NEAR_T / 2; T.ny = (cy >> 1) - NEAR_T / 2; T.nz = (cz >> 1) - NEAR_T / 2;
+        stage_bits<NEAR_T, 1>(S.ntile, V.tex, T.nx, T.ny, T.nz);
+        T.wn = S.ntile;
+    }
     __syncthreads();
     T.enabled = true;
     return T;
@@ -178,6 +186,8 @@ __device__ __forceinline__ void flush_stats(BS& S, unsigned long long* __restric
         if (v) atomicAdd(&g_stats[(blockIdx.x & (STAT_SLOTS - 1)) * 4 + threadIdx.x], (unsigned long long)v);
     }
 }
+
+constexpr int AO_N2 = 23;          // phase-2 probes of a SuperSparse ray with dist = 128: d = 17.5, 22.5, ..., 127.5 (:121)
 
 // -------------------------------------------------------------------------------------------------
 // LightAmbient.frag:134-175 + calculateAmbientIrradiance :111-126
@@ -234,7 +244,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_ambient(VolV
                     const uint32_t ni = (i == 0) ? n : get_noise(F, K, p, i);
                     const float3 rv = cosine_sample_hemisphere(S.lut, ni, ni >> 8);                       // :118
                     const float3 dir = tangent * rv.x + bitangent * rv.y + normal * rv.z;                 // :119
-                    const float d = ray_march<MODE, true, false, G>(V, C, origin, dir, 128.0f, steps, exact) / 128.0f;   // :121
+                    const float d = (MODE > 0 ? march_scan_super<false, MODE == 2, G::NEAR, G::SHIFT, G::TY, G::TW, AO_N2>(V, C, origin, dir, 128.0f, steps, nullptr, exact)
+                                              : march<false>(V, origin, dir, 128.0f, 2.5f, steps, nullptr)) / 128.0f;            // :121
                     acc += d * d;
                 }
                 ao = (acc / (float)n_ao) * 0.05f;                                                         // :125

@@ -323,6 +323,7 @@ int vxl_volume_destroy(vxl_volume* v) {
     if (!v) return VXL_OK;
     cudaStreamSynchronize(v->ctx->stream);
     cudaFree(v->d_bytes);
+    cudaFree(v->tex.d_words);
     for (auto& L : v->occ) cudaFree(L.d_words);
     for (auto& L : v->dil) cudaFree(L.d_words);
     delete v;
