@@ -64,7 +64,7 @@ struct Emul {
 
 template <int SHIFT, int TY, int TW, int DT, int DW, int GH, bool SCAN = false>
 void trace_geom(Emul* e, const float* rays, long long n, int variant, const int* center, int fast, int direct, int lockstep, vxl_hit* out,
-                unsigned long long* counters, bool near = true) {
+                unsigned long long* counters, bool near = true, bool pre = false) {
     VolView V;
     V.bytes = e->vol.data(); V.sx = e->sx; V.sy = e->sy; V.sz = e->sz;
     std::vector<uint32_t> w, wd;
@@ -90,7 +90,10 @@ void trace_geom(Emul* e, const float* rays, long long n, int variant, const int*
         unsigned fetched = 0;
         const float3 o = make_float3(r[0], r[1], r[2]), d = make_float3(r[3], r[4], r[5]);
         if (SCAN && variant == 1 && r[6] == 128.0f) {
-            if (near) march_scan_super<true, true, true, SHIFT, TY, TW, 23>(V, T, o, d, r[6], steps, &M, fetched);
+            if (near && pre) {          // bundle precheck with the ray's own |dir| as the bound
+                const ScanPre P = scan_precheck<SHIFT, TY, TW>(T, o, make_float3(fabsf(d.x), fabsf(d.y), fabsf(d.z)), 129.0f, 20.0f);
+                march_scan_super<true, true, true, SHIFT, TY, TW, 23>(V, T, o, d, r[6], steps, &M, fetched, P);
+            } else if (near) march_scan_super<true, true, true, SHIFT, TY, TW, 23>(V, T, o, d, r[6], steps, &M, fetched);
             else march_scan_super<true, true, false, SHIFT, TY, TW, 23>(V, T, o, d, r[6], steps, &M, fetched);
         } else if (lockstep) {
             if (variant == 0) march_bits<false, true, true, true, SHIFT, TY, TW, DT, DW, GH>(V, T, o, d, r[6], steps, &M, fetched);
@@ -139,7 +142,8 @@ void emul_trace(void* h, const float* rays, long long n, int variant, const int*
     // the geometries of vxl_passes.cu (AmbientGeom == LocalGeom, ReflGeom) and a GH = 0 twin without probe groups
     if (geom == 0) trace_geom<2, 69, 3, 36, 2, 7>(e, rays, n, variant, center, fast, direct, lockstep, out, counters);
     else if (geom == 3) trace_geom<2, 69, 3, 36, 2, 7, true>(e, rays, n, variant, center, fast, direct, lockstep, out, counters);   // AO rays (SuperSparse, dist 128) by scan + resolve, near tile
-    else if (geom == 4) trace_geom<2, 69, 3, 36, 2, 7, true>(e, rays, n, variant, center, fast, direct, lockstep, out, counters, false);   // the same without the near tile
+    else if (geom == 4) trace_geom<2, 69, 3, 36, 2, 7, true>(e, rays, n, variant, center, fast, direct, lockstep, out, counters, false);
+    else if (geom == 5) trace_geom<2, 69, 3, 36, 2, 7, true>(e, rays, n, variant, center, fast, direct, lockstep, out, counters, true, true);   // with the per-bundle precheck   // the same without the near tile
     else if (geom == 1) trace_geom<2, 70, 3, 36, 2, 0>(e, rays, n, variant, center, fast, direct, lockstep, out, counters);
     else trace_geom<3, 70, 3, 36, 2, 10>(e, rays, n, variant, center, fast, direct, lockstep, out, counters);
 }

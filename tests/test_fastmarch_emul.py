@@ -97,6 +97,9 @@ def test_emulated_scan_march_matches_oracle_on_ao_like_rays(oracle, terrain, emu
         assert steps == int(want["steps"].sum())
         got, fetched_far, _ = emul.trace(rays, 1, center, geom="scan_far")       # without the near (texel-level) tile
         _compare(got, want)
+        got, fetched_pre, _ = emul.trace(rays, 1, center, geom="scan_pre")       # eligibility from the bundle precheck
+        _compare(got, want)
+        assert fetched_pre <= fetched_far
         assert fetched < fetched_far
         total_fetched += fetched
         total_steps += steps
@@ -126,7 +129,7 @@ def test_emulated_fast_march_matches_oracle_on_arbitrary_rays(oracle, terrain, e
     rays["dist"][6 * k:] = np.where(rs.uniform(size=len(rays) - 6 * k) < 0.5, np.float32(128.0), rays["dist"][6 * k:])
     want = oracle.trace_rays(vol, rays, variant)
     for geom, center in [("ambient", (sx, sy, sz)), ("nogroup", (10, 2 * sy - 5, 2 * sz - 3)), ("reflection", (-40, 50, 300)),
-                         ("ambient", (3, 3, 3)), ("scan", (sx, sy, sz)), ("scan", (3, 3, 3))]:
+                         ("ambient", (3, 3, 3)), ("scan", (sx, sy, sz)), ("scan", (3, 3, 3)), ("scan_pre", (sx, sy, sz)), ("scan_pre", (2, 5, 3))]:
         got, _, steps = emul.trace(rays, variant, center, geom=geom)
         _compare(got, want)
 

@@ -373,14 +373,39 @@ VXL_DI unsigned funnel_r(unsigned lo, unsigned hi, unsigned sh) {
 // KN = 8 probes (d <= 25) stay inside it tests those probes against the texel bits instead of the 4-voxel cells: a
 // phase-2 probe is then answered exactly (the bit IS getVolumeAt(pos, 1)), and a phase-1 probe is a candidate only when
 // its texel is non-zero (a quarter of the cell-level candidates, measured on config 3).
+// ScanPre: what the caller already proved for every ray of a bundle that shares `origin` and whose directions obey
+// |dir_a| <= bound_a (the 16 AO rays of a pixel): the box origin +- reach * bound lies inside the tile / the near tile.
+struct ScanPre { bool ok, near_ok; float hi_max; };
+
+template <int SHIFT, int TY, int TW>
+VXL_DI ScanPre scan_precheck(const BitTile& T, float3 origin, float3 bound, float reach, float near_reach) {
+    ScanPre P;
+    const float cell = (float)(1 << SHIFT);
+    const float3 r = bound * (reach * 1.00002f);
+    const float3 lo = origin - r, hi = origin + r;
+    const float3 tlo = make_float3((float)T.ox * cell, (float)T.oy * cell, (float)T.oz * cell);
+    bool ok = T.enabled && T.direct;
+    ok = ok && (lo.x >= fmaxf(tlo.x, 0.0f) + BM_MARGIN) && (lo.y >= fmaxf(tlo.y, 0.0f) + BM_MARGIN) && (lo.z >= fmaxf(tlo.z, 0.0f) + BM_MARGIN);
+    ok = ok && (hi.x <= fminf(tlo.x + (float)(TW * 32) * cell, BM_MAXCOORD) - BM_MARGIN) &&
+         (hi.y <= fminf(tlo.y + (float)TY * cell, BM_MAXCOORD) - BM_MARGIN) && (hi.z <= fminf(tlo.z + (float)TY * cell, BM_MAXCOORD) - BM_MARGIN);
+    P.ok = ok;                                                             // NaN anywhere makes a comparison fail
+    P.hi_max = fmaxf(fmaxf(hi.x, hi.y), hi.z);
+    const float3 n = bound * (near_reach * 1.00002f);
+    const float lx = (float)T.nx * 2.0f + BM_MARGIN, ly = (float)T.ny * 2.0f + BM_MARGIN, lz = (float)T.nz * 2.0f + BM_MARGIN;
+    const float w = (float)(2 * NEAR_T) - 2.0f * BM_MARGIN;
+    P.near_ok = ok && T.wn != nullptr && origin.x - n.x >= lx && origin.x + n.x <= lx + w && origin.y - n.y >= ly && origin.y + n.y <= ly + w &&
+                origin.z - n.z >= lz && origin.z + n.z <= lz + w;
+    return P;
+}
+
 template <bool RECORD, bool COUNT, bool NEAR, int SHIFT, int TY, int TW, int N2>
 VXL_DI float march_scan_super(const VolView& V, const BitTile& T, float3 origin, float3 dir, float dist, int& steps_out,
-                              MarchResult* rec, unsigned& fetched) {
+                              MarchResult* rec, unsigned& fetched, ScanPre pre = ScanPre{false, false, 0.0f}) {
     constexpr int N1 = 6, N = N1 + N2, KN = 8;
     static_assert(N <= 32 && KN <= N, "candidate mask is one word");
     const float lim = fminf(dist, 164.0f);
-    float hi_max;
-    if (!T.direct || !tile_eligible<SHIFT, TY, TW>(T, origin, dir, fmaxf(lim, 16.0f) + 1.0f, hi_max))
+    float hi_max = pre.hi_max;
+    if (!pre.ok && (!T.direct || !tile_eligible<SHIFT, TY, TW>(T, origin, dir, fmaxf(lim, 16.0f) + 1.0f, hi_max)))
         return march<RECORD>(V, origin, dir, dist, 2.5f, steps_out, rec);
 
     typedef TileAddr<SHIFT, TY, TW> TA;
@@ -390,8 +415,8 @@ VXL_DI float march_scan_super(const VolView& V, const BitTile& T, float3 origin,
     // ---- scan: probe k ends up in bit k ----
     unsigned cand = 0u;
     float3 pos = origin;
-    bool near_ok = false;
-    if (NEAR) {
+    bool near_ok = pre.near_ok;
+    if (NEAR && !pre.ok) {
         const float3 e = fma3(s1, (float)(2 * (KN - 1) - N1), origin);       // probe KN - 1, up to rounding (<< margin)
         const float lx = (float)T.nx * 2.0f + BM_MARGIN, ly = (float)T.ny * 2.0f + BM_MARGIN, lz = (float)T.nz * 2.0f + BM_MARGIN;
         const float w = (float)(2 * NEAR_T) - 2.0f * BM_MARGIN;

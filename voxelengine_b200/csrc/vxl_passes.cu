@@ -239,12 +239,20 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_ambient(VolV
                 const float3 tangent = fabsf(normal.z) > 0.5f ? make_float3(0.0f, -normal.z, normal.y)
                                                              : make_float3(-normal.y, normal.x, 0.0f);    // :112
                 const float3 bitangent = cross3(normal, tangent);                                         // :113
+                // every AO direction is tangent * x + bitangent * y + normal * z with |x|, |y|, |z| <= 1: one eligibility
+                // test per pixel covers all its rays (reach: 128 + 1 voxels of march, 20 for the near tile's 8 probes)
+                ScanPre pre = ScanPre{false, false, 0.0f};
+                if (MODE > 0) {
+                    const float3 bound = make_float3(fabsf(tangent.x) + fabsf(bitangent.x) + fabsf(normal.x), fabsf(tangent.y) + fabsf(bitangent.y) + fabsf(normal.y),
+                                                     fabsf(tangent.z) + fabsf(bitangent.z) + fabsf(normal.z));
+                    pre = scan_precheck<G::SHIFT, G::TY, G::TW>(C, origin, bound, 129.0f, 20.0f);
+                }
                 float acc = 0.0f;
                 for (int i = 0; i < n_ao; ++i) {
                     const uint32_t ni = (i == 0) ? n : get_noise(F, K, p, i);
                     const float3 rv = cosine_sample_hemisphere(S.lut, ni, ni >> 8);                       // :118
                     const float3 dir = tangent * rv.x + bitangent * rv.y + normal * rv.z;                 // :119
-                    const float d = (MODE > 0 ? march_scan_super<false, MODE == 2, G::NEAR, G::SHIFT, G::TY, G::TW, AO_N2>(V, C, origin, dir, 128.0f, steps, nullptr, exact)
+                    const float d = (MODE > 0 ? march_scan_super<false, MODE == 2, G::NEAR, G::SHIFT, G::TY, G::TW, AO_N2>(V, C, origin, dir, 128.0f, steps, nullptr, exact, pre)
                                               : march<false>(V, origin, dir, 128.0f, 2.5f, steps, nullptr)) / 128.0f;            // :121
                     acc += d * d;
                 }
