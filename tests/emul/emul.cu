@@ -91,10 +91,7 @@ void trace_geom(Emul* e, const float* rays, long long n, int variant, const int*
         const float3 o = make_float3(r[0], r[1], r[2]), d = make_float3(r[3], r[4], r[5]);
         bool done = false;
         if constexpr (SCAN) { done = true;
-        if (variant == 0) {
-            if (near) march_scan_sparse<true, true, true, SHIFT, TY, TW, DT, DW, GH>(V, T, o, d, r[6], steps, &M, fetched);
-            else march_scan_sparse<true, true, false, SHIFT, TY, TW, DT, DW, GH>(V, T, o, d, r[6], steps, &M, fetched);
-        } else if (variant == 1 && r[6] == 128.0f) {
+        if (variant == 1 && r[6] == 128.0f) {
             if (near && pre) {          // bundle precheck with the ray's own |dir| as the bound
                 const ScanPre P = scan_precheck<SHIFT, TY, TW>(T, o, make_float3(fabsf(d.x), fabsf(d.y), fabsf(d.z)), 129.0f, 20.0f);
                 march_scan_super<true, true, true, SHIFT, TY, TW, 23>(V, T, o, d, r[6], steps, &M, fetched, P);
@@ -152,8 +149,6 @@ void emul_trace(void* h, const float* rays, long long n, int variant, const int*
     else if (geom == 4) trace_geom<2, 69, 3, 36, 2, 7, true>(e, rays, n, variant, center, fast, direct, lockstep, out, counters, false);
     else if (geom == 5) trace_geom<2, 69, 3, 36, 2, 7, true>(e, rays, n, variant, center, fast, direct, lockstep, out, counters, true, true);   // with the per-bundle precheck   // the same without the near tile
     else if (geom == 1) trace_geom<2, 70, 3, 36, 2, 0>(e, rays, n, variant, center, fast, direct, lockstep, out, counters);
-    else if (geom == 6) trace_geom<3, 69, 3, 36, 2, 10, true>(e, rays, n, variant, center, fast, direct, lockstep, out, counters);          // reflection geometry, scan marches
-    else if (geom == 7) trace_geom<3, 69, 3, 36, 2, 10, true>(e, rays, n, variant, center, fast, direct, lockstep, out, counters, false);   // ... without the near tile
     else trace_geom<3, 70, 3, 36, 2, 10>(e, rays, n, variant, center, fast, direct, lockstep, out, counters);
 }
 

@@ -63,7 +63,7 @@ class Emul:
         lib().emul_level(self.h, shift, out.ctypes.data, dims.ctypes.data)
         return out
 
-    GEOMS = {"ambient": 0, "nogroup": 1, "reflection": 2, "scan": 3, "scan_far": 4, "scan_pre": 5, "scan_refl": 6, "scan_refl_far": 7}
+    GEOMS = {"ambient": 0, "nogroup": 1, "reflection": 2, "scan": 3, "scan_far": 4, "scan_pre": 5}
 
     def trace(self, rays: np.ndarray, variant: int, center, fast: bool = True, geom: str = "ambient", direct: bool = True, lockstep: bool = True):
         """-> (hit records, probes that read the volume, total probe count)"""

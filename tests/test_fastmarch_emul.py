@@ -110,26 +110,6 @@ def test_emulated_scan_march_matches_oracle_on_ao_like_rays(oracle, terrain, emu
     _compare(got, oracle.trace_rays(vol, rays, 1))
 
 
-@pytest.mark.parametrize("geom", ["scan", "scan_far", "scan_refl", "scan_refl_far"])
-def test_emulated_scan_march_matches_oracle_on_sparse_rays(oracle, terrain, emul, geom):
-    """Sparse rays (sun / point / reflection shadows) through probe groups + scan + resolve: dilated-level group
-    skips, group scans with a ragged last group, quarter-voxel pinning of the position-hashed bit in phase 1, texel
-    pinning in phase 2, exact replays; with and without the near tile, both tile geometries."""
-    vol = terrain["volume"]
-    rs = np.random.RandomState(77)
-    total_fetched = total_steps = 0
-    for center in _surface_points(vol, 8, rs):
-        rays = _surface_rays(rs, vol, 20_000, center, 6.0, [128.0, 256.0, 40.0, 73.3, 17.0, 10.0, 164.0, 500.0, 16.0, 16.5, 31.0, 31.0001])
-        rays["oy"] -= rs.uniform(-1.0, 2.5, size=len(rays)).astype(np.float32)
-        want = oracle.trace_rays(vol, rays, 0)
-        got, fetched, steps = emul.trace(rays, 0, center, geom=geom)
-        _compare(got, want)
-        assert steps == int(want["steps"].sum())
-        total_fetched += fetched
-        total_steps += steps
-    assert 0 < total_fetched < 0.5 * total_steps, (total_fetched, total_steps)
-
-
 @pytest.mark.parametrize("variant", [0, 1])
 def test_emulated_fast_march_matches_oracle_on_arbitrary_rays(oracle, terrain, emul, variant):
     """Rays that start outside the volume, at negative coordinates, axis-parallel, on voxel boundaries, far from
@@ -149,7 +129,7 @@ def test_emulated_fast_march_matches_oracle_on_arbitrary_rays(oracle, terrain, e
     rays["dist"][6 * k:] = np.where(rs.uniform(size=len(rays) - 6 * k) < 0.5, np.float32(128.0), rays["dist"][6 * k:])
     want = oracle.trace_rays(vol, rays, variant)
     for geom, center in [("ambient", (sx, sy, sz)), ("nogroup", (10, 2 * sy - 5, 2 * sz - 3)), ("reflection", (-40, 50, 300)),
-                         ("ambient", (3, 3, 3)), ("scan", (sx, sy, sz)), ("scan", (3, 3, 3)), ("scan_pre", (sx, sy, sz)), ("scan_pre", (2, 5, 3)), ("scan_refl", (sx, sy, sz)), ("scan_refl_far", (-40, 50, 300))]:
+                         ("ambient", (3, 3, 3)), ("scan", (sx, sy, sz)), ("scan", (3, 3, 3)), ("scan_pre", (sx, sy, sz)), ("scan_pre", (2, 5, 3))]:
         got, _, steps = emul.trace(rays, variant, center, geom=geom)
         _compare(got, want)
 

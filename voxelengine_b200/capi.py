@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvxl.so")
+LIB_PATH = os.environ.get("VXL_LIB") or os.path.join(_HERE, "libvxl.so")     # VXL_LIB: A/B experiments with differently compiled kernels
 
 # every symbol include/vxl.h declares (tests check the library exports each one)
 SYMBOLS = [

@@ -60,16 +60,6 @@ VXL_DI unsigned magic_floor_bits(float p, float m, int S, int o) {
 #endif
 }
 
-// bits of (p + 2^21) rounded toward zero: the mantissa field holds floor(4 p) for 0 <= p < 2^19
-VXL_DI unsigned magic_floor_bits4(float p, float m) {
-#ifdef __CUDA_ARCH__
-    return __float_as_uint(__fadd_rz(p, m));
-#else
-    (void)m;
-    return 0x4A000000u + (unsigned)(int)floorf(p * 4.0f);
-#endif
-}
-
 constexpr int NEAR_T = 32;                   // near tile: 32^3 texels = 64^3 voxels = 4 KB
 
 // Lookup in the near tile: word = z * 32 + y, bit = x, all relative to the tile origin.
@@ -513,177 +503,6 @@ VXL_DI float march_scan_super(const VolView& V, const BitTile& T, float3 origin,
             rec->vx = h ? f2i(p.x) : 0; rec->vy = h ? f2i(p.y) : 0; rec->vz = h ? f2i(p.z) : 0;
         }
         rec->pos = h ? p : make_float3(0.f, 0.f, 0.f);
-    }
-    return d;
-}
-
-// ---- Sparse rays (sun, point-light, reflection shadows) by probe groups + scan + resolve ------------------------
-// Phase 1 (31 probes, step 0.5) is one group; phase 2 (step 1) runs in groups of G = 2 GH + 1 probes.  One test of
-// the dilated level at a group's middle probe clears the whole group when it reads 0 (every probe of the group is
-// within one dilated cell of the middle one; checked per ray); the group then costs its additions only.  A group that
-// is not clear is SCANNED like the AO rays (occupancy bits of its probes packed into one word, branch-free), and its
-// set bits are RESOLVED in probe order with the reference's texel test at q = fma(stepDir, i, group start), which is
-// within eps of the recurrence's position; q - eps and q + eps falling into the same quarter voxel (phase 1: the
-// position-hashed bit flips at multiples of 0.25, Light.frag:143-147) / the same texel (phase 2) pins the result,
-// otherwise the recurrence is replayed from the group start.  With the near tile, phase 1 scans texel bits.
-template <bool RECORD, bool COUNT, bool NEAR, int SHIFT, int TY, int TW, int DT, int DW, int GH>
-VXL_DI float march_scan_sparse(const VolView& V, const BitTile& T, float3 origin, float3 dir, float dist, int& steps_out,
-                               MarchResult* rec, unsigned& fetched) {
-    constexpr int N1 = 31, G = 2 * GH + 1;
-    static_assert(G <= 32 && GH >= 1, "group mask is one word");
-    const float lim = fminf(dist, 164.0f);
-    float hi_max;
-    if (!T.direct || !tile_eligible<SHIFT, TY, TW>(T, origin, dir, fmaxf(lim, 16.0f) + 1.0f, hi_max))
-        return march<RECORD>(V, origin, dir, dist, 0.5f, steps_out, rec);
-
-    typedef TileAddr<SHIFT, TY, TW> TA;
-    const TA A(T);
-    const TileAddr<SHIFT + 1, DT, DW> D(T.wd, T.dx, T.dy, T.dz);
-    const float eps = (hi_max + 1.0f) * (1.0f / 262144.0f);
-    const float dcell = (float)(2 << SHIFT) - 2.0f * BM_MARGIN;
-    const unsigned SXY = (unsigned)(V.sx * V.sy), SX = (unsigned)V.sx;
-    float3 s = dir * 0.5f;
-    float3 pos = origin;
-    int hit = -1;                       // probe index over both phases
-    unsigned hbit = 0u;
-    float3 hpos = origin;
-
-    // ---- phase 1 (:138-154) ----
-    {
-        const float m1 = fmaxf(fmaxf(fabsf(s.x), fabsf(s.y)), fabsf(s.z));
-        float3 mid = origin;
-#pragma unroll
-        for (int i = 0; i < 15; ++i) mid = mid + s;                         // probe 15, the middle of 0..30
-        if (15.0f * m1 <= dcell && !D.test(mid)) {
-            pos = mid;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) pos = pos + s;
-        } else {
-            unsigned cand = 0u;
-            bool near_ok = false;
-            if (NEAR) {
-                const float3 e = fma3(s, 30.0f, origin);
-                const float lx = (float)T.nx * 2.0f + BM_MARGIN, ly = (float)T.ny * 2.0f + BM_MARGIN, lz = (float)T.nz * 2.0f + BM_MARGIN;
-                const float w = (float)(2 * NEAR_T) - 2.0f * BM_MARGIN;
-                near_ok = T.wn != nullptr && fminf(origin.x, e.x) >= lx && fmaxf(origin.x, e.x) <= lx + w && fminf(origin.y, e.y) >= ly &&
-                          fmaxf(origin.y, e.y) <= ly + w && fminf(origin.z, e.z) >= lz && fmaxf(origin.z, e.z) <= lz + w;
-            }
-            if (NEAR && near_ok) {
-                const NearAddr B(T);
-#pragma unroll
-                for (int k = 0; k < N1; ++k) { cand = funnel_r(cand, B.bit(pos), 1u); pos = pos + s; }
-            } else {
-#pragma unroll
-                for (int k = 0; k < N1; ++k) { cand = funnel_r(cand, A.bit(pos), 1u); pos = pos + s; }
-            }
-            cand >>= (32 - N1);
-            while (cand) {
-#ifdef __CUDA_ARCH__
-                const int k = __ffs((int)cand) - 1;
-#else
-                const int k = __builtin_ctz(cand);
-#endif
-                cand &= cand - 1u;
-                if (COUNT) ++fetched;
-                const float3 q = fma3(s, (float)k, origin);
-                const float MQ = 2097152.0f;                                 // 2^21: floats spaced 0.25
-                const unsigned ax = magic_floor_bits4(q.x - eps, MQ), bx = magic_floor_bits4(q.x + eps, MQ);
-                const unsigned ay = magic_floor_bits4(q.y - eps, MQ), by = magic_floor_bits4(q.y + eps, MQ);
-                const unsigned az = magic_floor_bits4(q.z - eps, MQ), bz = magic_floor_bits4(q.z + eps, MQ);
-                unsigned off, bit;
-                float3 p = q;
-                if ((ax ^ bx) | (ay ^ by) | (az ^ bz)) {                     // within eps of a quarter-voxel plane: exact position
-                    p = origin;
-                    for (int i = 0; i < k; ++i) p = p + s;
-                    off = TA::texel_offset(V, T.koff, p);
-                    bit = (gmod(p.x, 0.5f) > 0.25f ? 1u : 0u) + (gmod(p.y, 0.5f) > 0.25f ? 2u : 0u) + (gmod(p.z, 0.5f) > 0.25f ? 4u : 0u);
-                } else {                                                     // floor(4 q) per axis: texel = >> 3, hashed bit = & 1
-                    off = ((bz & 0x1FFFFFu) >> 3) * SXY + ((by & 0x1FFFFFu) >> 3) * SX + ((bx & 0x1FFFFFu) >> 3);
-                    bit = (bx & 1u) | ((by & 1u) << 1) | ((bz & 1u) << 2);
-                }
-                const unsigned v = V.bytes[off];
-                if ((v >> bit) & 1u) {
-                    hit = k; hbit = bit;
-                    if (RECORD) { hpos = origin; for (int i = 0; i < k; ++i) hpos = hpos + s; }
-                    break;
-                }
-            }
-        }
-    }
-
-    // ---- phase 2 (:156-170) ----
-    const int n2 = phase2_count<false>(lim);
-    if (hit < 0) {
-        s = s * 2.0f;
-        const float m2 = fmaxf(fmaxf(fabsf(s.x), fabsf(s.y)), fabsf(s.z));
-        const bool can_group = (float)GH * m2 <= dcell;
-        int j = 0;
-#pragma unroll 1
-        while (j < n2) {
-            const int cnt = n2 - j < G ? n2 - j : G;
-            const float3 p0 = pos;
-            if (cnt == G && can_group) {
-                float3 mid = pos;
-#pragma unroll
-                for (int i = 0; i < GH; ++i) mid = mid + s;                  // middle probe of the group
-                if (!D.test(mid)) {
-                    pos = mid;
-#pragma unroll
-                    for (int i = 0; i < GH + 1; ++i) pos = pos + s;          // first probe of the next group
-                    j += G;
-                    continue;
-                }
-            }
-            unsigned cand = 0u;
-#pragma unroll
-            for (int i = 0; i < G; ++i) {
-                unsigned b = 0u;
-                if (i < cnt) { b = A.bit(pos); pos = pos + s; }
-                cand = funnel_r(cand, b, 1u);
-            }
-            cand >>= (32 - G);
-            while (cand) {
-#ifdef __CUDA_ARCH__
-                const int i = __ffs((int)cand) - 1;
-#else
-                const int i = __builtin_ctz(cand);
-#endif
-                cand &= cand - 1u;
-                if (COUNT) ++fetched;
-                const float3 q = fma3(s, (float)i, p0);
-                const float M1 = 16777216.0f;
-                const unsigned ax = magic_floor_bits(q.x - eps, M1, 1, 0), bx = magic_floor_bits(q.x + eps, M1, 1, 0);
-                const unsigned ay = magic_floor_bits(q.y - eps, M1, 1, 0), by = magic_floor_bits(q.y + eps, M1, 1, 0);
-                const unsigned az = magic_floor_bits(q.z - eps, M1, 1, 0), bz = magic_floor_bits(q.z + eps, M1, 1, 0);
-                unsigned off = bz * SXY + by * SX + bx - T.koff;
-                if ((ax ^ bx) | (ay ^ by) | (az ^ bz)) {                     // within eps of a texel face: exact position
-                    float3 p = p0;
-                    for (int r = 0; r < i; ++r) p = p + s;
-                    off = TA::texel_offset(V, T.koff, p);
-                }
-                if (V.bytes[off] != 0u) {
-                    hit = N1 + j + i;
-                    if (RECORD) { hpos = p0; for (int r = 0; r < i; ++r) hpos = hpos + s; }
-                    break;
-                }
-            }
-            if (hit >= 0) break;
-            j += cnt;
-        }
-    }
-    const bool h = hit >= 0;
-    const int nsteps = h ? hit + 1 : N1 + n2;
-    const float d = !h ? dist : (hit < N1 ? 0.5f * (float)(hit + 1) : 16.0f + (float)(hit - N1));
-    steps_out += nsteps;
-    if (RECORD) {
-        rec->d = d; rec->steps = nsteps; rec->status = !h ? 0 : (hit < N1 ? 1 : 2);
-        if (h && hit < N1) {
-            const int tx = f2i(hpos.x / 2.0f), ty = f2i(hpos.y / 2.0f), tz = f2i(hpos.z / 2.0f);
-            rec->vx = tx * 2 + (int)(hbit & 1u); rec->vy = ty * 2 + (int)((hbit >> 1) & 1u); rec->vz = tz * 2 + (int)((hbit >> 2) & 1u);
-        } else {
-            rec->vx = h ? f2i(hpos.x) : 0; rec->vy = h ? f2i(hpos.y) : 0; rec->vz = h ? f2i(hpos.z) : 0;
-        }
-        rec->pos = h ? hpos : make_float3(0.f, 0.f, 0.f);
     }
     return d;
 }

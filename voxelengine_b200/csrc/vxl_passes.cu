@@ -115,8 +115,8 @@ constexpr size_t smem_bytes() {
 // NEAR: also stage the near tile (texel bits of the 64^3 voxels around the ray origins, 4 KB; vxl_bitmarch.cuh).
 // 57.1 / 58.8 KB + 10.4 KB + 4 KB LUTs (+ 4 KB near tile) per block: three 512-thread blocks per SM (<= 75 KB each).
 struct AmbientGeom { static constexpr int SHIFT = 2, TY = 69, TW = 3, DT = 36, DW = 2, GH = 7; static constexpr bool NEAR = true; };     // +-138 voxels (AO 128, sun 128)
-struct LocalGeom   { static constexpr int SHIFT = 2, TY = 69, TW = 3, DT = 36, DW = 2, GH = 7; static constexpr bool NEAR = true; };     // point/spot rays beyond +-138 voxels take the plain march
-struct ReflGeom    { static constexpr int SHIFT = 3, TY = 69, TW = 3, DT = 36, DW = 2, GH = 10; static constexpr bool NEAR = true; };    // +-276 voxels (164 steps * |wd| <= 1.5)
+struct LocalGeom   { static constexpr int SHIFT = 2, TY = 70, TW = 3, DT = 36, DW = 2, GH = 7; static constexpr bool NEAR = false; };    // point/spot rays beyond +-140 voxels take the plain march
+struct ReflGeom    { static constexpr int SHIFT = 3, TY = 70, TW = 3, DT = 36, DW = 2, GH = 10; static constexpr bool NEAR = false; };   // +-280 voxels (164 steps * |wd| <= 1.5)
 
 // Bounding box of the block's ray origins -> tile placement -> stage the occupancy tile.
 // `hint` is (close to) the thread's ray origin in voxel units; threads without rays pass valid = false.
@@ -166,7 +166,6 @@ __device__ __forceinline__ BitTile block_prologue(const VolView& V, BlockShared<
 // MODE: 0 plain march on the bytes, 1 tile march, 2 tile march that also counts the probes that read the volume
 template <int MODE, bool SUPER, bool UNIFORM, typename G>
 __device__ __forceinline__ float ray_march(const VolView& V, const BitTile& T, float3 origin, float3 dir, float dist, int& steps, unsigned& fetched) {
-    if (MODE > 0 && !SUPER) return march_scan_sparse<false, MODE == 2, G::NEAR, G::SHIFT, G::TY, G::TW, G::DT, G::DW, G::GH>(V, T, origin, dir, dist, steps, nullptr, fetched);
     if (MODE > 0) return march_bits<SUPER, false, UNIFORM, MODE == 2, G::SHIFT, G::TY, G::TW, G::DT, G::DW, G::GH>(V, T, origin, dir, dist, steps, nullptr, fetched);
     return march<false>(V, origin, dir, dist, SUPER ? 2.5f : 0.5f, steps, nullptr);
 }

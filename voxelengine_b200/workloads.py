@@ -98,12 +98,16 @@ class Workload:
         o = self.out
         return dict(shadow=o[0, :n], ao=o[1, :n], spec_t=o[2, :n], point=o[3:, :n])
 
-    def step(self, gather: bool = True):
+    def advance(self):
+        """Dynamic scene: move the entities, re-voxelise them (ShadowVoxSystem::OnUpdate) and rebuild the occupancy levels."""
+        self.entities, self._pos, self._yaw = S.advance_entities(self.entities, self._pos, self._yaw)
+        self.vol.OnUpdate(self.entities, want_regions=False)
+        self.vol.build_occupancy()
+
+    def step(self, gather: bool = True, advance: bool = True):
         """One frame over this rank's tiles; with world > 1, all-gather the packed output tiles."""
-        if self.cfg["scene"] == "dynamic":
-            self.entities, self._pos, self._yaw = S.advance_entities(self.entities, self._pos, self._yaw)
-            self.vol.OnUpdate(self.entities, want_regions=False)
-            self.vol.build_occupancy()
+        if advance and self.cfg["scene"] == "dynamic":
+            self.advance()
         n = self.gb.n_tiles
         o = self.out
         E.LightAmbientPipeline.Get().Use(self.view, self.gb, self.vol, n_ao=self.n_ao, out_shadow=o[0, :n], out_ao=o[1, :n])
