@@ -131,6 +131,7 @@ def run_reference(args):
     from oracle import vxo_py as O
     from voxelengine_b200 import scenes as S
     from voxelengine_b200.workloads import CONFIGS
+    O.set_num_threads(len(os.sched_getaffinity(0)))     # all host threads (torchrun exports OMP_NUM_THREADS=1)
     cfg = CONFIGS[args.config]
     sx, sy, sz = cfg["texels"]
     W, H = cfg["res"]
@@ -304,6 +305,7 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu:
         from oracle import vxo_py as O
+        O.set_num_threads(len(os.sched_getaffinity(0)))
         vol_h = wl.host_volume if wl.host_volume is not None else wl.vol.download()
         gbh = {k: getattr(wl.gb, k).cpu().numpy().view(np.uint32)[0] for k in ("depth24", "normal", "material")}
         gbh["noise"] = wl.gb.noise.cpu().numpy().view(np.uint32)

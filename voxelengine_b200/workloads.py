@@ -88,7 +88,14 @@ class Workload:
             self.host_volume = vol.download()
         elif cfg["scene"] == "dynamic":
             mid = vol.add_model(S.shell_cube_model(16))
-            self.entities, self._pos, self._yaw = S.dynamic_entities(self.texels, cfg["n_entities"], seed=3, model=mid)
+            self.entities, pos, yaw = S.dynamic_entities(self.texels, cfg["n_entities"], seed=3, model=mid)
+            # The motion is INPUT, not part of the measured path: the 60 frames of transforms are generated
+            # once here; a step walks them forwards then backwards so that every frame's `prev` is the previous frame's `cur`.
+            frames, e = [self.entities["cur"].copy()], self.entities
+            for _ in range(59):
+                e, pos, yaw = S.advance_entities(e, pos, yaw)
+                frames.append(e["cur"].copy())
+            self._frames, self._t = np.stack(frames), 0
             vol.OnUpdate(self.entities, want_regions=False)     # first frame: prev = identity (reference quirk)
             self.host_volume = None                              # changes every frame; download on demand
 
@@ -100,7 +107,11 @@ class Workload:
 
     def advance(self):
         """Dynamic scene: move the entities, re-voxelise them (ShadowVoxSystem::OnUpdate) and rebuild the occupancy levels."""
-        self.entities, self._pos, self._yaw = S.advance_entities(self.entities, self._pos, self._yaw)
+        n = len(self._frames)
+        tri = lambda t: (n - 1) - abs((t % (2 * n - 2)) - (n - 1))     # 0, 1, ..., n-1, n-2, ..., 1, 0, 1, ...
+        self._t += 1
+        self.entities["prev"] = self._frames[tri(self._t - 1)]
+        self.entities["cur"] = self._frames[tri(self._t)]
         self.vol.OnUpdate(self.entities, want_regions=False)
         self.vol.build_occupancy()
 
