@@ -1,5 +1,6 @@
 // vxl_api.cu -- context, error reporting, memory helpers, counters and the whole-frame host
 // drop-in of libvxl.so.  No CPU fallback anywhere: every entry point needs a CUDA device.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -32,6 +33,7 @@ int frame_view(const vxl_frame* f, FrameView* out) {
     }
     out->width = f->width; out->height = f->height; out->tile_w = f->tile_w; out->tile_h = f->tile_h;
     out->tile_first = f->tile_first; out->tile_stride = f->tile_stride; out->n_tiles = f->n_tiles; out->tiles_x = tiles_x;
+    out->row0 = 0; out->rows = f->tile_h;
     out->depth24 = f->depth24; out->normal = f->normal; out->material = f->material; out->noise = f->noise;
     return VXL_OK;
 }
@@ -106,6 +108,8 @@ int vxl_ctx_destroy(vxl_ctx* c) {
     for (auto& m : c->models) cudaFree((void*)m.voxels);
     cudaFree(c->d_models); cudaFree(c->d_hkeys); cudaFree(c->d_hvals); cudaFree(c->d_ents); cudaFree(c->d_aabb);
     cudaFree(c->h_planes); cudaFree(c->h_out); cudaFree(c->h_noise);
+    if (c->s_h2d) { cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h); }
+    for (auto& e : c->ev) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return VXL_OK;
@@ -232,32 +236,83 @@ int vxl_lighting_host(vxl_ctx* c, vxl_volume* vol, const vxl_lighting_host_args*
     if (int e = ensure((void**)&c->h_out, &c->h_out_bytes, px * 4 * n_out)) return e;
     if (!c->h_noise) VXL_CUDA(cudaMalloc(&c->h_noise, 512 * 512 * 4));
     uint32_t* d_depth = c->h_planes; uint32_t* d_normal = d_depth + px; uint32_t* d_mat = d_normal + px;
-    VXL_CUDA(cudaMemcpyAsync(d_depth, a->frame.depth24, px * 4, cudaMemcpyHostToDevice, c->stream));
-    VXL_CUDA(cudaMemcpyAsync(d_normal, a->frame.normal, px * 4, cudaMemcpyHostToDevice, c->stream));
-    if (want_rf) VXL_CUDA(cudaMemcpyAsync(d_mat, a->frame.material, px * 4, cudaMemcpyHostToDevice, c->stream));
-    VXL_CUDA(cudaMemcpyAsync(c->h_noise, a->frame.noise, 512 * 512 * 4, cudaMemcpyHostToDevice, c->stream));
+    // Three streams: uploads, passes (the context's stream), read-backs; the frame goes through in NB row bands (rows of
+    // every tile of the shard).  PCIe is full duplex and the copy engines run beside the SMs, so band b+1 uploads and band
+    // b-1 reads back while band b is in the passes; within a band the local-light planes (the largest output) go first.
+    int NB = a->frame.tile_h >= 256 ? 4 : 1;
+    if (const char* nb = getenv("VXL_HOST_BANDS")) NB = std::max(1, std::min(64, atoi(nb)));   // tuning knob
+    const int band_h = ((a->frame.tile_h + NB - 1) / NB + 15) / 16 * 16;          // whole 16-row thread blocks
+    const size_t n_ev = 2 + (size_t)NB * 5;
+    if (!c->s_h2d) {
+        VXL_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+        VXL_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    }
+    while (c->ev.size() < n_ev) { cudaEvent_t e; VXL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->ev.push_back(e); }
+    cudaEvent_t* ev = c->ev.data();
+    const size_t tile_px = (size_t)a->frame.tile_w * a->frame.tile_h;
+    const int nt = a->frame.n_tiles;
+    // rows [r0, r0 + rows) of every tile of a tile-compact plane: nt chunks of rows * tile_w pixels, tile_px apart
+    auto copy_band = [&](void* dst, const void* src, int r0, int rows, cudaMemcpyKind kind, cudaStream_t st) -> cudaError_t {
+        const size_t off = (size_t)r0 * a->frame.tile_w * 4;
+        if (nt == 1) return cudaMemcpyAsync((char*)dst + off, (const char*)src + off, (size_t)rows * a->frame.tile_w * 4, kind, st);
+        return cudaMemcpy2DAsync((char*)dst + off, tile_px * 4, (const char*)src + off, tile_px * 4, (size_t)rows * a->frame.tile_w * 4, (size_t)nt, kind, st);
+    };
+    VXL_CUDA(cudaEventRecord(ev[0], c->stream));                          // order behind whatever the caller queued (voxelise, ...)
+    VXL_CUDA(cudaStreamWaitEvent(c->s_h2d, ev[0], 0));
+    VXL_CUDA(cudaStreamWaitEvent(c->s_d2h, ev[0], 0));
+    VXL_CUDA(cudaMemcpyAsync(c->h_noise, a->frame.noise, 512 * 512 * 4, cudaMemcpyHostToDevice, c->s_h2d));
     vxl_frame fd = a->frame;
     fd.depth24 = d_depth; fd.normal = d_normal; fd.material = d_mat; fd.noise = c->h_noise;
     float* o_shadow = c->h_out; float* o_ao = o_shadow + px; float* o_spec = o_ao + px;
     float* o_pt = o_spec + px; float* o_sp = o_pt + px * (size_t)a->n_point;
-    if (want_amb) {
-        if (int e = vxl_pass_ambient(c, vol, a->view, &fd, a->n_ao, a->out_shadow ? o_shadow : nullptr, a->out_ao ? o_ao : nullptr)) return e;
-        if (a->out_shadow) VXL_CUDA(cudaMemcpyAsync(a->out_shadow, o_shadow, px * 4, cudaMemcpyDeviceToHost, c->stream));
-        if (a->out_ao) VXL_CUDA(cudaMemcpyAsync(a->out_ao, o_ao, px * 4, cudaMemcpyDeviceToHost, c->stream));
+    int rc = VXL_OK;
+    for (int b = 0; b < NB && rc == VXL_OK; ++b) {
+        const int r0 = b * band_h, rows = std::min(band_h, a->frame.tile_h - r0);
+        if (rows <= 0) break;
+        cudaEvent_t* eb = ev + 2 + (size_t)b * 5;
+        VXL_CUDA(copy_band(d_depth, a->frame.depth24, r0, rows, cudaMemcpyHostToDevice, c->s_h2d));
+        VXL_CUDA(copy_band(d_normal, a->frame.normal, r0, rows, cudaMemcpyHostToDevice, c->s_h2d));
+        if (want_rf) VXL_CUDA(copy_band(d_mat, a->frame.material, r0, rows, cudaMemcpyHostToDevice, c->s_h2d));
+        VXL_CUDA(cudaEventRecord(eb[0], c->s_h2d));
+        VXL_CUDA(cudaStreamWaitEvent(c->stream, eb[0], 0));
+        c->band_row0 = r0; c->band_rows = rows;
+        if (want_pt && rc == VXL_OK) {
+            rc = vxl_pass_point(c, vol, a->view, &fd, a->point, a->n_point, o_pt);
+            if (rc == VXL_OK) {
+                cudaEventRecord(eb[1], c->stream); cudaStreamWaitEvent(c->s_d2h, eb[1], 0);
+                for (int l = 0; l < a->n_point; ++l) copy_band(a->out_point_shadow + px * (size_t)l, o_pt + px * (size_t)l, r0, rows, cudaMemcpyDeviceToHost, c->s_d2h);
+            }
+        }
+        if (want_sp && rc == VXL_OK) {
+            rc = vxl_pass_spot(c, vol, a->view, &fd, a->spot, a->n_spot, o_sp);
+            if (rc == VXL_OK) {
+                cudaEventRecord(eb[2], c->stream); cudaStreamWaitEvent(c->s_d2h, eb[2], 0);
+                for (int l = 0; l < a->n_spot; ++l) copy_band(a->out_spot_shadow + px * (size_t)l, o_sp + px * (size_t)l, r0, rows, cudaMemcpyDeviceToHost, c->s_d2h);
+            }
+        }
+        if (want_amb && rc == VXL_OK) {
+            rc = vxl_pass_ambient(c, vol, a->view, &fd, a->n_ao, a->out_shadow ? o_shadow : nullptr, a->out_ao ? o_ao : nullptr);
+            if (rc == VXL_OK) {
+                cudaEventRecord(eb[3], c->stream); cudaStreamWaitEvent(c->s_d2h, eb[3], 0);
+                if (a->out_shadow) copy_band(a->out_shadow, o_shadow, r0, rows, cudaMemcpyDeviceToHost, c->s_d2h);
+                if (a->out_ao) copy_band(a->out_ao, o_ao, r0, rows, cudaMemcpyDeviceToHost, c->s_d2h);
+            }
+        }
+        if (want_rf && rc == VXL_OK) {
+            rc = vxl_pass_reflection(c, vol, a->view, &fd, o_spec);
+            if (rc == VXL_OK) {
+                cudaEventRecord(eb[4], c->stream); cudaStreamWaitEvent(c->s_d2h, eb[4], 0);
+                copy_band(a->out_spec_t, o_spec, r0, rows, cudaMemcpyDeviceToHost, c->s_d2h);
+            }
+        }
     }
-    if (want_pt) {
-        if (int e = vxl_pass_point(c, vol, a->view, &fd, a->point, a->n_point, o_pt)) return e;
-        VXL_CUDA(cudaMemcpyAsync(a->out_point_shadow, o_pt, px * 4 * (size_t)a->n_point, cudaMemcpyDeviceToHost, c->stream));
-    }
-    if (want_sp) {
-        if (int e = vxl_pass_spot(c, vol, a->view, &fd, a->spot, a->n_spot, o_sp)) return e;
-        VXL_CUDA(cudaMemcpyAsync(a->out_spot_shadow, o_sp, px * 4 * (size_t)a->n_spot, cudaMemcpyDeviceToHost, c->stream));
-    }
-    if (want_rf) {
-        if (int e = vxl_pass_reflection(c, vol, a->view, &fd, o_spec)) return e;
-        VXL_CUDA(cudaMemcpyAsync(a->out_spec_t, o_spec, px * 4, cudaMemcpyDeviceToHost, c->stream));
-    }
+    c->band_row0 = 0; c->band_rows = 0;
+    VXL_CUDA(cudaEventRecord(ev[1], c->s_d2h));
+    VXL_CUDA(cudaStreamWaitEvent(c->stream, ev[1], 0));                   // the context's stream stays the single point of order
+    VXL_CUDA(cudaStreamSynchronize(c->s_h2d));
     VXL_CUDA(cudaStreamSynchronize(c->stream));
+    if (rc != VXL_OK) return rc;
+    if (cudaError_t e = cudaGetLastError()) return cuda_fail(e, "vxl_lighting_host copies");
     return VXL_OK;
 }
 

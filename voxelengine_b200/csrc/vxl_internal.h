@@ -31,6 +31,7 @@ struct VolView {
 
 struct FrameView {
     int width, height, tile_w, tile_h, tile_first, tile_stride, n_tiles, tiles_x;
+    int row0, rows;                      // the light passes cover rows [row0, row0 + rows) of every tile (a band; default: all)
     const uint32_t* __restrict__ depth24;
     const uint32_t* __restrict__ normal;
     const uint32_t* __restrict__ material;
@@ -69,6 +70,9 @@ struct vxl_ctx {
     float* h_out = nullptr;
     size_t h_out_bytes = 0;
     uint32_t* h_noise = nullptr;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // copy streams of vxl_lighting_host (uploads / read-backs overlap the passes)
+    std::vector<cudaEvent_t> ev;
+    int band_row0 = 0, band_rows = 0;                // > 0 rows: the pass entry points cover this row band of every tile only
 };
 
 struct vxl_volume {

@@ -36,19 +36,20 @@ struct PixelCtx {
 // thread -> pixel of the shard.  blockIdx.x enumerates (tile, block-in-tile).
 __device__ __forceinline__ PixelCtx pixel_ctx(const FrameView& F, const ViewK& K) {
     PixelCtx p;
-    const int bpt_x = (F.tile_w + BLOCK_W - 1) / BLOCK_W, bpt_y = (F.tile_h + BLOCK_H - 1) / BLOCK_H;
+    const int bpt_x = (F.tile_w + BLOCK_W - 1) / BLOCK_W, bpt_y = (F.rows + BLOCK_H - 1) / BLOCK_H;
     const int bpt = bpt_x * bpt_y;
     const int lt = blockIdx.x / bpt, b = blockIdx.x - lt * bpt;
     const int by = b / bpt_x, bx = b - by * bpt_x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // 16 warps as 4 (x) by 4 (y); each warp 8 (x) by 4 (y)
     const int lx = bx * BLOCK_W + (warp & 3) * 8 + (lane & 7);
-    const int ly = by * BLOCK_H + (warp >> 2) * 4 + (lane >> 3);
+    const int lb = by * BLOCK_H + (warp >> 2) * 4 + (lane >> 3);      // row within the band
+    const int ly = F.row0 + lb;
     const int gt = F.tile_first + lt * F.tile_stride;
     const int ty = gt / F.tiles_x, tx = gt - ty * F.tiles_x;
     p.px = tx * F.tile_w + lx;
     p.py = ty * F.tile_h + ly;
-    p.valid = lx < F.tile_w && ly < F.tile_h && p.px < F.width && p.py < F.height && lt < F.n_tiles;
+    p.valid = lx < F.tile_w && lb < F.rows && ly < F.tile_h && p.px < F.width && p.py < F.height && lt < F.n_tiles;
     p.idx = ((size_t)lt * F.tile_h + ly) * F.tile_w + lx;
     p.u = ((float)p.px + 0.5f) / (float)F.width;
     p.v = ((float)p.py + 0.5f) / (float)F.height;
@@ -418,8 +419,13 @@ static ViewK make_viewk(const vxl_view* v) {
     return k;
 }
 
+// vxl_lighting_host runs the passes band by band (rows of every tile) so that copies overlap them
+static void apply_band(const vxl_ctx* ctx, FrameView& F) {
+    if (ctx->band_rows > 0) { F.row0 = ctx->band_row0; F.rows = ctx->band_rows < F.tile_h - F.row0 ? ctx->band_rows : F.tile_h - F.row0; }
+}
+
 static unsigned grid_for(const FrameView& F) {
-    const int bpt_x = (F.tile_w + BLOCK_W - 1) / BLOCK_W, bpt_y = (F.tile_h + BLOCK_H - 1) / BLOCK_H;
+    const int bpt_x = (F.tile_w + BLOCK_W - 1) / BLOCK_W, bpt_y = (F.rows + BLOCK_H - 1) / BLOCK_H;
     return (unsigned)(bpt_x * bpt_y * F.n_tiles);
 }
 
@@ -434,6 +440,7 @@ int vxl_pass_ambient(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, const 
     if (!ctx || !vol || !view || !frame || n_ao < 0) { set_error("vxl_pass_ambient: bad argument"); return VXL_ERR_INVALID; }
     FrameView F;
     if (int e = frame_view(frame, &F)) return e;
+    apply_band(ctx, F);
     if (!out_shadow && !out_ao) return VXL_OK;
     if (F.n_tiles == 0) return VXL_OK;
     if (vol->dirty) { if (int e = vxl_volume_build_occupancy(vol)) return e; }
@@ -458,6 +465,7 @@ static int local_lights(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, con
     if (n_lights > VXL_MAX_LIGHTS) { set_error("more than VXL_MAX_LIGHTS lights"); return VXL_ERR_LIMIT; }
     FrameView F;
     if (int e = frame_view(frame, &F)) return e;
+    apply_band(ctx, F);
     if (n_lights == 0 || F.n_tiles == 0) return VXL_OK;
     if (vol->dirty) { if (int e = vxl_volume_build_occupancy(vol)) return e; }
     VXL_CUDA(cudaMemcpyAsync(ctx->d_lights, lights, (size_t)n_lights * light_bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -490,6 +498,7 @@ int vxl_pass_reflection(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, con
     if (!out_spec_t) return VXL_OK;
     FrameView F;
     if (int e = frame_view(frame, &F)) return e;
+    apply_band(ctx, F);
     if (!F.material) { set_error("vxl_pass_reflection: frame.material is NULL"); return VXL_ERR_INVALID; }
     if (F.n_tiles == 0) return VXL_OK;
     if (vol->dirty) { if (int e = vxl_volume_build_occupancy(vol)) return e; }
