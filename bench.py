@@ -410,6 +410,11 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: native libraries that write to fd 1 (NCCL prints its version banner there when
+    # NCCL_DEBUG is set) are pointed at stderr, Python's print keeps the real stdout
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.impl == "reference":
         run_reference(args)
     else:
