@@ -298,6 +298,33 @@ def run_ours(args):
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes, "kernel_ms": ktime[dom],
                 "all_kernels_ms": ktime, "probes_per_s": per[dom]["steps"] / (ktime[dom] * 1e-3)}
 
+    # ---- light-buffer resolve: elementwise, HBM-bound; timed beside the march, not part of `value` ----
+    resolve = None
+    if world == 1:
+        alb = torch.randint(0, 2 ** 31 - 1, wl.gb.shape, dtype=torch.int32, device=dev)
+        lb = E.LightBuffer(wl.gb, alb)
+        pl = wl.planes()
+
+        def res():
+            lb.Ambient(wl.view, pl["shadow"], pl["ao"])
+            if wl.n_point:
+                lb.Point(wl.view, wl.lights, pl["point"])
+        res(); torch.cuda.synchronize()
+        tt = 0.0
+        for _ in range(args.steps):
+            flush()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); res(); b.record()
+            torch.cuda.synchronize()
+            tt += a.elapsed_time(b)
+        npx = int(np.prod(wl.gb.shape))
+        # per pixel: depth, normal, material, albedo, shadow, ao in (24 B) + rgba out (16 B); point: the same planes minus ao
+        # plus one shadow plane per light in and rgba in + out
+        rbytes = npx * (24 + 16) + (npx * (16 + 4 * wl.n_point + 32) if wl.n_point else 0)
+        resolve = {"ms": tt / args.steps, "bytes": rbytes, "GB/s": rbytes / (tt / args.steps * 1e-3) / 1e9,
+                   "frac_of_hbm_peak": rbytes / (tt / args.steps * 1e-3) / 1e9 / peak,
+                   "kernels": "k_resolve_ambient" + (" + k_resolve_local<point>" if wl.n_point else "")}
+
     # ---- end to end: host buffers in, host buffers out, every step ----
     e2e = None if args.no_e2e else run_e2e(args, wl, torch, dist, world, rank, rays)
 
@@ -325,7 +352,7 @@ def run_ours(args):
                        "l2": "flushed between timed steps (256 MiB fill outside the event pairs); per-step working set 128 MiB volume + 100 MB G-buffer + 232 MB outputs",
                        "ms_per_step_warm_l2": ms_warm, "ms_per_step_plain_march_variant0": ms_plain,
                        "probes_that_read_the_volume": int(fetched_probes)},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(),
+            "roofline": roofline, "light_buffer_resolve": resolve, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(),
         }))
     wl.close()
     if world > 1:

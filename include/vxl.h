@@ -208,6 +208,26 @@ int vxl_pass_spot(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, const vxl
                   const vxl_spot_light* lights, int n_lights, float* out_shadow);
 int vxl_pass_reflection(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, const vxl_frame* frame,
                         float* out_spec_t);
+/* ---- light-buffer resolve -------------------------------------------------- */
+/* The colour the reference's light passes add to the RGBA16F light buffer, i.e. what the fragment shaders compute
+ * after the march (LightAmbient.frag:178-214 with calculateOcclusion :89-109; LightPoint.frag:131-152;
+ * LightSpot.frag:118-138; lib/PBR.frag:48-69), as float32 RGBA (tile-compact, 16 B per pixel) BEFORE the attachment
+ * conversion and blend.  Inputs: the frame's planes, COLOR_TEXTURE (albedo), and the shadow / ao planes of the march
+ * passes above.  vxl_resolve_ambient writes (sky pixels, whose colour is a sky-box look-up outside this path, get 0);
+ * vxl_resolve_point / _spot ADD the lights' colours in list order, like the reference's one additive draw per light.
+ * pow() is specified by accuracy only, so these planes carry a tolerance (1e-5 relative), unlike the march planes. */
+typedef struct vxl_resolve {
+    const uint32_t* albedo;      /* DEVICE, tile-compact like the frame's planes: R8G8B8A8_UNORM colour attachment (Graphics.h:55) */
+    const uint32_t* depth_full;  /* DEVICE, [height][width] D24 of the WHOLE frame: screenspaceOcclusion (LightAmbient.frag:66) samples
+                                    other pixels.  NULL = the frame is one whole-frame tile and frame.depth24 is used */
+} vxl_resolve;
+int vxl_resolve_ambient(vxl_ctx* ctx, const vxl_view* view, const vxl_frame* frame, const vxl_resolve* r,
+                        const float* shadow, const float* ao, float* out_rgba);
+int vxl_resolve_point(vxl_ctx* ctx, const vxl_view* view, const vxl_frame* frame, const vxl_resolve* r,
+                      const vxl_point_light* lights /* HOST */, int n_lights, const float* shadow /* [n_lights] planes */, float* inout_rgba);
+int vxl_resolve_spot(vxl_ctx* ctx, const vxl_view* view, const vxl_frame* frame, const vxl_resolve* r,
+                     const vxl_spot_light* lights /* HOST */, int n_lights, const float* shadow, float* inout_rgba);
+
 /* rays/out are DEVICE pointers */
 int vxl_trace_rays(vxl_ctx* ctx, vxl_volume* vol, const vxl_ray* rays, int64_t n, int variant, vxl_hit* out);
 

@@ -500,6 +500,175 @@ void vxo_pass_reflection(const vxo_volume* vol, const vxo_view* view, const vxo_
 // A7  Sources/World/Systems/ShadowVoxSystem.cpp
 // ---------------------------------------------------------------------------------------------
 // :82-94 SetVolumeAt
+// ---------------------------------------------------------------------------------------------
+// the colour the light passes write to the RGBA16F light buffer (additive blend),
+// i.e. what the reference's main() computes AFTER the shadow / AO march, as float32 before the
+// attachment conversion.  Inputs: the same G-buffer plus COLOR_TEXTURE (albedo, RGBA8 UNORM) and the
+// shadow / ao planes of the march passes.  pow() is powf (GLSL specifies pow by accuracy only): parity
+// for these planes is a tolerance, not bit equality.  Sky pixels (which sample the sky-box cube map,
+// outside the path) are written as 0.
+// ---------------------------------------------------------------------------------------------
+}  // extern "C"
+namespace {
+const float PI_ = 3.14159265359f;                           // PBR.frag:1
+
+inline V3 splat(float v) { return V3{v, v, v}; }
+inline V3 max3(V3 a, V3 b) { return V3{fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)}; }
+inline V3 div3(V3 a, float s) { return V3{a.x / s, a.y / s, a.z / s}; }
+inline V3 unorm8x3(uint32_t c) { return V3{unorm8(c), unorm8(c >> 8), unorm8(c >> 16)}; }
+
+// PBR.frag:48-69.  NDF and G are evaluated by the shader but do not reach Lo (the specular term is commented out).
+inline V3 pbr_direct_light(V3 radiance, V3 albedo, V3 V, V3 N, V3 L, float metallic) {
+    const V3 F0 = mix3(splat(0.04f), splat(1.0f), metallic);                                   // :51
+    const float p5 = powf(fmaxf(1.0f - fmaxf(dot3(N, V), 0.0f), 0.0f), 5.0f);                   // :3-5
+    const V3 F = F0 + (splat(1.0f) - F0) * p5;
+    V3 kD = splat(1.0f) - F;                                                                   // :58
+    kD = kD * (1.0f - metallic);                                                               // :59
+    const float NdotL = fmaxf(dot3(N, L), 0.0f);                                               // :65
+    return (div3(kD * albedo, PI_) * radiance) * NdotL;                                        // :66
+}
+
+// LightAmbient.frag:54-79 screenspaceOcclusion (depth sampled with the nearest filter of evk's samplers; out of
+// range reads 0, as the harness that runs the reference shader defines it)
+inline float depth_at_uv(const vxo_gbuffer& gb, float u, float v) {
+    const int x = (int)floorf(u * (float)gb.width), y = (int)floorf(v * (float)gb.height);
+    if (x < 0 || y < 0 || x >= gb.width || y >= gb.height) return 0.0f;
+    return unorm24(gb.depth24[(size_t)y * gb.width + x]);
+}
+inline float screenspace_occlusion(const vxo_view& view, const vxo_gbuffer& gb, V3 pos, V3 dir, float dist) {
+    const V3 mid = pos + dir * dist;                                                           // :60
+    const V4 midProj = mat_mul(view.ProjectionMatrix, V4{mid.x, mid.y, mid.z, 1.0f});          // :62
+    const float sampleDepth = (midProj.w - NEAR_) / (FAR_ - NEAR_);                            // :63
+    const float u = ((midProj.x / midProj.w) * 1.0f) * 0.5f + 0.5f;                            // :54-57 worldToUV
+    const float v = ((midProj.y / midProj.w) * -1.0f) * 0.5f + 0.5f;
+    const float minDepth = depth_at_uv(gb, u, v);                                              // :67
+    const float maxDepth = minDepth + 0.2f / FAR_;                                             // :68 OCCLUSION_TICKNESS
+    if (gclamp(u, 0.0f, 1.0f) != u || gclamp(v, 0.0f, 1.0f) != v) return 0.0f;                 // :70-72
+    if (minDepth < sampleDepth && sampleDepth < maxDepth) return gsmoothstep(maxDepth, minDepth, sampleDepth) * dist;   // :75-77
+    return 0.0f;
+}
+
+// LightAmbient.frag:89-109 calculateOcclusion(N) -- N is the VIEW-space normal
+inline float calculate_occlusion(const vxo_view& view, const vxo_gbuffer& gb, const Luts& L, const Pixel& p, float depth, V3 N) {
+    const V3 tangent = normalize3(fabsf(N.z) > 0.5f ? v3(0.0f, -N.z, N.y) : v3(-N.y, N.x, 0.0f));
+    const V3 bitangent = normalize3(cross3(N, tangent));
+    const V3 pos = p.farvec * (depth * (1.0f + 1.0f / FAR_) + NEAR_ / FAR_);                  // :94
+    float occlusion = 0.0f;
+    const float sizeMultiplier = 0.2f * (1.0f + depth * 0.0f);                                 // :97
+    for (int i = 0; i < 4; ++i) {                                                              // SAMPLES
+        const uint32_t n = get_noise(gb, view, p, i);
+        const V3 rv = cosine_sample_hemisphere(L, n, n >> 8);
+        const V3 dir = tangent * rv.x + bitangent * rv.y + N * rv.z;
+        occlusion += screenspace_occlusion(view, gb, pos, normalize3(dir) * sizeMultiplier, unorm8(n >> 16));
+    }
+    occlusion /= 4.0f;
+    occlusion *= 3.0f;                                                                         // OCCLUSION_STRENGTH
+    return gclamp(1.0f - occlusion, 0.0f, 1.0f);
+}
+}  // namespace
+extern "C" {
+
+// LightAmbient.frag:134-214 after the march: out_Color = vec4(ambient + Lo, 0).  `ao` is the n_ao = 1 plane
+// (d*d * AMBIENT_LIGHT_FACTOR); with the multi-sample extension it is the mean, used the same way.
+void vxo_resolve_ambient(const vxo_view* view, const vxo_gbuffer* gb, const uint32_t* albedo_rgba8, const float* shadow,
+                         const float* ao, vxo_rows rows, float* out_rgba) {
+    const Luts& L = luts();
+    const int W = gb->width, H = gb->height;
+    const V3 SUN = sun_dir();
+    const V3 SUN_COLOR = v3(0.9f, 0.9f, 0.8f) * 0.5f;                                          // :16
+    if (rows.step < 1) rows.step = 1;
+    const int nrows = rows.end > rows.begin ? (rows.end - rows.begin + rows.step - 1) / rows.step : 0;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int ri = 0; ri < nrows; ++ri) {
+        const int py = rows.begin + ri * rows.step;
+        if (py < 0 || py >= H) continue;
+        for (int px = 0; px < W; ++px) {
+            const size_t idx = (size_t)py * W + px;
+            float* o = out_rgba + idx * 4;
+            o[0] = o[1] = o[2] = o[3] = 0.0f;
+            const float depth = unorm24(gb->depth24[idx]);
+            if (!(depth < 0.999f)) continue;                                                   // :138 (sky box look-up: outside the path)
+            const Pixel p = pixel_setup(*view, W, H, px, py);
+            const V3 alb = unorm8x3(albedo_rgba8[idx]);                                        // :139
+            const uint32_t m = gb->material[idx];
+            const float roughness = unorm8(m), metallic = unorm8(m >> 8), emit = unorm8(m >> 16);   // :182-184
+            const V3 pos = p.farvec * (depth * (1.0f + 1.0f / FAR_));                          // :141
+            const V3 normal = decode_normal(gb->normal[idx]);
+            const V3 sunDir = xyz(mat_mul(view->ViewMatrix, V4{SUN.x, SUN.y, SUN.z, 0.0f}));    // :179
+            V3 F0 = mix3(splat(0.04f), alb, metallic);                                         // :187-188
+            const V3 Vv = normalize3(pos) * -1.0f;                                             // :190
+            const V3 N = xyz(mat_mul(view->ViewMatrix, V4{normal.x, normal.y, normal.z, 0.0f}));   // :191
+            const V3 radiance = (SUN_COLOR * 1.0f) * shadow[idx];                              // :198
+            const V3 Lo = pbr_direct_light(radiance, alb, Vv, N, sunDir, metallic);            // :199
+            const float c = fmaxf(dot3(N, Vv), 0.0f);
+            const V3 F = F0 + (max3(splat(1.0f - roughness), F0) - F0) * powf(fmaxf(1.0f - c, 0.0f), 5.0f);   // :204, PBR.frag:8-10
+            const V3 kD = splat(1.0f) - F;                                                     // :206
+            const float ey = (fmaxf(0.0f, 0.0f) * 0.8f + 0.2f) * 0.8f;                         // :128-131 getSkyColor(vec3(1,0,0))
+            const V3 irradiance = v3(powf(1.0f - ey, 2.0f), 1.0f - ey, 0.6f + (1.0f - ey) * 0.4f) * 1.1f;
+            const V3 diffuse = irradiance * alb;                                               // :208
+            const V3 ambientIrradiance = splat(ao[idx]);                                       // :125
+            const float occ = calculate_occlusion(*view, *gb, L, p, depth, N);
+            const V3 ambient = diffuse * (splat(emit * 10.0f) + (kD * ambientIrradiance) * occ);   // :210
+            const V3 c3 = ambient + Lo;                                                        // :213
+            o[0] = c3.x; o[1] = c3.y; o[2] = c3.z; o[3] = 0.0f;
+        }
+    }
+}
+
+// LightPoint.frag:131-152 / LightSpot.frag:118-138 after the march: inout_rgba += sum over the lights, in list order,
+// of vec4(Lo, 0) (the reference draws one additive full-screen pass per light).  Range-culled pixels add nothing.
+// light stride: 8 floats (vxo_point_light) or 16 (vxo_spot_light).  shadow: [n_lights][H][W].
+void vxo_resolve_local(const vxo_view* view, const vxo_gbuffer* gb, const uint32_t* albedo_rgba8, const float* lights,
+                       int n_lights, int spot, const float* shadow, vxo_rows rows, float* inout_rgba) {
+    const int W = gb->width, H = gb->height;
+    const int stride = spot ? 16 : 8;
+    if (rows.step < 1) rows.step = 1;
+    const int nrows = rows.end > rows.begin ? (rows.end - rows.begin + rows.step - 1) / rows.step : 0;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int ri = 0; ri < nrows; ++ri) {
+        const int py = rows.begin + ri * rows.step;
+        if (py < 0 || py >= H) continue;
+        for (int px = 0; px < W; ++px) {
+            const size_t idx = (size_t)py * W + px;
+            const float depth = unorm24(gb->depth24[idx]);
+            const Pixel p = pixel_setup(*view, W, H, px, py);
+            const uint32_t m = gb->material[idx];
+            const float metallic = unorm8(m >> 8);
+            const V3 alb = unorm8x3(albedo_rgba8[idx]);
+            const V3 pos = p.farvec * (depth * (1.0f + 1.0f / FAR_));
+            const V3 normal = decode_normal(gb->normal[idx]);
+            const V3 worldPos = xyz(mat_mul(view->InverseViewMatrix, V4{pos.x, pos.y, pos.z, 1.0f}));
+            const V3 Vv = normalize3(pos) * -1.0f;                                             // :139
+            const V3 N = xyz(mat_mul(view->ViewMatrix, V4{normal.x, normal.y, normal.z, 0.0f}));
+            float* o = inout_rgba + idx * 4;
+            for (int li = 0; li < n_lights; ++li) {
+                const float* lt = lights + (size_t)li * stride;
+                const V3 lpos{lt[0], lt[1], lt[2]};
+                const float range = lt[3];
+                const V3 color{lt[4], lt[5], lt[6]};
+                const float atten = lt[7];
+                const V3 lightPos = xyz(mat_mul(view->ViewMatrix, V4{lpos.x, lpos.y, lpos.z, 1.0f}));   // :96
+                const V3 lightDir = lpos - worldPos;
+                const float lightDistance = length3(lightDir);
+                if (lightDistance > range) continue;                                           // discard
+                const V3 Lv = xyz(mat_mul(view->ViewMatrix, V4{lightDir.x, lightDir.y, lightDir.z, 0.0f}));   // :141
+                const float dist = length3(lightPos - pos);                                    // :143 distance()
+                float attenuation;
+                if (!spot) attenuation = gclamp(range - lightDistance, 0.0f, 1.0f) / powf(dist, atten);   // :144
+                else {
+                    const V3 sdir{lt[8], lt[9], lt[10]};
+                    const float angle = lt[11], angleAtten = lt[12];
+                    const float angleDist = fmaxf(dot3(normalize3(lightDir), sdir) - (1.0f - angle), 0.0f) / angle;   // LightSpot.frag:132
+                    attenuation = (powf(angleDist, angleAtten) * gclamp(range - lightDistance, 0.0f, 1.0f)) / powf(dist, atten);   // :133
+                }
+                const V3 radiance = (color * attenuation) * shadow[(size_t)li * W * H + idx];  // :146
+                const V3 Lo = pbr_direct_light(radiance, alb, Vv, N, Lv, metallic);
+                o[0] += Lo.x; o[1] += Lo.y; o[2] += Lo.z; o[3] += 0.0f;
+            }
+        }
+    }
+}
+
 void vxo_set_volume_at(uint8_t* data, int sx, int sy, int sz, int x, int y, int z, int value) {
     if (x < 0 || y < 0 || z < 0 || x >= sx * 2 || y >= sy * 2 || z >= sz * 2) return;
     int bit = (x & 1) | ((y & 1) << 1) | ((z & 1) << 2);

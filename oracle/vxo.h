@@ -120,6 +120,13 @@ void vxo_pass_spot(const vxo_volume* vol, const vxo_view* view, const vxo_gbuffe
 void vxo_pass_reflection(const vxo_volume* vol, const vxo_view* view, const vxo_gbuffer* gb,
                          vxo_rows rows, float* out_t, vxo_stats* stats);
 
+/* the colour the passes add to the light buffer (float32 RGBA, before the RGBA16F attachment
+ * conversion), from the planes above + COLOR_TEXTURE (albedo RGBA8 UNORM).  Tolerance parity (pow). */
+void vxo_resolve_ambient(const vxo_view* view, const vxo_gbuffer* gb, const uint32_t* albedo_rgba8, const float* shadow,
+                         const float* ao, vxo_rows rows, float* out_rgba /* [H][W][4] */);
+void vxo_resolve_local(const vxo_view* view, const vxo_gbuffer* gb, const uint32_t* albedo_rgba8, const float* lights,
+                       int n_lights, int spot, const float* shadow /* [n][H][W] */, vxo_rows rows, float* inout_rgba);
+
 /* ShadowVoxSystem::SetVolumeAt / OnUpdate / OnVoxDestroyed on a host staging buffer. */
 void vxo_set_volume_at(uint8_t* data, int sx, int sy, int sz, int x, int y, int z, int value);
 int  vxo_get_volume_at(const vxo_volume* vol, int x, int y, int z, int mip);

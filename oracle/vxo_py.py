@@ -151,9 +151,13 @@ def shader_trace(volume, rays, variant):
     return out
 
 
-def shader_pass(which, volume, view, gb, lights=None, light_index=0, rect=None):
-    """Run the reference fragment shader `which` over the pixel rectangle (x0, y0, x1, y1); one SHADER_PIXREC per pixel."""
+def shader_pass(which, volume, view, gb, lights=None, light_index=0, rect=None, albedo=None):
+    """Run the reference fragment shader `which` over the pixel rectangle (x0, y0, x1, y1); one SHADER_PIXREC per pixel.
+    albedo: COLOR_TEXTURE as (H, W) uint32 RGBA8 (default: unbound, reads 0)."""
     L = shader_lib()
+    alb = None if albedo is None else np.ascontiguousarray(albedo, np.uint32)
+    L.vxshader_set_albedo.argtypes = [C.c_void_p]
+    L.vxshader_set_albedo(None if alb is None else _p(alb))
     volume = np.ascontiguousarray(volume, np.uint8)
     sz, sy, sx = volume.shape
     h, w = gb["depth24"].shape
@@ -170,6 +174,7 @@ def shader_pass(which, volume, view, gb, lights=None, light_index=0, rect=None):
     vw = _view(view)
     L.vxshader_pass(int(which), _p(vw), w, h, _p(keep[0]), _p(keep[1]), _p(keep[2]), _p(keep[3]), lp, int(light_index),
                     int(x0), int(y0), int(x1), int(y1), _p(out))
+    L.vxshader_set_albedo(None)
     return out
 
 
@@ -254,6 +259,29 @@ def pass_ambient(volume, view, gb, n_ao=1, rows=None):
     v, g, vw = _vol(volume), _gb(gb), _view(view)
     lib().vxo_pass_ambient(C.byref(v), _p(vw), C.byref(g), int(n_ao), _rows(rows, h), _p(shadow), _p(ao), C.byref(st))
     return shadow, ao, dict(rays=st.rays, steps=st.steps, pixels=st.pixels)
+
+
+def resolve_ambient(view, gb, albedo, shadow, ao, rows=None):
+    """LightAmbient.frag's out_Color (float32 RGBA, (H, W, 4)) from the march planes + COLOR_TEXTURE (albedo RGBA8)."""
+    h, w = gb["depth24"].shape
+    alb = np.ascontiguousarray(albedo, np.uint32)
+    sh, a = np.ascontiguousarray(shadow, np.float32), np.ascontiguousarray(ao, np.float32)
+    out = np.zeros((h, w, 4), np.float32)
+    g, vw = _gb(gb), _view(view)
+    lib().vxo_resolve_ambient(_p(vw), C.byref(g), _p(alb), _p(sh), _p(a), _rows(rows, h), _p(out))
+    return out
+
+
+def resolve_local(view, gb, albedo, lights, shadow, spot=False, rows=None, accumulate=None):
+    """LightPoint / LightSpot.frag's out_Color summed over `lights` in order, added to `accumulate` (or zeros)."""
+    h, w = gb["depth24"].shape
+    alb = np.ascontiguousarray(albedo, np.uint32)
+    lights = np.ascontiguousarray(lights, dtype=SPOT_LIGHT_DTYPE if spot else POINT_LIGHT_DTYPE)
+    sh = np.ascontiguousarray(shadow, np.float32).reshape(len(lights), h, w)
+    out = np.zeros((h, w, 4), np.float32) if accumulate is None else np.ascontiguousarray(accumulate, np.float32).copy()
+    g, vw = _gb(gb), _view(view)
+    lib().vxo_resolve_local(_p(vw), C.byref(g), _p(alb), _p(lights), len(lights), int(bool(spot)), _p(sh), _rows(rows, h), _p(out))
+    return out
 
 
 def pass_point(volume, view, gb, lights, rows=None):

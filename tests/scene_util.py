@@ -80,3 +80,27 @@ def voxeliser_case(n=14, seed=5):
         e[i]["pivot"] = (1.2, 0.0, 1.2) if i % 2 else (0.0, 0.0, 0.0)
     destroy = np.zeros(n, np.int32); destroy[[1, 6, 9]] = 1
     return models, e, destroy
+
+
+def resolve_case(sc, seed=5):
+    """Inputs of the light-buffer resolve for a scene: a random albedo plane, random material bytes
+    (roughness / metallic / emit all exercised), and point / spot lights placed at the camera so that most lit pixels
+    fall inside their range and cone."""
+    gb = dict(sc["gb"])
+    h, w = gb["depth24"].shape
+    rs = np.random.RandomState(seed)
+    albedo = rs.randint(0, 2 ** 32, size=(h, w), dtype=np.uint64).astype(np.uint32)
+    gb["material"] = rs.randint(0, 2 ** 32, size=(h, w), dtype=np.uint64).astype(np.uint32)
+    cam = np.asarray(sc["view"]["CameraPosition"], np.float64).reshape(3)
+    ext = 2 * sc["volume"].shape[2] * 0.1
+    centre = np.array([ext * 0.5, ext * 0.25, ext * 0.5])
+    aim = (centre - cam) / np.linalg.norm(centre - cam)
+    pos = [tuple(cam + aim * 0.3), tuple(cam + np.array([0.4, -0.2, 0.3]))]
+    point = S.point_lights(pos, [ext * 2.5, ext * 1.2])
+    point["Color"][0] = (3.0, 2.5, 2.0); point["Attenuation"][0] = 1.7
+    point["Color"][1] = (0.5, 4.0, 1.0); point["Attenuation"][1] = 2.0
+    # LightSpot.frag:132 compares Direction with normalize(light - surface): the cone axis points back along the beam
+    spot = S.spot_lights(pos, [ext * 2.5, ext * 1.5], [tuple(-aim), tuple(-aim)])
+    spot["Angle"][0] = 0.45; spot["AngleAttenuation"][0] = 1.5; spot["Color"][0] = (4.0, 4.0, 3.0); spot["Attenuation"][0] = 1.2
+    spot["Angle"][1] = 0.9; spot["AngleAttenuation"][1] = 0.7; spot["Color"][1] = (1.0, 2.0, 6.0); spot["Attenuation"][1] = 2.2
+    return gb, albedo, point, spot

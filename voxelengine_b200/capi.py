@@ -19,6 +19,7 @@ SYMBOLS = [
     "vxl_pass_ambient", "vxl_pass_point", "vxl_pass_spot", "vxl_pass_reflection", "vxl_trace_rays",
     "vxl_lighting_host", "vxl_volume_gen_terrain", "vxl_gbuffer_primary",
     "vxl_debug_set_variant", "vxl_debug_fetched_probes", "vxl_volume_debug_occupancy",
+    "vxl_resolve_ambient", "vxl_resolve_point", "vxl_resolve_spot",
 ]
 
 VXL_MAX_LIGHTS = 64
@@ -38,6 +39,11 @@ class Frame(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("steps", C.c_uint64), ("pixels", C.c_uint64)]
+
+
+class Resolve(C.Structure):
+    """vxl_resolve"""
+    _fields_ = [("albedo", C.c_void_p), ("depth_full", C.c_void_p)]
 
 
 class LightingHostArgs(C.Structure):
@@ -78,6 +84,9 @@ def load():
         "vxl_pass_point": [vp, vp, vp, P(Frame), vp, i32, vp],
         "vxl_pass_spot": [vp, vp, vp, P(Frame), vp, i32, vp],
         "vxl_pass_reflection": [vp, vp, vp, P(Frame), vp],
+        "vxl_resolve_ambient": [vp, vp, P(Frame), P(Resolve), vp, vp, vp],
+        "vxl_resolve_point": [vp, vp, P(Frame), P(Resolve), vp, i32, vp, vp],
+        "vxl_resolve_spot": [vp, vp, P(Frame), P(Resolve), vp, i32, vp, vp],
         "vxl_trace_rays": [vp, vp, vp, i64, i32, vp],
         "vxl_lighting_host": [vp, vp, P(LightingHostArgs)],
         "vxl_volume_gen_terrain": [vp], "vxl_gbuffer_primary": [vp, vp, vp, P(Frame)],

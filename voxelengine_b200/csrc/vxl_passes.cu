@@ -9,91 +9,11 @@
 #include "vxl_math.cuh"
 #include "vxl_trace.cuh"
 #include "vxl_bitmarch.cuh"
+#include "vxl_pixel.cuh"
 
 #include <cstddef>
 
 namespace vxl {
-
-constexpr float FAR_ = 4096.0f;                     // Sources/Shaders/lib/Common.frag:13
-constexpr float GOLDEN_RATIO = 2.118033988749895f;  // Common.frag:9 (sic)
-
-constexpr int BLOCK_W = 32, BLOCK_H = 16;           // pixels per thread block (16 warps of 8x4)
-constexpr int BLOCK_THREADS = BLOCK_W * BLOCK_H;
-#ifndef VXL_PASS_BLOCKS
-#define VXL_PASS_BLOCKS 3         // resident 512-thread blocks per SM the pass kernels' registers are capped for (<= 42 regs);
-#endif                            // measured: 3 blocks 5.91 ms vs 2 blocks 6.51 ms for k_ambient on config 3 (profiles/r1f)
-
-struct ViewK { float InvView[16], View[16], InvProj[16]; int Frame; };
-
-struct PixelCtx {
-    bool valid;
-    int px, py;       // frame coordinates
-    size_t idx;       // index into the tile-compact planes
-    float u, v;       // In.UV
-    float3 farvec;    // LightAmbient.vert:32-36, evaluated per pixel
-};
-
-// thread -> pixel of the shard.  blockIdx.x enumerates (tile, block-in-tile).
-__device__ __forceinline__ PixelCtx pixel_ctx(const FrameView& F, const ViewK& K) {
-    PixelCtx p;
-    const int bpt_x = (F.tile_w + BLOCK_W - 1) / BLOCK_W, bpt_y = (F.rows + BLOCK_H - 1) / BLOCK_H;
-    const int bpt = bpt_x * bpt_y;
-    const int lt = blockIdx.x / bpt, b = blockIdx.x - lt * bpt;
-    const int by = b / bpt_x, bx = b - by * bpt_x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // 16 warps as 4 (x) by 4 (y); each warp 8 (x) by 4 (y)
-    const int lx = bx * BLOCK_W + (warp & 3) * 8 + (lane & 7);
-    const int lb = by * BLOCK_H + (warp >> 2) * 4 + (lane >> 3);      // row within the band
-    const int ly = F.row0 + lb;
-    const int gt = F.tile_first + lt * F.tile_stride;
-    const int ty = gt / F.tiles_x, tx = gt - ty * F.tiles_x;
-    p.px = tx * F.tile_w + lx;
-    p.py = ty * F.tile_h + ly;
-    p.valid = lx < F.tile_w && lb < F.rows && ly < F.tile_h && p.px < F.width && p.py < F.height && lt < F.n_tiles;
-    p.idx = ((size_t)lt * F.tile_h + ly) * F.tile_w + lx;
-    p.u = ((float)p.px + 0.5f) / (float)F.width;
-    p.v = ((float)p.py + 0.5f) / (float)F.height;
-    const float ndcx = 2.0f * p.u - 1.0f, ndcy = 1.0f - 2.0f * p.v;
-    const float4 f = mat_mul(K.InvProj, make_float4(ndcx, ndcy, 1.0f, 1.0f));
-    p.farvec = make_float3(f.x / f.w, f.y / f.w, f.z / f.w);
-    return p;
-}
-
-// LightAmbient.frag:44-52 getNoise() (s < 0) / getNoise(int s)
-__device__ __forceinline__ uint32_t get_noise(const FrameView& F, const ViewK& K, const PixelCtx& p, int s) {
-    float fx, fy;
-    if (s < 0) {
-        fx = GOLDEN_RATIO * gmod((float)K.Frame, 16.0f);
-        fy = GOLDEN_RATIO * gmod((float)(K.Frame + 1), 16.0f);
-    } else {
-        fx = GOLDEN_RATIO * gmod((float)(K.Frame + s * 5), 64.0f);
-        fy = GOLDEN_RATIO * gmod((float)(K.Frame + s * 7 + 1), 64.0f);
-    }
-    const int cx = f2i((p.u + fx) * (float)F.width) % 512;
-    const int cy = f2i((p.v + fy) * (float)F.height) % 512;
-    return __ldg(F.noise + cy * 512 + cx);
-}
-
-// LightAmbient.frag:81-87 with the cos/sin of theta = 6.283*(k/255) tabulated (host, double, rounded once)
-// and r = sqrt(u), z = sqrt(max(0, 1-u)) tabulated per block over the 256 possible u = k/255 (same
-// device sqrtf on the same input as the per-ray evaluation, so the values are identical).
-constexpr int LUT_FLOATS = 1024;   // cos[256] sin[256] r[256] z[256]
-__device__ __forceinline__ float3 cosine_sample_hemisphere(const float* __restrict__ lut, uint32_t nx, uint32_t ny) {
-    const float r = lut[512 + (nx & 0xFFu)];
-    const float x = r * lut[ny & 0xFFu];
-    const float y = r * lut[256 + (ny & 0xFFu)];
-    return make_float3(x, y, lut[768 + (nx & 0xFFu)]);
-}
-
-// (no barrier: the caller's block prologue synchronises before the first use)
-__device__ __forceinline__ void load_luts(float* s_lut, const float* __restrict__ g_lut) {
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_lut[i] = g_lut[i];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-        const float u = unorm8((uint32_t)i);
-        s_lut[512 + i] = sqrtf(u);
-        s_lut[768 + i] = sqrtf(fmaxf(0.0f, 1.0f - u));
-    }
-}
 
 // Shared-memory state of one thread block (dynamic: the tile exceeds the 48 KB static limit).
 template <typename G>
@@ -410,23 +330,6 @@ __global__ void __launch_bounds__(256) k_trace_rays(VolView V, const vxl_ray* __
         h.px = M.pos.x; h.py = M.pos.y; h.pz = M.pos.z;
     }
     out[i] = h;
-}
-
-static ViewK make_viewk(const vxl_view* v) {
-    ViewK k;
-    for (int i = 0; i < 16; ++i) { k.InvView[i] = v->InverseViewMatrix[i]; k.View[i] = v->ViewMatrix[i]; k.InvProj[i] = v->InverseProjectionMatrix[i]; }
-    k.Frame = v->Frame;
-    return k;
-}
-
-// vxl_lighting_host runs the passes band by band (rows of every tile) so that copies overlap them
-static void apply_band(const vxl_ctx* ctx, FrameView& F) {
-    if (ctx->band_rows > 0) { F.row0 = ctx->band_row0; F.rows = ctx->band_rows < F.tile_h - F.row0 ? ctx->band_rows : F.tile_h - F.row0; }
-}
-
-static unsigned grid_for(const FrameView& F) {
-    const int bpt_x = (F.tile_w + BLOCK_W - 1) / BLOCK_W, bpt_y = (F.rows + BLOCK_H - 1) / BLOCK_H;
-    return (unsigned)(bpt_x * bpt_y * F.n_tiles);
 }
 
 }  // namespace vxl

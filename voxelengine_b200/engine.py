@@ -371,6 +371,40 @@ class LightReflectionPipeline:
         return out_spec_t
 
 
+class LightBuffer:
+    """The light buffer the reference's light passes blend into (WorldRenderer.cpp:242-258), as float32 RGBA in
+    tile-compact layout: what LightAmbient / LightPoint / LightSpot.frag compute after the march.
+    `albedo`: torch int32 tensor shaped like the frame's planes (COLOR_TEXTURE, RGBA8 UNORM).  `depth_full`: the whole
+    frame's depth plane (H, W) for tile-sharded frames (the screen-space occlusion samples other pixels)."""
+
+    def __init__(self, geometryFB: GeometryBuffer, albedo, depth_full=None):
+        torch = _torch()
+        self.gb, self.ctx = geometryFB, geometryFB.ctx
+        self.albedo, self.depth_full = albedo, depth_full
+        self.rgba = torch.zeros(geometryFB.shape + (4,), dtype=torch.float32, device=self.ctx.torch_device)
+        self._r = capi.Resolve(albedo.data_ptr(), depth_full.data_ptr() if depth_full is not None else None)
+
+    def Ambient(self, viewBuffer, shadow, ao):
+        v, vp = _view_ptr(viewBuffer)
+        f = self.gb.frame()
+        check(self.ctx.lib.vxl_resolve_ambient(self.ctx.h, vp, C.byref(f), C.byref(self._r), _dev_ptr(shadow), _dev_ptr(ao), _dev_ptr(self.rgba)),
+              "vxl_resolve_ambient")
+        return self.rgba
+
+    def _local(self, fn, dtype, viewBuffer, lights, shadow):
+        lights = np.ascontiguousarray(lights, dtype=dtype)
+        v, vp = _view_ptr(viewBuffer)
+        f = self.gb.frame()
+        check(getattr(self.ctx.lib, fn)(self.ctx.h, vp, C.byref(f), C.byref(self._r), _np_ptr(lights), len(lights), _dev_ptr(shadow), _dev_ptr(self.rgba)), fn)
+        return self.rgba
+
+    def Point(self, viewBuffer, lights, shadow):
+        return self._local("vxl_resolve_point", POINT_LIGHT_DTYPE, viewBuffer, lights, shadow)
+
+    def Spot(self, viewBuffer, lights, shadow):
+        return self._local("vxl_resolve_spot", SPOT_LIGHT_DTYPE, viewBuffer, lights, shadow)
+
+
 def lighting_host(ctx: Context, shadowVox: ShadowVoxSystem, view, frame_desc: dict, planes: dict, outs: dict,
                   n_ao: int = 1, point=None, spot=None):
     """vxl_lighting_host: HOST (pinned torch / numpy) G-buffer planes in, HOST output planes out.
