@@ -242,6 +242,9 @@ def run_ours(args):
     ms_per_step = t_ms / args.steps
     value = rays / (ms_per_step * 1e-3) / 1e6
 
+    if world > 1:   # the gathered stacks carry this rank's own tiles unchanged (outside the timed region)
+        assert torch.equal(wl.gathered_main[rank], wl.out[:3]) and (not wl.n_point or torch.equal(wl.gathered_point[rank], wl.out[3:])), "gather mismatch"
+
     # warm-L2 variant (no flush), reported beside the flushed figure
     ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for a, b in ev2:
@@ -400,8 +403,9 @@ def run_e2e(args, wl, torch, dist, world, rank, rays):
         assert torch.equal(outs["shadow"], ref[0, :n]) and torch.equal(outs["ao"], ref[1, :n]), "e2e planes differ from the resident path"
         return {"value": rays / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3,
                 "api": "vxl_lighting_host (pinned host buffers)"}
-    host_full = torch.empty((world,) + tuple(wl.out.shape), dtype=torch.float32).pin_memory() if rank == 0 else None
-    d2h = int(host_full.numel()) * 4 if rank == 0 else 0
+    host_main = torch.empty((world, 3) + tuple(wl.out.shape[1:]), dtype=torch.float32).pin_memory() if rank == 0 else None
+    host_point = torch.empty((world, wl.n_point) + tuple(wl.out.shape[1:]), dtype=torch.float32).pin_memory() if rank == 0 and wl.n_point else None
+    d2h = (int(host_main.numel()) + (int(host_point.numel()) if host_point is not None else 0)) * 4 if rank == 0 else 0
 
     def one():
         for k in ("depth24", "normal", "material"):
@@ -409,7 +413,9 @@ def run_e2e(args, wl, torch, dist, world, rank, rays):
         wl.gb.noise.copy_(planes["noise"], non_blocking=True)
         wl.step(gather=True)
         if rank == 0:
-            host_full.copy_(wl.gathered, non_blocking=True)
+            host_main.copy_(wl.gathered_main, non_blocking=True)
+            if host_point is not None:
+                host_point.copy_(wl.gathered_point, non_blocking=True)
         torch.cuda.synchronize()
     for _ in range(2):
         one()

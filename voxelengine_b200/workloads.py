@@ -57,7 +57,8 @@ class Workload:
         self.n_planes = 3 + self.n_point
         self.out = torch.zeros((self.n_planes, self.tiles_padded, self.gb.tile_h, self.gb.tile_w), dtype=torch.float32,
                                device=self.ctx.torch_device)
-        self.gathered = None
+        self.gathered_main = self.gathered_point = None      # (world, 3, tiles, th, tw) / (world, n_point, tiles, th, tw)
+        self._side = torch.cuda.Stream(device=self.ctx.torch_device) if world > 1 else None
         self.ctx.sync()
 
     # -- scene -------------------------------------------------------------------------------------
@@ -121,22 +122,41 @@ class Workload:
             self.advance()
         n = self.gb.n_tiles
         o = self.out
-        E.LightAmbientPipeline.Get().Use(self.view, self.gb, self.vol, n_ao=self.n_ao, out_shadow=o[0, :n], out_ao=o[1, :n])
+        torch = self.torch
+        gather = gather and self.world > 1
+        if gather:
+            from .tiles import gather_tiles
         if self.n_point:
             # point planes are [n_point][tiles_padded] inside `out`; the C ABI wants consecutive planes of the
             # shard's own size, which holds when tiles_padded == n_tiles; otherwise stage through a view copy
             if n == self.tiles_padded:
                 self._point(o[3:])
             else:
-                tmp = self.ctx.empty((self.n_point, n, self.gb.tile_h, self.gb.tile_w), self.torch.float32)
+                tmp = self.ctx.empty((self.n_point, n, self.gb.tile_h, self.gb.tile_w), torch.float32)
                 self._point(tmp)
                 o[3:, :n].copy_(tmp)
+            if gather:
+                # the local-light planes are the largest output: their all-gather runs on a side stream under the
+                # ambient and reflection passes (the one collective of the path, SURVEY 8e, in two pieces)
+                self._side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self._side):
+                    self.gathered_point = gather_tiles(o[3:], out=self.gathered_point)
+        E.LightAmbientPipeline.Get().Use(self.view, self.gb, self.vol, n_ao=self.n_ao, out_shadow=o[0, :n], out_ao=o[1, :n])
         if self.spec:
             E.LightReflectionPipeline.Get().Use(self.view, self.gb, self.vol, out_spec_t=o[2, :n])
-        if gather and self.world > 1:
-            from .tiles import gather_tiles
-            self.gathered = gather_tiles(self.out, out=self.gathered)   # the one collective of the path
+        if gather:
+            self.gathered_main = gather_tiles(o[:3], out=self.gathered_main)
+            torch.cuda.current_stream().wait_stream(self._side)
         return self.out
+
+    @property
+    def gathered(self):
+        """(world, n_planes, tiles_padded, tile_h, tile_w): every rank's packed output tiles after a gathering step."""
+        if self.gathered_main is None:
+            return None
+        if self.gathered_point is None:
+            return self.gathered_main
+        return self.torch.cat([self.gathered_main, self.gathered_point], dim=1)
 
     def _point(self, out):
         L = self.lights
