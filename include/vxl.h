@@ -228,6 +228,18 @@ int vxl_resolve_point(vxl_ctx* ctx, const vxl_view* view, const vxl_frame* frame
 int vxl_resolve_spot(vxl_ctx* ctx, const vxl_view* view, const vxl_frame* frame, const vxl_resolve* r,
                      const vxl_spot_light* lights /* HOST */, int n_lights, const float* shadow, float* inout_rgba);
 
+/* ---- model traversal (core) -------------------------------------------------- */
+/* The G-buffer producer's traversal of one model volume: VoxAsset::Upload's mip chain (Sources/Asset/VoxAsset.cpp:3-64,
+ * built on the device on first use) and GeometryVoxel.frag's clipToAABB (:49-61) + intersectVolume (:64-125) -- the
+ * reference's hierarchical-mip DDA with its LOD early accept and glass checkerboard.  Ray-level entry: one record per
+ * fragment, in = (In.localCameraPos, In.localDirection, UV), out = (hit, hitMat, texel fetches, DDA steps, hitPos,
+ * hitNormal).  frame / res_x / res_y: GetFrame() and GetRes() of the view.  rays / out are DEVICE pointers.
+ * float -> int of a NaN (only reachable with an exactly zero direction component) follows cvt.rzi (0); GLSL leaves it undefined. */
+typedef struct vxl_model_ray { float cam[3], dir[3], uv[2]; } vxl_model_ray;
+typedef struct vxl_model_hit { int32_t hit; uint32_t material; int32_t fetches, steps; float pos[3], normal[3]; } vxl_model_hit;
+int vxl_trace_model_rays(vxl_ctx* ctx, int model_id, const vxl_model_ray* rays, int64_t n, int frame, float res_x, float res_y,
+                         vxl_model_hit* out);
+
 /* rays/out are DEVICE pointers */
 int vxl_trace_rays(vxl_ctx* ctx, vxl_volume* vol, const vxl_ray* rays, int64_t n, int variant, vxl_hit* out);
 

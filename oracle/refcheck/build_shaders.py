@@ -29,6 +29,7 @@ SUBSTITUTIONS = [
     (r"^#extension .*$", r"// \g<0>", "GLSL-only directive"),
     (r'^#include "(lib/)?Common.frag"\s*$', r"// \g<0>", "Common.frag is spliced once at global scope"),
     (r"\bout vec3\b", r"vec3&", "GLSL out-parameter -> C++ reference"),
+    (r"\bout uint\b", r"uint&", "GLSL out-parameter -> C++ reference"),
     (r"layout\(push_constant\) uniform uPushConstant\s*\{", r'extern "C++" {', "push-constant block members become plain globals"),
     # the two march functions are renamed so that the prelude's wrappers (same name, same signature) can log each call
     (r"^float raycastShadowVolume(Sparse|SuperSparse)\(vec3 origin, vec3 dir, float dist\) \{",
@@ -79,6 +80,10 @@ def translation_unit() -> str:
                  "\nViewBuffer_t ViewBuffer[1];\n}\n")
     for ns, fn, defs in PASSES:
         parts.append("namespace %s {\n%s\n%s\n%s\n}\n" % (ns, WRAPPERS, splice_includes(adapt(read(fn))), defs))
+    # the G-buffer producer's traversal: GeometryVoxel.frag up to, not including, its main() -- clipToAABB
+    # and intersectVolume with the globals they read
+    geom = adapt(read("GeometryVoxel.frag")).split("void main()")[0]
+    parts.append("namespace geom {\nfloat gl_FragDepth;\n" + geom + "\nViewBuffer_t ViewBuffer[1]; VoxCmdsBuffer_t VoxCmdsBuffer[1];\n}\n")
     with open(os.path.join(HERE, "shader_driver.inc"), "r") as f:
         parts.append(f.read())
     return "".join(parts)

@@ -42,7 +42,7 @@ extern thread_local bool g_discarded;
 using namespace glm;
 
 // ---- resources --------------------------------------------------------------------------------------
-struct usampler3D { const uint8_t* data; int sx, sy, sz; };
+struct usampler3D { const uint8_t* data; int sx, sy, sz; const uint8_t* mip1; const uint8_t* mip2; };   // mips: VoxAsset volumes (3 levels, sizes halve)
 enum TexFmt { TEX_NONE = 0, TEX_D24, TEX_RGBA8_SNORM, TEX_RGBA8_UNORM };
 struct sampler2D { const uint32_t* data; int w, h; TexFmt fmt; };
 struct samplerCube { int unused; };
@@ -65,8 +65,11 @@ inline vec4 vxref_decode(const sampler2D& t, int x, int y) {
 }
 inline uvec4 texelFetch(const usampler3D& t, ivec3 p, int lod) {
     vxref::g_fetch.count++; vxref::g_fetch.x = p.x; vxref::g_fetch.y = p.y; vxref::g_fetch.z = p.z;
-    if (lod != 0 || !t.data || p.x < 0 || p.y < 0 || p.z < 0 || p.x >= t.sx || p.y >= t.sy || p.z >= t.sz) return uvec4(0u);
-    return uvec4((uint)t.data[(size_t)p.x + (size_t)p.y * t.sx + (size_t)p.z * t.sx * t.sy], 0u, 0u, 1u);
+    const uint8_t* d = lod == 0 ? t.data : (lod == 1 ? t.mip1 : (lod == 2 ? t.mip2 : nullptr));
+    int sx = t.sx, sy = t.sy, sz = t.sz;
+    for (int l = 0; l < lod; ++l) { sx = sx > 1 ? sx / 2 : 1; sy = sy > 1 ? sy / 2 : 1; sz = sz > 1 ? sz / 2 : 1; }
+    if (!d || p.x < 0 || p.y < 0 || p.z < 0 || p.x >= sx || p.y >= sy || p.z >= sz) return uvec4(0u);
+    return uvec4((uint)d[(size_t)p.x + (size_t)p.y * sx + (size_t)p.z * sx * sy], 0u, 0u, 1u);
 }
 inline vec4 texelFetch(const sampler2D& t, ivec2 p, int) { return vxref_decode(t, p.x, p.y); }
 inline ivec3 textureSize(const usampler3D& t, int) { return ivec3(t.sx, t.sy, t.sz); }
@@ -79,7 +82,9 @@ inline vec4 texture(const samplerCube&, vec3) { return vec4(0.0f); }
 namespace glm {
 inline vec3 operator/(ivec3 const& a, float b) { return vec3(a) / b; }
 inline vec3 operator/(vec3 const& a, int b) { return a / (float)b; }
+inline vec2 operator+(ivec2 const& a, vec2 const& b) { return vec2(a) + b; }
 inline float mod(int a, int b) { return glm::mod((float)a, (float)b); }
+inline float mod(float a, int b) { return glm::mod(a, (float)b); }
 inline vec2 clamp(vec2 const& v, int lo, int hi) { return glm::clamp(v, (float)lo, (float)hi); }
 inline float clamp(float v, int lo, int hi) { return glm::clamp(v, (float)lo, (float)hi); }
 }  // namespace glm

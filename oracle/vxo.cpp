@@ -669,6 +669,121 @@ void vxo_resolve_local(const vxo_view* view, const vxo_gbuffer* gb, const uint32
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// the G-buffer producer's traversal of ONE model volume -- the reference's
+// hierarchical-mip DDA.  VoxAsset::Upload's mip rule (Sources/Asset/VoxAsset.cpp:3-64), clipToAABB
+// (Sources/Shaders/GeometryVoxel.frag:49-61) and intersectVolume (:64-125).  Ray-level entry: what one
+// fragment of GeometryVoxel.frag does between its inputs (In.localCameraPos, In.localDirection, UV) and
+// (hit, hitPos, hitNormal, hitMat); the rasterisation around it is not restated.
+// ---------------------------------------------------------------------------------------------
+
+// One mip level from its parent: voxel = first non-zero of the 2x2x2 children in the order vi = 0..7 (x fastest, then
+// y, then z); the reference's loop runs to vi = 8, which revisits child 0.  Sizes halve while > 1 (VoxAsset.cpp:19-21).
+void vxo_model_mip(const uint8_t* parent, int psx, int psy, int psz, uint8_t* out) {
+    const int sx = psx > 1 ? psx / 2 : 1, sy = psy > 1 ? psy / 2 : 1, sz = psz > 1 ? psz / 2 : 1;
+    for (int z = 0; z < sz; ++z)
+        for (int y = 0; y < sy; ++y)
+            for (int x = 0; x < sx; ++x) {
+                uint8_t vox = 0;
+                for (int vi = 0; vi < 8; ++vi) {
+                    const int cx = 2 * x + (vi & 1), cy = 2 * y + ((vi >> 1) & 1), cz = 2 * z + ((vi >> 2) & 1);
+                    if (cx >= psx || cy >= psy || cz >= psz) continue;   // (sizes are multiples of 4, VoxAsset.h:27-29: never taken for 3 mips)
+                    const uint8_t up = parent[(size_t)cx + (size_t)cy * psx + (size_t)cz * psx * psy];
+                    if (up) { vox = up; break; }
+                }
+                out[(size_t)x + (size_t)y * sx + (size_t)z * sx * sy] = vox;
+            }
+}
+
+}  // extern "C"
+namespace {
+struct ModelMips { const uint8_t* d[3]; int sx[3], sy[3], sz[3]; };
+inline unsigned model_fetch(const ModelMips& M, int x, int y, int z, int mip) {   // texelFetch(VOLUME_TEXTURE, p, mip).r, out of range -> 0
+    if (mip < 0 || mip > 2 || x < 0 || y < 0 || z < 0 || x >= M.sx[mip] || y >= M.sy[mip] || z >= M.sz[mip]) return 0u;
+    return M.d[mip][(size_t)x + (size_t)y * M.sx[mip] + (size_t)z * M.sx[mip] * M.sy[mip]];
+}
+inline float ground(float x) { return roundf(x); }       // glm::round -> std::round (func_common.inl:203-209)
+}  // namespace
+extern "C" {
+
+// rays: vxo_model_ray {cam[3] = In.localCameraPos, dir[3] = In.localDirection (not normalised), uv[2]}.
+// out: vxo_model_hit {hit, material, fetches (texelFetch calls), steps (nt), pos[3], normal[3]}.
+void vxo_trace_model_rays(const uint8_t* mip0, const uint8_t* mip1, const uint8_t* mip2, int sx, int sy, int sz,
+                          const vxo_model_ray* rays, int64_t n, int frame, float res_x, float res_y, vxo_model_hit* out) {
+    ModelMips M;
+    M.d[0] = mip0; M.d[1] = mip1; M.d[2] = mip2;
+    M.sx[0] = sx; M.sy[0] = sy; M.sz[0] = sz;
+    for (int m = 1; m < 3; ++m) { M.sx[m] = M.sx[m - 1] > 1 ? M.sx[m - 1] / 2 : 1; M.sy[m] = M.sy[m - 1] > 1 ? M.sy[m - 1] / 2 : 1; M.sz[m] = M.sz[m - 1] > 1 ? M.sz[m - 1] / 2 : 1; }
+    const V3 vsize = v3((float)sx, (float)sy, (float)sz);
+#pragma omp parallel for schedule(static)
+    for (int64_t ri = 0; ri < n; ++ri) {
+        const vxo_model_ray& r = rays[ri];
+        vxo_model_hit h;
+        memset(&h, 0, sizeof h);
+        const V3 cam = v3(r.cam[0], r.cam[1], r.cam[2]);
+        const V3 direction = normalize3(v3(r.dir[0], r.dir[1], r.dir[2]));                    // GeometryVoxel.frag:145
+        // clipToAABB :49-61
+        V3 origin = cam;
+        if (!(gclamp(cam.x, 0.0f, vsize.x) == cam.x && gclamp(cam.y, 0.0f, vsize.y) == cam.y && gclamp(cam.z, 0.0f, vsize.z) == cam.z)) {
+            const V3 invDir = v3(1.0f, 1.0f, 1.0f) / direction;
+            const V3 sgn = v3(gstep(direction.x, 0.0f), gstep(direction.y, 0.0f), gstep(direction.z, 0.0f));
+            const V3 t = (sgn * vsize - cam) * invDir;
+            const float tmin = fmaxf(fmaxf(t.x, t.y), t.z);
+            origin = cam + direction * (tmin - 0.001f);
+        }
+        // intersectVolume :64-125
+        const V3 stepSign = v3(gsign(direction.x), gsign(direction.y), gsign(direction.z));
+        const V3 t_delta = v3(1.0f, 1.0f, 1.0f) / (direction * stepSign);
+        int mip = 2, i = 0, nt = 0, fetches = 0;
+        bool done = false;
+        do {
+            const float mipSize = (float)(1 << mip);
+            origin = v3(origin.x / mipSize, origin.y / mipSize, origin.z / mipSize);
+            int cx = f2i(floorf(origin.x)), cy = f2i(floorf(origin.y)), cz = f2i(floorf(origin.z));
+            const V3 next_bounds = v3((float)cx, (float)cy, (float)cz) + (stepSign * 0.5f + v3(0.5f, 0.5f, 0.5f));
+            V3 t_max = (next_bounds - origin) / direction;
+            // ivec3(volumeDimension / mipSize) + 1
+            const int hx = f2i((float)sx / mipSize) + 1, hy = f2i((float)sy / mipSize) + 1, hz = f2i((float)sz / mipSize) + 1;
+            int nn = 0;
+            do {
+                const V3 select = v3(gstep(t_max.x, t_max.z) * gstep(t_max.x, t_max.y), gstep(t_max.y, t_max.x) * gstep(t_max.y, t_max.z),
+                                     gstep(t_max.z, t_max.y) * gstep(t_max.z, t_max.x));
+                const V3 adv = select * stepSign;
+                cx += f2i(adv.x); cy += f2i(adv.y); cz += f2i(adv.z);
+                if (cx < -1 || cy < -1 || cz < -1 || cx > hx || cy > hy || cz > hz) { done = true; break; }   // :84-86 return false
+                const unsigned voxel = model_fetch(M, cx, cy, cz, mip);
+                ++fetches;
+                if (voxel != 0u) {
+                    const float best_t = dot3(t_max, select);
+                    const V3 at = (origin + direction * best_t) * mipSize;
+                    if (mip == 0 || (float)mip < 0.001f * length3(at - cam)) {                   // :92-96 LOD early accept
+                        const float cxr = ground(r.uv[0] * res_x * 0.5f), cyr = ground(r.uv[1] * res_y * 0.5f);   // :99
+                        const bool glass = voxel < 16u && gmod(cyr + cxr, 2.0f) == (float)(frame % 2);            // :100
+                        if (!glass) {
+                            h.hit = 1; h.material = voxel;
+                            const V3 nrm = (stepSign * -1.0f) * select;
+                            h.normal[0] = nrm.x; h.normal[1] = nrm.y; h.normal[2] = nrm.z;
+                            h.pos[0] = at.x; h.pos[1] = at.y; h.pos[2] = at.z;
+                            done = true;
+                            break;
+                        }
+                    } else {
+                        mip--;                                                                   // :110-112
+                        origin = origin + v3((direction.x * best_t) / mipSize, (direction.y * best_t) / mipSize, (direction.z * best_t) / mipSize);
+                        break;
+                    }
+                }
+                t_max = t_max + t_delta * select;
+                nt++;
+            } while (++nn < 512);
+            if (done) break;
+            origin = origin * mipSize;                                                           // :121
+        } while (++i < 4);
+        h.fetches = fetches; h.steps = nt;
+        out[ri] = h;
+    }
+}
+
 void vxo_set_volume_at(uint8_t* data, int sx, int sy, int sz, int x, int y, int z, int value) {
     if (x < 0 || y < 0 || z < 0 || x >= sx * 2 || y >= sy * 2 || z >= sz * 2) return;
     int bit = (x & 1) | ((y & 1) << 1) | ((z & 1) << 2);

@@ -127,6 +127,13 @@ void vxo_resolve_ambient(const vxo_view* view, const vxo_gbuffer* gb, const uint
 void vxo_resolve_local(const vxo_view* view, const vxo_gbuffer* gb, const uint32_t* albedo_rgba8, const float* lights,
                        int n_lights, int spot, const float* shadow /* [n][H][W] */, vxo_rows rows, float* inout_rgba);
 
+/* VoxAsset's mip rule and the hierarchical-mip DDA of GeometryVoxel.frag on one model volume. */
+typedef struct vxo_model_ray { float cam[3], dir[3], uv[2]; } vxo_model_ray;
+typedef struct vxo_model_hit { int32_t hit; uint32_t material; int32_t fetches, steps; float pos[3], normal[3]; } vxo_model_hit;
+void vxo_model_mip(const uint8_t* parent, int psx, int psy, int psz, uint8_t* out);
+void vxo_trace_model_rays(const uint8_t* mip0, const uint8_t* mip1, const uint8_t* mip2, int sx, int sy, int sz,
+                          const vxo_model_ray* rays, int64_t n, int frame, float res_x, float res_y, vxo_model_hit* out);
+
 /* ShadowVoxSystem::SetVolumeAt / OnUpdate / OnVoxDestroyed on a host staging buffer. */
 void vxo_set_volume_at(uint8_t* data, int sx, int sy, int sz, int x, int y, int z, int value);
 int  vxo_get_volume_at(const vxo_volume* vol, int x, int y, int z, int mip);

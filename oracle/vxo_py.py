@@ -261,6 +261,48 @@ def pass_ambient(volume, view, gb, n_ao=1, rows=None):
     return shadow, ao, dict(rays=st.rays, steps=st.steps, pixels=st.pixels)
 
 
+MODEL_RAY_DTYPE = np.dtype([("cam", "<f4", (3,)), ("dir", "<f4", (3,)), ("uv", "<f4", (2,))])
+MODEL_HIT_DTYPE = np.dtype([("hit", "<i4"), ("material", "<u4"), ("fetches", "<i4"), ("steps", "<i4"), ("pos", "<f4", (3,)), ("normal", "<f4", (3,))])
+assert MODEL_RAY_DTYPE.itemsize == 32 and MODEL_HIT_DTYPE.itemsize == 40
+
+
+def model_mips(voxels):
+    """VoxAsset::Upload's mip chain: [level 0, level 1, level 2] as (sz, sy, sx) uint8 arrays."""
+    m0 = np.ascontiguousarray(voxels, np.uint8)
+    out = [m0]
+    for _ in range(2):
+        p = out[-1]
+        psz, psy, psx = p.shape
+        q = np.zeros((max(psz // 2, 1), max(psy // 2, 1), max(psx // 2, 1)), np.uint8)
+        lib().vxo_model_mip(_p(p), psx, psy, psz, _p(q))
+        out.append(q)
+    return out
+
+
+def trace_model_rays(voxels, rays, frame=0, res=(1920.0, 1080.0), mips=None):
+    """GeometryVoxel.frag's clipToAABB + intersectVolume on one model volume (hierarchical-mip DDA)."""
+    m = model_mips(voxels) if mips is None else mips
+    sz, sy, sx = m[0].shape
+    rays = np.ascontiguousarray(rays, dtype=MODEL_RAY_DTYPE)
+    out = np.zeros(len(rays), dtype=MODEL_HIT_DTYPE)
+    f = lib().vxo_trace_model_rays
+    f.argtypes = [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_void_p]
+    f(_p(m[0]), _p(m[1]), _p(m[2]), sx, sy, sz, _p(rays), len(rays), int(frame), float(res[0]), float(res[1]), _p(out))
+    return out
+
+
+def shader_model_trace(voxels, rays, frame=0, res=(1920.0, 1080.0), mips=None):
+    """The reference's own clipToAABB + intersectVolume (GeometryVoxel.frag compiled for the host); `steps` is not reported."""
+    L = shader_lib()
+    m = model_mips(voxels) if mips is None else mips
+    sz, sy, sx = m[0].shape
+    rays = np.ascontiguousarray(rays, dtype=MODEL_RAY_DTYPE)
+    out = np.zeros(len(rays), dtype=MODEL_HIT_DTYPE)
+    L.vxshader_model_trace.argtypes = [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_float, C.c_void_p]
+    L.vxshader_model_trace(_p(m[0]), _p(m[1]), _p(m[2]), sx, sy, sz, _p(rays), len(rays), int(frame), float(res[0]), float(res[1]), _p(out))
+    return out
+
+
 def resolve_ambient(view, gb, albedo, shadow, ao, rows=None):
     """LightAmbient.frag's out_Color (float32 RGBA, (H, W, 4)) from the march planes + COLOR_TEXTURE (albedo RGBA8)."""
     h, w = gb["depth24"].shape

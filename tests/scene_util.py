@@ -104,3 +104,36 @@ def resolve_case(sc, seed=5):
     spot["Angle"][0] = 0.45; spot["AngleAttenuation"][0] = 1.5; spot["Color"][0] = (4.0, 4.0, 3.0); spot["Attenuation"][0] = 1.2
     spot["Angle"][1] = 0.9; spot["AngleAttenuation"][1] = 0.7; spot["Color"][1] = (1.0, 2.0, 6.0); spot["Attenuation"][1] = 2.2
     return gb, albedo, point, spot
+
+
+def model_rays(shape, n, seed=1):
+    """Fragment inputs of GeometryVoxel.frag for a model of `shape` (sz, sy, sx): cameras outside and inside the box,
+    directions toward it (some missing it), and the degenerate cases with exactly zero direction components."""
+    sz, sy, sx = shape
+    rs = np.random.RandomState(seed)
+    ext = np.array([sx, sy, sz], np.float32)
+    r = np.zeros(n, S.MODEL_RAY_DTYPE)
+    cam = (rs.uniform(-1.5, 2.5, size=(n, 3)) * ext).astype(np.float32)
+    inside = rs.uniform(size=n) < 0.2
+    cam[inside] = (rs.uniform(0.05, 0.95, size=(int(inside.sum()), 3)) * ext).astype(np.float32)
+    far = rs.uniform(size=n) < 0.1                                   # far cameras: the LOD rule accepts coarse voxels
+    cam[far] = (cam[far] - ext * 0.5) * np.float32(40.0)
+    tgt = (rs.uniform(-0.1, 1.1, size=(n, 3)) * ext).astype(np.float32)
+    d = tgt - cam
+    k = n // 20
+    d[:k, 0] = 0.0
+    d[k:2 * k, 1] = 0.0
+    d[2 * k:3 * k, 0] = 0.0
+    d[2 * k:3 * k, 2] = 0.0
+    r["cam"], r["dir"] = cam, d
+    r["uv"] = rs.uniform(-1, 1, size=(n, 2)).astype(np.float32)
+    return r
+
+
+def glassy_house(size=40, seed=1):
+    """house_model with random palette indices, a quarter of them glass (< 16)."""
+    m = S.house_model(size, seed=seed)
+    rs = np.random.RandomState(seed + 100)
+    solid = m > 0
+    m[solid] = rs.randint(1, 64, size=int(solid.sum())).astype(np.uint8)
+    return m

@@ -38,7 +38,7 @@ struct FrameView {
     const uint32_t* __restrict__ noise;
 };
 
-struct ModelDev { const uint8_t* voxels; int sx, sy, sz; unsigned solid; };
+struct ModelDev { const uint8_t* voxels; int sx, sy, sz; unsigned solid; const uint8_t* mip1; const uint8_t* mip2; };   // mips: VoxAsset::Upload's chain, built on first use
 
 constexpr int STAT_SLOTS = 64;   // striped counters: slot = blockIdx & 63, 4 x u64 each
 

@@ -403,7 +403,7 @@ int vxl_model_create(vxl_ctx* ctx, const uint8_t* voxels, int sx, int sy, int sz
     VXL_CUDA(cudaStreamSynchronize(ctx->stream));
     unsigned solid = 0;
     for (size_t i = 0; i < n; ++i) solid += voxels[i] >= 16;
-    m.voxels = d; m.sx = sx; m.sy = sy; m.sz = sz; m.solid = solid;
+    m.voxels = d; m.sx = sx; m.sy = sy; m.sz = sz; m.solid = solid; m.mip1 = nullptr; m.mip2 = nullptr;
     ctx->models.push_back(m);
     *out_id = (int)ctx->models.size() - 1;
     return VXL_OK;

@@ -371,6 +371,23 @@ class LightReflectionPipeline:
         return out_spec_t
 
 
+def trace_model_rays(ctx: Context, model_id: int, rays: np.ndarray, frame: int = 0, res=(1920.0, 1080.0)) -> np.ndarray:
+    """GeometryVoxel.frag's clipToAABB + intersectVolume on a registered model (core): host rays
+    (scenes.MODEL_RAY_DTYPE) in, host hit records (scenes.MODEL_HIT_DTYPE) out, through device buffers."""
+    from .scenes import MODEL_HIT_DTYPE, MODEL_RAY_DTYPE
+    torch = _torch()
+    rays = np.ascontiguousarray(rays, dtype=MODEL_RAY_DTYPE)
+    n = len(rays)
+    if n == 0:
+        return np.zeros(0, dtype=MODEL_HIT_DTYPE)
+    d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1)).to(ctx.torch_device)
+    d_out = torch.empty(n * MODEL_HIT_DTYPE.itemsize, dtype=torch.uint8, device=ctx.torch_device)
+    check(ctx.lib.vxl_trace_model_rays(ctx.h, int(model_id), _dev_ptr(d_rays), n, int(frame), float(res[0]), float(res[1]), _dev_ptr(d_out)),
+          "vxl_trace_model_rays")
+    ctx.sync()
+    return d_out.cpu().numpy().view(MODEL_HIT_DTYPE).copy()
+
+
 class LightBuffer:
     """The light buffer the reference's light passes blend into (WorldRenderer.cpp:242-258), as float32 RGBA in
     tile-compact layout: what LightAmbient / LightPoint / LightSpot.frag compute after the march.

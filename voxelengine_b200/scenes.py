@@ -128,6 +128,11 @@ def blue_noise(seed=4):
     return rs.randint(0, 2 ** 32, size=(512, 512), dtype=np.uint64).astype(np.uint32)
 
 
+MODEL_RAY_DTYPE = np.dtype([("cam", "<f4", (3,)), ("dir", "<f4", (3,)), ("uv", "<f4", (2,))])                     # vxl_model_ray
+MODEL_HIT_DTYPE = np.dtype([("hit", "<i4"), ("material", "<u4"), ("fetches", "<i4"), ("steps", "<i4"), ("pos", "<f4", (3,)),
+                            ("normal", "<f4", (3,))])                                                                 # vxl_model_hit
+
+
 def point_lights(positions, ranges, color=(2.0, 2.0, 2.0), attenuation=2.0):
     n = len(positions)
     a = np.zeros(n, dtype=POINT_LIGHT_DTYPE)
