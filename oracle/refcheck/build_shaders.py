@@ -80,9 +80,8 @@ def translation_unit() -> str:
                  "\nViewBuffer_t ViewBuffer[1];\n}\n")
     for ns, fn, defs in PASSES:
         parts.append("namespace %s {\n%s\n%s\n%s\n}\n" % (ns, WRAPPERS, splice_includes(adapt(read(fn))), defs))
-    # the G-buffer producer's traversal: GeometryVoxel.frag up to, not including, its main() -- clipToAABB
-    # and intersectVolume with the globals they read
-    geom = adapt(read("GeometryVoxel.frag")).split("void main()")[0]
+    # the G-buffer producer: GeometryVoxel.frag -- clipToAABB, intersectVolume and the fragment main()
+    geom = adapt(read("GeometryVoxel.frag"))
     parts.append("namespace geom {\nfloat gl_FragDepth;\n" + geom + "\nViewBuffer_t ViewBuffer[1]; VoxCmdsBuffer_t VoxCmdsBuffer[1];\n}\n")
     with open(os.path.join(HERE, "shader_driver.inc"), "r") as f:
         parts.append(f.read())

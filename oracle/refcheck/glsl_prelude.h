@@ -85,6 +85,7 @@ inline vec3 operator/(vec3 const& a, int b) { return a / (float)b; }
 inline vec2 operator+(ivec2 const& a, vec2 const& b) { return vec2(a) + b; }
 inline float mod(int a, int b) { return glm::mod((float)a, (float)b); }
 inline float mod(float a, int b) { return glm::mod(a, (float)b); }
+inline float step(uint edge, int x) { return glm::step((float)edge, (float)x); }
 inline vec2 clamp(vec2 const& v, int lo, int hi) { return glm::clamp(v, (float)lo, (float)hi); }
 inline float clamp(float v, int lo, int hi) { return glm::clamp(v, (float)lo, (float)hi); }
 }  // namespace glm

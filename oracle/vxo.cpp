@@ -706,81 +706,143 @@ inline float ground(float x) { return roundf(x); }       // glm::round -> std::r
 }  // namespace
 extern "C" {
 
-// rays: vxo_model_ray {cam[3] = In.localCameraPos, dir[3] = In.localDirection (not normalised), uv[2]}.
-// out: vxo_model_hit {hit, material, fetches (texelFetch calls), steps (nt), pos[3], normal[3]}.
-void vxo_trace_model_rays(const uint8_t* mip0, const uint8_t* mip1, const uint8_t* mip2, int sx, int sy, int sz,
-                          const vxo_model_ray* rays, int64_t n, int frame, float res_x, float res_y, vxo_model_hit* out) {
+}  // extern "C"
+namespace {
+inline ModelMips make_mips(const uint8_t* mip0, const uint8_t* mip1, const uint8_t* mip2, int sx, int sy, int sz) {
     ModelMips M;
     M.d[0] = mip0; M.d[1] = mip1; M.d[2] = mip2;
     M.sx[0] = sx; M.sy[0] = sy; M.sz[0] = sz;
     for (int m = 1; m < 3; ++m) { M.sx[m] = M.sx[m - 1] > 1 ? M.sx[m - 1] / 2 : 1; M.sy[m] = M.sy[m - 1] > 1 ? M.sy[m - 1] / 2 : 1; M.sz[m] = M.sz[m - 1] > 1 ? M.sz[m - 1] / 2 : 1; }
+    return M;
+}
+
+// clipToAABB (:49-61) + intersectVolume (:64-125) for one fragment: cam = In.localCameraPos, dir = In.localDirection, uv = UV
+inline vxo_model_hit traverse_model(const ModelMips& M, V3 cam, V3 dir, float u, float v, int frame, float res_x, float res_y) {
+    vxo_model_hit h;
+    memset(&h, 0, sizeof h);
+    const int sx = M.sx[0], sy = M.sy[0], sz = M.sz[0];
     const V3 vsize = v3((float)sx, (float)sy, (float)sz);
+    const V3 direction = normalize3(dir);                                                     // GeometryVoxel.frag:145
+    V3 origin = cam;
+    if (!(gclamp(cam.x, 0.0f, vsize.x) == cam.x && gclamp(cam.y, 0.0f, vsize.y) == cam.y && gclamp(cam.z, 0.0f, vsize.z) == cam.z)) {
+        const V3 invDir = v3(1.0f, 1.0f, 1.0f) / direction;
+        const V3 sgn = v3(gstep(direction.x, 0.0f), gstep(direction.y, 0.0f), gstep(direction.z, 0.0f));
+        const V3 t = (sgn * vsize - cam) * invDir;
+        const float tmin = fmaxf(fmaxf(t.x, t.y), t.z);
+        origin = cam + direction * (tmin - 0.001f);
+    }
+    const V3 stepSign = v3(gsign(direction.x), gsign(direction.y), gsign(direction.z));
+    const V3 t_delta = v3(1.0f, 1.0f, 1.0f) / (direction * stepSign);
+    int mip = 2, i = 0, nt = 0, fetches = 0;
+    bool done = false;
+    do {
+        const float mipSize = (float)(1 << mip);
+        origin = v3(origin.x / mipSize, origin.y / mipSize, origin.z / mipSize);
+        int cx = f2i(floorf(origin.x)), cy = f2i(floorf(origin.y)), cz = f2i(floorf(origin.z));
+        const V3 next_bounds = v3((float)cx, (float)cy, (float)cz) + (stepSign * 0.5f + v3(0.5f, 0.5f, 0.5f));
+        V3 t_max = (next_bounds - origin) / direction;
+        const int hx = f2i((float)sx / mipSize) + 1, hy = f2i((float)sy / mipSize) + 1, hz = f2i((float)sz / mipSize) + 1;   // ivec3(volumeDimension / mipSize) + 1
+        int nn = 0;
+        do {
+            const V3 select = v3(gstep(t_max.x, t_max.z) * gstep(t_max.x, t_max.y), gstep(t_max.y, t_max.x) * gstep(t_max.y, t_max.z),
+                                 gstep(t_max.z, t_max.y) * gstep(t_max.z, t_max.x));
+            const V3 adv = select * stepSign;
+            cx += f2i(adv.x); cy += f2i(adv.y); cz += f2i(adv.z);
+            if (cx < -1 || cy < -1 || cz < -1 || cx > hx || cy > hy || cz > hz) { done = true; break; }   // :84-86 return false
+            const unsigned voxel = model_fetch(M, cx, cy, cz, mip);
+            ++fetches;
+            if (voxel != 0u) {
+                const float best_t = dot3(t_max, select);
+                const V3 at = (origin + direction * best_t) * mipSize;
+                if (mip == 0 || (float)mip < 0.001f * length3(at - cam)) {                       // :92-96 LOD early accept
+                    const float cxr = ground(u * res_x * 0.5f), cyr = ground(v * res_y * 0.5f);   // :99
+                    const bool glass = voxel < 16u && gmod(cyr + cxr, 2.0f) == (float)(frame % 2);   // :100
+                    if (!glass) {
+                        h.hit = 1; h.material = voxel;
+                        const V3 nrm = (stepSign * -1.0f) * select;
+                        h.normal[0] = nrm.x; h.normal[1] = nrm.y; h.normal[2] = nrm.z;
+                        h.pos[0] = at.x; h.pos[1] = at.y; h.pos[2] = at.z;
+                        done = true;
+                        break;
+                    }
+                } else {
+                    mip--;                                                                       // :110-112
+                    origin = origin + v3((direction.x * best_t) / mipSize, (direction.y * best_t) / mipSize, (direction.z * best_t) / mipSize);
+                    break;
+                }
+            }
+            t_max = t_max + t_delta * select;
+            nt++;
+        } while (++nn < 512);
+        if (done) break;
+        origin = origin * mipSize;                                                               // :121
+    } while (++i < 4);
+    h.fetches = fetches; h.steps = nt;
+    return h;
+}
+
+// mat4 * mat4 in glm's order (type_mat4x4.inl operator*): column j of the product = A0*B[j][0] + A1*B[j][1] + A2*B[j][2] + A3*B[j][3],
+// summed left to right
+inline void mat_mat(const float* A, const float* B, float* R) {
+    for (int j = 0; j < 4; ++j)
+        for (int r = 0; r < 4; ++r)
+            R[j * 4 + r] = ((A[0 + r] * B[j * 4 + 0] + A[4 + r] * B[j * 4 + 1]) + A[8 + r] * B[j * 4 + 2]) + A[12 + r] * B[j * 4 + 3];
+}
+inline V4 normalize4(V4 v) {
+    const float inv = 1.0f / sqrtf((v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w));      // glm dot(vec4): (x + y) + (z + w), func_geometric.inl:58-64
+    return V4{v.x * inv, v.y * inv, v.z * inv, v.w * inv};
+}
+}  // namespace
+extern "C" {
+
+// rays: vxo_model_ray {cam[3] = In.localCameraPos, dir[3] = In.localDirection (not normalised), uv[2]}.
+// out: vxo_model_hit {hit, material, fetches (texelFetch calls), steps (nt), pos[3], normal[3]}.
+void vxo_trace_model_rays(const uint8_t* mip0, const uint8_t* mip1, const uint8_t* mip2, int sx, int sy, int sz,
+                          const vxo_model_ray* rays, int64_t n, int frame, float res_x, float res_y, vxo_model_hit* out) {
+    const ModelMips M = make_mips(mip0, mip1, mip2, sx, sy, sz);
 #pragma omp parallel for schedule(static)
     for (int64_t ri = 0; ri < n; ++ri) {
         const vxo_model_ray& r = rays[ri];
-        vxo_model_hit h;
-        memset(&h, 0, sizeof h);
-        const V3 cam = v3(r.cam[0], r.cam[1], r.cam[2]);
-        const V3 direction = normalize3(v3(r.dir[0], r.dir[1], r.dir[2]));                    // GeometryVoxel.frag:145
-        // clipToAABB :49-61
-        V3 origin = cam;
-        if (!(gclamp(cam.x, 0.0f, vsize.x) == cam.x && gclamp(cam.y, 0.0f, vsize.y) == cam.y && gclamp(cam.z, 0.0f, vsize.z) == cam.z)) {
-            const V3 invDir = v3(1.0f, 1.0f, 1.0f) / direction;
-            const V3 sgn = v3(gstep(direction.x, 0.0f), gstep(direction.y, 0.0f), gstep(direction.z, 0.0f));
-            const V3 t = (sgn * vsize - cam) * invDir;
-            const float tmin = fmaxf(fmaxf(t.x, t.y), t.z);
-            origin = cam + direction * (tmin - 0.001f);
+        out[ri] = traverse_model(M, v3(r.cam[0], r.cam[1], r.cam[2]), v3(r.dir[0], r.dir[1], r.dir[2]), r.uv[0], r.uv[1], frame, res_x, res_y);
+    }
+}
+
+// One fragment of GeometryVoxel.frag's main() (:127-182) from its interpolated inputs: UV (:140-142), traversal, and on a
+// hit the G-buffer outputs -- palette colour with alpha = step(hitMat, 16), palette material, world normal, motion
+// vector, gl_FragDepth with the anti-z-fight factor (1 - 1e-7 * VolumeRID).  Floats, before the attachment conversions.
+void vxo_geometry_fragment(const vxo_model* model_mips /* [3] */, const vxo_view* view, const vxo_vox_cmd* cmd,
+                           const uint32_t* pal_color, const uint32_t* pal_material, const vxo_frag_in* in, int64_t n, vxo_frag_out* out) {
+    const ModelMips M = make_mips(model_mips[0].voxels, model_mips[1].voxels, model_mips[2].voxels, model_mips[0].sx, model_mips[0].sy, model_mips[0].sz);
+    float PV[16];
+    mat_mat(view->ProjectionMatrix, view->ViewMatrix, PV);
+    float PVlast[16];
+    mat_mat(view->ProjectionMatrix, view->LastViewMatrix, PVlast);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        const vxo_frag_in& f = in[i];
+        vxo_frag_out o;
+        memset(&o, 0, sizeof o);
+        const V4 sd = mat_mul(f.mvp, V4{f.dir[0], f.dir[1], f.dir[2], 0.0f});                              // :140
+        float u = sd.x / sd.w, v = sd.y / sd.w;                                                        // :141
+        u += view->Jitter[0] * view->iRes[0]; v += view->Jitter[1] * view->iRes[1];                       // :142
+        const vxo_model_hit h = traverse_model(M, v3(f.cam[0], f.cam[1], f.cam[2]), v3(f.dir[0], f.dir[1], f.dir[2]), u, v, view->Frame, view->Res[0], view->Res[1]);
+        o.hit = h.hit; o.material_index = h.material; o.fetches = h.fetches;
+        if (h.hit) {
+            const uint32_t pc = pal_color[(size_t)cmd->PalleteIndex * 256 + h.material], pm = pal_material[(size_t)cmd->PalleteIndex * 256 + h.material];
+            o.color[0] = unorm8(pc); o.color[1] = unorm8(pc >> 8); o.color[2] = unorm8(pc >> 16);
+            o.color[3] = gstep((float)h.material, 16.0f);                                              // :155 step(hitMat, 16)
+            o.material[0] = unorm8(pm); o.material[1] = unorm8(pm >> 8); o.material[2] = unorm8(pm >> 16); o.material[3] = unorm8(pm >> 24);
+            const V4 nw = normalize4(mat_mul(cmd->WorldMatrix, V4{h.normal[0], h.normal[1], h.normal[2], 0.0f}));   // :157
+            o.normal[0] = nw.x; o.normal[1] = nw.y; o.normal[2] = nw.z; o.normal[3] = nw.w;
+            const V4 hp = V4{h.pos[0] * 0.1f, h.pos[1] * 0.1f, h.pos[2] * 0.1f, 1.0f};
+            const V4 worldHit = mat_mul(cmd->WorldMatrix, hp), lastWorldHit = mat_mul(cmd->LastWorldMatrix, hp);   // :159-160
+            const V4 cur = mat_mul(PV, worldHit), last = mat_mul(PVlast, lastWorldHit);                    // :161-162
+            o.motion[0] = -0.5f * (cur.x / cur.w - last.x / last.w);                                    // :166
+            o.motion[1] = 0.5f * (cur.y / cur.w - last.y / last.w);
+            const float linearDepth = cur.w;                                                           // :169
+            o.depth = (1.0f - 0.0000001f * (float)cmd->VolumeRID) * (linearDepth - 0.1f) / (FAR_ - 0.1f);   // :170
         }
-        // intersectVolume :64-125
-        const V3 stepSign = v3(gsign(direction.x), gsign(direction.y), gsign(direction.z));
-        const V3 t_delta = v3(1.0f, 1.0f, 1.0f) / (direction * stepSign);
-        int mip = 2, i = 0, nt = 0, fetches = 0;
-        bool done = false;
-        do {
-            const float mipSize = (float)(1 << mip);
-            origin = v3(origin.x / mipSize, origin.y / mipSize, origin.z / mipSize);
-            int cx = f2i(floorf(origin.x)), cy = f2i(floorf(origin.y)), cz = f2i(floorf(origin.z));
-            const V3 next_bounds = v3((float)cx, (float)cy, (float)cz) + (stepSign * 0.5f + v3(0.5f, 0.5f, 0.5f));
-            V3 t_max = (next_bounds - origin) / direction;
-            // ivec3(volumeDimension / mipSize) + 1
-            const int hx = f2i((float)sx / mipSize) + 1, hy = f2i((float)sy / mipSize) + 1, hz = f2i((float)sz / mipSize) + 1;
-            int nn = 0;
-            do {
-                const V3 select = v3(gstep(t_max.x, t_max.z) * gstep(t_max.x, t_max.y), gstep(t_max.y, t_max.x) * gstep(t_max.y, t_max.z),
-                                     gstep(t_max.z, t_max.y) * gstep(t_max.z, t_max.x));
-                const V3 adv = select * stepSign;
-                cx += f2i(adv.x); cy += f2i(adv.y); cz += f2i(adv.z);
-                if (cx < -1 || cy < -1 || cz < -1 || cx > hx || cy > hy || cz > hz) { done = true; break; }   // :84-86 return false
-                const unsigned voxel = model_fetch(M, cx, cy, cz, mip);
-                ++fetches;
-                if (voxel != 0u) {
-                    const float best_t = dot3(t_max, select);
-                    const V3 at = (origin + direction * best_t) * mipSize;
-                    if (mip == 0 || (float)mip < 0.001f * length3(at - cam)) {                   // :92-96 LOD early accept
-                        const float cxr = ground(r.uv[0] * res_x * 0.5f), cyr = ground(r.uv[1] * res_y * 0.5f);   // :99
-                        const bool glass = voxel < 16u && gmod(cyr + cxr, 2.0f) == (float)(frame % 2);            // :100
-                        if (!glass) {
-                            h.hit = 1; h.material = voxel;
-                            const V3 nrm = (stepSign * -1.0f) * select;
-                            h.normal[0] = nrm.x; h.normal[1] = nrm.y; h.normal[2] = nrm.z;
-                            h.pos[0] = at.x; h.pos[1] = at.y; h.pos[2] = at.z;
-                            done = true;
-                            break;
-                        }
-                    } else {
-                        mip--;                                                                   // :110-112
-                        origin = origin + v3((direction.x * best_t) / mipSize, (direction.y * best_t) / mipSize, (direction.z * best_t) / mipSize);
-                        break;
-                    }
-                }
-                t_max = t_max + t_delta * select;
-                nt++;
-            } while (++nn < 512);
-            if (done) break;
-            origin = origin * mipSize;                                                           // :121
-        } while (++i < 4);
-        h.fetches = fetches; h.steps = nt;
-        out[ri] = h;
+        out[i] = o;
     }
 }
 

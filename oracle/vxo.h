@@ -134,6 +134,15 @@ void vxo_model_mip(const uint8_t* parent, int psx, int psy, int psz, uint8_t* ou
 void vxo_trace_model_rays(const uint8_t* mip0, const uint8_t* mip1, const uint8_t* mip2, int sx, int sy, int sz,
                           const vxo_model_ray* rays, int64_t n, int frame, float res_x, float res_y, vxo_model_hit* out);
 
+/* One fragment of GeometryVoxel.frag's main(): GeometryVoxelPipeline::Cmd (Pipelines/GeometryVoxelPipeline.h:30-36) + the
+ * interpolated inputs of the fragment stage in, G-buffer outputs (floats, before attachment conversion) out. */
+typedef struct vxo_vox_cmd { float WorldMatrix[16], LastWorldMatrix[16]; int32_t VolumeRID, PalleteIndex, _pad[2]; } vxo_vox_cmd;
+typedef struct vxo_frag_in { float cam[3], dir[3], mvp[16]; } vxo_frag_in;          /* In.localCameraPos, In.localDirection, In.MVPMatrix */
+typedef struct vxo_frag_out { int32_t hit; uint32_t material_index; int32_t fetches, _pad; float color[4], normal[4], material[4], motion[2], depth, _pad2; } vxo_frag_out;
+void vxo_geometry_fragment(const vxo_model* model_mips /* [3]: levels 0, 1, 2 */, const vxo_view* view, const vxo_vox_cmd* cmd,
+                           const uint32_t* pal_color /* [palettes][256] RGBA8 */, const uint32_t* pal_material, const vxo_frag_in* in,
+                           int64_t n, vxo_frag_out* out);
+
 /* ShadowVoxSystem::SetVolumeAt / OnUpdate / OnVoxDestroyed on a host staging buffer. */
 void vxo_set_volume_at(uint8_t* data, int sx, int sy, int sz, int x, int y, int z, int value);
 int  vxo_get_volume_at(const vxo_volume* vol, int x, int y, int z, int mip);

@@ -303,6 +303,41 @@ def shader_model_trace(voxels, rays, frame=0, res=(1920.0, 1080.0), mips=None):
     return out
 
 
+VOX_CMD_DTYPE = np.dtype([("WorldMatrix", "<f4", (16,)), ("LastWorldMatrix", "<f4", (16,)), ("VolumeRID", "<i4"), ("PalleteIndex", "<i4"), ("_pad", "<i4", (2,))])
+FRAG_IN_DTYPE = np.dtype([("cam", "<f4", (3,)), ("dir", "<f4", (3,)), ("mvp", "<f4", (16,))])
+FRAG_OUT_DTYPE = np.dtype([("hit", "<i4"), ("material_index", "<u4"), ("fetches", "<i4"), ("_pad", "<i4"), ("color", "<f4", (4,)), ("normal", "<f4", (4,)),
+                           ("material", "<f4", (4,)), ("motion", "<f4", (2,)), ("depth", "<f4"), ("_pad2", "<f4")])
+assert VOX_CMD_DTYPE.itemsize == 144 and FRAG_IN_DTYPE.itemsize == 88 and FRAG_OUT_DTYPE.itemsize == 80
+
+
+class _Model(C.Structure):
+    _fields_ = [("voxels", C.c_void_p), ("sx", C.c_int32), ("sy", C.c_int32), ("sz", C.c_int32)]
+
+
+def geometry_fragment(voxels, view, cmd, pal_color, pal_material, frags, mips=None, reference=False):
+    """One fragment of GeometryVoxel.frag's main() per entry of `frags` (FRAG_IN_DTYPE) -> FRAG_OUT_DTYPE.
+    reference=True runs the reference's own shader compiled for the host instead of the oracle."""
+    m = model_mips(voxels) if mips is None else mips
+    sz, sy, sx = m[0].shape
+    cmd = np.ascontiguousarray(cmd, dtype=VOX_CMD_DTYPE).reshape(())
+    pc, pm = np.ascontiguousarray(pal_color, np.uint32), np.ascontiguousarray(pal_material, np.uint32)
+    assert pc.ndim == 2 and pc.shape[1] == 256 and pm.shape == pc.shape
+    frags = np.ascontiguousarray(frags, dtype=FRAG_IN_DTYPE)
+    out = np.zeros(len(frags), dtype=FRAG_OUT_DTYPE)
+    vw = _view(view)
+    if reference:
+        L = shader_lib()
+        L.vxshader_geometry_fragment.argtypes = [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]
+        L.vxshader_geometry_fragment(_p(m[0]), _p(m[1]), _p(m[2]), sx, sy, sz, _p(vw), cmd.ctypes.data_as(C.c_void_p), _p(pc), _p(pm), pc.shape[0],
+                                     _p(frags), len(frags), _p(out))
+        return out
+    mm = (_Model * 3)(*[_Model(a.ctypes.data, a.shape[2], a.shape[1], a.shape[0]) for a in m])
+    f = lib().vxo_geometry_fragment
+    f.argtypes = [C.c_void_p] * 6 + [C.c_int64, C.c_void_p]
+    f(C.cast(mm, C.c_void_p), _p(vw), cmd.ctypes.data_as(C.c_void_p), _p(pc), _p(pm), _p(frags), len(frags), _p(out))
+    return out
+
+
 def resolve_ambient(view, gb, albedo, shadow, ao, rows=None):
     """LightAmbient.frag's out_Color (float32 RGBA, (H, W, 4)) from the march planes + COLOR_TEXTURE (albedo RGBA8)."""
     h, w = gb["depth24"].shape
