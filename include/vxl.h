@@ -240,6 +240,17 @@ typedef struct vxl_model_hit { int32_t hit; uint32_t material; int32_t fetches, 
 int vxl_trace_model_rays(vxl_ctx* ctx, int model_id, const vxl_model_ray* rays, int64_t n, int frame, float res_x, float res_y,
                          vxl_model_hit* out);
 
+/* The geometry pass over a draw list (GeometryVoxelPipeline::Use, Pipelines/GeometryVoxelPipeline.h:49-71; row f1): per pixel, in
+ * list order, every model whose box the pixel's view ray enters from outside runs GeometryVoxel.frag's main(); depth test LESS on
+ * D24; planes written in the attachment formats of Graphics.h:51-60 (sky: depth 0xFFFFFF, the rest 0).  vxl_vox_cmd is
+ * GeometryVoxelPipeline::Cmd (:30-36) with PADDING[0] carrying the vxl model id; VolumeRID only feeds the anti-z-fight depth factor.
+ * The fragment stage's interpolated inputs are evaluated at the pixel centre (In.localDirection = the view ray in model space).
+ * cmds: HOST.  pal_color / pal_material: DEVICE [n_palettes][256] RGBA8 (PalleteAsset images).  out planes: DEVICE, tile-compact. */
+typedef struct vxl_vox_cmd { float WorldMatrix[16], LastWorldMatrix[16]; int32_t VolumeRID, PalleteIndex, model, _pad; } vxl_vox_cmd;
+typedef struct vxl_gbuffer_out { uint32_t* depth24; uint32_t* normal; uint32_t* material; uint32_t* albedo; float* motion /* [2] per pixel, may be NULL */; } vxl_gbuffer_out;
+int vxl_gbuffer_models(vxl_ctx* ctx, const vxl_view* view, const vxl_frame* frame /* geometry only: sizes and tiles */, const vxl_vox_cmd* cmds,
+                       int n_cmds, const uint32_t* pal_color, const uint32_t* pal_material, const vxl_gbuffer_out* out);
+
 /* rays/out are DEVICE pointers */
 int vxl_trace_rays(vxl_ctx* ctx, vxl_volume* vol, const vxl_ray* rays, int64_t n, int variant, vxl_hit* out);
 

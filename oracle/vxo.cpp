@@ -846,6 +846,102 @@ void vxo_geometry_fragment(const vxo_model* model_mips /* [3] */, const vxo_view
     }
 }
 
+}  // extern "C"
+namespace {
+// inverse of an affine mat4 (last row 0 0 0 1; TransformSystem.cpp:124-135 builds T*R*S): adjugate / determinant of the 3x3
+// block, then -A^-1 t.  Stands in for the vertex shader's inverse(cmd.WorldMatrix) (GeometryVoxel.vert:66).
+inline void affine_inverse(const float* M, float* R) {
+    const float a = M[0], b = M[4], c = M[8], d = M[1], e = M[5], f = M[9], g = M[2], h = M[6], i = M[10];
+    const float A = e * i - f * h, B = f * g - d * i, C = d * h - e * g;
+    const float det = (a * A + b * B) + c * C;
+    const float id = 1.0f / det;
+    const float r00 = A * id, r01 = (c * h - b * i) * id, r02 = (b * f - c * e) * id;
+    const float r10 = B * id, r11 = (a * i - c * g) * id, r12 = (c * d - a * f) * id;
+    const float r20 = C * id, r21 = (b * g - a * h) * id, r22 = (a * e - b * d) * id;
+    const float tx = M[12], ty = M[13], tz = M[14];
+    R[0] = r00; R[4] = r01; R[8] = r02; R[12] = -((r00 * tx + r01 * ty) + r02 * tz);
+    R[1] = r10; R[5] = r11; R[9] = r12; R[13] = -((r10 * tx + r11 * ty) + r12 * tz);
+    R[2] = r20; R[6] = r21; R[10] = r22; R[14] = -((r20 * tx + r21 * ty) + r22 * tz);
+    R[3] = 0.0f; R[7] = 0.0f; R[11] = 0.0f; R[15] = 1.0f;
+}
+inline uint32_t pack_unorm8x4(const float* v) {
+    uint32_t r = 0;
+    for (int k = 0; k < 4; ++k) r |= (uint32_t)rintf(gclamp(v[k], 0.0f, 1.0f) * 255.0f) << (8 * k);
+    return r;
+}
+inline uint32_t pack_snorm8x4(const float* v) {
+    uint32_t r = 0;
+    for (int k = 0; k < 4; ++k) r |= ((uint32_t)(int)rintf(gclamp(v[k], -1.0f, 1.0f) * 127.0f) & 0xFFu) << (8 * k);
+    return r;
+}
+}  // namespace
+extern "C" {
+
+// The geometry pass over a list of draws (GeometryVoxelPipeline::Use, Pipelines/GeometryVoxelPipeline.h:49-71): per pixel, in
+// list order, every model whose box the pixel's view ray enters from outside (the pipeline culls back faces, evk.cpp:470, so a
+// camera inside a box sees nothing of it) runs the fragment above; depth test LESS on the D24 value (evk.cpp:481), outputs
+// converted to the attachment formats (Graphics.h:51-60).  Declared definition: the interpolated fragment inputs are
+// evaluated per pixel centre (In.localDirection = the pixel's view ray in model space), like In.FarVec for the light passes.
+void vxo_gbuffer_models(const vxo_view* view, int W, int H, const vxo_vox_cmd* cmds, int n_cmds, const vxo_model* mips /* [n_models][3] */,
+                        const uint32_t* pal_color, const uint32_t* pal_material, uint32_t* depth24, uint32_t* normal, uint32_t* material,
+                        uint32_t* albedo, float* motion /* [H][W][2] or NULL */) {
+    struct Derived { float inv[16], mvp[16]; V3 cam; V3 size; };
+    std::vector<Derived> D((size_t)n_cmds);
+    float PV[16];
+    mat_mat(view->ProjectionMatrix, view->ViewMatrix, PV);
+    const V3 camW = v3(view->CameraPosition[0], view->CameraPosition[1], view->CameraPosition[2]);
+    for (int c = 0; c < n_cmds; ++c) {
+        affine_inverse(cmds[c].WorldMatrix, D[c].inv);
+        mat_mat(PV, cmds[c].WorldMatrix, D[c].mvp);                                             // GeometryVoxel.vert:62
+        D[c].cam = xyz(mat_mul(D[c].inv, V4{camW.x, camW.y, camW.z, 1.0f})) * 10.0f;            // :66
+        const vxo_model& m0 = mips[(size_t)cmds[c]._pad[0] * 3];
+        D[c].size = v3((float)m0.sx, (float)m0.sy, (float)m0.sz);
+    }
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int py = 0; py < H; ++py)
+        for (int px = 0; px < W; ++px) {
+            const size_t idx = (size_t)py * W + px;
+            uint32_t best = 0xFFFFFFu, onrm = 0u, omat = 0u, oalb = 0u;
+            float omx = 0.0f, omy = 0.0f;
+            // the pixel's view ray in world space (un-jittered: the vertex shader shifts the geometry by +jitter, :70-71)
+            const float u = ((float)px + 0.5f) / (float)W, v = ((float)py + 0.5f) / (float)H;
+            const float ndcx = (2.0f * u - 1.0f) - view->Jitter[0] * view->iRes[0] * 2.0f, ndcy = (1.0f - 2.0f * v) - view->Jitter[1] * view->iRes[1] * 2.0f;
+            const V4 fp = mat_mul(view->InverseProjectionMatrix, V4{ndcx, ndcy, 1.0f, 1.0f});
+            const V3 farv = v3(fp.x / fp.w, fp.y / fp.w, fp.z / fp.w);
+            const V3 farW = xyz(mat_mul(view->InverseViewMatrix, V4{farv.x, farv.y, farv.z, 1.0f}));
+            const V3 dirW = farW - camW;
+            for (int c = 0; c < n_cmds; ++c) {
+                const Derived& d = D[c];
+                const V3 ld = xyz(mat_mul(d.inv, V4{dirW.x, dirW.y, dirW.z, 0.0f})) * 10.0f;
+                // coverage: camera outside the box and the ray enters it in front of the camera (slab test)
+                const V3 lc = d.cam;
+                if (lc.x >= 0.0f && lc.x <= d.size.x && lc.y >= 0.0f && lc.y <= d.size.y && lc.z >= 0.0f && lc.z <= d.size.z) continue;
+                float t0 = 0.0f, t1 = 3.0e38f;
+                bool miss = false;
+                const float lo[3] = {lc.x, lc.y, lc.z}, dd[3] = {ld.x, ld.y, ld.z}, sz3[3] = {d.size.x, d.size.y, d.size.z};
+                for (int a = 0; a < 3; ++a) {
+                    if (dd[a] == 0.0f) { if (lo[a] < 0.0f || lo[a] > sz3[a]) miss = true; continue; }
+                    const float ta = (0.0f - lo[a]) / dd[a], tb = (sz3[a] - lo[a]) / dd[a];
+                    t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
+                }
+                if (miss || !(t0 <= t1)) continue;
+                vxo_frag_in fi;
+                fi.cam[0] = lc.x; fi.cam[1] = lc.y; fi.cam[2] = lc.z; fi.dir[0] = ld.x; fi.dir[1] = ld.y; fi.dir[2] = ld.z;
+                memcpy(fi.mvp, d.mvp, 64);
+                vxo_frag_out fo;
+                vxo_geometry_fragment(&mips[(size_t)cmds[c]._pad[0] * 3], view, &cmds[c], pal_color, pal_material, &fi, 1, &fo);
+                if (!fo.hit) continue;                                                          // discard
+                const uint32_t d24 = (uint32_t)rintf(gclamp(fo.depth, 0.0f, 1.0f) * 16777215.0f);
+                if (d24 < best) {                                                               // CompareOp::eLess
+                    best = d24; onrm = pack_snorm8x4(fo.normal); omat = pack_unorm8x4(fo.material); oalb = pack_unorm8x4(fo.color);
+                    omx = fo.motion[0]; omy = fo.motion[1];
+                }
+            }
+            depth24[idx] = best; normal[idx] = onrm; material[idx] = omat; albedo[idx] = oalb;
+            if (motion) { motion[idx * 2] = omx; motion[idx * 2 + 1] = omy; }
+        }
+}
+
 void vxo_set_volume_at(uint8_t* data, int sx, int sy, int sz, int x, int y, int z, int value) {
     if (x < 0 || y < 0 || z < 0 || x >= sx * 2 || y >= sy * 2 || z >= sz * 2) return;
     int bit = (x & 1) | ((y & 1) << 1) | ((z & 1) << 2);

@@ -143,6 +143,12 @@ void vxo_geometry_fragment(const vxo_model* model_mips /* [3]: levels 0, 1, 2 */
                            const uint32_t* pal_color /* [palettes][256] RGBA8 */, const uint32_t* pal_material, const vxo_frag_in* in,
                            int64_t n, vxo_frag_out* out);
 
+/* The geometry pass over a draw list: per pixel the nearest model hit (depth test LESS on D24), outputs in the attachment formats.
+ * cmds[c]._pad[0] = index of the draw's model in `mips` ([n_models][3]). */
+void vxo_gbuffer_models(const vxo_view* view, int W, int H, const vxo_vox_cmd* cmds, int n_cmds, const vxo_model* mips,
+                        const uint32_t* pal_color, const uint32_t* pal_material, uint32_t* depth24, uint32_t* normal, uint32_t* material,
+                        uint32_t* albedo, float* motion);
+
 /* ShadowVoxSystem::SetVolumeAt / OnUpdate / OnVoxDestroyed on a host staging buffer. */
 void vxo_set_volume_at(uint8_t* data, int sx, int sy, int sz, int x, int y, int z, int value);
 int  vxo_get_volume_at(const vxo_volume* vol, int x, int y, int z, int mip);

@@ -338,6 +338,23 @@ def geometry_fragment(voxels, view, cmd, pal_color, pal_material, frags, mips=No
     return out
 
 
+def gbuffer_models(view, W, H, cmds, models, pal_color, pal_material, want_motion=True):
+    """The geometry pass over a draw list: cmds (VOX_CMD_DTYPE, _pad[0] = index into `models`), models = list of voxel arrays.
+    -> dict(depth24, normal, material, albedo (uint32 (H, W)), motion (H, W, 2))."""
+    cmds = np.ascontiguousarray(cmds, dtype=VOX_CMD_DTYPE)
+    keep = [model_mips(m) for m in models]
+    flat = (_Model * (3 * len(keep)))(*[_Model(a.ctypes.data, a.shape[2], a.shape[1], a.shape[0]) for mm in keep for a in mm])
+    pc, pm = np.ascontiguousarray(pal_color, np.uint32), np.ascontiguousarray(pal_material, np.uint32)
+    out = {k: np.zeros((H, W), np.uint32) for k in ("depth24", "normal", "material", "albedo")}
+    out["motion"] = np.zeros((H, W, 2), np.float32)
+    vw = _view(view)
+    f = lib().vxo_gbuffer_models
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 8
+    f(_p(vw), W, H, _p(cmds), len(cmds), C.cast(flat, C.c_void_p), _p(pc), _p(pm), _p(out["depth24"]), _p(out["normal"]), _p(out["material"]),
+      _p(out["albedo"]), _p(out["motion"]) if want_motion else None)
+    return out
+
+
 def resolve_ambient(view, gb, albedo, shadow, ao, rows=None):
     """LightAmbient.frag's out_Color (float32 RGBA, (H, W, 4)) from the march planes + COLOR_TEXTURE (albedo RGBA8)."""
     h, w = gb["depth24"].shape

@@ -137,3 +137,22 @@ def glassy_house(size=40, seed=1):
     solid = m > 0
     m[solid] = rs.randint(1, 64, size=int(solid.sum())).astype(np.uint8)
     return m
+
+
+def model_scene(width=160, height=96, frame=2):
+    """A small draw list for the geometry pass: three models (two sizes), five instances with rotations and overlaps, two palettes."""
+    rs = np.random.RandomState(21)
+    models = [glassy_house(40, seed=1), glassy_house(24, seed=2), np.full((8, 4, 12), 77, np.uint8)]
+    cmds = np.zeros(5, S.VOX_CMD_DTYPE)
+    place = [((0.0, 0.0, 0.0), (0.0, 0.3, 0.0), 0), ((3.0, 0.2, 1.0), (0.1, -0.8, 0.05), 1), ((1.0, 0.5, 1.5), (0.0, 1.1, 0.0), 1),   # overlaps the first
+             ((-1.5, 1.0, 2.5), (0.4, 0.2, -0.3), 2), ((2.0, 3.0, 2.0), (0.0, 0.0, 0.0), 0)]
+    for i, (pos, rot, mi) in enumerate(place):
+        cmds[i]["WorldMatrix"] = S.transform_matrix(pos, rot)
+        cmds[i]["LastWorldMatrix"] = S.transform_matrix((pos[0] + 0.02, pos[1], pos[2] - 0.01), rot)
+        cmds[i]["VolumeRID"] = 3 + i
+        cmds[i]["PalleteIndex"] = i % 2
+        cmds[i]["model"] = mi
+    pal_c = rs.randint(0, 2 ** 32, size=(2, 256), dtype=np.uint64).astype(np.uint32)
+    pal_m = rs.randint(0, 2 ** 32, size=(2, 256), dtype=np.uint64).astype(np.uint32)
+    view = S.make_view((7.5, 5.0, -4.0), 2.45, -0.45, width, height, frame)
+    return models, cmds, pal_c, pal_m, view

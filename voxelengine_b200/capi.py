@@ -19,7 +19,7 @@ SYMBOLS = [
     "vxl_pass_ambient", "vxl_pass_point", "vxl_pass_spot", "vxl_pass_reflection", "vxl_trace_rays",
     "vxl_lighting_host", "vxl_volume_gen_terrain", "vxl_gbuffer_primary",
     "vxl_debug_set_variant", "vxl_debug_fetched_probes", "vxl_volume_debug_occupancy",
-    "vxl_resolve_ambient", "vxl_resolve_point", "vxl_resolve_spot", "vxl_trace_model_rays",
+    "vxl_resolve_ambient", "vxl_resolve_point", "vxl_resolve_spot", "vxl_trace_model_rays", "vxl_gbuffer_models",
 ]
 
 VXL_MAX_LIGHTS = 64
@@ -44,6 +44,11 @@ class Stats(C.Structure):
 class Resolve(C.Structure):
     """vxl_resolve"""
     _fields_ = [("albedo", C.c_void_p), ("depth_full", C.c_void_p)]
+
+
+class GBufferOut(C.Structure):
+    """vxl_gbuffer_out"""
+    _fields_ = [("depth24", C.c_void_p), ("normal", C.c_void_p), ("material", C.c_void_p), ("albedo", C.c_void_p), ("motion", C.c_void_p)]
 
 
 class LightingHostArgs(C.Structure):
@@ -89,6 +94,7 @@ def load():
         "vxl_resolve_spot": [vp, vp, P(Frame), P(Resolve), vp, i32, vp, vp],
         "vxl_trace_rays": [vp, vp, vp, i64, i32, vp],
         "vxl_trace_model_rays": [vp, i32, vp, i64, i32, C.c_float, C.c_float, vp],
+        "vxl_gbuffer_models": [vp, vp, P(Frame), vp, i32, vp, vp, P(GBufferOut)],
         "vxl_lighting_host": [vp, vp, P(LightingHostArgs)],
         "vxl_volume_gen_terrain": [vp], "vxl_gbuffer_primary": [vp, vp, vp, P(Frame)],
         "vxl_debug_set_variant": [vp, i32], "vxl_debug_fetched_probes": [vp, P(C.c_uint64)],

@@ -388,6 +388,33 @@ def trace_model_rays(ctx: Context, model_id: int, rays: np.ndarray, frame: int =
     return d_out.cpu().numpy().view(MODEL_HIT_DTYPE).copy()
 
 
+class GeometryVoxelPipeline:
+    """The geometry pass over a draw list (Sources/Graphics/Pipelines/GeometryVoxelPipeline.h:49-71): fills a GeometryBuffer's
+    depth / normal / material planes plus an albedo plane (and optionally motion vectors) from model instances."""
+    _inst = None
+
+    @classmethod
+    def Get(cls):
+        cls._inst = cls._inst or cls()
+        return cls._inst
+
+    def Use(self, viewBuffer, geometryFB: GeometryBuffer, cmds: np.ndarray, pal_color, pal_material, albedo=None, motion=None):
+        """cmds: scenes.VOX_CMD_DTYPE (model = id from ShadowVoxSystem.add_model).  pal_*: torch int32 [n_palettes][256] RGBA8."""
+        from .scenes import VOX_CMD_DTYPE
+        torch = _torch()
+        ctx = geometryFB.ctx
+        cmds = np.ascontiguousarray(cmds, dtype=VOX_CMD_DTYPE)
+        if albedo is None:
+            albedo = torch.zeros(geometryFB.shape, dtype=torch.int32, device=ctx.torch_device)
+        v, vp = _view_ptr(viewBuffer)
+        f = geometryFB.frame()
+        o = capi.GBufferOut(geometryFB.depth24.data_ptr(), geometryFB.normal.data_ptr(), geometryFB.material.data_ptr(), albedo.data_ptr(),
+                            motion.data_ptr() if motion is not None else None)
+        check(ctx.lib.vxl_gbuffer_models(ctx.h, vp, C.byref(f), _np_ptr(cmds), len(cmds), _dev_ptr(pal_color), _dev_ptr(pal_material), C.byref(o)),
+              "vxl_gbuffer_models")
+        return albedo
+
+
 class LightBuffer:
     """The light buffer the reference's light passes blend into (WorldRenderer.cpp:242-258), as float32 RGBA in
     tile-compact layout: what LightAmbient / LightPoint / LightSpot.frag compute after the march.

@@ -133,6 +133,10 @@ MODEL_HIT_DTYPE = np.dtype([("hit", "<i4"), ("material", "<u4"), ("fetches", "<i
                             ("normal", "<f4", (3,))])                                                                 # vxl_model_hit
 
 
+VOX_CMD_DTYPE = np.dtype([("WorldMatrix", "<f4", (16,)), ("LastWorldMatrix", "<f4", (16,)), ("VolumeRID", "<i4"), ("PalleteIndex", "<i4"),
+                          ("model", "<i4"), ("_pad", "<i4")])                                                           # vxl_vox_cmd
+
+
 def point_lights(positions, ranges, color=(2.0, 2.0, 2.0), attenuation=2.0):
     n = len(positions)
     a = np.zeros(n, dtype=POINT_LIGHT_DTYPE)
