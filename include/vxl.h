@@ -228,6 +228,29 @@ int vxl_resolve_point(vxl_ctx* ctx, const vxl_view* view, const vxl_frame* frame
 int vxl_resolve_spot(vxl_ctx* ctx, const vxl_view* view, const vxl_frame* frame, const vxl_resolve* r,
                      const vxl_spot_light* lights /* HOST */, int n_lights, const float* shadow, float* inout_rgba);
 
+/* ---- after the light passes -------------------------------------------------- */
+/* LightTAAPipeline::Use (Pipelines/LightTAAPipeline.h:34-53 -> Sources/Shaders/LightTAA.frag:37-141): temporal + spatial
+ * accumulation of the light buffer; and the colour LightReflection.frag writes around its march (:60-139; the march itself is
+ * vxl_pass_reflection).  Both sample OTHER pixels, so their inputs are whole-frame row-major planes; the output pixels and their
+ * tile-compact layout come from `frame` as in every other pass (frame.depth24 / normal / material / noise: the shard's own
+ * planes).  Nearest sampling (evk.cpp:277-293), out of range reads 0.  Light / motion planes are float32: the values before the
+ * RGBA16F / RG16F attachment conversion.  vxl_light_taa is bit-exact against the oracle (cos / sin tabulated as correctly
+ * rounded values); vxl_resolve_reflection carries pow() (1e-5 relative).  The sky box is a uniform colour `sky_rgb` (the cube
+ * map is outside the path; NULL = black).  All plane pointers: DEVICE. */
+typedef struct vxl_full_planes {
+    const uint32_t* depth24;     /* [height][width] D24 */
+    const uint32_t* normal;      /* R8G8B8A8_SNORM */
+    const uint32_t* material;    /* RGBA8 UNORM */
+    const uint32_t* albedo;      /* RGBA8 UNORM colour attachment */
+    const float* motion;         /* [height][width][2] (GeometryVoxel.frag:166 out_Motion) */
+    const float* light;          /* [height][width][4] the current light buffer (vxl_resolve_ambient + _point + _spot) */
+    const float* last_light;     /* [height][width][4] the previous frame's vxl_light_taa output (alpha = variance) */
+} vxl_full_planes;
+int vxl_light_taa(vxl_ctx* ctx, const vxl_view* view, const vxl_frame* frame, const vxl_full_planes* full, float* out_rgba /* tile-compact [4] */);
+int vxl_resolve_reflection(vxl_ctx* ctx, const vxl_view* view, const vxl_frame* frame, const float* spec_t /* tile-compact */,
+                           const uint32_t* depth_full /* NULL: one whole-frame tile */, const float* light_full /* [h][w][4] TAA light, may be NULL */,
+                           const float* sky_rgb /* HOST [3] or NULL */, float* out_rgba /* tile-compact [4] */);
+
 /* ---- model traversal (core) -------------------------------------------------- */
 /* The G-buffer producer's traversal of one model volume: VoxAsset::Upload's mip chain (Sources/Asset/VoxAsset.cpp:3-64,
  * built on the device on first use) and GeometryVoxel.frag's clipToAABB (:49-61) + intersectVolume (:64-125) -- the

@@ -36,6 +36,13 @@ SUBSTITUTIONS = [
      r"float raycastShadowVolume\1_impl(vec3 origin, vec3 dir, float dist) {", "call logging hook"),
     # GLSL constructors consume only as many components as they need (vec4(vec3, vec3) takes the second one's .x); colour output only
     (r"vec4\(ambient\*F\*\(1\.0-roughness\), F\)", r"vec4(ambient*F*(1.0-roughness), (F).x)", "GLSL constructor truncation"),
+    # writes through a swizzle (LightTAA.frag:123,124,129): glm's function-style swizzles return values, so the statement is
+    # re-spelt on the whole vec4 with the same right-hand side
+    (r"^(\s*)(\w+)\.xyz\s*([+/])=\s*([^;]+);", r"\1\2 = vec4(vec3(\2) \3 (\4), \2.w);", "swizzle compound assignment"),
+    (r"^(\s*)(\w+)\.xyz\s*=\s*([^;=][^;]*);", r"\1\2 = vec4(\3, \2.w);", "swizzle assignment"),
+    # LightTAA.frag:30-35 names a parameter `rgb`, which collides with the swizzle macro of the prelude
+    (r"\(vec3 rgb\)", r"(vec3 rgb_)", "parameter name vs swizzle macro"),
+    (r"dot\(rgb, W\)", r"dot(rgb_, W)", "parameter name vs swizzle macro"),
 ]
 
 
@@ -82,6 +89,8 @@ def translation_unit() -> str:
         parts.append("namespace %s {\n%s\n%s\n%s\n}\n" % (ns, WRAPPERS, splice_includes(adapt(read(fn))), defs))
     # the G-buffer producer: GeometryVoxel.frag -- clipToAABB, intersectVolume and the fragment main()
     geom = adapt(read("GeometryVoxel.frag"))
+    # the step after the light passes: LightTAA.frag
+    parts.append("namespace taa {\n%s\nViewBuffer_t ViewBuffer[1];\n}\n" % adapt(read("LightTAA.frag")))
     parts.append("namespace geom {\nfloat gl_FragDepth;\n" + geom + "\nViewBuffer_t ViewBuffer[1]; VoxCmdsBuffer_t VoxCmdsBuffer[1];\n}\n")
     with open(os.path.join(HERE, "shader_driver.inc"), "r") as f:
         parts.append(f.read())

@@ -43,12 +43,14 @@ using namespace glm;
 
 // ---- resources --------------------------------------------------------------------------------------
 struct usampler3D { const uint8_t* data; int sx, sy, sz; const uint8_t* mip1; const uint8_t* mip2; };   // mips: VoxAsset volumes (3 levels, sizes halve)
-enum TexFmt { TEX_NONE = 0, TEX_D24, TEX_RGBA8_SNORM, TEX_RGBA8_UNORM };
+enum TexFmt { TEX_NONE = 0, TEX_D24, TEX_RGBA8_SNORM, TEX_RGBA8_UNORM, TEX_RGBA32F, TEX_RG32F };   // the float formats hold the light / motion planes (values before the RGBA16F / RG16F attachment conversion)
 struct sampler2D { const uint32_t* data; int w, h; TexFmt fmt; };
-struct samplerCube { int unused; };
+struct samplerCube { float r, g, b; };                                     // a uniform sky (the cube map itself is outside the path)
 
 inline vec4 vxref_decode(const sampler2D& t, int x, int y) {
     if (!t.data || x < 0 || y < 0 || x >= t.w || y >= t.h) return vec4(0.0f);
+    if (t.fmt == TEX_RGBA32F) { const float* f = (const float*)t.data + ((size_t)y * t.w + x) * 4; return vec4(f[0], f[1], f[2], f[3]); }
+    if (t.fmt == TEX_RG32F) { const float* f = (const float*)t.data + ((size_t)y * t.w + x) * 2; return vec4(f[0], f[1], 0.0f, 1.0f); }
     const uint32_t v = t.data[(size_t)y * t.w + x];
     switch (t.fmt) {
         case TEX_D24: return vec4((float)(v & 0xFFFFFFu) / 16777215.0f, 0.0f, 0.0f, 1.0f);      // D24_UNORM
@@ -76,13 +78,15 @@ inline ivec3 textureSize(const usampler3D& t, int) { return ivec3(t.sx, t.sy, t.
 inline ivec2 textureSize(const sampler2D& t, int) { return ivec2(t.w, t.h); }
 // nearest filtering (the reference's samplers, Vendor/evk/evk.cpp:277-293), unnormalised coordinate = uv * size, floor
 inline vec4 texture(const sampler2D& t, vec2 uv) { return vxref_decode(t, (int)std::floor(uv.x * (float)t.w), (int)std::floor(uv.y * (float)t.h)); }
-inline vec4 texture(const samplerCube&, vec3) { return vec4(0.0f); }
+inline vec4 texture(const samplerCube& c, vec3) { return vec4(c.r, c.g, c.b, 1.0f); }
 
 // ---- GLSL implicit conversions glm's templates do not perform (int -> float promotes first) -------------
 namespace glm {
 inline vec3 operator/(ivec3 const& a, float b) { return vec3(a) / b; }
 inline vec3 operator/(vec3 const& a, int b) { return a / (float)b; }
 inline vec2 operator+(ivec2 const& a, vec2 const& b) { return vec2(a) + b; }
+inline vec2 operator/(float a, ivec2 const& b) { return a / vec2(b); }
+inline float max(float a, int b) { return glm::max(a, (float)b); }
 inline float mod(int a, int b) { return glm::mod((float)a, (float)b); }
 inline float mod(float a, int b) { return glm::mod(a, (float)b); }
 inline float step(uint edge, int x) { return glm::step((float)edge, (float)x); }

@@ -670,6 +670,185 @@ void vxo_resolve_local(const vxo_view* view, const vxo_gbuffer* gb, const uint32
 }
 
 // ---------------------------------------------------------------------------------------------
+// the steps after the light passes.
+//   vxo_light_taa           Sources/Shaders/LightTAA.frag:37-141 (temporal + spatial accumulation of the light buffer)
+//   vxo_resolve_reflection  Sources/Shaders/LightReflection.frag:60-139 (the colour around the specular-occlusion march)
+// Textures are sampled with the nearest filter of evk's samplers (Vendor/evk/evk.cpp:277-293): texel = floor(uv * size),
+// out of range reads 0.  Light / motion planes are float32 (the reference's attachments are RGBA16F / RG16F; as in row f2
+// the values are those before the attachment conversion).  glm's min / max / clamp are the ternaries of
+// func_common.inl (they differ from fminf / fmaxf on NaN, which a zero weight sum can produce here).
+// ---------------------------------------------------------------------------------------------
+}  // extern "C"
+namespace {
+inline float tmin(float a, float b) { return (b < a) ? b : a; }            // glm::min
+inline float tmax(float a, float b) { return (a < b) ? b : a; }            // glm::max
+inline float tclamp(float x, float lo, float hi) { return tmin(tmax(x, lo), hi); }
+inline int tex_index(int W, int H, float u, float v) {                     // nearest; -1 = outside
+    const int x = (int)floorf(u * (float)W), y = (int)floorf(v * (float)H);
+    if (x < 0 || y < 0 || x >= W || y >= H) return -1;
+    return y * W + x;
+}
+struct TaaTexel { V3 color, normal, light; V4 material; float depth, mx, my; };
+inline TaaTexel taa_fetch(const vxo_gbuffer& gb, const uint32_t* albedo, const float* motion, const float* light, float u, float v) {
+    TaaTexel t;
+    const int i = tex_index(gb.width, gb.height, u, v);
+    if (i < 0) { t.color = t.normal = t.light = v3(0, 0, 0); t.material = V4{0, 0, 0, 0}; t.depth = t.mx = t.my = 0.0f; return t; }
+    t.color = unorm8x3(albedo[i]);
+    t.normal = decode_normal(gb.normal[i]);
+    const uint32_t m = gb.material[i];
+    t.material = V4{unorm8(m), unorm8(m >> 8), unorm8(m >> 16), unorm8(m >> 24)};
+    t.depth = unorm24(gb.depth24[i]);
+    t.mx = motion[(size_t)i * 2]; t.my = motion[(size_t)i * 2 + 1];
+    t.light = v3(light[(size_t)i * 4], light[(size_t)i * 4 + 1], light[(size_t)i * 4 + 2]);
+    return t;
+}
+inline float length4(V4 a) { return sqrtf((a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w)); }   // glm compute_dot<vec4>
+inline float length2(float x, float y) { return sqrtf(x * x + y * y); }
+}  // namespace
+extern "C" {
+
+void vxo_light_taa(const vxo_view* view, const vxo_gbuffer* gb, const uint32_t* albedo_rgba8, const float* motion /* [H][W][2] */,
+                   const float* light /* [H][W][4] */, const float* last_light /* [H][W][4] */, vxo_rows rows, float* out_rgba) {
+    const int W = gb->width, H = gb->height;
+    if (rows.step < 1) rows.step = 1;
+    const int nrows = rows.end > rows.begin ? (rows.end - rows.begin + rows.step - 1) / rows.step : 0;
+    const float iRx = 1.0f / (float)W, iRy = 1.0f / (float)H;                                   // :38
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int ri = 0; ri < nrows; ++ri) {
+        const int py = rows.begin + ri * rows.step;
+        if (py < 0 || py >= H) continue;
+        for (int px = 0; px < W; ++px) {
+            const size_t idx = (size_t)py * W + px;
+            float* o = out_rgba + idx * 4;
+            const Pixel p = pixel_setup(*view, W, H, px, py);
+            const TaaTexel c = taa_fetch(*gb, albedo_rgba8, motion, light, p.u, p.v);           // :40-47
+            const float cla = light[idx * 4 + 3];
+            const float oldU = p.u + c.mx, oldV = p.v + c.my;                                   // :41
+            if (c.depth == 1.0f) { o[0] = c.light.x; o[1] = c.light.y; o[2] = c.light.z; o[3] = cla; continue; }   // :49-52
+            const int li = tex_index(W, H, oldU, oldV);                                         // :53
+            V3 lastLight = li < 0 ? v3(0, 0, 0) : v3(last_light[(size_t)li * 4], last_light[(size_t)li * 4 + 1], last_light[(size_t)li * 4 + 2]);
+            float lastVariance = li < 0 ? 0.0f : last_light[(size_t)li * 4 + 3];               // :54
+            if (tclamp(oldU, 0.0f, 1.0f) != oldU || tclamp(oldV, 0.0f, 1.0f) != oldV) {         // :57 out of bounds: current frame only
+                float count = 0.0f;
+                V3 neighColors = v3(0, 0, 0);
+                for (int x = -9; x <= 9; ++x)
+                    for (int y = -9; y <= 9; ++y) {
+                        const float ox = (float)x * iRx, oy = (float)y * iRy;                   // :62
+                        const float u = tclamp(p.u + ox, 0.001f, 0.999f), v = tclamp(p.v + oy, 0.001f, 0.999f);
+                        const TaaTexel n = taa_fetch(*gb, albedo_rgba8, motion, light, u, v);
+                        float factor = tmax(dot3(c.normal, n.normal), 0.0f);                    // :71
+                        factor *= gstep(0.8f, 1.0f - length4(V4{c.material.x - n.material.x, c.material.y - n.material.y, c.material.z - n.material.z, c.material.w - n.material.w}));
+                        factor *= 1.0f - tclamp(fabsf(c.depth - n.depth) * FAR_, 0.0f, 1.0f);   // :73
+                        factor *= 1.0f - tclamp(length3(c.color - n.color), 0.0f, 1.0f);        // :74
+                        if (length2(c.mx - n.mx, c.my - n.my) > 0.1f) factor = 0.0f;            // :76
+                        neighColors = neighColors + n.light * factor;                           // :79
+                        count += factor;
+                    }
+                o[0] = neighColors.x / count; o[1] = neighColors.y / count; o[2] = neighColors.z / count; o[3] = 1.0f;   // :83
+                continue;
+            }
+            V3 nmin = splat(10000.0f), nmax = splat(0.0f), neighColors = splat(0.0f);           // :89-91
+            float diffSum = 1.0f, count = 0.0f, radius = 1.0f;
+            const float size = 12.0f;
+            const uint32_t nz = get_noise(*gb, *view, p, -1);
+            V3 cur = c.light;
+            for (float angle = (unorm8(nz) * 3.1415f) * GOLDEN_RATIO; radius <= size; angle += 2.39f) {   // :96
+                radius += 1.0f;
+                const float cs = (float)cos((double)angle), sn = (float)sin((double)angle);     // correctly rounded (oracle definition)
+                const float k1 = radius * (lastVariance + 1.0f), k2 = tclamp(0.1f, 0.5f, 1.0f / c.depth);   // :99 (sic: clamp(x = 0.1, 0.5, 1/depth))
+                const float ox = ((cs * iRx) * k1) * k2, oy = ((sn * iRy) * k1) * k2;
+                const float u = tclamp(p.u + ox, 0.001f, 0.999f), v = tclamp(p.v + oy, 0.001f, 0.999f);
+                const TaaTexel n = taa_fetch(*gb, albedo_rgba8, motion, light, u, v);
+                float factor = 1.212f - radius / size;                                          // :108
+                factor *= gstep(0.8f, 1.0f - length4(V4{c.material.x - n.material.x, c.material.y - n.material.y, c.material.z - n.material.z, c.material.w - n.material.w}));
+                factor *= tmax(dot3(c.normal, n.normal), 0.0f);
+                factor *= 1.0f - tclamp(fabsf(c.depth - n.depth) * FAR_, 0.0f, 1.0f);
+                factor *= 1.0f - tclamp(length3(c.color - n.color) * 10000.0f, 0.0f, 1.0f);
+                if (length2(c.mx - n.mx, c.my - n.my) > 0.1f) factor = 0.0f;
+                nmin = v3(tmin(nmin.x, n.light.x), tmin(nmin.y, n.light.y), tmin(nmin.z, n.light.z));   // :116
+                nmax = v3(tmax(nmax.x, n.light.x), tmax(nmax.y, n.light.y), tmax(nmax.z, n.light.z));
+                neighColors = neighColors + n.light * factor;
+                count += factor;
+                diffSum += length3(n.light - c.light) * factor;                                 // :121
+            }
+            cur = cur + neighColors;                                                            // :123
+            cur = div3(cur, count + 1.0f);                                                      // :124
+            diffSum /= radius;                                                                  // :125
+            lastLight = v3(tclamp(lastLight.x, nmin.x, nmax.x), tclamp(lastLight.y, nmin.y, nmax.y), tclamp(lastLight.z, nmin.z, nmax.z));   // :129
+            const V3 ad = v3(fabsf(cur.x - lastLight.x), fabsf(cur.y - lastLight.y), fabsf(cur.z - lastLight.z));
+            float variance = dot3(ad, v3(0.2125f, 0.7154f, 0.0721f));                           // :132, :30-35
+            variance = tclamp(variance * 5.5f, 0.0f, 1.0f);
+            lastVariance += variance;
+            lastVariance -= diffSum * 0.08f;
+            lastVariance += length2(c.mx, c.my) * 20.0f;                                        // :136
+            const V3 m = mix3(cur, lastLight, tclamp(1.0f - lastVariance, 0.3f, 0.9f));         // :141
+            o[0] = m.x; o[1] = m.y; o[2] = m.z; o[3] = tclamp(lastVariance * 0.7f, 0.0f, 1.0f);
+        }
+    }
+}
+
+// LightReflection.frag:60-139: out_Color = vec4(ambient * F * (1 - roughness), F.x), ambient = the (TAA) light buffer where the
+// reflected ray's end point is the visible surface, the sky-box colour on a miss (`sky_rgb`: a uniform sky stands in for the
+// cube map, which is outside the path).  `t` is the plane of vxo_pass_reflection.  Tolerance parity (pow).
+void vxo_resolve_reflection(const vxo_view* view, const vxo_gbuffer* gb, const float* t_plane, const float* light /* [H][W][4] or NULL */,
+                            const float* sky_rgb, vxo_rows rows, float* out_rgba) {
+    const Luts& L = luts();
+    const int W = gb->width, H = gb->height;
+    if (rows.step < 1) rows.step = 1;
+    const int nrows = rows.end > rows.begin ? (rows.end - rows.begin + rows.step - 1) / rows.step : 0;
+    const V3 sky = v3(sky_rgb[0], sky_rgb[1], sky_rgb[2]);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int ri = 0; ri < nrows; ++ri) {
+        const int py = rows.begin + ri * rows.step;
+        if (py < 0 || py >= H) continue;
+        for (int px = 0; px < W; ++px) {
+            const size_t idx = (size_t)py * W + px;
+            float* o = out_rgba + idx * 4;
+            const Pixel p = pixel_setup(*view, W, H, px, py);
+            const uint32_t mt = gb->material[idx];
+            const float roughness = unorm8(mt), metallic = unorm8(mt >> 8);                     // :68-69
+            const float depth = unorm24(gb->depth24[idx]);
+            const V3 pos = p.farvec * (depth * (1.0f + 1.0f / FAR_));                           // :64
+            const V3 normal = decode_normal(gb->normal[idx]);
+            const V3 F0 = mix3(splat(0.04f), splat(1.0f), metallic);                            // :74-77
+            const V3 V = normalize3(pos) * -1.0f;                                               // :79
+            const V3 N = xyz(mat_mul(view->ViewMatrix, V4{normal.x, normal.y, normal.z, 0.0f}));
+            const V3 I = V * -1.0f;
+            const V3 R = I - N * dot3(N, I) * 2.0f;                                             // :81
+            V3 ambient = splat(0.0f);
+            const float cth = fmaxf(dot3(N, V), 0.0f);
+            const V3 F = (F0 + (max3(splat(1.0f - roughness), F0) - F0) * powf(fmaxf(1.0f - cth, 0.0f), 5.0f)) * 5.0f + splat(0.0f);   // :86
+            if (depth < 0.999f) {
+                V3 wd = normalize3(xyz(mat_mul(view->InverseViewMatrix, V4{R.x, R.y, R.z, 0.0f})));
+                V3 wcp = xyz(mat_mul(view->InverseViewMatrix, V4{pos.x, pos.y, pos.z, 1.0f})) * 10.0f;
+                const uint32_t n = get_noise(*gb, *view, p, -1);
+                V3 rv = cosine_sample_hemisphere(L, n, n >> 8);
+                rv.z *= gsign(unorm8(n >> 16) - 0.5f);
+                wd = mix3(wd, rv, roughness * 0.1f);
+                const float nw = unorm8(n >> 24);
+                wcp = wcp + normal * nw;
+                wd = wd * (1.0f + nw * 0.5f);
+                const float t = t_plane[idx];                                                   // :113
+                const V3 e = (wcp + wd * t) * 0.1f;
+                const V3 hp = xyz(mat_mul(view->ViewMatrix, V4{e.x, e.y, e.z, 1.0f}));           // :115
+                const V4 pp = mat_mul(view->ProjectionMatrix, V4{hp.x, hp.y, hp.z, 1.0f});       // :116
+                const float linearDepth = (pp.w - NEAR_) / (FAR_ - NEAR_);                      // :117
+                const float u = ((pp.x / pp.w) * 1.0f) * 0.5f + 0.5f, v = ((pp.y / pp.w) * -1.0f) * 0.5f + 0.5f;   // :118
+                const int ti = tex_index(W, H, u, v);
+                const float d2 = ti < 0 ? 0.0f : unorm24(gb->depth24[ti]);                      // :119
+                if (t == 256.0f) ambient = ambient + sky;                                       // :121-122
+                else if (linearDepth > d2 - 0.001f) {                                           // :124
+                    if (linearDepth < d2 + 0.001f && ti >= 0 && light)                          // :125-126
+                        ambient = ambient + v3(light[(size_t)ti * 4], light[(size_t)ti * 4 + 1], light[(size_t)ti * 4 + 2]);
+                }
+            }
+            const V3 c3 = (ambient * F) * (1.0f - roughness);                                   // :139
+            o[0] = c3.x; o[1] = c3.y; o[2] = c3.z; o[3] = F.x;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // the G-buffer producer's traversal of ONE model volume -- the reference's
 // hierarchical-mip DDA.  VoxAsset::Upload's mip rule (Sources/Asset/VoxAsset.cpp:3-64), clipToAABB
 // (Sources/Shaders/GeometryVoxel.frag:49-61) and intersectVolume (:64-125).  Ray-level entry: what one

@@ -127,6 +127,15 @@ void vxo_resolve_ambient(const vxo_view* view, const vxo_gbuffer* gb, const uint
 void vxo_resolve_local(const vxo_view* view, const vxo_gbuffer* gb, const uint32_t* albedo_rgba8, const float* lights,
                        int n_lights, int spot, const float* shadow /* [n][H][W] */, vxo_rows rows, float* inout_rgba);
 
+/* LightTAA.frag (temporal + spatial accumulation of the light buffer) and the colour LightReflection.frag
+ * writes around its march.  Full-frame row-major planes; light / motion planes are float32 (values before the RGBA16F / RG16F
+ * attachment conversion); nearest sampling, out of range reads 0.  vxo_light_taa is bit-exact arithmetic (cos / sin correctly
+ * rounded); vxo_resolve_reflection carries pow (tolerance parity). */
+void vxo_light_taa(const vxo_view* view, const vxo_gbuffer* gb, const uint32_t* albedo_rgba8, const float* motion /* [H][W][2] */,
+                   const float* light /* [H][W][4] */, const float* last_light /* [H][W][4] */, vxo_rows rows, float* out_rgba);
+void vxo_resolve_reflection(const vxo_view* view, const vxo_gbuffer* gb, const float* t_plane, const float* light /* [H][W][4] or NULL */,
+                            const float* sky_rgb /* [3] */, vxo_rows rows, float* out_rgba);
+
 /* VoxAsset's mip rule and the hierarchical-mip DDA of GeometryVoxel.frag on one model volume. */
 typedef struct vxo_model_ray { float cam[3], dir[3], uv[2]; } vxo_model_ray;
 typedef struct vxo_model_hit { int32_t hit; uint32_t material; int32_t fetches, steps; float pos[3], normal[3]; } vxo_model_hit;

@@ -151,13 +151,19 @@ def shader_trace(volume, rays, variant):
     return out
 
 
-def shader_pass(which, volume, view, gb, lights=None, light_index=0, rect=None, albedo=None):
+def shader_pass(which, volume, view, gb, lights=None, light_index=0, rect=None, albedo=None, light=None, sky=(0.0, 0.0, 0.0)):
     """Run the reference fragment shader `which` over the pixel rectangle (x0, y0, x1, y1); one SHADER_PIXREC per pixel.
-    albedo: COLOR_TEXTURE as (H, W) uint32 RGBA8 (default: unbound, reads 0)."""
+    albedo: COLOR_TEXTURE as (H, W) uint32 RGBA8 (default: unbound, reads 0).  light: LIGHT_TEXTURE of the reflection pass as
+    (H, W, 4) float32 (default: unbound).  sky: the sky box as a uniform colour."""
     L = shader_lib()
     alb = None if albedo is None else np.ascontiguousarray(albedo, np.uint32)
     L.vxshader_set_albedo.argtypes = [C.c_void_p]
     L.vxshader_set_albedo(None if alb is None else _p(alb))
+    lt = None if light is None else np.ascontiguousarray(light, np.float32)
+    L.vxshader_set_light.argtypes = [C.c_void_p]
+    L.vxshader_set_light(None if lt is None else _p(lt))
+    L.vxshader_set_sky.argtypes = [C.c_float] * 3
+    L.vxshader_set_sky(float(sky[0]), float(sky[1]), float(sky[2]))
     volume = np.ascontiguousarray(volume, np.uint8)
     sz, sy, sx = volume.shape
     h, w = gb["depth24"].shape
@@ -175,6 +181,24 @@ def shader_pass(which, volume, view, gb, lights=None, light_index=0, rect=None, 
     L.vxshader_pass(int(which), _p(vw), w, h, _p(keep[0]), _p(keep[1]), _p(keep[2]), _p(keep[3]), lp, int(light_index),
                     int(x0), int(y0), int(x1), int(y1), _p(out))
     L.vxshader_set_albedo(None)
+    L.vxshader_set_light(None)
+    L.vxshader_set_sky(0.0, 0.0, 0.0)
+    return out
+
+
+def shader_taa(view, gb, albedo, motion, light, last_light, rect=None):
+    """The reference's LightTAA.frag main() over the pixel rectangle -> out_Color, float32 (y1 - y0, x1 - x0, 4)."""
+    L = shader_lib()
+    h, w = gb["depth24"].shape
+    x0, y0, x1, y1 = rect if rect is not None else (0, 0, w, h)
+    keep = [np.ascontiguousarray(gb[k], np.uint32) for k in ("depth24", "normal", "material")] + [np.ascontiguousarray(albedo, np.uint32),
+            np.ascontiguousarray(gb["noise"], np.uint32)]
+    fl = [np.ascontiguousarray(a, np.float32) for a in (motion, light, last_light)]
+    assert fl[0].shape == (h, w, 2) and fl[1].shape == (h, w, 4) and fl[2].shape == (h, w, 4)
+    out = np.zeros((y1 - y0, x1 - x0, 4), np.float32)
+    vw = _view(view)
+    L.vxshader_taa.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 8 + [C.c_int] * 4 + [C.c_void_p]
+    L.vxshader_taa(_p(vw), w, h, *[_p(a) for a in keep], *[_p(a) for a in fl], int(x0), int(y0), int(x1), int(y1), _p(out))
     return out
 
 
@@ -363,6 +387,34 @@ def resolve_ambient(view, gb, albedo, shadow, ao, rows=None):
     out = np.zeros((h, w, 4), np.float32)
     g, vw = _gb(gb), _view(view)
     lib().vxo_resolve_ambient(_p(vw), C.byref(g), _p(alb), _p(sh), _p(a), _rows(rows, h), _p(out))
+    return out
+
+
+def light_taa(view, gb, albedo, motion, light, last_light, rows=None):
+    """LightTAA.frag's out_Color (float32 (H, W, 4)) from full-frame planes: motion (H, W, 2), light / last_light (H, W, 4)."""
+    h, w = gb["depth24"].shape
+    alb = np.ascontiguousarray(albedo, np.uint32)
+    mo, li, la = (np.ascontiguousarray(a, np.float32) for a in (motion, light, last_light))
+    assert mo.shape == (h, w, 2) and li.shape == (h, w, 4) and la.shape == (h, w, 4)
+    out = np.zeros((h, w, 4), np.float32)
+    g, vw = _gb(gb), _view(view)
+    f = lib().vxo_light_taa
+    f.argtypes = [C.c_void_p] * 6 + [_Rows, C.c_void_p]
+    f(_p(vw), C.byref(g), _p(alb), _p(mo), _p(li), _p(la), _rows(rows, h), _p(out))
+    return out
+
+
+def resolve_reflection(view, gb, t_plane, light=None, sky=(0.0, 0.0, 0.0), rows=None):
+    """LightReflection.frag's out_Color (float32 (H, W, 4)) from the march's t plane, the (TAA) light buffer and a uniform sky."""
+    h, w = gb["depth24"].shape
+    t = np.ascontiguousarray(t_plane, np.float32)
+    li = None if light is None else np.ascontiguousarray(light, np.float32)
+    sk = np.asarray(sky, np.float32)
+    out = np.zeros((h, w, 4), np.float32)
+    g, vw = _gb(gb), _view(view)
+    f = lib().vxo_resolve_reflection
+    f.argtypes = [C.c_void_p] * 5 + [_Rows, C.c_void_p]
+    f(_p(vw), C.byref(g), _p(t), None if li is None else _p(li), _p(sk), _rows(rows, h), _p(out))
     return out
 
 

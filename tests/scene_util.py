@@ -156,3 +156,33 @@ def model_scene(width=160, height=96, frame=2):
     pal_m = rs.randint(0, 2 ** 32, size=(2, 256), dtype=np.uint64).astype(np.uint32)
     view = S.make_view((7.5, 5.0, -4.0), 2.45, -0.45, width, height, frame)
     return models, cmds, pal_c, pal_m, view
+
+
+def f3_case(oracle, sc, seed=9):
+    """Inputs of LightTAA.frag / LightReflection.frag's colour for a scene: block-constant albedo and material
+    (so that the neighbour weights are a mix of zeros and non-zeros), a smooth motion field with a discontinuity and a band whose
+    history falls outside the frame, a current light buffer (the oracle's ambient colour plus noise), a perturbed history with
+    variance in alpha, and the reflection march's t plane."""
+    gb = dict(sc["gb"])
+    h, w = gb["depth24"].shape
+    rs = np.random.RandomState(seed)
+    by, bx = np.meshgrid(np.arange(h) // 6, np.arange(w) // 8, indexing="ij")
+    pal_a = rs.randint(0, 2 ** 32, size=64, dtype=np.uint64).astype(np.uint32)
+    pal_m = (rs.randint(0, 64, size=(64, 4)).astype(np.uint32) * np.array([1, 1 << 8, 1 << 16, 1 << 24], np.uint32)).sum(axis=1).astype(np.uint32)
+    blk = (by * 3 + bx) % 5
+    albedo = pal_a[blk]
+    gb["material"] = (pal_m[blk] + ((by % 2).astype(np.uint32) * np.uint32(40))).astype(np.uint32)     # rows of blocks differ by 40/255 in roughness (< 0.2)
+    yy, xx = np.meshgrid(np.arange(h, dtype=np.float32), np.arange(w, dtype=np.float32), indexing="ij")
+    motion = np.zeros((h, w, 2), np.float32)
+    motion[..., 0] = 0.004 * np.sin(xx * 0.2) + 0.002
+    motion[..., 1] = 0.003 * np.cos(yy * 0.3)
+    motion[h // 2:, w // 2:, 0] += np.float32(0.15)                  # discontinuity: neighbours across it are rejected (> 0.1)
+    motion[: h // 6, :, 1] -= np.float32(0.5)                        # history above the frame: the current-frame-only branch
+    sh, ao, _ = oracle.pass_ambient(sc["volume"], sc["view"], gb, 1)
+    light = oracle.resolve_ambient(sc["view"], gb, albedo, sh, ao)
+    light[..., :3] += rs.rand(h, w, 3).astype(np.float32) * np.float32(0.05)
+    light[..., 3] = rs.rand(h, w).astype(np.float32)
+    last = light * (np.float32(0.7) + np.float32(0.6) * rs.rand(h, w, 1).astype(np.float32))
+    last[..., 3] = rs.rand(h, w).astype(np.float32) * np.float32(1.2)
+    t, _ = oracle.pass_reflection(sc["volume"], sc["view"], gb)
+    return dict(gb=gb, albedo=albedo, motion=motion, light=light.astype(np.float32), last_light=last.astype(np.float32), t=t, sky=(0.3, 0.5, 0.9))

@@ -20,6 +20,7 @@ SYMBOLS = [
     "vxl_lighting_host", "vxl_volume_gen_terrain", "vxl_gbuffer_primary",
     "vxl_debug_set_variant", "vxl_debug_fetched_probes", "vxl_volume_debug_occupancy",
     "vxl_resolve_ambient", "vxl_resolve_point", "vxl_resolve_spot", "vxl_trace_model_rays", "vxl_gbuffer_models",
+    "vxl_light_taa", "vxl_resolve_reflection",
 ]
 
 VXL_MAX_LIGHTS = 64
@@ -49,6 +50,11 @@ class Resolve(C.Structure):
 class GBufferOut(C.Structure):
     """vxl_gbuffer_out"""
     _fields_ = [("depth24", C.c_void_p), ("normal", C.c_void_p), ("material", C.c_void_p), ("albedo", C.c_void_p), ("motion", C.c_void_p)]
+
+
+class FullPlanes(C.Structure):
+    """vxl_full_planes"""
+    _fields_ = [(k, C.c_void_p) for k in ("depth24", "normal", "material", "albedo", "motion", "light", "last_light")]
 
 
 class LightingHostArgs(C.Structure):
@@ -95,6 +101,8 @@ def load():
         "vxl_trace_rays": [vp, vp, vp, i64, i32, vp],
         "vxl_trace_model_rays": [vp, i32, vp, i64, i32, C.c_float, C.c_float, vp],
         "vxl_gbuffer_models": [vp, vp, P(Frame), vp, i32, vp, vp, P(GBufferOut)],
+        "vxl_light_taa": [vp, vp, P(Frame), P(FullPlanes), vp],
+        "vxl_resolve_reflection": [vp, vp, P(Frame), vp, vp, vp, vp, vp],
         "vxl_lighting_host": [vp, vp, P(LightingHostArgs)],
         "vxl_volume_gen_terrain": [vp], "vxl_gbuffer_primary": [vp, vp, vp, P(Frame)],
         "vxl_debug_set_variant": [vp, i32], "vxl_debug_fetched_probes": [vp, P(C.c_uint64)],

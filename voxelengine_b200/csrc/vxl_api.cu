@@ -104,7 +104,7 @@ int vxl_ctx_destroy(vxl_ctx* c) {
     if (!c) return VXL_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_stats); cudaFree(c->d_luts); cudaFree(c->d_lights); cudaFree(c->d_perm);
+    cudaFree(c->d_stats); cudaFree(c->d_luts); cudaFree(c->d_taa_lut); cudaFree(c->d_lights); cudaFree(c->d_perm);
     for (auto& m : c->models) { cudaFree((void*)m.voxels); cudaFree((void*)m.mip1); cudaFree((void*)m.mip2); }
     cudaFree(c->d_models); cudaFree(c->d_hkeys); cudaFree(c->d_hvals); cudaFree(c->d_ents); cudaFree(c->d_aabb);
     cudaFree(c->h_planes); cudaFree(c->h_out); cudaFree(c->h_noise);

@@ -52,6 +52,7 @@ struct vxl_ctx {
     int variant = 1;                         // 0: plain march on the volume bytes; 1: occupancy-bit tile in shared memory (default)
     unsigned long long* d_stats = nullptr;   // [STAT_SLOTS][4]
     float* d_luts = nullptr;                 // cos[256] sin[256]
+    float* d_taa_lut = nullptr;              // (cos, sin)[256][12] of LightTAA's spiral angles (vxl_post.cu), built on first use
     void* d_lights = nullptr;                // VXL_MAX_LIGHTS * 64 B
     uint8_t* d_perm = nullptr;               // perm[512] perm12[512] (terrain generator)
     std::vector<vxl::ModelDev> models;

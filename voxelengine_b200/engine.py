@@ -370,6 +370,67 @@ class LightReflectionPipeline:
         check(ctx.lib.vxl_pass_reflection(ctx.h, shadowVox.h, vp, C.byref(f), _dev_ptr(out_spec_t)), "vxl_pass_reflection")
         return out_spec_t
 
+    def Colour(self, viewBuffer, geometryFB: GeometryBuffer, spec_t, full, light_full, sky=(0.0, 0.0, 0.0), out=None):
+        """LightReflection.frag's out_Color (:60-139) from the march's t plane: the TAA light buffer (`light_full`, torch float32
+        (H, W, 4) or None) where the reflected ray ends on the visible surface, `sky` on a miss.  full: FullFrame (its depth)."""
+        torch = _torch()
+        ctx = geometryFB.ctx
+        if out is None:
+            out = torch.zeros(geometryFB.shape + (4,), dtype=torch.float32, device=ctx.torch_device)
+        v, vp = _view_ptr(viewBuffer)
+        f = geometryFB.frame()
+        sk = np.ascontiguousarray(sky, dtype=np.float32)
+        check(ctx.lib.vxl_resolve_reflection(ctx.h, vp, C.byref(f), _dev_ptr(spec_t), _dev_ptr(full.depth24) if full is not None else None,
+                                             _dev_ptr(light_full), _np_ptr(sk), _dev_ptr(out)), "vxl_resolve_reflection")
+        return out
+
+
+class FullFrame:
+    """Whole-frame row-major planes in HBM for the passes that sample other pixels (vxl_full_planes): the G-buffer attachments
+    (depth, normal, material, colour, motion).  On several GPUs this is the all-gathered frame."""
+
+    def __init__(self, ctx: Context, depth24, normal, material, albedo, motion):
+        torch = _torch()
+        self.ctx = ctx
+        dev = ctx.torch_device
+
+        def u32(a):
+            return a if hasattr(a, "data_ptr") else torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint32).view(np.int32)).to(dev)
+
+        def f32(a):
+            return a if hasattr(a, "data_ptr") else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+        self.depth24, self.normal, self.material, self.albedo = u32(depth24), u32(normal), u32(material), u32(albedo)
+        self.motion = f32(motion)
+        self.height, self.width = self.depth24.shape[-2:]
+        assert tuple(self.motion.shape[-3:]) == (self.height, self.width, 2)
+
+
+class LightTAAPipeline:
+    """Temporal + spatial accumulation of the light buffer (Sources/Graphics/Pipelines/LightTAAPipeline.h:34-53, LightTAA.frag;
+    SURVEY 8f row f3).  Use() keeps the reference's argument order minus the command buffer: view, (blue noise: the frame's),
+    last TAA light buffer, current light buffer, G-buffer."""
+    _inst = None
+
+    @classmethod
+    def Get(cls):
+        cls._inst = cls._inst or cls()
+        return cls._inst
+
+    def Use(self, viewBuffer, geometryFB: GeometryBuffer, full: FullFrame, light_full, last_light_full, out=None):
+        """light_full / last_light_full: torch float32 (H, W, 4) whole-frame planes.  Returns the shard's TAA light (tile-compact)."""
+        torch = _torch()
+        ctx = geometryFB.ctx
+        assert tuple(light_full.shape) == (full.height, full.width, 4) and tuple(last_light_full.shape) == (full.height, full.width, 4)
+        assert (full.width, full.height) == (geometryFB.width, geometryFB.height)
+        if out is None:
+            out = torch.zeros(geometryFB.shape + (4,), dtype=torch.float32, device=ctx.torch_device)
+        v, vp = _view_ptr(viewBuffer)
+        f = geometryFB.frame()
+        fp = capi.FullPlanes(full.depth24.data_ptr(), full.normal.data_ptr(), full.material.data_ptr(), full.albedo.data_ptr(),
+                             full.motion.data_ptr(), light_full.data_ptr(), last_light_full.data_ptr())
+        check(ctx.lib.vxl_light_taa(ctx.h, vp, C.byref(f), C.byref(fp), _dev_ptr(out)), "vxl_light_taa")
+        return out
+
 
 def trace_model_rays(ctx: Context, model_id: int, rays: np.ndarray, frame: int = 0, res=(1920.0, 1080.0)) -> np.ndarray:
     """GeometryVoxel.frag's clipToAABB + intersectVolume on a registered model (core): host rays
