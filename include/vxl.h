@@ -274,6 +274,42 @@ typedef struct vxl_gbuffer_out { uint32_t* depth24; uint32_t* normal; uint32_t* 
 int vxl_gbuffer_models(vxl_ctx* ctx, const vxl_view* view, const vxl_frame* frame /* geometry only: sizes and tiles */, const vxl_vox_cmd* cmds,
                        int n_cmds, const uint32_t* pal_color, const uint32_t* pal_material, const vxl_gbuffer_out* out);
 
+/* ---- on-disk formats --------------------------------------------------------- */
+/* The files the reference's scenes are made of, read by host code (vxl_assets.cu); all paths are file-system paths, all buffers HOST.
+ *   vxl_asset_guid         Assets::Hash (Sources/Asset/Assets.h:207-210): FNV-1a 64 of the asset path relative to Mods/
+ *                          ("default/ModernHouse/0.v" -> 0x44B7A418296B6797, the GUID the shipped ModernHouse.pf stores)
+ *   vxl_vox_file_read      VoxAsset::Serialize (Sources/Asset/VoxAsset.h:42-50): int32 dims[3] + dims[0]*dims[1]*dims[2] palette indices,
+ *                          x fastest; out == NULL only fills dims
+ *   vxl_model_load_v       the same, registered as a model (vxl_model_create)
+ *   vxl_pallete_file_read  PalleteAsset::Serialize (Sources/Asset/PalleteAsset.h:63-69) + PalleteCache::UploadPallete
+ *                          (Sources/Vox/PalleteCache.cpp:5-25): the 256 colour texels (r, g, b, 255) and material texels (roughness,
+ *                          metallic, emit, 0) of one palette row, the layout vxl_gbuffer_models reads
+ *   vxl_prefab_file_read   PrefabAsset::Spawn (Sources/Asset/PrefabAsset.cpp:30-141) + TransformSystem::RealculateMatrix
+ *                          (Sources/World/Systems/TransformSystem.cpp:124-135): the entities of a .pf scene in file order with their local
+ *                          and world matrices (T * Rz * Ry * Rx * S, glm arithmetic); cap == 0 only counts.  Nested prefab instances: error.
+ *   vxl_scene_load         the same for `prefab_path` relative to a Mods directory, with nested instances expanded in place (the nested
+ *                          root takes the instancing entity's Id, Name, Parent and components, PrefabAsset.cpp:47-56,87-139); GUIDs
+ *                          resolve to the files under `mods_dir` by hashing their relative paths, like ModLoader */
+enum { VXL_PF_TRANSFORM = 1, VXL_PF_VOX = 2, VXL_PF_LIGHT = 4, VXL_PF_INSTANCE = 8 };
+typedef struct vxl_prefab_entity {
+    int32_t  id, parent;             /* "Id"; parent = index into the returned array, -1 for a root */
+    uint32_t has;                    /* VXL_PF_* */
+    int32_t  light_type;             /* Light::Type: 0 point, 1 spot, 2 directional, 3 ambient (World/Components.h:39-44) */
+    float    position[3], rotation[3], scale[3];
+    float    pivot[3];
+    float    matrix[16], world[16];  /* Transform::Matrix, Transform::WorldMatrix (column-major) */
+    uint64_t vox_guid, pallete_guid;
+    uint64_t instance_guid;          /* VXL_PF_INSTANCE: this entity is the root of that nested prefab (Components: Instance) */
+    float    intensity, color[3], attenuation, range, angle, angle_attenuation;
+    char     name[64];
+} vxl_prefab_entity;
+int vxl_asset_guid(const char* path, uint64_t* out);
+int vxl_vox_file_read(const char* path, int32_t dims[3], uint8_t* out, uint64_t cap);
+int vxl_model_load_v(vxl_ctx* ctx, const char* path, int* out_model_id);
+int vxl_pallete_file_read(const char* path, uint32_t* color256, uint32_t* material256);
+int vxl_prefab_file_read(const char* path, vxl_prefab_entity* out, int cap, int* n_out);
+int vxl_scene_load(const char* mods_dir, const char* prefab_path, vxl_prefab_entity* out, int cap, int* n_out);
+
 /* rays/out are DEVICE pointers */
 int vxl_trace_rays(vxl_ctx* ctx, vxl_volume* vol, const vxl_ray* rays, int64_t n, int variant, vxl_hit* out);
 

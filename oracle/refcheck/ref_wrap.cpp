@@ -49,6 +49,19 @@ void ref_camera(const float* pos, float yaw, float pitch, float* out) {
     M = glm::rotate(M, pitch, glm::vec3(1, 0, 0));
     memcpy(out, &M, 64);
 }
+// TransformSystem::RealculateMatrix (Sources/World/Systems/TransformSystem.cpp:124-135) with glm itself: matrix = T * Rz * Ry * Rx * S,
+// world = parent * matrix
+void ref_transform(const float* pos, const float* rot, const float* scl, const float* parent, float* matrix, float* world) {
+    glm::mat4 M = glm::identity<glm::mat4>();
+    M = glm::translate(M, glm::vec3(pos[0], pos[1], pos[2]));
+    M = glm::rotate(M, rot[2], glm::vec3(0, 0, 1));
+    M = glm::rotate(M, rot[1], glm::vec3(0, 1, 0));
+    M = glm::rotate(M, rot[0], glm::vec3(1, 0, 0));
+    M = glm::scale(M, glm::vec3(scl[0], scl[1], scl[2]));
+    glm::mat4 P; memcpy(&P, parent, 64);
+    glm::mat4 W = P * M;
+    memcpy(matrix, &M, 64); memcpy(world, &W, 64);
+}
 float ref_terrain_noise(float x, float y, float z) {
     TerrainNoiseInfo info;
     info.Bias2D = 0; info.Scale2D = 1; info.Frequency2D = 1; info.Octaves2D = 4;

@@ -238,8 +238,9 @@ def test_voxelize_matches_sequential_reference(gpu_ctx, oracle):
     vol = E.ShadowVoxSystem(gpu_ctx, dims)
     vol.upload(base)
     ids = [vol.add_model(m) for m in models]
-    assert ids == [0, 1, 2]
-    reg, valid = vol.OnUpdate(e)
+    ge = e.copy()                                          # model ids are per context (other tests registered theirs first)
+    ge["model"] = np.asarray(ids, np.int32)[e["model"]]
+    reg, valid = vol.OnUpdate(ge)
     got = vol.download()
     assert np.array_equal(got, want), f"{(got != want).sum()} bytes differ"
     assert np.array_equal(valid, wvalid)

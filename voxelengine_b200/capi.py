@@ -21,6 +21,7 @@ SYMBOLS = [
     "vxl_debug_set_variant", "vxl_debug_fetched_probes", "vxl_volume_debug_occupancy",
     "vxl_resolve_ambient", "vxl_resolve_point", "vxl_resolve_spot", "vxl_trace_model_rays", "vxl_gbuffer_models",
     "vxl_light_taa", "vxl_resolve_reflection",
+    "vxl_asset_guid", "vxl_vox_file_read", "vxl_model_load_v", "vxl_pallete_file_read", "vxl_prefab_file_read", "vxl_scene_load",
 ]
 
 VXL_MAX_LIGHTS = 64
@@ -102,6 +103,9 @@ def load():
         "vxl_trace_model_rays": [vp, i32, vp, i64, i32, C.c_float, C.c_float, vp],
         "vxl_gbuffer_models": [vp, vp, P(Frame), vp, i32, vp, vp, P(GBufferOut)],
         "vxl_light_taa": [vp, vp, P(Frame), P(FullPlanes), vp],
+        "vxl_asset_guid": [C.c_char_p, P(C.c_uint64)], "vxl_vox_file_read": [C.c_char_p, vp, vp, C.c_uint64],
+        "vxl_model_load_v": [vp, C.c_char_p, P(C.c_int)], "vxl_pallete_file_read": [C.c_char_p, vp, vp],
+        "vxl_prefab_file_read": [C.c_char_p, vp, i32, P(C.c_int)], "vxl_scene_load": [C.c_char_p, C.c_char_p, vp, i32, P(C.c_int)],
         "vxl_resolve_reflection": [vp, vp, P(Frame), vp, vp, vp, vp, vp],
         "vxl_lighting_host": [vp, vp, P(LightingHostArgs)],
         "vxl_volume_gen_terrain": [vp], "vxl_gbuffer_primary": [vp, vp, vp, P(Frame)],

@@ -398,31 +398,17 @@ VXL_DI ScanPre scan_precheck(const BitTile& T, float3 origin, float3 bound, floa
     return P;
 }
 
-template <bool RECORD, bool COUNT, bool NEAR, int SHIFT, int TY, int TW, int N2>
-VXL_DI float march_scan_super(const VolView& V, const BitTile& T, float3 origin, float3 dir, float dist, int& steps_out,
-                              MarchResult* rec, unsigned& fetched, ScanPre pre = ScanPre{false, false, 0.0f}) {
+// The scan of march_scan_super on its own: candidate word of an eligible ray (probe k in bit k).
+template <bool NEAR, int SHIFT, int TY, int TW, int N2>
+VXL_DI unsigned scan_super_cand(const BitTile& T, float3 origin, float3 dir, bool near_ok) {
     constexpr int N1 = 6, N = N1 + N2, KN = 8;
     static_assert(N <= 32 && KN <= N, "candidate mask is one word");
-    const float lim = fminf(dist, 164.0f);
-    float hi_max = pre.hi_max;
-    if (!pre.ok && (!T.direct || !tile_eligible<SHIFT, TY, TW>(T, origin, dir, fmaxf(lim, 16.0f) + 1.0f, hi_max)))
-        return march<RECORD>(V, origin, dir, dist, 2.5f, steps_out, rec);
-
     typedef TileAddr<SHIFT, TY, TW> TA;
     const TA A(T);
     const float3 s1 = dir * 2.5f;
     const float3 s2 = s1 * 2.0f;
-    // ---- scan: probe k ends up in bit k ----
     unsigned cand = 0u;
     float3 pos = origin;
-    bool near_ok = pre.near_ok;
-    if (NEAR && !pre.ok) {
-        const float3 e = fma3(s1, (float)(2 * (KN - 1) - N1), origin);       // probe KN - 1, up to rounding (<< margin)
-        const float lx = (float)T.nx * 2.0f + BM_MARGIN, ly = (float)T.ny * 2.0f + BM_MARGIN, lz = (float)T.nz * 2.0f + BM_MARGIN;
-        const float w = (float)(2 * NEAR_T) - 2.0f * BM_MARGIN;
-        near_ok = T.wn != nullptr && fminf(origin.x, e.x) >= lx && fmaxf(origin.x, e.x) <= lx + w && fminf(origin.y, e.y) >= ly &&
-                  fmaxf(origin.y, e.y) <= ly + w && fminf(origin.z, e.z) >= lz && fmaxf(origin.z, e.z) <= lz + w;
-    }
     if (NEAR && near_ok) {
         const NearAddr B(T);
 #pragma unroll
@@ -442,7 +428,72 @@ VXL_DI float march_scan_super(const VolView& V, const BitTile& T, float3 origin,
         cand = funnel_r(cand, A.bit(pos), 1u);
         if (k + 1 < N) pos = pos + s2;
     }
-    cand >>= (32 - N);
+    return cand >> (32 - N);
+}
+
+// The reference's own test of candidate probe k (see above): true = the march returns at this probe.
+// PHASE: 0 = k decides; 1 / 2 = the caller knows k < 6 / k >= 6 (only that test is compiled in).
+template <bool COUNT, bool NEAR, int SHIFT, int TY, int TW, int N2, int PHASE = 0>
+VXL_DI bool resolve_super_cand(const VolView& V, const BitTile& T, float3 origin, float3 s1, int k, bool near_ok, float eps, unsigned& fetched, unsigned& hbit) {
+    constexpr int N1 = 6, KN = 8;
+    typedef TileAddr<SHIFT, TY, TW> TA;
+    if (PHASE == 1 || (PHASE == 0 && k < N1)) {
+        if (COUNT) ++fetched;
+        float3 p = origin;
+#pragma unroll
+        for (int i = 0; i < N1 - 1; ++i)
+            if (i < k) p = p + s1;
+        const unsigned v = V.bytes[TA::texel_offset(V, T.koff, p)];
+        if (v != 0u) {
+            unsigned bit = 0u;
+            bit += gmod(p.x, 0.5f) > 0.25f ? 1u : 0u;
+            bit += gmod(p.y, 0.5f) > 0.25f ? 2u : 0u;
+            bit += gmod(p.z, 0.5f) > 0.25f ? 4u : 0u;
+            if ((v >> bit) & 1u) { hbit = bit; return true; }
+        }
+        return false;
+    }
+    if (NEAR && near_ok && k < KN) return true;                           // texel bit set = byte != 0 = the reference's test
+    if (COUNT) ++fetched;
+    const float3 s2 = s1 * 2.0f;
+    const float3 q = fma3(s1, (float)(2 * k - N1), origin);
+    const float M1 = 16777216.0f;
+    const unsigned ax = magic_floor_bits(q.x - eps, M1, 1, 0), bx = magic_floor_bits(q.x + eps, M1, 1, 0);
+    const unsigned ay = magic_floor_bits(q.y - eps, M1, 1, 0), by = magic_floor_bits(q.y + eps, M1, 1, 0);
+    const unsigned az = magic_floor_bits(q.z - eps, M1, 1, 0), bz = magic_floor_bits(q.z + eps, M1, 1, 0);
+    unsigned off = bz * (unsigned)(V.sx * V.sy) + by * (unsigned)V.sx + bx - T.koff;
+    if ((ax ^ bx) | (ay ^ by) | (az ^ bz)) {                             // within eps of a texel face: exact position
+        float3 p = origin;
+        for (int i = 0; i < N1; ++i) p = p + s1;
+        for (int i = N1; i < k; ++i) p = p + s2;
+        off = TA::texel_offset(V, T.koff, p);
+    }
+    return V.bytes[off] != 0u;
+}
+
+VXL_DI float super_hit_distance(int hit) { return hit < 6 ? 2.5f * (float)(hit + 1) : 17.5f + 5.0f * (float)(hit - 6); }
+
+template <bool RECORD, bool COUNT, bool NEAR, int SHIFT, int TY, int TW, int N2>
+VXL_DI float march_scan_super(const VolView& V, const BitTile& T, float3 origin, float3 dir, float dist, int& steps_out,
+                              MarchResult* rec, unsigned& fetched, ScanPre pre = ScanPre{false, false, 0.0f}) {
+    constexpr int N1 = 6, N = N1 + N2, KN = 8;
+    const float lim = fminf(dist, 164.0f);
+    float hi_max = pre.hi_max;
+    if (!pre.ok && (!T.direct || !tile_eligible<SHIFT, TY, TW>(T, origin, dir, fmaxf(lim, 16.0f) + 1.0f, hi_max)))
+        return march<RECORD>(V, origin, dir, dist, 2.5f, steps_out, rec);
+
+    const float3 s1 = dir * 2.5f;
+    const float3 s2 = s1 * 2.0f;
+    bool near_ok = pre.near_ok;
+    if (NEAR && !pre.ok) {
+        const float3 e = fma3(s1, (float)(2 * (KN - 1) - N1), origin);       // probe KN - 1, up to rounding (<< margin)
+        const float lx = (float)T.nx * 2.0f + BM_MARGIN, ly = (float)T.ny * 2.0f + BM_MARGIN, lz = (float)T.nz * 2.0f + BM_MARGIN;
+        const float w = (float)(2 * NEAR_T) - 2.0f * BM_MARGIN;
+        near_ok = T.wn != nullptr && fminf(origin.x, e.x) >= lx && fmaxf(origin.x, e.x) <= lx + w && fminf(origin.y, e.y) >= ly &&
+                  fmaxf(origin.y, e.y) <= ly + w && fminf(origin.z, e.z) >= lz && fmaxf(origin.z, e.z) <= lz + w;
+    }
+    // ---- scan: probe k ends up in bit k ----
+    unsigned cand = scan_super_cand<NEAR, SHIFT, TY, TW, N2>(T, origin, dir, near_ok);
     // ---- resolve ----
     const float eps = (hi_max + 1.0f) * (1.0f / 262144.0f);
     int hit = -1;
@@ -454,43 +505,11 @@ VXL_DI float march_scan_super(const VolView& V, const BitTile& T, float3 origin,
         const int k = __builtin_ctz(cand);
 #endif
         cand &= cand - 1u;
-        if (k < N1) {
-            if (COUNT) ++fetched;
-            float3 p = origin;
-#pragma unroll
-            for (int i = 0; i < N1 - 1; ++i)
-                if (i < k) p = p + s1;
-            const unsigned v = V.bytes[TA::texel_offset(V, T.koff, p)];
-            if (v != 0u) {
-                unsigned bit = 0u;
-                bit += gmod(p.x, 0.5f) > 0.25f ? 1u : 0u;
-                bit += gmod(p.y, 0.5f) > 0.25f ? 2u : 0u;
-                bit += gmod(p.z, 0.5f) > 0.25f ? 4u : 0u;
-                if ((v >> bit) & 1u) { hit = k; hbit = bit; break; }
-            }
-        } else if (NEAR && near_ok && k < KN) {
-            hit = k;                                                      // texel bit set = byte != 0 = the reference's test
-            break;
-        } else {
-            if (COUNT) ++fetched;
-            const float3 q = fma3(s1, (float)(2 * k - N1), origin);
-            const float M1 = 16777216.0f;
-            const unsigned ax = magic_floor_bits(q.x - eps, M1, 1, 0), bx = magic_floor_bits(q.x + eps, M1, 1, 0);
-            const unsigned ay = magic_floor_bits(q.y - eps, M1, 1, 0), by = magic_floor_bits(q.y + eps, M1, 1, 0);
-            const unsigned az = magic_floor_bits(q.z - eps, M1, 1, 0), bz = magic_floor_bits(q.z + eps, M1, 1, 0);
-            unsigned off = bz * (unsigned)(V.sx * V.sy) + by * (unsigned)V.sx + bx - T.koff;
-            if ((ax ^ bx) | (ay ^ by) | (az ^ bz)) {                     // within eps of a texel face: exact position
-                float3 p = origin;
-                for (int i = 0; i < N1; ++i) p = p + s1;
-                for (int i = N1; i < k; ++i) p = p + s2;
-                off = TA::texel_offset(V, T.koff, p);
-            }
-            if (V.bytes[off] != 0u) { hit = k; break; }
-        }
+        if (resolve_super_cand<COUNT, NEAR, SHIFT, TY, TW, N2>(V, T, origin, s1, k, near_ok, eps, fetched, hbit)) { hit = k; break; }
     }
     const bool h = hit >= 0;
     const int nsteps = h ? hit + 1 : N;
-    const float d = !h ? dist : (hit < N1 ? 2.5f * (float)(hit + 1) : 17.5f + 5.0f * (float)(hit - N1));
+    const float d = !h ? dist : super_hit_distance(hit);
     steps_out += nsteps;
     if (RECORD) {
         float3 p = origin;

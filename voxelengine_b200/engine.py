@@ -533,3 +533,52 @@ def lighting_host(ctx: Context, shadowVox: ShadowVoxSystem, view, frame_desc: di
                               hp(outs.get("shadow")), hp(outs.get("ao")), hp(outs.get("point_shadow")),
                               hp(outs.get("spot_shadow")), hp(outs.get("spec_t")))
     check(ctx.lib.vxl_lighting_host(ctx.h, shadowVox.h, C.byref(a)), "vxl_lighting_host")
+
+
+# ---- on-disk formats: thin wrappers over the host-side readers of libvxl.so ---------------------------------
+def asset_guid(path: str) -> int:
+    """Assets::Hash (Sources/Asset/Assets.h:207-210): the GUID of an asset path relative to Mods/."""
+    lib = capi.load()
+    out = C.c_uint64()
+    check(lib.vxl_asset_guid(path.encode(), C.byref(out)), "vxl_asset_guid")
+    return int(out.value)
+
+
+def read_vox_file(path: str) -> np.ndarray:
+    """A .v volume (VoxAsset::Serialize) -> uint8 (sz, sy, sx) palette indices."""
+    lib = capi.load()
+    dims = np.zeros(3, np.int32)
+    check(lib.vxl_vox_file_read(path.encode(), _np_ptr(dims), None, 0), "vxl_vox_file_read")
+    out = np.zeros((int(dims[2]), int(dims[1]), int(dims[0])), np.uint8)
+    check(lib.vxl_vox_file_read(path.encode(), _np_ptr(dims), _np_ptr(out), out.size), "vxl_vox_file_read")
+    return out
+
+
+def read_pallete_file(path: str):
+    """A .p palette (PalleteAsset::Serialize) -> (colour[256], material[256]) uint32 texels of one palette row."""
+    lib = capi.load()
+    color, material = np.zeros(256, np.uint32), np.zeros(256, np.uint32)
+    check(lib.vxl_pallete_file_read(path.encode(), _np_ptr(color), _np_ptr(material)), "vxl_pallete_file_read")
+    return color, material
+
+
+def read_prefab_file(path: str) -> np.ndarray:
+    """A .pf scene (PrefabAsset::Spawn + TransformSystem) -> array of scenes.PREFAB_ENTITY_DTYPE in file order."""
+    from .scenes import PREFAB_ENTITY_DTYPE
+    lib = capi.load()
+    n = C.c_int()
+    check(lib.vxl_prefab_file_read(path.encode(), None, 0, C.byref(n)), "vxl_prefab_file_read")
+    out = np.zeros(n.value, PREFAB_ENTITY_DTYPE)
+    check(lib.vxl_prefab_file_read(path.encode(), _np_ptr(out), n.value, C.byref(n)), "vxl_prefab_file_read")
+    return out
+
+
+def load_scene(mods_dir: str, prefab_path: str) -> np.ndarray:
+    """vxl_scene_load: a .pf scene relative to a Mods directory with nested prefab instances expanded."""
+    from .scenes import PREFAB_ENTITY_DTYPE
+    lib = capi.load()
+    n = C.c_int()
+    check(lib.vxl_scene_load(mods_dir.encode(), prefab_path.encode(), None, 0, C.byref(n)), "vxl_scene_load")
+    out = np.zeros(n.value, PREFAB_ENTITY_DTYPE)
+    check(lib.vxl_scene_load(mods_dir.encode(), prefab_path.encode(), _np_ptr(out), n.value, C.byref(n)), "vxl_scene_load")
+    return out

@@ -137,6 +137,14 @@ VOX_CMD_DTYPE = np.dtype([("WorldMatrix", "<f4", (16,)), ("LastWorldMatrix", "<f
                           ("model", "<i4"), ("_pad", "<i4")])                                                           # vxl_vox_cmd
 
 
+PREFAB_ENTITY_DTYPE = np.dtype([("id", "<i4"), ("parent", "<i4"), ("has", "<u4"), ("light_type", "<i4"), ("position", "<f4", (3,)),
+                                ("rotation", "<f4", (3,)), ("scale", "<f4", (3,)), ("pivot", "<f4", (3,)), ("matrix", "<f4", (16,)),
+                                ("world", "<f4", (16,)), ("vox_guid", "<u8"), ("pallete_guid", "<u8"), ("instance_guid", "<u8"), ("intensity", "<f4"),
+                                ("color", "<f4", (3,)), ("attenuation", "<f4"), ("range", "<f4"), ("angle", "<f4"),
+                                ("angle_attenuation", "<f4"), ("name", "S64")])                                          # vxl_prefab_entity
+PF_TRANSFORM, PF_VOX, PF_LIGHT, PF_INSTANCE = 1, 2, 4, 8
+
+
 def point_lights(positions, ranges, color=(2.0, 2.0, 2.0), attenuation=2.0):
     n = len(positions)
     a = np.zeros(n, dtype=POINT_LIGHT_DTYPE)
