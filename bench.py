@@ -328,6 +328,53 @@ def run_ours(args):
                    "frac_of_hbm_peak": rbytes / (tt / args.steps * 1e-3) / 1e9 / peak,
                    "kernels": "k_resolve_ambient" + (" + k_resolve_local<point>" if wl.n_point else "")}
 
+    # ---- the rows either side of the path, timed beside the march, not part of `value` ----
+    def timed(fn):
+        fn(); torch.cuda.synchronize()
+        tt = 0.0
+        for _ in range(args.steps):
+            flush()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            tt += a.elapsed_time(b)
+        return tt / args.steps
+
+    post = geom = None
+    if world == 1 and resolve is not None:
+        npx = int(np.prod(wl.gb.shape))
+        g = torch.Generator(device=dev); g.manual_seed(7)
+        motion = (torch.rand((H, W, 2), device=dev, generator=g) - 0.5) * 0.004
+        full = E.FullFrame(wl.ctx, wl.gb.depth24[0], wl.gb.normal[0], wl.gb.material[0], alb[0], motion)
+        light = lb.rgba[0].clone()
+        last = light * 0.9
+        last[..., 3] = torch.rand((H, W), device=dev, generator=g)
+        taa_out = torch.zeros_like(lb.rgba)
+        refl_out = torch.zeros_like(lb.rgba)
+        t_taa = timed(lambda: E.LightTAAPipeline.Get().Use(wl.view, wl.gb, full, light, last, out=taa_out))
+        # per pixel: centre texel of 6 planes (40 B) + history (16 B) + 12 taps x 40 B + rgba out (16 B); the taps fall within
+        # +-13 pixels, so the compulsory HBM traffic is one pass over the planes (40 + 16 + 16 B)
+        taa_alg, taa_min = npx * (40 + 16 + 12 * 40 + 16), npx * (40 + 16 + 16)
+        post = {"taa_ms": t_taa, "taa_algorithmic_GB/s": taa_alg / (t_taa * 1e-3) / 1e9, "taa_compulsory_GB/s": taa_min / (t_taa * 1e-3) / 1e9,
+                "taa_compulsory_frac_of_hbm_peak": taa_min / (t_taa * 1e-3) / 1e9 / peak, "kernels": "k_light_taa"}
+        if wl.spec:
+            t_rf = timed(lambda: E.LightReflectionPipeline.Get().Colour(wl.view, wl.gb, pl["spec_t"], full, taa_out[0], (0.3, 0.5, 0.9), out=refl_out))
+            rf_bytes = npx * (12 + 4 + 4 + 16 + 16)                 # depth / normal / material + t + end-point depth + light + rgba out
+            post.update({"reflection_colour_ms": t_rf, "reflection_colour_GB/s": rf_bytes / (t_rf * 1e-3) / 1e9,
+                         "reflection_colour_frac_of_hbm_peak": rf_bytes / (t_rf * 1e-3) / 1e9 / peak, "kernels": "k_light_taa + k_resolve_reflection"})
+        if wl.props is not None:
+            from voxelengine_b200 import scenes as S
+            cmds = np.zeros(len(wl.props), S.VOX_CMD_DTYPE)
+            cmds["WorldMatrix"] = wl.props["cur"]; cmds["LastWorldMatrix"] = wl.props["cur"]
+            cmds["VolumeRID"] = 3 + np.arange(len(cmds)); cmds["model"] = wl.props["model"]
+            pal = torch.randint(0, 2 ** 31 - 1, (1, 256), dtype=torch.int32, device=dev)
+            gfb = E.GeometryBuffer(wl.ctx, W, H)
+            galb = torch.zeros(gfb.shape, dtype=torch.int32, device=dev)
+            t_g = timed(lambda: E.GeometryVoxelPipeline.Get().Use(wl.view, gfb, cmds, pal, pal, albedo=galb))
+            covered = int((gfb.depth24 != 0xFFFFFF).sum().item())
+            geom = {"ms": t_g, "draws": int(len(cmds)), "covered_pixels": covered, "Mpixels/s": npx / (t_g * 1e-3) / 1e6,
+                    "kernels": "k_gbuffer_models", "note": "the config's instanced models only (the terrain is not a model)"}
+
     # ---- end to end: host buffers in, host buffers out, every step ----
     e2e = None if args.no_e2e else run_e2e(args, wl, torch, dist, world, rank, rays)
 
@@ -355,7 +402,7 @@ def run_ours(args):
                        "l2": "flushed between timed steps (256 MiB fill outside the event pairs); per-step working set 128 MiB volume + 100 MB G-buffer + 232 MB outputs",
                        "ms_per_step_warm_l2": ms_warm, "ms_per_step_plain_march_variant0": ms_plain,
                        "probes_that_read_the_volume": int(fetched_probes)},
-            "roofline": roofline, "light_buffer_resolve": resolve, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(),
+            "roofline": roofline, "light_buffer_resolve": resolve, "post_passes": post, "geometry_pass": geom, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(),
         }))
     wl.close()
     if world > 1:

@@ -122,6 +122,7 @@ struct DrawDev {                     // per draw, derived on the host like Geome
     int rid, palette;
     ModelMips M;
 };
+constexpr int GEOM_MAX_DRAWS = 4096;   // GeometryVoxelPipeline MAX_INSTANCES
 struct GeomK { float InvView[16], InvProj[16], PV[16], PVlast[16]; float cam[3], jit[2], ires[2], res[2]; int frame; };
 
 __device__ __forceinline__ uint32_t pack_unorm8x4(float a, float b, float c, float d) {
@@ -147,8 +148,36 @@ __global__ void __launch_bounds__(256) k_gbuffer_models(FrameView F, GeomK K, co
     const int gt = F.tile_first + lt * F.tile_stride;
     const int tyy = gt / F.tiles_x, txx = gt - tyy * F.tiles_x;
     const int px = txx * F.tile_w + lx, py = tyy * F.tile_h + ly;
-    if (!(lx < F.tile_w && ly < F.tile_h && px < F.width && py < F.height && lt < F.n_tiles)) return;
+    const bool valid = lx < F.tile_w && ly < F.tile_h && px < F.width && py < F.height && lt < F.n_tiles;
     const size_t idx = ((size_t)lt * F.tile_h + ly) * F.tile_w + lx;
+
+    // Draw culling per block: a draw stays on the block's list unless the screen bounding box of its model box (the 8 corners
+    // through In.MVPMatrix, +-2 pixels for rounding and the sub-pixel jitter) misses the block's 32x8 pixels.  Boxes with a corner
+    // at or behind the camera plane always stay.  The list is a bit mask, walked in draw order (ties keep the first draw); the
+    // exact per-pixel coverage test below still decides, so culling never changes a result.
+    __shared__ uint32_t s_draws[GEOM_MAX_DRAWS / 32];
+    const int n_words = (n_draws + 31) >> 5;
+    for (int w = threadIdx.x; w < n_words; w += blockDim.x) s_draws[w] = 0u;
+    __syncthreads();
+    {
+        const float bx0 = (float)(txx * F.tile_w + bx * 32) - 2.0f, bx1 = bx0 + 32.0f + 4.0f;
+        const float by0 = (float)(tyy * F.tile_h + by * 8) - 2.0f, by1 = by0 + 8.0f + 4.0f;
+        for (int c = threadIdx.x; c < n_draws; c += blockDim.x) {
+            const DrawDev& d = draws[c];
+            float mnx = 3.0e38f, mny = 3.0e38f, mxx = -3.0e38f, mxy = -3.0e38f;
+            bool keep = false;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float4 cp = mat_mul(d.mvp, make_float4((k & 1) ? d.size[0] * 0.1f : 0.0f, (k & 2) ? d.size[1] * 0.1f : 0.0f, (k & 4) ? d.size[2] * 0.1f : 0.0f, 1.0f));
+                if (!(cp.w > 1.0e-3f)) keep = true;                                             // also catches NaN
+                const float sx = (cp.x / cp.w * 0.5f + 0.5f) * (float)F.width - 0.5f, sy = (0.5f - cp.y / cp.w * 0.5f) * (float)F.height - 0.5f;
+                mnx = fminf(mnx, sx); mxx = fmaxf(mxx, sx); mny = fminf(mny, sy); mxy = fmaxf(mxy, sy);
+            }
+            if (keep || !(mxx < bx0 || mnx > bx1 || mxy < by0 || mny > by1)) atomicOr(&s_draws[c >> 5], 1u << (c & 31));
+        }
+    }
+    __syncthreads();
+    if (!valid) return;
 
     uint32_t best = 0xFFFFFFu, onrm = 0u, omat = 0u, oalb = 0u;
     float omx = 0.0f, omy = 0.0f;
@@ -158,7 +187,9 @@ __global__ void __launch_bounds__(256) k_gbuffer_models(FrameView F, GeomK K, co
     const float3 farv = make_float3(fp.x / fp.w, fp.y / fp.w, fp.z / fp.w);
     const float3 camW = make_float3(K.cam[0], K.cam[1], K.cam[2]);
     const float3 dirW = xyz(mat_mul(K.InvView, make_float4(farv.x, farv.y, farv.z, 1.0f))) - camW;
-    for (int c = 0; c < n_draws; ++c) {
+    for (int w = 0; w < n_words; ++w)
+    for (uint32_t live = s_draws[w]; live; live &= live - 1u) {
+        const int c = (w << 5) + __ffs((int)live) - 1;
         const DrawDev& d = draws[c];
         const float3 ld = xyz(mat_mul(d.inv, make_float4(dirW.x, dirW.y, dirW.z, 0.0f))) * 10.0f;
         const float lo[3] = {d.cam[0], d.cam[1], d.cam[2]}, dd[3] = {ld.x, ld.y, ld.z};

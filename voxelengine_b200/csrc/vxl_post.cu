@@ -41,7 +41,9 @@ __device__ __forceinline__ int tex_index(int W, int H, float u, float v) {
 __device__ __forceinline__ float3 splat3(float v) { return make_float3(v, v, v); }
 
 struct TaaTexel { float3 color, normal, light; float4 material; float depth, mx, my, la; };
-__device__ __forceinline__ TaaTexel taa_fetch(const FullView& P, int W, int H, float u, float v) {
+// lut: unorm8[256] then snorm8[256], filled per block by the same divisions the decoders perform (13 texels x 10 channels per
+// pixel would otherwise be 130 IEEE divisions)
+__device__ __forceinline__ TaaTexel taa_fetch(const FullView& P, const float* __restrict__ lut, int W, int H, float u, float v) {
     TaaTexel t;
     const int i = tex_index(W, H, u, v);
     if (i < 0) {
@@ -49,9 +51,10 @@ __device__ __forceinline__ TaaTexel taa_fetch(const FullView& P, int W, int H, f
         return t;
     }
     const uint32_t a = __ldg(P.albedo + i), m = __ldg(P.material + i);
-    t.color = make_float3(unorm8(a), unorm8(a >> 8), unorm8(a >> 16));
-    t.normal = decode_normal(__ldg(P.normal + i));
-    t.material = make_float4(unorm8(m), unorm8(m >> 8), unorm8(m >> 16), unorm8(m >> 24));
+    const uint32_t nn = __ldg(P.normal + i);
+    t.color = make_float3(lut[a & 0xFFu], lut[(a >> 8) & 0xFFu], lut[(a >> 16) & 0xFFu]);
+    t.normal = make_float3(lut[256 + (nn & 0xFFu)], lut[256 + ((nn >> 8) & 0xFFu)], lut[256 + ((nn >> 16) & 0xFFu)]);
+    t.material = make_float4(lut[m & 0xFFu], lut[(m >> 8) & 0xFFu], lut[(m >> 16) & 0xFFu], lut[m >> 24]);
     t.depth = unorm24(__ldg(P.depth24 + i));
     const float2 mo = __ldg(P.motion + i);
     t.mx = mo.x; t.my = mo.y;
@@ -65,13 +68,16 @@ __device__ __forceinline__ float material_distance(float4 a, float4 b) {        
 }
 __device__ __forceinline__ float length2(float x, float y) { return sqrtf(x * x + y * y); }
 
-__global__ void __launch_bounds__(BLOCK_THREADS) k_light_taa(FrameView F, ViewK K, FullView P, const float2* __restrict__ g_cs /* [256][12] */,
+__global__ void __launch_bounds__(BLOCK_THREADS, 2) k_light_taa(FrameView F, ViewK K, FullView P, const float2* __restrict__ g_cs /* [256][12] */,
                                                              float4* __restrict__ out) {
+    __shared__ float lut[512];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { lut[i] = unorm8((uint32_t)i); lut[256 + i] = snorm8((uint32_t)i); }
+    __syncthreads();
     const PixelCtx p = pixel_ctx(F, K);
     if (!p.valid) return;
     const int W = F.width, H = F.height;
     const float iRx = 1.0f / (float)W, iRy = 1.0f / (float)H;                                 // :38
-    const TaaTexel c = taa_fetch(P, W, H, p.u, p.v);                                          // :40-47
+    const TaaTexel c = taa_fetch(P, lut, W, H, p.u, p.v);                                     // :40-47
     if (c.depth == 1.0f) { out[p.idx] = make_float4(c.light.x, c.light.y, c.light.z, c.la); return; }   // :49-52
     const float oldU = p.u + c.mx, oldV = p.v + c.my;                                         // :41
     const int li = tex_index(W, H, oldU, oldV);
@@ -84,7 +90,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_light_taa(FrameView F, ViewK 
         for (int x = -9; x <= 9; ++x)
             for (int y = -9; y <= 9; ++y) {
                 const float u = tclamp(p.u + (float)x * iRx, 0.001f, 0.999f), v = tclamp(p.v + (float)y * iRy, 0.001f, 0.999f);   // :62-63
-                const TaaTexel n = taa_fetch(P, W, H, u, v);
+                const TaaTexel n = taa_fetch(P, lut, W, H, u, v);
                 float factor = tmax(dot3(c.normal, n.normal), 0.0f);                          // :71
                 factor *= gstep(0.8f, 1.0f - material_distance(c.material, n.material));      // :72
                 factor *= 1.0f - tclamp(fabsf(c.depth - n.depth) * FAR_, 0.0f, 1.0f);          // :73
@@ -102,14 +108,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_light_taa(FrameView F, ViewK 
     const uint32_t nz = get_noise(F, K, p, -1);
     const float2* cs = g_cs + (nz & 0xFFu) * TAA_TAPS;
     const float k2 = tclamp(0.1f, 0.5f, 1.0f / c.depth);                                      // :99 (sic: clamp(x = 0.1, 0.5, 1/depth))
-#pragma unroll 1
+#pragma unroll 3
     for (int k = 0; k < TAA_TAPS; ++k) {                                                      // :96 radius <= size
         radius += 1.0f;
         const float2 a = __ldg(cs + k);
         const float k1 = radius * (lastVariance + 1.0f);
         const float ox = ((a.x * iRx) * k1) * k2, oy = ((a.y * iRy) * k1) * k2;
         const float u = tclamp(p.u + ox, 0.001f, 0.999f), v = tclamp(p.v + oy, 0.001f, 0.999f);
-        const TaaTexel n = taa_fetch(P, W, H, u, v);
+        const TaaTexel n = taa_fetch(P, lut, W, H, u, v);
         float factor = 1.212f - radius / size;                                                // :108
         factor *= gstep(0.8f, 1.0f - material_distance(c.material, n.material));
         factor *= tmax(dot3(c.normal, n.normal), 0.0f);

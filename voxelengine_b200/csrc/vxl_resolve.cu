@@ -60,18 +60,22 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_resolve_ambient(FrameView F, 
                                                                    const float* __restrict__ shadow, const float* __restrict__ ao,
                                                                    float4* __restrict__ out) {
     __shared__ float s_lut[LUT_FLOATS];
+    __shared__ float s_dec[512];             // unorm8[256], snorm8[256]: the decoders' own divisions, done once per block
     load_luts(s_lut, g_lut);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { s_dec[i] = unorm8((uint32_t)i); s_dec[256 + i] = snorm8((uint32_t)i); }
     __syncthreads();
     const PixelCtx p = pixel_ctx(F, K);
     if (!p.valid) return;
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     const float depth = unorm24(__ldg(F.depth24 + p.idx));
     if (depth < 0.999f) {                                                                     // :138
-        const float3 alb = unorm8x3(__ldg(albedo + p.idx));                                    // :139
+        const uint32_t ab = __ldg(albedo + p.idx);
+        const float3 alb = make_float3(s_dec[ab & 0xFFu], s_dec[(ab >> 8) & 0xFFu], s_dec[(ab >> 16) & 0xFFu]);                                    // :139
         const uint32_t m = __ldg(F.material + p.idx);
-        const float roughness = unorm8(m), metallic = unorm8(m >> 8), emit = unorm8(m >> 16);  // :182-184
+        const float roughness = s_dec[m & 0xFFu], metallic = s_dec[(m >> 8) & 0xFFu], emit = s_dec[(m >> 16) & 0xFFu];  // :182-184
         const float3 pos = p.farvec * (depth * (1.0f + 1.0f / FAR_));                          // :141
-        const float3 normal = decode_normal(__ldg(F.normal + p.idx));
+        const uint32_t nb = __ldg(F.normal + p.idx);
+        const float3 normal = make_float3(s_dec[256 + (nb & 0xFFu)], s_dec[256 + ((nb >> 8) & 0xFFu)], s_dec[256 + ((nb >> 16) & 0xFFu)]);
         const float3 SUN = normalize3(make_float3(0.3f, 0.4f, 0.5f));
         const float3 sunDir = xyz(mat_mul(K.View, make_float4(SUN.x, SUN.y, SUN.z, 0.0f)));     // :179
         const float3 F0 = mix3(splat(0.04f), alb, metallic);                                   // :187-188
@@ -98,7 +102,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_resolve_ambient(FrameView F, 
             const uint32_t n = get_noise(F, K, p, i);
             const float3 rv = cosine_sample_hemisphere(s_lut, n, n >> 8);
             const float3 dir = tangent * rv.x + bitangent * rv.y + N * rv.z;
-            occlusion += screenspace_occlusion(K, depth_full, F.width, F.height, opos, normalize3(dir) * sizeMultiplier, unorm8(n >> 16));
+            occlusion += screenspace_occlusion(K, depth_full, F.width, F.height, opos, normalize3(dir) * sizeMultiplier, s_dec[(n >> 16) & 0xFFu]);
         }
         occlusion /= 4.0f;
         occlusion *= 3.0f;

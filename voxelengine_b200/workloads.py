@@ -45,6 +45,7 @@ class Workload:
             self.gb = E.GeometryBuffer(self.ctx, W, H, tile[0], tile[1], rank=rank, world=world)
         self.host_volume = None
         self.entities = None
+        self.props = None
         self._build_scene(scale)
         self.view = S.default_camera(tex, W, H, frame_index) if cfg["scene"] != "house" else self._house_view(W, H, frame_index)
         self.gb.set_noise(S.blue_noise(4))
@@ -85,6 +86,7 @@ class Workload:
             msz = max(8, int(round(40 * scale)))
             mid = vol.add_model(S.house_model(msz, seed=1))
             e = S.prop_entities(self.host_volume, n=cfg["n_props"], model_size=msz, seed=2, model=mid)
+            self.props = e                                       # the instanced models, also the draw list of the geometry pass
             vol.OnUpdate(e, want_regions=False)
             self.host_volume = vol.download()
         elif cfg["scene"] == "dynamic":
