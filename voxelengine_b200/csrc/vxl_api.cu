@@ -106,7 +106,7 @@ int vxl_ctx_destroy(vxl_ctx* c) {
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_stats); cudaFree(c->d_luts); cudaFree(c->d_taa_lut); cudaFree(c->d_lights); cudaFree(c->d_perm);
     for (auto& m : c->models) { cudaFree((void*)m.voxels); cudaFree((void*)m.mip1); cudaFree((void*)m.mip2); }
-    cudaFree(c->d_models); cudaFree(c->d_hkeys); cudaFree(c->d_hvals); cudaFree(c->d_ents); cudaFree(c->d_aabb);
+    cudaFree(c->d_models); cudaFree(c->d_draws); cudaFree(c->d_hkeys); cudaFree(c->d_hvals); cudaFree(c->d_ents); cudaFree(c->d_aabb);
     cudaFree(c->h_planes); cudaFree(c->h_out); cudaFree(c->h_noise);
     if (c->s_h2d) { cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h); }
     for (auto& e : c->ev) cudaEventDestroy(e);

@@ -58,6 +58,8 @@ struct vxl_ctx {
     std::vector<vxl::ModelDev> models;
     vxl::ModelDev* d_models = nullptr;
     int d_models_cap = 0;
+    void* d_draws = nullptr;                 // draw list of vxl_gbuffer_models (vxl_model.cu), grown on demand
+    int draws_cap = 0;
     // voxeliser scratch
     unsigned long long* d_hkeys = nullptr;
     unsigned* d_hvals = nullptr;

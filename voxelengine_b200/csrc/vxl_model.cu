@@ -318,17 +318,20 @@ int vxl_gbuffer_models(vxl_ctx* ctx, const vxl_view* view, const vxl_frame* fram
     }
     DrawDev* d_draws = nullptr;
     if (n_cmds > 0) {
-        VXL_CUDA(cudaMallocAsync((void**)&d_draws, sizeof(DrawDev) * (size_t)n_cmds, ctx->stream));
+        if (ctx->draws_cap < n_cmds) {                                       // persistent, grown on demand
+            if (ctx->d_draws) VXL_CUDA(cudaFree(ctx->d_draws));
+            ctx->d_draws = nullptr; ctx->draws_cap = 0;
+            VXL_CUDA(cudaMalloc(&ctx->d_draws, sizeof(DrawDev) * (size_t)n_cmds));
+            ctx->draws_cap = n_cmds;
+        }
+        d_draws = (DrawDev*)ctx->d_draws;
+        // pageable source: the call returns once `draws` has been copied to the driver's staging memory
         VXL_CUDA(cudaMemcpyAsync(d_draws, draws.data(), sizeof(DrawDev) * (size_t)n_cmds, cudaMemcpyHostToDevice, ctx->stream));
     }
     const int bpt = ((F.tile_w + 31) / 32) * ((F.tile_h + 7) / 8);
     k_gbuffer_models<<<(unsigned)(bpt * F.n_tiles), 256, 0, ctx->stream>>>(F, K, d_draws, n_cmds, pal_color, pal_material, out->depth24, out->normal,
                                                                          out->material, out->albedo, (float2*)out->motion);
     VXL_LAUNCH_CHECK(ctx);
-    if (d_draws) {
-        VXL_CUDA(cudaStreamSynchronize(ctx->stream));                       // `draws` (pageable) must outlive the copy
-        VXL_CUDA(cudaFreeAsync(d_draws, ctx->stream));
-    }
     return VXL_OK;
 }
 
