@@ -310,6 +310,36 @@ int vxl_pallete_file_read(const char* path, uint32_t* color256, uint32_t* materi
 int vxl_prefab_file_read(const char* path, vxl_prefab_entity* out, int cap, int* n_out);
 int vxl_scene_load(const char* mods_dir, const char* prefab_path, vxl_prefab_entity* out, int cap, int* n_out);
 
+/* The MagicaVoxel .vox importer (Sources/Editor/Importer/VoxImporter.cpp:284-520, host code in vxl_voximport.cu): what the reference's
+ * editor runs on a dropped .vox file to produce the .v / .p / .pf files above.
+ *   vxl_vox_import / _memory  VoxImportContext::Import (:284-394) + CreateEntity (:397-476): the chunk loop, then the node tree as entities in
+ *                             creation order (a group before its children) with Transform.Position in world units (voxel * 0.1, z-up -> y-up)
+ *                             and one model per shape node, voxels re-oriented by the node's `_r` byte into a volume whose sizes are rounded
+ *                             up to a multiple of 4 (VoxAsset.h:26-30).  Unnamed shapes are named "0", "1", ... in creation order.
+ *   vxl_vox_scene_model       the .v contents of model `model` (dims + palette indices, x fastest); out == NULL only fills dims / name
+ *   vxl_vox_scene_pallete     the .p contents: 256 x {r, g, b, a, roughness, metallic, emit}; `a` is uninitialised in the reference, 0 here
+ *   vxl_vox_scene_write       VoxImporter::Import (:478-520) + Assets::CreateAsset + PrefabAsset::FromWorld: writes
+ *                             <mods_dir>/<path>/<file_name>/<shape>.v, <mods_dir>/<path>/<file_name>/<file_name>.p and <mods_dir>/<path>/<file_name>.pf
+ *                             (json11's dump format, fmt's "{}" floats, GUIDs = vxl_asset_guid of the paths relative to mods_dir); the root
+ *                             entity is named <file_name>.
+ * Pinned against the reference's own imports: Assets/Mods/default ships FarmHouse / ModernHouse / Player .vox next to the files its importer
+ * wrote from them.  Malformed input returns VXL_ERR_INVALID. */
+typedef struct vxl_vox_scene vxl_vox_scene;
+typedef struct vxl_vox_import_entity {
+    int32_t parent;                  /* index into the entity array, -1 for the root */
+    int32_t model;                   /* index for vxl_vox_scene_model, -1 for a group */
+    float   position[3];             /* Transform.Position; Rotation = 0, Scale = 1, Pivot = 0 */
+    char    name[64];                /* the shape's name ("" for groups); the written .pf names the root <file_name> */
+} vxl_vox_import_entity;
+int vxl_vox_import(const char* vox_path, vxl_vox_scene** out);
+int vxl_vox_import_memory(const void* data, uint64_t size, vxl_vox_scene** out);
+int vxl_vox_scene_counts(const vxl_vox_scene* scene, int* n_entities, int* n_models);
+int vxl_vox_scene_entities(const vxl_vox_scene* scene, vxl_vox_import_entity* out, int cap);
+int vxl_vox_scene_model(const vxl_vox_scene* scene, int model, int32_t dims[3], char name[64], uint8_t* out, uint64_t cap);
+int vxl_vox_scene_pallete(const vxl_vox_scene* scene, uint8_t records[1792]);
+int vxl_vox_scene_write(const vxl_vox_scene* scene, const char* mods_dir, const char* path, const char* file_name);
+int vxl_vox_scene_free(vxl_vox_scene* scene);
+
 /* rays/out are DEVICE pointers */
 int vxl_trace_rays(vxl_ctx* ctx, vxl_volume* vol, const vxl_ray* rays, int64_t n, int variant, vxl_hit* out);
 

@@ -159,3 +159,195 @@ def load_scene(mods_dir: str, prefab_path: str):
     out = []
     _spawn(os.path.join(mods_dir, prefab_path), -1, paths, mods_dir, out)
     return _finish(out)
+
+
+# ---- MagicaVoxel .vox importer (Sources/Editor/Importer/VoxImporter.cpp) --------------------------------------------------------
+# Pinned against the reference's own import results: Assets/Mods/default ships FarmHouse.vox / ModernHouse.vox / Player.vox NEXT TO
+# the .v / .p / .pf files the reference's importer wrote from them (tests/test_vox_import.py compares them byte for byte).
+
+def _vox_matrix(r):
+    """VoxTransformMatrix (VoxImporter.cpp:37-84): axis map + sign bits of a row-major signed permutation packed in a byte."""
+    r &= 0xFF
+    rx, ry = r & 3, (r >> 2) & 3
+    return dict(rx=rx, ry=ry, rz=3 - (rx | ry), sx=(r >> 4) & 1, sy=(r >> 5) & 1, sz=(r >> 6) & 1)
+
+
+def _from_chars_int(s, default=0):
+    """std::from_chars<int> on a prefix: optional '-', decimal digits; no leading white space; no match leaves the value."""
+    i, n = 0, len(s)
+    if i < n and s[i] == "-":
+        i += 1
+    j = i
+    while j < n and s[j].isdigit():
+        j += 1
+    return int(s[:j]) if j > i else default
+
+
+def _from_chars_float(s, default=0.0):
+    """std::from_chars<float> on a prefix (general format: no leading '+' / white space), correctly rounded."""
+    import re
+    m = re.match(r"-?(\d+\.?\d*([eE][-+]?\d+)?|\.\d+([eE][-+]?\d+)?|inf(inity)?|nan)", s, re.I)
+    return F(float(m.group(0))) if m else F(default)
+
+
+def _u8_of_float(x):
+    """float -> uint8 conversion of `emit * 255.0f` (VoxImporter.cpp:200-202): truncation, values in [0, 256) only."""
+    return int(F(x)) & 0xFF
+
+
+def vox_import(data: bytes):
+    """VoxImportContext::Import (:284-394) + CreateEntity (:397-476) + VoxImporter::Import (:478-520).
+    -> dict(models=[(name, uint8[sz][sy][sx])], records=uint8[256][7] (.p file contents), entities=[dict(name, parent, model, position)])
+    Entities are in creation order (depth first, a group before its children) -- the order PrefabAsset::FromWorld numbers them."""
+    import struct
+    pos = 0
+
+    def take(n):
+        nonlocal pos
+        b = data[pos:pos + n]
+        pos += n
+        return b + b"\0" * (n - len(b))          # a FileReader past the end leaves the destination untouched: zeros / blanks stop the loop
+
+    def i32():
+        return struct.unpack("<i", take(4))[0]
+
+    def string():
+        n = i32()
+        return take(max(n, 0)).decode("latin-1")
+
+    def dictionary():
+        d = {}
+        for _ in range(i32()):
+            k = string()
+            d[k] = string()
+        return d
+
+    if take(4) != b"VOX ":
+        raise ValueError("not a .vox file")
+    i32()                                         # version
+    pallete = np.zeros((257, 4), np.uint8)
+    surfaces = np.zeros((257, 3), np.uint8)       # e, r, m  (uninitialised in the reference; zero here and in vxl_vox_import)
+    size = (0, 0, 0)
+    shapes, nodes = [], []
+    while True:
+        header = take(4) if pos < len(data) else b"    "
+        if pos >= len(data) and header == b"    ":
+            break
+        i32(); i32()                              # chunk content size, children size (not used to skip: every known chunk is read field by field)
+        h0, h1, h2 = chr(header[0]), chr(header[1]), chr(header[2])
+        if h0 == "M":
+            if h2 == "T":                         # MATL
+                mid = i32()
+                p = dictionary()
+                rough = emit = metal = F(0)
+                typ = p.get("_type", "")
+                if typ in ("_metal", "_blend"):
+                    if "_rough" in p: rough = _from_chars_float(p["_rough"])
+                    if "_metal" in p: metal = _from_chars_float(p["_metal"])
+                elif typ == "_emit":
+                    if "_emit" in p: emit = _from_chars_float(p["_emit"])
+                elif typ == "_diffuse":
+                    rough = F(0.9)
+                if 0 <= mid <= 256:
+                    surfaces[mid] = (_u8_of_float(F(emit) * F(255)), _u8_of_float(F(rough) * F(255)), _u8_of_float(F(metal) * F(255)))
+            # 'I' = MAIN: nothing
+        elif h0 == "P":
+            i32()
+        elif h0 == "S":
+            size = (i32(), i32(), i32())
+        elif h0 == "X":
+            n = i32()
+            vox = np.frombuffer(take(4 * max(n, 0)), np.uint8).reshape(-1, 4).copy()
+            shapes.append((size, vox))
+        elif h0 == "R":
+            pallete[1:257] = np.frombuffer(take(1024), np.uint8).reshape(256, 4)
+        elif h0 == "L":
+            i32(); dictionary(); i32()
+        elif h0 == "I":
+            take(256)
+        elif h0 == "r":
+            dictionary()
+        elif h0 == "n":
+            i32()                                 # node id
+            nd = dictionary()
+            name = nd.get("_name", "")
+            if h1 == "T":
+                child = i32(); i32(); i32(); i32()
+                m = dictionary()
+                x = y = z = 0
+                t = m.get("_t", "")
+                if t:
+                    e1 = t.find(" ", 1) + 1
+                    x = _from_chars_int(t[0:e1])
+                    e2 = t.find(" ", e1 + 1) + 1
+                    y = _from_chars_int(t[e1:e2])
+                    z = _from_chars_int(t[e2:])
+                r = 0b0100
+                if m.get("_r", ""):
+                    r = _from_chars_int(m["_r"], r)
+                nodes.append(dict(kind="T", name=name, child=child, t=(x, y, z), m=_vox_matrix(r)))
+            elif h1 == "G":
+                nodes.append(dict(kind="G", children=[i32() for _ in range(i32())]))
+            elif h1 == "S":
+                i32()
+                nodes.append(dict(kind="S", shape=i32()))
+                dictionary()
+        else:
+            break
+
+    records = np.zeros((256, 7), np.uint8)        # VoxImporter::Import :489-497; `a` keeps VoxMaterial's default
+    records[:, 0:3] = pallete[:256, 0:3]
+    records[:, 3] = _VOXMATERIAL_DEFAULT_A
+    records[:, 4] = surfaces[:256, 1]
+    records[:, 5] = surfaces[:256, 2]
+    records[:, 6] = surfaces[:256, 0]
+
+    models, entities = [], []
+    counter = [0]
+
+    def create(root, parent):
+        node = nodes[root["child"]]
+        tx, ty, tz = root["t"]
+        p = [F(F(tx) * F(0.1)), F(F(tz) * F(0.1)), F(F(-ty) * F(0.1))]
+        e = dict(name="", parent=parent, model=-1, position=p)
+        idx = len(entities)
+        if node["kind"] == "G":
+            entities.append(e)
+            for c in node["children"]:
+                create(nodes[c], idx)
+            return idx
+        if node["kind"] == "S":
+            (sx, sy, sz), vox = shapes[node["shape"]]
+            M = root["m"]
+            size = (sx, sy, sz)
+            ts = (size[M["rx"]], size[M["ry"]], size[M["rz"]])
+            center = (ts[0] - ts[0] // 2 if M["sx"] else ts[0] // 2,
+                      ts[2] - ts[2] // 2 if M["sz"] else ts[2] // 2,
+                      ts[1] - ts[1] // 2 if not M["sy"] else ts[1] // 2)
+            e["position"] = [F(p[i] - F(F(center[i]) * F(0.1))) for i in range(3)]
+            pad = lambda n: ((n - 1) & ~3) + 4                           # VoxAsset(int32, int32, int32) rounds every size up to a multiple of 4 (VoxAsset.h:26-30)
+            out = np.zeros((pad(ts[1]), pad(ts[2]), pad(ts[0])), np.uint8)  # VoxAsset(tSize.x, tSize.z, tSize.y): [z][y][x]; voxels placed by the unpadded tSize
+            v = vox.astype(np.int64)
+            comp = (v[:, 0], v[:, 1], v[:, 2])
+            cx, cy, cz = comp[M["rx"]], comp[M["ry"]], comp[M["rz"]]
+            if M["sx"]: cx = ts[0] - cx - 1
+            if M["sy"]: cy = ts[1] - cy - 1
+            if M["sz"]: cz = ts[2] - cz - 1
+            for i in range(len(v)):                                       # in file order: a later record overwrites an earlier one
+                out[ts[1] - 1 - cy[i], cz[i], cx[i]] = v[i, 3]
+            if root["name"]:
+                e["name"] = root["name"]
+            else:
+                e["name"] = str(counter[0])
+                counter[0] += 1
+            e["model"] = len(models)
+            models.append((e["name"], out))
+            entities.append(e)
+            return idx
+        return -1
+
+    create(nodes[0], -1)
+    return dict(models=models, records=records, entities=entities)
+
+
+_VOXMATERIAL_DEFAULT_A = 0

@@ -22,6 +22,8 @@ SYMBOLS = [
     "vxl_resolve_ambient", "vxl_resolve_point", "vxl_resolve_spot", "vxl_trace_model_rays", "vxl_gbuffer_models",
     "vxl_light_taa", "vxl_resolve_reflection",
     "vxl_asset_guid", "vxl_vox_file_read", "vxl_model_load_v", "vxl_pallete_file_read", "vxl_prefab_file_read", "vxl_scene_load",
+    "vxl_vox_import", "vxl_vox_import_memory", "vxl_vox_scene_counts", "vxl_vox_scene_entities", "vxl_vox_scene_model",
+    "vxl_vox_scene_pallete", "vxl_vox_scene_write", "vxl_vox_scene_free",
 ]
 
 VXL_MAX_LIGHTS = 64
@@ -106,6 +108,10 @@ def load():
         "vxl_asset_guid": [C.c_char_p, P(C.c_uint64)], "vxl_vox_file_read": [C.c_char_p, vp, vp, C.c_uint64],
         "vxl_model_load_v": [vp, C.c_char_p, P(C.c_int)], "vxl_pallete_file_read": [C.c_char_p, vp, vp],
         "vxl_prefab_file_read": [C.c_char_p, vp, i32, P(C.c_int)], "vxl_scene_load": [C.c_char_p, C.c_char_p, vp, i32, P(C.c_int)],
+        "vxl_vox_import": [C.c_char_p, P(vp)], "vxl_vox_import_memory": [vp, C.c_uint64, P(vp)],
+        "vxl_vox_scene_counts": [vp, P(C.c_int), P(C.c_int)], "vxl_vox_scene_entities": [vp, vp, i32],
+        "vxl_vox_scene_model": [vp, i32, vp, vp, vp, C.c_uint64], "vxl_vox_scene_pallete": [vp, vp],
+        "vxl_vox_scene_write": [vp, C.c_char_p, C.c_char_p, C.c_char_p], "vxl_vox_scene_free": [vp],
         "vxl_resolve_reflection": [vp, vp, P(Frame), vp, vp, vp, vp, vp],
         "vxl_lighting_host": [vp, vp, P(LightingHostArgs)],
         "vxl_volume_gen_terrain": [vp], "vxl_gbuffer_primary": [vp, vp, vp, P(Frame)],

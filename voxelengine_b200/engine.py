@@ -582,3 +582,50 @@ def load_scene(mods_dir: str, prefab_path: str) -> np.ndarray:
     out = np.zeros(n.value, PREFAB_ENTITY_DTYPE)
     check(lib.vxl_scene_load(mods_dir.encode(), prefab_path.encode(), _np_ptr(out), n.value, C.byref(n)), "vxl_scene_load")
     return out
+
+
+VOX_IMPORT_ENTITY_DTYPE = np.dtype([("parent", "<i4"), ("model", "<i4"), ("position", "<f4", 3), ("name", "S64")])
+
+
+class VoxImporter:
+    """Sources/Editor/Importer/VoxImporter.cpp: a MagicaVoxel .vox file -> models (.v), palette (.p), entity tree (.pf)."""
+
+    def __init__(self, source):
+        self.lib = capi.load()
+        self.h = C.c_void_p()
+        if isinstance(source, (bytes, bytearray)):
+            buf = (C.c_char * len(source)).from_buffer_copy(bytes(source))
+            check(self.lib.vxl_vox_import_memory(C.addressof(buf), len(source), C.byref(self.h)), "vxl_vox_import_memory")
+        else:
+            check(self.lib.vxl_vox_import(str(source).encode(), C.byref(self.h)), "vxl_vox_import")
+        ne, nm = C.c_int(), C.c_int()
+        check(self.lib.vxl_vox_scene_counts(self.h, C.byref(ne), C.byref(nm)), "vxl_vox_scene_counts")
+        self.n_entities, self.n_models = ne.value, nm.value
+
+    def entities(self) -> np.ndarray:
+        out = np.zeros(self.n_entities, VOX_IMPORT_ENTITY_DTYPE)
+        check(self.lib.vxl_vox_scene_entities(self.h, _np_ptr(out), len(out)), "vxl_vox_scene_entities")
+        return out
+
+    def model(self, i: int):
+        """-> (name, uint8 (sz, sy, sx))"""
+        dims = np.zeros(3, np.int32)
+        name = C.create_string_buffer(64)
+        check(self.lib.vxl_vox_scene_model(self.h, i, _np_ptr(dims), C.addressof(name), None, 0), "vxl_vox_scene_model")
+        out = np.zeros((int(dims[2]), int(dims[1]), int(dims[0])), np.uint8)
+        check(self.lib.vxl_vox_scene_model(self.h, i, _np_ptr(dims), C.addressof(name), _np_ptr(out), out.size), "vxl_vox_scene_model")
+        return name.value.decode("latin-1"), out
+
+    def pallete_records(self) -> np.ndarray:
+        out = np.zeros((256, 7), np.uint8)
+        check(self.lib.vxl_vox_scene_pallete(self.h, _np_ptr(out)), "vxl_vox_scene_pallete")
+        return out
+
+    def write(self, mods_dir: str, path: str, file_name: str):
+        """VoxImporter::Import's asset files under <mods_dir>/<path>/."""
+        check(self.lib.vxl_vox_scene_write(self.h, mods_dir.encode(), path.encode(), file_name.encode()), "vxl_vox_scene_write")
+
+    def close(self):
+        if self.h:
+            self.lib.vxl_vox_scene_free(self.h)
+            self.h = C.c_void_p()
