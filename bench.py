@@ -102,18 +102,23 @@ def algorithmic_bytes(pass_name: str, st: dict, n_ao: int) -> int:
 # reference arm: the CPU oracle (a port of the reference shaders; the reference itself is Vulkan/Windows
 # only and cannot run here) on all host cores, inputs generated on the CPU as well.
 # ------------------------------------------------------------------------------------------------------
-def cpu_frame(O, vol, view, gb, lights, cfg, rows):
+def cpu_frame(O, vol, view, gb, lights, cfg, rows, keep=None):
+    """One pass of the oracle over `rows`; keep (a dict) receives the planes it computed (for the parity check)."""
     t0 = time.perf_counter()
     rays = steps = 0
-    _, _, st = O.pass_ambient(vol, view, gb, cfg["n_ao"], rows=rows)
+    sh, ao, st = O.pass_ambient(vol, view, gb, cfg["n_ao"], rows=rows)
     rays += st["rays"]; steps += st["steps"]
+    pt = sp = None
     if cfg["n_point"]:
-        _, st = O.pass_point(vol, view, gb, lights, rows=rows)
+        pt, st = O.pass_point(vol, view, gb, lights, rows=rows)
         rays += st["rays"]; steps += st["steps"]
     if cfg["spec"]:
-        _, st = O.pass_reflection(vol, view, gb, rows=rows)
+        sp, st = O.pass_reflection(vol, view, gb, rows=rows)
         rays += st["rays"]; steps += st["steps"]
-    return rays, steps, time.perf_counter() - t0
+    dt = time.perf_counter() - t0
+    if keep is not None:
+        keep.update(shadow=sh, ao=ao, point=pt, spec_t=sp)
+    return rays, steps, dt
 
 
 def pick_rows(O, vol, view, gb, lights, cfg, H, target_s=12.0):
@@ -379,7 +384,7 @@ def run_ours(args):
     e2e = None if args.no_e2e else run_e2e(args, wl, torch, dist, world, rank, rays)
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample of the same frame ----
-    cpu = None
+    cpu = parity = None
     if world == 1 and not args.no_cpu:
         from oracle import vxo_py as O
         O.set_num_threads(len(os.sched_getaffinity(0)))
@@ -387,9 +392,28 @@ def run_ours(args):
         gbh = {k: getattr(wl.gb, k).cpu().numpy().view(np.uint32)[0] for k in ("depth24", "normal", "material")}
         gbh["noise"] = wl.gb.noise.cpu().numpy().view(np.uint32)
         rows = pick_rows(O, vol_h, wl.view, gbh, wl.lights, cfg, H, target_s=15.0)
-        r, s, dt = cpu_frame(O, vol_h, wl.view, gbh, wl.lights, cfg, rows)
+        want = {}
+        r, s, dt = cpu_frame(O, vol_h, wl.view, gbh, wl.lights, cfg, rows, keep=want)
         cpu = {"value": r / dt / 1e6, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
                "sample": f"rows {rows[0]}:{rows[1]}:{rows[2]} of the {W}x{H} frame ({r} rays, {dt:.1f} s)"}
+        # The oracle's planes are in hand: check the frame the GPU just timed against them, bit for bit, at the bench's full size.
+        if cfg["scene"] != "dynamic":
+            wl.step(gather=False); torch.cuda.synchronize()
+            got = wl.assemble()
+            sel = slice(rows[0], rows[1], rows[2])
+            planes = {"shadow": (got[0], want["shadow"]), "ao": (got[1], want["ao"])}
+            if wl.spec:
+                planes["spec_t"] = (got[2], want["spec_t"])
+            for li in range(wl.n_point):
+                planes[f"point{li}"] = (got[3 + li], want["point"][li])
+            res_p = {k: bool(np.array_equal(g[sel].view(np.uint32), w[sel].view(np.uint32))) for k, (g, w) in planes.items()}
+            parity = {"checker": "oracle (cpu_baseline leg)", "rows": f"{rows[0]}:{rows[1]}:{rows[2]}", "pixels": int(got[0][sel].size),
+                      "planes_bit_exact": res_p, "bit_exact": all(res_p.values())}
+            if rows[2] == 1:
+                parity["rays_equal"] = bool(int(rays) == int(r))
+                parity["probes_equal"] = bool(int(probes) == int(s))
+            if not parity["bit_exact"]:
+                sys.stderr.write(f"PARITY FAILURE at full size: {res_p}\n")
 
     if rank == 0:
         print(json.dumps({
@@ -402,7 +426,7 @@ def run_ours(args):
                        "l2": "flushed between timed steps (256 MiB fill outside the event pairs); per-step working set 128 MiB volume + 100 MB G-buffer + 232 MB outputs",
                        "ms_per_step_warm_l2": ms_warm, "ms_per_step_plain_march_variant0": ms_plain,
                        "probes_that_read_the_volume": int(fetched_probes)},
-            "roofline": roofline, "light_buffer_resolve": resolve, "post_passes": post, "geometry_pass": geom, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(),
+            "roofline": roofline, "light_buffer_resolve": resolve, "post_passes": post, "geometry_pass": geom, "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(),
         }))
     wl.close()
     if world > 1:

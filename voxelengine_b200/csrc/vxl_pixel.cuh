@@ -17,7 +17,8 @@ constexpr int BLOCK_THREADS = BLOCK_W * BLOCK_H;
 #define VXL_PASS_BLOCKS 3         // resident 512-thread blocks per SM the pass kernels' registers are capped for (<= 42 regs);
 #endif                            // measured: 3 blocks 5.91 ms vs 2 blocks 6.51 ms for k_ambient on config 3 (profiles/r1f)
 
-struct ViewK { float InvView[16], View[16], InvProj[16], Proj[16]; int Frame; };
+constexpr int NOISE_OFFS = 17;                      // getNoise() and getNoise(0..15): the frame-dependent texture offsets, per launch not per ray
+struct ViewK { float InvView[16], View[16], InvProj[16], Proj[16]; int Frame; float nfx[NOISE_OFFS], nfy[NOISE_OFFS]; };
 
 struct PixelCtx {
     bool valid;
@@ -56,10 +57,8 @@ __device__ __forceinline__ PixelCtx pixel_ctx(const FrameView& F, const ViewK& K
 // LightAmbient.frag:44-52 getNoise() (s < 0) / getNoise(int s)
 __device__ __forceinline__ uint32_t get_noise(const FrameView& F, const ViewK& K, const PixelCtx& p, int s) {
     float fx, fy;
-    if (s < 0) {
-        fx = GOLDEN_RATIO * gmod((float)K.Frame, 16.0f);
-        fy = GOLDEN_RATIO * gmod((float)(K.Frame + 1), 16.0f);
-    } else {
+    if (s + 1 < NOISE_OFFS) { fx = K.nfx[s + 1]; fy = K.nfy[s + 1]; }      // make_viewk: the same expressions, evaluated once on the host
+    else {
         fx = GOLDEN_RATIO * gmod((float)(K.Frame + s * 5), 64.0f);
         fy = GOLDEN_RATIO * gmod((float)(K.Frame + s * 7 + 1), 64.0f);
     }
@@ -93,6 +92,13 @@ static inline ViewK make_viewk(const vxl_view* v) {
     ViewK k;
     for (int i = 0; i < 16; ++i) { k.InvView[i] = v->InverseViewMatrix[i]; k.View[i] = v->ViewMatrix[i]; k.InvProj[i] = v->InverseProjectionMatrix[i]; k.Proj[i] = v->ProjectionMatrix[i]; }
     k.Frame = v->Frame;
+    // LightAmbient.frag:44-52: index 0 = getNoise(), 1 + s = getNoise(s); IEEE division / floor / multiply / subtract, identical on host and device
+    k.nfx[0] = GOLDEN_RATIO * gmod((float)k.Frame, 16.0f);
+    k.nfy[0] = GOLDEN_RATIO * gmod((float)(k.Frame + 1), 16.0f);
+    for (int s = 0; s + 1 < NOISE_OFFS; ++s) {
+        k.nfx[s + 1] = GOLDEN_RATIO * gmod((float)(k.Frame + s * 5), 64.0f);
+        k.nfy[s + 1] = GOLDEN_RATIO * gmod((float)(k.Frame + s * 7 + 1), 64.0f);
+    }
     return k;
 }
 
