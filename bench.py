@@ -397,8 +397,10 @@ def run_ours(args):
         cpu = {"value": r / dt / 1e6, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
                "sample": f"rows {rows[0]}:{rows[1]}:{rows[2]} of the {W}x{H} frame ({r} rays, {dt:.1f} s)"}
         # The oracle's planes are in hand: check the frame the GPU just timed against them, bit for bit, at the bench's full size.
-        if cfg["scene"] != "dynamic":
-            wl.step(gather=False); torch.cuda.synchronize()
+        if True:
+            wl.ctx.stats_reset()
+            wl.step(gather=False, advance=False); torch.cuda.synchronize()       # dynamic scene: the frame whose volume was just downloaded
+            st_now = wl.ctx.stats()
             got = wl.assemble()
             sel = slice(rows[0], rows[1], rows[2])
             planes = {"shadow": (got[0], want["shadow"]), "ao": (got[1], want["ao"])}
@@ -410,8 +412,8 @@ def run_ours(args):
             parity = {"checker": "oracle (cpu_baseline leg)", "rows": f"{rows[0]}:{rows[1]}:{rows[2]}", "pixels": int(got[0][sel].size),
                       "planes_bit_exact": res_p, "bit_exact": all(res_p.values())}
             if rows[2] == 1:
-                parity["rays_equal"] = bool(int(rays) == int(r))
-                parity["probes_equal"] = bool(int(probes) == int(s))
+                parity["rays_equal"] = bool(int(st_now["rays"]) == int(r))
+                parity["probes_equal"] = bool(int(st_now["steps"]) == int(s))
             if not parity["bit_exact"]:
                 sys.stderr.write(f"PARITY FAILURE at full size: {res_p}\n")
 
@@ -474,34 +476,82 @@ def run_e2e(args, wl, torch, dist, world, rank, rays):
         assert torch.equal(outs["shadow"], ref[0, :n]) and torch.equal(outs["ao"], ref[1, :n]), "e2e planes differ from the resident path"
         return {"value": rays / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3,
                 "api": "vxl_lighting_host (pinned host buffers)"}
-    host_main = torch.empty((world, 3) + tuple(wl.out.shape[1:]), dtype=torch.float32).pin_memory() if rank == 0 else None
-    host_point = torch.empty((world, wl.n_point) + tuple(wl.out.shape[1:]), dtype=torch.float32).pin_memory() if rank == 0 and wl.n_point else None
-    d2h = (int(host_main.numel()) + (int(host_point.numel()) if host_point is not None else 0)) * 4 if rank == 0 else 0
+    # N > 1: every rank runs the same host-facing call on its tile shard, and its outputs land -- over its own PCIe link -- in ONE
+    # host frame shared by all ranks (POSIX shared memory, page-locked by each rank with cudaHostRegister): [rank][plane][tile].
+    # No rank reads back another rank's tiles; the NCCL all-gather belongs to the device-resident path (`value`).
+    from multiprocessing import shared_memory
+    n_planes = wl.n_planes
+    slot = n_planes * wl.tiles_padded * wl.gb.tile_h * wl.gb.tile_w          # floats per rank (padded to the largest shard)
+    name = f"vxl_e2e_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}"
+    if rank == 0:
+        try:
+            shared_memory.SharedMemory(name=name).unlink()
+        except FileNotFoundError:
+            pass
+        shm = shared_memory.SharedMemory(name=name, create=True, size=world * slot * 4)
+    dist.barrier()
+    if rank != 0:
+        shm = shared_memory.SharedMemory(name=name)
+        try:                                   # rank 0 owns the segment: keep this process's resource tracker from unlinking it again at exit
+            from multiprocessing import resource_tracker
+            resource_tracker.unregister(shm._name, "shared_memory")
+        except Exception:
+            pass
+    frame_host = np.ndarray((world, slot), dtype=np.float32, buffer=shm.buf)
+    mine = torch.from_numpy(frame_host[rank])
+    rc = torch.cuda.cudart().cudaHostRegister(mine.data_ptr(), slot * 4, 0)
+    assert int(rc) == 0, f"cudaHostRegister failed: {rc}"
+    plane = n * wl.gb.tile_h * wl.gb.tile_w
+    outs = dict(shadow=mine[0:plane], ao=mine[plane:2 * plane])
+    if wl.spec:
+        outs["spec_t"] = mine[2 * plane:3 * plane]
+    if wl.n_point:
+        outs["point_shadow"] = mine[3 * plane:(3 + wl.n_point) * plane]
+    d2h = sum(int(t.numel()) * 4 for t in outs.values())
+    desc = dict(width=wl.gb.width, height=wl.gb.height, tile_w=wl.gb.tile_w, tile_h=wl.gb.tile_h, tile_first=wl.gb.tile_first,
+                tile_stride=wl.gb.tile_stride, n_tiles=n)
 
     def one():
-        for k in ("depth24", "normal", "material"):
-            getattr(wl.gb, k).copy_(planes[k], non_blocking=True)
-        wl.gb.noise.copy_(planes["noise"], non_blocking=True)
-        wl.step(gather=True)
-        if rank == 0:
-            host_main.copy_(wl.gathered_main, non_blocking=True)
-            if host_point is not None:
-                host_point.copy_(wl.gathered_point, non_blocking=True)
-        torch.cuda.synchronize()
+        if n:
+            E.lighting_host(wl.ctx, wl.vol, wl.view, desc, planes, outs, n_ao=wl.n_ao, point=wl.lights)   # blocks until the planes are in host memory
     for _ in range(2):
         one()
     dist.barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
         one()
-    dist.barrier()
+        dist.barrier()                      # the frame is complete when every rank's tiles have landed
     dt = (time.perf_counter() - t0) / steps
-    t = torch.tensor([dt, float(h2d)], dtype=torch.float64, device=wl.ctx.torch_device)
+    # every rank's region of the shared frame must equal the device-resident result of that rank (checked by rank 0 through the gather)
+    wl.step(gather=True); torch.cuda.synchronize()
+    counts = [torch.zeros(1, dtype=torch.int64, device=wl.ctx.torch_device) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([n], dtype=torch.int64, device=wl.ctx.torch_device))
+    if rank == 0:
+        g = wl.gathered.cpu().numpy()                                         # (world, n_planes, tiles_padded, th, tw)
+        for r in range(world):
+            nr = int(counts[r].item())
+            pr = nr * wl.gb.tile_h * wl.gb.tile_w
+            want = np.concatenate([g[r, 0, :nr].ravel(), g[r, 1, :nr].ravel()] + ([g[r, 2, :nr].ravel()] if wl.spec else [np.zeros(0, np.float32)]))
+            got = frame_host[r, :2 * pr] if not wl.spec else frame_host[r, :3 * pr]
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"e2e: rank {r}'s tiles in the shared host frame differ from the resident path"
+            if wl.n_point:
+                wantp = g[r, 3:, :nr].reshape(-1)
+                assert np.array_equal(frame_host[r, 3 * pr:(3 + wl.n_point) * pr].view(np.uint32), wantp.view(np.uint32)), f"e2e: rank {r} point planes differ"
+    dist.barrier()
+    torch.cuda.cudart().cudaHostUnregister(mine.data_ptr())
+    del mine, outs, frame_host
+    try:
+        shm.close()
+    except BufferError:
+        pass
+    if rank == 0:
+        shm.unlink()
+    t = torch.tensor([dt, float(h2d), float(d2h)], dtype=torch.float64, device=wl.ctx.torch_device)
     tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     tsum = t.clone(); dist.all_reduce(tsum)
     dt = float(tmax[0].item())
-    return {"value": rays / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(tsum[1].item()), "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3,
-            "api": "pinned shard upload + passes + NCCL all-gather + rank-0 readback"}
+    return {"value": rays / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(tsum[1].item()), "d2h_bytes_per_step": int(tsum[2].item()), "ms_per_step": dt * 1e3,
+            "api": "vxl_lighting_host per rank on its tile shard (pinned host planes in, one shared page-locked host frame out, a barrier per frame)"}
 
 
 def main():
