@@ -194,7 +194,7 @@ def run_ours(args):
     from voxelengine_b200 import engine as E
     from voxelengine_b200.workloads import Workload
 
-    wl = Workload(args.config, rank=rank, world=world, device=local)
+    wl = Workload(args.config, rank=rank, world=world, device=local, gather=args.gather)
     cfg = wl.cfg
     W, H = wl.res
     dev = wl.ctx.torch_device
@@ -247,8 +247,16 @@ def run_ours(args):
     ms_per_step = t_ms / args.steps
     value = rays / (ms_per_step * 1e-3) / 1e6
 
-    if world > 1:   # the gathered stacks carry this rank's own tiles unchanged (outside the timed region)
-        assert torch.equal(wl.gathered_main[rank], wl.out[:3]) and (not wl.n_point or torch.equal(wl.gathered_point[rank], wl.out[3:])), "gather mismatch"
+    if world > 1:   # outside the timed region: what every rank holds after a step
+        if wl.stack is not None:
+            # fused gather: every rank's copy of the stack must equal an NCCL all-gather of the ranks' own tiles
+            from voxelengine_b200.tiles import gather_tiles
+            ref = gather_tiles(wl.out.clone())
+            torch.cuda.synchronize()
+            assert torch.equal(ref, wl.stack.tensor), "fused gather: the stack assembled by peer stores differs from an NCCL all-gather"
+            del ref
+        else:
+            assert torch.equal(wl.gathered_main[rank], wl.out[:3]) and (not wl.n_point or torch.equal(wl.gathered_point[rank], wl.out[3:])), "gather mismatch"
 
     # warm-L2 variant (no flush), reported beside the flushed figure
     ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -424,7 +432,10 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": cfg["name"], "volume_texels": list(wl.texels), "resolution": [W, H],
                        "rays_per_step": int(rays), "probes_per_step": int(probes), "lit_pixels": int(lit),
-                       "parallelism": "1 GPU, whole frame" if world == 1 else f"{world} GPUs, 128x128 screen tiles round-robin, volume replicated, NCCL all-gather of output tiles",
+                       "parallelism": "1 GPU, whole frame" if world == 1 else f"{world} GPUs, 128x128 screen tiles round-robin, volume replicated, " + (
+                           "output tiles gathered INSIDE the pass kernels: every output store repeated into each peer's stack over NVLink peer memory (CUDA IPC), one fence per frame"
+                           if wl.stack is not None else "NCCL all-gather of output tiles"),
+                       "gather": wl.gather_mode,
                        "l2": "flushed between timed steps (256 MiB fill outside the event pairs); per-step working set 128 MiB volume + 100 MB G-buffer + 232 MB outputs",
                        "ms_per_step_warm_l2": ms_warm, "ms_per_step_plain_march_variant0": ms_plain,
                        "probes_that_read_the_volume": int(fetched_probes)},
@@ -563,6 +574,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
+    ap.add_argument("--gather", choices=["auto", "fused", "nccl"], default="auto",
+                    help="N > 1: output-tile exchange -- fused = peer-memory stores from the pass kernels (default on NCCL), nccl = one all-gather after the passes")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: native libraries that write to fd 1 (NCCL prints its version banner there when
     # NCCL_DEBUG is set) are pointed at stderr, Python's print keeps the real stdout

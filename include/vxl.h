@@ -145,6 +145,22 @@ int vxl_stats_read(vxl_ctx* ctx, vxl_stats* out /* HOST */);
 /* number of kernels this library launched on the context since creation (bench gpu_launches) */
 int vxl_launch_count(vxl_ctx* ctx, uint64_t* out /* HOST */);
 
+/* ---- peer memory: the fused output-tile gather (one process per GPU on one node) -------------------------------
+ * The light-pass kernels can repeat every output store at (address + delta[i]): with each peer's copy of the gathered tile stack
+ * mapped into this process through CUDA IPC, delta[i] = peer_i_base - own_base, and a rank's tiles land in every rank's stack by
+ * peer-to-peer stores over NVLink while the pass is still running -- no separate collective moves the planes; a barrier closes
+ * the frame.  vxl_ipc_export / _open / _close wrap cudaIpcGetMemHandle / OpenMemHandle / CloseMemHandle for buffers from
+ * vxl_malloc (peer access is enabled lazily).  vxl_ctx_set_output_mirrors(ctx, 0, NULL) turns mirroring off; vxl_lighting_host
+ * ignores it.  vxl_ctx_set_light_plane_stride: distance in pixels between consecutive light planes of vxl_pass_point / _spot
+ * (0 = the shard's own n_tiles * tile_h * tile_w), so a rank can write straight into a stack padded to the largest shard. */
+#define VXL_MAX_MIRRORS 15
+typedef struct vxl_ipc_handle { unsigned char bytes[64]; } vxl_ipc_handle;
+int vxl_ipc_export(vxl_ctx* ctx, void* dev, vxl_ipc_handle* out /* HOST */);
+int vxl_ipc_open(vxl_ctx* ctx, const vxl_ipc_handle* handle /* HOST */, void** out_dev);
+int vxl_ipc_close(vxl_ctx* ctx, void* dev);
+int vxl_ctx_set_output_mirrors(vxl_ctx* ctx, int n, const int64_t* byte_deltas /* HOST */);
+int vxl_ctx_set_light_plane_stride(vxl_ctx* ctx, uint64_t pixels);
+
 /* diagnostics (no reference counterpart): kernel variant 0 = plain march on the volume bytes, 1 = march
  * against the per-block occupancy-bit tile in shared memory (default; also env VXL_VARIANT), 2 = variant 1
  * that also counts the probes that had to read the volume; all produce identical results.

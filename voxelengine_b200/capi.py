@@ -24,6 +24,7 @@ SYMBOLS = [
     "vxl_asset_guid", "vxl_vox_file_read", "vxl_model_load_v", "vxl_pallete_file_read", "vxl_prefab_file_read", "vxl_scene_load",
     "vxl_vox_import", "vxl_vox_import_memory", "vxl_vox_scene_counts", "vxl_vox_scene_entities", "vxl_vox_scene_model",
     "vxl_vox_scene_pallete", "vxl_vox_scene_write", "vxl_vox_scene_free",
+    "vxl_ipc_export", "vxl_ipc_open", "vxl_ipc_close", "vxl_ctx_set_output_mirrors", "vxl_ctx_set_light_plane_stride",
 ]
 
 VXL_MAX_LIGHTS = 64
@@ -108,6 +109,8 @@ def load():
         "vxl_asset_guid": [C.c_char_p, P(C.c_uint64)], "vxl_vox_file_read": [C.c_char_p, vp, vp, C.c_uint64],
         "vxl_model_load_v": [vp, C.c_char_p, P(C.c_int)], "vxl_pallete_file_read": [C.c_char_p, vp, vp],
         "vxl_prefab_file_read": [C.c_char_p, vp, i32, P(C.c_int)], "vxl_scene_load": [C.c_char_p, C.c_char_p, vp, i32, P(C.c_int)],
+        "vxl_ipc_export": [vp, vp, vp], "vxl_ipc_open": [vp, vp, P(vp)], "vxl_ipc_close": [vp, vp],
+        "vxl_ctx_set_output_mirrors": [vp, i32, vp], "vxl_ctx_set_light_plane_stride": [vp, C.c_uint64],
         "vxl_vox_import": [C.c_char_p, P(vp)], "vxl_vox_import_memory": [vp, C.c_uint64, P(vp)],
         "vxl_vox_scene_counts": [vp, P(C.c_int), P(C.c_int)], "vxl_vox_scene_entities": [vp, vp, i32],
         "vxl_vox_scene_model": [vp, i32, vp, vp, vp, C.c_uint64], "vxl_vox_scene_pallete": [vp, vp],

@@ -34,6 +34,8 @@ int frame_view(const vxl_frame* f, FrameView* out) {
     out->width = f->width; out->height = f->height; out->tile_w = f->tile_w; out->tile_h = f->tile_h;
     out->tile_first = f->tile_first; out->tile_stride = f->tile_stride; out->n_tiles = f->n_tiles; out->tiles_x = tiles_x;
     out->row0 = 0; out->rows = f->tile_h;
+    out->n_mirror = 0;
+    for (int i = 0; i < 15; ++i) out->mirror[i] = 0;
     out->depth24 = f->depth24; out->normal = f->normal; out->material = f->material; out->noise = f->noise;
     return VXL_OK;
 }
@@ -104,6 +106,7 @@ int vxl_ctx_destroy(vxl_ctx* c) {
     if (!c) return VXL_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    for (void* p : c->ipc_open) cudaIpcCloseMemHandle(p);
     cudaFree(c->d_stats); cudaFree(c->d_luts); cudaFree(c->d_taa_lut); cudaFree(c->d_lights); cudaFree(c->d_perm);
     for (auto& m : c->models) { cudaFree((void*)m.voxels); cudaFree((void*)m.mip1); cudaFree((void*)m.mip2); }
     cudaFree(c->d_models); cudaFree(c->d_draws); cudaFree(c->d_hkeys); cudaFree(c->d_hvals); cudaFree(c->d_ents); cudaFree(c->d_aabb);
@@ -120,6 +123,57 @@ int vxl_ctx_set_stream(vxl_ctx* c, void* s) {
     VXL_CUDA(cudaStreamSynchronize(c->stream));
     if (c->own_stream) { cudaStreamDestroy(c->stream); c->own_stream = false; }
     c->stream = (cudaStream_t)s;
+    return VXL_OK;
+}
+
+// ---- peer memory: one process per GPU on one node ---------------------------------------------------------------
+int vxl_ipc_export(vxl_ctx* c, void* dev, vxl_ipc_handle* out) {
+    if (!c || !dev || !out) { set_error("vxl_ipc_export: bad argument"); return VXL_ERR_INVALID; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == sizeof(vxl_ipc_handle), "vxl_ipc_handle must hold a cudaIpcMemHandle_t");
+    VXL_CUDA(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    VXL_CUDA(cudaIpcGetMemHandle(&h, dev));
+    memcpy(out->bytes, &h, sizeof h);
+    return VXL_OK;
+}
+
+int vxl_ipc_open(vxl_ctx* c, const vxl_ipc_handle* handle, void** out_dev) {
+    if (!c || !handle || !out_dev) { set_error("vxl_ipc_open: bad argument"); return VXL_ERR_INVALID; }
+    VXL_CUDA(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle->bytes, sizeof h);
+    void* p = nullptr;
+    VXL_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->ipc_open.push_back(p);
+    *out_dev = p;
+    return VXL_OK;
+}
+
+int vxl_ipc_close(vxl_ctx* c, void* dev) {
+    if (!c || !dev) { set_error("vxl_ipc_close: bad argument"); return VXL_ERR_INVALID; }
+    for (size_t i = 0; i < c->ipc_open.size(); ++i)
+        if (c->ipc_open[i] == dev) {
+            c->ipc_open.erase(c->ipc_open.begin() + (long)i);
+            VXL_CUDA(cudaStreamSynchronize(c->stream));
+            VXL_CUDA(cudaIpcCloseMemHandle(dev));
+            return VXL_OK;
+        }
+    set_error("vxl_ipc_close: not a mapping opened by this context");
+    return VXL_ERR_INVALID;
+}
+
+int vxl_ctx_set_output_mirrors(vxl_ctx* c, int n, const int64_t* byte_deltas) {
+    if (!c || n < 0 || n > VXL_MAX_MIRRORS || (n > 0 && !byte_deltas)) { set_error("vxl_ctx_set_output_mirrors: bad argument (at most VXL_MAX_MIRRORS mirrors)"); return VXL_ERR_INVALID; }
+    for (int i = 0; i < n; ++i)
+        if (byte_deltas[i] % 4 != 0) { set_error("vxl_ctx_set_output_mirrors: deltas must be multiples of 4 bytes"); return VXL_ERR_INVALID; }
+    c->n_mirror = n;
+    for (int i = 0; i < n; ++i) c->mirror[i] = (long long)byte_deltas[i];
+    return VXL_OK;
+}
+
+int vxl_ctx_set_light_plane_stride(vxl_ctx* c, uint64_t pixels) {
+    if (!c) { set_error("vxl_ctx_set_light_plane_stride: ctx is NULL"); return VXL_ERR_INVALID; }
+    c->light_plane_stride = (size_t)pixels;
     return VXL_OK;
 }
 
@@ -230,6 +284,9 @@ int vxl_lighting_host(vxl_ctx* c, vxl_volume* vol, const vxl_lighting_host_args*
     const bool want_sp = a->n_spot > 0 && a->out_spot_shadow;
     const bool want_rf = a->out_spec_t != nullptr;
     if (want_rf && !a->frame.material) { set_error("vxl_lighting_host: spec pass needs frame.material"); return VXL_ERR_INVALID; }
+    // the host drop-in writes to its own staging planes: no mirrored stores, default plane stride (restored on every exit path)
+    struct Restore { vxl_ctx* c; int n; size_t st; ~Restore() { c->n_mirror = n; c->light_plane_stride = st; } } restore{c, c->n_mirror, c->light_plane_stride};
+    c->n_mirror = 0; c->light_plane_stride = 0;
     VXL_CUDA(cudaSetDevice(c->device));
     if (int e = ensure((void**)&c->h_planes, &c->h_planes_bytes, px * 4 * 3)) return e;
     const size_t n_out = 3 + (size_t)a->n_point + (size_t)a->n_spot;

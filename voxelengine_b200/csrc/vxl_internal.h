@@ -36,6 +36,10 @@ struct FrameView {
     const uint32_t* __restrict__ normal;
     const uint32_t* __restrict__ material;
     const uint32_t* __restrict__ noise;
+    // multi-GPU: every output store of the light-pass kernels is repeated at (address + mirror[i]) -- the same offset inside each
+    // peer's copy of the gathered tile stack, mapped through CUDA IPC (vxl_ctx_set_output_mirrors); 0 on one GPU
+    int n_mirror;
+    long long mirror[15];
 };
 
 struct ModelDev { const uint8_t* voxels; int sx, sy, sz; unsigned solid; const uint8_t* mip1; const uint8_t* mip2; };   // mips: VoxAsset::Upload's chain, built on first use
@@ -76,6 +80,10 @@ struct vxl_ctx {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // copy streams of vxl_lighting_host (uploads / read-backs overlap the passes)
     std::vector<cudaEvent_t> ev;
     int band_row0 = 0, band_rows = 0;                // > 0 rows: the pass entry points cover this row band of every tile only
+    int n_mirror = 0;                                // vxl_ctx_set_output_mirrors
+    long long mirror[15] = {0};
+    size_t light_plane_stride = 0;                   // vxl_ctx_set_light_plane_stride (pixels; 0 = the shard's own size)
+    std::vector<void*> ipc_open;                     // peer mappings to close with the context
 };
 
 struct vxl_volume {

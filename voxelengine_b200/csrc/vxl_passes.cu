@@ -139,8 +139,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_ambient(VolV
     const BitTile C = block_prologue<(MODE > 0), G>(V, S, lit, wcp0 + normal * bias);
     unsigned rays = 0, pixels = 0, exact = 0;
     int steps = 0;
+    float shadow = 1.0f, ao = 0.0f;
     if (p.valid) {
-        float shadow = 1.0f, ao = 0.0f;
         if (lit) {
             float3 wd = normalize3(make_float3(0.3f, 0.4f, 0.5f));                     // SUN_DIR :15,:149
             float3 wcp = wcp0;
@@ -182,8 +182,16 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_ambient(VolV
             }
             pixels = 1;
         }
-        if (out_shadow) out_shadow[p.idx] = shadow;
-        if (out_ao) out_ao[p.idx] = ao;
+        if (F.n_mirror == 0) {
+            if (out_shadow) out_shadow[p.idx] = shadow;
+            if (out_ao) out_ao[p.idx] = ao;
+        }
+    }
+    if (F.n_mirror) {                                   // several GPUs: row-major write-out into every copy of the stack (vxl_pixel.cuh)
+        __syncthreads();                                // the LUTs are no longer read: their 4 KB become the staging planes
+        float* const planes[2] = {out_shadow, out_ao};
+        const float vals[2] = {shadow, ao};
+        store_rows<2>(F, S.lut, planes, vals);
     }
     flush_stats(S, g_stats, rays, (unsigned)steps, pixels, exact);
 }
@@ -225,6 +233,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_local_lights
     const BitTile C = block_prologue<(MODE > 0), G>(V, S, hint_ok, worldPos * 10.0f);
     unsigned rays = 0, pixels = 0, exact = 0;
     int steps = 0;
+    unsigned long long shadowed = 0ull;                  // bit li: light li is occluded at this pixel (the mirrored write-out below)
     if (p.valid) {
         const uint32_t n = get_noise(F, K, p, -1);
         float3 rv0 = cosine_sample_hemisphere(S.lut, n, n >> 8) * 0.1f;                      // :111
@@ -249,7 +258,16 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_local_lights
                 rays += 1;
                 pixels = 1;
             }
-            out_shadow[(size_t)li * plane_stride + p.idx] = shadow;
+            if (F.n_mirror == 0) out_shadow[(size_t)li * plane_stride + p.idx] = shadow;
+            else if (shadow == 0.0f) shadowed |= 1ull << li;
+        }
+    }
+    if (F.n_mirror) {                                   // several GPUs: two light planes per round through the LUTs' 4 KB
+        for (int li = 0; li < n_lights; li += 2) {
+            __syncthreads();
+            float* const planes[2] = {out_shadow + (size_t)li * plane_stride, li + 1 < n_lights ? out_shadow + (size_t)(li + 1) * plane_stride : nullptr};
+            const float vals[2] = {(shadowed >> li) & 1ull ? 0.0f : 1.0f, (shadowed >> (li + 1)) & 1ull ? 0.0f : 1.0f};
+            store_rows<2>(F, S.lut, planes, vals);
         }
     }
     flush_stats(S, g_stats, rays, (unsigned)steps, pixels, exact);
@@ -281,8 +299,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_reflection(V
     const BitTile C = block_prologue<(MODE > 0), G>(V, S, lit, wcp0 + normal);
     unsigned rays = 0, pixels = 0, exact = 0;
     int steps = 0;
+    float t = 256.0f;
     if (p.valid) {
-        float t = 256.0f;
         if (lit) {
             const float roughness = unorm8(__ldg(F.material + p.idx));                       // :68
             const float3 Vv = normalize3(pos) * -1.0f;                                       // :79
@@ -301,7 +319,13 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_reflection(V
             t = ray_march<MODE, false, false, G>(V, C, wcp + normal, wd, 256.0f, steps, exact);        // :113
             rays = 1; pixels = 1;
         }
-        out_t[p.idx] = t;
+        if (F.n_mirror == 0) out_t[p.idx] = t;
+    }
+    if (F.n_mirror) {
+        __syncthreads();
+        float* const planes[1] = {out_t};
+        const float vals[1] = {t};
+        store_rows<1>(F, S.lut, planes, vals);
     }
     flush_stats(S, g_stats, rays, (unsigned)steps, pixels, exact);
 }
@@ -344,6 +368,7 @@ int vxl_pass_ambient(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, const 
     FrameView F;
     if (int e = frame_view(frame, &F)) return e;
     apply_band(ctx, F);
+    apply_mirrors(ctx, F);
     if (!out_shadow && !out_ao) return VXL_OK;
     if (F.n_tiles == 0) return VXL_OK;
     if (vol->dirty) { if (int e = vxl_volume_build_occupancy(vol)) return e; }
@@ -369,10 +394,11 @@ static int local_lights(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, con
     FrameView F;
     if (int e = frame_view(frame, &F)) return e;
     apply_band(ctx, F);
+    apply_mirrors(ctx, F);
     if (n_lights == 0 || F.n_tiles == 0) return VXL_OK;
     if (vol->dirty) { if (int e = vxl_volume_build_occupancy(vol)) return e; }
     VXL_CUDA(cudaMemcpyAsync(ctx->d_lights, lights, (size_t)n_lights * light_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    const size_t plane = frame_pixels(frame);
+    const size_t plane = ctx->light_plane_stride ? ctx->light_plane_stride : frame_pixels(frame);
 #define VXL_LL(SPOT_, MODE_)                                                                                                              \
     do {                                                                                                                              \
         if (MODE_) VXL_CUDA(cudaFuncSetAttribute(k_local_lights<SPOT_, MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<LocalGeom, (MODE_ > 0)>())); \
@@ -402,6 +428,7 @@ int vxl_pass_reflection(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, con
     FrameView F;
     if (int e = frame_view(frame, &F)) return e;
     apply_band(ctx, F);
+    apply_mirrors(ctx, F);
     if (!F.material) { set_error("vxl_pass_reflection: frame.material is NULL"); return VXL_ERR_INVALID; }
     if (F.n_tiles == 0) return VXL_OK;
     if (vol->dirty) { if (int e = vxl_volume_build_occupancy(vol)) return e; }

@@ -107,6 +107,53 @@ static inline void apply_band(const vxl_ctx* ctx, FrameView& F) {
     if (ctx->band_rows > 0) { F.row0 = ctx->band_row0; F.rows = ctx->band_rows < F.tile_h - F.row0 ? ctx->band_rows : F.tile_h - F.row0; }
 }
 
+static inline void apply_mirrors(const vxl_ctx* ctx, FrameView& F) {
+    F.n_mirror = ctx->n_mirror;
+    for (int i = 0; i < 15; ++i) F.mirror[i] = i < ctx->n_mirror ? ctx->mirror[i] : 0;
+}
+
+// one output value of a light pass: the rank's own plane and, on several GPUs, the same slot of every peer's gathered stack
+// (peer-to-peer stores over NVLink, issued while the block's other warps are still marching: the transfer hides under the pass)
+__device__ __forceinline__ void store_out(const FrameView& F, float* p, float v) {
+    *p = v;
+    for (int i = 0; i < F.n_mirror; ++i) *reinterpret_cast<float*>(reinterpret_cast<char*>(p) + F.mirror[i]) = v;
+}
+
+// Multi-GPU write-out.  A warp covers an 8x4 pixel patch (coherent rays), i.e. four 32-byte pieces per plane: fine for local
+// HBM, poor for NVLink, where every piece is a packet.  With mirrors on, the block first parks its values in shared memory and
+// writes them back row-major: one warp = one 32-pixel row = one 128-byte store per plane and per copy of the stack.
+// block_pixel: plane index of the pixel at (x, y) inside this block's 32x16 rectangle (false = outside the shard).
+__device__ __forceinline__ bool block_pixel(const FrameView& F, int x, int y, size_t& idx) {
+    const int bpt_x = (F.tile_w + BLOCK_W - 1) / BLOCK_W, bpt_y = (F.rows + BLOCK_H - 1) / BLOCK_H;
+    const int bpt = bpt_x * bpt_y;
+    const int lt = blockIdx.x / bpt, b = blockIdx.x - lt * bpt;
+    const int by = b / bpt_x, bx = b - by * bpt_x;
+    const int lx = bx * BLOCK_W + x, lb = by * BLOCK_H + y, ly = F.row0 + lb;
+    const int gt = F.tile_first + lt * F.tile_stride;
+    const int ty = gt / F.tiles_x, tx = gt - ty * F.tiles_x;
+    idx = ((size_t)lt * F.tile_h + ly) * F.tile_w + lx;
+    return lx < F.tile_w && lb < F.rows && ly < F.tile_h && tx * F.tile_w + lx < F.width && ty * F.tile_h + ly < F.height && lt < F.n_tiles;
+}
+// slot of this thread's own pixel in a 16x32 row-major staging plane (the inverse of pixel_ctx's warp layout)
+__device__ __forceinline__ int own_slot() {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    return ((warp >> 2) * 4 + (lane >> 3)) * BLOCK_W + (warp & 3) * 8 + (lane & 7);
+}
+// NPL <= 2 planes through `stage` (>= NPL * 512 floats of shared memory no warp still reads: the caller's barrier comes first)
+template <int NPL>
+__device__ __forceinline__ void store_rows(const FrameView& F, float* stage, float* const (&planes)[NPL], const float (&vals)[NPL]) {
+    const int slot = own_slot();
+#pragma unroll
+    for (int k = 0; k < NPL; ++k) stage[k * BLOCK_THREADS + slot] = vals[k];
+    __syncthreads();
+    size_t idx;
+    if (block_pixel(F, (int)(threadIdx.x & 31), (int)(threadIdx.x >> 5), idx)) {
+#pragma unroll
+        for (int k = 0; k < NPL; ++k)
+            if (planes[k]) store_out(F, planes[k] + idx, stage[k * BLOCK_THREADS + threadIdx.x]);
+    }
+}
+
 static inline unsigned grid_for(const FrameView& F) {
     const int bpt_x = (F.tile_w + BLOCK_W - 1) / BLOCK_W, bpt_y = (F.rows + BLOCK_H - 1) / BLOCK_H;
     return (unsigned)(bpt_x * bpt_y * F.n_tiles);

@@ -80,6 +80,50 @@ class Context:
         check(self.lib.vxl_launch_count(self.h, C.byref(n)), "vxl_launch_count")
         return int(n.value)
 
+    # -- raw device memory and peer mappings (the fused output-tile gather, tiles.PeerStack) --
+    def malloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        check(self.lib.vxl_malloc(self.h, int(nbytes), C.byref(p)), "vxl_malloc")
+        return int(p.value)
+
+    def free(self, ptr: int):
+        check(self.lib.vxl_free(self.h, C.c_void_p(ptr)), "vxl_free")
+
+    def memset(self, ptr: int, value: int, nbytes: int):
+        check(self.lib.vxl_memset(self.h, C.c_void_p(ptr), int(value), int(nbytes)), "vxl_memset")
+
+    def ipc_export(self, ptr: int) -> bytes:
+        h = (C.c_ubyte * 64)()
+        check(self.lib.vxl_ipc_export(self.h, C.c_void_p(ptr), C.byref(h)), "vxl_ipc_export")
+        return bytes(h)
+
+    def ipc_open(self, handle: bytes) -> int:
+        h = (C.c_ubyte * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        check(self.lib.vxl_ipc_open(self.h, C.byref(h), C.byref(p)), "vxl_ipc_open")
+        return int(p.value)
+
+    def ipc_close(self, ptr: int):
+        check(self.lib.vxl_ipc_close(self.h, C.c_void_p(ptr)), "vxl_ipc_close")
+
+    def set_output_mirrors(self, byte_deltas):
+        """Every output store of the light-pass kernels is repeated at address + delta (vxl_ctx_set_output_mirrors); [] = off."""
+        d = np.ascontiguousarray(byte_deltas, dtype=np.int64)
+        check(self.lib.vxl_ctx_set_output_mirrors(self.h, len(d), _np_ptr(d) if len(d) else None), "vxl_ctx_set_output_mirrors")
+
+    def set_light_plane_stride(self, pixels: int):
+        check(self.lib.vxl_ctx_set_light_plane_stride(self.h, int(pixels)), "vxl_ctx_set_light_plane_stride")
+
+    def tensor_view(self, ptr: int, shape, dtype="float32"):
+        """A torch tensor over raw device memory of this context's GPU (no copy; the caller keeps the memory alive)."""
+        torch = _torch()
+
+        class _Raw:
+            pass
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {"shape": tuple(int(v) for v in shape), "typestr": np.dtype(dtype).str, "data": (int(ptr), False), "version": 2}
+        return torch.as_tensor(raw, device=self.torch_device)
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.vxl_ctx_destroy(self.h)

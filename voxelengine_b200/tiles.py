@@ -66,3 +66,55 @@ def gather_tiles(local, group=None, out=None):
         out = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out.view(-1), local.contiguous().view(-1), group=group)
     return out
+
+
+def mirror_deltas(bases, rank):
+    """Byte deltas from rank's own copy of the gathered stack to every peer's copy, as mapped in THIS process: a store at
+    own_base + off repeated at own_base + off + delta lands at the same offset of the peer's stack."""
+    return [int(b) - int(bases[rank]) for r, b in enumerate(bases) if r != rank]
+
+
+class PeerStack:
+    """The gathered tile stack (world, planes, tiles_padded, tile_h, tile_w), one copy per rank in vxl_malloc'ed memory, every
+    copy mapped into every process through CUDA IPC.  With the mirrors enabled the light-pass kernels store each output value into
+    all copies -- the rank's own slot of its own stack and, by peer-to-peer stores over NVLink, the same slot of every peer's -- so
+    the all-gather of SURVEY 8e happens inside the passes; `fence()` (one tiny stream-ordered all-reduce) closes the frame."""
+
+    def __init__(self, ctx, shape_per_rank, rank, world, group=None):
+        import torch
+        import torch.distributed as dist
+        self.ctx, self.rank, self.world, self.group = ctx, int(rank), int(world), group
+        self.shape = (world,) + tuple(int(v) for v in shape_per_rank)
+        self.nbytes = int(np.prod(self.shape)) * 4
+        self.base = ctx.malloc(self.nbytes)
+        ctx.memset(self.base, 0, self.nbytes)
+        ctx.sync()
+        handles = [None] * world
+        dist.all_gather_object(handles, ctx.ipc_export(self.base), group=group)
+        self.mapped = [self.base if r == rank else ctx.ipc_open(handles[r]) for r in range(world)]
+        self.deltas = mirror_deltas(self.mapped, rank)
+        self.tensor = ctx.tensor_view(self.base, self.shape)          # (world, planes, tiles_padded, th, tw)
+        self._fence = torch.zeros(1, dtype=torch.float32, device=ctx.torch_device)
+        dist.barrier(group=group)                                     # every copy is zeroed and mapped before anyone stores into it
+
+    def enable(self):
+        self.ctx.set_output_mirrors(self.deltas)
+
+    def disable(self):
+        self.ctx.set_output_mirrors([])
+
+    def fence(self):
+        """Stream-ordered: returns (on the stream) once every rank's passes, and with them their peer stores, have completed."""
+        import torch.distributed as dist
+        dist.all_reduce(self._fence, group=self.group)
+
+    def close(self):
+        import torch.distributed as dist
+        self.disable()
+        self.ctx.sync()
+        dist.barrier(group=self.group)                                # nobody is still storing into a copy that is about to go
+        self.tensor = None
+        for r, p in enumerate(self.mapped):
+            if r != self.rank:
+                self.ctx.ipc_close(p)
+        self.ctx.free(self.base)

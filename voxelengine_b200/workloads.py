@@ -27,8 +27,11 @@ CONFIGS = {
 
 class Workload:
     def __init__(self, config: int, rank: int = 0, world: int = 1, device: int | None = None, tile=(128, 128),
-                 scale: float = 1.0, frame_index: int = 0):
-        """scale < 1 shrinks volume and resolution proportionally (tests only; the bench uses 1.0)."""
+                 scale: float = 1.0, frame_index: int = 0, gather: str = "auto"):
+        """scale < 1 shrinks volume and resolution proportionally (tests only; the bench uses 1.0).
+        gather: how the output tiles of world > 1 are exchanged -- "fused": the pass kernels store every output value into all
+        ranks' stacks over peer memory (tiles.PeerStack); "nccl": one all-gather after the passes; "auto": fused when
+        torch.distributed runs on NCCL, else nccl (also: no process group, e.g. shards run one after another on one GPU)."""
         import torch
         self.torch = torch
         cfg = dict(CONFIGS[config])
@@ -56,9 +59,20 @@ class Workload:
         total_tiles = self.gb.tiles_x * self.gb.tiles_y
         self.tiles_padded = -(-total_tiles // world)
         self.n_planes = 3 + self.n_point
-        self.out = torch.zeros((self.n_planes, self.tiles_padded, self.gb.tile_h, self.gb.tile_w), dtype=torch.float32,
-                               device=self.ctx.torch_device)
         self.gathered_main = self.gathered_point = None      # (world, 3, tiles, th, tw) / (world, n_point, tiles, th, tw)
+        self.stack = None
+        if gather == "auto":
+            import torch.distributed as dist
+            gather = "fused" if world > 1 and dist.is_available() and dist.is_initialized() and dist.get_backend() == "nccl" else "nccl"
+        self.gather_mode = gather if world > 1 else "none"
+        if world > 1 and gather == "fused":
+            from .tiles import PeerStack
+            self.stack = PeerStack(self.ctx, (self.n_planes, self.tiles_padded, self.gb.tile_h, self.gb.tile_w), rank, world)
+            self.out = self.stack.tensor[rank]                # this rank's slot of its own copy; the mirrors fill the peers' copies
+            self.gathered_main, self.gathered_point = self.stack.tensor[:, :3], self.stack.tensor[:, 3:]
+        else:
+            self.out = torch.zeros((self.n_planes, self.tiles_padded, self.gb.tile_h, self.gb.tile_w), dtype=torch.float32,
+                                   device=self.ctx.torch_device)
         self._side = torch.cuda.Stream(device=self.ctx.torch_device) if world > 1 else None
         self.ctx.sync()
 
@@ -126,6 +140,23 @@ class Workload:
         o = self.out
         torch = self.torch
         gather = gather and self.world > 1
+        if self.stack is not None:
+            # fused gather: the passes write this rank's tiles into every rank's stack (peer-to-peer stores); one fence ends the frame.
+            # Mirrors and the padded plane stride are on only here, where every output pointer lies inside the stack.
+            self.stack.enable()
+            self.ctx.set_light_plane_stride(self.tiles_padded * self.gb.tile_h * self.gb.tile_w)
+            try:
+                if self.n_point:
+                    self._point(o[3:])
+                E.LightAmbientPipeline.Get().Use(self.view, self.gb, self.vol, n_ao=self.n_ao, out_shadow=o[0, :n], out_ao=o[1, :n])
+                if self.spec:
+                    E.LightReflectionPipeline.Get().Use(self.view, self.gb, self.vol, out_spec_t=o[2, :n])
+            finally:
+                self.stack.disable()
+                self.ctx.set_light_plane_stride(0)
+            if gather:
+                self.stack.fence()
+            return self.out
         if gather:
             from .tiles import gather_tiles
         if self.n_point:
@@ -203,5 +234,9 @@ class Workload:
         return self.gb.layout.assemble(g)
 
     def close(self):
+        if self.stack is not None:
+            self.out = self.gathered_main = self.gathered_point = None
+            self.stack.close()
+            self.stack = None
         self.vol.close()
         self.ctx.close()
