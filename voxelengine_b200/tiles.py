@@ -74,6 +74,10 @@ def mirror_deltas(bases, rank):
     return [int(b) - int(bases[rank]) for r, b in enumerate(bases) if r != rank]
 
 
+class PeerStackUnavailable(RuntimeError):
+    pass
+
+
 class PeerStack:
     """The gathered tile stack (world, planes, tiles_padded, tile_h, tile_w), one copy per rank in vxl_malloc'ed memory, every
     copy mapped into every process through CUDA IPC.  With the mirrors enabled the light-pass kernels store each output value into
@@ -91,7 +95,22 @@ class PeerStack:
         ctx.sync()
         handles = [None] * world
         dist.all_gather_object(handles, ctx.ipc_export(self.base), group=group)
-        self.mapped = [self.base if r == rank else ctx.ipc_open(handles[r]) for r in range(world)]
+        self.mapped, err = [self.base if r == rank else 0 for r in range(world)], None
+        try:
+            for r in range(world):
+                if r != rank:
+                    self.mapped[r] = ctx.ipc_open(handles[r])
+        except Exception as e:                                        # no peer access between two of the GPUs, IPC disabled, ...
+            err = e
+        ok = torch.tensor([0.0 if err else 1.0], device=ctx.torch_device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)        # all ranks take the same decision
+        if float(ok.item()) == 0.0:
+            for r, p in enumerate(self.mapped):
+                if r != rank and p:
+                    ctx.ipc_close(p)
+            dist.barrier(group=group)
+            ctx.free(self.base)
+            raise PeerStackUnavailable(f"peer mapping failed on at least one rank ({err})")
         self.deltas = mirror_deltas(self.mapped, rank)
         self.tensor = ctx.tensor_view(self.base, self.shape)          # (world, planes, tiles_padded, th, tw)
         self._fence = torch.zeros(1, dtype=torch.float32, device=ctx.torch_device)

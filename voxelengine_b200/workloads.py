@@ -61,13 +61,20 @@ class Workload:
         self.n_planes = 3 + self.n_point
         self.gathered_main = self.gathered_point = None      # (world, 3, tiles, th, tw) / (world, n_point, tiles, th, tw)
         self.stack = None
-        if gather == "auto":
+        auto = gather == "auto"
+        if auto:
             import torch.distributed as dist
             gather = "fused" if world > 1 and dist.is_available() and dist.is_initialized() and dist.get_backend() == "nccl" else "nccl"
-        self.gather_mode = gather if world > 1 else "none"
         if world > 1 and gather == "fused":
-            from .tiles import PeerStack
-            self.stack = PeerStack(self.ctx, (self.n_planes, self.tiles_padded, self.gb.tile_h, self.gb.tile_w), rank, world)
+            from .tiles import PeerStack, PeerStackUnavailable
+            try:
+                self.stack = PeerStack(self.ctx, (self.n_planes, self.tiles_padded, self.gb.tile_h, self.gb.tile_w), rank, world)
+            except PeerStackUnavailable:
+                if not auto:
+                    raise
+                gather = "nccl"                                   # every rank reaches the same decision (PeerStack agrees on it collectively)
+        self.gather_mode = gather if world > 1 else "none"
+        if self.stack is not None:
             self.out = self.stack.tensor[rank]                # this rank's slot of its own copy; the mirrors fill the peers' copies
             self.gathered_main, self.gathered_point = self.stack.tensor[:, :3], self.stack.tensor[:, 3:]
         else:
