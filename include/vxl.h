@@ -379,6 +379,11 @@ typedef struct vxl_lighting_host_args {
     float* out_spec_t;               /* [tiles] */
 } vxl_lighting_host_args;
 int vxl_lighting_host(vxl_ctx* ctx, vxl_volume* vol, const vxl_lighting_host_args* args);
+/* The same frame with DEVICE pointers throughout (frame planes, outputs; view and lights stay HOST): the ambient pass on the context's
+ * stream, the local-light passes and the reflection pass on two side streams forked from it and joined back before the call returns
+ * (stream-ordered, asynchronous).  The passes are independent, so the tail of one kernel overlaps the head of the next.  Same
+ * results as the single vxl_pass_* calls; output mirrors and the light plane stride apply. */
+int vxl_lighting(vxl_ctx* ctx, vxl_volume* vol, const vxl_lighting_host_args* args);
 
 /* ---- synthetic inputs (not reference passes) ------------------------------------- */
 /* FastNoise-Perlin terrain: voxel solid iff GetTerrainNoise(x,y,z) > (y/NY - 0.5)*2

@@ -17,7 +17,7 @@ SYMBOLS = [
     "vxl_volume_upload", "vxl_volume_download", "vxl_volume_clear", "vxl_volume_device_ptr",
     "vxl_volume_mark_dirty", "vxl_volume_build_occupancy", "vxl_model_create", "vxl_volume_voxelize",
     "vxl_pass_ambient", "vxl_pass_point", "vxl_pass_spot", "vxl_pass_reflection", "vxl_trace_rays",
-    "vxl_lighting_host", "vxl_volume_gen_terrain", "vxl_gbuffer_primary",
+    "vxl_lighting_host", "vxl_lighting", "vxl_volume_gen_terrain", "vxl_gbuffer_primary",
     "vxl_debug_set_variant", "vxl_debug_fetched_probes", "vxl_volume_debug_occupancy",
     "vxl_resolve_ambient", "vxl_resolve_point", "vxl_resolve_spot", "vxl_trace_model_rays", "vxl_gbuffer_models",
     "vxl_light_taa", "vxl_resolve_reflection",
@@ -116,7 +116,7 @@ def load():
         "vxl_vox_scene_model": [vp, i32, vp, vp, vp, C.c_uint64], "vxl_vox_scene_pallete": [vp, vp],
         "vxl_vox_scene_write": [vp, C.c_char_p, C.c_char_p, C.c_char_p], "vxl_vox_scene_free": [vp],
         "vxl_resolve_reflection": [vp, vp, P(Frame), vp, vp, vp, vp, vp],
-        "vxl_lighting_host": [vp, vp, P(LightingHostArgs)],
+        "vxl_lighting_host": [vp, vp, P(LightingHostArgs)], "vxl_lighting": [vp, vp, P(LightingHostArgs)],
         "vxl_volume_gen_terrain": [vp], "vxl_gbuffer_primary": [vp, vp, vp, P(Frame)],
         "vxl_debug_set_variant": [vp, i32], "vxl_debug_fetched_probes": [vp, P(C.c_uint64)],
         "vxl_volume_debug_occupancy": [vp, i32, vp, vp],

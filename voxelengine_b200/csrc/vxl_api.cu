@@ -272,6 +272,51 @@ static int ensure(void** p, size_t* cap, size_t need) {
     return VXL_OK;
 }
 
+// All requested passes of one frame with DEVICE planes, the three kernels side by side: the ambient pass on the context's stream,
+// the local-light passes and the reflection pass on two side streams forked from it and joined back before the call returns
+// (stream-ordered; nothing blocks).  The passes are independent (same inputs, disjoint output planes), so a kernel's last,
+// partially filled wave of blocks overlaps the next kernel's first -- which matters when a rank's share of a frame is only a few
+// waves (8 GPUs: 4.6 waves per kernel).  Mirrors and the light plane stride apply as in the single passes.
+int vxl_lighting(vxl_ctx* c, vxl_volume* vol, const vxl_lighting_host_args* a) {
+    if (!c || !vol || !a || !a->view) { set_error("vxl_lighting: bad argument"); return VXL_ERR_INVALID; }
+    if (a->n_point < 0 || a->n_spot < 0 || a->n_point > VXL_MAX_LIGHTS || a->n_spot > VXL_MAX_LIGHTS) { set_error("vxl_lighting: light count out of range"); return VXL_ERR_LIMIT; }
+    const bool want_amb = a->out_shadow || a->out_ao;
+    const bool want_pt = a->n_point > 0 && a->out_point_shadow;
+    const bool want_sp = a->n_spot > 0 && a->out_spot_shadow;
+    const bool want_rf = a->out_spec_t != nullptr;
+    VXL_CUDA(cudaSetDevice(c->device));
+    if (vol->dirty) { if (int e = vxl_volume_build_occupancy(vol)) return e; }       // once, before the fork
+    if (!c->s_h2d) {
+        VXL_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+        VXL_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    }
+    while (c->ev.size() < 3) { cudaEvent_t e; VXL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->ev.push_back(e); }
+    cudaEvent_t* ev = c->ev.data();
+    cudaStream_t main = c->stream, side[2] = {c->s_h2d, c->s_d2h};
+    struct Restore { vxl_ctx* c; cudaStream_t s; ~Restore() { c->stream = s; } } restore{c, main};
+    VXL_CUDA(cudaEventRecord(ev[0], main));
+    int rc = VXL_OK;
+    if (want_amb) rc = vxl_pass_ambient(c, vol, a->view, &a->frame, a->n_ao, a->out_shadow, a->out_ao);   // first in the queue: its blocks fill the machine first
+    if (rc == VXL_OK && (want_pt || want_sp)) {
+        VXL_CUDA(cudaStreamWaitEvent(side[0], ev[0], 0));
+        c->stream = side[0];                                                        // point then spot: they share the light staging buffer
+        if (want_pt) rc = vxl_pass_point(c, vol, a->view, &a->frame, a->point, a->n_point, a->out_point_shadow);
+        if (rc == VXL_OK && want_sp) rc = vxl_pass_spot(c, vol, a->view, &a->frame, a->spot, a->n_spot, a->out_spot_shadow);
+        c->stream = main;
+        VXL_CUDA(cudaEventRecord(ev[1], side[0]));
+        VXL_CUDA(cudaStreamWaitEvent(main, ev[1], 0));
+    }
+    if (rc == VXL_OK && want_rf) {
+        VXL_CUDA(cudaStreamWaitEvent(side[1], ev[0], 0));
+        c->stream = side[1];
+        rc = vxl_pass_reflection(c, vol, a->view, &a->frame, a->out_spec_t);
+        c->stream = main;
+        VXL_CUDA(cudaEventRecord(ev[2], side[1]));
+        VXL_CUDA(cudaStreamWaitEvent(main, ev[2], 0));
+    }
+    return rc;
+}
+
 int vxl_lighting_host(vxl_ctx* c, vxl_volume* vol, const vxl_lighting_host_args* a) {
     if (!c || !vol || !a || !a->view) { set_error("vxl_lighting_host: bad argument"); return VXL_ERR_INVALID; }
     if (a->n_point < 0 || a->n_spot < 0 || a->n_point > VXL_MAX_LIGHTS || a->n_spot > VXL_MAX_LIGHTS) { set_error("vxl_lighting_host: light count out of range"); return VXL_ERR_LIMIT; }

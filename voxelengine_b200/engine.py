@@ -579,6 +579,20 @@ def lighting_host(ctx: Context, shadowVox: ShadowVoxSystem, view, frame_desc: di
     check(ctx.lib.vxl_lighting_host(ctx.h, shadowVox.h, C.byref(a)), "vxl_lighting_host")
 
 
+def lighting(ctx: Context, shadowVox: ShadowVoxSystem, view, geometryFB: "GeometryBuffer", outs: dict, n_ao: int = 1, point=None, spot=None):
+    """vxl_lighting: all requested passes of one frame on DEVICE planes, the three kernels on concurrent streams (joined on the
+    context's stream).  outs: any of shadow, ao, point_shadow, spot_shadow, spec_t (device tensors in the frame's tile-compact layout)."""
+    dp = lambda x: None if x is None else x.data_ptr()
+    v, vp = _view_ptr(view)
+    fr = geometryFB.frame()
+    pt = np.ascontiguousarray(point, dtype=POINT_LIGHT_DTYPE) if point is not None else None
+    sp = np.ascontiguousarray(spot, dtype=SPOT_LIGHT_DTYPE) if spot is not None else None
+    a = capi.LightingHostArgs(fr, vp, int(n_ao), 0 if pt is None else len(pt), 0 if sp is None else len(sp),
+                              None if pt is None else pt.ctypes.data, None if sp is None else sp.ctypes.data,
+                              dp(outs.get("shadow")), dp(outs.get("ao")), dp(outs.get("point_shadow")), dp(outs.get("spot_shadow")), dp(outs.get("spec_t")))
+    check(ctx.lib.vxl_lighting(ctx.h, shadowVox.h, C.byref(a)), "vxl_lighting")
+
+
 # ---- on-disk formats (SURVEY 8f row f4): thin wrappers over the host-side readers of libvxl.so ---------------------------------
 def asset_guid(path: str) -> int:
     """Assets::Hash (Sources/Asset/Assets.h:207-210): the GUID of an asset path relative to Mods/."""

@@ -61,6 +61,8 @@ class Workload:
         self.n_planes = 3 + self.n_point
         self.gathered_main = self.gathered_point = None      # (world, 3, tiles, th, tw) / (world, n_point, tiles, th, tw)
         self.stack = None
+        import os
+        self.concurrent = os.environ.get("VXL_CONCURRENT", "1") != "0"
         auto = gather == "auto"
         if auto:
             import torch.distributed as dist
@@ -153,16 +155,15 @@ class Workload:
             self.stack.enable()
             self.ctx.set_light_plane_stride(self.tiles_padded * self.gb.tile_h * self.gb.tile_w)
             try:
-                if self.n_point:
-                    self._point(o[3:])
-                E.LightAmbientPipeline.Get().Use(self.view, self.gb, self.vol, n_ao=self.n_ao, out_shadow=o[0, :n], out_ao=o[1, :n])
-                if self.spec:
-                    E.LightReflectionPipeline.Get().Use(self.view, self.gb, self.vol, out_spec_t=o[2, :n])
+                self._passes(o, n)
             finally:
                 self.stack.disable()
                 self.ctx.set_light_plane_stride(0)
             if gather:
                 self.stack.fence()
+            return self.out
+        if self.world == 1 and self.concurrent:
+            self._passes(o, n)                                   # one GPU: the three pass kernels side by side (vxl_lighting)
             return self.out
         if gather:
             from .tiles import gather_tiles
@@ -188,6 +189,23 @@ class Workload:
             self.gathered_main = gather_tiles(o[:3], out=self.gathered_main)
             torch.cuda.current_stream().wait_stream(self._side)
         return self.out
+
+    def _passes(self, o, n):
+        """All passes of this rank's shard.  Default: vxl_lighting, the three kernels on concurrent streams joined on the context's
+        stream; VXL_CONCURRENT=0: one pass after the other (the A/B baseline)."""
+        if self.concurrent:
+            outs = dict(shadow=o[0, :n], ao=o[1, :n])
+            if self.spec:
+                outs["spec_t"] = o[2, :n]
+            if self.n_point:
+                outs["point_shadow"] = o[3:]
+            E.lighting(self.ctx, self.vol, self.view, self.gb, outs, n_ao=self.n_ao, point=self.lights)
+            return
+        if self.n_point:
+            self._point(o[3:])
+        E.LightAmbientPipeline.Get().Use(self.view, self.gb, self.vol, n_ao=self.n_ao, out_shadow=o[0, :n], out_ao=o[1, :n])
+        if self.spec:
+            E.LightReflectionPipeline.Get().Use(self.view, self.gb, self.vol, out_spec_t=o[2, :n])
 
     @property
     def gathered(self):
