@@ -159,6 +159,7 @@ public:
         std::memcpy(l.Direction, direction, 12); l.Angle = angle; l.AngleAttenuation = angleAttenuation;
     }
     int LightCount() const { return _CurrentLightIndex; }
+    const vxl_spot_light* Lights() const { return _Lights; }
     void Use(Context& cmd, const vxl_view& view, const GeometryFramebuffer& geometryFB, ShadowVoxSystem& shadowVox,
              const std::function<void(LightSpotPipeline& P)>& cb, float* outShadow) {
         _CurrentLightIndex = 0;
@@ -216,6 +217,24 @@ public:
     }
     static GeometryVoxelPipeline& Get() { static GeometryVoxelPipeline Instance; return Instance; }
 };
+
+// The "Lights" + "Reflection" blocks of WorldRenderer::DrawWorld (WorldRenderer.cpp:239-274) as ONE call on device planes: the lights
+// recorded by the two callbacks, then vxl_lighting -- the three pass kernels on concurrent streams, joined on the context's stream.
+// Any output may be null (that pass is skipped).  outPointShadow / outSpotShadow: one plane per drawn light.
+inline void DrawLights(Context& cmd, const vxl_view& view, const GeometryFramebuffer& geometryFB, ShadowVoxSystem& shadowVox, int aoRays,
+                       const std::function<void(LightPointPipeline& P)>& pointCb, const std::function<void(LightSpotPipeline& P)>& spotCb,
+                       float* outShadow, float* outAO, float* outPointShadow, float* outSpotShadow, float* outSpecT) {
+    struct Collect : LightPointPipeline { using LightPointPipeline::LightPointPipeline; } point;
+    struct CollectSpot : LightSpotPipeline { using LightSpotPipeline::LightSpotPipeline; } spot;
+    if (pointCb) pointCb(point);
+    if (spotCb) spotCb(spot);
+    vxl_lighting_host_args a{};
+    a.frame = geometryFB.Frame; a.view = &view; a.n_ao = aoRays;
+    a.n_point = point.LightCount(); a.point = point.Lights();
+    a.n_spot = spot.LightCount(); a.spot = spot.Lights();
+    a.out_shadow = outShadow; a.out_ao = outAO; a.out_point_shadow = outPointShadow; a.out_spot_shadow = outSpotShadow; a.out_spec_t = outSpecT;
+    Check(vxl_lighting(cmd, shadowVox.GetVolumeImage(), &a), "vxl_lighting");
+}
 
 // VoxImporter (Editor/Importer/VoxImporter.cpp): a dropped .vox file -> <mods>/<path>/<file>/<shape>.v, <file>.p, <path>/<file>.pf
 struct VoxImporter {

@@ -6,6 +6,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 struct Header { int32_t magic, sx, sy, sz, W, H, n_ao, n_point, n_spot; };
@@ -54,6 +55,18 @@ int main(int argc, char** argv) {
         vxl::LightReflectionPipeline::Get().Use(ctx, view, fb, shadowVox, spec);
         vxl_stats st;
         vxl::Check(vxl_stats_read(ctx, &st), "vxl_stats_read");
+        // the same frame through the one-call form (vxl_lighting: concurrent pass kernels) must give the same planes
+        float* out2 = ctx.Alloc<float>(planes * px);
+        vxl::DrawLights(ctx, view, fb, shadowVox, h.n_ao,
+                        [&](vxl::LightPointPipeline& P) { for (auto& l : pl) P.DrawLight(l.Position, l.Range, l.Color, l.Attenuation); },
+                        [&](vxl::LightSpotPipeline& P) { for (auto& l : sl) P.DrawLight(l.Position, l.Range, l.Color, l.Attenuation, l.Direction, l.Angle, l.AngleAttenuation); },
+                        out2, out2 + px, h.n_point ? out2 + 3 * px : nullptr, h.n_spot ? out2 + (3 + (size_t)h.n_point) * px : nullptr, out2 + 2 * px);
+        {
+            std::vector<float> a(planes * px), b(planes * px);
+            ctx.Download(a.data(), out, a.size() * 4); ctx.Download(b.data(), out2, b.size() * 4);
+            if (memcmp(a.data(), b.data(), a.size() * 4) != 0) { fprintf(stderr, "DrawLights planes differ from the single passes\n"); return 6; }
+        }
+        ctx.Free(out2);
 
         std::vector<float> host(planes * px);
         std::vector<uint32_t> gb(3 * px);
