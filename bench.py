@@ -88,6 +88,23 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def issue_roofline(kernel: str, kernel_ms: float, sm_mhz: float, n_sm: int):
+    """The bound the ncu captures point at: warp instructions of one launch (profiles/kernel_counters.json, ncu capture of
+    the same kernel on the same workload) against the SMs' issue rate, 4 warp instructions per clock per SM, at the live kernel time and
+    the SM clock sampled during the timed region.  None when the counters are missing."""
+    path = os.path.join(ROOT, "profiles", "kernel_counters.json")
+    if not os.path.exists(path) or not sm_mhz or not n_sm or kernel_ms <= 0:
+        return None
+    c = json.load(open(path)).get(kernel.split("<")[0])
+    if not c or not c.get("warp_instructions"):
+        return None
+    peak = float(n_sm) * 4.0 * float(sm_mhz) * 1e6
+    ach = float(c["warp_instructions"]) / (kernel_ms * 1e-3)
+    return {"warp_instructions_per_launch": c["warp_instructions"], "active_threads_per_instruction": c.get("active_threads_per_inst"),
+            "achieved_warp_inst_per_s": ach, "peak_warp_inst_per_s": peak, "frac": ach / peak,
+            "source": "instruction count: profiles/kernel_counters.json (ncu, same kernel and workload); time and clock: this run"}
+
+
 def algorithmic_bytes(pass_name: str, st: dict, n_ao: int) -> int:
     """sum_rays steps*1 B + sum_lit_pixels (in_px + out_px).  in_px = depth 4 + normal 4 + 4 per
     distinct blue-noise texel (+ material 4 for the spec pass); out_px = 4 B per output scalar."""
@@ -425,6 +442,13 @@ def run_ours(args):
             if not parity["bit_exact"]:
                 sys.stderr.write(f"PARITY FAILURE at full size: {res_p}\n")
 
+    if world == 1 and args.config == 3:      # the instruction counts on file are those of config 3's whole-frame launches
+        try:
+            roofline["issue"] = issue_roofline(roofline["kernel"], roofline["kernel_ms"], clk.summary().get("sm_mhz"),
+                                               torch.cuda.get_device_properties(dev).multi_processor_count)
+        except Exception as e:               # never let a derived figure cost the bench line
+            roofline["issue"] = None
+            sys.stderr.write(f"issue roofline skipped: {e}\n")
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -42,6 +42,7 @@ def main():
     idx = {h: i for i, h in enumerate(hdr)}
     out = [f"# ncu summary `{tag}` ({os.path.basename(rep)}; `ncu --set full --clock-control none`)\n"]
     traffic = {}
+    counters = {}
     for r in rows[2:]:
         name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "")
         out.append(f"\n## {name}\n\n| metric | value |\n|---|---|")
@@ -53,6 +54,14 @@ def main():
                 v, u = float(r[idx[k]]), units[idx[k]]
                 return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
             traffic[name.split("<")[0]] = b("dram__bytes_read.sum") + b("dram__bytes_write.sum")
+        except Exception:
+            pass
+        try:    # warp instructions per launch: bench.py turns them into a live fraction of the SM issue rate
+            counters.setdefault(name.split("<")[0], {})
+            if not counters[name.split("<")[0]]:
+                counters[name.split("<")[0]] = {"warp_instructions": float(r[idx["smsp__inst_executed.sum"]]),
+                                            "active_threads_per_inst": float(r[idx["smsp__thread_inst_executed_per_inst_executed.ratio"]]),
+                                            "issue_slots_busy_pct_ncu": float(r[idx["smsp__issue_active.avg.pct_of_peak_sustained_active"]])}
         except Exception:
             pass
     here = os.path.dirname(os.path.abspath(__file__))
@@ -73,6 +82,7 @@ def main():
             out.append(f"| {k} | {a[0]} | {a[1]:.3f} | {100 * a[1] / tot:.1f}% |")
     open(os.path.join(here, f"{tag}_summary.md"), "w").write("\n".join(out) + "\n")
     json.dump(traffic, open(os.path.join(here, "dram_traffic.json"), "w"), indent=1)
+    json.dump(counters, open(os.path.join(here, "kernel_counters.json"), "w"), indent=1)
     print("\n".join(out))
 
 
