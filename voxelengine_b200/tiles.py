@@ -136,4 +136,5 @@ class PeerStack:
         for r, p in enumerate(self.mapped):
             if r != self.rank:
                 self.ctx.ipc_close(p)
+        dist.barrier(group=self.group)                                # an exported allocation is freed only after every importer has closed it
         self.ctx.free(self.base)
