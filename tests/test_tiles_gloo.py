@@ -76,3 +76,86 @@ def test_gather_world2_gloo():
     for p in ps:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+# ---- the fused gather's host logic (tiles.PeerStack) on two gloo ranks with a stand-in context -------------------------------------
+class _FakeCtx:
+    """What PeerStack needs from engine.Context, on host memory: 'device' allocations are numpy buffers kept alive in a dict, an IPC
+    handle is (pid, address), and opening rank `fail_on`'s handle fails when asked to -- the peer-mapping failure of one rank."""
+
+    def __init__(self, rank, fail=False):
+        import torch
+        self.rank, self.fail, self.torch_device = rank, fail, torch.device("cpu")
+        self.bufs, self.mirrors, self.closed, self.freed = {}, None, [], []
+
+    def malloc(self, n):
+        b = np.zeros(n, np.uint8)
+        self.bufs[b.ctypes.data] = b
+        return b.ctypes.data
+
+    def memset(self, p, v, n):
+        self.bufs[p][:n] = v
+
+    def sync(self):
+        pass
+
+    def ipc_export(self, p):
+        return (str(os.getpid()) + ":" + str(p)).encode().ljust(64, b"\0")
+
+    def ipc_open(self, h):
+        if self.fail:
+            raise RuntimeError("peer access is not supported between these two devices")
+        return 0x10000000 + int(h.rstrip(b"\0").split(b":")[1]) % 0x1000000      # 'mapped' somewhere else in this process
+
+    def ipc_close(self, p):
+        self.closed.append(p)
+
+    def free(self, p):
+        self.freed.append(p)
+
+    def set_output_mirrors(self, d):
+        self.mirrors = list(d)
+
+    def tensor_view(self, p, shape, dtype="float32"):
+        import torch
+        return torch.from_numpy(self.bufs[p].view(np.float32).reshape(shape))
+
+
+def _stack_worker(rank, world, port, q, failing_rank):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from voxelengine_b200.tiles import PeerStack, PeerStackUnavailable
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ctx = _FakeCtx(rank, fail=(rank == failing_rank))
+    try:
+        st = PeerStack(ctx, (3, 2, 4, 4), rank, world)
+        ok = st.tensor.shape == (world, 3, 2, 4, 4) and len(st.deltas) == world - 1 and all(d == st.mapped[r] - st.base for d, r in zip(st.deltas, [r for r in range(world) if r != rank]))
+        st.enable()
+        ok = ok and ctx.mirrors == st.deltas
+        st.fence()
+        st.close()
+        ok = ok and ctx.mirrors == [] and len(ctx.closed) == world - 1 and ctx.freed == [st.base]
+        q.put((rank, "stack" if ok else "broken"))
+    except PeerStackUnavailable:
+        q.put((rank, "unavailable" if ctx.freed and (rank == failing_rank or len(ctx.closed) == world - 1) else "leaked"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("failing_rank", [-1, 1])
+def test_peer_stack_ranks_agree_world2_gloo(failing_rank):
+    """Both ranks build the stack, or -- when one rank cannot map its peer -- both give it up together (no rank is left waiting in a
+    collective), close what they had opened and free their allocation: Workload then falls back to the NCCL gather on every rank."""
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_stack_worker, args=(r, 2, port, q, failing_rank)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+    want = "stack" if failing_rank < 0 else "unavailable"
+    assert res == [(0, want), (1, want)]
