@@ -21,6 +21,7 @@
 #include <filesystem>
 #include <map>
 #include <memory>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -202,7 +203,8 @@ struct Importer {
             const Matrix& M = root.m;
             if (M.rx > 2 || M.ry > 2 || M.rz < 0 || M.rz > 2) { err = "nTRN _r is not a permutation"; return -2; }   // the reference CHECK(0)s
             const int ts[3] = {sh.size[M.rx], sh.size[M.ry], sh.size[M.rz]};
-            if (ts[0] <= 0 || ts[1] <= 0 || ts[2] <= 0 || ts[0] > 4096 || ts[1] > 4096 || ts[2] > 4096) { err = "bad SIZE"; return -2; }
+            if (ts[0] <= 0 || ts[1] <= 0 || ts[2] <= 0 || ts[0] > 4096 || ts[1] > 4096 || ts[2] > 4096 ||
+                (long long)ts[0] * ts[1] * ts[2] > (1ll << 28)) { err = "bad SIZE (XYZI coordinates are bytes: a model is at most 256^3)"; return -2; }
             const int center[3] = {M.sx ? ts[0] - ts[0] / 2 : ts[0] / 2, M.sz ? ts[2] - ts[2] / 2 : ts[2] / 2, !M.sy ? ts[1] - ts[1] / 2 : ts[1] / 2};
             for (int i = 0; i < 3; ++i) e.position[i] = p[i] - (float)center[i] * 0.1f;
             vxl_vox_scene::Model mdl;
@@ -276,6 +278,7 @@ extern "C" {
 
 int vxl_vox_import_memory(const void* data, uint64_t size, vxl_vox_scene** out) {
     if (!data || !out) { set_error("vxl_vox_import_memory: bad argument"); return VXL_ERR_INVALID; }
+    try {
     Importer im;
     if (!im.parse((const uint8_t*)data, (size_t)size)) { set_error("vxl_vox_import: " + im.err); return VXL_ERR_INVALID; }
     if (im.nodes.empty() || im.nodes[0].kind != 'T') { set_error("vxl_vox_import: the file has no root transform node"); return VXL_ERR_INVALID; }
@@ -289,6 +292,10 @@ int vxl_vox_import_memory(const void* data, uint64_t size, vxl_vox_scene** out) 
     if (im.create(*sc, im.nodes[0], -1, counter, 0) == -2) { set_error("vxl_vox_import: " + im.err); return VXL_ERR_INVALID; }
     *out = sc.release();
     return VXL_OK;
+    } catch (const std::bad_alloc&) {                             // nothing crosses the C boundary
+        set_error("vxl_vox_import: out of memory");
+        return VXL_ERR_OOM;
+    }
 }
 
 int vxl_vox_import(const char* vox_path, vxl_vox_scene** out) {
