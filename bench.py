@@ -105,6 +105,24 @@ def issue_roofline(kernel: str, kernel_ms: float, sm_mhz: float, n_sm: int):
             "source": "instruction count: profiles/kernel_counters.json (ncu, same kernel and workload); time and clock: this run"}
 
 
+def config_of(cfg: dict) -> dict:
+    """The `config` object of the JSON line: the same keys and values from both arms (ours and --impl reference)."""
+    W, H = cfg["res"]
+    return {"workload": cfg["name"], "volume_texels": list(cfg["texels"]), "resolution": [W, H],
+            "rays_per_lit_pixel": {"sun_shadow": 1, "ao": cfg["n_ao"], "point_light_shadow": cfg["n_point"], "spec_occlusion": int(cfg["spec"])},
+            "l2": "GPU arm: flushed between timed steps (256 MiB fill outside the event pairs); CPU arm: not applicable"}
+
+
+def dram_traffic(kernel: str, config: int, world: int):
+    """ncu `dram__bytes_read.sum + dram__bytes_write.sum` of one launch of `kernel`, from the committed capture of THIS config at
+    THIS GPU count (profiles/dram_traffic.json: {"cfg<config>_n<world>": {kernel: bytes}}); None when no such capture exists."""
+    tp = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    try:
+        return json.load(open(tp)).get(f"cfg{config}_n{world}", {}).get(kernel)
+    except Exception:
+        return None
+
+
 def algorithmic_bytes(pass_name: str, st: dict, n_ao: int) -> int:
     """sum_rays steps*1 B + sum_lit_pixels (in_px + out_px).  in_px = depth 4 + normal 4 + 4 per
     distinct blue-noise texel (+ material 4 for the spec pass); out_px = 4 B per output scalar."""
@@ -185,7 +203,7 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32+u8", "data": "synthetic", "config": {"workload": cfg["name"], "volume_texels": list(cfg["texels"]), "resolution": [W, H]},
+        "dtype": "f32+u8", "data": "synthetic", "config": config_of(cfg),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": O.num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -319,17 +337,23 @@ def run_ours(args):
     peak, peak_src = hbm_peak()
     abytes = algorithmic_bytes(dom, per[dom], wl.n_ao)
     achieved = abytes / (ktime[dom] * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "dram_traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get({"ambient": "k_ambient", "point": "k_local_lights", "reflection": "k_reflection"}[dom])
-        except Exception:
-            traffic = None
+    traffic = dram_traffic({"ambient": "k_ambient", "point": "k_local_lights", "reflection": "k_reflection"}[dom], args.config, world)
     roofline = {"bound": "hbm", "kernel": {"ambient": "k_ambient", "point": "k_local_lights<false>", "reflection": "k_reflection"}[dom],
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes, "kernel_ms": ktime[dom],
                 "all_kernels_ms": ktime, "probes_per_s": per[dom]["steps"] / (ktime[dom] * 1e-3)}
+    # The volume the probes read is L2-resident (98 % L2 hit rate in the ncu captures), so north_star's "HBM (or L2) roofline"
+    # is also quoted against the L2 read bandwidth -- measured live on this GPU (SURVEY 8d / BASELINE.md: "by a microbench in the
+    # bench harness"): 16-byte .cg loads over a 48 MiB buffer from every SM, and the same over 2 GiB for HBM reads.
+    try:
+        l2_gbs = max(wl.ctx.read_bandwidth(48 << 20, 40) for _ in range(3))
+        hbm_read_gbs = max(wl.ctx.read_bandwidth(2 << 30, 2) for _ in range(2))
+        roofline["l2"] = {"peak": l2_gbs, "unit": "GB/s", "achieved": achieved, "frac": achieved / l2_gbs,
+                          "peak_source": "measured in this run: vxl_debug_read_bandwidth, 48 MiB buffer, best of 3",
+                          "hbm_read_gbs_same_probe": hbm_read_gbs}
+    except Exception as e:
+        roofline["l2"] = None
+        sys.stderr.write(f"L2 bandwidth probe skipped: {e}\n")
 
     # ---- light-buffer resolve: elementwise, HBM-bound; timed beside the march, not part of `value` ----
     resolve = None
@@ -439,8 +463,14 @@ def run_ours(args):
             if rows[2] == 1:
                 parity["rays_equal"] = bool(int(st_now["rays"]) == int(r))
                 parity["probes_equal"] = bool(int(st_now["steps"]) == int(s))
-            if not parity["bit_exact"]:
-                sys.stderr.write(f"PARITY FAILURE at full size: {res_p}\n")
+            ok = parity["bit_exact"] and parity.get("rays_equal", True) and parity.get("probes_equal", True)
+            if not ok:
+                # a frame that differs from the oracle has no throughput: no `value`, non-zero exit
+                sys.stderr.write(f"PARITY FAILURE at full size: {parity}\n")
+                print(json.dumps({"metric": METRIC, "error": "parity failure against the CPU oracle at the bench's own size", "parity": parity,
+                                  "n_gpus": world, "config": config_of(cfg)}))
+                wl.close()
+                sys.exit(3)
 
     if world == 1 and args.config == 3:      # the instruction counts on file are those of config 3's whole-frame launches
         try:
@@ -454,8 +484,8 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+u8",
             "data": "synthetic",
-            "config": {"workload": cfg["name"], "volume_texels": list(wl.texels), "resolution": [W, H],
-                       "rays_per_step": int(rays), "probes_per_step": int(probes), "lit_pixels": int(lit),
+            "config": config_of(cfg),
+            "detail": {"rays_per_step": int(rays), "probes_per_step": int(probes), "lit_pixels": int(lit),
                        "parallelism": "1 GPU, whole frame" if world == 1 else f"{world} GPUs, 128x128 screen tiles round-robin, volume replicated, " + (
                            "output tiles gathered INSIDE the pass kernels: every output store repeated into each peer's stack over NVLink peer memory (CUDA IPC), one fence per frame"
                            if wl.stack is not None else "NCCL all-gather of output tiles"),
@@ -489,28 +519,50 @@ def run_e2e(args, wl, torch, dist, world, rank, rays):
         if wl.n_point:
             outs["point_shadow"] = torch.empty((wl.n_point,) + shape, dtype=torch.float32).pin_memory()
         d2h = sum(int(t.numel()) * 4 for t in outs.values())
+        # packed planes (vxl_lighting_host_packed): one mask byte per 8 shadow planes, one code byte for spec_t, AO stays float32
+        mb = E.mask_bytes(wl.n_point, 0)
+        pk = dict(shadow_mask=torch.empty(shape + (mb,), dtype=torch.uint8).pin_memory(), ao=torch.empty(shape, dtype=torch.float32).pin_memory())
+        if wl.spec:
+            pk["spec_code"] = torch.empty(shape, dtype=torch.uint8).pin_memory()
+        d2h_packed = sum(int(t.numel()) * t.element_size() for t in pk.values())
         desc = dict(width=wl.gb.width, height=wl.gb.height, tile_w=wl.gb.tile_w, tile_h=wl.gb.tile_h, tile_first=wl.gb.tile_first,
                     tile_stride=wl.gb.tile_stride, n_tiles=n)
 
         dynamic = wl.cfg["scene"] == "dynamic"
 
-        def one():
-            if dynamic:      # config 4: the frame starts with the re-voxelisation of the moving entities + occupancy rebuild
-                wl.advance()
+        def timed_host(o):
+            def one():
+                if dynamic:      # config 4: the frame starts with the re-voxelisation of the moving entities + occupancy rebuild
+                    wl.advance()
+                E.lighting_host(wl.ctx, wl.vol, wl.view, desc, planes, o, n_ao=wl.n_ao, point=wl.lights)
+            for _ in range(2):
+                one()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                one()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / steps
+        dt_float = timed_host(outs)
+        dt = timed_host({"packed": pk})
+        # both must equal the resident path (same volume: the dynamic scene is not advanced for the check)
+        if dynamic:
             E.lighting_host(wl.ctx, wl.vol, wl.view, desc, planes, outs, n_ao=wl.n_ao, point=wl.lights)
-        for _ in range(2):
-            one()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            one()
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / steps
-        # the device planes must equal the resident path's (same volume: the dynamic scene is not advanced for the check)
+            E.lighting_host(wl.ctx, wl.vol, wl.view, desc, planes, {"packed": pk}, n_ao=wl.n_ao, point=wl.lights)
         ref = wl.step(gather=False, advance=False).cpu()
         assert torch.equal(outs["shadow"], ref[0, :n]) and torch.equal(outs["ao"], ref[1, :n]), "e2e planes differ from the resident path"
-        return {"value": rays / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3,
-                "api": "vxl_lighting_host (pinned host buffers)"}
+        un = E.unpack_planes(pk["shadow_mask"].numpy(), pk["spec_code"].numpy() if wl.spec else None, wl.n_point, 0)
+        assert torch.equal(pk["ao"], ref[1, :n]), "e2e (packed): ao differs from the resident path"
+        assert np.array_equal(un["shadow"].view(np.uint32), ref[0, :n].numpy().reshape(-1).view(np.uint32)), "e2e (packed): sun shadow differs"
+        if wl.spec:
+            assert np.array_equal(un["spec_t"].view(np.uint32), ref[2, :n].numpy().reshape(-1).view(np.uint32)), "e2e (packed): spec_t differs"
+        for li in range(wl.n_point):
+            assert np.array_equal(un["point_shadow"][li].view(np.uint32), ref[3 + li, :n].numpy().reshape(-1).view(np.uint32)), f"e2e (packed): point plane {li} differs"
+        return {"value": rays / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_packed, "ms_per_step": dt * 1e3,
+                "api": "vxl_lighting_host_packed (pinned host buffers; shadow planes as a bit mask, spec_t as its one-byte code, AO float32; decoded and compared "
+                       "bit for bit with the resident path after the timed region)",
+                "float_planes": {"value": rays / dt_float / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": dt_float * 1e3,
+                                 "api": "vxl_lighting_host (pinned host buffers, every plane float32)"}}
     # N > 1: every rank runs the same host-facing call on its tile shard, and its outputs land -- over its own PCIe link -- in ONE
     # host frame shared by all ranks (POSIX shared memory, page-locked by each rank with cudaHostRegister): [rank][plane][tile].
     # No rank reads back another rank's tiles; the NCCL all-gather belongs to the device-resident path (`value`).

@@ -172,6 +172,10 @@ int vxl_debug_fetched_probes(vxl_ctx* ctx, uint64_t* out /* HOST */);
  * voxels), 13, 14 = the 3x3x3-dilated levels 3, 4 including their 1-cell border; out_dims = {cx, cy, cz};
  * host_out may be NULL */
 int vxl_volume_debug_occupancy(vxl_volume* vol, int level, uint8_t* host_out /* HOST */, int* out_dims /* HOST[3] */);
+/* measurement helper (bench.py's roofline denominators, SURVEY 8d: "L2 read bandwidth ... measured by a microbench in the bench
+ * harness"): read a `bytes`-sized device buffer `reps` times with 16-byte loads from every SM (one warm-up pass first) and report
+ * bytes * reps / CUDA-event time.  A buffer well below the 126 MB L2 measures L2 read bandwidth, one of several GB HBM. */
+int vxl_debug_read_bandwidth(vxl_ctx* ctx, size_t bytes, int reps, double* out_gbs /* HOST */);
 
 /* raw memory helpers so a C caller needs no CUDA headers */
 int vxl_malloc(vxl_ctx* ctx, size_t bytes, void** out_dev);
@@ -379,6 +383,21 @@ typedef struct vxl_lighting_host_args {
     float* out_spec_t;               /* [tiles] */
 } vxl_lighting_host_args;
 int vxl_lighting_host(vxl_ctx* ctx, vxl_volume* vol, const vxl_lighting_host_args* args);
+/* The same call with PACKED output planes (HOST pointers, tile-compact like the float planes; any may be NULL = not wanted).
+ * Five of the seven float planes of a frame are 0 / 1 shadow flags (LightAmbient.frag:167-169, LightPoint.frag:125) and spec_t
+ * (LightReflection.frag:113) takes 180 values, so a frame that crosses PCIe as float32 is mostly air:
+ *   shadow_mask  uint8[px][mask_bytes], mask_bytes = (1 + n_point + n_spot + 7) / 8; bit p of the little-endian mask is plane p:
+ *                0 = sun shadow, 1 .. n_point = point lights, then the spot lights; set = the float plane holds 1.0f, clear = 0.0f
+ *   spec_code    uint8[px]: 0..30 -> 0.5 * (code + 1); 31..178 -> 16 + (code - 31); 255 -> 256.0f (miss / unlit).  Exactly invertible.
+ *   ao           float32[px], unchanged
+ * The out_* members of `args` are ignored.  Which passes run: ambient if shadow_mask or ao, local lights if shadow_mask and
+ * n_point / n_spot > 0, reflection if spec_code.  At 3840x2160 with 4 point lights the read-back is 50 MB instead of 232 MB. */
+typedef struct vxl_packed_planes {
+    uint8_t* shadow_mask;
+    uint8_t* spec_code;
+    float* ao;
+} vxl_packed_planes;
+int vxl_lighting_host_packed(vxl_ctx* ctx, vxl_volume* vol, const vxl_lighting_host_args* args, const vxl_packed_planes* out);
 /* The same frame with DEVICE pointers throughout (frame planes, outputs; view and lights stay HOST): the ambient pass on the context's
  * stream, the local-light passes and the reflection pass on two side streams forked from it and joined back before the call returns
  * (stream-ordered, asynchronous).  The passes are independent, so the tail of one kernel overlaps the head of the next.  Same

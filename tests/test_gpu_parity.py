@@ -332,6 +332,54 @@ def test_lighting_host_matches_passes(gpu_ctx, oracle, terrain):
     vol.close()
 
 
+def test_lighting_host_packed_decodes_to_the_float_planes(gpu_ctx, oracle, terrain):
+    """vxl_lighting_host_packed: the shadow planes as a bit mask per pixel, spec_t as its one-byte code (LightAmbient.frag:167-169,
+    LightPoint.frag:125, LightReflection.frag:113 take 2 / 2 / 180 values), AO float32.  Decoded, every plane equals what
+    vxl_lighting_host returns -- and therefore the oracle -- bit for bit; 9 point + 2 spot lights need a two-byte mask."""
+    import torch
+    E = _eng()
+    from voxelengine_b200 import scenes as S
+    sc = terrain
+    base = _test_lights(sc)
+    pts = np.concatenate([base] * 5)[:9].copy()
+    for i in range(len(pts)):
+        pts[i]["Position"][0] += 0.37 * i
+        pts[i]["Range"] = 4.0 + i
+    spots = S.spot_lights([tuple(float(v) for v in pts[0]["Position"]), tuple(float(v) for v in pts[3]["Position"])], 9.0, [(0.2, -1.0, 0.1)] * 2, 0.9)
+    sz, sy, sx = sc["volume"].shape
+    vol = E.ShadowVoxSystem(gpu_ctx, (sx, sy, sz))
+    vol.upload(sc["volume"])
+    h, w = sc["gb"]["depth24"].shape
+    planes = {k: torch.from_numpy(sc["gb"][k].view(np.int32)).pin_memory() for k in ("depth24", "normal", "material", "noise")}
+    desc = dict(width=w, height=h, tile_w=w, tile_h=h, tile_first=0, tile_stride=1, n_tiles=1)
+    f32 = lambda *shape: torch.empty(shape, dtype=torch.float32).pin_memory()
+    outs = dict(shadow=f32(h, w), ao=f32(h, w), point_shadow=f32(len(pts), h, w), spot_shadow=f32(len(spots), h, w), spec_t=f32(h, w))
+    E.lighting_host(gpu_ctx, vol, sc["view"], desc, planes, outs, n_ao=3, point=pts, spot=spots)
+    mb = E.mask_bytes(len(pts), len(spots))
+    assert mb == 2
+    pk = dict(shadow_mask=torch.full((h, w, mb), 0xAA, dtype=torch.uint8).pin_memory(), spec_code=torch.full((h, w), 0xAA, dtype=torch.uint8).pin_memory(), ao=f32(h, w))
+    E.lighting_host(gpu_ctx, vol, sc["view"], desc, planes, {"packed": pk}, n_ao=3, point=pts, spot=spots)
+    un = E.unpack_planes(pk["shadow_mask"].numpy(), pk["spec_code"].numpy(), len(pts), len(spots))
+    bits = lambda a: np.ascontiguousarray(a).reshape(-1).view(np.uint32)
+    assert np.array_equal(bits(pk["ao"].numpy()), bits(outs["ao"].numpy()))
+    assert np.array_equal(bits(un["shadow"]), bits(outs["shadow"].numpy()))
+    assert np.array_equal(bits(un["spec_t"]), bits(outs["spec_t"].numpy()))
+    assert np.array_equal(bits(un["point_shadow"]), bits(outs["point_shadow"].numpy()))
+    assert np.array_equal(bits(un["spot_shadow"]), bits(outs["spot_shadow"].numpy()))
+    # the float planes themselves against the oracle (shadows occur in every plane kind, so the masks are exercised both ways)
+    wsh, wao, _ = oracle.pass_ambient(sc["volume"], sc["view"], sc["gb"], 3)
+    wt, _ = oracle.pass_reflection(sc["volume"], sc["view"], sc["gb"])
+    _assert_plane("shadow", un["shadow"].reshape(h, w), wsh)
+    _assert_plane("spec_t", un["spec_t"].reshape(h, w), wt)
+    assert 0 < float(un["point_shadow"].mean()) < 1 and len(np.unique(pk["spec_code"].numpy())) > 3
+    # unused bits of the last mask byte stay clear; only some passes requested
+    assert int((pk["shadow_mask"].numpy()[..., 1] >> 4).max()) == 0
+    pk2 = dict(spec_code=torch.zeros((h, w), dtype=torch.uint8).pin_memory())
+    E.lighting_host(gpu_ctx, vol, sc["view"], desc, planes, {"packed": pk2}, n_ao=3)
+    assert np.array_equal(pk2["spec_code"].numpy(), pk["spec_code"].numpy())
+    vol.close()
+
+
 # ---- derived occupancy levels and the tile march ------------------------------------------------------
 @pytest.mark.parametrize("texels", [(64, 48, 64), (37, 21, 50), (16, 16, 16), (130, 9, 3)])
 def test_occupancy_levels_match_block_maxima(gpu_ctx, oracle, texels):

@@ -47,10 +47,11 @@ def nvcc_path() -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
-        return OUT
     extra = os.environ.get("VXL_NVCC_EXTRA", "").split()      # experiments only, e.g. -DVXL_AMBIENT_BLOCKS=3
-    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + sources()
+    out = os.environ.get("VXL_LIB_OUT") or OUT                # experiments only: a differently compiled copy for A/B runs (VXL_LIB loads it)
+    if out == OUT and not force and not is_stale():
+        return OUT
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + sources()
     env = dict(os.environ)
     if os.path.exists("/usr/bin/g++"):
         cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
@@ -59,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building libvxl.so")
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

@@ -17,8 +17,8 @@ SYMBOLS = [
     "vxl_volume_upload", "vxl_volume_download", "vxl_volume_clear", "vxl_volume_device_ptr",
     "vxl_volume_mark_dirty", "vxl_volume_build_occupancy", "vxl_model_create", "vxl_volume_voxelize",
     "vxl_pass_ambient", "vxl_pass_point", "vxl_pass_spot", "vxl_pass_reflection", "vxl_trace_rays",
-    "vxl_lighting_host", "vxl_lighting", "vxl_volume_gen_terrain", "vxl_gbuffer_primary",
-    "vxl_debug_set_variant", "vxl_debug_fetched_probes", "vxl_volume_debug_occupancy",
+    "vxl_lighting_host", "vxl_lighting_host_packed", "vxl_lighting", "vxl_volume_gen_terrain", "vxl_gbuffer_primary",
+    "vxl_debug_set_variant", "vxl_debug_fetched_probes", "vxl_volume_debug_occupancy", "vxl_debug_read_bandwidth",
     "vxl_resolve_ambient", "vxl_resolve_point", "vxl_resolve_spot", "vxl_trace_model_rays", "vxl_gbuffer_models",
     "vxl_light_taa", "vxl_resolve_reflection",
     "vxl_asset_guid", "vxl_vox_file_read", "vxl_model_load_v", "vxl_pallete_file_read", "vxl_prefab_file_read", "vxl_scene_load",
@@ -69,6 +69,11 @@ class LightingHostArgs(C.Structure):
                 ("out_spec_t", C.c_void_p)]
 
 
+class PackedPlanes(C.Structure):
+    """vxl_packed_planes"""
+    _fields_ = [("shadow_mask", C.c_void_p), ("spec_code", C.c_void_p), ("ao", C.c_void_p)]
+
+
 _lib = None
 
 
@@ -117,9 +122,10 @@ def load():
         "vxl_vox_scene_write": [vp, C.c_char_p, C.c_char_p, C.c_char_p], "vxl_vox_scene_free": [vp],
         "vxl_resolve_reflection": [vp, vp, P(Frame), vp, vp, vp, vp, vp],
         "vxl_lighting_host": [vp, vp, P(LightingHostArgs)], "vxl_lighting": [vp, vp, P(LightingHostArgs)],
+        "vxl_lighting_host_packed": [vp, vp, P(LightingHostArgs), P(PackedPlanes)],
         "vxl_volume_gen_terrain": [vp], "vxl_gbuffer_primary": [vp, vp, vp, P(Frame)],
         "vxl_debug_set_variant": [vp, i32], "vxl_debug_fetched_probes": [vp, P(C.c_uint64)],
-        "vxl_volume_debug_occupancy": [vp, i32, vp, vp],
+        "vxl_volume_debug_occupancy": [vp, i32, vp, vp], "vxl_debug_read_bandwidth": [vp, sz, i32, P(C.c_double)],
     }
     for name, argtypes in protos.items():
         fn = getattr(lib, name)

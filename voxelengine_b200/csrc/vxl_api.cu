@@ -56,6 +56,63 @@ static void build_perm(int seed, uint8_t* p, uint8_t* p12) {
     }
 }
 
+// vxl_debug_read_bandwidth: grid-stride 16-byte loads, 8 independent loads in flight per thread
+__global__ void __launch_bounds__(512) k_read_bw(const uint4* __restrict__ buf, size_t n_vec, int reps, unsigned* __restrict__ sink) {
+    unsigned acc = 0u;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (int r = 0; r < reps; ++r) {
+        size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i + 7 * stride < n_vec; i += 8 * stride) {
+            uint4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(buf + i + (size_t)u * stride);      // .cg: L2 only, so the figure is not an L1 figure
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc ^= v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
+        }
+        for (; i < n_vec; i += stride) { const uint4 v = __ldcg(buf + i); acc ^= v.x ^ v.y ^ v.z ^ v.w; }
+    }
+    if (acc == 0x9E3779B9u) *sink = acc;          // never true for the fill pattern; keeps the loads alive
+}
+
+// spec_t takes 180 values (Light.frag:131-173 with dist = 256: d = 0.5 (k + 1) for k < 31, 16 + j for j < 148, or 256 on a miss):
+// code 0..30 -> 0.5 (code + 1); 31..178 -> 16 + (code - 31); 255 -> 256.  254 = a value outside that set (never produced; the decoder rejects it)
+__device__ __forceinline__ unsigned spec_code_of(float t) {
+    if (t == 256.0f) return 255u;
+    if (t >= 16.0f) { const float j = t - 16.0f; return (j < 148.0f && j == floorf(j)) ? 31u + (unsigned)j : 254u; }
+    const float k = t * 2.0f - 1.0f;
+    return (k >= 0.0f && k < 31.0f && k == floorf(k)) ? (unsigned)k : 254u;
+}
+
+// Pack rows [row0, row0 + rows) of every tile: the 0/1 shadow planes (sun, point lights, spot lights; plane_stride pixels apart)
+// into mask_bytes bytes per pixel, bit p = plane p is lit (1.0f), and spec_t into its one-byte code.
+__global__ void __launch_bounds__(256) k_pack_planes(const float* __restrict__ shadow, const float* __restrict__ point, int n_point,
+                                                     const float* __restrict__ spot, int n_spot, size_t plane_stride,
+                                                     const float* __restrict__ spec, uint8_t* __restrict__ mask, int mask_bytes,
+                                                     uint8_t* __restrict__ code, int tile_w, int tile_h, int row0, int rows, int n_tiles) {
+    const size_t band = (size_t)rows * tile_w;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= band * (size_t)n_tiles) return;
+    const size_t t = i / band, r = i - t * band;
+    const size_t idx = t * ((size_t)tile_w * tile_h) + (size_t)row0 * tile_w + r;
+    if (mask) {
+        const int n_planes = 1 + n_point + n_spot;
+        for (int byte = 0; byte < mask_bytes; ++byte) {
+            unsigned m = 0u;
+            for (int bit = 0; bit < 8; ++bit) {
+                const int pl = byte * 8 + bit;
+                if (pl >= n_planes) break;
+                float v;
+                if (pl == 0) v = shadow ? shadow[idx] : 1.0f;
+                else if (pl <= n_point) v = point[(size_t)(pl - 1) * plane_stride + idx];
+                else v = spot[(size_t)(pl - 1 - n_point) * plane_stride + idx];
+                if (v != 0.0f) m |= 1u << bit;
+            }
+            mask[idx * (size_t)mask_bytes + byte] = (uint8_t)m;
+        }
+    }
+    if (code) code[idx] = (uint8_t)spec_code_of(spec[idx]);
+}
+
 }  // namespace vxl
 
 using namespace vxl;
@@ -63,6 +120,39 @@ using namespace vxl;
 extern "C" {
 
 int vxl_abi_version(void) { return VXL_ABI_VERSION; }
+
+int vxl_debug_read_bandwidth(vxl_ctx* c, size_t bytes, int reps, double* out_gbs) {
+    if (!c || !out_gbs || bytes < (1u << 20) || reps < 1) { set_error("vxl_debug_read_bandwidth: bad argument"); return VXL_ERR_INVALID; }
+    VXL_CUDA(cudaSetDevice(c->device));
+    uint4* buf = nullptr;
+    unsigned* sink = nullptr;
+    const size_t n_vec = bytes / sizeof(uint4);
+    VXL_CUDA(cudaMalloc(&buf, n_vec * sizeof(uint4) + 16));
+    sink = reinterpret_cast<unsigned*>(buf + n_vec);
+    cudaEvent_t a = nullptr, b = nullptr;
+    int rc = VXL_OK, sms = 0;
+    cudaError_t e = cudaMemsetAsync(buf, 0x5A, n_vec * sizeof(uint4) + 16, c->stream);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    if (e == cudaSuccess) e = cudaEventCreate(&a);
+    if (e == cudaSuccess) e = cudaEventCreate(&b);
+    if (e == cudaSuccess) {
+        const unsigned grid = (unsigned)sms * 4u;
+        k_read_bw<<<grid, 512, 0, c->stream>>>(buf, n_vec, 1, sink);             // warm-up: brings a small buffer into L2
+        cudaEventRecord(a, c->stream);
+        k_read_bw<<<grid, 512, 0, c->stream>>>(buf, n_vec, reps, sink);
+        cudaEventRecord(b, c->stream);
+        c->launches += 2;
+        e = cudaEventSynchronize(b);
+        float ms = 0.0f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, a, b);
+        if (e == cudaSuccess) *out_gbs = (double)(n_vec * sizeof(uint4)) * reps / ((double)ms * 1e6);
+    }
+    if (e != cudaSuccess) rc = cuda_fail(e, "vxl_debug_read_bandwidth");
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+    cudaFree(buf);
+    return rc;
+}
 const char* vxl_last_error_string(void) { return g_err.c_str(); }
 
 int vxl_ctx_create(int device, vxl_ctx** out) {
@@ -317,95 +407,122 @@ int vxl_lighting(vxl_ctx* c, vxl_volume* vol, const vxl_lighting_host_args* a) {
     return rc;
 }
 
-int vxl_lighting_host(vxl_ctx* c, vxl_volume* vol, const vxl_lighting_host_args* a) {
-    if (!c || !vol || !a || !a->view) { set_error("vxl_lighting_host: bad argument"); return VXL_ERR_INVALID; }
-    if (a->n_point < 0 || a->n_spot < 0 || a->n_point > VXL_MAX_LIGHTS || a->n_spot > VXL_MAX_LIGHTS) { set_error("vxl_lighting_host: light count out of range"); return VXL_ERR_LIMIT; }
+// Both host drop-ins.  packed == nullptr: float planes out (vxl_lighting_host); else the packed planes (vxl_lighting_host_packed).
+static int lighting_host_impl(vxl_ctx* c, vxl_volume* vol, const vxl_lighting_host_args* a, const vxl_packed_planes* packed) {
+    const char* const who = packed ? "vxl_lighting_host_packed" : "vxl_lighting_host";
+    if (!c || !vol || !a || !a->view) { set_error(std::string(who) + ": bad argument"); return VXL_ERR_INVALID; }
+    if (a->n_point < 0 || a->n_spot < 0 || a->n_point > VXL_MAX_LIGHTS || a->n_spot > VXL_MAX_LIGHTS) { set_error(std::string(who) + ": light count out of range"); return VXL_ERR_LIMIT; }
     FrameView Fh;
     if (int e = frame_view(&a->frame, &Fh)) return e;
     const size_t px = frame_pixels(&a->frame);
     if (px == 0) return VXL_OK;
-    const bool want_amb = a->out_shadow || a->out_ao;
-    const bool want_pt = a->n_point > 0 && a->out_point_shadow;
-    const bool want_sp = a->n_spot > 0 && a->out_spot_shadow;
-    const bool want_rf = a->out_spec_t != nullptr;
-    if (want_rf && !a->frame.material) { set_error("vxl_lighting_host: spec pass needs frame.material"); return VXL_ERR_INVALID; }
-    // the host drop-in writes to its own staging planes: no mirrored stores, default plane stride (restored on every exit path)
-    struct Restore { vxl_ctx* c; int n; size_t st; ~Restore() { c->n_mirror = n; c->light_plane_stride = st; } } restore{c, c->n_mirror, c->light_plane_stride};
-    c->n_mirror = 0; c->light_plane_stride = 0;
+    const bool want_mask = packed && packed->shadow_mask;
+    const bool want_sun = packed ? want_mask : a->out_shadow != nullptr;
+    const bool want_ao = packed ? packed->ao != nullptr : a->out_ao != nullptr;
+    const bool want_amb = want_sun || want_ao;
+    const bool want_pt = a->n_point > 0 && (packed ? want_mask : a->out_point_shadow != nullptr);
+    const bool want_sp = a->n_spot > 0 && (packed ? want_mask : a->out_spot_shadow != nullptr);
+    const bool want_rf = packed ? packed->spec_code != nullptr : a->out_spec_t != nullptr;
+    if (want_rf && !a->frame.material) { set_error(std::string(who) + ": spec pass needs frame.material"); return VXL_ERR_INVALID; }
+    if ((want_pt && !a->point) || (want_sp && !a->spot)) { set_error(std::string(who) + ": light list is NULL"); return VXL_ERR_INVALID; }
     VXL_CUDA(cudaSetDevice(c->device));
-    if (int e = ensure((void**)&c->h_planes, &c->h_planes_bytes, px * 4 * 3)) return e;
-    const size_t n_out = 3 + (size_t)a->n_point + (size_t)a->n_spot;
-    if (int e = ensure((void**)&c->h_out, &c->h_out_bytes, px * 4 * n_out)) return e;
-    if (!c->h_noise) VXL_CUDA(cudaMalloc(&c->h_noise, 512 * 512 * 4));
-    uint32_t* d_depth = c->h_planes; uint32_t* d_normal = d_depth + px; uint32_t* d_mat = d_normal + px;
-    // Three streams: uploads, passes (the context's stream), read-backs; the frame goes through in NB row bands (rows of
-    // every tile of the shard).  PCIe is full duplex and the copy engines run beside the SMs, so band b+1 uploads and band
-    // b-1 reads back while band b is in the passes; within a band the local-light planes (the largest output) go first.
-    int NB = a->frame.tile_h >= 256 ? 4 : 1;
-    if (const char* nb = getenv("VXL_HOST_BANDS")) NB = std::max(1, std::min(64, atoi(nb)));   // tuning knob
-    const int band_h = ((a->frame.tile_h + NB - 1) / NB + 15) / 16 * 16;          // whole 16-row thread blocks
-    const size_t n_ev = 2 + (size_t)NB * 5;
     if (!c->s_h2d) {
         VXL_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
         VXL_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
     }
+    // The host drop-in writes to its own staging planes (no mirrored stores, default plane stride) and walks the frame in row
+    // bands.  Whatever path leaves this function -- including a CUDA error in the middle of the band loop -- the context gets its
+    // mirror / stride / band state back and the two copy streams are joined to the context's stream again.
+    struct Restore {
+        vxl_ctx* c; int n; size_t st; cudaEvent_t join[2] = {nullptr, nullptr};
+        ~Restore() {
+            c->n_mirror = n; c->light_plane_stride = st; c->band_row0 = 0; c->band_rows = 0;
+            cudaStream_t side[2] = {c->s_h2d, c->s_d2h};
+            for (int i = 0; i < 2; ++i)
+                if (join[i] && cudaEventRecord(join[i], side[i]) == cudaSuccess) cudaStreamWaitEvent(c->stream, join[i], 0);
+        }
+    } restore{c, c->n_mirror, c->light_plane_stride};
+    c->n_mirror = 0; c->light_plane_stride = 0;
+    if (int e = ensure((void**)&c->h_planes, &c->h_planes_bytes, px * 4 * 3)) return e;
+    const size_t n_out = 3 + (size_t)a->n_point + (size_t)a->n_spot;
+    const int n_planes = 1 + a->n_point + a->n_spot, mask_bytes = (n_planes + 7) / 8;
+    // float planes, then (packed mode) the mask and code planes
+    if (int e = ensure((void**)&c->h_out, &c->h_out_bytes, px * 4 * n_out + (packed ? px * (size_t)(mask_bytes + 1) : 0))) return e;
+    if (!c->h_noise) VXL_CUDA(cudaMalloc(&c->h_noise, 512 * 512 * 4));
+    uint32_t* d_depth = c->h_planes; uint32_t* d_normal = d_depth + px; uint32_t* d_mat = d_normal + px;
+    // Three streams: uploads, passes (the context's stream), read-backs; the frame goes through in NB row bands (rows of
+    // every tile of the shard).  PCIe is full duplex and the copy engines run beside the SMs, so band b+1 uploads and band
+    // b-1 reads back while band b is in the passes; within a band the largest output goes first.
+    int NB = a->frame.tile_h >= 256 ? 4 : 1;
+    if (const char* nb = getenv("VXL_HOST_BANDS")) NB = std::max(1, std::min(64, atoi(nb)));   // tuning knob
+    const int band_h = ((a->frame.tile_h + NB - 1) / NB + 15) / 16 * 16;          // whole 16-row thread blocks
+    const size_t n_ev = 4 + (size_t)NB * 5;
     while (c->ev.size() < n_ev) { cudaEvent_t e; VXL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->ev.push_back(e); }
     cudaEvent_t* ev = c->ev.data();
     const size_t tile_px = (size_t)a->frame.tile_w * a->frame.tile_h;
     const int nt = a->frame.n_tiles;
-    // rows [r0, r0 + rows) of every tile of a tile-compact plane: nt chunks of rows * tile_w pixels, tile_px apart
-    auto copy_band = [&](void* dst, const void* src, int r0, int rows, cudaMemcpyKind kind, cudaStream_t st) -> cudaError_t {
-        const size_t off = (size_t)r0 * a->frame.tile_w * 4;
-        if (nt == 1) return cudaMemcpyAsync((char*)dst + off, (const char*)src + off, (size_t)rows * a->frame.tile_w * 4, kind, st);
-        return cudaMemcpy2DAsync((char*)dst + off, tile_px * 4, (const char*)src + off, tile_px * 4, (size_t)rows * a->frame.tile_w * 4, (size_t)nt, kind, st);
+    // rows [r0, r0 + rows) of every tile of a tile-compact plane of `el`-byte pixels: nt chunks of rows * tile_w pixels, tile_px apart
+    auto copy_band = [&](void* dst, const void* src, int r0, int rows, size_t el, cudaMemcpyKind kind, cudaStream_t st) -> cudaError_t {
+        const size_t off = (size_t)r0 * a->frame.tile_w * el;
+        if (nt == 1) return cudaMemcpyAsync((char*)dst + off, (const char*)src + off, (size_t)rows * a->frame.tile_w * el, kind, st);
+        return cudaMemcpy2DAsync((char*)dst + off, tile_px * el, (const char*)src + off, tile_px * el, (size_t)rows * a->frame.tile_w * el, (size_t)nt, kind, st);
     };
     VXL_CUDA(cudaEventRecord(ev[0], c->stream));                          // order behind whatever the caller queued (voxelise, ...)
     VXL_CUDA(cudaStreamWaitEvent(c->s_h2d, ev[0], 0));
     VXL_CUDA(cudaStreamWaitEvent(c->s_d2h, ev[0], 0));
+    restore.join[0] = ev[2]; restore.join[1] = ev[3];                     // from here on the side streams carry work
     VXL_CUDA(cudaMemcpyAsync(c->h_noise, a->frame.noise, 512 * 512 * 4, cudaMemcpyHostToDevice, c->s_h2d));
     vxl_frame fd = a->frame;
     fd.depth24 = d_depth; fd.normal = d_normal; fd.material = d_mat; fd.noise = c->h_noise;
     float* o_shadow = c->h_out; float* o_ao = o_shadow + px; float* o_spec = o_ao + px;
     float* o_pt = o_spec + px; float* o_sp = o_pt + px * (size_t)a->n_point;
-    int rc = VXL_OK;
-    for (int b = 0; b < NB && rc == VXL_OK; ++b) {
+    uint8_t* o_mask = reinterpret_cast<uint8_t*>(o_sp + px * (size_t)a->n_spot); uint8_t* o_code = o_mask + px * (size_t)mask_bytes;
+    for (int b = 0; b < NB; ++b) {
         const int r0 = b * band_h, rows = std::min(band_h, a->frame.tile_h - r0);
         if (rows <= 0) break;
-        cudaEvent_t* eb = ev + 2 + (size_t)b * 5;
-        VXL_CUDA(copy_band(d_depth, a->frame.depth24, r0, rows, cudaMemcpyHostToDevice, c->s_h2d));
-        VXL_CUDA(copy_band(d_normal, a->frame.normal, r0, rows, cudaMemcpyHostToDevice, c->s_h2d));
-        if (want_rf) VXL_CUDA(copy_band(d_mat, a->frame.material, r0, rows, cudaMemcpyHostToDevice, c->s_h2d));
+        cudaEvent_t* eb = ev + 4 + (size_t)b * 5;
+        VXL_CUDA(copy_band(d_depth, a->frame.depth24, r0, rows, 4, cudaMemcpyHostToDevice, c->s_h2d));
+        VXL_CUDA(copy_band(d_normal, a->frame.normal, r0, rows, 4, cudaMemcpyHostToDevice, c->s_h2d));
+        if (want_rf) VXL_CUDA(copy_band(d_mat, a->frame.material, r0, rows, 4, cudaMemcpyHostToDevice, c->s_h2d));
         VXL_CUDA(cudaEventRecord(eb[0], c->s_h2d));
         VXL_CUDA(cudaStreamWaitEvent(c->stream, eb[0], 0));
         c->band_row0 = r0; c->band_rows = rows;
-        if (want_pt && rc == VXL_OK) {
-            rc = vxl_pass_point(c, vol, a->view, &fd, a->point, a->n_point, o_pt);
-            if (rc == VXL_OK) {
-                cudaEventRecord(eb[1], c->stream); cudaStreamWaitEvent(c->s_d2h, eb[1], 0);
-                for (int l = 0; l < a->n_point; ++l) copy_band(a->out_point_shadow + px * (size_t)l, o_pt + px * (size_t)l, r0, rows, cudaMemcpyDeviceToHost, c->s_d2h);
+        if (want_pt) {
+            if (int e = vxl_pass_point(c, vol, a->view, &fd, a->point, a->n_point, o_pt)) return e;
+            if (!packed) {
+                VXL_CUDA(cudaEventRecord(eb[1], c->stream)); VXL_CUDA(cudaStreamWaitEvent(c->s_d2h, eb[1], 0));
+                for (int l = 0; l < a->n_point; ++l) VXL_CUDA(copy_band(a->out_point_shadow + px * (size_t)l, o_pt + px * (size_t)l, r0, rows, 4, cudaMemcpyDeviceToHost, c->s_d2h));
             }
         }
-        if (want_sp && rc == VXL_OK) {
-            rc = vxl_pass_spot(c, vol, a->view, &fd, a->spot, a->n_spot, o_sp);
-            if (rc == VXL_OK) {
-                cudaEventRecord(eb[2], c->stream); cudaStreamWaitEvent(c->s_d2h, eb[2], 0);
-                for (int l = 0; l < a->n_spot; ++l) copy_band(a->out_spot_shadow + px * (size_t)l, o_sp + px * (size_t)l, r0, rows, cudaMemcpyDeviceToHost, c->s_d2h);
+        if (want_sp) {
+            if (int e = vxl_pass_spot(c, vol, a->view, &fd, a->spot, a->n_spot, o_sp)) return e;
+            if (!packed) {
+                VXL_CUDA(cudaEventRecord(eb[2], c->stream)); VXL_CUDA(cudaStreamWaitEvent(c->s_d2h, eb[2], 0));
+                for (int l = 0; l < a->n_spot; ++l) VXL_CUDA(copy_band(a->out_spot_shadow + px * (size_t)l, o_sp + px * (size_t)l, r0, rows, 4, cudaMemcpyDeviceToHost, c->s_d2h));
             }
         }
-        if (want_amb && rc == VXL_OK) {
-            rc = vxl_pass_ambient(c, vol, a->view, &fd, a->n_ao, a->out_shadow ? o_shadow : nullptr, a->out_ao ? o_ao : nullptr);
-            if (rc == VXL_OK) {
-                cudaEventRecord(eb[3], c->stream); cudaStreamWaitEvent(c->s_d2h, eb[3], 0);
-                if (a->out_shadow) copy_band(a->out_shadow, o_shadow, r0, rows, cudaMemcpyDeviceToHost, c->s_d2h);
-                if (a->out_ao) copy_band(a->out_ao, o_ao, r0, rows, cudaMemcpyDeviceToHost, c->s_d2h);
+        if (want_amb) {
+            if (int e = vxl_pass_ambient(c, vol, a->view, &fd, a->n_ao, want_sun ? o_shadow : nullptr, want_ao ? o_ao : nullptr)) return e;
+            VXL_CUDA(cudaEventRecord(eb[3], c->stream)); VXL_CUDA(cudaStreamWaitEvent(c->s_d2h, eb[3], 0));
+            if (!packed && a->out_shadow) VXL_CUDA(copy_band(a->out_shadow, o_shadow, r0, rows, 4, cudaMemcpyDeviceToHost, c->s_d2h));
+            if (want_ao) VXL_CUDA(copy_band(packed ? packed->ao : a->out_ao, o_ao, r0, rows, 4, cudaMemcpyDeviceToHost, c->s_d2h));
+        }
+        if (want_rf) {
+            if (int e = vxl_pass_reflection(c, vol, a->view, &fd, o_spec)) return e;
+            if (!packed) {
+                VXL_CUDA(cudaEventRecord(eb[4], c->stream)); VXL_CUDA(cudaStreamWaitEvent(c->s_d2h, eb[4], 0));
+                VXL_CUDA(copy_band(a->out_spec_t, o_spec, r0, rows, 4, cudaMemcpyDeviceToHost, c->s_d2h));
             }
         }
-        if (want_rf && rc == VXL_OK) {
-            rc = vxl_pass_reflection(c, vol, a->view, &fd, o_spec);
-            if (rc == VXL_OK) {
-                cudaEventRecord(eb[4], c->stream); cudaStreamWaitEvent(c->s_d2h, eb[4], 0);
-                copy_band(a->out_spec_t, o_spec, r0, rows, cudaMemcpyDeviceToHost, c->s_d2h);
-            }
+        if (packed && (want_mask || want_rf)) {
+            const size_t n = (size_t)rows * a->frame.tile_w * (size_t)nt;
+            k_pack_planes<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(want_sun ? o_shadow : nullptr, o_pt, want_pt ? a->n_point : 0, o_sp, want_sp ? a->n_spot : 0, px,
+                                                                              o_spec, want_mask ? o_mask : nullptr, mask_bytes, want_rf ? o_code : nullptr,
+                                                                              a->frame.tile_w, a->frame.tile_h, r0, rows, nt);
+            VXL_LAUNCH_CHECK(c);
+            VXL_CUDA(cudaEventRecord(eb[4], c->stream)); VXL_CUDA(cudaStreamWaitEvent(c->s_d2h, eb[4], 0));
+            if (want_mask) VXL_CUDA(copy_band(packed->shadow_mask, o_mask, r0, rows, (size_t)mask_bytes, cudaMemcpyDeviceToHost, c->s_d2h));
+            if (want_rf) VXL_CUDA(copy_band(packed->spec_code, o_code, r0, rows, 1, cudaMemcpyDeviceToHost, c->s_d2h));
         }
     }
     c->band_row0 = 0; c->band_rows = 0;
@@ -413,9 +530,15 @@ int vxl_lighting_host(vxl_ctx* c, vxl_volume* vol, const vxl_lighting_host_args*
     VXL_CUDA(cudaStreamWaitEvent(c->stream, ev[1], 0));                   // the context's stream stays the single point of order
     VXL_CUDA(cudaStreamSynchronize(c->s_h2d));
     VXL_CUDA(cudaStreamSynchronize(c->stream));
-    if (rc != VXL_OK) return rc;
     if (cudaError_t e = cudaGetLastError()) return cuda_fail(e, "vxl_lighting_host copies");
     return VXL_OK;
+}
+
+int vxl_lighting_host(vxl_ctx* c, vxl_volume* vol, const vxl_lighting_host_args* a) { return lighting_host_impl(c, vol, a, nullptr); }
+
+int vxl_lighting_host_packed(vxl_ctx* c, vxl_volume* vol, const vxl_lighting_host_args* a, const vxl_packed_planes* out) {
+    if (!out) { set_error("vxl_lighting_host_packed: out is NULL"); return VXL_ERR_INVALID; }
+    return lighting_host_impl(c, vol, a, out);
 }
 
 }  // extern "C"

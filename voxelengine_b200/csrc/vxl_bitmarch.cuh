@@ -18,6 +18,8 @@
 // origins; neighbouring pixels start within a few voxels of each other (median spread 2 voxels at 4K).
 #pragma once
 #include "vxl_internal.h"
+#include <cmath>
+#include <cstring>
 #include "vxl_math.cuh"
 #include "vxl_trace.cuh"
 
@@ -431,6 +433,129 @@ VXL_DI unsigned scan_super_cand(const BitTile& T, float3 origin, float3 dir, boo
     return cand >> (32 - N);
 }
 
+// ---- two rays per lane, packed (sm_100a add.f32x2) ------------------------------------------------------------------------
+// The scan is bound by issue slots (13 per probe: 3 FADD recurrence + 3 FADD.RZ cell index + 4 address + LDS + 2 funnel shifts), not
+// by FP throughput.  Blackwell's FADD2 adds two independent binary32 pairs in one issue slot with the same IEEE rounding per half
+// (rn for the recurrence, rz for the magic floor), so two rays that share an origin (two AO rays of a pixel) scan side by side with
+// 6 packed additions per probe PAIR instead of 12: 10 issue slots per probe.  Same values, bit for bit.
+struct F2 {
+#ifdef __CUDA_ARCH__
+    unsigned long long v;
+#else
+    float lo, hi;
+#endif
+};
+VXL_DI F2 f2_pack(float lo, float hi) {
+    F2 r;
+#ifdef __CUDA_ARCH__
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+#else
+    r.lo = lo; r.hi = hi;
+#endif
+    return r;
+}
+VXL_DI F2 f2_add(F2 a, F2 b) {
+    F2 r;
+#ifdef __CUDA_ARCH__
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+#else
+    r.lo = a.lo + b.lo; r.hi = a.hi + b.hi;
+#endif
+    return r;
+}
+#ifndef __CUDA_ARCH__
+// host emulation of add.rz.f32: the exact sum in double (53 bits hold any sum of two binary32 of the magnitudes used here), truncated
+VXL_DI unsigned host_add_rz_bits(float a, float b) {
+    const double e = (double)a + (double)b;
+    float r = (float)e;                                   // round to nearest
+    if (fabs((double)r) > fabs(e)) r = nextafterf(r, 0.0f);
+    unsigned u;
+    memcpy(&u, &r, 4);
+    return u;
+}
+#endif
+// both halves of (p + m) rounded toward zero, as raw bits (magic_floor_bits on two values)
+VXL_DI void f2_floor_bits(F2 p, F2 m, int S, int o, unsigned& lo, unsigned& hi) {
+#ifdef __CUDA_ARCH__
+    (void)S; (void)o;
+    unsigned long long r;
+    asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(p.v), "l"(m.v));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(r));
+#else
+    (void)S; (void)o;
+    lo = host_add_rz_bits(p.lo, m.lo); hi = host_add_rz_bits(p.hi, m.hi);
+#endif
+}
+
+// Where the probes of one stretch of a scan look: a bit tile ([z][y][x word], 32 cells per word) described by run-time values, so
+// that ONE unrolled scan serves the near tile, the block's main tile and the level array in global memory.
+//   b_a  = MB + rel_a  (float bits of p_a + m_a rounded toward zero; MB = 0x4B000000 + (S << 23), a multiple of 32)
+//   word = rel_z * sz + rel_y * sy + (rel_x >> 5) = b_z * sz + b_y * sy + (b_x >> 5) - CC,  CC = MB * (sz + sy) + (MB >> 5)   (mod 2^32)
+// SY / SZ > 0: the strides are compile-time constants (immediate operands); 0: taken from sy / sz.
+template <bool GLOBAL, unsigned SY = 0, unsigned SZ = 0>
+struct ScanLook {
+    float mx, my, mz;          // 2^(23+S) - o_a * 2^S
+    unsigned sy, sz;           // words per row / per slice
+    unsigned sbase;            // shared memory: byte address of word 0 minus 4 * CC (wraps); global memory: CC
+    const uint32_t* w;         // word 0 (global memory; host emulation)
+    VXL_DI static ScanLook make(const uint32_t* words, int S, int ox, int oy, int oz, unsigned sy_, unsigned sz_) {
+        ScanLook L;
+        const float M = (float)(1 << 23) * (float)(1 << S), cell = (float)(1 << S);
+        L.mx = M - (float)ox * cell; L.my = M - (float)oy * cell; L.mz = M - (float)oz * cell;
+        L.sy = SY ? SY : sy_; L.sz = SZ ? SZ : sz_; L.w = words;
+        const unsigned MB = 0x4B000000u + ((unsigned)S << 23);
+        const unsigned CC = MB * (L.sz + L.sy) + (MB >> 5);
+#ifdef __CUDA_ARCH__
+        L.sbase = GLOBAL ? CC : (unsigned)__cvta_generic_to_shared(words) - 4u * CC;
+#else
+        L.sbase = CC;
+#endif
+        return L;
+    }
+    VXL_DI unsigned word(unsigned bx, unsigned by, unsigned bz) const {
+        const unsigned idx = bz * (SZ ? SZ : sz) + by * (SY ? SY : sy) + (bx >> 5);
+#ifdef __CUDA_ARCH__
+        if (GLOBAL) return __ldg(w + (idx - sbase));
+        unsigned v;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sbase + 4u * idx));
+        return v;
+#else
+        return w[idx - sbase];
+#endif
+    }
+};
+
+// scan_super_cand for two rays from the same origin (two AO rays of a pixel): probe k of ray a / b ends up in bit k of cand_a /
+// cand_b.  The first KN = 8 probes look at `first` (the near tile when the pixel's rays stay inside it, else the same as `rest`).
+template <int N2, typename LookA, typename LookB>
+VXL_DI void scan_super_pair(const LookA& first, const LookB& rest, float3 origin, float3 dir_a, float3 dir_b,
+                            unsigned& cand_a, unsigned& cand_b) {
+    constexpr int N1 = 6, N = N1 + N2, KN = 8;
+    static_assert(N <= 32 && KN <= N, "candidate mask is one word");
+    const float3 s1a = dir_a * 2.5f, s1b = dir_b * 2.5f;
+    const float3 s2a = s1a * 2.0f, s2b = s1b * 2.0f;
+    const F2 s1x = f2_pack(s1a.x, s1b.x), s1y = f2_pack(s1a.y, s1b.y), s1z = f2_pack(s1a.z, s1b.z);
+    const F2 s2x = f2_pack(s2a.x, s2b.x), s2y = f2_pack(s2a.y, s2b.y), s2z = f2_pack(s2a.z, s2b.z);
+    F2 px = f2_pack(origin.x, origin.x), py = f2_pack(origin.y, origin.y), pz = f2_pack(origin.z, origin.z);
+    unsigned ca = 0u, cb = 0u;
+    auto look = [&](const auto& L) {
+        unsigned xa, xb, ya, yb, za, zb;
+        f2_floor_bits(px, f2_pack(L.mx, L.mx), 0, 0, xa, xb);
+        f2_floor_bits(py, f2_pack(L.my, L.my), 0, 0, ya, yb);
+        f2_floor_bits(pz, f2_pack(L.mz, L.mz), 0, 0, za, zb);
+        ca = funnel_r(ca, funnel_r(L.word(xa, ya, za), 0u, xa), 1u);
+        cb = funnel_r(cb, funnel_r(L.word(xb, yb, zb), 0u, xb), 1u);
+    };
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        if (k < KN) look(first); else look(rest);
+        if (k + 1 <= N1) { px = f2_add(px, s1x); py = f2_add(py, s1y); pz = f2_add(pz, s1z); }      // the addition after probe 5 still uses s1 (:151)
+        else if (k + 1 < N) { px = f2_add(px, s2x); py = f2_add(py, s2y); pz = f2_add(pz, s2z); }
+    }
+    cand_a = ca >> (32 - N);
+    cand_b = cb >> (32 - N);
+}
+
 // The reference's own test of candidate probe k (see above): true = the march returns at this probe.
 // PHASE: 0 = k decides; 1 / 2 = the caller knows k < 6 / k >= 6 (only that test is compiled in).
 template <bool COUNT, bool NEAR, int SHIFT, int TY, int TW, int N2, int PHASE = 0>
@@ -469,6 +594,56 @@ VXL_DI bool resolve_super_cand(const VolView& V, const BitTile& T, float3 origin
         off = TA::texel_offset(V, T.koff, p);
     }
     return V.bytes[off] != 0u;
+}
+
+// Light.frag:142-146 for one coordinate 0 <= x < 2^21:  mod(x, 0.5) > 0.25.  The shader's float evaluation is exact (2x, floor, the
+// product with 0.5 and the final difference are all representable), so the test is frac(2x) > 0.5, i.e. m = floor(4x) is odd and
+// 4x != m.  x + 2^21 rounded toward zero has m in its low mantissa bits, and the addition was inexact iff 4x was not an integer.
+VXL_DI unsigned hash_bit1(float x) {
+#ifdef __CUDA_ARCH__
+    const float r = __fadd_rz(x, 2097152.0f);
+    return (__float_as_uint(r) & 1u) & (unsigned)(__fadd_rn(r, -2097152.0f) != x);
+#else
+    return gmod(x, 0.5f) > 0.25f ? 1u : 0u;
+#endif
+}
+
+// The reference's test of candidate probe k of a scanned SuperSparse ray, as one converged piece of code for a warp that holds a mix
+// of phase-1 (k < 6) and phase-2 candidates (ao_pooled's resolve passes).  Both phases fetch ONE texel byte; they differ in the position
+// it is fetched at -- phase 1 replays the recurrence (<= 5 predicated additions: its bit hash needs the exact position), phase 2
+// uses q = fma(s1, 2k - 6, origin) with the eps argument of resolve_super_cand -- and in the final test of the byte.
+// near_ok: the ray's first 8 probes were scanned against the near tile, where a set bit of probe 6 / 7 IS the reference's test.
+template <bool COUNT>
+VXL_DI bool test_super_cand(const VolView& V, unsigned koff, float3 origin, float3 s1, int k, bool near_ok, float eps, unsigned& fetched) {
+    constexpr int N1 = 6, KN = 8;
+    if (near_ok && k >= N1 && k < KN) return true;
+    const bool ph1 = k < N1;
+    float3 p = origin;
+#pragma unroll
+    for (int i = 0; i < N1 - 1; ++i)
+        if (i < k) p = p + s1;                                         // exact for k < 6; unused otherwise
+    const float3 q = fma3(s1, (float)(2 * k - N1), origin);
+    const float3 pos = ph1 ? p : q;
+    const float e = ph1 ? 0.0f : eps;
+    const float M1 = 16777216.0f;
+    const unsigned ax = magic_floor_bits(pos.x - e, M1, 1, 0), bx = magic_floor_bits(pos.x + e, M1, 1, 0);
+    const unsigned ay = magic_floor_bits(pos.y - e, M1, 1, 0), by = magic_floor_bits(pos.y + e, M1, 1, 0);
+    const unsigned az = magic_floor_bits(pos.z - e, M1, 1, 0), bz = magic_floor_bits(pos.z + e, M1, 1, 0);
+    unsigned off = bz * (unsigned)(V.sx * V.sy) + by * (unsigned)V.sx + bx - koff;
+    if ((ax ^ bx) | (ay ^ by) | (az ^ bz)) {                           // phase 2 within eps of a texel face (about 1 %): exact position
+        const float3 s2 = s1 * 2.0f;
+        float3 r = origin;
+#pragma unroll 1
+        for (int i = 0; i < k; ++i) r = r + (i < N1 ? s1 : s2);
+        const unsigned tx = magic_floor_bits(r.x, M1, 1, 0), ty = magic_floor_bits(r.y, M1, 1, 0), tz = magic_floor_bits(r.z, M1, 1, 0);
+        off = tz * (unsigned)(V.sx * V.sy) + ty * (unsigned)V.sx + tx - koff;
+    }
+    if (COUNT) ++fetched;
+    const unsigned v = ldg(V.bytes + off);
+    if (v == 0u) return false;
+    if (!ph1) return true;
+    const unsigned bit = hash_bit1(pos.x) | (hash_bit1(pos.y) << 1) | (hash_bit1(pos.z) << 2);
+    return ((v >> bit) & 1u) != 0u;
 }
 
 VXL_DI float super_hit_distance(int hit) { return hit < 6 ? 2.5f * (float)(hit + 1) : 17.5f + 5.0f * (float)(hit - 6); }

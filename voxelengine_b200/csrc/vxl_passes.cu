@@ -24,20 +24,27 @@ struct BlockShared {
     uint32_t tile[G::TY * G::TY * G::TW];     // from here on: kernel variant 0 allocates only the header
     uint32_t dtile[G::DT * G::DT * G::DW];
     uint32_t ntile[G::NEAR ? NEAR_T * NEAR_T : 1];
+    // pooled AO resolve (ao_pooled): per warp a stack of pending candidate tests and the per-pixel AO sums
+    uint4 q_ent[G::QCAP ? BLOCK_THREADS / 32 : 1][G::QCAP ? G::QCAP : 1];       // (s1.xyz, remaining candidate bits)
+    uint8_t q_own[G::QCAP ? BLOCK_THREADS / 32 : 1][G::QCAP ? G::QCAP : 4];     // owner lane | near_ok << 5
+    unsigned ao_acc[G::QCAP ? BLOCK_THREADS : 1];                               // sum of (256 d / 128)^2 over the rays resolved from the stack
 };
 template <typename G, bool FAST>
 constexpr size_t smem_bytes() {
     typedef BlockShared<G> BS;
-    return FAST ? sizeof(BS) : sizeof(BS) - sizeof(uint32_t) * (G::TY * G::TY * G::TW + G::DT * G::DT * G::DW + (G::NEAR ? NEAR_T * NEAR_T : 1));
+    return FAST ? sizeof(BS) : offsetof(BS, tile);
 }
 // Tile geometry per pass.  Plain tile: cells of 2^SHIFT voxels, TW*32 x TY x TY cells.  Dilated tile: cells of
 // 2^(SHIFT+1) voxels, DW*32 x DT x DT cells, covering at least the plain tile.  GH: half width of a probe group of the
 // Sparse march (GH * max|stepDir_a| must stay <= the dilated cell: 7 * 1.0 <= 8, 10 * 1.5 <= 16).
 // NEAR: also stage the near tile (texel bits of the 64^3 voxels around the ray origins, 4 KB; vxl_bitmarch.cuh).
 // 57.1 / 58.8 KB + 10.4 KB + 4 KB LUTs (+ 4 KB near tile) per block: three 512-thread blocks per SM (<= 75 KB each).
-struct AmbientGeom { static constexpr int SHIFT = 2, TY = 69, TW = 3, DT = 36, DW = 2, GH = 7; static constexpr bool NEAR = true; };     // +-138 voxels (AO 128, sun 128)
-struct LocalGeom   { static constexpr int SHIFT = 2, TY = 70, TW = 3, DT = 36, DW = 2, GH = 7; static constexpr bool NEAR = false; };    // point/spot rays beyond +-140 voxels take the plain march
-struct ReflGeom    { static constexpr int SHIFT = 3, TY = 70, TW = 3, DT = 36, DW = 2, GH = 10; static constexpr bool NEAR = false; };   // +-280 voxels (164 steps * |wd| <= 1.5)
+#ifndef VXL_AO_QCAP
+#define VXL_AO_QCAP 64            // pending candidate tests per warp (>= 63: 31 left over + 32 new); 0 = per-lane resolve (round-1 kernel)
+#endif
+struct AmbientGeom { static constexpr int SHIFT = 2, TY = 69, TW = 3, DT = 36, DW = 2, GH = 7, QCAP = VXL_AO_QCAP; static constexpr bool NEAR = true; };     // +-138 voxels (AO 128, sun 128)
+struct LocalGeom   { static constexpr int SHIFT = 2, TY = 70, TW = 3, DT = 36, DW = 2, GH = 7, QCAP = 0; static constexpr bool NEAR = false; };    // point/spot rays beyond +-140 voxels take the plain march
+struct ReflGeom    { static constexpr int SHIFT = 3, TY = 70, TW = 3, DT = 36, DW = 2, GH = 10, QCAP = 0; static constexpr bool NEAR = false; };   // +-280 voxels (164 steps * |wd| <= 1.5)
 
 // Bounding box of the block's ray origins -> tile placement -> stage the occupancy tile.
 // `hint` is (close to) the thread's ray origin in voxel units; threads without rays pass valid = false.
@@ -110,11 +117,194 @@ __device__ __forceinline__ void flush_stats(BS& S, unsigned long long* __restric
 
 constexpr int AO_N2 = 23;          // phase-2 probes of a SuperSparse ray with dist = 128: d = 17.5, 22.5, ..., 127.5 (:121)
 
+
+// (256 * d / 128)^2 of a SuperSparse ray that returns at probe k: d = 2.5 (k + 1) in phase 1, 17.5 + 5 (k - 6) = 2.5 (2k - 5) in
+// phase 2 (Light.frag:181-211), so 256 d / 128 = 5 (k + 1) or 5 (2k - 5); a miss returns dist = 128 -> 256.
+__device__ __forceinline__ unsigned ao_term(int k) {
+    const unsigned n = 5u * (unsigned)(k < 6 ? k + 1 : 2 * k - 5);
+    return n * n;
+}
+constexpr unsigned AO_MISS = 65536u;
+constexpr int AO_POOL_MAX_RAYS = 256;     // the sums below stay < 2^24, where float and integer accumulation agree exactly
+
+// One AO ray the slow way (a pixel whose rays leave the volume, or whose coordinates are too large for the scan's folded
+// addressing): the per-ray tile march / plain march of round 1.  Cold code, one copy.
+template <int MODE, typename G>
+__device__ __noinline__ float ao_ray_slow(const VolView& V, const BitTile& C, float3 origin, float3 dir, int& steps, unsigned& exact) {
+    const float d = march_scan_super<false, MODE == 2, G::NEAR, G::SHIFT, G::TY, G::TW, AO_N2>(V, C, origin, dir, 128.0f, steps, nullptr, exact) / 128.0f;   // :121
+    return d * d;
+}
+
+// The AO rays of a warp's 32 pixels with a pooled resolve (LightAmbient.frag:111-126, n_ao rays per pixel).
+//
+// Every lane scans its own rays, two at a time (scan_super_pair: all 29 probes of both, branch-free, packed f32x2 additions).
+// What the scan cannot decide -- a probe in an occupied cell needs the reference's texel test on the volume bytes -- used to be
+// resolved by the lane itself, a loop that ran at 4-8 live lanes (34 % of the round-1 kernel's instructions).  Here the undecided
+// rays go on a per-warp stack in shared memory, (2.5 dir, candidate bits, owner lane), and whenever 32 are pending the warp tests
+// the first candidate of each in one converged pass: a hit (or the last candidate failing) adds the ray's term to the owner's sum
+// with a shared-memory atomic, a failure with candidates left goes back on the stack.  The reference returns at the FIRST probe
+// whose test passes, and candidates are tested in probe order per ray, so the result is the same ray by ray.
+//
+// Where a pixel's rays look: the block's tiles in shared memory when the box around its rays lies inside them (scan_precheck);
+// otherwise -- far terrain, silhouettes: the block's ray origins spread over more voxels than the tile has slack -- the same scan
+// reads the 4-voxel level from global memory (L2-resident), as long as the box lies inside the volume.  Both feed the same stack.
+//
+// acc = sum over rays of (d / 128)^2 is exact in binary32 whatever the order: every term is a multiple of 2^-16 that is <= 1, so for
+// n_ao <= 256 all partial sums are multiples of 2^-16 below 2^8.  It is therefore kept as the integer sum of (256 d / 128)^2.
+template <int MODE, typename G>
+__device__ __forceinline__ float ao_pooled(const VolView& V, const BitTile& C, BlockShared<G>& S, const FrameView& F, const ViewK& K, const PixelCtx& p,
+                                           bool lit, float3 origin, float3 normal, uint32_t n0, int n_ao, int& steps, unsigned& exact) {
+    constexpr int N = 6 + AO_N2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    uint4* const qe = S.q_ent[warp];
+    uint8_t* const qo = S.q_own[warp];
+    unsigned* const wacc = S.ao_acc + warp * 32;
+    wacc[lane] = 0u;
+    float3 tangent = make_float3(0.f, 0.f, 0.f), bitangent = tangent;
+    // mode of this pixel: 0 = no rays, 1 = scan in shared memory, 2 = scan in global memory, 3 = slow path
+    int mode = 0;
+    bool near_ok = false;
+    if (lit) {
+        tangent = fabsf(normal.z) > 0.5f ? make_float3(0.0f, -normal.z, normal.y) : make_float3(-normal.y, normal.x, 0.0f);    // :112
+        bitangent = cross3(normal, tangent);                                                                                   // :113
+        // Every AO direction is tangent * x + bitangent * y + normal * z with (x, y, z) the LUT's hemisphere sample, x^2 + y^2 + z^2 =
+        // u (cos^2 + sin^2) + (1 - u) = 1 up to a few ulp: by Cauchy-Schwarz |dir_a| <= |(tangent_a, bitangent_a, normal_a)|, which
+        // is <= 1 for an orthonormal frame whatever its orientation.  One eligibility test per pixel covers all its rays (reach:
+        // 128 + 1 voxels of march, 20 for the near tile's 8 probes; the 1.0001 and scan_precheck's own factor and margin absorb the roundings).
+        const float3 bound = make_float3(sqrtf(tangent.x * tangent.x + bitangent.x * bitangent.x + normal.x * normal.x) * 1.0001f,
+                                         sqrtf(tangent.y * tangent.y + bitangent.y * bitangent.y + normal.y * normal.y) * 1.0001f,
+                                         sqrtf(tangent.z * tangent.z + bitangent.z * bitangent.z + normal.z * normal.z) * 1.0001f);
+        const ScanPre pre = scan_precheck<G::SHIFT, G::TY, G::TW>(C, origin, bound, 129.0f, 20.0f);
+        near_ok = pre.near_ok;
+        if (pre.ok) mode = 1;
+        else {
+            // the box around the rays inside the volume (and below the magic floor's coordinate limit): the level array can be indexed directly
+            const float3 r = bound * (129.0f * 1.00002f);
+            const float3 hi = make_float3(fminf((float)(2 * V.sx), BM_MAXCOORD), fminf((float)(2 * V.sy), BM_MAXCOORD), fminf((float)(2 * V.sz), BM_MAXCOORD));
+            const bool inside = C.direct && origin.x - r.x >= BM_MARGIN && origin.y - r.y >= BM_MARGIN && origin.z - r.z >= BM_MARGIN &&
+                                origin.x + r.x <= hi.x - BM_MARGIN && origin.y + r.y <= hi.y - BM_MARGIN && origin.z + r.z <= hi.z - BM_MARGIN;
+            mode = inside ? 2 : 3;                                                  // (NaN anywhere fails the comparisons)
+        }
+    }
+    // one eps for everybody (resolve_super_cand): no coordinate of a scanned ray exceeds the volume's extent
+    const float eps = (fminf((float)(2 * max(V.sx, max(V.sy, V.sz))), BM_MAXCOORD) + 1.0f) * (1.0f / 262144.0f);
+    typedef ScanLook<false, (unsigned)G::TW, (unsigned)(G::TY * G::TW)> TileLook;
+    const TileLook look_tile = TileLook::make(C.w, G::SHIFT, C.ox, C.oy, C.oz, 0u, 0u);
+    const ScanLook<false> look_near = (G::NEAR && near_ok) ? ScanLook<false>::make(C.wn, 1, C.nx, C.ny, C.nz, 1u, (unsigned)NEAR_T)
+                                                           : ScanLook<false>::make(C.w, G::SHIFT, C.ox, C.oy, C.oz, (unsigned)G::TW, (unsigned)(G::TY * G::TW));
+    int qn = 0;                       // entries on the stack (warp-uniform)
+    unsigned own = 0u;                // terms of the rays this lane decided itself
+    float accf = 0.0f;                // mode 3: sequential float sum like the reference
+    __syncwarp();
+
+    // what a lane can decide itself about a scanned ray; returns the candidate word that has to go on the stack (0 = decided)
+    auto decide = [&](unsigned cand) -> unsigned {
+#ifdef VXL_EXP_ABLATE             // timing experiments only (results are wrong): 1 = no resolve, 2 = no scan either
+        own += cand; cand = 0u;
+#endif
+        if (cand == 0u) { own += AO_MISS; steps += N; return 0u; }
+        if (G::NEAR && near_ok) {
+            // inside the near tile bits 6 and 7 ARE the reference's test (texel != 0): a first candidate there is the hit
+            const int k = __ffs((int)cand) - 1;
+            if (k == 6 || k == 7) { own += ao_term(k); steps += k + 1; return 0u; }
+        }
+        return cand;
+    };
+    // the noise texels of a ray pair are fetched one trip ahead, so that their L2 latency hides under the scan of the current pair
+    auto noise_of = [&](int i) -> uint32_t { return (i == 0) ? n0 : ((mode != 0 && i < n_ao) ? get_noise(F, K, p, i) : 0u); };
+    auto ray_dir = [&](uint32_t ni) -> float3 {
+        const float3 rv = cosine_sample_hemisphere(S.lut, ni, ni >> 8);                           // :118
+        return tangent * rv.x + bitangent * rv.y + normal * rv.z;                                 // :119
+    };
+    uint32_t na = noise_of(0), nb = noise_of(1);
+    const int n_pairs = (n_ao + 1) >> 1;
+    for (int it = 0; it <= n_pairs; ++it) {             // the last trip only drains the stack
+        unsigned ca = 0u, cb = 0u;
+        float3 sa = make_float3(0.f, 0.f, 0.f), sb = sa;
+        if (it < n_pairs && mode != 0) {
+            const int i = 2 * it;
+            const bool two = i + 1 < n_ao;
+            const float3 da = ray_dir(na), db = two ? ray_dir(nb) : da;                           // odd n_ao: the last ray scans twice, counts once
+            na = noise_of(i + 2); nb = noise_of(i + 3);
+            if (mode == 1) {
+#if defined(VXL_EXP_ABLATE) && VXL_EXP_ABLATE == 2
+                ca = __float_as_uint(da.x + da.y + da.z); cb = __float_as_uint(db.x + db.y + db.z);
+#else
+                scan_super_pair<AO_N2>(look_near, look_tile, origin, da, db, ca, cb);
+#endif
+            } else if (mode == 2) {
+                const BitView& L4 = V.occ[G::SHIFT - 2];
+                const ScanLook<true> look_glob = ScanLook<true>::make(L4.words, G::SHIFT, 0, 0, 0, (unsigned)L4.pitch, (unsigned)(L4.pitch * L4.cy));
+                scan_super_pair<AO_N2>(look_glob, look_glob, origin, da, db, ca, cb);
+            }
+            if (mode != 3) {
+                sa = da * 2.5f; sb = db * 2.5f;
+                ca = decide(ca);
+                cb = two ? decide(cb) : 0u;
+            } else {
+                accf += ao_ray_slow<MODE, G>(V, C, origin, da, steps, exact);
+                if (two) accf += ao_ray_slow<MODE, G>(V, C, origin, db, steps, exact);
+            }
+        }
+        // push the undecided rays, one ray of the pair per round (a round adds at most 32 entries to at most 31 left over),
+        // each followed by the converged passes over the top of the stack: ONE copy of that code for both rounds and for the
+        // final trip that drains whatever is left
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+        const unsigned ch = h ? cb : ca;
+        const unsigned mh = __ballot_sync(0xFFFFFFFFu, ch != 0u);
+        if (mh) {
+            if (ch != 0u) {
+                const float3 sh = h ? sb : sa;
+                const int idx = qn + __popc(mh & lt);
+                qe[idx] = make_uint4(__float_as_uint(sh.x), __float_as_uint(sh.y), __float_as_uint(sh.z), ch);
+                qo[idx] = (uint8_t)((unsigned)lane | (near_ok ? 32u : 0u));
+            }
+            qn += __popc(mh);
+            __syncwarp();
+        }
+        // converged passes over the top of the stack: full ones while rays are still being scanned, whatever is left at the end
+        const int need = it < n_pairs ? 32 : 1;
+        while (qn >= need) {
+            const int nb = qn < 32 ? qn : 32;
+            const int base = qn - nb;
+            const bool act = lane < nb;
+            uint4 e = make_uint4(0u, 0u, 0u, 1u);
+            unsigned ow = (unsigned)lane;
+            if (act) { e = qe[base + lane]; ow = qo[base + lane]; }
+            const int owner = (int)(ow & 31u);
+            const float3 o = make_float3(__shfl_sync(0xFFFFFFFFu, origin.x, owner), __shfl_sync(0xFFFFFFFFu, origin.y, owner), __shfl_sync(0xFFFFFFFFu, origin.z, owner));
+            const int k = __ffs((int)e.w) - 1;
+            const unsigned rest = e.w & (e.w - 1u);
+            const float3 s1 = make_float3(__uint_as_float(e.x), __uint_as_float(e.y), __uint_as_float(e.z));
+            const bool hit = act && test_super_cand<MODE == 2>(V, C.koff, o, s1, k, (ow >> 5) != 0u, eps, exact);
+            const bool done = act && (hit || rest == 0u);                 // the ray returns at probe k, or no candidate is left: a miss
+            if (done) {
+                atomicAdd(&wacc[owner], hit ? ao_term(k) : AO_MISS);
+                steps += hit ? k + 1 : N;
+            }
+            const bool again = act && !done;
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, again);
+            if (again) {
+                const int idx = base + __popc(m & lt);
+                qe[idx] = make_uint4(e.x, e.y, e.z, rest);
+                qo[idx] = (uint8_t)ow;
+            }
+            qn = base + __popc(m);
+            __syncwarp();
+        }
+        }
+    }
+    const float acc = mode == 3 ? accf : (float)(own + wacc[lane]) * (1.0f / 65536.0f);
+    return (acc / (float)n_ao) * 0.05f;                                                           // :125
+}
+
 // -------------------------------------------------------------------------------------------------
 // LightAmbient.frag:134-175 + calculateAmbientIrradiance :111-126
 // -------------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_ambient(VolView V, FrameView F, ViewK K, const float* __restrict__ g_lut, int n_ao,
+__global__ void __launch_bounds__(BLOCK_THREADS, VXL_AMBIENT_BLOCKS) k_ambient(VolView V, FrameView F, ViewK K, const float* __restrict__ g_lut, int n_ao,
                                                  float* __restrict__ out_shadow, float* __restrict__ out_ao,
                                                  unsigned long long* __restrict__ g_stats) {
     typedef AmbientGeom G;
@@ -140,6 +330,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_ambient(VolV
     unsigned rays = 0, pixels = 0, exact = 0;
     int steps = 0;
     float shadow = 1.0f, ao = 0.0f;
+    // the AO rays of tile-march launches go through the warp-pooled resolve (all 32 lanes take part, lit or not)
+    const bool POOL = MODE > 0 && G::QCAP > 0 && n_ao <= AO_POOL_MAX_RAYS;
+    float3 ao_origin = make_float3(0.f, 0.f, 0.f);
+    uint32_t ao_noise = 0u;
     if (p.valid) {
         if (lit) {
             float3 wd = normalize3(make_float3(0.3f, 0.4f, 0.5f));                     // SUN_DIR :15,:149
@@ -156,7 +350,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_ambient(VolV
                 if (ray_march<MODE, false, false, G>(V, C, origin, wd, 128.0f, steps, exact) != 128.0f) shadow = 0.0f;   // :167-169
                 rays += 1;
             }
-            if (out_ao && n_ao > 0) {
+            if (out_ao && n_ao > 0 && !POOL) {
                 const float3 tangent = fabsf(normal.z) > 0.5f ? make_float3(0.0f, -normal.z, normal.y)
                                                              : make_float3(-normal.y, normal.x, 0.0f);    // :112
                 const float3 bitangent = cross3(normal, tangent);                                         // :113
@@ -178,10 +372,17 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_ambient(VolV
                     acc += d * d;
                 }
                 ao = (acc / (float)n_ao) * 0.05f;                                                         // :125
-                rays += (unsigned)n_ao;
             }
+            if (out_ao && n_ao > 0) rays += (unsigned)n_ao;
+            ao_origin = origin; ao_noise = n;
             pixels = 1;
         }
+    }
+    if (G::QCAP > 0 && POOL && out_ao && n_ao > 0) {
+        const float a = ao_pooled<MODE, G>(V, C, S, F, K, p, p.valid && lit, ao_origin, normal, ao_noise, n_ao, steps, exact);
+        if (p.valid && lit) ao = a;
+    }
+    if (p.valid) {
         if (F.n_mirror == 0) {
             if (out_shadow) out_shadow[p.idx] = shadow;
             if (out_ao) out_ao[p.idx] = ao;

@@ -16,6 +16,9 @@ constexpr int BLOCK_THREADS = BLOCK_W * BLOCK_H;
 #ifndef VXL_PASS_BLOCKS
 #define VXL_PASS_BLOCKS 3         // resident 512-thread blocks per SM the pass kernels' registers are capped for (<= 42 regs);
 #endif                            // measured: 3 blocks 5.91 ms vs 2 blocks 6.51 ms for k_ambient on config 3 (profiles/r1f)
+#ifndef VXL_AMBIENT_BLOCKS
+#define VXL_AMBIENT_BLOCKS 2      // k_ambient with the pooled AO resolve: 93 KB of shared memory per block, <= 64 registers
+#endif
 
 constexpr int NOISE_OFFS = 17;                      // getNoise() and getNoise(0..15): the frame-dependent texture offsets, per launch not per ray
 struct ViewK { float InvView[16], View[16], InvProj[16], Proj[16]; int Frame; float nfx[NOISE_OFFS], nfy[NOISE_OFFS]; };

@@ -179,9 +179,21 @@ struct Importer {
     }
 
     // CreateEntity :397-476
+    // A valid scene graph is a tree: a node that is referenced twice (a DAG re-instantiates every shared sub-tree, so a
+    // 2 KB file of 24 doubled levels would ask for 2^25 entities) or that closes a cycle is rejected.
+    std::vector<char> visited;
+    size_t model_bytes = 0;                                      // all models of this import together
+    static constexpr size_t MAX_MODEL_BYTES = (size_t)1 << 30;
+    bool visit(int id) {
+        if (visited.size() != nodes.size()) visited.assign(nodes.size(), 0);
+        if (visited[(size_t)id]) { err = "scene node referenced twice (the node graph must be a tree)"; return false; }
+        visited[(size_t)id] = 1;
+        return true;
+    }
     int create(vxl_vox_scene& out, const Node& root, int parent, int& counter, int depth) {
         if (depth > 64) { err = "node tree deeper than 64 levels (cycle?)"; return -2; }
         if (root.child < 0 || root.child >= (int)nodes.size()) { err = "nTRN child id does not name a node"; return -2; }
+        if (!visit(root.child)) return -2;
         const Node& node = nodes[(size_t)root.child];
         vxl_vox_import_entity e;
         memset(&e, 0, sizeof e);
@@ -193,6 +205,7 @@ struct Importer {
             out.entities.push_back(e);
             for (int c : node.children) {
                 if (c < 0 || c >= (int)nodes.size() || nodes[(size_t)c].kind != 'T') { err = "nGRP child is not a transform node"; return -2; }
+                if (!visit(c)) return -2;
                 if (create(out, nodes[(size_t)c], idx, counter, depth + 1) == -2) return -2;
             }
             return idx;
@@ -203,13 +216,15 @@ struct Importer {
             const Matrix& M = root.m;
             if (M.rx > 2 || M.ry > 2 || M.rz < 0 || M.rz > 2) { err = "nTRN _r is not a permutation"; return -2; }   // the reference CHECK(0)s
             const int ts[3] = {sh.size[M.rx], sh.size[M.ry], sh.size[M.rz]};
-            if (ts[0] <= 0 || ts[1] <= 0 || ts[2] <= 0 || ts[0] > 4096 || ts[1] > 4096 || ts[2] > 4096 ||
-                (long long)ts[0] * ts[1] * ts[2] > (1ll << 28)) { err = "bad SIZE (XYZI coordinates are bytes: a model is at most 256^3)"; return -2; }
+            if (ts[0] <= 0 || ts[1] <= 0 || ts[2] <= 0 || ts[0] > 256 || ts[1] > 256 || ts[2] > 256) {
+                err = "bad SIZE (XYZI coordinates are bytes: a model is at most 256^3)"; return -2; }
             const int center[3] = {M.sx ? ts[0] - ts[0] / 2 : ts[0] / 2, M.sz ? ts[2] - ts[2] / 2 : ts[2] / 2, !M.sy ? ts[1] - ts[1] / 2 : ts[1] / 2};
             for (int i = 0; i < 3; ++i) e.position[i] = p[i] - (float)center[i] * 0.1f;
             vxl_vox_scene::Model mdl;
             auto pad = [](int v) { return ((v - 1) & ~3) + 4; };                       // VoxAsset(int32, int32, int32)
             mdl.dims[0] = pad(ts[0]); mdl.dims[1] = pad(ts[2]); mdl.dims[2] = pad(ts[1]);
+            model_bytes += (size_t)mdl.dims[0] * mdl.dims[1] * mdl.dims[2];
+            if (model_bytes > MAX_MODEL_BYTES) { err = "the models of this file exceed 1 GiB together"; return -2; }
             mdl.data.assign((size_t)mdl.dims[0] * mdl.dims[1] * mdl.dims[2], 0);
             for (uint32_t d : sh.voxels) {
                 const int v[3] = {(int)(d & 0xFF), (int)((d >> 8) & 0xFF), (int)((d >> 16) & 0xFF)};
@@ -219,7 +234,7 @@ struct Importer {
                 if (X < 0 || Y < 0 || Z < 0 || X >= mdl.dims[0] || Y >= mdl.dims[1] || Z >= mdl.dims[2]) { err = "XYZI voxel outside SIZE"; return -2; }
                 mdl.data[(size_t)X + (size_t)Y * mdl.dims[0] + (size_t)Z * mdl.dims[0] * mdl.dims[1]] = (uint8_t)(d >> 24);
             }
-            mdl.name = root.name.empty() ? std::to_string(counter++) : root.name;
+            mdl.name = root.name.empty() ? std::to_string(counter++) : root.name.substr(0, sizeof e.name - 1);   // one name for the file, the entity and the .pf
             strncpy(e.name, mdl.name.c_str(), sizeof e.name - 1);
             e.model = (int)out.models.size();
             out.models.push_back(std::move(mdl));
@@ -295,6 +310,9 @@ int vxl_vox_import_memory(const void* data, uint64_t size, vxl_vox_scene** out) 
     } catch (const std::bad_alloc&) {                             // nothing crosses the C boundary
         set_error("vxl_vox_import: out of memory");
         return VXL_ERR_OOM;
+    } catch (const std::exception& ex) {
+        set_error(std::string("vxl_vox_import: ") + ex.what());
+        return VXL_ERR_INVALID;
     }
 }
 
@@ -303,9 +321,15 @@ int vxl_vox_import(const char* vox_path, vxl_vox_scene** out) {
     FILE* f = fopen(vox_path, "rb");
     if (!f) { set_error(std::string("vxl_vox_import: cannot open ") + vox_path); return VXL_ERR_INVALID; }
     std::vector<uint8_t> buf;
-    uint8_t chunk[65536];
-    size_t k;
-    while ((k = fread(chunk, 1, sizeof chunk, f)) > 0) buf.insert(buf.end(), chunk, chunk + k);
+    try {
+        uint8_t chunk[65536];
+        size_t k;
+        while ((k = fread(chunk, 1, sizeof chunk, f)) > 0) buf.insert(buf.end(), chunk, chunk + k);
+    } catch (const std::exception&) {
+        fclose(f);
+        set_error("vxl_vox_import: out of memory reading the file");
+        return VXL_ERR_OOM;
+    }
     fclose(f);
     return vxl_vox_import_memory(buf.data(), buf.size(), out);
 }
@@ -343,8 +367,19 @@ int vxl_vox_scene_pallete(const vxl_vox_scene* sc, uint8_t records[1792]) {
 int vxl_vox_scene_write(const vxl_vox_scene* sc, const char* mods_dir, const char* path, const char* file_name) {
     if (!sc || !mods_dir || !path || !file_name || !*file_name) { set_error("vxl_vox_scene_write: bad argument"); return VXL_ERR_INVALID; }
     namespace fs = std::filesystem;
+    try {
     const fs::path mods(mods_dir), P(path), F(file_name);
     std::string err;
+    // shape names come verbatim from the (untrusted) .vox file and become file names under Mods/<path>/<file_name>/: a name that is
+    // absolute, climbs with "..", or carries a separator / NUL would write outside that directory
+    auto unsafe = [](const std::string& n) {
+        return n.empty() || n == "." || n == ".." || n.find('/') != std::string::npos || n.find('\\') != std::string::npos ||
+               n.find('\0') != std::string::npos || n.find(':') != std::string::npos;
+    };
+    for (const auto& m : sc->models)
+        if (unsafe(m.name)) { set_error("vxl_vox_scene_write: shape name '" + m.name + "' is not a plain file name"); return VXL_ERR_INVALID; }
+    if (unsafe(F.generic_string()) || P.is_absolute()) { set_error("vxl_vox_scene_write: file_name must be a plain name and path relative"); return VXL_ERR_INVALID; }
+    for (const auto& part : P) if (part == "..") { set_error("vxl_vox_scene_write: path must not contain '..'"); return VXL_ERR_INVALID; }
     // Assets::CreateAsset (Assets.cpp:24-42): GUID = Hash(path relative to Mods/), file = Mods/<path>
     const std::string p_rel = (P / F / F).replace_extension("p").generic_string();
     uint64_t p_guid; vxl_asset_guid(p_rel.c_str(), &p_guid);
@@ -376,6 +411,13 @@ int vxl_vox_scene_write(const vxl_vox_scene* sc, const char* mods_dir, const cha
     const std::string pf_rel = (P / pf.replace_extension("pf")).generic_string();
     if (!write_file(mods / pf_rel, js.data(), js.size(), nullptr, 0, err)) { set_error("vxl_vox_scene_write: " + err); return VXL_ERR_INVALID; }
     return VXL_OK;
+    } catch (const std::bad_alloc&) {
+        set_error("vxl_vox_scene_write: out of memory");
+        return VXL_ERR_OOM;
+    } catch (const std::exception& ex) {                         // std::filesystem errors
+        set_error(std::string("vxl_vox_scene_write: ") + ex.what());
+        return VXL_ERR_INVALID;
+    }
 }
 
 int vxl_vox_scene_free(vxl_vox_scene* sc) {

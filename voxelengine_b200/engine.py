@@ -75,6 +75,13 @@ class Context:
         check(self.lib.vxl_debug_fetched_probes(self.h, C.byref(n)), "vxl_debug_fetched_probes")
         return int(n.value)
 
+    def read_bandwidth(self, nbytes: int, reps: int = 20) -> float:
+        """GB/s of 16-byte reads over an nbytes device buffer from every SM (vxl_debug_read_bandwidth): a buffer well below
+        the L2 size measures L2 read bandwidth, one of several GB HBM."""
+        g = C.c_double()
+        check(self.lib.vxl_debug_read_bandwidth(self.h, int(nbytes), int(reps), C.byref(g)), "vxl_debug_read_bandwidth")
+        return float(g.value)
+
     def launch_count(self) -> int:
         n = C.c_uint64()
         check(self.lib.vxl_launch_count(self.h, C.byref(n)), "vxl_launch_count")
@@ -576,7 +583,35 @@ def lighting_host(ctx: Context, shadowVox: ShadowVoxSystem, view, frame_desc: di
                               None if pt is None else pt.ctypes.data, None if sp is None else sp.ctypes.data,
                               hp(outs.get("shadow")), hp(outs.get("ao")), hp(outs.get("point_shadow")),
                               hp(outs.get("spot_shadow")), hp(outs.get("spec_t")))
+    if "packed" in outs:                      # vxl_lighting_host_packed: outs["packed"] = dict(shadow_mask=, spec_code=, ao=)
+        pk = outs["packed"]
+        pp = capi.PackedPlanes(hp(pk.get("shadow_mask")), hp(pk.get("spec_code")), hp(pk.get("ao")))
+        check(ctx.lib.vxl_lighting_host_packed(ctx.h, shadowVox.h, C.byref(a), C.byref(pp)), "vxl_lighting_host_packed")
+        return
     check(ctx.lib.vxl_lighting_host(ctx.h, shadowVox.h, C.byref(a)), "vxl_lighting_host")
+
+
+def mask_bytes(n_point: int = 0, n_spot: int = 0) -> int:
+    """bytes per pixel of vxl_packed_planes.shadow_mask"""
+    return (1 + int(n_point) + int(n_spot) + 7) // 8
+
+
+def unpack_planes(shadow_mask: np.ndarray, spec_code: np.ndarray, n_point: int = 0, n_spot: int = 0) -> dict:
+    """Invert vxl_lighting_host_packed's encoding (include/vxl.h) into the float planes of vxl_lighting_host:
+    shadow [px], point_shadow [n_point][px], spot_shadow [n_spot][px], spec_t [px]."""
+    out = {}
+    if shadow_mask is not None:
+        m = np.asarray(shadow_mask, dtype=np.uint8).reshape(-1, mask_bytes(n_point, n_spot))
+        plane = lambda p: ((m[:, p >> 3] >> (p & 7)) & 1).astype(np.float32)
+        out["shadow"] = plane(0)
+        out["point_shadow"] = np.stack([plane(1 + i) for i in range(n_point)]) if n_point else np.zeros((0, m.shape[0]), np.float32)
+        out["spot_shadow"] = np.stack([plane(1 + n_point + i) for i in range(n_spot)]) if n_spot else np.zeros((0, m.shape[0]), np.float32)
+    if spec_code is not None:
+        c = np.asarray(spec_code, dtype=np.uint8).reshape(-1).astype(np.int32)
+        if np.any((c > 178) & (c != 255)):
+            raise ValueError("spec_code holds a value outside the code set")
+        out["spec_t"] = np.where(c < 31, 0.5 * (c + 1), np.where(c == 255, 256.0, 16.0 + (c - 31))).astype(np.float32)
+    return out
 
 
 def lighting(ctx: Context, shadowVox: ShadowVoxSystem, view, geometryFB: "GeometryBuffer", outs: dict, n_ao: int = 1, point=None, spot=None):
