@@ -52,7 +52,7 @@ void build_tile(const HostOcc& L, int ox, int oy, int oz, bool dilated, std::vec
                     for (int dz = -1; dz <= 1 && !b; ++dz)
                         for (int dy = -1; dy <= 1 && !b; ++dy)
                             for (int dx = -1; dx <= 1 && !b; ++dx) b = L.at(ox + x + dx, oy + y + dy, oz + z + dz);
-                if (b) w[(size_t)(z * TY + y) * TW + (x >> 5)] |= 1u << (x & 31);
+                if (b) w[(size_t)((x >> 5) * TY + z) * TY + y] |= 1u << (x & 31);      // words ordered [x word][z][y] like the product's tiles
             }
 }
 
@@ -144,12 +144,12 @@ void emul_trace(void* h, const float* rays, long long n, int variant, const int*
                 vxl_hit* out, unsigned long long* counters) {
     Emul* e = (Emul*)h;
     // the geometries of vxl_passes.cu (AmbientGeom == LocalGeom, ReflGeom) and a GH = 0 twin without probe groups
-    if (geom == 0) trace_geom<2, 69, 3, 36, 2, 7>(e, rays, n, variant, center, fast, direct, lockstep, out, counters);
-    else if (geom == 3) trace_geom<2, 69, 3, 36, 2, 7, true>(e, rays, n, variant, center, fast, direct, lockstep, out, counters);   // AO rays (SuperSparse, dist 128) by scan + resolve, near tile
-    else if (geom == 4) trace_geom<2, 69, 3, 36, 2, 7, true>(e, rays, n, variant, center, fast, direct, lockstep, out, counters, false);
-    else if (geom == 5) trace_geom<2, 69, 3, 36, 2, 7, true>(e, rays, n, variant, center, fast, direct, lockstep, out, counters, true, true);   // with the per-bundle precheck   // the same without the near tile
-    else if (geom == 1) trace_geom<2, 70, 3, 36, 2, 0>(e, rays, n, variant, center, fast, direct, lockstep, out, counters);
-    else trace_geom<3, 70, 3, 36, 2, 10>(e, rays, n, variant, center, fast, direct, lockstep, out, counters);
+    if (geom == 0) trace_geom<2, 76, 3, 39, 2, 7>(e, rays, n, variant, center, fast, direct, lockstep, out, counters);
+    else if (geom == 3) trace_geom<2, 76, 3, 39, 2, 7, true>(e, rays, n, variant, center, fast, direct, lockstep, out, counters);   // AO rays (SuperSparse, dist 128) by scan + resolve, near tile
+    else if (geom == 4) trace_geom<2, 76, 3, 39, 2, 7, true>(e, rays, n, variant, center, fast, direct, lockstep, out, counters, false);
+    else if (geom == 5) trace_geom<2, 76, 3, 39, 2, 7, true>(e, rays, n, variant, center, fast, direct, lockstep, out, counters, true, true);   // with the per-bundle precheck   // the same without the near tile
+    else if (geom == 1) trace_geom<2, 68, 3, 35, 2, 0>(e, rays, n, variant, center, fast, direct, lockstep, out, counters);
+    else trace_geom<3, 68, 3, 35, 2, 10>(e, rays, n, variant, center, fast, direct, lockstep, out, counters);
 }
 
 // experiment helper: classify every probe of the plain march by what a bit-occupancy hierarchy would know.

@@ -32,7 +32,10 @@ def main():
                                    C.c_void_p(o_ao.data_ptr()) if o_ao is not None else None), "ambient")
 
     out = []
-    for name, args in (("sun+ao", (wl.n_ao, sh, ao)), ("sun", (0, sh, None)), ("ao", (wl.n_ao, None, ao))):
+    runs = [("sun+ao", (wl.n_ao, sh, ao)), ("sun", (0, sh, None)), ("ao", (wl.n_ao, None, ao))]
+    for n in [int(x) for x in os.environ.get("VXL_EXP_NAO", "").split(",") if x]:
+        runs.append((f"ao{n}", (n, None, ao)))
+    for name, args in runs:
         ctx.stats_reset()
         run(*args)
         torch.cuda.synchronize()
@@ -44,7 +47,7 @@ def main():
             a.record(); run(*args); b.record()
             torch.cuda.synchronize()
             ts.append(a.elapsed_time(b))
-        out.append(f"{name} {float(np.median(ts)):.3f} ms (min {min(ts):.3f}) rays {st['rays']} probes {st['steps']}")
+        out.append(f"{name} {float(np.median(ts)):.3f} ms (min {min(ts):.3f}) rays {st['rays']} probes {st['steps']} px {st['pixels']} fetched {ctx.fetched_probes()}")
     run(wl.n_ao, sh, ao)
     torch.cuda.synchronize()
     dig = hashlib.sha1(sh.cpu().numpy().tobytes()).hexdigest()[:12] + " " + hashlib.sha1(ao.cpu().numpy().tobytes()).hexdigest()[:12]

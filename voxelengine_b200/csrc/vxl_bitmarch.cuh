@@ -29,13 +29,13 @@ constexpr float BM_MARGIN = 0.125f;          // > accumulated rounding drift of 
 constexpr float BM_MAXCOORD = 8191.0f;
 
 struct BitTile {
-    const uint32_t* w;     // [TY][TY][TW] words; bit (x & 31) of word x >> 5
+    const uint32_t* w;     // [TW][TY (z)][TY (y)] words, y innermost (the order the TMA box of the level array lands in); bit (x & 31) of word x >> 5
     int ox, oy, oz;        // tile origin, cells
     bool enabled;
     bool direct;           // texels of occupied cells can be fetched without bounds checks and with 32-bit offsets:
                            // volume dims are multiples of the cell's texel edge and the volume is < 4 GiB
     unsigned koff;         // folded constant of the direct texel offset (see TileAddr::texel_offset)
-    const uint32_t* wd;    // dilated level (cell = 2^(SHIFT+1) voxels): [DT][DT][DW] words
+    const uint32_t* wd;    // dilated level (cell = 2^(SHIFT+1) voxels): [DW][DT][DT] words
     int dx, dy, dz;        // its origin, cells
     const uint32_t* wn;    // near tile: texel level (cell = 2 voxels), [NEAR_T][NEAR_T] words of 32 texels; nullptr = none
     int nx, ny, nz;        // its origin, texels
@@ -95,24 +95,26 @@ struct NearAddr {
     }
 };
 
-// Tile lookup with everything constant folded once per ray:
+// Tile lookup with everything constant folded once per ray.  Tile words are ordered [x word][z][y]: a row of the tile along y
+// sits in consecutive banks and the next z is TY = 4 (mod 32) banks further, so the probes of neighbouring rays -- a few cells
+// apart in y and z -- hit different banks.
 //   b_a  = MB + rel_a                      (MB = 0x4B000000 + (SHIFT << 23), a multiple of 32)
-//   word = rel_z * (TY*TW) + rel_y * TW + (rel_x >> 5) = b_z * (TY*TW) + b_y * TW + (b_x >> 5) - CC      (mod 2^32)
+//   word = (rel_x >> 5) * (TY*TY) + rel_z * TY + rel_y = (b_x >> 5) * (TY*TY) + b_z * TY + b_y - CC      (mod 2^32)
 //   bit  = rel_x & 31 = b_x & 31
 template <int SHIFT, int TY, int TW>
 struct TileAddr {
     static constexpr unsigned MB = 0x4B000000u + ((unsigned)SHIFT << 23);
-    static constexpr unsigned CC0 = MB * (unsigned)(TY * TW) + MB * (unsigned)TW + (MB >> 5);
+    static constexpr unsigned CC0 = (MB >> 5) * (unsigned)(TY * TY) + MB * (unsigned)TY + MB;
     // Bias the per-axis origins by (32 JX, KY, KZ) cells so that the folded constant vanishes mod 2^30 (word index ->
-    // byte address drops two more bits): (MB + KZ) TY TW + (MB + KY) TW + (MB >> 5) + JX = 0, which saves the add of
-    // the constant per lookup.  The biased index must stay inside the binade of the magic sum (KZ + TY < 2^23); the
-    // narrow dilated tiles do not admit a solution and keep the constant.
+    // byte address drops two more bits): ((MB >> 5) + JX) TY TY + (MB + KZ) TY + MB + KY = 0, which saves the add of
+    // the constant per lookup.  The biased index must stay inside the binade of the magic sum (32 JX + 32 TW < 2^23); a
+    // tile that does not admit a solution keeps the constant.
     static constexpr unsigned RR = (0u - CC0) & 0x3FFFFFFFu;
-    static constexpr bool FOLD0 = RR / (unsigned)(TY * TW) < (1u << 23) - 4096u;
-    static constexpr int KZ = FOLD0 ? (int)(RR / (unsigned)(TY * TW)) : 0;
-    static constexpr int KY = FOLD0 ? (int)((RR % (unsigned)(TY * TW)) / (unsigned)TW) : 0;
-    static constexpr int JX = FOLD0 ? (int)(RR % (unsigned)TW) : 0;
-    static constexpr unsigned CC = CC0 + (unsigned)KZ * (unsigned)(TY * TW) + (unsigned)KY * (unsigned)TW + (unsigned)JX;   // 4 * CC == 0 (mod 2^32) when FOLD0
+    static constexpr bool FOLD0 = (RR / (unsigned)(TY * TY)) * 32u < (1u << 23) - 4096u;
+    static constexpr int JX = FOLD0 ? (int)(RR / (unsigned)(TY * TY)) : 0;
+    static constexpr int KZ = FOLD0 ? (int)((RR % (unsigned)(TY * TY)) / (unsigned)TY) : 0;
+    static constexpr int KY = FOLD0 ? (int)(RR % (unsigned)TY) : 0;
+    static constexpr unsigned CC = CC0 + (unsigned)JX * (unsigned)(TY * TY) + (unsigned)KZ * (unsigned)TY + (unsigned)KY;   // 4 * CC == 0 (mod 2^32) when FOLD0
     static constexpr unsigned MB1 = 0x4B000000u + (1u << 23);       // texel grid (2 voxels)
     const uint32_t* w;
     unsigned sbase;        // device: shared-window byte address of w[-CC] (wraps mod 2^32)
@@ -135,13 +137,13 @@ struct TileAddr {
     VXL_DI unsigned test(float3 p) const {
         const unsigned bx = magic_floor_bits(p.x, mx, SHIFT, ox), by = magic_floor_bits(p.y, my, SHIFT, oy), bz = magic_floor_bits(p.z, mz, SHIFT, oz);
 #ifdef __CUDA_ARCH__
-        const unsigned idx = bz * (unsigned)(TY * TW) + by * (unsigned)TW + (bx >> 5);
+        const unsigned idx = (bx >> 5) * (unsigned)(TY * TY) + bz * (unsigned)TY + by;
         unsigned word, mask;
         asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(sbase + 4u * idx));
         asm("shf.l.wrap.b32 %0, 0, 1, %1;" : "=r"(mask) : "r"(bx));       // high word of {1:0} << (bx & 31) = 1 << (bx & 31); opaque so it stays a mask test
         return word & mask;
 #else
-        const unsigned idx = (bz * (unsigned)(TY * TW) + by * (unsigned)TW + (bx >> 5) - CC) & 0x3FFFFFFFu;
+        const unsigned idx = ((bx >> 5) * (unsigned)(TY * TY) + bz * (unsigned)TY + by - CC) & 0x3FFFFFFFu;
         return w[idx] & (1u << (bx & 31));
 #endif
     }
@@ -149,12 +151,12 @@ struct TileAddr {
     VXL_DI unsigned bit(float3 p) const {
         const unsigned bx = magic_floor_bits(p.x, mx, SHIFT, ox), by = magic_floor_bits(p.y, my, SHIFT, oy), bz = magic_floor_bits(p.z, mz, SHIFT, oz);
 #ifdef __CUDA_ARCH__
-        const unsigned idx = bz * (unsigned)(TY * TW) + by * (unsigned)TW + (bx >> 5);
+        const unsigned idx = (bx >> 5) * (unsigned)(TY * TY) + bz * (unsigned)TY + by;
         unsigned word;
         asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(sbase + 4u * idx));
         return __funnelshift_r(word, 0u, bx);                             // word >> (bx & 31)
 #else
-        const unsigned idx = (bz * (unsigned)(TY * TW) + by * (unsigned)TW + (bx >> 5) - CC) & 0x3FFFFFFFu;
+        const unsigned idx = ((bx >> 5) * (unsigned)(TY * TY) + bz * (unsigned)TY + by - CC) & 0x3FFFFFFFu;
         return w[idx] >> (bx & 31);
 #endif
     }
@@ -379,12 +381,12 @@ VXL_DI unsigned funnel_r(unsigned lo, unsigned hi, unsigned sh) {
 // |dir_a| <= bound_a (the 16 AO rays of a pixel): the box origin +- reach * bound lies inside the tile / the near tile.
 struct ScanPre { bool ok, near_ok; float hi_max; };
 
+// blo / bhi: every direction of the bundle obeys -blo_a <= dir_a <= bhi_a (all >= 0)
 template <int SHIFT, int TY, int TW>
-VXL_DI ScanPre scan_precheck(const BitTile& T, float3 origin, float3 bound, float reach, float near_reach) {
+VXL_DI ScanPre scan_precheck(const BitTile& T, float3 origin, float3 blo, float3 bhi, float reach, float near_reach) {
     ScanPre P;
     const float cell = (float)(1 << SHIFT);
-    const float3 r = bound * (reach * 1.00002f);
-    const float3 lo = origin - r, hi = origin + r;
+    const float3 lo = origin - blo * (reach * 1.00002f), hi = origin + bhi * (reach * 1.00002f);
     const float3 tlo = make_float3((float)T.ox * cell, (float)T.oy * cell, (float)T.oz * cell);
     bool ok = T.enabled && T.direct;
     ok = ok && (lo.x >= fmaxf(tlo.x, 0.0f) + BM_MARGIN) && (lo.y >= fmaxf(tlo.y, 0.0f) + BM_MARGIN) && (lo.z >= fmaxf(tlo.z, 0.0f) + BM_MARGIN);
@@ -392,12 +394,16 @@ VXL_DI ScanPre scan_precheck(const BitTile& T, float3 origin, float3 bound, floa
          (hi.y <= fminf(tlo.y + (float)TY * cell, BM_MAXCOORD) - BM_MARGIN) && (hi.z <= fminf(tlo.z + (float)TY * cell, BM_MAXCOORD) - BM_MARGIN);
     P.ok = ok;                                                             // NaN anywhere makes a comparison fail
     P.hi_max = fmaxf(fmaxf(hi.x, hi.y), hi.z);
-    const float3 n = bound * (near_reach * 1.00002f);
+    const float3 nl = blo * (near_reach * 1.00002f), nh = bhi * (near_reach * 1.00002f);
     const float lx = (float)T.nx * 2.0f + BM_MARGIN, ly = (float)T.ny * 2.0f + BM_MARGIN, lz = (float)T.nz * 2.0f + BM_MARGIN;
     const float w = (float)(2 * NEAR_T) - 2.0f * BM_MARGIN;
-    P.near_ok = ok && T.wn != nullptr && origin.x - n.x >= lx && origin.x + n.x <= lx + w && origin.y - n.y >= ly && origin.y + n.y <= ly + w &&
-                origin.z - n.z >= lz && origin.z + n.z <= lz + w;
+    P.near_ok = ok && T.wn != nullptr && origin.x - nl.x >= lx && origin.x + nh.x <= lx + w && origin.y - nl.y >= ly && origin.y + nh.y <= ly + w &&
+                origin.z - nl.z >= lz && origin.z + nh.z <= lz + w;
     return P;
+}
+template <int SHIFT, int TY, int TW>
+VXL_DI ScanPre scan_precheck(const BitTile& T, float3 origin, float3 bound, float reach, float near_reach) {
+    return scan_precheck<SHIFT, TY, TW>(T, origin, bound, bound, reach, near_reach);
 }
 
 // The scan of march_scan_super on its own: candidate word of an eligible ray (probe k in bit k).
@@ -487,15 +493,15 @@ VXL_DI void f2_floor_bits(F2 p, F2 m, int S, int o, unsigned& lo, unsigned& hi) 
 #endif
 }
 
-// Where the probes of one stretch of a scan look: a bit tile ([z][y][x word], 32 cells per word) described by run-time values, so
-// that ONE unrolled scan serves the near tile, the block's main tile and the level array in global memory.
+// Where the probes of one stretch of a scan look: a bit array (32 cells per word along x, y innermost) described by run-time values,
+// so that ONE unrolled scan serves the near tile, the block's main tile and the level array in global memory.
 //   b_a  = MB + rel_a  (float bits of p_a + m_a rounded toward zero; MB = 0x4B000000 + (S << 23), a multiple of 32)
-//   word = rel_z * sz + rel_y * sy + (rel_x >> 5) = b_z * sz + b_y * sy + (b_x >> 5) - CC,  CC = MB * (sz + sy) + (MB >> 5)   (mod 2^32)
+//   word = (rel_x >> 5) * sy + rel_z * sz + rel_y = (b_x >> 5) * sy + b_z * sz + b_y - CC,  CC = (MB >> 5) * sy + MB * (sz + 1)   (mod 2^32)
 // SY / SZ > 0: the strides are compile-time constants (immediate operands); 0: taken from sy / sz.
 template <bool GLOBAL, unsigned SY = 0, unsigned SZ = 0>
 struct ScanLook {
     float mx, my, mz;          // 2^(23+S) - o_a * 2^S
-    unsigned sy, sz;           // words per row / per slice
+    unsigned sy, sz;           // words from one x word to the next / from one z to the next
     unsigned sbase;            // shared memory: byte address of word 0 minus 4 * CC (wraps); global memory: CC
     const uint32_t* w;         // word 0 (global memory; host emulation)
     VXL_DI static ScanLook make(const uint32_t* words, int S, int ox, int oy, int oz, unsigned sy_, unsigned sz_) {
@@ -504,7 +510,7 @@ struct ScanLook {
         L.mx = M - (float)ox * cell; L.my = M - (float)oy * cell; L.mz = M - (float)oz * cell;
         L.sy = SY ? SY : sy_; L.sz = SZ ? SZ : sz_; L.w = words;
         const unsigned MB = 0x4B000000u + ((unsigned)S << 23);
-        const unsigned CC = MB * (L.sz + L.sy) + (MB >> 5);
+        const unsigned CC = MB * (L.sz + 1u) + (MB >> 5) * L.sy;
 #ifdef __CUDA_ARCH__
         L.sbase = GLOBAL ? CC : (unsigned)__cvta_generic_to_shared(words) - 4u * CC;
 #else
@@ -513,7 +519,7 @@ struct ScanLook {
         return L;
     }
     VXL_DI unsigned word(unsigned bx, unsigned by, unsigned bz) const {
-        const unsigned idx = bz * (SZ ? SZ : sz) + by * (SY ? SY : sy) + (bx >> 5);
+        const unsigned idx = (bx >> 5) * (SY ? SY : sy) + bz * (SZ ? SZ : sz) + by;
 #ifdef __CUDA_ARCH__
         if (GLOBAL) return __ldg(w + (idx - sbase));
         unsigned v;
@@ -701,15 +707,15 @@ VXL_DI float march_scan_super(const VolView& V, const BitTile& T, float3 origin,
     return d;
 }
 
-// Stage the TW*32 x TY x TY-cell window of an occupancy level whose origin cell is (ox, oy, oz).
-// Everything outside the level's array is empty.
+// Stage the TW*32 x TY x TY-cell window of an occupancy level whose origin cell is (ox, oy, oz), words ordered [x word][z][y].  The window may start at any bit of the level's words (funnel shift).  Everything outside the level's
+// array is empty.  Consecutive threads take consecutive y: coalesced reads, conflict-free writes.
 #ifdef __CUDACC__
 template <int TY, int TW>
 __device__ __forceinline__ void stage_bits(uint32_t* __restrict__ dst, const BitView& M, int ox, int oy, int oz) {
     const int ax0 = ox + M.border;                          // array index = cell index + border
     const int w0 = ax0 >> 5;                                // arithmetic shift: floor for negatives
     const int sh = ax0 & 31;
-    const int words_x = M.pitch - 1;                        // the spare word of each row is zero
+#pragma unroll 2
     for (int r = threadIdx.x; r < TY * TY; r += blockDim.x) {   // one tile row (TW words) per iteration
         const int z = r / TY, y = r - z * TY;
         const int ay = oy + y + M.border, az = oz + z + M.border;
@@ -717,13 +723,13 @@ __device__ __forceinline__ void stage_bits(uint32_t* __restrict__ dst, const Bit
 #pragma unroll
         for (int k = 0; k <= TW; ++k) g[k] = 0u;
         if ((unsigned)ay < (unsigned)M.cy && (unsigned)az < (unsigned)M.cz) {
-            const uint32_t* row = M.words + ((size_t)az * M.cy + ay) * M.pitch;
+            const uint32_t* row = M.words + (size_t)az * M.xw * M.cyp + ay;
 #pragma unroll
             for (int k = 0; k <= TW; ++k)
-                if ((unsigned)(w0 + k) < (unsigned)words_x) g[k] = __ldg(row + w0 + k);
+                if ((unsigned)(w0 + k) < (unsigned)M.xw) g[k] = __ldg(row + (size_t)(w0 + k) * M.cyp);   // the last word of each row is zero
         }
 #pragma unroll
-        for (int k = 0; k < TW; ++k) dst[r * TW + k] = __funnelshift_r(g[k], g[k + 1], sh);   // sh == 0 returns g[k]
+        for (int k = 0; k < TW; ++k) dst[(k * TY + z) * TY + y] = __funnelshift_r(g[k], g[k + 1], sh);   // sh == 0 returns g[k]
     }
 }
 #endif

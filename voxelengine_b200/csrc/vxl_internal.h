@@ -1,5 +1,6 @@
 // vxl_internal.h -- private definitions shared by the .cu files of libvxl.so.
 #pragma once
+#include <cuda.h>             // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
@@ -12,12 +13,18 @@ namespace vxl {
 // One occupancy bitmask level (vxl_occupancy.cu): bit (x & 31) of word x >> 5, cell = 2^shift voxels.
 struct BitLevel {
     uint32_t* d_words = nullptr;
-    int cx = 0, cy = 0, cz = 0;          // cells
-    int pitch = 0;                       // words per row (ceil(cx/32) + 1 spare zero word)
+    int cx = 0, cy = 0, cz = 0;          // array extent in cells, borders included
+    int xw = 0;                          // words per (y, z) row: ceil(cx/32) + 1 spare zero word
+    int cyp = 0;                         // cy rounded up to a multiple of 4: the words are ordered [az][word][ay], y innermost
     int shift = 0;                       // log2(voxels per cell edge)
-    int border = 0;                      // array index = cell index + border (dilated levels: 1)
+    int border = 0;                      // array index = cell index + border (zero cells around the level proper)
+    int copies = 1;                      // 2: a second copy of the array follows, shifted by 16 cells along x (k_occ_shift16)
+    // TMA descriptors of this array as a 3-D tensor of 32-bit words (cyp, xw, cz), one per box shape a kernel stages
+    // (vxl_passes.cu); built on first use by level_tensor_map (vxl_occupancy.cu); ty = key of the box shape
+    struct BoxMap { int ty = 0; CUtensorMap map; };
+    BoxMap box[2];
 };
-struct BitView { const uint32_t* __restrict__ words; int cx, cy, cz, pitch, border; };
+struct BitView { const uint32_t* __restrict__ words; int cx, cy, cz, xw, cyp, border, copies; };
 
 // Device-side view of the occupancy volume handed to kernels by value.
 struct VolView {
@@ -114,11 +121,14 @@ int cuda_fail(cudaError_t e, const char* what);
 inline VolView vol_view(const vxl_volume* v) {
     VolView r;
     r.bytes = v->d_bytes; r.sx = v->sx; r.sy = v->sy; r.sz = v->sz;
-    r.tex = BitView{v->tex.d_words, v->tex.cx, v->tex.cy, v->tex.cz, v->tex.pitch, v->tex.border};
-    for (int i = 0; i < 3; ++i) r.occ[i] = BitView{v->occ[i].d_words, v->occ[i].cx, v->occ[i].cy, v->occ[i].cz, v->occ[i].pitch, v->occ[i].border};
-    for (int i = 0; i < 2; ++i) r.dil[i] = BitView{v->dil[i].d_words, v->dil[i].cx, v->dil[i].cy, v->dil[i].cz, v->dil[i].pitch, v->dil[i].border};
+    auto view = [](const BitLevel& L) { return BitView{L.d_words, L.cx, L.cy, L.cz, L.xw, L.cyp, L.border, L.copies}; };
+    r.tex = view(v->tex);
+    for (int i = 0; i < 3; ++i) r.occ[i] = view(v->occ[i]);
+    for (int i = 0; i < 2; ++i) r.dil[i] = view(v->dil[i]);
     return r;
 }
+// TMA descriptor for boxes of ty cells (y, a multiple of 4) x tw words (x) x tz slices of an occupancy level (cached in the level)
+int level_tensor_map(BitLevel& L, int tw, int ty, int tz, const CUtensorMap** out);
 int frame_view(const vxl_frame* f, FrameView* out);
 size_t frame_pixels(const vxl_frame* f);   // n_tiles * tile_w * tile_h
 }  // namespace vxl

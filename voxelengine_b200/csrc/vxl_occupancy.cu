@@ -16,10 +16,19 @@
 //   (per axis) of any point of c lies in an empty cell, so one test clears a whole run of small-step probes.
 //   Stored with a 1-cell border so that cells just outside the volume still see their occupied neighbours.
 // Cells outside a level's array are empty (texelFetch out of range reads 0).
-// Storage: 32 cells per word along x, pitch = words holding cells + 1 spare zero word.
+// Storage (one array per level): bit (ax & 31) of word (ax >> 5) of row (ay, az), array index a = cell index + border, the words of
+//   the array ordered [az][word][ay] -- y innermost.  A window of the array is then a 3-D box whose innermost extent runs along y in
+//   single cells, which is what lets the Tensor Memory Accelerator fetch it (cp.async.bulk.tensor wants the box to start on a
+//   16-byte boundary of the innermost dimension: 4 cells along y here, against 128 cells if x words were innermost).  Rows are
+//   padded to cyp = a multiple of 4 words; each (ay, az) row has one spare all-zero word at the end (staging funnel shift).
+//   The plain levels carry a zero border of 192 voxels per side (96 / 48 / 24 / 12 cells: each level's border is twice the next
+//   coarser one's, so 2x2x2 children stay aligned), so that a ray box that pokes out of the volume can still be looked up
+//   without bounds checks; the dilated levels add one more cell.
 #include "vxl_internal.h"
 
 namespace vxl {
+
+__device__ __forceinline__ size_t level_index(int xw, int cyp, int w, int ay, int az) { return ((size_t)az * xw + w) * cyp + ay; }
 
 // texel level: one thread per output word = 32 consecutive bytes of a volume row; HBM-bound (reads the volume once)
 __device__ __forceinline__ uint32_t nonzero_bytes4(uint32_t v) {        // bit i = (byte i of v != 0)
@@ -27,14 +36,14 @@ __device__ __forceinline__ uint32_t nonzero_bytes4(uint32_t v) {        // bit i
     return ((m >> 7) & 1u) | ((m >> 14) & 2u) | ((m >> 21) & 4u) | ((m >> 28) & 8u);
 }
 __global__ void __launch_bounds__(256) k_occ_texels(const uint8_t* __restrict__ bytes, int sx, int sy, int sz,
-                                                    int pitch, uint32_t* __restrict__ out) {
+                                                    int xw, int cyp, int cz, int border, uint32_t* __restrict__ out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)pitch * sy * sz;
+    const long long total = (long long)xw * cyp * cz;
     if (i >= total) return;
-    const int w = (int)(i % pitch), y = (int)((i / pitch) % sy), z = (int)(i / ((long long)pitch * sy));
+    const int ay = (int)(i % cyp), w = (int)((i / cyp) % xw), az = (int)(i / ((long long)cyp * xw));
+    const int y = ay - border, z = az - border, x0 = w * 32 - border;      // border is a multiple of 32: x0 stays 32-aligned
     uint32_t word = 0;
-    const int x0 = w * 32;
-    if (x0 < sx) {
+    if (y >= 0 && y < sy && z >= 0 && z < sz && x0 >= 0 && x0 < sx) {
         const uint8_t* row = bytes + (size_t)y * sx + (size_t)z * ((size_t)sx * sy) + x0;
         if (x0 + 32 <= sx && (reinterpret_cast<uintptr_t>(row) & 15) == 0) {
             const uint4 a = __ldg(reinterpret_cast<const uint4*>(row)), b = __ldg(reinterpret_cast<const uint4*>(row) + 1);
@@ -49,24 +58,24 @@ __global__ void __launch_bounds__(256) k_occ_texels(const uint8_t* __restrict__ 
     out[i] = word;
 }
 
-// coarser plain level from a finer one: bit c = OR of the 2x2x2 child cells
-__global__ void __launch_bounds__(256) k_occ_coarsen(const uint32_t* __restrict__ fine, int fcy, int fcz, int fpitch,
-                                                     int cy, int cz, int pitch, uint32_t* __restrict__ out) {
+// coarser plain level from a finer one: bit c = OR of the 2x2x2 child cells.  border_fine = 2 * border_coarse, so array index
+// a of the coarse level has the children 2a, 2a + 1 of the fine array on every axis.
+__global__ void __launch_bounds__(256) k_occ_coarsen(const uint32_t* __restrict__ fine, int fcy, int fcz, int fxw, int fcyp,
+                                                     int xw, int cyp, int cz, uint32_t* __restrict__ out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)pitch * cy * cz;
+    const long long total = (long long)xw * cyp * cz;
     if (i >= total) return;
-    const int w = (int)(i % pitch), y = (int)((i / pitch) % cy), z = (int)(i / ((long long)pitch * cy));
+    const int ay = (int)(i % cyp), w = (int)((i / cyp) % xw), az = (int)(i / ((long long)cyp * xw));
     uint32_t word = 0;
     for (int dz = 0; dz < 2; ++dz)
         for (int dy = 0; dy < 2; ++dy) {
-            const int fy = 2 * y + dy, fz = 2 * z + dz;
+            const int fy = 2 * ay + dy, fz = 2 * az + dz;
             if (fy >= fcy || fz >= fcz) continue;
-            const uint32_t* row = fine + ((size_t)fz * fcy + fy) * fpitch;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int fw = 2 * w + h;
-                if (fw >= fpitch) continue;
-                uint32_t v = row[fw];
+                if (fw >= fxw) continue;
+                uint32_t v = fine[level_index(fxw, fcyp, fw, fy, fz)];
                 v = (v | (v >> 1)) & 0x55555555u;                  // OR of bit pairs at even positions
                 v = (v | (v >> 1)) & 0x33333333u; v = (v | (v >> 2)) & 0x0F0F0F0Fu;
                 v = (v | (v >> 4)) & 0x00FF00FFu; v = (v | (v >> 8)) & 0x0000FFFFu;   // compact to 16 bits
@@ -76,33 +85,81 @@ __global__ void __launch_bounds__(256) k_occ_coarsen(const uint32_t* __restrict_
     out[i] = word;
 }
 
-// dilated level (array index = cell + 1): OR over the 3x3x3 neighbourhood of the plain level
-__global__ void __launch_bounds__(256) k_occ_dilate(const uint32_t* __restrict__ in, int icy, int icz, int ipitch,
-                                                    int cy, int cz, int pitch, uint32_t* __restrict__ out) {
+// dilated level (array index = input array index + 1): OR over the 3x3x3 neighbourhood of the plain level
+__global__ void __launch_bounds__(256) k_occ_dilate(const uint32_t* __restrict__ in, int icy, int icz, int ixw, int icyp,
+                                                    int xw, int cyp, int cz, uint32_t* __restrict__ out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)pitch * cy * cz;
+    const long long total = (long long)xw * cyp * cz;
     if (i >= total) return;
-    const int w = (int)(i % pitch), y = (int)((i / pitch) % cy) - 1, z = (int)(i / ((long long)pitch * cy)) - 1;   // cell coords
-    // output bit b of word w is cell x = 32*w + b - 1; gather input bits x-1, x, x+1 = input positions 32*w + b - 2 .. 32*w + b
+    const int w = (int)((i / cyp) % xw), y = (int)(i % cyp) - 1, z = (int)(i / ((long long)cyp * xw)) - 1;   // input array coords
+    // output bit b of word w is input x = 32*w + b - 1; gather input bits x-1, x, x+1 = input positions 32*w + b - 2 .. 32*w + b
     uint32_t word = 0;
     for (int dz = -1; dz <= 1; ++dz)
         for (int dy = -1; dy <= 1; ++dy) {
             const int iy = y + dy, iz = z + dz;
             if (iy < 0 || iz < 0 || iy >= icy || iz >= icz) continue;
-            const uint32_t* row = in + ((size_t)iz * icy + iy) * ipitch;
-            const uint32_t cur = w < ipitch ? row[w] : 0u;
-            const uint32_t prev = (w >= 1 && w - 1 < ipitch) ? row[w - 1] : 0u;
+            const uint32_t cur = w < ixw ? in[level_index(ixw, icyp, w, iy, iz)] : 0u;
+            const uint32_t prev = (w >= 1 && w - 1 < ixw) ? in[level_index(ixw, icyp, w - 1, iy, iz)] : 0u;
             // input position p = 32*w + b - s for s = 0, 1, 2  ->  (cur << s) | (prev >> (32 - s))
             word |= cur | (cur << 1) | (prev >> 31) | (cur << 2) | (prev >> 30);
         }
     out[i] = word;
 }
 
-static int alloc_level(BitLevel& L, int shift, int cx, int cy, int cz, int border) {
-    L.shift = shift; L.border = border;
-    L.cx = cx + 2 * border; L.cy = cy + 2 * border; L.cz = cz + 2 * border;
-    L.pitch = (L.cx + 31) / 32 + 1;                           // one spare (all-zero) word per row for the staging funnel shift
-    VXL_CUDA(cudaMalloc(&L.d_words, (size_t)L.pitch * L.cy * L.cz * 4));
+// second copy of a level, shifted by 16 cells along x: bit (ax + 16) & 31 of word (ax + 16) >> 5.  A TMA box starts on a word
+// boundary, so with the two copies a staged window can start every 16 cells instead of every 32.
+__global__ void __launch_bounds__(256) k_occ_shift16(const uint32_t* __restrict__ in, int xw, int cyp, int cz, uint32_t* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)xw * cyp * cz;
+    if (i >= total) return;
+    const int w = (int)((i / cyp) % xw);
+    out[i] = (in[i] << 16) | (w >= 1 ? in[i - cyp] >> 16 : 0u);          // the word before along x is cyp words back
+}
+
+// ncx, ncy, ncz: cells of the level proper; border: zero cells added on every side; copies: 1, or 2 = also the copy shifted by 16 cells
+static int alloc_level(BitLevel& L, int shift, int ncx, int ncy, int ncz, int border, int copies = 1) {
+    L.shift = shift; L.border = border; L.copies = copies;
+    L.cx = ncx + 2 * border; L.cy = ncy + 2 * border; L.cz = ncz + 2 * border;
+    L.xw = (L.cx + 31) / 32 + 1;                              // one spare (all-zero) word per row: the staging funnel shift / the shifted copy
+    L.cyp = (L.cy + 3) & ~3;                                  // rows of whole 16 bytes (TMA strides)
+    VXL_CUDA(cudaMalloc(&L.d_words, (size_t)L.xw * L.cyp * L.cz * 4 * copies));
+    for (auto& b : L.box) b.ty = 0;
+    return VXL_OK;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libvxl.so does not link libcuda, so it still loads on a box without a driver)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int level_tensor_map(BitLevel& L, int tw, int ty, int tz, const CUtensorMap** out) {
+    const int key = (tw << 20) | (ty << 10) | tz;
+    for (auto& b : L.box)
+        if (b.ty == key) { *out = &b.map; return VXL_OK; }
+    BitLevel::BoxMap* slot = nullptr;
+    for (auto& b : L.box)
+        if (b.ty == 0) { slot = &b; break; }
+    if (!slot || !L.d_words || tw < 1 || ty < 4 || tz < 1 || tw > 256 || ty > 256 || tz > 256 || (ty & 3)) { set_error("level_tensor_map: no free slot / bad box"); return VXL_ERR_INVALID; }
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        VXL_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (q != cudaDriverEntryPointSuccess || !fn) { set_error("cuTensorMapEncodeTiled is not available in this driver"); return VXL_ERR_CUDA; }
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    // the level (words [copy][az][word][ay] in memory) as a tensor with dimensions (y, z, x word, copy): a box is ty cells along y
+    // (a multiple of 4) x tz slices x tw words of one copy and lands densely in shared memory in that order, [x word][z][y];
+    // everything outside the array reads as zero = empty (texelFetch out of range)
+    const cuuint64_t plane = (cuuint64_t)L.cyp * (cuuint64_t)L.xw * (cuuint64_t)L.cz * 4u;
+    const cuuint64_t dims[4] = {(cuuint64_t)L.cyp, (cuuint64_t)L.cz, (cuuint64_t)L.xw, (cuuint64_t)L.copies};
+    const cuuint64_t strides[3] = {(cuuint64_t)L.cyp * (cuuint64_t)L.xw * 4u, (cuuint64_t)L.cyp * 4u, plane};
+    const cuuint32_t box[4] = {(cuuint32_t)ty, (cuuint32_t)tz, (cuuint32_t)tw, 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    const CUresult r = encode(&slot->map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, L.d_words, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: CUresult " + std::to_string((int)r)); return VXL_ERR_CUDA; }
+    slot->ty = key;
+    *out = &slot->map;
     return VXL_OK;
 }
 
@@ -117,30 +174,36 @@ int vxl_volume_build_occupancy(vxl_volume* v) {
     vxl_ctx* c = v->ctx;
     VXL_CUDA(cudaSetDevice(c->device));
     if (!v->occ[0].d_words) {
-        if (int e = alloc_level(v->tex, 1, v->sx, v->sy, v->sz, 0)) return e;
+        // borders: 192 voxels of zero cells around every plain level (a multiple of 32 texels, so that the texel level's words
+        // stay aligned with 32-byte pieces of the volume rows); each level's border is half the next finer one's
+        if (int e = alloc_level(v->tex, 1, v->sx, v->sy, v->sz, 96)) return e;
         for (int li = 0; li < 3; ++li) {
             const int tpc = 2 << li;                          // texels per cell edge: 2, 4, 8
-            if (int e = alloc_level(v->occ[li], 2 + li, (v->sx + tpc - 1) / tpc, (v->sy + tpc - 1) / tpc, (v->sz + tpc - 1) / tpc, 0)) return e;
+            if (int e = alloc_level(v->occ[li], 2 + li, (v->sx + tpc - 1) / tpc, (v->sy + tpc - 1) / tpc, (v->sz + tpc - 1) / tpc, 48 >> li, li == 0 ? 2 : 1)) return e;
         }
         for (int li = 0; li < 2; ++li) {
             const BitLevel& P = v->occ[1 + li];
-            if (int e = alloc_level(v->dil[li], P.shift, P.cx, P.cy, P.cz, 1)) return e;
+            if (int e = alloc_level(v->dil[li], P.shift, P.cx - 2 * P.border, P.cy - 2 * P.border, P.cz - 2 * P.border, P.border + 1)) return e;
         }
     }
-    auto grid_of = [](const BitLevel& L) { return (unsigned)(((long long)L.pitch * L.cy * L.cz + 255) / 256); };
+    auto grid_of = [](const BitLevel& L) { return (unsigned)(((long long)L.xw * L.cyp * L.cz + 255) / 256); };
     BitLevel& L1 = v->tex;
-    k_occ_texels<<<grid_of(L1), 256, 0, c->stream>>>(v->d_bytes, v->sx, v->sy, v->sz, L1.pitch, L1.d_words);
+    k_occ_texels<<<grid_of(L1), 256, 0, c->stream>>>(v->d_bytes, v->sx, v->sy, v->sz, L1.xw, L1.cyp, L1.cz, L1.border, L1.d_words);
     VXL_LAUNCH_CHECK(c);
     for (int li = 0; li < 3; ++li) {
         const BitLevel& F = li ? v->occ[li - 1] : v->tex;
         BitLevel& L = v->occ[li];
-        k_occ_coarsen<<<grid_of(L), 256, 0, c->stream>>>(F.d_words, F.cy, F.cz, F.pitch, L.cy, L.cz, L.pitch, L.d_words);
+        k_occ_coarsen<<<grid_of(L), 256, 0, c->stream>>>(F.d_words, F.cy, F.cz, F.xw, F.cyp, L.xw, L.cyp, L.cz, L.d_words);
         VXL_LAUNCH_CHECK(c);
+        if (L.copies == 2) {
+            k_occ_shift16<<<grid_of(L), 256, 0, c->stream>>>(L.d_words, L.xw, L.cyp, L.cz, L.d_words + (size_t)L.xw * L.cyp * L.cz);
+            VXL_LAUNCH_CHECK(c);
+        }
     }
     for (int li = 0; li < 2; ++li) {
         const BitLevel& P = v->occ[1 + li];
         BitLevel& D = v->dil[li];
-        k_occ_dilate<<<grid_of(D), 256, 0, c->stream>>>(P.d_words, P.cy, P.cz, P.pitch, D.cy, D.cz, D.pitch, D.d_words);
+        k_occ_dilate<<<grid_of(D), 256, 0, c->stream>>>(P.d_words, P.cy, P.cz, P.xw, P.cyp, D.xw, D.cyp, D.cz, D.d_words);
         VXL_LAUNCH_CHECK(c);
     }
     v->dirty = false;
@@ -153,16 +216,21 @@ int vxl_volume_debug_occupancy(vxl_volume* v, int level, uint8_t* host_out, int*
     if (!v || !((level >= 1 && level <= 4) || level == 13 || level == 14)) { set_error("vxl_volume_debug_occupancy: bad argument"); return VXL_ERR_INVALID; }
     if (v->dirty || !v->occ[0].d_words) { if (int e = vxl_volume_build_occupancy(v)) return e; }
     const BitLevel& L = level == 1 ? v->tex : (level < 10 ? v->occ[level - 2] : v->dil[level - 13]);
-    if (out_dims) { out_dims[0] = L.cx; out_dims[1] = L.cy; out_dims[2] = L.cz; }
+    // the cells of the level proper; the dilated levels with one cell of border (cells -1 .. n)
+    const int keep = level < 10 ? 0 : 1, skip = L.border - keep;
+    const int nx = L.cx - 2 * skip, ny = L.cy - 2 * skip, nz = L.cz - 2 * skip;
+    if (out_dims) { out_dims[0] = nx; out_dims[1] = ny; out_dims[2] = nz; }
     if (!host_out) return VXL_OK;
-    const size_t words = (size_t)L.pitch * L.cy * L.cz;
+    const size_t words = (size_t)L.xw * L.cyp * L.cz;
     std::vector<uint32_t> h(words);
     VXL_CUDA(cudaMemcpyAsync(h.data(), L.d_words, words * 4, cudaMemcpyDeviceToHost, v->ctx->stream));
     VXL_CUDA(cudaStreamSynchronize(v->ctx->stream));
-    for (int z = 0; z < L.cz; ++z)
-        for (int y = 0; y < L.cy; ++y)
-            for (int x = 0; x < L.cx; ++x)
-                host_out[((size_t)z * L.cy + y) * L.cx + x] = (uint8_t)((h[((size_t)z * L.cy + y) * L.pitch + (x >> 5)] >> (x & 31)) & 1u);
+    for (int z = 0; z < nz; ++z)
+        for (int y = 0; y < ny; ++y)
+            for (int x = 0; x < nx; ++x) {
+                const int ax = x + skip, ay = y + skip, az = z + skip;
+                host_out[((size_t)z * ny + y) * nx + x] = (uint8_t)((h[((size_t)az * L.xw + (ax >> 5)) * L.cyp + ay] >> (ax & 31)) & 1u);
+            }
     return VXL_OK;
 }
 

@@ -10,6 +10,7 @@
 #include "vxl_trace.cuh"
 #include "vxl_bitmarch.cuh"
 #include "vxl_pixel.cuh"
+#include "vxl_tma.cuh"
 
 #include <cstddef>
 
@@ -19,10 +20,11 @@ namespace vxl {
 template <typename G>
 struct BlockShared {
     float lut[LUT_FLOATS];
-    int bb[6];
+    int bb[12];                               // boxes of the block's rays: [0..5] whole rays, [6..11] their first stretch (near tile)
     unsigned acc[4];
-    uint32_t tile[G::TY * G::TY * G::TW];     // from here on: kernel variant 0 allocates only the header
-    uint32_t dtile[G::DT * G::DT * G::DW];
+    uint64_t bar;                             // mbarrier the TMA copy of `tile` completes
+    alignas(128) uint32_t tile[G::TY * G::TY * G::TW];     // from here on: kernel variant 0 allocates only the header
+    uint32_t dtile[G::DW * G::DT * G::DT];
     uint32_t ntile[G::NEAR ? NEAR_T * NEAR_T : 1];
     // pooled AO resolve (ao_pooled): per warp a stack of pending candidate tests and the per-pixel AO sums
     uint4 q_ent[G::QCAP ? BLOCK_THREADS / 32 : 1][G::QCAP ? G::QCAP : 1];       // (s1.xyz, remaining candidate bits)
@@ -38,19 +40,30 @@ constexpr size_t smem_bytes() {
 // 2^(SHIFT+1) voxels, DW*32 x DT x DT cells, covering at least the plain tile.  GH: half width of a probe group of the
 // Sparse march (GH * max|stepDir_a| must stay <= the dilated cell: 7 * 1.0 <= 8, 10 * 1.5 <= 16).
 // NEAR: also stage the near tile (texel bits of the 64^3 voxels around the ray origins, 4 KB; vxl_bitmarch.cuh).
-// 57.1 / 58.8 KB + 10.4 KB + 4 KB LUTs (+ 4 KB near tile) per block: three 512-thread blocks per SM (<= 75 KB each).
+// The plain tile is one TMA box of the level array (vxl_occupancy.cu; it lands ordered [x word][z][y]): TY cells along y starting
+// on a multiple of 4 cells, TY slices, and TW = 3 words (96 cells) along x starting on a word boundary of the array or of its copy
+// shifted by 16 cells -- so the window reaches at least 40 cells (160 voxels) either side of the block's centre along x.
+// Ambient: 67.7 KB + 11.9 KB + 4 KB near tile + 4 KB LUTs + 19 KB pooled-resolve state = 107 KB, two 512-thread blocks per SM.
+// Local lights / reflection: three blocks per SM with TY = 68 (54.2 + 9.6 + 4 KB), or two with TY = 80 (VXL_PASS_BLOCKS = 2).
 #ifndef VXL_AO_QCAP
 #define VXL_AO_QCAP 64            // pending candidate tests per warp (>= 63: 31 left over + 32 new); 0 = per-lane resolve (round-1 kernel)
 #endif
-struct AmbientGeom { static constexpr int SHIFT = 2, TY = 69, TW = 3, DT = 36, DW = 2, GH = 7, QCAP = VXL_AO_QCAP; static constexpr bool NEAR = true; };     // +-138 voxels (AO 128, sun 128)
-struct LocalGeom   { static constexpr int SHIFT = 2, TY = 70, TW = 3, DT = 36, DW = 2, GH = 7, QCAP = 0; static constexpr bool NEAR = false; };    // point/spot rays beyond +-140 voxels take the plain march
-struct ReflGeom    { static constexpr int SHIFT = 3, TY = 70, TW = 3, DT = 36, DW = 2, GH = 10, QCAP = 0; static constexpr bool NEAR = false; };   // +-280 voxels (164 steps * |wd| <= 1.5)
+#ifndef VXL_PASS_TY
+#define VXL_PASS_TY (VXL_PASS_BLOCKS >= 3 ? 68 : 80)
+#endif
+struct AmbientGeom { static constexpr int SHIFT = 2, TY = 76, TW = 3, DT = 39, DW = 2, GH = 7, QCAP = VXL_AO_QCAP; static constexpr bool NEAR = true; };     // +-152 voxels in y and z (AO 128, sun 128)
+struct LocalGeom   { static constexpr int SHIFT = 2, TY = VXL_PASS_TY, TW = 3, DT = VXL_PASS_TY / 2 + 1, DW = 2, GH = 7, QCAP = 0; static constexpr bool NEAR = false; };    // point/spot rays that leave the window take the plain march
+struct ReflGeom    { static constexpr int SHIFT = 3, TY = VXL_PASS_TY, TW = 3, DT = VXL_PASS_TY / 2 + 1, DW = 2, GH = 10, QCAP = 0; static constexpr bool NEAR = false; };   // 8-voxel cells (164 steps * |wd| <= 1.5)
 
-// Bounding box of the block's ray origins -> tile placement -> stage the occupancy tile.
-// `hint` is (close to) the thread's ray origin in voxel units; threads without rays pass valid = false.
-// Ends with a block barrier (which also publishes the LUTs).
+// Bounding box of the block's rays -> tile placement -> stage the occupancy tile.
+// [flo, fhi] is (close to) the box the thread's rays stay in, [nlo, nhi] the box of their first 20 voxels, in voxel units; threads
+// without rays pass valid = false.  The tiles are centred on the union of the boxes, not on the ray origins: the AO rays of a pixel
+// fill the hemisphere around its normal, so a block of terrain pixels needs 129 voxels upward and next to nothing downward.
+// The plain tile arrives by TMA (one box copy issued by thread 0, vxl_tma.cuh) while all threads stage the two small tiles, whose
+// rows start at an arbitrary bit of the level's words (funnel shift).  Ends with a block barrier (which also publishes the LUTs).
 template <bool FAST, typename G>
-__device__ __forceinline__ BitTile block_prologue(const VolView& V, BlockShared<G>& S, bool valid, float3 hint) {
+__device__ __forceinline__ BitTile block_prologue(const VolView& V, BlockShared<G>& S, const CUtensorMap* tm_tile, bool valid, float3 flo, float3 fhi,
+                                                  float3 nlo, float3 nhi) {
     BitTile T;
     T.w = S.tile; T.ox = T.oy = T.oz = 0; T.enabled = false;
     T.wd = S.dtile; T.dx = T.dy = T.dz = 0;
@@ -58,33 +71,50 @@ __device__ __forceinline__ BitTile block_prologue(const VolView& V, BlockShared<
     constexpr int TPC = 1 << (G::SHIFT - 1);                // texels per cell edge
     T.direct = (V.sx % TPC == 0) && (V.sy % TPC == 0) && (V.sz % TPC == 0) && ((unsigned long long)V.sx * V.sy * V.sz < (1ull << 32));
     T.koff = TileAddr<G::SHIFT, G::TY, G::TW>::texel_koff(V);
-    if (threadIdx.x < 3) { S.bb[threadIdx.x] = 0x7fffffff; S.bb[3 + threadIdx.x] = -0x7fffffff - 1; }
+    constexpr int NBB = G::NEAR ? 12 : 6;
+    if (threadIdx.x < NBB) S.bb[threadIdx.x] = (threadIdx.x % 6) < 3 ? 0x7fffffff : -0x7fffffff - 1;
     if (threadIdx.x < 4) S.acc[threadIdx.x] = 0u;
+    if (FAST && threadIdx.x == 0) mbar_init(&S.bar, 1u);
     __syncthreads();
     if (!FAST) return T;
+    // bounding box of the block's ray boxes (and of their first stretch, for the near tile): warp reductions, then shared atomics
     const int big = 1 << 24;
-    int ix = valid ? max(-big, min(big, f2i(hint.x))) : 0x7fffffff, iy = valid ? max(-big, min(big, f2i(hint.y))) : 0x7fffffff,
-        iz = valid ? max(-big, min(big, f2i(hint.z))) : 0x7fffffff;
-    const int mnx = __reduce_min_sync(0xFFFFFFFFu, ix), mny = __reduce_min_sync(0xFFFFFFFFu, iy), mnz = __reduce_min_sync(0xFFFFFFFFu, iz);
-    if (!valid) { ix = iy = iz = -0x7fffffff - 1; }
-    const int mxx = __reduce_max_sync(0xFFFFFFFFu, ix), mxy = __reduce_max_sync(0xFFFFFFFFu, iy), mxz = __reduce_max_sync(0xFFFFFFFFu, iz);
-    if ((threadIdx.x & 31) == 0 && mnx != 0x7fffffff) {
-        atomicMin(&S.bb[0], mnx); atomicMin(&S.bb[1], mny); atomicMin(&S.bb[2], mnz);
-        atomicMax(&S.bb[3], mxx); atomicMax(&S.bb[4], mxy); atomicMax(&S.bb[5], mxz);
+    auto clampi = [&](float v) { return max(-big, min(big, f2i(floorf(v)))); };
+    {
+        const float lo[6] = {flo.x, flo.y, flo.z, nlo.x, nlo.y, nlo.z}, hi[6] = {fhi.x, fhi.y, fhi.z, nhi.x, nhi.y, nhi.z};
+#pragma unroll
+        for (int a = 0; a < NBB / 2; ++a) {
+            const int g = a / 3, c = a % 3;
+            const int mn = __reduce_min_sync(0xFFFFFFFFu, valid ? clampi(lo[a]) : 0x7fffffff);
+            const int mx = __reduce_max_sync(0xFFFFFFFFu, valid ? clampi(hi[a]) : -0x7fffffff - 1);
+            if ((threadIdx.x & 31) == 0 && mn != 0x7fffffff) { atomicMin(&S.bb[g * 6 + c], mn); atomicMax(&S.bb[g * 6 + 3 + c], mx); }
+        }
     }
     __syncthreads();
     if (S.bb[0] == 0x7fffffff) return T;                    // no ray in this block (uniform)
     const int cx = (S.bb[0] + S.bb[3]) >> 1, cy = (S.bb[1] + S.bb[4]) >> 1, cz = (S.bb[2] + S.bb[5]) >> 1;
-    T.ox = (cx >> G::SHIFT) - G::TW * 16; T.oy = (cy >> G::SHIFT) - G::TY / 2; T.oz = (cz >> G::SHIFT) - G::TY / 2;
+    const BitView& L = V.occ[G::SHIFT - 2];
+    // x origin: a word boundary of the level array -- of its copy shifted by 16 cells where there is one and that comes closer to
+    // (centre - half a window); y origin: a multiple of 4 cells (the borders are)
+    const int ax_want = (cx >> G::SHIFT) - G::TW * 16 + L.border;
+    const int ax = L.copies == 2 ? ((ax_want + 8) >> 4) << 4 : ((ax_want + 16) >> 5) << 5;
+    const int copy = (ax & 16) ? 1 : 0;                     // in the shifted copy array cell a sits at bit a + 16
+    T.ox = ax - L.border;
+    T.oy = (((cy >> G::SHIFT) - G::TY / 2 + 2) >> 2) << 2; T.oz = (cz >> G::SHIFT) - G::TY / 2;
     T.dx = T.ox >> 1; T.dy = T.oy >> 1; T.dz = T.oz >> 1;   // floor: the dilated tile starts at or before the plain one
-    stage_bits<G::TY, G::TW>(S.tile, V.occ[G::SHIFT - 2], T.ox, T.oy, T.oz);
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(&S.bar, (unsigned)sizeof(S.tile));
+        tma_load_4d(S.tile, tm_tile, T.oy + L.border, T.oz + L.border, (ax + 16 * copy) >> 5, copy, &S.bar);
+    }
     stage_bits<G::DT, G::DW>(S.dtile, V.dil[G::SHIFT - 2], T.dx, T.dy, T.dz);
     if (G::NEAR) {
-        T.nx = (cx >> 1) - NEAR_T / 2; T.ny = (cy >> 1) - NEAR_T / 2; T.nz = (cz >> 1) - NEAR_T / 2;
+        const int ncx = (S.bb[6] + S.bb[9]) >> 1, ncy = (S.bb[7] + S.bb[10]) >> 1, ncz = (S.bb[8] + S.bb[11]) >> 1;
+        T.nx = (ncx >> 1) - NEAR_T / 2; T.ny = (ncy >> 1) - NEAR_T / 2; T.nz = (ncz >> 1) - NEAR_T / 2;
         stage_bits<NEAR_T, 1>(S.ntile, V.tex, T.nx, T.ny, T.nz);
         T.wn = S.ntile;
     }
     __syncthreads();
+    mbar_wait(&S.bar, 0u);                                  // the box has landed (and is visible to every waiting thread)
     T.enabled = true;
     return T;
 }
@@ -115,6 +145,10 @@ __device__ __forceinline__ void flush_stats(BS& S, unsigned long long* __restric
     }
 }
 
+static_assert(smem_bytes<AmbientGeom, true>() <= (size_t)(233472 / VXL_AMBIENT_BLOCKS - 1024), "k_ambient: shared memory per block exceeds the SM's share");
+static_assert(smem_bytes<LocalGeom, true>() + 1024 <= (size_t)(233472 / VXL_PASS_BLOCKS - 1024), "k_local_lights: shared memory per block exceeds the SM's share");
+static_assert(smem_bytes<ReflGeom, true>() <= (size_t)(233472 / VXL_PASS_BLOCKS - 1024), "k_reflection: shared memory per block exceeds the SM's share");
+
 constexpr int AO_N2 = 23;          // phase-2 probes of a SuperSparse ray with dist = 128: d = 17.5, 22.5, ..., 127.5 (:121)
 
 
@@ -135,6 +169,26 @@ __device__ __noinline__ float ao_ray_slow(const VolView& V, const BitTile& C, fl
     return d * d;
 }
 
+// Where the AO rays of a pixel can go (LightAmbient.frag:112-119).  Every direction is tangent * x + bitangent * y + normal * z with
+// (x, y, z) the LUT's hemisphere sample: x^2 + y^2 + z^2 = u (cos^2 + sin^2) + (1 - u) = 1 up to a few ulp and z >= 0.  On that half
+// sphere the component along axis a, T_a x + B_a y + N_a z, is at most |(T_a, B_a, N_a)| when N_a >= 0 (Cauchy-Schwarz, attained at
+// z >= 0) and at most |(T_a, B_a)| when N_a < 0 (the N_a z term only subtracts; the rest is bounded on the rim z = 0); the minimum
+// mirrors that.  Result: -blo_a <= dir_a <= bhi_a; the factor absorbs the roundings.
+__device__ __forceinline__ void ao_bounds(float3 normal, float3& blo, float3& bhi) {
+    const float3 t = fabsf(normal.z) > 0.5f ? make_float3(0.0f, -normal.z, normal.y) : make_float3(-normal.y, normal.x, 0.0f);    // :112
+    const float3 b = cross3(normal, t);                                                                                           // :113
+    const float n[3] = {normal.x, normal.y, normal.z};
+    const float r2[3] = {t.x * t.x + b.x * b.x, t.y * t.y + b.y * b.y, t.z * t.z + b.z * b.z};
+    float lo[3], hi[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float full = sqrtf(r2[a] + n[a] * n[a]) * 1.0001f, rim = sqrtf(r2[a]) * 1.0001f;
+        hi[a] = n[a] >= 0.0f ? full : rim;
+        lo[a] = n[a] <= 0.0f ? full : rim;
+    }
+    blo = make_float3(lo[0], lo[1], lo[2]); bhi = make_float3(hi[0], hi[1], hi[2]);
+}
+
 // The AO rays of a warp's 32 pixels with a pooled resolve (LightAmbient.frag:111-126, n_ao rays per pixel).
 //
 // Every lane scans its own rays, two at a time (scan_super_pair: all 29 probes of both, branch-free, packed f32x2 additions).
@@ -153,7 +207,7 @@ __device__ __noinline__ float ao_ray_slow(const VolView& V, const BitTile& C, fl
 // n_ao <= 256 all partial sums are multiples of 2^-16 below 2^8.  It is therefore kept as the integer sum of (256 d / 128)^2.
 template <int MODE, typename G>
 __device__ __forceinline__ float ao_pooled(const VolView& V, const BitTile& C, BlockShared<G>& S, const FrameView& F, const ViewK& K, const PixelCtx& p,
-                                           bool lit, float3 origin, float3 normal, uint32_t n0, int n_ao, int& steps, unsigned& exact) {
+                                           bool lit, float3 origin, float3 normal, float3 blo, float3 bhi, uint32_t n0, int n_ao, int& steps, unsigned& exact) {
     constexpr int N = 6 + AO_N2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
@@ -168,31 +222,34 @@ __device__ __forceinline__ float ao_pooled(const VolView& V, const BitTile& C, B
     if (lit) {
         tangent = fabsf(normal.z) > 0.5f ? make_float3(0.0f, -normal.z, normal.y) : make_float3(-normal.y, normal.x, 0.0f);    // :112
         bitangent = cross3(normal, tangent);                                                                                   // :113
-        // Every AO direction is tangent * x + bitangent * y + normal * z with (x, y, z) the LUT's hemisphere sample, x^2 + y^2 + z^2 =
-        // u (cos^2 + sin^2) + (1 - u) = 1 up to a few ulp: by Cauchy-Schwarz |dir_a| <= |(tangent_a, bitangent_a, normal_a)|, which
-        // is <= 1 for an orthonormal frame whatever its orientation.  One eligibility test per pixel covers all its rays (reach:
-        // 128 + 1 voxels of march, 20 for the near tile's 8 probes; the 1.0001 and scan_precheck's own factor and margin absorb the roundings).
-        const float3 bound = make_float3(sqrtf(tangent.x * tangent.x + bitangent.x * bitangent.x + normal.x * normal.x) * 1.0001f,
-                                         sqrtf(tangent.y * tangent.y + bitangent.y * bitangent.y + normal.y * normal.y) * 1.0001f,
-                                         sqrtf(tangent.z * tangent.z + bitangent.z * bitangent.z + normal.z * normal.z) * 1.0001f);
-        const ScanPre pre = scan_precheck<G::SHIFT, G::TY, G::TW>(C, origin, bound, 129.0f, 20.0f);
+        // one eligibility test per pixel covers all its rays: -blo_a <= dir_a <= bhi_a (ao_bounds); reach: 128 + 1 voxels of march, 20 for
+        // the near tile's 8 probes
+        const ScanPre pre = scan_precheck<G::SHIFT, G::TY, G::TW>(C, origin, blo, bhi, 129.0f, 20.0f);
         near_ok = pre.near_ok;
         if (pre.ok) mode = 1;
         else {
-            // the box around the rays inside the volume (and below the magic floor's coordinate limit): the level array can be indexed directly
-            const float3 r = bound * (129.0f * 1.00002f);
-            const float3 hi = make_float3(fminf((float)(2 * V.sx), BM_MAXCOORD), fminf((float)(2 * V.sy), BM_MAXCOORD), fminf((float)(2 * V.sz), BM_MAXCOORD));
-            const bool inside = C.direct && origin.x - r.x >= BM_MARGIN && origin.y - r.y >= BM_MARGIN && origin.z - r.z >= BM_MARGIN &&
-                                origin.x + r.x <= hi.x - BM_MARGIN && origin.y + r.y <= hi.y - BM_MARGIN && origin.z + r.z <= hi.z - BM_MARGIN;
+            // the box around the rays at non-negative coordinates (there floor == the reference's truncation) and at most 160 voxels past
+            // the volume's far faces (the level array has 192 voxels of empty cells around it) and below the magic floor's coordinate
+            // limit: the level array can be indexed directly
+            const float3 rl = blo * (129.0f * 1.00002f), rh = bhi * (129.0f * 1.00002f);
+            const float3 hi = make_float3(fminf((float)(2 * V.sx + 160), BM_MAXCOORD), fminf((float)(2 * V.sy + 160), BM_MAXCOORD), fminf((float)(2 * V.sz + 160), BM_MAXCOORD));
+            const bool inside = C.direct && origin.x - rl.x >= BM_MARGIN && origin.y - rl.y >= BM_MARGIN && origin.z - rl.z >= BM_MARGIN &&
+                                origin.x + rh.x <= hi.x - BM_MARGIN && origin.y + rh.y <= hi.y - BM_MARGIN && origin.z + rh.z <= hi.z - BM_MARGIN;
             mode = inside ? 2 : 3;                                                  // (NaN anywhere fails the comparisons)
         }
+#ifdef VXL_EXP_SKIP        // timing experiments only (results are wrong): drop the pixels of mode >= VXL_EXP_SKIP
+        if (mode >= VXL_EXP_SKIP) mode = 0;
+#endif
+#ifdef VXL_EXP_MODECNT     // diagnostics: `exact` (vxl_debug_fetched_probes) counts the pixels of mode VXL_EXP_MODECNT
+        exact += mode == VXL_EXP_MODECNT ? 1u : 0u;
+#endif
     }
     // one eps for everybody (resolve_super_cand): no coordinate of a scanned ray exceeds the volume's extent
     const float eps = (fminf((float)(2 * max(V.sx, max(V.sy, V.sz))), BM_MAXCOORD) + 1.0f) * (1.0f / 262144.0f);
-    typedef ScanLook<false, (unsigned)G::TW, (unsigned)(G::TY * G::TW)> TileLook;
+    typedef ScanLook<false, (unsigned)(G::TY * G::TY), (unsigned)G::TY> TileLook;
     const TileLook look_tile = TileLook::make(C.w, G::SHIFT, C.ox, C.oy, C.oz, 0u, 0u);
-    const ScanLook<false> look_near = (G::NEAR && near_ok) ? ScanLook<false>::make(C.wn, 1, C.nx, C.ny, C.nz, 1u, (unsigned)NEAR_T)
-                                                           : ScanLook<false>::make(C.w, G::SHIFT, C.ox, C.oy, C.oz, (unsigned)G::TW, (unsigned)(G::TY * G::TW));
+    const ScanLook<false> look_near = (G::NEAR && near_ok) ? ScanLook<false>::make(C.wn, 1, C.nx, C.ny, C.nz, (unsigned)NEAR_T, (unsigned)NEAR_T)
+                                                           : ScanLook<false>::make(C.w, G::SHIFT, C.ox, C.oy, C.oz, (unsigned)(G::TY * G::TY), (unsigned)G::TY);
     int qn = 0;                       // entries on the stack (warp-uniform)
     unsigned own = 0u;                // terms of the rays this lane decided itself
     float accf = 0.0f;                // mode 3: sequential float sum like the reference
@@ -235,7 +292,7 @@ __device__ __forceinline__ float ao_pooled(const VolView& V, const BitTile& C, B
 #endif
             } else if (mode == 2) {
                 const BitView& L4 = V.occ[G::SHIFT - 2];
-                const ScanLook<true> look_glob = ScanLook<true>::make(L4.words, G::SHIFT, 0, 0, 0, (unsigned)L4.pitch, (unsigned)(L4.pitch * L4.cy));
+                const ScanLook<true> look_glob = ScanLook<true>::make(L4.words, G::SHIFT, -L4.border, -L4.border, -L4.border, (unsigned)L4.cyp, (unsigned)(L4.xw * L4.cyp));   // [az][word][ay]
                 scan_super_pair<AO_N2>(look_glob, look_glob, origin, da, db, ca, cb);
             }
             if (mode != 3) {
@@ -304,11 +361,11 @@ __device__ __forceinline__ float ao_pooled(const VolView& V, const BitTile& C, B
 // LightAmbient.frag:134-175 + calculateAmbientIrradiance :111-126
 // -------------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(BLOCK_THREADS, VXL_AMBIENT_BLOCKS) k_ambient(VolView V, FrameView F, ViewK K, const float* __restrict__ g_lut, int n_ao,
+__global__ void __launch_bounds__(BLOCK_THREADS, VXL_AMBIENT_BLOCKS) k_ambient(VolView V, const __grid_constant__ CUtensorMap tm_tile, FrameView F, ViewK K, const float* __restrict__ g_lut, int n_ao,
                                                  float* __restrict__ out_shadow, float* __restrict__ out_ao,
                                                  unsigned long long* __restrict__ g_stats) {
     typedef AmbientGeom G;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     BlockShared<G>& S = *reinterpret_cast<BlockShared<G>*>(smem_raw);
     load_luts(S.lut, g_lut);
     const PixelCtx p = pixel_ctx(F, K);
@@ -326,7 +383,22 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_AMBIENT_BLOCKS) k_ambient(V
             bias = gsmoothstep(0.0f, 0.2f, depth) * 50.0f + 1.5f;                      // :158
         }
     }
-    const BitTile C = block_prologue<(MODE > 0), G>(V, S, lit, wcp0 + normal * bias);
+    // the box this pixel's rays stay in, for the placement of the block's tiles (approximate: the exact origin comes later)
+    float3 blo = make_float3(0.f, 0.f, 0.f), bhi = blo, flo = blo, fhi = blo, nlo = blo, nhi = blo;
+    if (lit) {
+        const float3 o = wcp0 + normal * bias;
+        flo = fhi = nlo = nhi = o;
+        if (out_ao && n_ao > 0) {
+            ao_bounds(normal, blo, bhi);
+            flo = o - blo * 130.0f; fhi = o + bhi * 130.0f;
+            nlo = o - blo * 21.0f; nhi = o + bhi * 21.0f;
+        }
+        if (out_shadow) {          // 128 voxels along normalize(mix(SUN_DIR, jitter, 0.5)): (54, 72, 91) +- 14 of jitter, from an origin jittered by 1.25
+            flo = make_float3(fminf(flo.x, o.x - 16.0f), fminf(flo.y, o.y - 16.0f), fminf(flo.z, o.z - 16.0f));
+            fhi = make_float3(fmaxf(fhi.x, o.x + 70.0f), fmaxf(fhi.y, o.y + 88.0f), fmaxf(fhi.z, o.z + 107.0f));
+        }
+    }
+    const BitTile C = block_prologue<(MODE > 0), G>(V, S, &tm_tile, lit, flo, fhi, nlo, nhi);
     unsigned rays = 0, pixels = 0, exact = 0;
     int steps = 0;
     float shadow = 1.0f, ao = 0.0f;
@@ -357,11 +429,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_AMBIENT_BLOCKS) k_ambient(V
                 // every AO direction is tangent * x + bitangent * y + normal * z with |x|, |y|, |z| <= 1: one eligibility
                 // test per pixel covers all its rays (reach: 128 + 1 voxels of march, 20 for the near tile's 8 probes)
                 ScanPre pre = ScanPre{false, false, 0.0f};
-                if (MODE > 0) {
-                    const float3 bound = make_float3(fabsf(tangent.x) + fabsf(bitangent.x) + fabsf(normal.x), fabsf(tangent.y) + fabsf(bitangent.y) + fabsf(normal.y),
-                                                     fabsf(tangent.z) + fabsf(bitangent.z) + fabsf(normal.z));
-                    pre = scan_precheck<G::SHIFT, G::TY, G::TW>(C, origin, bound, 129.0f, 20.0f);
-                }
+                if (MODE > 0) pre = scan_precheck<G::SHIFT, G::TY, G::TW>(C, origin, blo, bhi, 129.0f, 20.0f);
                 float acc = 0.0f;
                 for (int i = 0; i < n_ao; ++i) {
                     const uint32_t ni = (i == 0) ? n : get_noise(F, K, p, i);
@@ -379,7 +447,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_AMBIENT_BLOCKS) k_ambient(V
         }
     }
     if (G::QCAP > 0 && POOL && out_ao && n_ao > 0) {
-        const float a = ao_pooled<MODE, G>(V, C, S, F, K, p, p.valid && lit, ao_origin, normal, ao_noise, n_ao, steps, exact);
+        const float a = ao_pooled<MODE, G>(V, C, S, F, K, p, p.valid && lit, ao_origin, normal, blo, bhi, ao_noise, n_ao, steps, exact);
         if (p.valid && lit) ao = a;
     }
     if (p.valid) {
@@ -402,12 +470,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_AMBIENT_BLOCKS) k_ambient(V
 // G-buffer, noise and world position are read / derived once per pixel instead of once per light.
 // -------------------------------------------------------------------------------------------------
 template <bool SPOT, int MODE>
-__global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_local_lights(VolView V, FrameView F, ViewK K, const float* __restrict__ g_lut,
+__global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_local_lights(VolView V, const __grid_constant__ CUtensorMap tm_tile, FrameView F, ViewK K, const float* __restrict__ g_lut,
                                                       const float* __restrict__ lights, int n_lights,
                                                       float* __restrict__ out_shadow, size_t plane_stride,
                                                       unsigned long long* __restrict__ g_stats) {
     typedef LocalGeom G;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     BlockShared<G>& S = *reinterpret_cast<BlockShared<G>*>(smem_raw);
     __shared__ float s_light[VXL_MAX_LIGHTS * 4];   // position.xyz, range
     load_luts(S.lut, g_lut);
@@ -419,19 +487,30 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_local_lights
     // Tile placement considers the pixels that will cast a ray from the scene: not sky (which the reference shades
     // like any other pixel -- no depth test here -- but whose world position is ~40000 voxels away) and inside
     // some light's range.  A block without such pixels stages nothing.
+    // The box of this pixel's shadow rays: from the surface point towards every light in range, as far as the march goes
+    // (min(hitDist, 164) + 1 voxels along a unit direction; hitDist = 10.5 |L| world units = 1.05 x the way to the light).
     bool hint_ok = false;
+    float3 hlo = make_float3(0.f, 0.f, 0.f), hhi = hlo;
     if (p.valid) {
         const float depth = unorm24(__ldg(F.depth24 + p.idx));
         const float3 pos = p.farvec * (depth * (1.0f + 1.0f / FAR_));                        // LightPoint.frag:89
         normal = decode_normal(__ldg(F.normal + p.idx));                                     // :90
         worldPos = xyz(mat_mul(K.InvView, make_float4(pos.x, pos.y, pos.z, 1.0f)));          // :95
-        if (depth < 0.999f)
-            for (int li = 0; li < n_lights && !hint_ok; ++li) {
+        if (depth < 0.999f) {
+            const float3 o = worldPos * 10.0f;
+            hlo = o - make_float3(3.f, 3.f, 3.f); hhi = o + make_float3(3.f, 3.f, 3.f);     // origin jitter: normal * 0.5 + wd * n.w + rv * 2.5
+            for (int li = 0; li < n_lights; ++li) {
                 const float3 L = make_float3(s_light[li * 4], s_light[li * 4 + 1], s_light[li * 4 + 2]) - worldPos;
-                hint_ok = !(length3(L) > s_light[li * 4 + 3]);
+                const float len = length3(L);
+                if (len > s_light[li * 4 + 3]) continue;
+                hint_ok = true;
+                const float3 e = o + L * (fminf(len * 10.5f, 166.0f) / fmaxf(len, 1e-6f));
+                hlo = make_float3(fminf(hlo.x, e.x), fminf(hlo.y, e.y), fminf(hlo.z, e.z));
+                hhi = make_float3(fmaxf(hhi.x, e.x), fmaxf(hhi.y, e.y), fmaxf(hhi.z, e.z));
             }
+        }
     }
-    const BitTile C = block_prologue<(MODE > 0), G>(V, S, hint_ok, worldPos * 10.0f);
+    const BitTile C = block_prologue<(MODE > 0), G>(V, S, &tm_tile, hint_ok, hlo, hhi, hlo, hhi);
     unsigned rays = 0, pixels = 0, exact = 0;
     int steps = 0;
     unsigned long long shadowed = 0ull;                  // bit li: light li is occluded at this pixel (the mirrored write-out below)
@@ -478,10 +557,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_local_lights
 // LightReflection.frag:60-113
 // -------------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_reflection(VolView V, FrameView F, ViewK K, const float* __restrict__ g_lut,
+__global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_reflection(VolView V, const __grid_constant__ CUtensorMap tm_tile, FrameView F, ViewK K, const float* __restrict__ g_lut,
                                                     float* __restrict__ out_t, unsigned long long* __restrict__ g_stats) {
     typedef ReflGeom G;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     BlockShared<G>& S = *reinterpret_cast<BlockShared<G>*>(smem_raw);
     load_luts(S.lut, g_lut);
     const PixelCtx p = pixel_ctx(F, K);
@@ -497,7 +576,20 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_reflection(V
             wcp0 = xyz(mat_mul(K.InvView, make_float4(pos.x, pos.y, pos.z, 1.0f))) * 10.0f;  // :93
         }
     }
-    const BitTile C = block_prologue<(MODE > 0), G>(V, S, lit, wcp0 + normal);
+    // the box of the reflection ray: from the surface point along the mirror direction (:79-92), 165 steps of up to 1.5 voxels; the
+    // roughness jitter (:96) bends it by at most a tenth
+    float3 hlo = make_float3(0.f, 0.f, 0.f), hhi = hlo;
+    if (lit) {
+        const float3 Vv = normalize3(pos) * -1.0f;
+        const float3 N = xyz(mat_mul(K.View, make_float4(normal.x, normal.y, normal.z, 0.0f)));
+        const float3 I = Vv * -1.0f;
+        const float3 R = I - N * dot3(N, I) * 2.0f;
+        const float3 wd = normalize3(xyz(mat_mul(K.InvView, make_float4(R.x, R.y, R.z, 0.0f))));
+        const float3 o = wcp0 + normal, e = o + wd * 210.0f;
+        hlo = make_float3(fminf(o.x, e.x) - 20.0f, fminf(o.y, e.y) - 20.0f, fminf(o.z, e.z) - 20.0f);
+        hhi = make_float3(fmaxf(o.x, e.x) + 20.0f, fmaxf(o.y, e.y) + 20.0f, fmaxf(o.z, e.z) + 20.0f);
+    }
+    const BitTile C = block_prologue<(MODE > 0), G>(V, S, &tm_tile, lit, hlo, hhi, hlo, hhi);
     unsigned rays = 0, pixels = 0, exact = 0;
     int steps = 0;
     float t = 256.0f;
@@ -573,11 +665,13 @@ int vxl_pass_ambient(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, const 
     if (!out_shadow && !out_ao) return VXL_OK;
     if (F.n_tiles == 0) return VXL_OK;
     if (vol->dirty) { if (int e = vxl_volume_build_occupancy(vol)) return e; }
+    const CUtensorMap* tm = nullptr;
+    if (int e = level_tensor_map(vol->occ[AmbientGeom::SHIFT - 2], AmbientGeom::TW, AmbientGeom::TY, AmbientGeom::TY, &tm)) return e;
 #define VXL_AMB(MODE_)                                                                                                                  \
     do {                                                                                                                            \
         if (MODE_) VXL_CUDA(cudaFuncSetAttribute(k_ambient<MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<AmbientGeom, (MODE_ > 0)>())); \
         k_ambient<MODE_><<<grid_for(F), BLOCK_THREADS, smem_bytes<AmbientGeom, (MODE_ > 0)>(), ctx->stream>>>(                       \
-            vol_view(vol), F, make_viewk(view), ctx->d_luts, n_ao, out_shadow, out_ao, ctx->d_stats);                               \
+            vol_view(vol), *tm, F, make_viewk(view), ctx->d_luts, n_ao, out_shadow, out_ao, ctx->d_stats);                               \
     } while (0)
     if (ctx->variant == 0) VXL_AMB(0); else if (ctx->variant == 1) VXL_AMB(1); else VXL_AMB(2);
 #undef VXL_AMB
@@ -600,11 +694,13 @@ static int local_lights(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, con
     if (vol->dirty) { if (int e = vxl_volume_build_occupancy(vol)) return e; }
     VXL_CUDA(cudaMemcpyAsync(ctx->d_lights, lights, (size_t)n_lights * light_bytes, cudaMemcpyHostToDevice, ctx->stream));
     const size_t plane = ctx->light_plane_stride ? ctx->light_plane_stride : frame_pixels(frame);
+    const CUtensorMap* tm = nullptr;
+    if (int e = level_tensor_map(vol->occ[LocalGeom::SHIFT - 2], LocalGeom::TW, LocalGeom::TY, LocalGeom::TY, &tm)) return e;
 #define VXL_LL(SPOT_, MODE_)                                                                                                              \
     do {                                                                                                                              \
         if (MODE_) VXL_CUDA(cudaFuncSetAttribute(k_local_lights<SPOT_, MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<LocalGeom, (MODE_ > 0)>())); \
         k_local_lights<SPOT_, MODE_><<<grid_for(F), BLOCK_THREADS, smem_bytes<LocalGeom, (MODE_ > 0)>(), ctx->stream>>>(              \
-            vol_view(vol), F, make_viewk(view), ctx->d_luts, (const float*)ctx->d_lights, n_lights, out_shadow, plane, ctx->d_stats); \
+            vol_view(vol), *tm, F, make_viewk(view), ctx->d_luts, (const float*)ctx->d_lights, n_lights, out_shadow, plane, ctx->d_stats); \
     } while (0)
     if (spot) { if (ctx->variant == 0) VXL_LL(true, 0); else if (ctx->variant == 1) VXL_LL(true, 1); else VXL_LL(true, 2); }
     else { if (ctx->variant == 0) VXL_LL(false, 0); else if (ctx->variant == 1) VXL_LL(false, 1); else VXL_LL(false, 2); }
@@ -633,11 +729,13 @@ int vxl_pass_reflection(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, con
     if (!F.material) { set_error("vxl_pass_reflection: frame.material is NULL"); return VXL_ERR_INVALID; }
     if (F.n_tiles == 0) return VXL_OK;
     if (vol->dirty) { if (int e = vxl_volume_build_occupancy(vol)) return e; }
+    const CUtensorMap* tm = nullptr;
+    if (int e = level_tensor_map(vol->occ[ReflGeom::SHIFT - 2], ReflGeom::TW, ReflGeom::TY, ReflGeom::TY, &tm)) return e;
 #define VXL_RF(MODE_)                                                                                                                   \
     do {                                                                                                                            \
         if (MODE_) VXL_CUDA(cudaFuncSetAttribute(k_reflection<MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<ReflGeom, (MODE_ > 0)>())); \
         k_reflection<MODE_><<<grid_for(F), BLOCK_THREADS, smem_bytes<ReflGeom, (MODE_ > 0)>(), ctx->stream>>>(                       \
-            vol_view(vol), F, make_viewk(view), ctx->d_luts, out_spec_t, ctx->d_stats);                                             \
+            vol_view(vol), *tm, F, make_viewk(view), ctx->d_luts, out_spec_t, ctx->d_stats);                                             \
     } while (0)
     if (ctx->variant == 0) VXL_RF(0); else if (ctx->variant == 1) VXL_RF(1); else VXL_RF(2);
 #undef VXL_RF
