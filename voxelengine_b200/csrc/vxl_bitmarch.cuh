@@ -382,14 +382,19 @@ VXL_DI unsigned funnel_r(unsigned lo, unsigned hi, unsigned sh) {
 struct ScanPre { bool ok, near_ok; float hi_max; };
 
 // blo / bhi: every direction of the bundle obeys -blo_a <= dir_a <= bhi_a (all >= 0)
+// low: the lowest coordinate the caller's lookups and texel tests can handle: 0 (there floor == the reference's truncation), or
+// -BM_LOWCOORD for a caller whose candidate test reproduces the truncation at negative coordinates (test_super_cand); the occupancy
+// levels repeat texel 0 at texel -1 for exactly this (vxl_occupancy.cu) and are empty further out.  The near tile's bits are
+// taken as the reference's answer, so it is only used at non-negative coordinates.
+constexpr float BM_LOWCOORD = 150.0f;
 template <int SHIFT, int TY, int TW>
-VXL_DI ScanPre scan_precheck(const BitTile& T, float3 origin, float3 blo, float3 bhi, float reach, float near_reach) {
+VXL_DI ScanPre scan_precheck(const BitTile& T, float3 origin, float3 blo, float3 bhi, float reach, float near_reach, float low = 0.0f) {
     ScanPre P;
     const float cell = (float)(1 << SHIFT);
     const float3 lo = origin - blo * (reach * 1.00002f), hi = origin + bhi * (reach * 1.00002f);
     const float3 tlo = make_float3((float)T.ox * cell, (float)T.oy * cell, (float)T.oz * cell);
     bool ok = T.enabled && T.direct;
-    ok = ok && (lo.x >= fmaxf(tlo.x, 0.0f) + BM_MARGIN) && (lo.y >= fmaxf(tlo.y, 0.0f) + BM_MARGIN) && (lo.z >= fmaxf(tlo.z, 0.0f) + BM_MARGIN);
+    ok = ok && (lo.x >= fmaxf(tlo.x, low) + BM_MARGIN) && (lo.y >= fmaxf(tlo.y, low) + BM_MARGIN) && (lo.z >= fmaxf(tlo.z, low) + BM_MARGIN);
     ok = ok && (hi.x <= fminf(tlo.x + (float)(TW * 32) * cell, BM_MAXCOORD) - BM_MARGIN) &&
          (hi.y <= fminf(tlo.y + (float)TY * cell, BM_MAXCOORD) - BM_MARGIN) && (hi.z <= fminf(tlo.z + (float)TY * cell, BM_MAXCOORD) - BM_MARGIN);
     P.ok = ok;                                                             // NaN anywhere makes a comparison fail
@@ -397,8 +402,8 @@ VXL_DI ScanPre scan_precheck(const BitTile& T, float3 origin, float3 blo, float3
     const float3 nl = blo * (near_reach * 1.00002f), nh = bhi * (near_reach * 1.00002f);
     const float lx = (float)T.nx * 2.0f + BM_MARGIN, ly = (float)T.ny * 2.0f + BM_MARGIN, lz = (float)T.nz * 2.0f + BM_MARGIN;
     const float w = (float)(2 * NEAR_T) - 2.0f * BM_MARGIN;
-    P.near_ok = ok && T.wn != nullptr && origin.x - nl.x >= lx && origin.x + nh.x <= lx + w && origin.y - nl.y >= ly && origin.y + nh.y <= ly + w &&
-                origin.z - nl.z >= lz && origin.z + nh.z <= lz + w;
+    P.near_ok = ok && T.wn != nullptr && origin.x - nl.x >= fmaxf(lx, BM_MARGIN) && origin.x + nh.x <= lx + w && origin.y - nl.y >= fmaxf(ly, BM_MARGIN) &&
+                origin.y + nh.y <= ly + w && origin.z - nl.z >= fmaxf(lz, BM_MARGIN) && origin.z + nh.z <= lz + w;
     return P;
 }
 template <int SHIFT, int TY, int TW>
@@ -635,20 +640,24 @@ VXL_DI bool test_super_cand(const VolView& V, unsigned koff, float3 origin, floa
     const unsigned ax = magic_floor_bits(pos.x - e, M1, 1, 0), bx = magic_floor_bits(pos.x + e, M1, 1, 0);
     const unsigned ay = magic_floor_bits(pos.y - e, M1, 1, 0), by = magic_floor_bits(pos.y + e, M1, 1, 0);
     const unsigned az = magic_floor_bits(pos.z - e, M1, 1, 0), bz = magic_floor_bits(pos.z + e, M1, 1, 0);
-    unsigned off = bz * (unsigned)(V.sx * V.sy) + by * (unsigned)V.sx + bx - koff;
-    if ((ax ^ bx) | (ay ^ by) | (az ^ bz)) {                           // phase 2 within eps of a texel face (about 1 %): exact position
+    const unsigned off = bz * (unsigned)(V.sx * V.sy) + by * (unsigned)V.sx + bx - koff;
+    if (COUNT) ++fetched;
+    unsigned v;
+    const bool low = fminf(fminf(pos.x, pos.y), pos.z) - e < 0.0f;    // a coordinate below zero: the reference truncates toward zero there
+    if (((ax ^ bx) | (ay ^ by) | (az ^ bz)) != 0u || low) {            // phase 2 within eps of a texel face (about 1 %), or a negative coordinate: exact position
         const float3 s2 = s1 * 2.0f;
         float3 r = origin;
 #pragma unroll 1
         for (int i = 0; i < k; ++i) r = r + (i < N1 ? s1 : s2);
-        const unsigned tx = magic_floor_bits(r.x, M1, 1, 0), ty = magic_floor_bits(r.y, M1, 1, 0), tz = magic_floor_bits(r.z, M1, 1, 0);
-        off = tz * (unsigned)(V.sx * V.sy) + ty * (unsigned)V.sx + tx - koff;
-    }
-    if (COUNT) ++fetched;
-    const unsigned v = ldg(V.bytes + off);
+        // Light.frag:140 ivec3(pos / 2) in phase 1, :163 ivec3(pos) / 2 in phase 2; out of range reads 0
+        if (ph1) v = fetch_texel(V, f2i(r.x / 2.0f), f2i(r.y / 2.0f), f2i(r.z / 2.0f));
+        else v = fetch_texel(V, f2i(r.x) / 2, f2i(r.y) / 2, f2i(r.z) / 2);
+    } else v = ldg(V.bytes + off);
     if (v == 0u) return false;
     if (!ph1) return true;
-    const unsigned bit = hash_bit1(pos.x) | (hash_bit1(pos.y) << 1) | (hash_bit1(pos.z) << 2);
+    unsigned bit;
+    if (low) bit = (gmod(pos.x, 0.5f) > 0.25f ? 1u : 0u) | (gmod(pos.y, 0.5f) > 0.25f ? 2u : 0u) | (gmod(pos.z, 0.5f) > 0.25f ? 4u : 0u);    // :142-146
+    else bit = hash_bit1(pos.x) | (hash_bit1(pos.y) << 1) | (hash_bit1(pos.z) << 2);
     return ((v >> bit) & 1u) != 0u;
 }
 

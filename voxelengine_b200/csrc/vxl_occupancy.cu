@@ -41,18 +41,28 @@ __global__ void __launch_bounds__(256) k_occ_texels(const uint8_t* __restrict__ 
     const long long total = (long long)xw * cyp * cz;
     if (i >= total) return;
     const int ay = (int)(i % cyp), w = (int)((i / cyp) % xw), az = (int)(i / ((long long)cyp * xw));
-    const int y = ay - border, z = az - border, x0 = w * 32 - border;      // border is a multiple of 32: x0 stays 32-aligned
+    // Texel -1 of every axis repeats texel 0: the reference truncates toward zero (ivec3(pos / 2), ivec3(pos) / 2), so a probe at a
+    // coordinate in (-2, 0) reads texel 0.  With floor(pos / 2) = -1 there, the repeated texel gives the same answer, and the
+    // coarser levels built from this one inherit it (cell -1 = texel -1 | texel -2 = texel 0).  Everything further out is empty.
+    int y = ay - border, z = az - border;
+    const int x0 = w * 32 - border;                                        // border is a multiple of 32: x0 stays 32-aligned
+    if (y == -1) y = 0;
+    if (z == -1) z = 0;
     uint32_t word = 0;
-    if (y >= 0 && y < sy && z >= 0 && z < sz && x0 >= 0 && x0 < sx) {
-        const uint8_t* row = bytes + (size_t)y * sx + (size_t)z * ((size_t)sx * sy) + x0;
-        if (x0 + 32 <= sx && (reinterpret_cast<uintptr_t>(row) & 15) == 0) {
-            const uint4 a = __ldg(reinterpret_cast<const uint4*>(row)), b = __ldg(reinterpret_cast<const uint4*>(row) + 1);
-            word = nonzero_bytes4(a.x) | (nonzero_bytes4(a.y) << 4) | (nonzero_bytes4(a.z) << 8) | (nonzero_bytes4(a.w) << 12) |
-                   (nonzero_bytes4(b.x) << 16) | (nonzero_bytes4(b.y) << 20) | (nonzero_bytes4(b.z) << 24) | (nonzero_bytes4(b.w) << 28);
-        } else {
-            const int n = min(32, sx - x0);
-            for (int k = 0; k < n; ++k)
-                if (row[k]) word |= 1u << k;
+    if (y >= 0 && y < sy && z >= 0 && z < sz) {
+        const uint8_t* row0 = bytes + (size_t)y * sx + (size_t)z * ((size_t)sx * sy);
+        if (x0 == -32) word = row0[0] ? 0x80000000u : 0u;                  // texel -1 along x
+        else if (x0 >= 0 && x0 < sx) {
+            const uint8_t* row = row0 + x0;
+            if (x0 + 32 <= sx && (reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+                const uint4 a = __ldg(reinterpret_cast<const uint4*>(row)), b = __ldg(reinterpret_cast<const uint4*>(row) + 1);
+                word = nonzero_bytes4(a.x) | (nonzero_bytes4(a.y) << 4) | (nonzero_bytes4(a.z) << 8) | (nonzero_bytes4(a.w) << 12) |
+                       (nonzero_bytes4(b.x) << 16) | (nonzero_bytes4(b.y) << 20) | (nonzero_bytes4(b.z) << 24) | (nonzero_bytes4(b.w) << 28);
+            } else {
+                const int n = min(32, sx - x0);
+                for (int k = 0; k < n; ++k)
+                    if (row[k]) word |= 1u << k;
+            }
         }
     }
     out[i] = word;

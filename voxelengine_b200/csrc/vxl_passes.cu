@@ -1,6 +1,6 @@
 // vxl_passes.cu -- the four light passes and the ray-level entry as sm_100a kernels.
 //
-// One thread per pixel of a tile-compact frame shard; a thread block covers 32x16 pixels (a warp 8x4).
+// A thread block covers a 64x32-pixel region of a tile-compact frame shard; its 16 warps draw 8x4-pixel work items from it.
 // Ray generation follows the reference fragment shaders line by line (citations inline).  The
 // rays of a block start within a few voxels of each other, so the block stages the occupancy-bit
 // tile around them in shared memory once and every probe tests that tile before touching the
@@ -23,6 +23,7 @@ struct BlockShared {
     int bb[12];                               // boxes of the block's rays: [0..5] whole rays, [6..11] their first stretch (near tile)
     unsigned acc[4];
     uint64_t bar;                             // mbarrier the TMA copy of `tile` completes
+    int next_item;                            // work items of the region handed out so far
     alignas(128) uint32_t tile[G::TY * G::TY * G::TW];     // from here on: kernel variant 0 allocates only the header
     uint32_t dtile[G::DW * G::DT * G::DT];
     uint32_t ntile[G::NEAR ? NEAR_T * NEAR_T : 1];
@@ -45,6 +46,9 @@ constexpr size_t smem_bytes() {
 // shifted by 16 cells -- so the window reaches at least 40 cells (160 voxels) either side of the block's centre along x.
 // Ambient: 67.7 KB + 11.9 KB + 4 KB near tile + 4 KB LUTs + 19 KB pooled-resolve state = 107 KB, two 512-thread blocks per SM.
 // Local lights / reflection: three blocks per SM with TY = 68 (54.2 + 9.6 + 4 KB), or two with TY = 80 (VXL_PASS_BLOCKS = 2).
+#ifndef VXL_AO_PROMOTE
+#define VXL_AO_PROMOTE 0
+#endif
 #ifndef VXL_AO_QCAP
 #define VXL_AO_QCAP 64            // pending candidate tests per warp (>= 63: 31 left over + 32 new); 0 = per-lane resolve (round-1 kernel)
 #endif
@@ -74,6 +78,7 @@ __device__ __forceinline__ BitTile block_prologue(const VolView& V, BlockShared<
     constexpr int NBB = G::NEAR ? 12 : 6;
     if (threadIdx.x < NBB) S.bb[threadIdx.x] = (threadIdx.x % 6) < 3 ? 0x7fffffff : -0x7fffffff - 1;
     if (threadIdx.x < 4) S.acc[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) S.next_item = 0;
     if (FAST && threadIdx.x == 0) mbar_init(&S.bar, 1u);
     __syncthreads();
     if (!FAST) return T;
@@ -118,6 +123,22 @@ __device__ __forceinline__ BitTile block_prologue(const VolView& V, BlockShared<
     T.enabled = true;
     return T;
 }
+
+// the next work item of the region for this warp (>= REGION_ITEMS: none left)
+template <typename BS>
+__device__ __forceinline__ int next_item(BS& S) {
+    int item = 0;
+    if ((threadIdx.x & 31) == 0) item = atomicAdd(&S.next_item, 1);
+    return __shfl_sync(0xFFFFFFFFu, item, 0);
+}
+struct Box3 {
+    float3 lo, hi;
+    __device__ __forceinline__ Box3() : lo(make_float3(3e38f, 3e38f, 3e38f)), hi(make_float3(-3e38f, -3e38f, -3e38f)) {}
+    __device__ __forceinline__ void add(float3 p) {
+        lo = make_float3(fminf(lo.x, p.x), fminf(lo.y, p.y), fminf(lo.z, p.z));
+        hi = make_float3(fmaxf(hi.x, p.x), fmaxf(hi.y, p.y), fmaxf(hi.z, p.z));
+    }
+};
 
 // UNIFORM: `dist` is the same for every lane of the warp, which allows the masked-lane lockstep loops of
 // march_bits.  Measured slower than per-lane exits on config 3 (profiles/r1e vs r1d), so the passes use false.
@@ -224,19 +245,22 @@ __device__ __forceinline__ float ao_pooled(const VolView& V, const BitTile& C, B
         bitangent = cross3(normal, tangent);                                                                                   // :113
         // one eligibility test per pixel covers all its rays: -blo_a <= dir_a <= bhi_a (ao_bounds); reach: 128 + 1 voxels of march, 20 for
         // the near tile's 8 probes
-        const ScanPre pre = scan_precheck<G::SHIFT, G::TY, G::TW>(C, origin, blo, bhi, 129.0f, 20.0f);
+        const ScanPre pre = scan_precheck<G::SHIFT, G::TY, G::TW>(C, origin, blo, bhi, 129.0f, 20.0f, -BM_LOWCOORD);
         near_ok = pre.near_ok;
-        if (pre.ok) mode = 1;
-        else {
-            // the box around the rays at non-negative coordinates (there floor == the reference's truncation) and at most 160 voxels past
-            // the volume's far faces (the level array has 192 voxels of empty cells around it) and below the magic floor's coordinate
-            // limit: the level array can be indexed directly
-            const float3 rl = blo * (129.0f * 1.00002f), rh = bhi * (129.0f * 1.00002f);
-            const float3 hi = make_float3(fminf((float)(2 * V.sx + 160), BM_MAXCOORD), fminf((float)(2 * V.sy + 160), BM_MAXCOORD), fminf((float)(2 * V.sz + 160), BM_MAXCOORD));
-            const bool inside = C.direct && origin.x - rl.x >= BM_MARGIN && origin.y - rl.y >= BM_MARGIN && origin.z - rl.z >= BM_MARGIN &&
-                                origin.x + rh.x <= hi.x - BM_MARGIN && origin.y + rh.y <= hi.y - BM_MARGIN && origin.z + rh.z <= hi.z - BM_MARGIN;
-            mode = inside ? 2 : 3;                                                  // (NaN anywhere fails the comparisons)
-        }
+        // the box around the rays no more than 150 voxels below zero and 160 voxels past the volume's far faces (the level array
+        // has 192 voxels of border around it: texel -1 repeats texel 0, the rest is empty) and below the magic floor's
+        // coordinate limit: the level array can be indexed directly
+        const float3 rl = blo * (129.0f * 1.00002f), rh = bhi * (129.0f * 1.00002f);
+        const float3 hi = make_float3(fminf((float)(2 * V.sx + 160), BM_MAXCOORD), fminf((float)(2 * V.sy + 160), BM_MAXCOORD), fminf((float)(2 * V.sz + 160), BM_MAXCOORD));
+        const float lowc = BM_MARGIN - BM_LOWCOORD;
+        const bool inside = C.direct && origin.x - rl.x >= lowc && origin.y - rl.y >= lowc && origin.z - rl.z >= lowc &&
+                            origin.x + rh.x <= hi.x - BM_MARGIN && origin.y + rh.y <= hi.y - BM_MARGIN && origin.z + rh.z <= hi.z - BM_MARGIN;
+        mode = pre.ok ? 1 : (inside ? 2 : 3);                                       // (NaN anywhere fails the comparisons)
+#if VXL_AO_PROMOTE
+        // a warp whose pixels disagree would run the scan twice, once per source: when some pixel has to look in global memory,
+        // the others of the warp do too (the same bits, read from L2)
+        if (__any_sync(__activemask(), mode == 2) && mode == 1 && inside) { mode = 2; near_ok = false; }
+#endif
 #ifdef VXL_EXP_SKIP        // timing experiments only (results are wrong): drop the pixels of mode >= VXL_EXP_SKIP
         if (mode >= VXL_EXP_SKIP) mode = 0;
 #endif
@@ -244,8 +268,8 @@ __device__ __forceinline__ float ao_pooled(const VolView& V, const BitTile& C, B
         exact += mode == VXL_EXP_MODECNT ? 1u : 0u;
 #endif
     }
-    // one eps for everybody (resolve_super_cand): no coordinate of a scanned ray exceeds the volume's extent
-    const float eps = (fminf((float)(2 * max(V.sx, max(V.sy, V.sz))), BM_MAXCOORD) + 1.0f) * (1.0f / 262144.0f);
+    // one eps for everybody (test_super_cand): no coordinate of a scanned ray is further than 200 voxels from the volume
+    const float eps = (fminf((float)(2 * max(V.sx, max(V.sy, V.sz)) + 200), BM_MAXCOORD) + 1.0f) * (1.0f / 262144.0f);
     typedef ScanLook<false, (unsigned)(G::TY * G::TY), (unsigned)G::TY> TileLook;
     const TileLook look_tile = TileLook::make(C.w, G::SHIFT, C.ox, C.oy, C.oz, 0u, 0u);
     const ScanLook<false> look_near = (G::NEAR && near_ok) ? ScanLook<false>::make(C.wn, 1, C.nx, C.ny, C.nz, (unsigned)NEAR_T, (unsigned)NEAR_T)
@@ -360,56 +384,70 @@ __device__ __forceinline__ float ao_pooled(const VolView& V, const BitTile& C, B
 // -------------------------------------------------------------------------------------------------
 // LightAmbient.frag:134-175 + calculateAmbientIrradiance :111-126
 // -------------------------------------------------------------------------------------------------
+// what the ambient pass derives from the G-buffer for one pixel
+struct AmbPixel { bool lit; float3 normal, wcp0; float bias; };
+__device__ __forceinline__ AmbPixel ambient_pixel(const FrameView& F, const ViewK& K, const PixelCtx& p) {
+    AmbPixel a;
+    a.lit = false; a.normal = make_float3(0.f, 0.f, 0.f); a.wcp0 = a.normal; a.bias = 0.0f;
+    if (p.valid) {
+        const float depth = unorm24(__ldg(F.depth24 + p.idx));
+        if (depth < 0.999f) {                                                         // :138
+            a.lit = true;
+            const float3 pos = p.farvec * (depth * (1.0f + 1.0f / FAR_));              // :141
+            a.normal = decode_normal(__ldg(F.normal + p.idx));                         // :142
+            a.wcp0 = xyz(mat_mul(K.InvView, make_float4(pos.x, pos.y, pos.z, 1.0f))) * 10.0f;   // :150
+            a.bias = gsmoothstep(0.0f, 0.2f, depth) * 50.0f + 1.5f;                    // :158
+        }
+    }
+    return a;
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(BLOCK_THREADS, VXL_AMBIENT_BLOCKS) k_ambient(VolView V, const __grid_constant__ CUtensorMap tm_tile, FrameView F, ViewK K, const float* __restrict__ g_lut, int n_ao,
+__global__ void __launch_bounds__(BLOCK_THREADS, VXL_AMBIENT_BLOCKS) k_ambient(const __grid_constant__ VolView V, const __grid_constant__ CUtensorMap tm_tile, const __grid_constant__ FrameView F, const __grid_constant__ ViewK K, const float* __restrict__ g_lut, int n_ao,
                                                  float* __restrict__ out_shadow, float* __restrict__ out_ao,
                                                  unsigned long long* __restrict__ g_stats) {
     typedef AmbientGeom G;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BlockShared<G>& S = *reinterpret_cast<BlockShared<G>*>(smem_raw);
     load_luts(S.lut, g_lut);
-    const PixelCtx p = pixel_ctx(F, K);
-    float depth = 1.0f;
-    float3 normal = make_float3(0.f, 0.f, 0.f), wcp0 = make_float3(0.f, 0.f, 0.f);
-    float bias = 0.0f;
-    bool lit = false;
-    if (p.valid) {
-        depth = unorm24(__ldg(F.depth24 + p.idx));
-        if (depth < 0.999f) {                                                         // :138
-            lit = true;
-            const float3 pos = p.farvec * (depth * (1.0f + 1.0f / FAR_));              // :141
-            normal = decode_normal(__ldg(F.normal + p.idx));                           // :142
-            wcp0 = xyz(mat_mul(K.InvView, make_float4(pos.x, pos.y, pos.z, 1.0f))) * 10.0f;   // :150
-            bias = gsmoothstep(0.0f, 0.2f, depth) * 50.0f + 1.5f;                      // :158
-        }
-    }
-    // the box this pixel's rays stay in, for the placement of the block's tiles (approximate: the exact origin comes later)
-    float3 blo = make_float3(0.f, 0.f, 0.f), bhi = blo, flo = blo, fhi = blo, nlo = blo, nhi = blo;
-    if (lit) {
-        const float3 o = wcp0 + normal * bias;
-        flo = fhi = nlo = nhi = o;
-        if (out_ao && n_ao > 0) {
-            ao_bounds(normal, blo, bhi);
-            flo = o - blo * 130.0f; fhi = o + bhi * 130.0f;
-            nlo = o - blo * 21.0f; nhi = o + bhi * 21.0f;
+    const RegionCtx R = region_ctx(F);
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const bool want_ao = out_ao && n_ao > 0;
+    // ---- the boxes the region's rays stay in, for the placement of the block's tiles (approximate: the exact origins come later) ----
+    Box3 far, near;
+    bool any = false;
+    for (int item = warp; item < REGION_ITEMS; item += nwarps) {
+        const AmbPixel a = ambient_pixel(F, K, item_pixel(F, K, R, item));
+        if (!a.lit) continue;
+        any = true;
+        const float3 o = a.wcp0 + a.normal * a.bias;
+        far.add(o); near.add(o);
+        if (want_ao) {
+            float3 blo, bhi;
+            ao_bounds(a.normal, blo, bhi);
+            far.add(o - blo * 130.0f); far.add(o + bhi * 130.0f);
+            near.add(o - blo * 21.0f); near.add(o + bhi * 21.0f);
         }
         if (out_shadow) {          // 128 voxels along normalize(mix(SUN_DIR, jitter, 0.5)): (54, 72, 91) +- 14 of jitter, from an origin jittered by 1.25
-            flo = make_float3(fminf(flo.x, o.x - 16.0f), fminf(flo.y, o.y - 16.0f), fminf(flo.z, o.z - 16.0f));
-            fhi = make_float3(fmaxf(fhi.x, o.x + 70.0f), fmaxf(fhi.y, o.y + 88.0f), fmaxf(fhi.z, o.z + 107.0f));
+            far.add(o - make_float3(16.0f, 16.0f, 16.0f)); far.add(o + make_float3(70.0f, 88.0f, 107.0f));
         }
     }
-    const BitTile C = block_prologue<(MODE > 0), G>(V, S, &tm_tile, lit, flo, fhi, nlo, nhi);
+    const BitTile C = block_prologue<(MODE > 0), G>(V, S, &tm_tile, any, far.lo, far.hi, near.lo, near.hi);
     unsigned rays = 0, pixels = 0, exact = 0;
     int steps = 0;
-    float shadow = 1.0f, ao = 0.0f;
     // the AO rays of tile-march launches go through the warp-pooled resolve (all 32 lanes take part, lit or not)
     const bool POOL = MODE > 0 && G::QCAP > 0 && n_ao <= AO_POOL_MAX_RAYS;
-    float3 ao_origin = make_float3(0.f, 0.f, 0.f);
-    uint32_t ao_noise = 0u;
-    if (p.valid) {
-        if (lit) {
+    // ---- the region's 8x4-pixel work items, handed to whichever warp is free ----
+    for (int item = next_item(S); item < REGION_ITEMS; item = next_item(S)) {
+        const PixelCtx p = item_pixel(F, K, R, item);
+        const AmbPixel a = ambient_pixel(F, K, p);
+        const float3 normal = a.normal;
+        float shadow = 1.0f, ao = 0.0f;
+        float3 ao_origin = make_float3(0.f, 0.f, 0.f), blo = ao_origin, bhi = ao_origin;
+        uint32_t ao_noise = 0u;
+        if (a.lit) {
             float3 wd = normalize3(make_float3(0.3f, 0.4f, 0.5f));                     // SUN_DIR :15,:149
-            float3 wcp = wcp0;
+            float3 wcp = a.wcp0;
             const uint32_t n = get_noise(F, K, p, -1);
             float3 randomVec = cosine_sample_hemisphere(S.lut, n, n >> 8) * 0.1f;      // :151
             randomVec.z *= gsign(unorm8(n >> 16) - 0.5f);                             // :152
@@ -417,17 +455,17 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_AMBIENT_BLOCKS) k_ambient(V
             wd = normalize3(wd);                                                       // :154
             wcp = wcp + wd * (unorm8(n >> 24) * 1.0f);                                 // :155
             wcp = wcp + randomVec * 2.5f;                                              // :156
-            const float3 origin = wcp + normal * bias;
+            const float3 origin = wcp + normal * a.bias;
             if (out_shadow) {
                 if (ray_march<MODE, false, false, G>(V, C, origin, wd, 128.0f, steps, exact) != 128.0f) shadow = 0.0f;   // :167-169
                 rays += 1;
             }
-            if (out_ao && n_ao > 0 && !POOL) {
+            if (want_ao) ao_bounds(normal, blo, bhi);
+            if (want_ao && !POOL) {
                 const float3 tangent = fabsf(normal.z) > 0.5f ? make_float3(0.0f, -normal.z, normal.y)
                                                              : make_float3(-normal.y, normal.x, 0.0f);    // :112
                 const float3 bitangent = cross3(normal, tangent);                                         // :113
-                // every AO direction is tangent * x + bitangent * y + normal * z with |x|, |y|, |z| <= 1: one eligibility
-                // test per pixel covers all its rays (reach: 128 + 1 voxels of march, 20 for the near tile's 8 probes)
+                // one eligibility test per pixel covers all its rays (ao_bounds; reach: 128 + 1 voxels of march, 20 for the near tile's 8 probes)
                 ScanPre pre = ScanPre{false, false, 0.0f};
                 if (MODE > 0) pre = scan_precheck<G::SHIFT, G::TY, G::TW>(C, origin, blo, bhi, 129.0f, 20.0f);
                 float acc = 0.0f;
@@ -441,26 +479,23 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_AMBIENT_BLOCKS) k_ambient(V
                 }
                 ao = (acc / (float)n_ao) * 0.05f;                                                         // :125
             }
-            if (out_ao && n_ao > 0) rays += (unsigned)n_ao;
+            if (want_ao) rays += (unsigned)n_ao;
             ao_origin = origin; ao_noise = n;
-            pixels = 1;
+            pixels += 1;
         }
-    }
-    if (G::QCAP > 0 && POOL && out_ao && n_ao > 0) {
-        const float a = ao_pooled<MODE, G>(V, C, S, F, K, p, p.valid && lit, ao_origin, normal, blo, bhi, ao_noise, n_ao, steps, exact);
-        if (p.valid && lit) ao = a;
-    }
-    if (p.valid) {
-        if (F.n_mirror == 0) {
+        if (G::QCAP > 0 && POOL && want_ao) {
+            const float v = ao_pooled<MODE, G>(V, C, S, F, K, p, a.lit, ao_origin, normal, blo, bhi, ao_noise, n_ao, steps, exact);
+            if (a.lit) ao = v;
+        }
+        if (p.valid) {
             if (out_shadow) out_shadow[p.idx] = shadow;
             if (out_ao) out_ao[p.idx] = ao;
         }
     }
-    if (F.n_mirror) {                                   // several GPUs: row-major write-out into every copy of the stack (vxl_pixel.cuh)
-        __syncthreads();                                // the LUTs are no longer read: their 4 KB become the staging planes
-        float* const planes[2] = {out_shadow, out_ao};
-        const float vals[2] = {shadow, ao};
-        store_rows<2>(F, S.lut, planes, vals);
+    if (F.n_mirror) {                                   // several GPUs: the region's rows into every copy of the stack (vxl_pixel.cuh)
+        __syncthreads();
+        mirror_region(F, R, out_shadow, 1, 0);
+        mirror_region(F, R, out_ao, 1, 0);
     }
     flush_stats(S, g_stats, rays, (unsigned)steps, pixels, exact);
 }
@@ -470,7 +505,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_AMBIENT_BLOCKS) k_ambient(V
 // G-buffer, noise and world position are read / derived once per pixel instead of once per light.
 // -------------------------------------------------------------------------------------------------
 template <bool SPOT, int MODE>
-__global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_local_lights(VolView V, const __grid_constant__ CUtensorMap tm_tile, FrameView F, ViewK K, const float* __restrict__ g_lut,
+__global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_local_lights(const __grid_constant__ VolView V, const __grid_constant__ CUtensorMap tm_tile, const __grid_constant__ FrameView F, const __grid_constant__ ViewK K, const float* __restrict__ g_lut,
                                                       const float* __restrict__ lights, int n_lights,
                                                       float* __restrict__ out_shadow, size_t plane_stride,
                                                       unsigned long long* __restrict__ g_stats) {
@@ -482,43 +517,47 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_local_lights
     constexpr int STRIDE = SPOT ? 16 : 8;
     for (int i = threadIdx.x; i < n_lights * 4; i += blockDim.x) s_light[i] = lights[(i >> 2) * STRIDE + (i & 3)];
     __syncthreads();
-    const PixelCtx p = pixel_ctx(F, K);
-    float3 normal = make_float3(0.f, 0.f, 0.f), worldPos = make_float3(0.f, 0.f, 0.f);
+    const RegionCtx R = region_ctx(F);
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     // Tile placement considers the pixels that will cast a ray from the scene: not sky (which the reference shades
     // like any other pixel -- no depth test here -- but whose world position is ~40000 voxels away) and inside
     // some light's range.  A block without such pixels stages nothing.
-    // The box of this pixel's shadow rays: from the surface point towards every light in range, as far as the march goes
+    // The box of a pixel's shadow rays: from the surface point towards every light in range, as far as the march goes
     // (min(hitDist, 164) + 1 voxels along a unit direction; hitDist = 10.5 |L| world units = 1.05 x the way to the light).
-    bool hint_ok = false;
-    float3 hlo = make_float3(0.f, 0.f, 0.f), hhi = hlo;
-    if (p.valid) {
+    Box3 box;
+    bool any = false;
+    for (int item = warp; item < REGION_ITEMS; item += nwarps) {
+        const PixelCtx p = item_pixel(F, K, R, item);
+        if (!p.valid) continue;
         const float depth = unorm24(__ldg(F.depth24 + p.idx));
+        if (!(depth < 0.999f)) continue;
         const float3 pos = p.farvec * (depth * (1.0f + 1.0f / FAR_));                        // LightPoint.frag:89
-        normal = decode_normal(__ldg(F.normal + p.idx));                                     // :90
-        worldPos = xyz(mat_mul(K.InvView, make_float4(pos.x, pos.y, pos.z, 1.0f)));          // :95
-        if (depth < 0.999f) {
-            const float3 o = worldPos * 10.0f;
-            hlo = o - make_float3(3.f, 3.f, 3.f); hhi = o + make_float3(3.f, 3.f, 3.f);     // origin jitter: normal * 0.5 + wd * n.w + rv * 2.5
-            for (int li = 0; li < n_lights; ++li) {
-                const float3 L = make_float3(s_light[li * 4], s_light[li * 4 + 1], s_light[li * 4 + 2]) - worldPos;
-                const float len = length3(L);
-                if (len > s_light[li * 4 + 3]) continue;
-                hint_ok = true;
-                const float3 e = o + L * (fminf(len * 10.5f, 166.0f) / fmaxf(len, 1e-6f));
-                hlo = make_float3(fminf(hlo.x, e.x), fminf(hlo.y, e.y), fminf(hlo.z, e.z));
-                hhi = make_float3(fmaxf(hhi.x, e.x), fmaxf(hhi.y, e.y), fmaxf(hhi.z, e.z));
-            }
+        const float3 worldPos = xyz(mat_mul(K.InvView, make_float4(pos.x, pos.y, pos.z, 1.0f)));          // :95
+        const float3 o = worldPos * 10.0f;
+        for (int li = 0; li < n_lights; ++li) {
+            const float3 L = make_float3(s_light[li * 4], s_light[li * 4 + 1], s_light[li * 4 + 2]) - worldPos;
+            const float len = length3(L);
+            if (len > s_light[li * 4 + 3]) continue;
+            if (!any) { box.add(o - make_float3(3.f, 3.f, 3.f)); box.add(o + make_float3(3.f, 3.f, 3.f)); }     // origin jitter: normal * 0.5 + wd * n.w + rv * 2.5
+            any = true;
+            box.add(o + L * (fminf(len * 10.5f, 166.0f) / fmaxf(len, 1e-6f)));
         }
     }
-    const BitTile C = block_prologue<(MODE > 0), G>(V, S, &tm_tile, hint_ok, hlo, hhi, hlo, hhi);
+    const BitTile C = block_prologue<(MODE > 0), G>(V, S, &tm_tile, any, box.lo, box.hi, box.lo, box.hi);
     unsigned rays = 0, pixels = 0, exact = 0;
     int steps = 0;
-    unsigned long long shadowed = 0ull;                  // bit li: light li is occluded at this pixel (the mirrored write-out below)
-    if (p.valid) {
+    for (int item = next_item(S); item < REGION_ITEMS; item = next_item(S)) {
+        const PixelCtx p = item_pixel(F, K, R, item);
+        if (p.valid) {
+        const float depth = unorm24(__ldg(F.depth24 + p.idx));
+        const float3 pos = p.farvec * (depth * (1.0f + 1.0f / FAR_));                        // LightPoint.frag:89
+        const float3 normal = decode_normal(__ldg(F.normal + p.idx));                        // :90
+        const float3 worldPos = xyz(mat_mul(K.InvView, make_float4(pos.x, pos.y, pos.z, 1.0f)));          // :95
         const uint32_t n = get_noise(F, K, p, -1);
         float3 rv0 = cosine_sample_hemisphere(S.lut, n, n >> 8) * 0.1f;                      // :111
         rv0.z *= gsign(unorm8(n >> 16) - 0.5f);                                             // :112
         const float nw = unorm8(n >> 24) * 1.0f;
+        bool counted = false;
         for (int li = 0; li < n_lights; ++li) {
             const float3 lpos = make_float3(s_light[li * 4], s_light[li * 4 + 1], s_light[li * 4 + 2]);
             const float range = s_light[li * 4 + 3];
@@ -536,19 +575,16 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_local_lights
                 wcp = wcp + rv0 * 2.5f;                                                      // :116
                 if (ray_march<MODE, SPOT, false, G>(V, C, wcp + normal * 0.5f, wd, hitDist, steps, exact) < hitDist) shadow = 0.0f;   // :125
                 rays += 1;
-                pixels = 1;
+                counted = true;
             }
-            if (F.n_mirror == 0) out_shadow[(size_t)li * plane_stride + p.idx] = shadow;
-            else if (shadow == 0.0f) shadowed |= 1ull << li;
+            out_shadow[(size_t)li * plane_stride + p.idx] = shadow;
+        }
+        if (counted) pixels += 1;
         }
     }
-    if (F.n_mirror) {                                   // several GPUs: two light planes per round through the LUTs' 4 KB
-        for (int li = 0; li < n_lights; li += 2) {
-            __syncthreads();
-            float* const planes[2] = {out_shadow + (size_t)li * plane_stride, li + 1 < n_lights ? out_shadow + (size_t)(li + 1) * plane_stride : nullptr};
-            const float vals[2] = {(shadowed >> li) & 1ull ? 0.0f : 1.0f, (shadowed >> (li + 1)) & 1ull ? 0.0f : 1.0f};
-            store_rows<2>(F, S.lut, planes, vals);
-        }
+    if (F.n_mirror) {                                   // several GPUs: the region's rows of every light plane into every copy of the stack
+        __syncthreads();
+        mirror_region(F, R, out_shadow, n_lights, plane_stride);
     }
     flush_stats(S, g_stats, rays, (unsigned)steps, pixels, exact);
 }
@@ -556,69 +592,74 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_local_lights
 // -------------------------------------------------------------------------------------------------
 // LightReflection.frag:60-113
 // -------------------------------------------------------------------------------------------------
+struct ReflPixel { bool lit; float3 pos, normal, wcp0, wd; };      // wd: the mirror direction in world space (:79-92)
+__device__ __forceinline__ ReflPixel reflection_pixel(const FrameView& F, const ViewK& K, const PixelCtx& p) {
+    ReflPixel a;
+    a.lit = false; a.pos = make_float3(0.f, 0.f, 0.f); a.normal = a.pos; a.wcp0 = a.pos; a.wd = a.pos;
+    if (p.valid) {
+        const float depth = unorm24(__ldg(F.depth24 + p.idx));
+        if (depth < 0.999f) {                                                               // :88
+            a.lit = true;
+            a.pos = p.farvec * (depth * (1.0f + 1.0f / FAR_));                               // :64
+            a.normal = decode_normal(__ldg(F.normal + p.idx));                               // :65
+            a.wcp0 = xyz(mat_mul(K.InvView, make_float4(a.pos.x, a.pos.y, a.pos.z, 1.0f))) * 10.0f;  // :93
+            const float3 Vv = normalize3(a.pos) * -1.0f;                                     // :79
+            const float3 N = xyz(mat_mul(K.View, make_float4(a.normal.x, a.normal.y, a.normal.z, 0.0f)));   // :80
+            const float3 I = Vv * -1.0f;
+            const float3 Rr = I - N * dot3(N, I) * 2.0f;                                     // :81
+            a.wd = normalize3(xyz(mat_mul(K.InvView, make_float4(Rr.x, Rr.y, Rr.z, 0.0f))));          // :92
+        }
+    }
+    return a;
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_reflection(VolView V, const __grid_constant__ CUtensorMap tm_tile, FrameView F, ViewK K, const float* __restrict__ g_lut,
+__global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_reflection(const __grid_constant__ VolView V, const __grid_constant__ CUtensorMap tm_tile, const __grid_constant__ FrameView F, const __grid_constant__ ViewK K, const float* __restrict__ g_lut,
                                                     float* __restrict__ out_t, unsigned long long* __restrict__ g_stats) {
     typedef ReflGeom G;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BlockShared<G>& S = *reinterpret_cast<BlockShared<G>*>(smem_raw);
     load_luts(S.lut, g_lut);
-    const PixelCtx p = pixel_ctx(F, K);
-    float depth = 1.0f;
-    float3 pos = make_float3(0.f, 0.f, 0.f), normal = make_float3(0.f, 0.f, 0.f), wcp0 = make_float3(0.f, 0.f, 0.f);
-    bool lit = false;
-    if (p.valid) {
-        depth = unorm24(__ldg(F.depth24 + p.idx));
-        if (depth < 0.999f) {                                                               // :88
-            lit = true;
-            pos = p.farvec * (depth * (1.0f + 1.0f / FAR_));                                 // :64
-            normal = decode_normal(__ldg(F.normal + p.idx));                                 // :65
-            wcp0 = xyz(mat_mul(K.InvView, make_float4(pos.x, pos.y, pos.z, 1.0f))) * 10.0f;  // :93
-        }
+    const RegionCtx R = region_ctx(F);
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    // the box of a reflection ray: from the surface point along the mirror direction, 165 steps of up to 1.5 voxels; the roughness
+    // jitter (:96) bends it by at most a tenth
+    Box3 box;
+    bool any = false;
+    for (int item = warp; item < REGION_ITEMS; item += nwarps) {
+        const ReflPixel a = reflection_pixel(F, K, item_pixel(F, K, R, item));
+        if (!a.lit) continue;
+        any = true;
+        const float3 o = a.wcp0 + a.normal, e = o + a.wd * 210.0f;
+        box.add(o - make_float3(20.f, 20.f, 20.f)); box.add(o + make_float3(20.f, 20.f, 20.f));
+        box.add(e - make_float3(20.f, 20.f, 20.f)); box.add(e + make_float3(20.f, 20.f, 20.f));
     }
-    // the box of the reflection ray: from the surface point along the mirror direction (:79-92), 165 steps of up to 1.5 voxels; the
-    // roughness jitter (:96) bends it by at most a tenth
-    float3 hlo = make_float3(0.f, 0.f, 0.f), hhi = hlo;
-    if (lit) {
-        const float3 Vv = normalize3(pos) * -1.0f;
-        const float3 N = xyz(mat_mul(K.View, make_float4(normal.x, normal.y, normal.z, 0.0f)));
-        const float3 I = Vv * -1.0f;
-        const float3 R = I - N * dot3(N, I) * 2.0f;
-        const float3 wd = normalize3(xyz(mat_mul(K.InvView, make_float4(R.x, R.y, R.z, 0.0f))));
-        const float3 o = wcp0 + normal, e = o + wd * 210.0f;
-        hlo = make_float3(fminf(o.x, e.x) - 20.0f, fminf(o.y, e.y) - 20.0f, fminf(o.z, e.z) - 20.0f);
-        hhi = make_float3(fmaxf(o.x, e.x) + 20.0f, fmaxf(o.y, e.y) + 20.0f, fmaxf(o.z, e.z) + 20.0f);
-    }
-    const BitTile C = block_prologue<(MODE > 0), G>(V, S, &tm_tile, lit, hlo, hhi, hlo, hhi);
+    const BitTile C = block_prologue<(MODE > 0), G>(V, S, &tm_tile, any, box.lo, box.hi, box.lo, box.hi);
     unsigned rays = 0, pixels = 0, exact = 0;
     int steps = 0;
-    float t = 256.0f;
-    if (p.valid) {
-        if (lit) {
+    for (int item = next_item(S); item < REGION_ITEMS; item = next_item(S)) {
+        const PixelCtx p = item_pixel(F, K, R, item);
+        const ReflPixel a = reflection_pixel(F, K, p);
+        float t = 256.0f;
+        if (a.lit) {
             const float roughness = unorm8(__ldg(F.material + p.idx));                       // :68
-            const float3 Vv = normalize3(pos) * -1.0f;                                       // :79
-            const float3 N = xyz(mat_mul(K.View, make_float4(normal.x, normal.y, normal.z, 0.0f)));   // :80
-            const float3 I = Vv * -1.0f;
-            const float3 R = I - N * dot3(N, I) * 2.0f;                                      // :81
-            float3 wd = normalize3(xyz(mat_mul(K.InvView, make_float4(R.x, R.y, R.z, 0.0f))));        // :92
-            float3 wcp = wcp0;
+            float3 wd = a.wd;
+            float3 wcp = a.wcp0;
             const uint32_t n = get_noise(F, K, p, -1);
             float3 rv = cosine_sample_hemisphere(S.lut, n, n >> 8);                          // :94
             rv.z *= gsign(unorm8(n >> 16) - 0.5f);                                          // :95
             wd = mix3(wd, rv, roughness * 0.1f);                                             // :96
             const float nw = unorm8(n >> 24);
-            wcp = wcp + normal * nw;                                                         // :97
+            wcp = wcp + a.normal * nw;                                                       // :97
             wd = wd * (1.0f + nw * 0.5f);                                                    // :98
-            t = ray_march<MODE, false, false, G>(V, C, wcp + normal, wd, 256.0f, steps, exact);        // :113
-            rays = 1; pixels = 1;
+            t = ray_march<MODE, false, false, G>(V, C, wcp + a.normal, wd, 256.0f, steps, exact);        // :113
+            rays += 1; pixels += 1;
         }
-        if (F.n_mirror == 0) out_t[p.idx] = t;
+        if (p.valid) out_t[p.idx] = t;
     }
     if (F.n_mirror) {
         __syncthreads();
-        float* const planes[1] = {out_t};
-        const float vals[1] = {t};
-        store_rows<1>(F, S.lut, planes, vals);
+        mirror_region(F, R, out_t, 1, 0);
     }
     flush_stats(S, g_stats, rays, (unsigned)steps, pixels, exact);
 }
@@ -670,7 +711,7 @@ int vxl_pass_ambient(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, const 
 #define VXL_AMB(MODE_)                                                                                                                  \
     do {                                                                                                                            \
         if (MODE_) VXL_CUDA(cudaFuncSetAttribute(k_ambient<MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<AmbientGeom, (MODE_ > 0)>())); \
-        k_ambient<MODE_><<<grid_for(F), BLOCK_THREADS, smem_bytes<AmbientGeom, (MODE_ > 0)>(), ctx->stream>>>(                       \
+        k_ambient<MODE_><<<grid_regions(F), BLOCK_THREADS, smem_bytes<AmbientGeom, (MODE_ > 0)>(), ctx->stream>>>(                       \
             vol_view(vol), *tm, F, make_viewk(view), ctx->d_luts, n_ao, out_shadow, out_ao, ctx->d_stats);                               \
     } while (0)
     if (ctx->variant == 0) VXL_AMB(0); else if (ctx->variant == 1) VXL_AMB(1); else VXL_AMB(2);
@@ -699,7 +740,7 @@ static int local_lights(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, con
 #define VXL_LL(SPOT_, MODE_)                                                                                                              \
     do {                                                                                                                              \
         if (MODE_) VXL_CUDA(cudaFuncSetAttribute(k_local_lights<SPOT_, MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<LocalGeom, (MODE_ > 0)>())); \
-        k_local_lights<SPOT_, MODE_><<<grid_for(F), BLOCK_THREADS, smem_bytes<LocalGeom, (MODE_ > 0)>(), ctx->stream>>>(              \
+        k_local_lights<SPOT_, MODE_><<<grid_regions(F), BLOCK_THREADS, smem_bytes<LocalGeom, (MODE_ > 0)>(), ctx->stream>>>(              \
             vol_view(vol), *tm, F, make_viewk(view), ctx->d_luts, (const float*)ctx->d_lights, n_lights, out_shadow, plane, ctx->d_stats); \
     } while (0)
     if (spot) { if (ctx->variant == 0) VXL_LL(true, 0); else if (ctx->variant == 1) VXL_LL(true, 1); else VXL_LL(true, 2); }
@@ -734,7 +775,7 @@ int vxl_pass_reflection(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, con
 #define VXL_RF(MODE_)                                                                                                                   \
     do {                                                                                                                            \
         if (MODE_) VXL_CUDA(cudaFuncSetAttribute(k_reflection<MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<ReflGeom, (MODE_ > 0)>())); \
-        k_reflection<MODE_><<<grid_for(F), BLOCK_THREADS, smem_bytes<ReflGeom, (MODE_ > 0)>(), ctx->stream>>>(                       \
+        k_reflection<MODE_><<<grid_regions(F), BLOCK_THREADS, smem_bytes<ReflGeom, (MODE_ > 0)>(), ctx->stream>>>(                       \
             vol_view(vol), *tm, F, make_viewk(view), ctx->d_luts, out_spec_t, ctx->d_stats);                                             \
     } while (0)
     if (ctx->variant == 0) VXL_RF(0); else if (ctx->variant == 1) VXL_RF(1); else VXL_RF(2);

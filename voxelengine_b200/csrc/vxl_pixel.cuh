@@ -57,6 +57,78 @@ __device__ __forceinline__ PixelCtx pixel_ctx(const FrameView& F, const ViewK& K
     return p;
 }
 
+// ---- light passes: a thread block covers a REGION of the shard and its warps draw 8x4-pixel work items from it ----
+// The block stages ONE occupancy tile for the whole region (vxl_passes.cu: block_prologue), so the staging, the LUTs and the tile
+// placement are paid once per 2048 pixels, and a warp that finishes its item takes the next one instead of waiting at the block's
+// final barrier for the slowest warp.
+#ifndef VXL_REGION_W
+#define VXL_REGION_W 32
+#endif
+#ifndef VXL_REGION_H
+#define VXL_REGION_H 16
+#endif
+constexpr int REGION_W = VXL_REGION_W, REGION_H = VXL_REGION_H;
+constexpr int ITEM_W = 8, ITEM_H = 4;
+constexpr int REGION_ITEMS_X = REGION_W / ITEM_W, REGION_ITEMS = REGION_ITEMS_X * (REGION_H / ITEM_H);
+
+struct RegionCtx { int lt, x0, y0; };               // tile of the shard, pixel offset of the region inside the tile / the row band
+
+__device__ __forceinline__ RegionCtx region_ctx(const FrameView& F) {
+    const int rx = (F.tile_w + REGION_W - 1) / REGION_W, ry = (F.rows + REGION_H - 1) / REGION_H;
+    const int rpt = rx * ry;
+    RegionCtx R;
+    R.lt = blockIdx.x / rpt;
+    const int r = blockIdx.x - R.lt * rpt, iy = r / rx;
+    R.x0 = (r - iy * rx) * REGION_W; R.y0 = iy * REGION_H;
+    return R;
+}
+// pixel (x, y) of the region (0 <= x < REGION_W, 0 <= y < REGION_H)
+__device__ __forceinline__ PixelCtx region_pixel(const FrameView& F, const ViewK& K, const RegionCtx& R, int x, int y) {
+    PixelCtx p;
+    const int lx = R.x0 + x, lb = R.y0 + y, ly = F.row0 + lb;
+    const int gt = F.tile_first + R.lt * F.tile_stride;
+    const int ty = gt / F.tiles_x, tx = gt - ty * F.tiles_x;
+    p.px = tx * F.tile_w + lx;
+    p.py = ty * F.tile_h + ly;
+    p.valid = lx < F.tile_w && lb < F.rows && ly < F.tile_h && p.px < F.width && p.py < F.height && R.lt < F.n_tiles;
+    p.idx = ((size_t)R.lt * F.tile_h + ly) * F.tile_w + lx;
+    p.u = ((float)p.px + 0.5f) / (float)F.width;
+    p.v = ((float)p.py + 0.5f) / (float)F.height;
+    const float ndcx = 2.0f * p.u - 1.0f, ndcy = 1.0f - 2.0f * p.v;
+    const float4 f = mat_mul(K.InvProj, make_float4(ndcx, ndcy, 1.0f, 1.0f));
+    p.farvec = make_float3(f.x / f.w, f.y / f.w, f.z / f.w);
+    return p;
+}
+// this lane's pixel of work item `item` (a warp covers 8x4 pixels: coherent rays)
+__device__ __forceinline__ PixelCtx item_pixel(const FrameView& F, const ViewK& K, const RegionCtx& R, int item) {
+    const int lane = threadIdx.x & 31, iy = item / REGION_ITEMS_X, ix = item - iy * REGION_ITEMS_X;
+    return region_pixel(F, K, R, ix * ITEM_W + (lane & 7), iy * ITEM_H + (lane >> 3));
+}
+static inline unsigned grid_regions(const FrameView& F) {
+    const int rx = (F.tile_w + REGION_W - 1) / REGION_W, ry = (F.rows + REGION_H - 1) / REGION_H;
+    return (unsigned)(rx * ry * F.n_tiles);
+}
+// Several GPUs: the region's finished output rows, re-read from the rank's own planes (L2) after a block barrier, are repeated into
+// the same slot of every peer's copy of the gathered stack (peer-to-peer stores over NVLink; vxl_ctx_set_output_mirrors).  A warp
+// takes whole rows of the region: 128-byte stores -- an 8x4 item on its own would be four 32-byte packets per plane.
+__device__ __forceinline__ void mirror_region(const FrameView& F, const RegionCtx& R, float* planes, int n_planes, size_t plane_stride) {
+    if (!planes) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int gt = F.tile_first + R.lt * F.tile_stride;
+    const int ty = gt / F.tiles_x, tx = gt - ty * F.tiles_x;
+    for (int y = warp; y < REGION_H; y += nwarps)
+        for (int x = lane; x < REGION_W; x += 32) {
+            const int lx = R.x0 + x, lb = R.y0 + y, ly = F.row0 + lb;
+            if (!(lx < F.tile_w && lb < F.rows && ly < F.tile_h && tx * F.tile_w + lx < F.width && ty * F.tile_h + ly < F.height && R.lt < F.n_tiles)) continue;
+            const size_t idx = ((size_t)R.lt * F.tile_h + ly) * F.tile_w + lx;
+            for (int k = 0; k < n_planes; ++k) {
+                float* const q = planes + (size_t)k * plane_stride + idx;
+                const float v = __ldcg(q);                       // written by this block before the barrier; L2 is the point of coherence
+                for (int i = 0; i < F.n_mirror; ++i) *reinterpret_cast<float*>(reinterpret_cast<char*>(q) + F.mirror[i]) = v;
+            }
+        }
+}
+
 // LightAmbient.frag:44-52 getNoise() (s < 0) / getNoise(int s)
 __device__ __forceinline__ uint32_t get_noise(const FrameView& F, const ViewK& K, const PixelCtx& p, int s) {
     float fx, fy;
