@@ -19,7 +19,7 @@ f = wl.gb.frame()
 sh = ctx.empty(wl.gb.shape, torch.float32)
 ao = ctx.empty(wl.gb.shape, torch.float32)
 for _ in range(reps):
-    check(lib.vxl_pass_ambient(ctx.h, wl.vol.h, v.ctypes.data_as(C.c_void_p), C.byref(f), wl.n_ao if what != "sun" else 0,
+    check(lib.vxl_pass_ambient(ctx.h, wl.vol.h, v.ctypes.data_as(C.c_void_p), C.byref(f), int(os.environ.get("VXL_EXP_NAO1", wl.n_ao)) if what != "sun" else 0,
                                C.c_void_p(sh.data_ptr()) if what != "ao" else None, C.c_void_p(ao.data_ptr()) if what != "sun" else None), "ambient")
     torch.cuda.synchronize()
 wl.close()

@@ -1,6 +1,7 @@
 // vxl_passes.cu -- the four light passes and the ray-level entry as sm_100a kernels.
 //
-// A thread block covers a 64x32-pixel region of a tile-compact frame shard; its 16 warps draw 8x4-pixel work items from it.
+// A thread block covers a region of a tile-compact frame shard (32x16 pixels for the ambient pass, 64x32 for the others); its 16 warps
+// draw 8x4-pixel work items from it.
 // Ray generation follows the reference fragment shaders line by line (citations inline).  The
 // rays of a block start within a few voxels of each other, so the block stages the occupancy-bit
 // tile around them in shared memory once and every probe tests that tile before touching the
@@ -123,6 +124,8 @@ __device__ __forceinline__ BitTile block_prologue(const VolView& V, BlockShared<
     T.enabled = true;
     return T;
 }
+
+constexpr int NWARPS = BLOCK_THREADS / 32;
 
 // the next work item of the region for this warp (>= REGION_ITEMS: none left)
 template <typename BS>
@@ -407,17 +410,18 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_AMBIENT_BLOCKS) k_ambient(c
                                                  float* __restrict__ out_shadow, float* __restrict__ out_ao,
                                                  unsigned long long* __restrict__ g_stats) {
     typedef AmbientGeom G;
+    typedef AmbientRegion RG;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BlockShared<G>& S = *reinterpret_cast<BlockShared<G>*>(smem_raw);
     load_luts(S.lut, g_lut);
-    const RegionCtx R = region_ctx(F);
-    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const RegionCtx R = region_ctx<RG>(F);
+    const int warp = threadIdx.x >> 5;
     const bool want_ao = out_ao && n_ao > 0;
     // ---- the boxes the region's rays stay in, for the placement of the block's tiles (approximate: the exact origins come later) ----
     Box3 far, near;
     bool any = false;
-    for (int item = warp; item < REGION_ITEMS; item += nwarps) {
-        const AmbPixel a = ambient_pixel(F, K, item_pixel(F, K, R, item));
+    for (int item = warp; item < RG::ITEMS; item += NWARPS) {
+        const AmbPixel a = ambient_pixel(F, K, item_pixel<RG>(F, K, R, item));
         if (!a.lit) continue;
         any = true;
         const float3 o = a.wcp0 + a.normal * a.bias;
@@ -438,8 +442,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_AMBIENT_BLOCKS) k_ambient(c
     // the AO rays of tile-march launches go through the warp-pooled resolve (all 32 lanes take part, lit or not)
     const bool POOL = MODE > 0 && G::QCAP > 0 && n_ao <= AO_POOL_MAX_RAYS;
     // ---- the region's 8x4-pixel work items, handed to whichever warp is free ----
-    for (int item = next_item(S); item < REGION_ITEMS; item = next_item(S)) {
-        const PixelCtx p = item_pixel(F, K, R, item);
+    for (int item = next_item(S); item < RG::ITEMS; item = next_item(S)) {
+        const PixelCtx p = item_pixel<RG>(F, K, R, item);
         const AmbPixel a = ambient_pixel(F, K, p);
         const float3 normal = a.normal;
         float shadow = 1.0f, ao = 0.0f;
@@ -494,8 +498,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_AMBIENT_BLOCKS) k_ambient(c
     }
     if (F.n_mirror) {                                   // several GPUs: the region's rows into every copy of the stack (vxl_pixel.cuh)
         __syncthreads();
-        mirror_region(F, R, out_shadow, 1, 0);
-        mirror_region(F, R, out_ao, 1, 0);
+        mirror_region<RG>(F, R, out_shadow, 1, 0);
+        mirror_region<RG>(F, R, out_ao, 1, 0);
     }
     flush_stats(S, g_stats, rays, (unsigned)steps, pixels, exact);
 }
@@ -510,6 +514,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_local_lights
                                                       float* __restrict__ out_shadow, size_t plane_stride,
                                                       unsigned long long* __restrict__ g_stats) {
     typedef LocalGeom G;
+    typedef PassRegion RG;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BlockShared<G>& S = *reinterpret_cast<BlockShared<G>*>(smem_raw);
     __shared__ float s_light[VXL_MAX_LIGHTS * 4];   // position.xyz, range
@@ -517,8 +522,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_local_lights
     constexpr int STRIDE = SPOT ? 16 : 8;
     for (int i = threadIdx.x; i < n_lights * 4; i += blockDim.x) s_light[i] = lights[(i >> 2) * STRIDE + (i & 3)];
     __syncthreads();
-    const RegionCtx R = region_ctx(F);
-    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const RegionCtx R = region_ctx<RG>(F);
+    const int warp = threadIdx.x >> 5;
     // Tile placement considers the pixels that will cast a ray from the scene: not sky (which the reference shades
     // like any other pixel -- no depth test here -- but whose world position is ~40000 voxels away) and inside
     // some light's range.  A block without such pixels stages nothing.
@@ -526,8 +531,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_local_lights
     // (min(hitDist, 164) + 1 voxels along a unit direction; hitDist = 10.5 |L| world units = 1.05 x the way to the light).
     Box3 box;
     bool any = false;
-    for (int item = warp; item < REGION_ITEMS; item += nwarps) {
-        const PixelCtx p = item_pixel(F, K, R, item);
+    for (int item = warp; item < RG::ITEMS; item += NWARPS) {
+        const PixelCtx p = item_pixel<RG>(F, K, R, item);
         if (!p.valid) continue;
         const float depth = unorm24(__ldg(F.depth24 + p.idx));
         if (!(depth < 0.999f)) continue;
@@ -546,8 +551,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_local_lights
     const BitTile C = block_prologue<(MODE > 0), G>(V, S, &tm_tile, any, box.lo, box.hi, box.lo, box.hi);
     unsigned rays = 0, pixels = 0, exact = 0;
     int steps = 0;
-    for (int item = next_item(S); item < REGION_ITEMS; item = next_item(S)) {
-        const PixelCtx p = item_pixel(F, K, R, item);
+    for (int item = next_item(S); item < RG::ITEMS; item = next_item(S)) {
+        const PixelCtx p = item_pixel<RG>(F, K, R, item);
         if (p.valid) {
         const float depth = unorm24(__ldg(F.depth24 + p.idx));
         const float3 pos = p.farvec * (depth * (1.0f + 1.0f / FAR_));                        // LightPoint.frag:89
@@ -584,7 +589,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_local_lights
     }
     if (F.n_mirror) {                                   // several GPUs: the region's rows of every light plane into every copy of the stack
         __syncthreads();
-        mirror_region(F, R, out_shadow, n_lights, plane_stride);
+        mirror_region<RG>(F, R, out_shadow, n_lights, plane_stride);
     }
     flush_stats(S, g_stats, rays, (unsigned)steps, pixels, exact);
 }
@@ -617,17 +622,18 @@ template <int MODE>
 __global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_reflection(const __grid_constant__ VolView V, const __grid_constant__ CUtensorMap tm_tile, const __grid_constant__ FrameView F, const __grid_constant__ ViewK K, const float* __restrict__ g_lut,
                                                     float* __restrict__ out_t, unsigned long long* __restrict__ g_stats) {
     typedef ReflGeom G;
+    typedef PassRegion RG;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BlockShared<G>& S = *reinterpret_cast<BlockShared<G>*>(smem_raw);
     load_luts(S.lut, g_lut);
-    const RegionCtx R = region_ctx(F);
-    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const RegionCtx R = region_ctx<RG>(F);
+    const int warp = threadIdx.x >> 5;
     // the box of a reflection ray: from the surface point along the mirror direction, 165 steps of up to 1.5 voxels; the roughness
     // jitter (:96) bends it by at most a tenth
     Box3 box;
     bool any = false;
-    for (int item = warp; item < REGION_ITEMS; item += nwarps) {
-        const ReflPixel a = reflection_pixel(F, K, item_pixel(F, K, R, item));
+    for (int item = warp; item < RG::ITEMS; item += NWARPS) {
+        const ReflPixel a = reflection_pixel(F, K, item_pixel<RG>(F, K, R, item));
         if (!a.lit) continue;
         any = true;
         const float3 o = a.wcp0 + a.normal, e = o + a.wd * 210.0f;
@@ -637,8 +643,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_reflection(c
     const BitTile C = block_prologue<(MODE > 0), G>(V, S, &tm_tile, any, box.lo, box.hi, box.lo, box.hi);
     unsigned rays = 0, pixels = 0, exact = 0;
     int steps = 0;
-    for (int item = next_item(S); item < REGION_ITEMS; item = next_item(S)) {
-        const PixelCtx p = item_pixel(F, K, R, item);
+    for (int item = next_item(S); item < RG::ITEMS; item = next_item(S)) {
+        const PixelCtx p = item_pixel<RG>(F, K, R, item);
         const ReflPixel a = reflection_pixel(F, K, p);
         float t = 256.0f;
         if (a.lit) {
@@ -659,7 +665,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_reflection(c
     }
     if (F.n_mirror) {
         __syncthreads();
-        mirror_region(F, R, out_t, 1, 0);
+        mirror_region<RG>(F, R, out_t, 1, 0);
     }
     flush_stats(S, g_stats, rays, (unsigned)steps, pixels, exact);
 }
@@ -711,7 +717,7 @@ int vxl_pass_ambient(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, const 
 #define VXL_AMB(MODE_)                                                                                                                  \
     do {                                                                                                                            \
         if (MODE_) VXL_CUDA(cudaFuncSetAttribute(k_ambient<MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<AmbientGeom, (MODE_ > 0)>())); \
-        k_ambient<MODE_><<<grid_regions(F), BLOCK_THREADS, smem_bytes<AmbientGeom, (MODE_ > 0)>(), ctx->stream>>>(                       \
+        k_ambient<MODE_><<<grid_regions<AmbientRegion>(F), BLOCK_THREADS, smem_bytes<AmbientGeom, (MODE_ > 0)>(), ctx->stream>>>(                       \
             vol_view(vol), *tm, F, make_viewk(view), ctx->d_luts, n_ao, out_shadow, out_ao, ctx->d_stats);                               \
     } while (0)
     if (ctx->variant == 0) VXL_AMB(0); else if (ctx->variant == 1) VXL_AMB(1); else VXL_AMB(2);
@@ -740,7 +746,7 @@ static int local_lights(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, con
 #define VXL_LL(SPOT_, MODE_)                                                                                                              \
     do {                                                                                                                              \
         if (MODE_) VXL_CUDA(cudaFuncSetAttribute(k_local_lights<SPOT_, MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<LocalGeom, (MODE_ > 0)>())); \
-        k_local_lights<SPOT_, MODE_><<<grid_regions(F), BLOCK_THREADS, smem_bytes<LocalGeom, (MODE_ > 0)>(), ctx->stream>>>(              \
+        k_local_lights<SPOT_, MODE_><<<grid_regions<PassRegion>(F), BLOCK_THREADS, smem_bytes<LocalGeom, (MODE_ > 0)>(), ctx->stream>>>(              \
             vol_view(vol), *tm, F, make_viewk(view), ctx->d_luts, (const float*)ctx->d_lights, n_lights, out_shadow, plane, ctx->d_stats); \
     } while (0)
     if (spot) { if (ctx->variant == 0) VXL_LL(true, 0); else if (ctx->variant == 1) VXL_LL(true, 1); else VXL_LL(true, 2); }
@@ -775,7 +781,7 @@ int vxl_pass_reflection(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, con
 #define VXL_RF(MODE_)                                                                                                                   \
     do {                                                                                                                            \
         if (MODE_) VXL_CUDA(cudaFuncSetAttribute(k_reflection<MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<ReflGeom, (MODE_ > 0)>())); \
-        k_reflection<MODE_><<<grid_regions(F), BLOCK_THREADS, smem_bytes<ReflGeom, (MODE_ > 0)>(), ctx->stream>>>(                       \
+        k_reflection<MODE_><<<grid_regions<PassRegion>(F), BLOCK_THREADS, smem_bytes<ReflGeom, (MODE_ > 0)>(), ctx->stream>>>(                       \
             vol_view(vol), *tm, F, make_viewk(view), ctx->d_luts, out_spec_t, ctx->d_stats);                                             \
     } while (0)
     if (ctx->variant == 0) VXL_RF(0); else if (ctx->variant == 1) VXL_RF(1); else VXL_RF(2);

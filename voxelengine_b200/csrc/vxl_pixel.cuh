@@ -61,28 +61,42 @@ __device__ __forceinline__ PixelCtx pixel_ctx(const FrameView& F, const ViewK& K
 // The block stages ONE occupancy tile for the whole region (vxl_passes.cu: block_prologue), so the staging, the LUTs and the tile
 // placement are paid once per 2048 pixels, and a warp that finishes its item takes the next one instead of waiting at the block's
 // final barrier for the slowest warp.
-#ifndef VXL_REGION_W
-#define VXL_REGION_W 32
-#endif
-#ifndef VXL_REGION_H
-#define VXL_REGION_H 16
-#endif
-constexpr int REGION_W = VXL_REGION_W, REGION_H = VXL_REGION_H;
+// Region sizes per kernel: the AO pass wants its tile tight around few pixels (32x16: one item per warp; larger regions push more
+// pixels out of the window than the shared staging saves, measured r2i), the one-ray-per-pixel passes amortise the staging over
+// 64x32 pixels (point 0.52 -> 0.42 ms, reflection 1.46 -> 1.30 ms on config 3).
 constexpr int ITEM_W = 8, ITEM_H = 4;
-constexpr int REGION_ITEMS_X = REGION_W / ITEM_W, REGION_ITEMS = REGION_ITEMS_X * (REGION_H / ITEM_H);
+template <int RW, int RH>
+struct Region {
+    static constexpr int W = RW, H = RH, ITEMS_X = RW / ITEM_W, ITEMS = (RW / ITEM_W) * (RH / ITEM_H);
+};
+#ifndef VXL_AMB_REGION_W
+#define VXL_AMB_REGION_W 32
+#endif
+#ifndef VXL_AMB_REGION_H
+#define VXL_AMB_REGION_H 16
+#endif
+#ifndef VXL_PASS_REGION_W
+#define VXL_PASS_REGION_W 64
+#endif
+#ifndef VXL_PASS_REGION_H
+#define VXL_PASS_REGION_H 32
+#endif
+typedef Region<VXL_AMB_REGION_W, VXL_AMB_REGION_H> AmbientRegion;
+typedef Region<VXL_PASS_REGION_W, VXL_PASS_REGION_H> PassRegion;
 
 struct RegionCtx { int lt, x0, y0; };               // tile of the shard, pixel offset of the region inside the tile / the row band
 
+template <typename RG>
 __device__ __forceinline__ RegionCtx region_ctx(const FrameView& F) {
-    const int rx = (F.tile_w + REGION_W - 1) / REGION_W, ry = (F.rows + REGION_H - 1) / REGION_H;
+    const int rx = (F.tile_w + RG::W - 1) / RG::W, ry = (F.rows + RG::H - 1) / RG::H;
     const int rpt = rx * ry;
     RegionCtx R;
     R.lt = blockIdx.x / rpt;
     const int r = blockIdx.x - R.lt * rpt, iy = r / rx;
-    R.x0 = (r - iy * rx) * REGION_W; R.y0 = iy * REGION_H;
+    R.x0 = (r - iy * rx) * RG::W; R.y0 = iy * RG::H;
     return R;
 }
-// pixel (x, y) of the region (0 <= x < REGION_W, 0 <= y < REGION_H)
+// pixel (x, y) of the region
 __device__ __forceinline__ PixelCtx region_pixel(const FrameView& F, const ViewK& K, const RegionCtx& R, int x, int y) {
     PixelCtx p;
     const int lx = R.x0 + x, lb = R.y0 + y, ly = F.row0 + lb;
@@ -100,24 +114,27 @@ __device__ __forceinline__ PixelCtx region_pixel(const FrameView& F, const ViewK
     return p;
 }
 // this lane's pixel of work item `item` (a warp covers 8x4 pixels: coherent rays)
+template <typename RG>
 __device__ __forceinline__ PixelCtx item_pixel(const FrameView& F, const ViewK& K, const RegionCtx& R, int item) {
-    const int lane = threadIdx.x & 31, iy = item / REGION_ITEMS_X, ix = item - iy * REGION_ITEMS_X;
+    const int lane = threadIdx.x & 31, iy = item / RG::ITEMS_X, ix = item - iy * RG::ITEMS_X;
     return region_pixel(F, K, R, ix * ITEM_W + (lane & 7), iy * ITEM_H + (lane >> 3));
 }
+template <typename RG>
 static inline unsigned grid_regions(const FrameView& F) {
-    const int rx = (F.tile_w + REGION_W - 1) / REGION_W, ry = (F.rows + REGION_H - 1) / REGION_H;
+    const int rx = (F.tile_w + RG::W - 1) / RG::W, ry = (F.rows + RG::H - 1) / RG::H;
     return (unsigned)(rx * ry * F.n_tiles);
 }
 // Several GPUs: the region's finished output rows, re-read from the rank's own planes (L2) after a block barrier, are repeated into
 // the same slot of every peer's copy of the gathered stack (peer-to-peer stores over NVLink; vxl_ctx_set_output_mirrors).  A warp
 // takes whole rows of the region: 128-byte stores -- an 8x4 item on its own would be four 32-byte packets per plane.
+template <typename RG>
 __device__ __forceinline__ void mirror_region(const FrameView& F, const RegionCtx& R, float* planes, int n_planes, size_t plane_stride) {
     if (!planes) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int gt = F.tile_first + R.lt * F.tile_stride;
     const int ty = gt / F.tiles_x, tx = gt - ty * F.tiles_x;
-    for (int y = warp; y < REGION_H; y += nwarps)
-        for (int x = lane; x < REGION_W; x += 32) {
+    for (int y = warp; y < RG::H; y += nwarps)
+        for (int x = lane; x < RG::W; x += 32) {
             const int lx = R.x0 + x, lb = R.y0 + y, ly = F.row0 + lb;
             if (!(lx < F.tile_w && lb < F.rows && ly < F.tile_h && tx * F.tile_w + lx < F.width && ty * F.tile_h + ly < F.height && R.lt < F.n_tiles)) continue;
             const size_t idx = ((size_t)R.lt * F.tile_h + ly) * F.tile_w + lx;
