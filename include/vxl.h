@@ -161,6 +161,41 @@ int vxl_ipc_close(vxl_ctx* ctx, void* dev);
 int vxl_ctx_set_output_mirrors(vxl_ctx* ctx, int n, const int64_t* byte_deltas /* HOST */);
 int vxl_ctx_set_light_plane_stride(vxl_ctx* ctx, uint64_t pixels);
 
+/* ---- the frame sharded over the GPUs of one box, driven from C (SURVEY.md 8b "vxl_ctx_create(ndev) / vxl_gather", 8e) --------
+ * One process (or thread) per GPU holds one vxl_group member; there is no reference counterpart (one GPU, one process), the call
+ * sites served are WorldRenderer.cpp:239-274.  Each member owns one allocation -- n_stacks (1 or 2) copies of the gathered tile
+ * stack of stack_bytes each plus a page of arrival flags -- that every other member maps:
+ *   vxl_group_create            allocate this member (zeroed)
+ *   vxl_group_handle            64-byte handle of the allocation, to be shipped to every peer by whatever the host has (pipe, file,
+ *                               MPI, shared memory); vxl_group_connect takes all n_ranks handles (own slot ignored) and maps the peers.
+ *                               Members inside ONE process exchange vxl_group_base pointers with vxl_group_connect_pointers instead
+ *                               (CUDA IPC cannot open a handle in the process that exported it)
+ *   vxl_group_begin_frame       point the context's output mirrors at the peers: stack (frame % n_stacks) of every copy; returns
+ *                               this member's own stack of the frame, where its pass outputs must be placed (its slot of the
+ *                               caller's [rank][plane][tile] layout).  The pass kernels then store every value into all copies
+ *   vxl_group_fence             stream-ordered: completes when every member's kernels queued before ITS fence of this frame -- and
+ *                               with them their peer stores -- have completed.  One small kernel per member: it writes the frame
+ *                               number into its slot of each peer's flag page (st.release.sys) and waits for all slots of its own
+ *                               (ld.acquire.sys).  No collective launch, no host round trip.  A peer that never arrives is reported
+ *                               by vxl_group_status after 5 s instead of hanging the GPU
+ *   vxl_group_end_frame         mirrors off
+ * With n_stacks = 2 a member may consume frame N (stream-ordered behind its fence) while the peers already store frame N + 1 into
+ * the other stack; every consumer of frame N must be queued on the context's stream before the passes of frame N + 1.
+ * vxl_group_destroy closes the peer mappings and frees the allocation: the caller makes sure (barrier on its side) that no peer
+ * still stores into it and that every peer has closed its mapping. */
+typedef struct vxl_group vxl_group;
+int vxl_group_create(vxl_ctx* ctx, int rank, int n_ranks, size_t stack_bytes, int n_stacks, vxl_group** out);
+int vxl_group_handle(vxl_group* g, vxl_ipc_handle* out /* HOST */);
+int vxl_group_connect(vxl_group* g, const vxl_ipc_handle* handles /* HOST [n_ranks] */);
+int vxl_group_base(vxl_group* g, void** out_dev);
+int vxl_group_connect_pointers(vxl_group* g, void* const* bases /* HOST [n_ranks], device pointers */);
+int vxl_group_stack(vxl_group* g, int which, void** out_dev);
+int vxl_group_begin_frame(vxl_group* g, uint64_t frame, void** out_stack_dev /* may be NULL */);
+int vxl_group_fence(vxl_group* g);
+int vxl_group_end_frame(vxl_group* g);
+int vxl_group_status(vxl_group* g, int* out_rank_plus_one /* HOST: 0 = ok */);
+int vxl_group_destroy(vxl_group* g);
+
 /* diagnostics (no reference counterpart): kernel variant 0 = plain march on the volume bytes, 1 = march
  * against the per-block occupancy-bit tile in shared memory (default; also env VXL_VARIANT), 2 = variant 1
  * that also counts the probes that had to read the volume; all produce identical results.

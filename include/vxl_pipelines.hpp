@@ -100,6 +100,31 @@ public:
     void Download(uint8_t* hostBytes) { Check(vxl_volume_download(_Volume, hostBytes), "vxl_volume_download"); }
 };
 
+// The frame sharded over the GPUs of one box (no reference counterpart: one GPU there): one ShardGroup per process / GPU.  The
+// passes of a member store their output tiles into EVERY member's copy of the gathered stack (peer stores over NVLink), Fence()
+// closes the frame with peer-written arrival flags -- no collective.  Handles travel between the processes by whatever the host
+// has (a pipe, a file, MPI): Handle() out, Connect(all handles) in.
+class ShardGroup {
+    vxl_group* _Group = nullptr;
+public:
+    ShardGroup(Context& ctx, int rank, int ranks, size_t stackBytes, int stacks = 2) {
+        Check(vxl_group_create(ctx, rank, ranks, stackBytes, stacks, &_Group), "vxl_group_create");
+    }
+    ~ShardGroup() { if (_Group) vxl_group_destroy(_Group); }
+    ShardGroup(const ShardGroup&) = delete;
+    ShardGroup& operator=(const ShardGroup&) = delete;
+    vxl_ipc_handle Handle() { vxl_ipc_handle h; Check(vxl_group_handle(_Group, &h), "vxl_group_handle"); return h; }
+    void Connect(const std::vector<vxl_ipc_handle>& handles) { Check(vxl_group_connect(_Group, handles.data()), "vxl_group_connect"); }
+    void* Base() { void* p = nullptr; Check(vxl_group_base(_Group, &p), "vxl_group_base"); return p; }
+    void ConnectPointers(const std::vector<void*>& bases) { Check(vxl_group_connect_pointers(_Group, bases.data()), "vxl_group_connect_pointers"); }
+    // mirrors on; returns this member's copy of the frame's stack (its pass outputs go to its own slot in there)
+    float* BeginFrame(uint64_t frame) { void* p = nullptr; Check(vxl_group_begin_frame(_Group, frame, &p), "vxl_group_begin_frame"); return (float*)p; }
+    void EndFrame() { Check(vxl_group_end_frame(_Group), "vxl_group_end_frame"); }
+    void Fence() { Check(vxl_group_fence(_Group), "vxl_group_fence"); }
+    void CheckArrived() { int r = 0; Check(vxl_group_status(_Group, &r), "vxl_group_status"); }
+    void Release() { if (_Group) { vxl_group_destroy(_Group); _Group = nullptr; } }
+};
+
 class LightAmbientPipeline {
 public:
     // Use (LightAmbientPipeline.h:35-52): sun shadow + AO planes.  aoRays = 1 is the reference's one-sample estimate.

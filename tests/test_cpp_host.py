@@ -89,3 +89,38 @@ def test_cpp_host_planes_equal_the_oracle(exe, oracle, gpu_ctx, tmp_path, n_poin
         want_rays += s3["rays"]; want_steps += s3["steps"]
     assert (rays, steps) == (want_rays, want_steps)
     assert warned == (70 if n_point == 64 else 0)          # DrawLight beyond MAX_POINT_LIGHTS warns and drops, like the reference
+
+
+# ---- the tile-sharded frame from C++: two processes, vxl::ShardGroup (include/vxl_pipelines.hpp over vxl_group_*) ----------------------
+GROUP_SRC = os.path.join(ROOT, "tests", "cpp", "host_group.cpp")
+
+
+@pytest.fixture(scope="module")
+def group_exe(tmp_path_factory):
+    from voxelengine_b200.build import build
+    build()
+    out = str(tmp_path_factory.mktemp("cppg") / "host_group")
+    libdir = os.path.join(ROOT, "voxelengine_b200")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"), GROUP_SRC, "-o", out,
+                        "-L" + libdir, "-lvxl", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return out
+
+
+def test_cpp_group_program_compiles_and_fails_loudly_without_a_device(group_exe):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("covered by the GPU test")
+    r = subprocess.run([group_exe, "32", "64", "32"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 3 and "vxl_ctx_create" in r.stderr, (r.returncode, r.stderr)
+
+
+@pytest.mark.gpu
+def test_cpp_two_processes_share_one_gathered_frame(group_exe):
+    """Two C++ processes, one vxl::ShardGroup member each: each runs the ambient + reflection passes over its round-robin tile shard; the
+    mirrored stores put every tile into BOTH processes' copies of the stack, the flag fence (no collective) closes each of two frames.
+    The program checks that the copies are identical, that both ranks' slots are filled and that the frames differ."""
+    import torch
+    ndev = torch.cuda.device_count()
+    r = subprocess.run([group_exe, "128", "512", "256", str(min(ndev, 2))], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.startswith("OK"), (r.returncode, r.stdout, r.stderr)

@@ -71,3 +71,62 @@ def test_mirrored_stores_fill_every_copy(gpu_ctx, oracle, rank, world):
     torch.cuda.synchronize()
     assert copies[0].any() and not copies[1].any() and not copies[2].any()
     vol.close()
+
+
+@pytest.mark.gpu
+def test_group_two_members_on_one_gpu(oracle):
+    """vxl_group (the C side of the sharded frame): two members in ONE process on one GPU, each with its own context and stream, connected by
+    plain pointers.  Each runs the passes over its tile shard into its slot of the frame's stack; the mirrors fill the other member's copy,
+    the flag fence closes the frame without a collective, two frames alternate between the two stacks -- and both copies assemble to the
+    oracle's planes."""
+    import torch
+    from voxelengine_b200 import engine as E
+    sc = U.terrain_scene(oracle)
+    sz, sy, sx = sc["volume"].shape
+    h, w = sc["gb"]["depth24"].shape
+    world = 2
+    ctxs = [E.Context(0, use_torch_stream=False) for _ in range(world)]             # own streams: the two fence kernels wait for each other
+    vols, gbs, groups = [], [], []
+    for r, c in enumerate(ctxs):
+        v = E.ShadowVoxSystem(c, (sx, sy, sz)); v.upload(sc["volume"]); vols.append(v)
+        gb = E.GeometryBuffer(c, w, h, 64, 32, rank=r, world=world)
+        gb.set_noise(sc["gb"]["noise"]); gb.set_planes(sc["gb"]["depth24"], sc["gb"]["normal"], sc["gb"]["material"])
+        gbs.append(gb)
+    padded = max(g.n_tiles for g in gbs)
+    shape = (world, 3, padded, gbs[0].tile_h, gbs[0].tile_w)
+    nbytes = int(np.prod(shape)) * 4
+    groups = [c.group_create(r, world, nbytes, 2) for r, c in enumerate(ctxs)]
+    bases = [g.base() for g in groups]
+    for g in groups:
+        g.connect_pointers(bases)
+    wsh, wao, _ = oracle.pass_ambient(sc["volume"], sc["view"], sc["gb"], 2)
+    wt, _ = oracle.pass_reflection(sc["volume"], sc["view"], sc["gb"])
+    want = np.stack([wsh, wao, wt])
+    torch.cuda.synchronize()
+    for frame in range(3):
+        stacks = []
+        for r, (c, g, gb, v) in enumerate(zip(ctxs, groups, gbs, vols)):
+            p = g.begin_frame(frame)
+            assert p == g.stack(frame % 2)
+            t = c.tensor_view(p, shape)
+            stacks.append(t)
+            n = gb.n_tiles
+            own = t[r]
+            E.LightAmbientPipeline.Get().Use(sc["view"], gb, v, n_ao=2, out_shadow=own[0, :n], out_ao=own[1, :n])
+            E.LightReflectionPipeline.Get().Use(sc["view"], gb, v, out_spec_t=own[2, :n])
+            g.end_frame()
+            g.fence()
+        for c, g in zip(ctxs, groups):
+            c.sync()
+            assert g.status() == 0
+        a, b = stacks[0].cpu().numpy(), stacks[1].cpu().numpy()
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), frame             # both members hold the same gathered stack
+        full = np.zeros((3, h, w), np.float32)
+        for r, gb in enumerate(gbs):
+            for p in range(3):
+                gb.from_tiles(a[r][p, :gb.n_tiles], full[p])
+        assert np.array_equal(full.view(np.uint32), want.view(np.uint32)), frame
+    for g in groups:
+        g.destroy()
+    for v in vols:
+        v.close()

@@ -79,46 +79,61 @@ def test_gather_world2_gloo():
 
 
 # ---- the fused gather's host logic (tiles.PeerStack) on two gloo ranks with a stand-in context -------------------------------------
-class _FakeCtx:
-    """What PeerStack needs from engine.Context, on host memory: 'device' allocations are numpy buffers kept alive in a dict, an IPC
-    handle is (pid, address), and opening rank `fail_on`'s handle fails when asked to -- the peer-mapping failure of one rank."""
+class _FakeGroup:
+    """What PeerStack needs from engine.Group (vxl_group), on host memory: the allocation is a numpy buffer, a handle is
+    (pid, address), and connecting fails when asked to -- the peer-mapping failure of one rank."""
 
+    def __init__(self, ctx, rank, world, stack_bytes, n_stacks):
+        self.ctx, self.rank, self.world, self.n_stacks, self.stack_bytes = ctx, rank, world, n_stacks, (stack_bytes + 255) & ~255
+        self.buf = np.zeros(self.stack_bytes * n_stacks + 256, np.uint8)
+        self.connected, self.destroyed, self.frames, self.fences, self.mirrors_on = False, False, [], 0, False
+
+    def handle(self):
+        return (str(os.getpid()) + ":" + str(self.buf.ctypes.data)).encode().ljust(64, b"\0")
+
+    def connect(self, handles):
+        assert len(handles) == self.world and all(len(h) == 64 for h in handles)
+        if self.ctx.fail:
+            raise RuntimeError("peer access is not supported between these two devices")
+        self.connected = True
+
+    def stack(self, which):
+        return self.buf.ctypes.data + which * self.stack_bytes
+
+    def begin_frame(self, frame):
+        self.frames.append(frame); self.mirrors_on = True
+        return self.stack(frame % self.n_stacks)
+
+    def end_frame(self):
+        self.mirrors_on = False
+
+    def fence(self):
+        self.fences += 1
+
+    def destroy(self):
+        self.destroyed = True
+
+
+class _FakeCtx:
     def __init__(self, rank, fail=False):
         import torch
         self.rank, self.fail, self.torch_device = rank, fail, torch.device("cpu")
-        self.bufs, self.mirrors, self.closed, self.freed = {}, None, [], []
+        self.groups = []
 
-    def malloc(self, n):
-        b = np.zeros(n, np.uint8)
-        self.bufs[b.ctypes.data] = b
-        return b.ctypes.data
-
-    def memset(self, p, v, n):
-        self.bufs[p][:n] = v
+    def group_create(self, rank, world, stack_bytes, n_stacks=2):
+        g = _FakeGroup(self, rank, world, stack_bytes, n_stacks)
+        self.groups.append(g)
+        return g
 
     def sync(self):
         pass
 
-    def ipc_export(self, p):
-        return (str(os.getpid()) + ":" + str(p)).encode().ljust(64, b"\0")
-
-    def ipc_open(self, h):
-        if self.fail:
-            raise RuntimeError("peer access is not supported between these two devices")
-        return 0x10000000 + int(h.rstrip(b"\0").split(b":")[1]) % 0x1000000      # 'mapped' somewhere else in this process
-
-    def ipc_close(self, p):
-        self.closed.append(p)
-
-    def free(self, p):
-        self.freed.append(p)
-
-    def set_output_mirrors(self, d):
-        self.mirrors = list(d)
-
     def tensor_view(self, p, shape, dtype="float32"):
         import torch
-        return torch.from_numpy(self.bufs[p].view(np.float32).reshape(shape))
+        g = self.groups[-1]
+        off = p - g.buf.ctypes.data
+        n = int(np.prod(shape)) * 4
+        return torch.from_numpy(g.buf[off:off + n].view(np.float32).reshape(shape))
 
 
 def _stack_worker(rank, world, port, q, failing_rank):
@@ -131,15 +146,21 @@ def _stack_worker(rank, world, port, q, failing_rank):
     ctx = _FakeCtx(rank, fail=(rank == failing_rank))
     try:
         st = PeerStack(ctx, (3, 2, 4, 4), rank, world)
-        ok = st.tensor.shape == (world, 3, 2, 4, 4) and len(st.deltas) == world - 1 and all(d == st.mapped[r] - st.base for d, r in zip(st.deltas, [r for r in range(world) if r != rank]))
-        st.enable()
-        ok = ok and ctx.mirrors == st.deltas
-        st.fence()
+        g = ctx.groups[-1]
+        ok = st.tensor.shape == (world, 3, 2, 4, 4) and g.connected and len(st.tensors) == 2
+        t0 = st.begin()
+        ok = ok and g.mirrors_on and t0.data_ptr() == st.tensors[0].data_ptr()
+        st.end(); st.fence()
+        t1 = st.begin()                                               # frames alternate between the two stacks
+        ok = ok and t1.data_ptr() == st.tensors[1].data_ptr() and st.tensor.data_ptr() == t1.data_ptr() and g.frames == [0, 1]
+        st.end(); st.fence()
+        ok = ok and st.begin().data_ptr() == t0.data_ptr()
+        st.end()
         st.close()
-        ok = ok and ctx.mirrors == [] and len(ctx.closed) == world - 1 and ctx.freed == [st.base]
+        ok = ok and not g.mirrors_on and g.fences == 2 and g.destroyed
         q.put((rank, "stack" if ok else "broken"))
     except PeerStackUnavailable:
-        q.put((rank, "unavailable" if ctx.freed and (rank == failing_rank or len(ctx.closed) == world - 1) else "leaked"))
+        q.put((rank, "unavailable" if ctx.groups and ctx.groups[-1].destroyed else "leaked"))
     dist.destroy_process_group()
 
 

@@ -21,6 +21,8 @@ SYMBOLS = [
     "vxl_debug_set_variant", "vxl_debug_fetched_probes", "vxl_volume_debug_occupancy", "vxl_debug_read_bandwidth",
     "vxl_resolve_ambient", "vxl_resolve_point", "vxl_resolve_spot", "vxl_trace_model_rays", "vxl_gbuffer_models",
     "vxl_light_taa", "vxl_resolve_reflection",
+    "vxl_group_create", "vxl_group_handle", "vxl_group_connect", "vxl_group_base", "vxl_group_connect_pointers", "vxl_group_stack",
+    "vxl_group_begin_frame", "vxl_group_fence", "vxl_group_end_frame", "vxl_group_status", "vxl_group_destroy",
     "vxl_asset_guid", "vxl_vox_file_read", "vxl_model_load_v", "vxl_pallete_file_read", "vxl_prefab_file_read", "vxl_scene_load",
     "vxl_vox_import", "vxl_vox_import_memory", "vxl_vox_scene_counts", "vxl_vox_scene_entities", "vxl_vox_scene_model",
     "vxl_vox_scene_pallete", "vxl_vox_scene_write", "vxl_vox_scene_free",
@@ -116,6 +118,10 @@ def load():
         "vxl_prefab_file_read": [C.c_char_p, vp, i32, P(C.c_int)], "vxl_scene_load": [C.c_char_p, C.c_char_p, vp, i32, P(C.c_int)],
         "vxl_ipc_export": [vp, vp, vp], "vxl_ipc_open": [vp, vp, P(vp)], "vxl_ipc_close": [vp, vp],
         "vxl_ctx_set_output_mirrors": [vp, i32, vp], "vxl_ctx_set_light_plane_stride": [vp, C.c_uint64],
+        "vxl_group_create": [vp, i32, i32, sz, i32, P(vp)], "vxl_group_handle": [vp, vp], "vxl_group_connect": [vp, vp],
+        "vxl_group_base": [vp, P(vp)], "vxl_group_connect_pointers": [vp, vp], "vxl_group_stack": [vp, i32, P(vp)],
+        "vxl_group_begin_frame": [vp, C.c_uint64, P(vp)], "vxl_group_fence": [vp], "vxl_group_end_frame": [vp],
+        "vxl_group_status": [vp, P(C.c_int)], "vxl_group_destroy": [vp],
         "vxl_vox_import": [C.c_char_p, P(vp)], "vxl_vox_import_memory": [vp, C.c_uint64, P(vp)],
         "vxl_vox_scene_counts": [vp, P(C.c_int), P(C.c_int)], "vxl_vox_scene_entities": [vp, vp, i32],
         "vxl_vox_scene_model": [vp, i32, vp, vp, vp, C.c_uint64], "vxl_vox_scene_pallete": [vp, vp],

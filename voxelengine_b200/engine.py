@@ -118,6 +118,10 @@ class Context:
         d = np.ascontiguousarray(byte_deltas, dtype=np.int64)
         check(self.lib.vxl_ctx_set_output_mirrors(self.h, len(d), _np_ptr(d) if len(d) else None), "vxl_ctx_set_output_mirrors")
 
+    def group_create(self, rank: int, world: int, stack_bytes: int, n_stacks: int = 2):
+        """This rank's member of a group of `world` processes, one per GPU (vxl_group_create): the gathered stack(s) + arrival flags."""
+        return Group(self, rank, world, stack_bytes, n_stacks)
+
     def set_light_plane_stride(self, pixels: int):
         check(self.lib.vxl_ctx_set_light_plane_stride(self.h, int(pixels)), "vxl_ctx_set_light_plane_stride")
 
@@ -138,6 +142,63 @@ class Context:
 
     def empty(self, shape, dtype):
         return _torch().empty(shape, dtype=dtype, device=self.torch_device)
+
+
+class Group:
+    """vxl_group: the frame sharded over the GPUs of one box -- output mirrors into every member's stack, a frame fence by peer-written
+    arrival flags (no collective).  The handles travel between the processes by whatever the host has (here: torch.distributed)."""
+
+    def __init__(self, ctx, rank, world, stack_bytes, n_stacks=2):
+        self.ctx, self.lib, self.rank, self.world, self.n_stacks = ctx, ctx.lib, int(rank), int(world), int(n_stacks)
+        h = C.c_void_p()
+        check(self.lib.vxl_group_create(ctx.h, self.rank, self.world, int(stack_bytes), self.n_stacks, C.byref(h)), "vxl_group_create")
+        self.h = h
+
+    def handle(self) -> bytes:
+        b = (C.c_ubyte * 64)()
+        check(self.lib.vxl_group_handle(self.h, C.byref(b)), "vxl_group_handle")
+        return bytes(b)
+
+    def connect(self, handles):
+        buf = (C.c_ubyte * (64 * self.world))()
+        for r, hd in enumerate(handles):
+            buf[64 * r:64 * r + 64] = (hd or b"").ljust(64, b"\0")[:64]
+        check(self.lib.vxl_group_connect(self.h, C.byref(buf)), "vxl_group_connect")
+
+    def base(self) -> int:
+        p = C.c_void_p()
+        check(self.lib.vxl_group_base(self.h, C.byref(p)), "vxl_group_base")
+        return int(p.value)
+
+    def connect_pointers(self, bases):
+        arr = (C.c_void_p * self.world)(*[C.c_void_p(int(b)) for b in bases])
+        check(self.lib.vxl_group_connect_pointers(self.h, C.byref(arr)), "vxl_group_connect_pointers")
+
+    def stack(self, which: int) -> int:
+        p = C.c_void_p()
+        check(self.lib.vxl_group_stack(self.h, int(which), C.byref(p)), "vxl_group_stack")
+        return int(p.value)
+
+    def begin_frame(self, frame: int) -> int:
+        p = C.c_void_p()
+        check(self.lib.vxl_group_begin_frame(self.h, int(frame), C.byref(p)), "vxl_group_begin_frame")
+        return int(p.value)
+
+    def fence(self):
+        check(self.lib.vxl_group_fence(self.h), "vxl_group_fence")
+
+    def end_frame(self):
+        check(self.lib.vxl_group_end_frame(self.h), "vxl_group_end_frame")
+
+    def status(self):
+        v = C.c_int(0)
+        check(self.lib.vxl_group_status(self.h, C.byref(v)), "vxl_group_status")
+        return int(v.value)
+
+    def destroy(self):
+        if getattr(self, "h", None):
+            self.lib.vxl_group_destroy(self.h)
+            self.h = None
 
 
 class ShadowVoxSystem:

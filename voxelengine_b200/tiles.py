@@ -79,62 +79,61 @@ class PeerStackUnavailable(RuntimeError):
 
 
 class PeerStack:
-    """The gathered tile stack (world, planes, tiles_padded, tile_h, tile_w), one copy per rank in vxl_malloc'ed memory, every
-    copy mapped into every process through CUDA IPC.  With the mirrors enabled the light-pass kernels store each output value into
-    all copies -- the rank's own slot of its own stack and, by peer-to-peer stores over NVLink, the same slot of every peer's -- so
-    the all-gather of SURVEY 8e happens inside the passes; `fence()` (one tiny stream-ordered all-reduce) closes the frame."""
+    """The gathered tile stack (world, planes, tiles_padded, tile_h, tile_w), one copy per rank, every copy mapped into every process
+    (vxl_group: CUDA IPC).  Inside begin() ... end() the light-pass kernels store each output value into all copies -- the rank's own
+    slot of its own stack and, by peer-to-peer stores over NVLink, the same slot of every peer's -- so the all-gather of SURVEY 8e
+    happens inside the passes; fence() closes the frame with peer-written arrival flags (one tiny kernel, no collective).
+    Two stacks alternate frame by frame: a rank may still read frame N (queued on the context's stream behind fence N) while its
+    peers already store frame N + 1; consumers of frame N must be queued before the passes of frame N + 1."""
 
-    def __init__(self, ctx, shape_per_rank, rank, world, group=None):
+    def __init__(self, ctx, shape_per_rank, rank, world, group=None, n_stacks=2):
         import torch
         import torch.distributed as dist
         self.ctx, self.rank, self.world, self.group = ctx, int(rank), int(world), group
         self.shape = (world,) + tuple(int(v) for v in shape_per_rank)
         self.nbytes = int(np.prod(self.shape)) * 4
-        self.base = ctx.malloc(self.nbytes)
-        ctx.memset(self.base, 0, self.nbytes)
-        ctx.sync()
+        self.n_stacks, self.frame, self.cur = int(n_stacks), 0, 0
+        self.g = ctx.group_create(self.rank, self.world, self.nbytes, self.n_stacks)
         handles = [None] * world
-        dist.all_gather_object(handles, ctx.ipc_export(self.base), group=group)
-        self.mapped, err = [self.base if r == rank else 0 for r in range(world)], None
+        dist.all_gather_object(handles, self.g.handle(), group=group)
+        err = None
         try:
-            for r in range(world):
-                if r != rank:
-                    self.mapped[r] = ctx.ipc_open(handles[r])
+            self.g.connect(handles)
         except Exception as e:                                        # no peer access between two of the GPUs, IPC disabled, ...
             err = e
         ok = torch.tensor([0.0 if err else 1.0], device=ctx.torch_device)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)        # all ranks take the same decision
         if float(ok.item()) == 0.0:
-            for r, p in enumerate(self.mapped):
-                if r != rank and p:
-                    ctx.ipc_close(p)
             dist.barrier(group=group)
-            ctx.free(self.base)
+            self.g.destroy()                                          # closes whatever it had opened, frees the allocation
             raise PeerStackUnavailable(f"peer mapping failed on at least one rank ({err})")
-        self.deltas = mirror_deltas(self.mapped, rank)
-        self.tensor = ctx.tensor_view(self.base, self.shape)          # (world, planes, tiles_padded, th, tw)
-        self._fence = torch.zeros(1, dtype=torch.float32, device=ctx.torch_device)
+        self.tensors = [ctx.tensor_view(self.g.stack(w), self.shape) for w in range(self.n_stacks)]   # (world, planes, tiles_padded, th, tw)
         dist.barrier(group=group)                                     # every copy is zeroed and mapped before anyone stores into it
 
-    def enable(self):
-        self.ctx.set_output_mirrors(self.deltas)
+    @property
+    def tensor(self):
+        """The stack of the current frame (the one begin() last pointed the mirrors at)."""
+        return self.tensors[self.cur]
 
-    def disable(self):
-        self.ctx.set_output_mirrors([])
+    def begin(self):
+        """Mirrors on, pointed at this frame's stack of every peer; returns this rank's own copy of that stack."""
+        self.cur = self.frame % self.n_stacks
+        self.g.begin_frame(self.frame)
+        return self.tensors[self.cur]
+
+    def end(self):
+        self.g.end_frame()
 
     def fence(self):
-        """Stream-ordered: returns (on the stream) once every rank's passes, and with them their peer stores, have completed."""
-        import torch.distributed as dist
-        dist.all_reduce(self._fence, group=self.group)
+        """Stream-ordered: returns (on the stream) once every rank's passes of this frame, and with them their peer stores, have
+        completed; the next begin() moves on to the other stack."""
+        self.g.fence()
+        self.frame += 1
 
     def close(self):
         import torch.distributed as dist
-        self.disable()
         self.ctx.sync()
         dist.barrier(group=self.group)                                # nobody is still storing into a copy that is about to go
-        self.tensor = None
-        for r, p in enumerate(self.mapped):
-            if r != self.rank:
-                self.ctx.ipc_close(p)
-        dist.barrier(group=self.group)                                # an exported allocation is freed only after every importer has closed it
-        self.ctx.free(self.base)
+        self.tensors = None
+        self.g.destroy()                                              # closes the peer mappings, then frees the allocation
+        dist.barrier(group=self.group)

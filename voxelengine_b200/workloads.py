@@ -77,13 +77,16 @@ class Workload:
                 gather = "nccl"                                   # every rank reaches the same decision (PeerStack agrees on it collectively)
         self.gather_mode = gather if world > 1 else "none"
         if self.stack is not None:
-            self.out = self.stack.tensor[rank]                # this rank's slot of its own copy; the mirrors fill the peers' copies
-            self.gathered_main, self.gathered_point = self.stack.tensor[:, :3], self.stack.tensor[:, 3:]
+            self._bind_stack(self.stack.tensor)
         else:
             self.out = torch.zeros((self.n_planes, self.tiles_padded, self.gb.tile_h, self.gb.tile_w), dtype=torch.float32,
                                    device=self.ctx.torch_device)
         self._side = torch.cuda.Stream(device=self.ctx.torch_device) if world > 1 else None
         self.ctx.sync()
+
+    def _bind_stack(self, t):
+        self.out = t[self.rank]                                   # this rank's slot of its own copy; the mirrors fill the peers' copies
+        self.gathered_main, self.gathered_point = t[:, :3], t[:, 3:]
 
     # -- scene -------------------------------------------------------------------------------------
     def _house_view(self, W, H, frame):
@@ -152,12 +155,15 @@ class Workload:
         if self.stack is not None:
             # fused gather: the passes write this rank's tiles into every rank's stack (peer-to-peer stores); one fence ends the frame.
             # Mirrors and the padded plane stride are on only here, where every output pointer lies inside the stack.
-            self.stack.enable()
+            # Frames alternate between two stacks (tiles.PeerStack): whoever consumes this frame's stack queues that on the context's
+            # stream before the next step().
+            self._bind_stack(self.stack.begin())
+            o = self.out
             self.ctx.set_light_plane_stride(self.tiles_padded * self.gb.tile_h * self.gb.tile_w)
             try:
                 self._passes(o, n)
             finally:
-                self.stack.disable()
+                self.stack.end()
                 self.ctx.set_light_plane_stride(0)
             if gather:
                 self.stack.fence()
