@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""Summarise an ncu report into profiles/<tag>_summary.md (+ dram_traffic.json consumed by bench.py).
-usage: python profiles/summarize.py gpurun_out/prof_<tag>.ncu-rep <tag> [launches.csv]"""
+"""Summarise an ncu report into profiles/<tag>_summary.md (+ dram_traffic.json / kernel_counters.json consumed by bench.py).
+usage: python profiles/summarize.py gpurun_out/prof_<tag>.ncu-rep <tag> [launches.csv] [--config C] [--gpus N]
+dram_traffic.json is keyed by the capture's workload, {"cfg<C>_n<N>": {kernel: bytes per launch}}: bench.py quotes `roofline.traffic`
+only on a line of the same config at the same GPU count.  kernel_counters.json holds the config-3, one-GPU counters."""
 import csv
 import io
 import json
@@ -35,6 +37,17 @@ KEYS = [
 
 
 def main():
+    argv = list(sys.argv)
+    cfg, gpus = 3, 1
+    for flag in ("--config", "--gpus"):
+        if flag in argv:
+            i = argv.index(flag)
+            if flag == "--config":
+                cfg = int(argv[i + 1])
+            else:
+                gpus = int(argv[i + 1])
+            del argv[i:i + 2]
+    sys.argv = argv
     rep, tag = sys.argv[1], sys.argv[2]
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -81,8 +94,17 @@ def main():
         for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             out.append(f"| {k} | {a[0]} | {a[1]:.3f} | {100 * a[1] / tot:.1f}% |")
     open(os.path.join(here, f"{tag}_summary.md"), "w").write("\n".join(out) + "\n")
-    json.dump(traffic, open(os.path.join(here, "dram_traffic.json"), "w"), indent=1)
-    json.dump(counters, open(os.path.join(here, "kernel_counters.json"), "w"), indent=1)
+    tp = os.path.join(here, "dram_traffic.json")
+    try:
+        all_traffic = json.load(open(tp))
+        if not all(isinstance(v, dict) for v in all_traffic.values()):
+            all_traffic = {}
+    except Exception:
+        all_traffic = {}
+    all_traffic[f"cfg{cfg}_n{gpus}"] = traffic
+    json.dump(all_traffic, open(tp, "w"), indent=1, sort_keys=True)
+    if cfg == 3 and gpus == 1:
+        json.dump(counters, open(os.path.join(here, "kernel_counters.json"), "w"), indent=1)
     print("\n".join(out))
 
 

@@ -88,3 +88,124 @@ def test_config3_eight_shards_equal_whole_frame(wl3):
             w.close()
     assert np.array_equal(full.view(np.uint32), whole.view(np.uint32))
     assert rays == st["rays"] and steps == st["steps"]
+
+
+# ---- the other BASELINE.json configs at their own sizes -----------------------------------------------------------------------------
+def _host_gb(wl):
+    gbh = {k: getattr(wl.gb, k).cpu().numpy().view(np.uint32)[0] for k in ("depth24", "normal", "material")}
+    gbh["noise"] = wl.gb.noise.cpu().numpy().view(np.uint32)
+    return gbh
+
+
+def _assert_planes(names_got_want, sel=slice(None)):
+    for name, g, w in names_got_want:
+        a, b = g[sel].view(np.uint32), w[sel].view(np.uint32)
+        assert np.array_equal(a, b), f"{name}: {(a != b).sum()} of {a.size} pixels differ from the oracle"
+
+
+def test_config2_full_frame_equals_oracle_and_spot_lights_at_1080p(gpu_ctx, oracle):
+    """Config 2 (512^3-voxel terrain, 1920x1080, sun + 8 AO): every row against the oracle.  On the same frame: three spot lights
+    (LightSpot.frag:73-117: SuperSparse rays, dist = 10 |L|) -- the spot variant of k_local_lights above the 160x90 of the small tests."""
+    import os
+    import torch
+    from voxelengine_b200 import engine as E, scenes as S
+    from voxelengine_b200.workloads import Workload
+    wl = Workload(2)
+    try:
+        got, st = _frame(wl)
+        W, H = wl.res
+        assert (W, H) == (1920, 1080) and wl.texels == (256, 256, 256) and wl.n_ao == 8
+        oracle.set_num_threads(len(os.sched_getaffinity(0)))
+        gbh = _host_gb(wl)
+        sh, ao, s1 = oracle.pass_ambient(wl.host_volume, wl.view, gbh, wl.n_ao)
+        _assert_planes([("shadow", got[0], sh), ("ao", got[1], ao)])
+        assert st["rays"] == s1["rays"] and st["steps"] == s1["steps"] and st["rays"] > 9_000_000
+        ext = 2 * wl.texels[0] * 0.1
+        spots = S.spot_lights([(ext * 0.3, ext * 0.62, ext * 0.4), (ext * 0.7, ext * 0.6, ext * 0.6), (ext * 0.5, ext * 0.7, ext * 0.5)], ext * 0.45,
+                              [(0.2, -1.0, 0.1), (-0.3, -1.0, 0.2), (0.0, -1.0, 0.0)], 0.9)
+        out = wl.ctx.empty((len(spots),) + wl.gb.shape, torch.float32)
+        wl.ctx.stats_reset()
+        E.LightSpotPipeline.Get().Use(wl.view, wl.gb, wl.vol, lambda p: [p.DrawLight(l["Position"], l["Range"], l["Color"], l["Attenuation"], l["Direction"], l["Angle"], l["AngleAttenuation"]) for l in spots],
+                                      out_shadow=out)
+        torch.cuda.synchronize()
+        st2 = wl.ctx.stats()
+        wsp, s2 = oracle.pass_spot(wl.host_volume, wl.view, gbh, spots)
+        g = out.cpu().numpy()[:, 0, :H, :W]
+        _assert_planes([(f"spot{i}", g[i], wsp[i]) for i in range(len(spots))])
+        assert st2["rays"] == s2["rays"] and st2["steps"] == s2["steps"] and s2["rays"] > 1_000_000 and 0.02 < float((g == 0).mean()) < 0.98
+    finally:
+        wl.close()
+
+
+def test_config5_every_8th_row_equals_oracle(gpu_ctx, oracle):
+    """Config 5 (2048^3-voxel world, 7680x4320: BASELINE.json configs[4], the one the multi-GPU split is specified on): the whole 8K frame
+    on one GPU, the oracle on every 8th row (74 M rays), all seven planes bit for bit."""
+    import os
+    import torch
+    free_dev, _ = torch.cuda.mem_get_info()
+    try:
+        free_host = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+    except (ValueError, OSError):
+        free_host = 1 << 40
+    if free_dev < (8 << 30) or free_host < (8 << 30):
+        pytest.skip("needs 8 GB of free device and host memory")
+    from voxelengine_b200.workloads import Workload
+    wl = Workload(5)
+    try:
+        got, st = _frame(wl)
+        W, H = wl.res
+        assert (W, H) == (7680, 4320) and wl.texels == (1024, 1024, 1024)
+        oracle.set_num_threads(len(os.sched_getaffinity(0)))
+        gbh = _host_gb(wl)
+        rows = (0, H, 8)
+        sel = slice(*rows)
+        sh, ao, s1 = oracle.pass_ambient(wl.host_volume, wl.view, gbh, wl.n_ao, rows=rows)
+        pt, s2 = oracle.pass_point(wl.host_volume, wl.view, gbh, wl.lights, rows=rows)
+        sp, s3 = oracle.pass_reflection(wl.host_volume, wl.view, gbh, rows=rows)
+        assert s1["rays"] + s2["rays"] + s3["rays"] > 60_000_000
+        _assert_planes([("shadow", got[0], sh), ("ao", got[1], ao), ("spec_t", got[2], sp)] + [(f"point{i}", got[3 + i], pt[i]) for i in range(wl.n_point)], sel)
+        assert 0.05 < (got[0][sel] == 0).mean() < 0.95 and (got[2][sel] < 256).any()
+    finally:
+        wl.close()
+
+
+def test_config4_sixty_frames_of_revoxelisation(gpu_ctx, oracle):
+    """Config 4 as the loop it is: 60 frames of 1000 moving entities re-voxelised into the 1024^3-voxel volume (ShadowVoxSystem.cpp:116-201:
+    clear at the previous transform, set at the current one, sequentially over the entities) + occupancy rebuild + 1080p sun shadow / AO.
+    The oracle replays every frame's OnUpdate on the host; every 10th frame the device volume must equal it byte for byte, the rebuilt
+    4-voxel occupancy level must equal the block maxima of those bytes, and the shadow / AO planes must equal the oracle's passes."""
+    import os
+    import torch
+    from voxelengine_b200 import scenes as S
+    from voxelengine_b200.workloads import Workload
+    wl = Workload(4)
+    try:
+        oracle.set_num_threads(len(os.sched_getaffinity(0)))
+        host = wl.vol.download()                                       # after the first OnUpdate (prev = identity, covered by the small tests)
+        model = S.shell_cube_model(16)
+        ents = wl.entities.copy()
+        ents["model"] = 0
+        n = len(wl._frames)
+        tri = lambda t: (n - 1) - abs((t % (2 * n - 2)) - (n - 1))
+        gbh = None
+        checked = 0
+        for t in range(1, 61):
+            got, st = _frame(wl)                                        # advance() + the passes
+            ents["prev"], ents["cur"] = wl._frames[tri(t - 1)], wl._frames[tri(t)]
+            oracle.voxelize(host, [model], ents)
+            if t % 10:
+                continue
+            dev = wl.vol.download()
+            assert np.array_equal(dev, host), f"frame {t}: {(dev != host).sum()} volume bytes differ from the sequential reference"
+            occ = wl.vol.occupancy(2)                                   # 4-voxel cells = 2x2x2 texels
+            sz, sy, sx = host.shape
+            want_occ = (host.reshape(sz // 2, 2, sy // 2, 2, sx // 2, 2).max(axis=(1, 3, 5)) != 0).astype(np.uint8)
+            assert np.array_equal(occ, want_occ), f"frame {t}: rebuilt occupancy level differs from the volume"
+            gbh = gbh or _host_gb(wl)
+            sh, ao, s1 = oracle.pass_ambient(host, wl.view, gbh, wl.n_ao)
+            _assert_planes([(f"shadow@{t}", got[0], sh), (f"ao@{t}", got[1], ao)])
+            assert st["rays"] == s1["rays"] and st["steps"] == s1["steps"]
+            checked += 1
+        assert checked == 6
+    finally:
+        wl.close()
