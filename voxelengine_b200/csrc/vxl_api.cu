@@ -202,6 +202,7 @@ int vxl_ctx_destroy(vxl_ctx* c) {
     cudaFree(c->d_models); cudaFree(c->d_draws); cudaFree(c->d_hkeys); cudaFree(c->d_hvals); cudaFree(c->d_ents); cudaFree(c->d_aabb);
     cudaFree(c->h_planes); cudaFree(c->h_out); cudaFree(c->h_noise);
     if (c->s_h2d) { cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h); }
+    if (c->s_side[0]) { cudaStreamDestroy(c->s_side[0]); cudaStreamDestroy(c->s_side[1]); }
     for (auto& e : c->ev) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -376,13 +377,13 @@ int vxl_lighting(vxl_ctx* c, vxl_volume* vol, const vxl_lighting_host_args* a) {
     const bool want_rf = a->out_spec_t != nullptr;
     VXL_CUDA(cudaSetDevice(c->device));
     if (vol->dirty) { if (int e = vxl_volume_build_occupancy(vol)) return e; }       // once, before the fork
-    if (!c->s_h2d) {
-        VXL_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
-        VXL_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    if (!c->s_side[0]) {
+        VXL_CUDA(cudaStreamCreateWithFlags(&c->s_side[0], cudaStreamNonBlocking));
+        VXL_CUDA(cudaStreamCreateWithFlags(&c->s_side[1], cudaStreamNonBlocking));
     }
     while (c->ev.size() < 3) { cudaEvent_t e; VXL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->ev.push_back(e); }
     cudaEvent_t* ev = c->ev.data();
-    cudaStream_t main = c->stream, side[2] = {c->s_h2d, c->s_d2h};
+    cudaStream_t main = c->stream, side[2] = {c->s_side[0], c->s_side[1]};
     struct Restore { vxl_ctx* c; cudaStream_t s; ~Restore() { c->stream = s; } } restore{c, main};
     VXL_CUDA(cudaEventRecord(ev[0], main));
     int rc = VXL_OK;
@@ -430,18 +431,22 @@ static int lighting_host_impl(vxl_ctx* c, vxl_volume* vol, const vxl_lighting_ho
         VXL_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
         VXL_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
     }
+    if (!c->s_side[0]) {
+        VXL_CUDA(cudaStreamCreateWithFlags(&c->s_side[0], cudaStreamNonBlocking));
+        VXL_CUDA(cudaStreamCreateWithFlags(&c->s_side[1], cudaStreamNonBlocking));
+    }
     // The host drop-in writes to its own staging planes (no mirrored stores, default plane stride) and walks the frame in row
     // bands.  Whatever path leaves this function -- including a CUDA error in the middle of the band loop -- the context gets its
     // mirror / stride / band state back and the two copy streams are joined to the context's stream again.
     struct Restore {
-        vxl_ctx* c; int n; size_t st; cudaEvent_t join[2] = {nullptr, nullptr};
+        vxl_ctx* c; int n; size_t st; cudaStream_t main; cudaEvent_t join[4] = {nullptr, nullptr, nullptr, nullptr};
         ~Restore() {
-            c->n_mirror = n; c->light_plane_stride = st; c->band_row0 = 0; c->band_rows = 0;
-            cudaStream_t side[2] = {c->s_h2d, c->s_d2h};
-            for (int i = 0; i < 2; ++i)
-                if (join[i] && cudaEventRecord(join[i], side[i]) == cudaSuccess) cudaStreamWaitEvent(c->stream, join[i], 0);
+            c->n_mirror = n; c->light_plane_stride = st; c->band_row0 = 0; c->band_rows = 0; c->stream = main;
+            cudaStream_t side[4] = {c->s_h2d, c->s_d2h, c->s_side[0], c->s_side[1]};
+            for (int i = 0; i < 4; ++i)
+                if (join[i] && cudaEventRecord(join[i], side[i]) == cudaSuccess) cudaStreamWaitEvent(main, join[i], 0);
         }
-    } restore{c, c->n_mirror, c->light_plane_stride};
+    } restore{c, c->n_mirror, c->light_plane_stride, c->stream};
     c->n_mirror = 0; c->light_plane_stride = 0;
     if (int e = ensure((void**)&c->h_planes, &c->h_planes_bytes, px * 4 * 3)) return e;
     const size_t n_out = 3 + (size_t)a->n_point + (size_t)a->n_spot;
@@ -450,13 +455,14 @@ static int lighting_host_impl(vxl_ctx* c, vxl_volume* vol, const vxl_lighting_ho
     if (int e = ensure((void**)&c->h_out, &c->h_out_bytes, px * 4 * n_out + (packed ? px * (size_t)(mask_bytes + 1) : 0))) return e;
     if (!c->h_noise) VXL_CUDA(cudaMalloc(&c->h_noise, 512 * 512 * 4));
     uint32_t* d_depth = c->h_planes; uint32_t* d_normal = d_depth + px; uint32_t* d_mat = d_normal + px;
-    // Three streams: uploads, passes (the context's stream), read-backs; the frame goes through in NB row bands (rows of
-    // every tile of the shard).  PCIe is full duplex and the copy engines run beside the SMs, so band b+1 uploads and band
-    // b-1 reads back while band b is in the passes; within a band the largest output goes first.
+    // Streams: uploads, read-backs, and three for the passes (the context's stream for the ambient pass, two side streams for the
+    // local-light and reflection passes: the kernels are independent, so one's tail overlaps another's head).  The frame goes
+    // through in NB row bands (rows of every tile of the shard).  PCIe is full duplex and the copy engines run beside the SMs,
+    // so band b+1 uploads and band b-1 reads back while band b is in the passes.
     int NB = a->frame.tile_h >= 256 ? 4 : 1;
     if (const char* nb = getenv("VXL_HOST_BANDS")) NB = std::max(1, std::min(64, atoi(nb)));   // tuning knob
     const int band_h = ((a->frame.tile_h + NB - 1) / NB + 15) / 16 * 16;          // whole 16-row thread blocks
-    const size_t n_ev = 4 + (size_t)NB * 5;
+    const size_t n_ev = 6 + (size_t)NB * 6;
     while (c->ev.size() < n_ev) { cudaEvent_t e; VXL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->ev.push_back(e); }
     cudaEvent_t* ev = c->ev.data();
     const size_t tile_px = (size_t)a->frame.tile_w * a->frame.tile_h;
@@ -470,7 +476,10 @@ static int lighting_host_impl(vxl_ctx* c, vxl_volume* vol, const vxl_lighting_ho
     VXL_CUDA(cudaEventRecord(ev[0], c->stream));                          // order behind whatever the caller queued (voxelise, ...)
     VXL_CUDA(cudaStreamWaitEvent(c->s_h2d, ev[0], 0));
     VXL_CUDA(cudaStreamWaitEvent(c->s_d2h, ev[0], 0));
-    restore.join[0] = ev[2]; restore.join[1] = ev[3];                     // from here on the side streams carry work
+    VXL_CUDA(cudaStreamWaitEvent(c->s_side[0], ev[0], 0));
+    VXL_CUDA(cudaStreamWaitEvent(c->s_side[1], ev[0], 0));
+    restore.join[0] = ev[2]; restore.join[1] = ev[3]; restore.join[2] = ev[4]; restore.join[3] = ev[5];   // from here on the side streams carry work
+    cudaStream_t const main = c->stream, sl = c->s_side[0], sr = c->s_side[1];
     VXL_CUDA(cudaMemcpyAsync(c->h_noise, a->frame.noise, 512 * 512 * 4, cudaMemcpyHostToDevice, c->s_h2d));
     vxl_frame fd = a->frame;
     fd.depth24 = d_depth; fd.normal = d_normal; fd.material = d_mat; fd.noise = c->h_noise;
@@ -480,56 +489,68 @@ static int lighting_host_impl(vxl_ctx* c, vxl_volume* vol, const vxl_lighting_ho
     for (int b = 0; b < NB; ++b) {
         const int r0 = b * band_h, rows = std::min(band_h, a->frame.tile_h - r0);
         if (rows <= 0) break;
-        cudaEvent_t* eb = ev + 4 + (size_t)b * 5;
+        cudaEvent_t* eb = ev + 6 + (size_t)b * 6;
         VXL_CUDA(copy_band(d_depth, a->frame.depth24, r0, rows, 4, cudaMemcpyHostToDevice, c->s_h2d));
         VXL_CUDA(copy_band(d_normal, a->frame.normal, r0, rows, 4, cudaMemcpyHostToDevice, c->s_h2d));
         if (want_rf) VXL_CUDA(copy_band(d_mat, a->frame.material, r0, rows, 4, cudaMemcpyHostToDevice, c->s_h2d));
         VXL_CUDA(cudaEventRecord(eb[0], c->s_h2d));
-        VXL_CUDA(cudaStreamWaitEvent(c->stream, eb[0], 0));
+        VXL_CUDA(cudaStreamWaitEvent(main, eb[0], 0));
         c->band_row0 = r0; c->band_rows = rows;
-        if (want_pt) {
-            if (int e = vxl_pass_point(c, vol, a->view, &fd, a->point, a->n_point, o_pt)) return e;
-            if (!packed) {
-                VXL_CUDA(cudaEventRecord(eb[1], c->stream)); VXL_CUDA(cudaStreamWaitEvent(c->s_d2h, eb[1], 0));
-                for (int l = 0; l < a->n_point; ++l) VXL_CUDA(copy_band(a->out_point_shadow + px * (size_t)l, o_pt + px * (size_t)l, r0, rows, 4, cudaMemcpyDeviceToHost, c->s_d2h));
-            }
-        }
-        if (want_sp) {
-            if (int e = vxl_pass_spot(c, vol, a->view, &fd, a->spot, a->n_spot, o_sp)) return e;
-            if (!packed) {
-                VXL_CUDA(cudaEventRecord(eb[2], c->stream)); VXL_CUDA(cudaStreamWaitEvent(c->s_d2h, eb[2], 0));
-                for (int l = 0; l < a->n_spot; ++l) VXL_CUDA(copy_band(a->out_spot_shadow + px * (size_t)l, o_sp + px * (size_t)l, r0, rows, 4, cudaMemcpyDeviceToHost, c->s_d2h));
-            }
-        }
-        if (want_amb) {
+        if (want_amb) {                                                   // first in the queue: its blocks fill the machine first
             if (int e = vxl_pass_ambient(c, vol, a->view, &fd, a->n_ao, want_sun ? o_shadow : nullptr, want_ao ? o_ao : nullptr)) return e;
-            VXL_CUDA(cudaEventRecord(eb[3], c->stream)); VXL_CUDA(cudaStreamWaitEvent(c->s_d2h, eb[3], 0));
+            VXL_CUDA(cudaEventRecord(eb[3], main)); VXL_CUDA(cudaStreamWaitEvent(c->s_d2h, eb[3], 0));
             if (!packed && a->out_shadow) VXL_CUDA(copy_band(a->out_shadow, o_shadow, r0, rows, 4, cudaMemcpyDeviceToHost, c->s_d2h));
             if (want_ao) VXL_CUDA(copy_band(packed ? packed->ao : a->out_ao, o_ao, r0, rows, 4, cudaMemcpyDeviceToHost, c->s_d2h));
         }
-        if (want_rf) {
-            if (int e = vxl_pass_reflection(c, vol, a->view, &fd, o_spec)) return e;
-            if (!packed) {
-                VXL_CUDA(cudaEventRecord(eb[4], c->stream)); VXL_CUDA(cudaStreamWaitEvent(c->s_d2h, eb[4], 0));
-                VXL_CUDA(copy_band(a->out_spec_t, o_spec, r0, rows, 4, cudaMemcpyDeviceToHost, c->s_d2h));
+        if (want_pt || want_sp) {
+            VXL_CUDA(cudaStreamWaitEvent(sl, eb[0], 0));
+            c->stream = sl;                                               // point then spot: they share the light staging buffer
+            if (want_pt) {
+                if (int e = vxl_pass_point(c, vol, a->view, &fd, a->point, a->n_point, o_pt)) return e;
+                if (!packed) {
+                    VXL_CUDA(cudaEventRecord(eb[1], sl)); VXL_CUDA(cudaStreamWaitEvent(c->s_d2h, eb[1], 0));
+                    for (int l = 0; l < a->n_point; ++l) VXL_CUDA(copy_band(a->out_point_shadow + px * (size_t)l, o_pt + px * (size_t)l, r0, rows, 4, cudaMemcpyDeviceToHost, c->s_d2h));
+                }
             }
+            if (want_sp) {
+                if (int e = vxl_pass_spot(c, vol, a->view, &fd, a->spot, a->n_spot, o_sp)) return e;
+                if (!packed) {
+                    VXL_CUDA(cudaEventRecord(eb[2], sl)); VXL_CUDA(cudaStreamWaitEvent(c->s_d2h, eb[2], 0));
+                    for (int l = 0; l < a->n_spot; ++l) VXL_CUDA(copy_band(a->out_spot_shadow + px * (size_t)l, o_sp + px * (size_t)l, r0, rows, 4, cudaMemcpyDeviceToHost, c->s_d2h));
+                }
+            }
+            c->stream = main;
+            if (packed) { VXL_CUDA(cudaEventRecord(eb[1], sl)); VXL_CUDA(cudaStreamWaitEvent(main, eb[1], 0)); }
         }
-        if (packed && (want_mask || want_rf)) {
+        if (want_rf) {
+            VXL_CUDA(cudaStreamWaitEvent(sr, eb[0], 0));
+            c->stream = sr;
+            const int e = vxl_pass_reflection(c, vol, a->view, &fd, o_spec);
+            c->stream = main;
+            if (e) return e;
+            if (!packed) {
+                VXL_CUDA(cudaEventRecord(eb[4], sr)); VXL_CUDA(cudaStreamWaitEvent(c->s_d2h, eb[4], 0));
+                VXL_CUDA(copy_band(a->out_spec_t, o_spec, r0, rows, 4, cudaMemcpyDeviceToHost, c->s_d2h));
+            } else { VXL_CUDA(cudaEventRecord(eb[4], sr)); VXL_CUDA(cudaStreamWaitEvent(main, eb[4], 0)); }
+        }
+        if (packed && (want_mask || want_rf)) {                           // behind all three pass streams (joined into `main` above)
             const size_t n = (size_t)rows * a->frame.tile_w * (size_t)nt;
-            k_pack_planes<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(want_sun ? o_shadow : nullptr, o_pt, want_pt ? a->n_point : 0, o_sp, want_sp ? a->n_spot : 0, px,
-                                                                              o_spec, want_mask ? o_mask : nullptr, mask_bytes, want_rf ? o_code : nullptr,
-                                                                              a->frame.tile_w, a->frame.tile_h, r0, rows, nt);
+            k_pack_planes<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(want_sun ? o_shadow : nullptr, o_pt, want_pt ? a->n_point : 0, o_sp, want_sp ? a->n_spot : 0, px,
+                                                                         o_spec, want_mask ? o_mask : nullptr, mask_bytes, want_rf ? o_code : nullptr,
+                                                                         a->frame.tile_w, a->frame.tile_h, r0, rows, nt);
             VXL_LAUNCH_CHECK(c);
-            VXL_CUDA(cudaEventRecord(eb[4], c->stream)); VXL_CUDA(cudaStreamWaitEvent(c->s_d2h, eb[4], 0));
+            VXL_CUDA(cudaEventRecord(eb[5], main)); VXL_CUDA(cudaStreamWaitEvent(c->s_d2h, eb[5], 0));
             if (want_mask) VXL_CUDA(copy_band(packed->shadow_mask, o_mask, r0, rows, (size_t)mask_bytes, cudaMemcpyDeviceToHost, c->s_d2h));
             if (want_rf) VXL_CUDA(copy_band(packed->spec_code, o_code, r0, rows, 1, cudaMemcpyDeviceToHost, c->s_d2h));
         }
     }
     c->band_row0 = 0; c->band_rows = 0;
     VXL_CUDA(cudaEventRecord(ev[1], c->s_d2h));
-    VXL_CUDA(cudaStreamWaitEvent(c->stream, ev[1], 0));                   // the context's stream stays the single point of order
+    VXL_CUDA(cudaStreamWaitEvent(main, ev[1], 0));                        // the context's stream stays the single point of order
     VXL_CUDA(cudaStreamSynchronize(c->s_h2d));
-    VXL_CUDA(cudaStreamSynchronize(c->stream));
+    VXL_CUDA(cudaStreamSynchronize(sl));
+    VXL_CUDA(cudaStreamSynchronize(sr));
+    VXL_CUDA(cudaStreamSynchronize(main));
     if (cudaError_t e = cudaGetLastError()) return cuda_fail(e, "vxl_lighting_host copies");
     return VXL_OK;
 }

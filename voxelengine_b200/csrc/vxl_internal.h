@@ -85,6 +85,7 @@ struct vxl_ctx {
     size_t h_out_bytes = 0;
     uint32_t* h_noise = nullptr;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // copy streams of vxl_lighting_host (uploads / read-backs overlap the passes)
+    cudaStream_t s_side[2] = {nullptr, nullptr};     // side streams of vxl_lighting / vxl_lighting_host: the local-light and reflection passes beside the ambient pass
     std::vector<cudaEvent_t> ev;
     int band_row0 = 0, band_rows = 0;                // > 0 rows: the pass entry points cover this row band of every tile only
     int n_mirror = 0;                                // vxl_ctx_set_output_mirrors
