@@ -332,6 +332,52 @@ def test_lighting_host_matches_passes(gpu_ctx, oracle, terrain):
     vol.close()
 
 
+@pytest.mark.parametrize("rank,world", [(0, 2), (1, 3)])
+def test_lighting_host_on_a_tile_shard(gpu_ctx, oracle, terrain, rank, world):
+    """vxl_lighting_host / _packed on one rank's shard of a sharded frame (16x16 tiles, round-robin): many small tiles, so the call
+    walks the shard in bands of TILES (uploads, the three pass kernels and read-backs of consecutive bands overlap).  The planes,
+    scattered back into the frame, equal the oracle's on this rank's tiles -- float and packed output alike."""
+    import torch
+    E = _eng()
+    from voxelengine_b200.tiles import TileLayout
+    sc = terrain
+    lights = _test_lights(sc)
+    sz, sy, sx = sc["volume"].shape
+    vol = E.ShadowVoxSystem(gpu_ctx, (sx, sy, sz))
+    vol.upload(sc["volume"])
+    h, w = sc["gb"]["depth24"].shape
+    L = TileLayout(w, h, 16, 16, rank=rank, world=world)
+    n = L.n_tiles
+    assert n >= 8
+    planes = {k: torch.from_numpy(np.ascontiguousarray(L.to_tiles(sc["gb"][k])).view(np.int32)).pin_memory() for k in ("depth24", "normal", "material")}
+    planes["noise"] = torch.from_numpy(sc["gb"]["noise"].view(np.int32)).pin_memory()
+    desc = dict(width=w, height=h, tile_w=16, tile_h=16, tile_first=rank, tile_stride=world, n_tiles=n)
+    f32 = lambda *shape: torch.full(shape, -7.0, dtype=torch.float32).pin_memory()
+    outs = dict(shadow=f32(n, 16, 16), ao=f32(n, 16, 16), point_shadow=f32(len(lights), n, 16, 16), spec_t=f32(n, 16, 16))
+    E.lighting_host(gpu_ctx, vol, sc["view"], desc, planes, outs, n_ao=3, point=lights)
+    wsh, wao, _ = oracle.pass_ambient(sc["volume"], sc["view"], sc["gb"], 3)
+    wpt, _ = oracle.pass_point(sc["volume"], sc["view"], sc["gb"], lights)
+    wt, _ = oracle.pass_reflection(sc["volume"], sc["view"], sc["gb"])
+    bits = lambda a: np.ascontiguousarray(a).reshape(-1).view(np.uint32)
+    for name, got, want in [("shadow", outs["shadow"].numpy(), wsh), ("ao", outs["ao"].numpy(), wao), ("spec_t", outs["spec_t"].numpy(), wt)] + [
+            (f"point{i}", outs["point_shadow"].numpy()[i], wpt[i]) for i in range(len(lights))]:
+        ref = L.to_tiles(want)
+        # pixels of edge tiles beyond the frame are not written
+        mask = L.to_tiles(np.ones((h, w), np.uint8)).astype(bool)
+        assert np.array_equal(bits(got[mask]), bits(ref[mask])), name
+    mb = E.mask_bytes(len(lights), 0)
+    pk = dict(shadow_mask=torch.zeros((n, 16, 16, mb), dtype=torch.uint8).pin_memory(), spec_code=torch.zeros((n, 16, 16), dtype=torch.uint8).pin_memory(), ao=f32(n, 16, 16))
+    E.lighting_host(gpu_ctx, vol, sc["view"], desc, planes, {"packed": pk}, n_ao=3, point=lights)
+    un = E.unpack_planes(pk["shadow_mask"].numpy(), pk["spec_code"].numpy(), len(lights), 0)
+    mask = L.to_tiles(np.ones((h, w), np.uint8)).astype(bool)
+    assert np.array_equal(bits(pk["ao"].numpy()[mask]), bits(outs["ao"].numpy()[mask]))
+    assert np.array_equal(bits(un["shadow"].reshape(n, 16, 16)[mask]), bits(outs["shadow"].numpy()[mask]))
+    assert np.array_equal(bits(un["spec_t"].reshape(n, 16, 16)[mask]), bits(outs["spec_t"].numpy()[mask]))
+    for i in range(len(lights)):
+        assert np.array_equal(bits(un["point_shadow"][i].reshape(n, 16, 16)[mask]), bits(outs["point_shadow"].numpy()[i][mask]))
+    vol.close()
+
+
 def test_lighting_host_packed_decodes_to_the_float_planes(gpu_ctx, oracle, terrain):
     """vxl_lighting_host_packed: the shadow planes as a bit mask per pixel, spec_t as its one-byte code (LightAmbient.frag:167-169,
     LightPoint.frag:125, LightReflection.frag:113 take 2 / 2 / 180 values), AO float32.  Decoded, every plane equals what

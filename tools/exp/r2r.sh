@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_parity.py tests/test_cpp_host.py tests/test_assets.py -m gpu -x -q 2>&1 | tail -5 > gpurun_out/r2r_gpu_tests.log
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "lighting_host" 2>&1 | tail -15 > gpurun_out/r2r_gpu_tests.log
 cat gpurun_out/r2r_gpu_tests.log
 python bench.py --steps 10 --warmup 3 > gpurun_out/r2r_bench.json 2> gpurun_out/r2r_bench.err
 python - <<PY

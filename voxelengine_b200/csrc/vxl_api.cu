@@ -88,12 +88,21 @@ __device__ __forceinline__ unsigned spec_code_of(float t) {
 __global__ void __launch_bounds__(256) k_pack_planes(const float* __restrict__ shadow, const float* __restrict__ point, int n_point,
                                                      const float* __restrict__ spot, int n_spot, size_t plane_stride,
                                                      const float* __restrict__ spec, uint8_t* __restrict__ mask, int mask_bytes,
-                                                     uint8_t* __restrict__ code, int tile_w, int tile_h, int row0, int rows, int n_tiles) {
+                                                     uint8_t* __restrict__ code, int tile_w, int tile_h, int row0, int rows, int n_tiles,
+                                                     int width, int height, int tile_first, int tile_stride) {
     const size_t band = (size_t)rows * tile_w;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= band * (size_t)n_tiles) return;
     const size_t t = i / band, r = i - t * band;
     const size_t idx = t * ((size_t)tile_w * tile_h) + (size_t)row0 * tile_w + r;
+    // pixels of an edge tile that lie beyond the frame are not written by the passes: they pack as "lit" / "miss"
+    const int tiles_x = (width + tile_w - 1) / tile_w, gt = tile_first + (int)t * tile_stride;
+    const int py = (gt / tiles_x) * tile_h + row0 + (int)(r / (size_t)tile_w), pxl = (gt % tiles_x) * tile_w + (int)(r % (size_t)tile_w);
+    if (pxl >= width || py >= height) {
+        if (mask) for (int byte = 0; byte < mask_bytes; ++byte) mask[idx * (size_t)mask_bytes + byte] = 0;
+        if (code) code[idx] = 255;
+        return;
+    }
     if (mask) {
         const int n_planes = 1 + n_point + n_spot;
         for (int byte = 0; byte < mask_bytes; ++byte) {
@@ -459,16 +468,24 @@ static int lighting_host_impl(vxl_ctx* c, vxl_volume* vol, const vxl_lighting_ho
     // local-light and reflection passes: the kernels are independent, so one's tail overlaps another's head).  The frame goes
     // through in NB row bands (rows of every tile of the shard).  PCIe is full duplex and the copy engines run beside the SMs,
     // so band b+1 uploads and band b-1 reads back while band b is in the passes.
-    int NB = a->frame.tile_h >= 256 ? 4 : 1;
+    // A whole frame on one GPU is ONE tile: its bands are row ranges.  A rank's shard of a sharded frame is many small tiles: its
+    // bands are ranges of tiles (contiguous in the tile-compact planes).
+    const int nt = a->frame.n_tiles;
+    const bool by_tiles = a->frame.tile_h < 256 && nt >= 8;
+    int NB = (a->frame.tile_h >= 256 || by_tiles) ? 4 : 1;
     if (const char* nb = getenv("VXL_HOST_BANDS")) NB = std::max(1, std::min(64, atoi(nb)));   // tuning knob
+    if (by_tiles) NB = std::min(NB, nt);
     const int band_h = ((a->frame.tile_h + NB - 1) / NB + 15) / 16 * 16;          // whole 16-row thread blocks
+    const int band_t = (nt + NB - 1) / NB;
     const size_t n_ev = 6 + (size_t)NB * 6;
     while (c->ev.size() < n_ev) { cudaEvent_t e; VXL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->ev.push_back(e); }
     cudaEvent_t* ev = c->ev.data();
     const size_t tile_px = (size_t)a->frame.tile_w * a->frame.tile_h;
-    const int nt = a->frame.n_tiles;
-    // rows [r0, r0 + rows) of every tile of a tile-compact plane of `el`-byte pixels: nt chunks of rows * tile_w pixels, tile_px apart
-    auto copy_band = [&](void* dst, const void* src, int r0, int rows, size_t el, cudaMemcpyKind kind, cudaStream_t st) -> cudaError_t {
+    int r0 = 0, rows = a->frame.tile_h, t0 = 0, tn = nt;                          // the current band
+    // the current band of a tile-compact plane of `el`-byte pixels: rows [r0, r0 + rows) of every tile (nt pieces, tile_px apart), or
+    // the tiles [t0, t0 + tn) (one piece)
+    auto copy_band = [&](void* dst, const void* src, size_t el, cudaMemcpyKind kind, cudaStream_t st) -> cudaError_t {
+        if (by_tiles) { const size_t off = (size_t)t0 * tile_px * el; return cudaMemcpyAsync((char*)dst + off, (const char*)src + off, (size_t)tn * tile_px * el, kind, st); }
         const size_t off = (size_t)r0 * a->frame.tile_w * el;
         if (nt == 1) return cudaMemcpyAsync((char*)dst + off, (const char*)src + off, (size_t)rows * a->frame.tile_w * el, kind, st);
         return cudaMemcpy2DAsync((char*)dst + off, tile_px * el, (const char*)src + off, tile_px * el, (size_t)rows * a->frame.tile_w * el, (size_t)nt, kind, st);
@@ -481,42 +498,45 @@ static int lighting_host_impl(vxl_ctx* c, vxl_volume* vol, const vxl_lighting_ho
     restore.join[0] = ev[2]; restore.join[1] = ev[3]; restore.join[2] = ev[4]; restore.join[3] = ev[5];   // from here on the side streams carry work
     cudaStream_t const main = c->stream, sl = c->s_side[0], sr = c->s_side[1];
     VXL_CUDA(cudaMemcpyAsync(c->h_noise, a->frame.noise, 512 * 512 * 4, cudaMemcpyHostToDevice, c->s_h2d));
-    vxl_frame fd = a->frame;
-    fd.depth24 = d_depth; fd.normal = d_normal; fd.material = d_mat; fd.noise = c->h_noise;
     float* o_shadow = c->h_out; float* o_ao = o_shadow + px; float* o_spec = o_ao + px;
     float* o_pt = o_spec + px; float* o_sp = o_pt + px * (size_t)a->n_point;
     uint8_t* o_mask = reinterpret_cast<uint8_t*>(o_sp + px * (size_t)a->n_spot); uint8_t* o_code = o_mask + px * (size_t)mask_bytes;
+    if (by_tiles) c->light_plane_stride = px;                             // a band's light planes sit inside the shard's
     for (int b = 0; b < NB; ++b) {
-        const int r0 = b * band_h, rows = std::min(band_h, a->frame.tile_h - r0);
-        if (rows <= 0) break;
+        if (by_tiles) { t0 = b * band_t; tn = std::min(band_t, nt - t0); if (tn <= 0) break; }
+        else { r0 = b * band_h; rows = std::min(band_h, a->frame.tile_h - r0); if (rows <= 0) break; }
+        const size_t bo = by_tiles ? (size_t)t0 * tile_px : 0;            // where the band starts in every plane
+        vxl_frame fd = a->frame;
+        fd.depth24 = d_depth + bo; fd.normal = d_normal + bo; fd.material = d_mat + bo; fd.noise = c->h_noise;
+        if (by_tiles) { fd.tile_first = a->frame.tile_first + t0 * a->frame.tile_stride; fd.n_tiles = tn; }
         cudaEvent_t* eb = ev + 6 + (size_t)b * 6;
-        VXL_CUDA(copy_band(d_depth, a->frame.depth24, r0, rows, 4, cudaMemcpyHostToDevice, c->s_h2d));
-        VXL_CUDA(copy_band(d_normal, a->frame.normal, r0, rows, 4, cudaMemcpyHostToDevice, c->s_h2d));
-        if (want_rf) VXL_CUDA(copy_band(d_mat, a->frame.material, r0, rows, 4, cudaMemcpyHostToDevice, c->s_h2d));
+        VXL_CUDA(copy_band(d_depth, a->frame.depth24, 4, cudaMemcpyHostToDevice, c->s_h2d));
+        VXL_CUDA(copy_band(d_normal, a->frame.normal, 4, cudaMemcpyHostToDevice, c->s_h2d));
+        if (want_rf) VXL_CUDA(copy_band(d_mat, a->frame.material, 4, cudaMemcpyHostToDevice, c->s_h2d));
         VXL_CUDA(cudaEventRecord(eb[0], c->s_h2d));
         VXL_CUDA(cudaStreamWaitEvent(main, eb[0], 0));
-        c->band_row0 = r0; c->band_rows = rows;
+        if (!by_tiles) { c->band_row0 = r0; c->band_rows = rows; }
         if (want_amb) {                                                   // first in the queue: its blocks fill the machine first
-            if (int e = vxl_pass_ambient(c, vol, a->view, &fd, a->n_ao, want_sun ? o_shadow : nullptr, want_ao ? o_ao : nullptr)) return e;
+            if (int e = vxl_pass_ambient(c, vol, a->view, &fd, a->n_ao, want_sun ? o_shadow + bo : nullptr, want_ao ? o_ao + bo : nullptr)) return e;
             VXL_CUDA(cudaEventRecord(eb[3], main)); VXL_CUDA(cudaStreamWaitEvent(c->s_d2h, eb[3], 0));
-            if (!packed && a->out_shadow) VXL_CUDA(copy_band(a->out_shadow, o_shadow, r0, rows, 4, cudaMemcpyDeviceToHost, c->s_d2h));
-            if (want_ao) VXL_CUDA(copy_band(packed ? packed->ao : a->out_ao, o_ao, r0, rows, 4, cudaMemcpyDeviceToHost, c->s_d2h));
+            if (!packed && a->out_shadow) VXL_CUDA(copy_band(a->out_shadow, o_shadow, 4, cudaMemcpyDeviceToHost, c->s_d2h));
+            if (want_ao) VXL_CUDA(copy_band(packed ? packed->ao : a->out_ao, o_ao, 4, cudaMemcpyDeviceToHost, c->s_d2h));
         }
         if (want_pt || want_sp) {
             VXL_CUDA(cudaStreamWaitEvent(sl, eb[0], 0));
             c->stream = sl;                                               // point then spot: they share the light staging buffer
             if (want_pt) {
-                if (int e = vxl_pass_point(c, vol, a->view, &fd, a->point, a->n_point, o_pt)) return e;
+                if (int e = vxl_pass_point(c, vol, a->view, &fd, a->point, a->n_point, o_pt + bo)) return e;
                 if (!packed) {
                     VXL_CUDA(cudaEventRecord(eb[1], sl)); VXL_CUDA(cudaStreamWaitEvent(c->s_d2h, eb[1], 0));
-                    for (int l = 0; l < a->n_point; ++l) VXL_CUDA(copy_band(a->out_point_shadow + px * (size_t)l, o_pt + px * (size_t)l, r0, rows, 4, cudaMemcpyDeviceToHost, c->s_d2h));
+                    for (int l = 0; l < a->n_point; ++l) VXL_CUDA(copy_band(a->out_point_shadow + px * (size_t)l, o_pt + px * (size_t)l, 4, cudaMemcpyDeviceToHost, c->s_d2h));
                 }
             }
             if (want_sp) {
-                if (int e = vxl_pass_spot(c, vol, a->view, &fd, a->spot, a->n_spot, o_sp)) return e;
+                if (int e = vxl_pass_spot(c, vol, a->view, &fd, a->spot, a->n_spot, o_sp + bo)) return e;
                 if (!packed) {
                     VXL_CUDA(cudaEventRecord(eb[2], sl)); VXL_CUDA(cudaStreamWaitEvent(c->s_d2h, eb[2], 0));
-                    for (int l = 0; l < a->n_spot; ++l) VXL_CUDA(copy_band(a->out_spot_shadow + px * (size_t)l, o_sp + px * (size_t)l, r0, rows, 4, cudaMemcpyDeviceToHost, c->s_d2h));
+                    for (int l = 0; l < a->n_spot; ++l) VXL_CUDA(copy_band(a->out_spot_shadow + px * (size_t)l, o_sp + px * (size_t)l, 4, cudaMemcpyDeviceToHost, c->s_d2h));
                 }
             }
             c->stream = main;
@@ -525,23 +545,24 @@ static int lighting_host_impl(vxl_ctx* c, vxl_volume* vol, const vxl_lighting_ho
         if (want_rf) {
             VXL_CUDA(cudaStreamWaitEvent(sr, eb[0], 0));
             c->stream = sr;
-            const int e = vxl_pass_reflection(c, vol, a->view, &fd, o_spec);
+            const int e = vxl_pass_reflection(c, vol, a->view, &fd, o_spec + bo);
             c->stream = main;
             if (e) return e;
             if (!packed) {
                 VXL_CUDA(cudaEventRecord(eb[4], sr)); VXL_CUDA(cudaStreamWaitEvent(c->s_d2h, eb[4], 0));
-                VXL_CUDA(copy_band(a->out_spec_t, o_spec, r0, rows, 4, cudaMemcpyDeviceToHost, c->s_d2h));
+                VXL_CUDA(copy_band(a->out_spec_t, o_spec, 4, cudaMemcpyDeviceToHost, c->s_d2h));
             } else { VXL_CUDA(cudaEventRecord(eb[4], sr)); VXL_CUDA(cudaStreamWaitEvent(main, eb[4], 0)); }
         }
         if (packed && (want_mask || want_rf)) {                           // behind all three pass streams (joined into `main` above)
-            const size_t n = (size_t)rows * a->frame.tile_w * (size_t)nt;
-            k_pack_planes<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(want_sun ? o_shadow : nullptr, o_pt, want_pt ? a->n_point : 0, o_sp, want_sp ? a->n_spot : 0, px,
-                                                                         o_spec, want_mask ? o_mask : nullptr, mask_bytes, want_rf ? o_code : nullptr,
-                                                                         a->frame.tile_w, a->frame.tile_h, r0, rows, nt);
+            const int prow0 = by_tiles ? 0 : r0, prows = by_tiles ? a->frame.tile_h : rows, pnt = by_tiles ? tn : nt;
+            const size_t n = (size_t)prows * a->frame.tile_w * (size_t)pnt;
+            k_pack_planes<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(want_sun ? o_shadow + bo : nullptr, o_pt + bo, want_pt ? a->n_point : 0, o_sp + bo, want_sp ? a->n_spot : 0, px,
+                                                                         o_spec + bo, want_mask ? o_mask + bo * (size_t)mask_bytes : nullptr, mask_bytes, want_rf ? o_code + bo : nullptr,
+                                                                         a->frame.tile_w, a->frame.tile_h, prow0, prows, pnt, a->frame.width, a->frame.height, fd.tile_first, fd.tile_stride);
             VXL_LAUNCH_CHECK(c);
             VXL_CUDA(cudaEventRecord(eb[5], main)); VXL_CUDA(cudaStreamWaitEvent(c->s_d2h, eb[5], 0));
-            if (want_mask) VXL_CUDA(copy_band(packed->shadow_mask, o_mask, r0, rows, (size_t)mask_bytes, cudaMemcpyDeviceToHost, c->s_d2h));
-            if (want_rf) VXL_CUDA(copy_band(packed->spec_code, o_code, r0, rows, 1, cudaMemcpyDeviceToHost, c->s_d2h));
+            if (want_mask) VXL_CUDA(copy_band(packed->shadow_mask, o_mask, (size_t)mask_bytes, cudaMemcpyDeviceToHost, c->s_d2h));
+            if (want_rf) VXL_CUDA(copy_band(packed->spec_code, o_code, 1, cudaMemcpyDeviceToHost, c->s_d2h));
         }
     }
     c->band_row0 = 0; c->band_rows = 0;
