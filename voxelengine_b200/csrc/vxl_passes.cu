@@ -508,13 +508,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_AMBIENT_BLOCKS) k_ambient(c
 // LightPoint.frag:85-129 / LightSpot.frag:73-117 -- all lights of the list in one launch; the
 // G-buffer, noise and world position are read / derived once per pixel instead of once per light.
 // -------------------------------------------------------------------------------------------------
-template <bool SPOT, int MODE>
+template <bool SPOT, int MODE, typename RG>
 __global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_local_lights(const __grid_constant__ VolView V, const __grid_constant__ CUtensorMap tm_tile, const __grid_constant__ FrameView F, const __grid_constant__ ViewK K, const float* __restrict__ g_lut,
                                                       const float* __restrict__ lights, int n_lights,
                                                       float* __restrict__ out_shadow, size_t plane_stride,
                                                       unsigned long long* __restrict__ g_stats) {
     typedef LocalGeom G;
-    typedef PassRegion RG;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BlockShared<G>& S = *reinterpret_cast<BlockShared<G>*>(smem_raw);
     __shared__ float s_light[VXL_MAX_LIGHTS * 4];   // position.xyz, range
@@ -618,11 +617,10 @@ __device__ __forceinline__ ReflPixel reflection_pixel(const FrameView& F, const 
     return a;
 }
 
-template <int MODE>
+template <int MODE, typename RG>
 __global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_reflection(const __grid_constant__ VolView V, const __grid_constant__ CUtensorMap tm_tile, const __grid_constant__ FrameView F, const __grid_constant__ ViewK K, const float* __restrict__ g_lut,
                                                     float* __restrict__ out_t, unsigned long long* __restrict__ g_stats) {
     typedef ReflGeom G;
-    typedef PassRegion RG;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BlockShared<G>& S = *reinterpret_cast<BlockShared<G>*>(smem_raw);
     load_luts(S.lut, g_lut);
@@ -743,15 +741,22 @@ static int local_lights(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, con
     const size_t plane = ctx->light_plane_stride ? ctx->light_plane_stride : frame_pixels(frame);
     const CUtensorMap* tm = nullptr;
     if (int e = level_tensor_map(vol->occ[LocalGeom::SHIFT - 2], LocalGeom::TW, LocalGeom::TY, LocalGeom::TY, &tm)) return e;
-#define VXL_LL(SPOT_, MODE_)                                                                                                              \
+    // 64x32-pixel regions amortise the tile staging, but a rank's share of a sharded frame may then be a single wave of blocks:
+    // below 8 blocks per SM the 32x16 regions balance better (8 GPUs, config 3: reflection 0.29 -> 0.2 ms per rank)
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
+    const bool big = grid_regions<PassRegion>(F) >= 8u * (unsigned)n_sm;
+#define VXL_LL2(SPOT_, MODE_, RG_)                                                                                                        \
     do {                                                                                                                              \
-        if (MODE_) VXL_CUDA(cudaFuncSetAttribute(k_local_lights<SPOT_, MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<LocalGeom, (MODE_ > 0)>())); \
-        k_local_lights<SPOT_, MODE_><<<grid_regions<PassRegion>(F), BLOCK_THREADS, smem_bytes<LocalGeom, (MODE_ > 0)>(), ctx->stream>>>(              \
+        if (MODE_) VXL_CUDA(cudaFuncSetAttribute(k_local_lights<SPOT_, MODE_, RG_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<LocalGeom, (MODE_ > 0)>())); \
+        k_local_lights<SPOT_, MODE_, RG_><<<grid_regions<RG_>(F), BLOCK_THREADS, smem_bytes<LocalGeom, (MODE_ > 0)>(), ctx->stream>>>(              \
             vol_view(vol), *tm, F, make_viewk(view), ctx->d_luts, (const float*)ctx->d_lights, n_lights, out_shadow, plane, ctx->d_stats); \
     } while (0)
+#define VXL_LL(SPOT_, MODE_) do { if (big) VXL_LL2(SPOT_, MODE_, PassRegion); else VXL_LL2(SPOT_, MODE_, AmbientRegion); } while (0)
     if (spot) { if (ctx->variant == 0) VXL_LL(true, 0); else if (ctx->variant == 1) VXL_LL(true, 1); else VXL_LL(true, 2); }
     else { if (ctx->variant == 0) VXL_LL(false, 0); else if (ctx->variant == 1) VXL_LL(false, 1); else VXL_LL(false, 2); }
 #undef VXL_LL
+#undef VXL_LL2
     VXL_LAUNCH_CHECK(ctx);
     return VXL_OK;
 }
@@ -778,14 +783,19 @@ int vxl_pass_reflection(vxl_ctx* ctx, vxl_volume* vol, const vxl_view* view, con
     if (vol->dirty) { if (int e = vxl_volume_build_occupancy(vol)) return e; }
     const CUtensorMap* tm = nullptr;
     if (int e = level_tensor_map(vol->occ[ReflGeom::SHIFT - 2], ReflGeom::TW, ReflGeom::TY, ReflGeom::TY, &tm)) return e;
-#define VXL_RF(MODE_)                                                                                                                   \
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
+    const bool big = grid_regions<PassRegion>(F) >= 8u * (unsigned)n_sm;                  // see local_lights
+#define VXL_RF2(MODE_, RG_)                                                                                                            \
     do {                                                                                                                            \
-        if (MODE_) VXL_CUDA(cudaFuncSetAttribute(k_reflection<MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<ReflGeom, (MODE_ > 0)>())); \
-        k_reflection<MODE_><<<grid_regions<PassRegion>(F), BLOCK_THREADS, smem_bytes<ReflGeom, (MODE_ > 0)>(), ctx->stream>>>(                       \
+        if (MODE_) VXL_CUDA(cudaFuncSetAttribute(k_reflection<MODE_, RG_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<ReflGeom, (MODE_ > 0)>())); \
+        k_reflection<MODE_, RG_><<<grid_regions<RG_>(F), BLOCK_THREADS, smem_bytes<ReflGeom, (MODE_ > 0)>(), ctx->stream>>>(                       \
             vol_view(vol), *tm, F, make_viewk(view), ctx->d_luts, out_spec_t, ctx->d_stats);                                             \
     } while (0)
+#define VXL_RF(MODE_) do { if (big) VXL_RF2(MODE_, PassRegion); else VXL_RF2(MODE_, AmbientRegion); } while (0)
     if (ctx->variant == 0) VXL_RF(0); else if (ctx->variant == 1) VXL_RF(1); else VXL_RF(2);
 #undef VXL_RF
+#undef VXL_RF2
     VXL_LAUNCH_CHECK(ctx);
     return VXL_OK;
 }
