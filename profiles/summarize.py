@@ -48,6 +48,28 @@ def main():
                 gpus = int(argv[i + 1])
             del argv[i:i + 2]
     sys.argv = argv
+    if "--traffic-csv" in argv:      # a `--metrics dram__bytes_read.sum,dram__bytes_write.sum --csv` launch list: DRAM bytes of each kernel's first launch
+        path = argv[argv.index("--traffic-csv") + 1]
+        per = {}
+        seen = {}
+        for row in csv.DictReader(l for l in open(path) if not l.startswith("==")):
+            if row.get("Metric Name") not in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                continue
+            k = row["Kernel Name"].split("(")[0].replace("void ", "").split("<")[0]
+            if seen.setdefault(k, row["ID"]) != row["ID"]:
+                continue
+            v = float(row["Metric Value"].replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(row["Metric Unit"], 1)
+            per[k] = per.get(k, 0.0) + v
+        here = os.path.dirname(os.path.abspath(__file__))
+        tp = os.path.join(here, "dram_traffic.json")
+        try:
+            all_traffic = json.load(open(tp))
+        except Exception:
+            all_traffic = {}
+        all_traffic[f"cfg{cfg}_n{gpus}"] = per
+        json.dump(all_traffic, open(tp, "w"), indent=1, sort_keys=True)
+        print(json.dumps(per))
+        return
     rep, tag = sys.argv[1], sys.argv[2]
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))

@@ -25,6 +25,7 @@ struct BlockShared {
     unsigned acc[4];
     uint64_t bar;                             // mbarrier the TMA copy of `tile` completes
     int next_item;                            // work items of the region handed out so far
+    unsigned zero;                            // 0, read back through a volatile load: an addend the compiler cannot see through (ao_pooled)
     alignas(128) uint32_t tile[G::TY * G::TY * G::TW];     // from here on: kernel variant 0 allocates only the header
     uint32_t dtile[G::DW * G::DT * G::DT];
     uint32_t ntile[G::NEAR ? NEAR_T * NEAR_T : 1];
@@ -79,7 +80,7 @@ __device__ __forceinline__ BitTile block_prologue(const VolView& V, BlockShared<
     constexpr int NBB = G::NEAR ? 12 : 6;
     if (threadIdx.x < NBB) S.bb[threadIdx.x] = (threadIdx.x % 6) < 3 ? 0x7fffffff : -0x7fffffff - 1;
     if (threadIdx.x < 4) S.acc[threadIdx.x] = 0u;
-    if (threadIdx.x == 0) S.next_item = 0;
+    if (threadIdx.x == 0) { S.next_item = 0; S.zero = 0u; }
     if (FAST && threadIdx.x == 0) mbar_init(&S.bar, 1u);
     __syncthreads();
     if (!FAST) return T;
@@ -274,7 +275,10 @@ __device__ __forceinline__ float ao_pooled(const VolView& V, const BitTile& C, B
     // one eps for everybody (test_super_cand): no coordinate of a scanned ray is further than 200 voxels from the volume
     const float eps = (fminf((float)(2 * max(V.sx, max(V.sy, V.sz)) + 200), BM_MAXCOORD) + 1.0f) * (1.0f / 262144.0f);
     typedef ScanLook<false, (unsigned)(G::TY * G::TY), (unsigned)G::TY> TileLook;
-    const TileLook look_tile = TileLook::make(C.w, G::SHIFT, C.ox, C.oy, C.oz, 0u, 0u);
+    TileLook look_tile = TileLook::make(C.w, G::SHIFT, C.ox, C.oy, C.oz, 0u, 0u);
+    // The folded base (window address minus a compile-time constant) has to sit in ONE register so that a lookup's address is one
+    // LEA; left alone the compiler keeps the window address in a uniform register and adds the constant per lookup.
+    look_tile.sbase += *(volatile unsigned*)&S.zero;
     const ScanLook<false> look_near = (G::NEAR && near_ok) ? ScanLook<false>::make(C.wn, 1, C.nx, C.ny, C.nz, (unsigned)NEAR_T, (unsigned)NEAR_T)
                                                            : ScanLook<false>::make(C.w, G::SHIFT, C.ox, C.oy, C.oz, (unsigned)(G::TY * G::TY), (unsigned)G::TY);
     int qn = 0;                       // entries on the stack (warp-uniform)
