@@ -589,6 +589,15 @@ def run_e2e(args, wl, torch, dist, world, rank, rays):
     rc = torch.cuda.cudart().cudaHostRegister(mine.data_ptr(), slot * 4, 0)
     assert int(rc) == 0, f"cudaHostRegister failed: {rc}"
     plane = n * wl.gb.tile_h * wl.gb.tile_w
+    # the packed frame of the same call (vxl_lighting_host_packed) shares the rank's slot: [ao float32][shadow mask][spec code]; the
+    # float planes are timed first, verified, and only then overwritten
+    mb = E.mask_bytes(wl.n_point, 0)
+    assert plane * (4 + mb + 1) <= slot * 4
+    mine_b = torch.from_numpy(frame_host[rank].view(np.uint8))
+    pk = dict(ao=mine[0:plane].view(shape), shadow_mask=mine_b[4 * plane:(4 + mb) * plane].view(shape + (mb,)))
+    if wl.spec:
+        pk["spec_code"] = mine_b[(4 + mb) * plane:(5 + mb) * plane].view(shape)
+    d2h_packed = sum(int(t.numel()) * t.element_size() for t in pk.values())
     outs = dict(shadow=mine[0:plane], ao=mine[plane:2 * plane])
     if wl.spec:
         outs["spec_t"] = mine[2 * plane:3 * plane]
@@ -598,17 +607,19 @@ def run_e2e(args, wl, torch, dist, world, rank, rays):
     desc = dict(width=wl.gb.width, height=wl.gb.height, tile_w=wl.gb.tile_w, tile_h=wl.gb.tile_h, tile_first=wl.gb.tile_first,
                 tile_stride=wl.gb.tile_stride, n_tiles=n)
 
-    def one():
-        if n:
-            E.lighting_host(wl.ctx, wl.vol, wl.view, desc, planes, outs, n_ao=wl.n_ao, point=wl.lights)   # blocks until the planes are in host memory
-    for _ in range(2):
-        one()
-    dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        one()
-        dist.barrier()                      # the frame is complete when every rank's tiles have landed
-    dt = (time.perf_counter() - t0) / steps
+    def timed_host(o):
+        def one():
+            if n:
+                E.lighting_host(wl.ctx, wl.vol, wl.view, desc, planes, o, n_ao=wl.n_ao, point=wl.lights)   # blocks until the planes are in host memory
+        for _ in range(2):
+            one()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            one()
+            dist.barrier()                  # the frame is complete when every rank's tiles have landed
+        return (time.perf_counter() - t0) / steps
+    dt = timed_host(outs)
     # every rank's region of the shared frame must equal the device-resident result of that rank (checked by rank 0 through the gather)
     wl.step(gather=True); torch.cuda.synchronize()
     counts = [torch.zeros(1, dtype=torch.int64, device=wl.ctx.torch_device) for _ in range(world)]
@@ -625,20 +636,37 @@ def run_e2e(args, wl, torch, dist, world, rank, rays):
                 wantp = g[r, 3:, :nr].reshape(-1)
                 assert np.array_equal(frame_host[r, 3 * pr:(3 + wl.n_point) * pr].view(np.uint32), wantp.view(np.uint32)), f"e2e: rank {r} point planes differ"
     dist.barrier()
+    # packed planes: every rank keeps a copy of its float planes, times the packed call into the same slot and decodes it
+    if n:
+        keep = {k: v.clone() for k, v in outs.items()}
+    dt_packed = timed_host({"packed": pk})
+    if n:
+        un = E.unpack_planes(pk["shadow_mask"].numpy(), pk["spec_code"].numpy() if wl.spec else None, wl.n_point, 0)
+        assert torch.equal(pk["ao"].reshape(-1), keep["ao"].reshape(-1)), "e2e (packed): ao differs from the float planes"
+        assert np.array_equal(un["shadow"].view(np.uint32), keep["shadow"].numpy().reshape(-1).view(np.uint32)), "e2e (packed): sun shadow differs"
+        if wl.spec:
+            assert np.array_equal(un["spec_t"].view(np.uint32), keep["spec_t"].numpy().reshape(-1).view(np.uint32)), "e2e (packed): spec_t differs"
+        for li in range(wl.n_point):
+            assert np.array_equal(un["point_shadow"][li].view(np.uint32), keep["point_shadow"].numpy().reshape(wl.n_point, -1)[li].view(np.uint32)), f"e2e (packed): point plane {li} differs"
+        del keep, un
+    dist.barrier()
     torch.cuda.cudart().cudaHostUnregister(mine.data_ptr())
-    del mine, outs, frame_host
+    del mine, mine_b, pk, outs, frame_host
     try:
         shm.close()
     except BufferError:
         pass
     if rank == 0:
         shm.unlink()
-    t = torch.tensor([dt, float(h2d), float(d2h)], dtype=torch.float64, device=wl.ctx.torch_device)
+    t = torch.tensor([dt, float(h2d), float(d2h), dt_packed, float(d2h_packed)], dtype=torch.float64, device=wl.ctx.torch_device)
     tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     tsum = t.clone(); dist.all_reduce(tsum)
-    dt = float(tmax[0].item())
-    return {"value": rays / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(tsum[1].item()), "d2h_bytes_per_step": int(tsum[2].item()), "ms_per_step": dt * 1e3,
-            "api": "vxl_lighting_host per rank on its tile shard (pinned host planes in, one shared page-locked host frame out, a barrier per frame)"}
+    dt, dt_packed = float(tmax[0].item()), float(tmax[3].item())
+    return {"value": rays / dt_packed / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(tsum[1].item()), "d2h_bytes_per_step": int(tsum[4].item()), "ms_per_step": dt_packed * 1e3,
+            "api": "vxl_lighting_host_packed per rank on its tile shard (pinned host planes in, one shared page-locked host frame out, a barrier per frame; "
+                   "decoded and compared bit for bit with the float planes, which are compared with the resident path)",
+            "float_planes": {"value": rays / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(tsum[1].item()), "d2h_bytes_per_step": int(tsum[2].item()), "ms_per_step": dt * 1e3,
+                             "api": "vxl_lighting_host per rank on its tile shard (every plane float32)"}}
 
 
 def main():

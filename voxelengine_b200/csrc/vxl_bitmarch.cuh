@@ -644,14 +644,27 @@ VXL_DI bool test_super_cand(const VolView& V, unsigned koff, float3 origin, floa
     if (COUNT) ++fetched;
     unsigned v;
     const bool low = fminf(fminf(pos.x, pos.y), pos.z) - e < 0.0f;    // a coordinate below zero: the reference truncates toward zero there
-    if (((ax ^ bx) | (ay ^ by) | (az ^ bz)) != 0u || low) {            // phase 2 within eps of a texel face (about 1 %), or a negative coordinate: exact position
-        const float3 s2 = s1 * 2.0f;
-        float3 r = origin;
+    if (((ax ^ bx) | (ay ^ by) | (az ^ bz)) != 0u || low) {            // phase 2 within eps of a texel face (about 1 %), or a negative coordinate
+        bool decided = false;
+        v = 0u;
+        if (!low && !ph1 && (int)(ax != bx) + (int)(ay != by) + (int)(az != bz) == 1) {
+            // pos_k lies within eps of q on every axis, so its texel is one of the two that share the face (a: from q - eps, b: from
+            // q + eps); the phase-2 test only asks whether the byte is zero, and neighbouring texels mostly agree on that
+            const unsigned MB1 = 0x4B000000u + (1u << 23);
+            const unsigned va = fetch_texel(V, (int)(ax - MB1), (int)(ay - MB1), (int)(az - MB1));
+            const unsigned vb = fetch_texel(V, (int)(bx - MB1), (int)(by - MB1), (int)(bz - MB1));
+            decided = (va != 0u) == (vb != 0u);
+            v = vb;
+        }
+        if (!decided) {                                                  // the exact position: replay the recurrence
+            const float3 s2 = s1 * 2.0f;
+            float3 r = origin;
 #pragma unroll 1
-        for (int i = 0; i < k; ++i) r = r + (i < N1 ? s1 : s2);
-        // Light.frag:140 ivec3(pos / 2) in phase 1, :163 ivec3(pos) / 2 in phase 2; out of range reads 0
-        if (ph1) v = fetch_texel(V, f2i(r.x / 2.0f), f2i(r.y / 2.0f), f2i(r.z / 2.0f));
-        else v = fetch_texel(V, f2i(r.x) / 2, f2i(r.y) / 2, f2i(r.z) / 2);
+            for (int i = 0; i < k; ++i) r = r + (i < N1 ? s1 : s2);
+            // Light.frag:140 ivec3(pos / 2) in phase 1, :163 ivec3(pos) / 2 in phase 2; out of range reads 0
+            if (ph1) v = fetch_texel(V, f2i(r.x / 2.0f), f2i(r.y / 2.0f), f2i(r.z / 2.0f));
+            else v = fetch_texel(V, f2i(r.x) / 2, f2i(r.y) / 2, f2i(r.z) / 2);
+        }
     } else v = ldg(V.bytes + off);
     if (v == 0u) return false;
     if (!ph1) return true;

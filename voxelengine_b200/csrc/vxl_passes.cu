@@ -54,6 +54,9 @@ constexpr size_t smem_bytes() {
 #ifndef VXL_AO_QCAP
 #define VXL_AO_QCAP 64            // pending candidate tests per warp (>= 63: 31 left over + 32 new); 0 = per-lane resolve (round-1 kernel)
 #endif
+#ifndef VXL_AMB_STATIC
+#define VXL_AMB_STATIC 1
+#endif
 #ifndef VXL_PASS_TY
 #define VXL_PASS_TY (VXL_PASS_BLOCKS >= 3 ? 68 : 80)
 #endif
@@ -422,10 +425,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_AMBIENT_BLOCKS) k_ambient(c
     const int warp = threadIdx.x >> 5;
     const bool want_ao = out_ao && n_ao > 0;
     // ---- the boxes the region's rays stay in, for the placement of the block's tiles (approximate: the exact origins come later) ----
+    // STATIC: one item per warp (the AO pass's 32x16 regions) -- the pixels decoded here are the ones the warp works on below
+    constexpr bool STATIC = VXL_AMB_STATIC && RG::ITEMS == NWARPS;
+    PixelCtx p0 = item_pixel<RG>(F, K, R, warp);
+    AmbPixel a0 = ambient_pixel(F, K, p0);
     Box3 far, near;
     bool any = false;
     for (int item = warp; item < RG::ITEMS; item += NWARPS) {
-        const AmbPixel a = ambient_pixel(F, K, item_pixel<RG>(F, K, R, item));
+        const AmbPixel a = item == warp ? a0 : ambient_pixel(F, K, item_pixel<RG>(F, K, R, item));
         if (!a.lit) continue;
         any = true;
         const float3 o = a.wcp0 + a.normal * a.bias;
@@ -446,9 +453,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_AMBIENT_BLOCKS) k_ambient(c
     // the AO rays of tile-march launches go through the warp-pooled resolve (all 32 lanes take part, lit or not)
     const bool POOL = MODE > 0 && G::QCAP > 0 && n_ao <= AO_POOL_MAX_RAYS;
     // ---- the region's 8x4-pixel work items, handed to whichever warp is free ----
-    for (int item = next_item(S); item < RG::ITEMS; item = next_item(S)) {
-        const PixelCtx p = item_pixel<RG>(F, K, R, item);
-        const AmbPixel a = ambient_pixel(F, K, p);
+    for (int item = STATIC ? warp : next_item(S); item < RG::ITEMS; item = STATIC ? RG::ITEMS : next_item(S)) {
+        const PixelCtx p = STATIC ? p0 : item_pixel<RG>(F, K, R, item);
+        const AmbPixel a = STATIC ? a0 : ambient_pixel(F, K, p);
         const float3 normal = a.normal;
         float shadow = 1.0f, ao = 0.0f;
         float3 ao_origin = make_float3(0.f, 0.f, 0.f), blo = ao_origin, bhi = ao_origin;

@@ -154,8 +154,11 @@ __device__ __forceinline__ uint32_t get_noise(const FrameView& F, const ViewK& K
         fx = GOLDEN_RATIO * gmod((float)(K.Frame + s * 5), 64.0f);
         fy = GOLDEN_RATIO * gmod((float)(K.Frame + s * 7 + 1), 64.0f);
     }
-    const int cx = f2i((p.u + fx) * (float)F.width) % 512;
-    const int cy = f2i((p.v + fy) * (float)F.height) % 512;
+    // p.u, p.v > 0 and fx, fy >= 0 (GOLDEN_RATIO times a GLSL mod by 64), so the products are non-negative and % 512 is a mask
+    const int ix = f2i((p.u + fx) * (float)F.width), iy = f2i((p.v + fy) * (float)F.height);
+    __builtin_assume(ix >= 0);
+    __builtin_assume(iy >= 0);
+    const int cx = ix % 512, cy = iy % 512;
     return __ldg(F.noise + cy * 512 + cx);
 }
 
