@@ -8,6 +8,8 @@
 #include <random>
 
 #include "vxl_internal.h"
+#include "vxl_math.cuh"
+#include "vxl_pixel.cuh"
 
 namespace vxl {
 
@@ -190,8 +192,10 @@ int vxl_ctx_create(int device, vxl_ctx** out) {
         lut[k] = (float)cos((double)theta);
         lut[256 + k] = (float)sin((double)theta);
     }
-    VXL_CUDA(cudaMalloc(&c->d_luts, sizeof lut));
+    VXL_CUDA(cudaMalloc(&c->d_luts, LUT_FLOATS * sizeof(float)));
     VXL_CUDA(cudaMemcpy(c->d_luts, lut, sizeof lut, cudaMemcpyHostToDevice));
+    k_fill_sqrt_luts<<<1, 256, 0, c->stream>>>(c->d_luts);      // r[256] z[256]: the device's own sqrtf, once per context instead of once per block
+    VXL_CUDA(cudaStreamSynchronize(c->stream));
     VXL_CUDA(cudaMalloc(&c->d_lights, VXL_MAX_LIGHTS * sizeof(vxl_spot_light)));
     uint8_t perm[1024];
     build_perm(1337, perm, perm + 512);
@@ -206,7 +210,7 @@ int vxl_ctx_destroy(vxl_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (void* p : c->ipc_open) cudaIpcCloseMemHandle(p);
-    cudaFree(c->d_stats); cudaFree(c->d_luts); cudaFree(c->d_taa_lut); cudaFree(c->d_lights); cudaFree(c->d_perm);
+    cudaFree(c->d_stats); cudaFree(c->d_luts); cudaFree(c->d_taa_lut); cudaFree(c->d_taa_depth); cudaFree(c->d_lights); cudaFree(c->d_perm);
     for (auto& m : c->models) { cudaFree((void*)m.voxels); cudaFree((void*)m.mip1); cudaFree((void*)m.mip2); }
     cudaFree(c->d_models); cudaFree(c->d_draws); cudaFree(c->d_hkeys); cudaFree(c->d_hvals); cudaFree(c->d_ents); cudaFree(c->d_aabb);
     cudaFree(c->h_planes); cudaFree(c->h_out); cudaFree(c->h_noise);

@@ -64,6 +64,8 @@ struct vxl_ctx {
     unsigned long long* d_stats = nullptr;   // [STAT_SLOTS][4]
     float* d_luts = nullptr;                 // cos[256] sin[256]
     float* d_taa_lut = nullptr;              // (cos, sin)[256][12] of LightTAA's spiral angles (vxl_post.cu), built on first use
+    float* d_taa_depth = nullptr;            // the frame's depth plane decoded to float (vxl_light_taa), grown on demand
+    size_t taa_depth_cap = 0;
     void* d_lights = nullptr;                // VXL_MAX_LIGHTS * 64 B
     uint8_t* d_perm = nullptr;               // perm[512] perm12[512] (terrain generator)
     std::vector<vxl::ModelDev> models;

@@ -175,11 +175,16 @@ __device__ __forceinline__ float3 cosine_sample_hemisphere(const float* __restri
 
 // (no barrier: the caller's block prologue synchronises before the first use)
 __device__ __forceinline__ void load_luts(float* s_lut, const float* __restrict__ g_lut) {
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_lut[i] = g_lut[i];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    for (int i = threadIdx.x; i < LUT_FLOATS / 4; i += blockDim.x) reinterpret_cast<float4*>(s_lut)[i] = __ldg(reinterpret_cast<const float4*>(g_lut) + i);
+}
+// r = sqrt(u), z = sqrt(max(0, 1 - u)) over the 256 possible u = k / 255, written behind the host's cos / sin tables when the context is
+// created: the same device sqrtf on the same input as a per-ray evaluation
+static __global__ void k_fill_sqrt_luts(float* __restrict__ g_lut) {
+    const int i = threadIdx.x;
+    if (i < 256) {
         const float u = unorm8((uint32_t)i);
-        s_lut[512 + i] = sqrtf(u);
-        s_lut[768 + i] = sqrtf(fmaxf(0.0f, 1.0f - u));
+        g_lut[512 + i] = sqrtf(u);
+        g_lut[768 + i] = sqrtf(fmaxf(0.0f, 1.0f - u));
     }
 }
 

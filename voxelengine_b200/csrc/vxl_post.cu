@@ -26,6 +26,7 @@ constexpr float NEAR_P = 0.1f;                // Common.frag:12
 constexpr int TAA_TAPS = 12;                  // LightTAA.frag:96: radius runs 2..13 while radius <= size (12)
 
 struct FullView {
+    const float* __restrict__ depthf;         // unorm24 of the depth plane, decoded once per frame by k_decode_depth (13 taps per pixel read it)
     const uint32_t* __restrict__ depth24; const uint32_t* __restrict__ normal; const uint32_t* __restrict__ material; const uint32_t* __restrict__ albedo;
     const float2* __restrict__ motion; const float4* __restrict__ light; const float4* __restrict__ last_light;
 };
@@ -55,7 +56,7 @@ __device__ __forceinline__ TaaTexel taa_fetch(const FullView& P, const float* __
     t.color = make_float3(lut[a & 0xFFu], lut[(a >> 8) & 0xFFu], lut[(a >> 16) & 0xFFu]);
     t.normal = make_float3(lut[256 + (nn & 0xFFu)], lut[256 + ((nn >> 8) & 0xFFu)], lut[256 + ((nn >> 16) & 0xFFu)]);
     t.material = make_float4(lut[m & 0xFFu], lut[(m >> 8) & 0xFFu], lut[(m >> 16) & 0xFFu], lut[m >> 24]);
-    t.depth = unorm24(__ldg(P.depth24 + i));
+    t.depth = __ldg(P.depthf + i);
     const float2 mo = __ldg(P.motion + i);
     t.mx = mo.x; t.my = mo.y;
     const float4 l = __ldg(P.light + i);
@@ -67,6 +68,27 @@ __device__ __forceinline__ float material_distance(float4 a, float4 b) {        
     return sqrtf((x * x + y * y) + (z * z + w * w));
 }
 __device__ __forceinline__ float length2(float x, float y) { return sqrtf(x * x + y * y); }
+
+// The shader compares three square roots with constants.  sqrtf is correctly rounded, hence monotone, and so are the float
+// operations applied to it, so each comparison is a comparison of the radicand with ONE float found by bisection over the bit
+// patterns (tools/exp/taa_thresholds.py prints them and checks the neighbours):
+//   length(a) > 0.1            <=>  dot(a, a) > T_MOTION           (LightTAA.frag:76, :113)
+//   step(0.8, 1.0 - length(a)) == 0  <=>  dot(a, a) > T_MATERIAL   (:72, :109)
+//   clamp(length(a) * 10000.0, 0.0, 1.0) == 1.0  <=>  dot(a, a) >= T_COLOR   (:112)
+// A NaN radicand fails every comparison here exactly like the NaN root fails the shader's.
+constexpr float T_MOTION = 0x1.47ae16p-7f, T_MATERIAL = 0x1.47ae16p-5f, T_COLOR = 0x1.5798ecp-27f;
+__device__ __forceinline__ float material_dot(float4 a, float4 b) {
+    const float x = a.x - b.x, y = a.y - b.y, z = a.z - b.z, w = a.w - b.w;
+    return (x * x + y * y) + (z * z + w * w);
+}
+// 1.212 - radius / size for radius = 2 .. 13, size = 12 (:108): the quotients are constants of the loop
+__constant__ float c_taa_rs[TAA_TAPS] = {2.0f / 12.0f, 3.0f / 12.0f, 4.0f / 12.0f, 5.0f / 12.0f, 6.0f / 12.0f, 7.0f / 12.0f,
+                                         8.0f / 12.0f, 9.0f / 12.0f, 10.0f / 12.0f, 11.0f / 12.0f, 12.0f / 12.0f, 13.0f / 12.0f};
+
+__global__ void __launch_bounds__(256) k_decode_depth(const uint32_t* __restrict__ d24, float* __restrict__ out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = unorm24(__ldg(d24 + i));
+}
 
 __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_light_taa(FrameView F, ViewK K, FullView P, const float2* __restrict__ g_cs /* [256][12] */,
                                                              float4* __restrict__ out) {
@@ -92,10 +114,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_light_taa(FrameView F, Vie
                 const float u = tclamp(p.u + (float)x * iRx, 0.001f, 0.999f), v = tclamp(p.v + (float)y * iRy, 0.001f, 0.999f);   // :62-63
                 const TaaTexel n = taa_fetch(P, lut, W, H, u, v);
                 float factor = tmax(dot3(c.normal, n.normal), 0.0f);                          // :71
-                factor *= gstep(0.8f, 1.0f - material_distance(c.material, n.material));      // :72
+                factor *= material_dot(c.material, n.material) > T_MATERIAL ? 0.0f : 1.0f;     // :72
                 factor *= 1.0f - tclamp(fabsf(c.depth - n.depth) * FAR_, 0.0f, 1.0f);          // :73
                 factor *= 1.0f - tclamp(length3(c.color - n.color), 0.0f, 1.0f);              // :74
-                if (length2(c.mx - n.mx, c.my - n.my) > 0.1f) factor = 0.0f;                  // :76
+                { const float dx = c.mx - n.mx, dy = c.my - n.my; if (dx * dx + dy * dy > T_MOTION) factor = 0.0f; }   // :76
                 neigh = neigh + n.light * factor;                                             // :79
                 count += factor;
             }
@@ -104,7 +126,6 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_light_taa(FrameView F, Vie
     }
     float3 nmin = splat3(10000.0f), nmax = splat3(0.0f), neigh = splat3(0.0f);                // :89-91
     float diffSum = 1.0f, count = 0.0f, radius = 1.0f;
-    const float size = 12.0f;
     const uint32_t nz = get_noise(F, K, p, -1);
     const float2* cs = g_cs + (nz & 0xFFu) * TAA_TAPS;
     const float k2 = tclamp(0.1f, 0.5f, 1.0f / c.depth);                                      // :99 (sic: clamp(x = 0.1, 0.5, 1/depth))
@@ -116,12 +137,19 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_light_taa(FrameView F, Vie
         const float ox = ((a.x * iRx) * k1) * k2, oy = ((a.y * iRy) * k1) * k2;
         const float u = tclamp(p.u + ox, 0.001f, 0.999f), v = tclamp(p.v + oy, 0.001f, 0.999f);
         const TaaTexel n = taa_fetch(P, lut, W, H, u, v);
-        float factor = 1.212f - radius / size;                                                // :108
-        factor *= gstep(0.8f, 1.0f - material_distance(c.material, n.material));
+        float factor = 1.212f - c_taa_rs[k];                                                  // :108
+        factor *= material_dot(c.material, n.material) > T_MATERIAL ? 0.0f : 1.0f;
         factor *= tmax(dot3(c.normal, n.normal), 0.0f);
         factor *= 1.0f - tclamp(fabsf(c.depth - n.depth) * FAR_, 0.0f, 1.0f);
-        factor *= 1.0f - tclamp(length3(c.color - n.color) * 10000.0f, 0.0f, 1.0f);
-        if (length2(c.mx - n.mx, c.my - n.my) > 0.1f) factor = 0.0f;
+        {
+            const float3 dc = c.color - n.color;
+            const float s2 = dot3(dc, dc);
+            float cl = 1.0f;                                                                  // albedo bytes differ by >= 1/255: always here
+            if (s2 == 0.0f) cl = 0.0f;
+            else if (!(s2 >= T_COLOR)) cl = tclamp(sqrtf(s2) * 10000.0f, 0.0f, 1.0f);
+            factor *= 1.0f - cl;
+        }
+        { const float dx = c.mx - n.mx, dy = c.my - n.my; if (dx * dx + dy * dy > T_MOTION) factor = 0.0f; }
         nmin = make_float3(tmin(nmin.x, n.light.x), tmin(nmin.y, n.light.y), tmin(nmin.z, n.light.z));   // :116
         nmax = make_float3(tmax(nmax.x, n.light.x), tmax(nmax.y, n.light.y), tmax(nmax.z, n.light.z));
         neigh = neigh + n.light * factor;
@@ -149,7 +177,7 @@ __device__ __forceinline__ float pow5p(float x) { const float x2 = x * x; return
 __global__ void __launch_bounds__(BLOCK_THREADS) k_resolve_reflection(FrameView F, ViewK K, const float* __restrict__ g_lut, const float* __restrict__ spec_t,
                                                                       const uint32_t* __restrict__ depth_full, const float4* __restrict__ light_full,
                                                                       float3 sky, float4* __restrict__ out) {
-    __shared__ float s_lut[LUT_FLOATS];
+    __shared__ __align__(16) float s_lut[LUT_FLOATS];
     load_luts(s_lut, g_lut);
     __syncthreads();
     const PixelCtx p = pixel_ctx(F, K);
@@ -236,7 +264,16 @@ int vxl_light_taa(vxl_ctx* ctx, const vxl_view* view, const vxl_frame* frame, co
     if (F.n_tiles == 0) return VXL_OK;
     VXL_CUDA(cudaSetDevice(ctx->device));
     if (int e = ensure_taa_lut(ctx)) return e;
-    FullView P{full->depth24, full->normal, full->material, full->albedo, (const float2*)full->motion, (const float4*)full->light, (const float4*)full->last_light};
+    const size_t npx = (size_t)F.width * (size_t)F.height;
+    if (ctx->taa_depth_cap < npx) {
+        if (ctx->d_taa_depth) cudaFree(ctx->d_taa_depth);
+        ctx->d_taa_depth = nullptr; ctx->taa_depth_cap = 0;
+        VXL_CUDA(cudaMalloc((void**)&ctx->d_taa_depth, npx * sizeof(float)));
+        ctx->taa_depth_cap = npx;
+    }
+    k_decode_depth<<<(unsigned)((npx + 255) / 256), 256, 0, ctx->stream>>>(full->depth24, ctx->d_taa_depth, npx);
+    ctx->launches++;
+    FullView P{ctx->d_taa_depth, full->depth24, full->normal, full->material, full->albedo, (const float2*)full->motion, (const float4*)full->light, (const float4*)full->last_light};
     k_light_taa<<<grid_for(F), BLOCK_THREADS, 0, ctx->stream>>>(F, make_viewk(view), P, (const float2*)ctx->d_taa_lut, (float4*)out_rgba);
     VXL_LAUNCH_CHECK(ctx);
     return VXL_OK;

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_resolve_ambient(FrameView F, 
                                                                    const uint32_t* __restrict__ albedo, const uint32_t* __restrict__ depth_full,
                                                                    const float* __restrict__ shadow, const float* __restrict__ ao,
                                                                    float4* __restrict__ out) {
-    __shared__ float s_lut[LUT_FLOATS];
+    __shared__ __align__(16) float s_lut[LUT_FLOATS];
     __shared__ float s_dec[512];             // unorm8[256], snorm8[256]: the decoders' own divisions, done once per block
     load_luts(s_lut, g_lut);
     for (int i = threadIdx.x; i < 256; i += blockDim.x) { s_dec[i] = unorm8((uint32_t)i); s_dec[256 + i] = snorm8((uint32_t)i); }
