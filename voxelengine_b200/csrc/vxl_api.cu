@@ -476,8 +476,10 @@ static int lighting_host_impl(vxl_ctx* c, vxl_volume* vol, const vxl_lighting_ho
     // bands are ranges of tiles (contiguous in the tile-compact planes).
     const int nt = a->frame.n_tiles;
     const bool by_tiles = a->frame.tile_h < 256 && nt >= 8;
-    int NB = (a->frame.tile_h >= 256 || by_tiles) ? 4 : 1;
-    if (const char* nb = getenv("VXL_HOST_BANDS")) NB = std::max(1, std::min(64, atoi(nb)));   // tuning knob
+    // bands of a whole frame: about 1250 thread blocks of the ambient pass each (four waves), at most 16 -- 3 at 1080p, 12 at 4K
+    // (measured at 4K, float / packed planes: 4 bands 7.76 / 7.15 ms, 8: 7.03 / 6.74, 12: 6.86 / 6.71, 16: 6.84 / 6.79, 24: 7.22 / 7.55)
+    int NB = by_tiles ? 4 : (a->frame.tile_h >= 256 ? (int)std::max<size_t>(3, std::min<size_t>(16, px / 640000)) : 1);
+    if (const char* nb = getenv("VXL_HOST_BANDS")) { if (*nb) NB = std::max(1, std::min(64, atoi(nb))); }   // tuning knob
     if (by_tiles) NB = std::min(NB, nt);
     const int band_h = ((a->frame.tile_h + NB - 1) / NB + 15) / 16 * 16;          // whole 16-row thread blocks
     const int band_t = (nt + NB - 1) / NB;
@@ -544,7 +546,7 @@ static int lighting_host_impl(vxl_ctx* c, vxl_volume* vol, const vxl_lighting_ho
                 }
             }
             c->stream = main;
-            if (packed) { VXL_CUDA(cudaEventRecord(eb[1], sl)); VXL_CUDA(cudaStreamWaitEvent(main, eb[1], 0)); }
+            if (packed) { VXL_CUDA(cudaEventRecord(eb[1], sl)); VXL_CUDA(cudaStreamWaitEvent(c->s_d2h, eb[1], 0)); }
         }
         if (want_rf) {
             VXL_CUDA(cudaStreamWaitEvent(sr, eb[0], 0));
@@ -555,16 +557,16 @@ static int lighting_host_impl(vxl_ctx* c, vxl_volume* vol, const vxl_lighting_ho
             if (!packed) {
                 VXL_CUDA(cudaEventRecord(eb[4], sr)); VXL_CUDA(cudaStreamWaitEvent(c->s_d2h, eb[4], 0));
                 VXL_CUDA(copy_band(a->out_spec_t, o_spec, 4, cudaMemcpyDeviceToHost, c->s_d2h));
-            } else { VXL_CUDA(cudaEventRecord(eb[4], sr)); VXL_CUDA(cudaStreamWaitEvent(main, eb[4], 0)); }
+            } else { VXL_CUDA(cudaEventRecord(eb[4], sr)); VXL_CUDA(cudaStreamWaitEvent(c->s_d2h, eb[4], 0)); }
         }
-        if (packed && (want_mask || want_rf)) {                           // behind all three pass streams (joined into `main` above)
+        if (packed && (want_mask || want_rf)) {                           // on the read-back stream, behind all three pass streams (joined into it above):
+                                                                          // the next band's passes do not wait for this band's packing
             const int prow0 = by_tiles ? 0 : r0, prows = by_tiles ? a->frame.tile_h : rows, pnt = by_tiles ? tn : nt;
             const size_t n = (size_t)prows * a->frame.tile_w * (size_t)pnt;
-            k_pack_planes<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(want_sun ? o_shadow + bo : nullptr, o_pt + bo, want_pt ? a->n_point : 0, o_sp + bo, want_sp ? a->n_spot : 0, px,
+            k_pack_planes<<<(unsigned)((n + 255) / 256), 256, 0, c->s_d2h>>>(want_sun ? o_shadow + bo : nullptr, o_pt + bo, want_pt ? a->n_point : 0, o_sp + bo, want_sp ? a->n_spot : 0, px,
                                                                          o_spec + bo, want_mask ? o_mask + bo * (size_t)mask_bytes : nullptr, mask_bytes, want_rf ? o_code + bo : nullptr,
                                                                          a->frame.tile_w, a->frame.tile_h, prow0, prows, pnt, a->frame.width, a->frame.height, fd.tile_first, fd.tile_stride);
             VXL_LAUNCH_CHECK(c);
-            VXL_CUDA(cudaEventRecord(eb[5], main)); VXL_CUDA(cudaStreamWaitEvent(c->s_d2h, eb[5], 0));
             if (want_mask) VXL_CUDA(copy_band(packed->shadow_mask, o_mask, (size_t)mask_bytes, cudaMemcpyDeviceToHost, c->s_d2h));
             if (want_rf) VXL_CUDA(copy_band(packed->spec_code, o_code, 1, cudaMemcpyDeviceToHost, c->s_d2h));
         }
