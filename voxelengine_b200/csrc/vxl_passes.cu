@@ -57,6 +57,11 @@ constexpr size_t smem_bytes() {
 #ifndef VXL_AMB_STATIC
 #define VXL_AMB_STATIC 1
 #endif
+// The one-ray passes place their tile from a SAMPLE of the region's pixels: every VXL_PREPASS_STRIDE-th work item (the boxes carry
+// +-20 voxels of slack and every ray still checks its own eligibility, so a pixel the sample missed at worst takes the plain march).
+#ifndef VXL_PREPASS_STRIDE
+#define VXL_PREPASS_STRIDE 4
+#endif
 #ifndef VXL_PASS_TY
 #define VXL_PASS_TY (VXL_PASS_BLOCKS >= 3 ? 68 : 80)
 #endif
@@ -131,6 +136,14 @@ __device__ __forceinline__ BitTile block_prologue(const VolView& V, BlockShared<
 
 constexpr int NWARPS = BLOCK_THREADS / 32;
 
+// j-th item of the tile-placement sample of a region: every S-th item of each row of items, staggered from row to row (S = 1, or a
+// region too small to sample: every item)
+template <typename RG>
+struct PlaceSample {
+    static constexpr int S = (RG::ITEMS >= 4 * NWARPS && RG::ITEMS_X % VXL_PREPASS_STRIDE == 0) ? VXL_PREPASS_STRIDE : 1;
+    static constexpr int COUNT = RG::ITEMS / S, PER_ROW = RG::ITEMS_X / S;
+    __device__ __forceinline__ static int item(int j) { const int row = j / PER_ROW; return row * RG::ITEMS_X + (j - row * PER_ROW) * S + (row % S); }
+};
 // the next work item of the region for this warp (>= REGION_ITEMS: none left)
 template <typename BS>
 __device__ __forceinline__ int next_item(BS& S) {
@@ -541,8 +554,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_local_lights
     // (min(hitDist, 164) + 1 voxels along a unit direction; hitDist = 10.5 |L| world units = 1.05 x the way to the light).
     Box3 box;
     bool any = false;
-    for (int item = warp; item < RG::ITEMS; item += NWARPS) {
-        const PixelCtx p = item_pixel<RG>(F, K, R, item);
+    for (int j = warp; j < PlaceSample<RG>::COUNT; j += NWARPS) {
+        const PixelCtx p = item_pixel<RG>(F, K, R, PlaceSample<RG>::item(j));
         if (!p.valid) continue;
         const float depth = unorm24(__ldg(F.depth24 + p.idx));
         if (!(depth < 0.999f)) continue;
@@ -641,8 +654,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_PASS_BLOCKS) k_reflection(c
     // jitter (:96) bends it by at most a tenth
     Box3 box;
     bool any = false;
-    for (int item = warp; item < RG::ITEMS; item += NWARPS) {
-        const ReflPixel a = reflection_pixel(F, K, item_pixel<RG>(F, K, R, item));
+    for (int j = warp; j < PlaceSample<RG>::COUNT; j += NWARPS) {
+        const ReflPixel a = reflection_pixel(F, K, item_pixel<RG>(F, K, R, PlaceSample<RG>::item(j)));
         if (!a.lit) continue;
         any = true;
         const float3 o = a.wcp0 + a.normal, e = o + a.wd * 210.0f;
