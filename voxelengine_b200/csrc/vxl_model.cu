@@ -166,13 +166,18 @@ __global__ void __launch_bounds__(256) k_gbuffer_models(FrameView F, GeomK K, co
             const DrawDev& d = draws[c];
             float mnx = 3.0e38f, mny = 3.0e38f, mxx = -3.0e38f, mxy = -3.0e38f;
             bool keep = false;
+            int behind = 0;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const float4 cp = mat_mul(d.mvp, make_float4((k & 1) ? d.size[0] * 0.1f : 0.0f, (k & 2) ? d.size[1] * 0.1f : 0.0f, (k & 4) ? d.size[2] * 0.1f : 0.0f, 1.0f));
                 if (!(cp.w > 1.0e-3f)) keep = true;                                             // also catches NaN
+                behind += cp.w < -1.0e-2f ? 1 : 0;
                 const float sx = (cp.x / cp.w * 0.5f + 0.5f) * (float)F.width - 0.5f, sy = (0.5f - cp.y / cp.w * 0.5f) * (float)F.height - 0.5f;
                 mnx = fminf(mnx, sx); mxx = fmaxf(mxx, sx); mny = fminf(mny, sy); mxy = fmaxf(mxy, sy);
             }
+            // clip w is the view depth, linear over the box: with all 8 corners clearly behind the camera plane the whole box is, and
+            // a pixel's ray (w >= 0 along it) cannot enter it -- half of a scene's draws when the camera stands among them
+            if (behind == 8) continue;
             if (keep || !(mxx < bx0 || mnx > bx1 || mxy < by0 || mny > by1)) atomicOr(&s_draws[c >> 5], 1u << (c & 31));
         }
     }

@@ -62,12 +62,21 @@ constexpr size_t smem_bytes() {
 #ifndef VXL_PREPASS_STRIDE
 #define VXL_PREPASS_STRIDE 4
 #endif
+#ifndef VXL_AMB_GH
+#define VXL_AMB_GH 7
+#endif
+#ifndef VXL_LOCAL_GH
+#define VXL_LOCAL_GH 7
+#endif
+#ifndef VXL_REFL_GH
+#define VXL_REFL_GH 10
+#endif
 #ifndef VXL_PASS_TY
 #define VXL_PASS_TY (VXL_PASS_BLOCKS >= 3 ? 68 : 80)
 #endif
-struct AmbientGeom { static constexpr int SHIFT = 2, TY = 76, TW = 3, DT = 39, DW = 2, GH = 7, QCAP = VXL_AO_QCAP; static constexpr bool NEAR = true; };     // +-152 voxels in y and z (AO 128, sun 128)
-struct LocalGeom   { static constexpr int SHIFT = 2, TY = VXL_PASS_TY, TW = 3, DT = VXL_PASS_TY / 2 + 1, DW = 2, GH = 7, QCAP = 0; static constexpr bool NEAR = false; };    // point/spot rays that leave the window take the plain march
-struct ReflGeom    { static constexpr int SHIFT = 3, TY = VXL_PASS_TY, TW = 3, DT = VXL_PASS_TY / 2 + 1, DW = 2, GH = 10, QCAP = 0; static constexpr bool NEAR = false; };   // 8-voxel cells (164 steps * |wd| <= 1.5)
+struct AmbientGeom { static constexpr int SHIFT = 2, TY = 76, TW = 3, DT = 39, DW = 2, GH = VXL_AMB_GH, QCAP = VXL_AO_QCAP; static constexpr bool NEAR = true; };     // +-152 voxels in y and z (AO 128, sun 128)
+struct LocalGeom   { static constexpr int SHIFT = 2, TY = VXL_PASS_TY, TW = 3, DT = VXL_PASS_TY / 2 + 1, DW = 2, GH = VXL_LOCAL_GH, QCAP = 0; static constexpr bool NEAR = false; };    // point/spot rays that leave the window take the plain march
+struct ReflGeom    { static constexpr int SHIFT = 3, TY = VXL_PASS_TY, TW = 3, DT = VXL_PASS_TY / 2 + 1, DW = 2, GH = VXL_REFL_GH, QCAP = 0; static constexpr bool NEAR = false; };   // 8-voxel cells (164 steps * |wd| <= 1.5)
 
 // Bounding box of the block's rays -> tile placement -> stage the occupancy tile.
 // [flo, fhi] is (close to) the box the thread's rays stay in, [nlo, nhi] the box of their first 20 voxels, in voxel units; threads
