@@ -203,9 +203,11 @@ int vxl_group_destroy(vxl_group* g);
  * were answered by a clear occupancy bit). */
 int vxl_debug_set_variant(vxl_ctx* ctx, int variant);
 int vxl_debug_fetched_probes(vxl_ctx* ctx, uint64_t* out /* HOST */);
-/* download one occupancy level unpacked to 0/1 bytes [cz][cy][cx]: level 2, 3, 4 = plain (cell = 2^level
- * voxels), 13, 14 = the 3x3x3-dilated levels 3, 4 including their 1-cell border; out_dims = {cx, cy, cz};
- * host_out may be NULL */
+/* download one occupancy level unpacked to 0/1 bytes [cz][cy][cx]: level 1 = texels, 2, 3, 4 = plain (cell = 2^level
+ * voxels), 13, 14 = the 3x3x3-dilated levels 3, 4 including their 1-cell border, 22 = level 2 decoded from its copy shifted
+ * by 16 cells (what a TMA box at an odd origin reads); out_dims = {cx, cy, cz}; host_out may be NULL.
+ * The levels are rebuilt lazily by the next pass (or vxl_volume_build_occupancy): in full after an upload, inside the
+ * commands' voxel boxes only after a vxl_volume_voxelize call on levels that were up to date. */
 int vxl_volume_debug_occupancy(vxl_volume* vol, int level, uint8_t* host_out /* HOST */, int* out_dims /* HOST[3] */);
 /* measurement helper (bench.py's roofline denominators, SURVEY 8d: "L2 read bandwidth ... measured by a microbench in the bench
  * harness"): read a `bytes`-sized device buffer `reps` times with 16-byte loads from every SM (one warm-up pass first) and report

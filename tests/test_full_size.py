@@ -201,6 +201,14 @@ def test_config4_sixty_frames_of_revoxelisation(gpu_ctx, oracle):
             sz, sy, sx = host.shape
             want_occ = (host.reshape(sz // 2, 2, sy // 2, 2, sx // 2, 2).max(axis=(1, 3, 5)) != 0).astype(np.uint8)
             assert np.array_equal(occ, want_occ), f"frame {t}: rebuilt occupancy level differs from the volume"
+            # the levels were rebuilt inside the commands' boxes only (vxl_occupancy.cu: k_occ_boxes): every level, the dilated ones and
+            # the shifted copy must equal a full rebuild from the same bytes
+            levels = (1, 2, 3, 4, 13, 14, 22)
+            partial = [wl.vol.occupancy(l) for l in levels]
+            wl.vol.mark_dirty()
+            for l, a in zip(levels, partial):
+                assert np.array_equal(a, wl.vol.occupancy(l)), f"frame {t}: level {l} after the box rebuild differs from a full rebuild"
+            assert np.array_equal(partial[1], partial[6]), f"frame {t}: the shifted copy of level 2 differs from level 2"
             gbh = gbh or _host_gb(wl)
             sh, ao, s1 = oracle.pass_ambient(host, wl.view, gbh, wl.n_ao)
             _assert_planes([(f"shadow@{t}", got[0], sh), (f"ao@{t}", got[1], ao)])

@@ -80,6 +80,7 @@ struct vxl_ctx {
     vxl_entity* d_ents = nullptr;
     int* d_aabb = nullptr;                   // [n][6]
     int ents_cap = 0;
+    unsigned long long aabb_gen = 0;         // bumped by every voxelise call (they share the scratch block)
     // host drop-in scratch
     uint32_t* h_planes = nullptr;            // device buffers for vxl_lighting_host
     size_t h_planes_bytes = 0;
@@ -101,6 +102,12 @@ struct vxl_volume {
     int sx = 0, sy = 0, sz = 0;
     uint8_t* d_bytes = nullptr;
     bool dirty = true;
+    // dirty, the levels exist, and everything that changed since they were built lies inside the boxes of the last voxelise call
+    // (device, [n][6] voxel coordinates in the context's scratch block, valid while the context's aabb_gen still equals dirty_gen)
+    bool dirty_partial = false;
+    const int* dirty_boxes = nullptr;
+    int n_dirty_boxes = 0;
+    unsigned long long dirty_gen = 0;
     vxl::BitLevel tex;                   // occupancy bitmask at texel (2-voxel) cells
     vxl::BitLevel occ[3];                // occupancy bitmasks at 4-, 8-, 16-voxel cells
     vxl::BitLevel dil[2];                // 3x3x3-dilated bitmasks at 8-, 16-voxel cells

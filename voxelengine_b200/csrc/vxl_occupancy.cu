@@ -35,12 +35,7 @@ __device__ __forceinline__ uint32_t nonzero_bytes4(uint32_t v) {        // bit i
     const uint32_t m = (v | ((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu)) & 0x80808080u;
     return ((m >> 7) & 1u) | ((m >> 14) & 2u) | ((m >> 21) & 4u) | ((m >> 28) & 8u);
 }
-__global__ void __launch_bounds__(256) k_occ_texels(const uint8_t* __restrict__ bytes, int sx, int sy, int sz,
-                                                    int xw, int cyp, int cz, int border, uint32_t* __restrict__ out) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)xw * cyp * cz;
-    if (i >= total) return;
-    const int ay = (int)(i % cyp), w = (int)((i / cyp) % xw), az = (int)(i / ((long long)cyp * xw));
+__device__ __forceinline__ uint32_t texel_word(const uint8_t* __restrict__ bytes, int sx, int sy, int sz, int border, int w, int ay, int az) {
     // Texel -1 of every axis repeats texel 0: the reference truncates toward zero (ivec3(pos / 2), ivec3(pos) / 2), so a probe at a
     // coordinate in (-2, 0) reads texel 0.  With floor(pos / 2) = -1 there, the repeated texel gives the same answer, and the
     // coarser levels built from this one inherit it (cell -1 = texel -1 | texel -2 = texel 0).  Everything further out is empty.
@@ -65,17 +60,20 @@ __global__ void __launch_bounds__(256) k_occ_texels(const uint8_t* __restrict__ 
             }
         }
     }
-    out[i] = word;
+    return word;
 }
-
-// coarser plain level from a finer one: bit c = OR of the 2x2x2 child cells.  border_fine = 2 * border_coarse, so array index
-// a of the coarse level has the children 2a, 2a + 1 of the fine array on every axis.
-__global__ void __launch_bounds__(256) k_occ_coarsen(const uint32_t* __restrict__ fine, int fcy, int fcz, int fxw, int fcyp,
-                                                     int xw, int cyp, int cz, uint32_t* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_occ_texels(const uint8_t* __restrict__ bytes, int sx, int sy, int sz,
+                                                    int xw, int cyp, int cz, int border, uint32_t* __restrict__ out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)xw * cyp * cz;
     if (i >= total) return;
     const int ay = (int)(i % cyp), w = (int)((i / cyp) % xw), az = (int)(i / ((long long)cyp * xw));
+    out[i] = texel_word(bytes, sx, sy, sz, border, w, ay, az);
+}
+
+// coarser plain level from a finer one: bit c = OR of the 2x2x2 child cells.  border_fine = 2 * border_coarse, so array index
+// a of the coarse level has the children 2a, 2a + 1 of the fine array on every axis.
+__device__ __forceinline__ uint32_t coarsen_word(const uint32_t* __restrict__ fine, int fcy, int fcz, int fxw, int fcyp, int w, int ay, int az) {
     uint32_t word = 0;
     for (int dz = 0; dz < 2; ++dz)
         for (int dy = 0; dy < 2; ++dy) {
@@ -92,16 +90,20 @@ __global__ void __launch_bounds__(256) k_occ_coarsen(const uint32_t* __restrict_
                 word |= v << (16 * h);
             }
         }
-    out[i] = word;
+    return word;
 }
-
-// dilated level (array index = input array index + 1): OR over the 3x3x3 neighbourhood of the plain level
-__global__ void __launch_bounds__(256) k_occ_dilate(const uint32_t* __restrict__ in, int icy, int icz, int ixw, int icyp,
-                                                    int xw, int cyp, int cz, uint32_t* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_occ_coarsen(const uint32_t* __restrict__ fine, int fcy, int fcz, int fxw, int fcyp,
+                                                     int xw, int cyp, int cz, uint32_t* __restrict__ out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)xw * cyp * cz;
     if (i >= total) return;
-    const int w = (int)((i / cyp) % xw), y = (int)(i % cyp) - 1, z = (int)(i / ((long long)cyp * xw)) - 1;   // input array coords
+    const int ay = (int)(i % cyp), w = (int)((i / cyp) % xw), az = (int)(i / ((long long)cyp * xw));
+    out[i] = coarsen_word(fine, fcy, fcz, fxw, fcyp, w, ay, az);
+}
+
+// dilated level (array index = input array index + 1): OR over the 3x3x3 neighbourhood of the plain level
+__device__ __forceinline__ uint32_t dilate_word(const uint32_t* __restrict__ in, int icy, int icz, int ixw, int icyp, int w, int oy, int oz) {
+    const int y = oy - 1, z = oz - 1;                                      // input array coords
     // output bit b of word w is input x = 32*w + b - 1; gather input bits x-1, x, x+1 = input positions 32*w + b - 2 .. 32*w + b
     uint32_t word = 0;
     for (int dz = -1; dz <= 1; ++dz)
@@ -113,7 +115,14 @@ __global__ void __launch_bounds__(256) k_occ_dilate(const uint32_t* __restrict__
             // input position p = 32*w + b - s for s = 0, 1, 2  ->  (cur << s) | (prev >> (32 - s))
             word |= cur | (cur << 1) | (prev >> 31) | (cur << 2) | (prev >> 30);
         }
-    out[i] = word;
+    return word;
+}
+__global__ void __launch_bounds__(256) k_occ_dilate(const uint32_t* __restrict__ in, int icy, int icz, int ixw, int icyp,
+                                                    int xw, int cyp, int cz, uint32_t* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)xw * cyp * cz;
+    if (i >= total) return;
+    out[i] = dilate_word(in, icy, icz, ixw, icyp, (int)((i / cyp) % xw), (int)(i % cyp), (int)(i / ((long long)cyp * xw)));
 }
 
 // second copy of a level, shifted by 16 cells along x: bit (ax + 16) & 31 of word (ax + 16) >> 5.  A TMA box starts on a word
@@ -124,6 +133,41 @@ __global__ void __launch_bounds__(256) k_occ_shift16(const uint32_t* __restrict_
     if (i >= total) return;
     const int w = (int)((i / cyp) % xw);
     out[i] = (in[i] << 16) | (w >= 1 ? in[i - cyp] >> 16 : 0u);          // the word before along x is cyp words back
+}
+
+// ---- the same levels, rebuilt only where the volume changed -------------------------------------------------------------------
+// After a voxelise call the volume differs from the levels inside the entities' voxel boxes only (vxl_volume.cu keeps a tight box
+// per command next to the reference's dirty regions).  One block row per box: the words of the level whose cells meet the box
+// are recomputed by the very functions above, level after level, so the arrays end up identical to a full rebuild.
+//   sh:    cell of the level = 2^sh texels (0 texel level, 1..3 plain levels; dilated levels: that of their plain level)
+//   KIND:  0 texel level, 1 coarsen, 2 the shifted copy, 3 dilate (array index + 1, neighbourhood +-1)
+struct BoxLevel { int sx, sy, sz; int sh; int xw, cyp, cy, cz; int fcy, fcz, fxw, fcyp; };
+template <int KIND>
+__global__ void __launch_bounds__(256) k_occ_boxes(const int* __restrict__ boxes, BoxLevel P, const void* __restrict__ src, uint32_t* __restrict__ out) {
+    const int* b = boxes + (size_t)blockIdx.y * 6;
+    int lo[3], hi[3];
+    const int lim[3] = {P.sx, P.sy, P.sz};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const int mn = b[a], mx = b[3 + a];                                 // voxels, inclusive; an untouched command keeps mn > mx
+        if (mn > mx || mx < 0 || mn >= 2 * lim[a]) return;
+        const int t0 = max(mn >> 1, 0) - 1 + 96, t1 = min(mx >> 1, lim[a] - 1) + 96;    // texel-array indices; -1: the repeated texel
+        lo[a] = (t0 >> P.sh) + (KIND == 3 ? 0 : 0);
+        hi[a] = (t1 >> P.sh) + (KIND == 3 ? 2 : 0);
+    }
+    const int w0 = lo[0] >> 5, w1 = min((hi[0] >> 5) + (KIND == 2 ? 1 : 0), P.xw - 1);
+    const int y0 = lo[1], y1 = min(hi[1], P.cyp - 1), z0 = lo[2], z1 = min(hi[2], P.cz - 1);
+    const int nW = w1 - w0 + 1, nY = y1 - y0 + 1, nZ = z1 - z0 + 1;
+    if (nW <= 0 || nY <= 0 || nZ <= 0) return;
+    const int total = nW * nY * nZ;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int ay = y0 + i % nY, w = w0 + (i / nY) % nW, az = z0 + i / (nY * nW);
+        const size_t o = level_index(P.xw, P.cyp, w, ay, az);
+        if (KIND == 0) out[o] = texel_word((const uint8_t*)src, P.sx, P.sy, P.sz, 96, w, ay, az);
+        else if (KIND == 1) out[o] = coarsen_word((const uint32_t*)src, P.fcy, P.fcz, P.fxw, P.fcyp, w, ay, az);
+        else if (KIND == 2) { const uint32_t* in = (const uint32_t*)src; out[o] = (in[o] << 16) | (w >= 1 ? in[o - P.cyp] >> 16 : 0u); }
+        else out[o] = dilate_word((const uint32_t*)src, P.fcy, P.fcz, P.fxw, P.fcyp, w, ay, az);
+    }
 }
 
 // ncx, ncy, ncz: cells of the level proper; border: zero cells added on every side; copies: 1, or 2 = also the copy shifted by 16 cells
@@ -196,6 +240,34 @@ int vxl_volume_build_occupancy(vxl_volume* v) {
             if (int e = alloc_level(v->dil[li], P.shift, P.cx - 2 * P.border, P.cy - 2 * P.border, P.cz - 2 * P.border, P.border + 1)) return e;
         }
     }
+    if (v->dirty_partial && v->n_dirty_boxes > 0 && v->occ[0].d_words && v->dirty_gen == c->aabb_gen) {
+        // the levels exist and only the boxes of the last voxelise call changed
+        const dim3 grid(4u, (unsigned)v->n_dirty_boxes);
+        auto params = [&](const BitLevel& L, int sh, const BitLevel* F) {
+            BoxLevel P{v->sx, v->sy, v->sz, sh, L.xw, L.cyp, L.cy, L.cz, F ? F->cy : 0, F ? F->cz : 0, F ? F->xw : 0, F ? F->cyp : 0};
+            return P;
+        };
+        k_occ_boxes<0><<<grid, 256, 0, c->stream>>>(v->dirty_boxes, params(v->tex, 0, nullptr), v->d_bytes, v->tex.d_words);
+        VXL_LAUNCH_CHECK(c);
+        for (int li = 0; li < 3; ++li) {
+            const BitLevel& F = li ? v->occ[li - 1] : v->tex;
+            BitLevel& L = v->occ[li];
+            k_occ_boxes<1><<<grid, 256, 0, c->stream>>>(v->dirty_boxes, params(L, li + 1, &F), F.d_words, L.d_words);
+            VXL_LAUNCH_CHECK(c);
+            if (L.copies == 2) {
+                k_occ_boxes<2><<<grid, 256, 0, c->stream>>>(v->dirty_boxes, params(L, li + 1, nullptr), L.d_words, L.d_words + (size_t)L.xw * L.cyp * L.cz);
+                VXL_LAUNCH_CHECK(c);
+            }
+        }
+        for (int li = 0; li < 2; ++li) {
+            const BitLevel& Pl = v->occ[1 + li];
+            BitLevel& D = v->dil[li];
+            k_occ_boxes<3><<<grid, 256, 0, c->stream>>>(v->dirty_boxes, params(D, li + 2, &Pl), Pl.d_words, D.d_words);
+            VXL_LAUNCH_CHECK(c);
+        }
+        v->dirty = false; v->dirty_partial = false;
+        return VXL_OK;
+    }
     auto grid_of = [](const BitLevel& L) { return (unsigned)(((long long)L.xw * L.cyp * L.cz + 255) / 256); };
     BitLevel& L1 = v->tex;
     k_occ_texels<<<grid_of(L1), 256, 0, c->stream>>>(v->d_bytes, v->sx, v->sy, v->sz, L1.xw, L1.cyp, L1.cz, L1.border, L1.d_words);
@@ -216,13 +288,15 @@ int vxl_volume_build_occupancy(vxl_volume* v) {
         k_occ_dilate<<<grid_of(D), 256, 0, c->stream>>>(P.d_words, P.cy, P.cz, P.xw, P.cyp, D.xw, D.cyp, D.cz, D.d_words);
         VXL_LAUNCH_CHECK(c);
     }
-    v->dirty = false;
+    v->dirty = false; v->dirty_partial = false;
     return VXL_OK;
 }
 
 /* diagnostics: download one occupancy level unpacked to 0/1 bytes [cz][cy][cx]; level = 1, 2, 3, 4 (plain, cell =
  * 2^level voxels) or 13, 14 (dilated levels 3, 4, including their 1-cell border); out_dims = {cx, cy, cz} */
 int vxl_volume_debug_occupancy(vxl_volume* v, int level, uint8_t* host_out, int* out_dims) {
+    const bool shifted = level == 22;                        // level 2 read back from its copy shifted by 16 cells (what TMA boxes at odd origins see)
+    if (shifted) level = 2;
     if (!v || !((level >= 1 && level <= 4) || level == 13 || level == 14)) { set_error("vxl_volume_debug_occupancy: bad argument"); return VXL_ERR_INVALID; }
     if (v->dirty || !v->occ[0].d_words) { if (int e = vxl_volume_build_occupancy(v)) return e; }
     const BitLevel& L = level == 1 ? v->tex : (level < 10 ? v->occ[level - 2] : v->dil[level - 13]);
@@ -233,12 +307,13 @@ int vxl_volume_debug_occupancy(vxl_volume* v, int level, uint8_t* host_out, int*
     if (!host_out) return VXL_OK;
     const size_t words = (size_t)L.xw * L.cyp * L.cz;
     std::vector<uint32_t> h(words);
-    VXL_CUDA(cudaMemcpyAsync(h.data(), L.d_words, words * 4, cudaMemcpyDeviceToHost, v->ctx->stream));
+    if (shifted && L.copies != 2) { set_error("vxl_volume_debug_occupancy: level 2 has no shifted copy"); return VXL_ERR_INVALID; }
+    VXL_CUDA(cudaMemcpyAsync(h.data(), L.d_words + (shifted ? words : 0), words * 4, cudaMemcpyDeviceToHost, v->ctx->stream));
     VXL_CUDA(cudaStreamSynchronize(v->ctx->stream));
     for (int z = 0; z < nz; ++z)
         for (int y = 0; y < ny; ++y)
             for (int x = 0; x < nx; ++x) {
-                const int ax = x + skip, ay = y + skip, az = z + skip;
+                const int ax = x + skip + (shifted ? 16 : 0), ay = y + skip, az = z + skip;
                 host_out[((size_t)z * ny + y) * nx + x] = (uint8_t)((h[((size_t)az * L.xw + (ax >> 5)) * L.cyp + ay] >> (ax & 31)) & 1u);
             }
     return VXL_OK;

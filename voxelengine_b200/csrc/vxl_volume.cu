@@ -48,16 +48,18 @@ VXL_DI unsigned long long mix64(unsigned long long k) {
     return k;
 }
 
-__global__ void k_vox_init(VoxDims D, int n, int* __restrict__ aabb) {
+__global__ void k_vox_init(VoxDims D, int n, int* __restrict__ aabb, int* __restrict__ tight) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
+    tight[e * 6 + 0] = tight[e * 6 + 1] = tight[e * 6 + 2] = 0x7fffffff;                     // the box of what the command really wrote
+    tight[e * 6 + 3] = tight[e * 6 + 4] = tight[e * 6 + 5] = -0x7fffffff - 1;
     aabb[e * 6 + 0] = D.sx - 1; aabb[e * 6 + 1] = D.sy - 1; aabb[e * 6 + 2] = D.sz - 1;   // startmin (:128, texel units, sic)
     aabb[e * 6 + 3] = 0; aabb[e * 6 + 4] = 0; aabb[e * 6 + 5] = 0;                        // startmax
 }
 
 __global__ void __launch_bounds__(256) k_vox_emit(VoxDims D, const ModelDev* __restrict__ models, const vxl_entity* __restrict__ ents,
                                                   unsigned long long* __restrict__ keys, unsigned* __restrict__ vals,
-                                                  unsigned long long mask, int* __restrict__ aabb) {
+                                                  unsigned long long mask, int* __restrict__ aabb, int* __restrict__ tight) {
     const int e = blockIdx.y >> 1, phase = blockIdx.y & 1;
     const vxl_entity& en = ents[e];
     const bool destroy = (en.flags & VXL_ENT_DESTROY) != 0;
@@ -90,6 +92,10 @@ __global__ void __launch_bounds__(256) k_vox_emit(VoxDims D, const ModelDev* __r
     if ((threadIdx.x & 31) == 0 && mnx != 0x7fffffff) {
         atomicMin(&aabb[e * 6 + 0], mnx); atomicMin(&aabb[e * 6 + 1], mny); atomicMin(&aabb[e * 6 + 2], mnz);
         atomicMax(&aabb[e * 6 + 3], mxx); atomicMax(&aabb[e * 6 + 4], mxy); atomicMax(&aabb[e * 6 + 5], mxz);
+        // the same box without the reference's start values (:128 seeds the minimum with the TEXEL extent): what the occupancy
+        // levels have to be rebuilt for (vxl_occupancy.cu)
+        atomicMin(&tight[e * 6 + 0], mnx); atomicMin(&tight[e * 6 + 1], mny); atomicMin(&tight[e * 6 + 2], mnz);
+        atomicMax(&tight[e * 6 + 3], mxx); atomicMax(&tight[e * 6 + 4], mxy); atomicMax(&tight[e * 6 + 5], mxz);
     }
 }
 
@@ -314,7 +320,7 @@ int vxl_volume_create(vxl_ctx* ctx, int sx, int sy, int sz, vxl_volume** out) {
     cudaError_t e = cudaMalloc(&v->d_bytes, padded_bytes(v));
     if (e != cudaSuccess) { delete v; return cuda_fail(e, "cudaMalloc(volume)"); }
     VXL_CUDA(cudaMemsetAsync(v->d_bytes, 0, padded_bytes(v), ctx->stream));   // ShadowVoxSystem.cpp:66-70
-    v->dirty = true;
+    v->dirty = true; v->dirty_partial = false;
     *out = v;
     return VXL_OK;
 }
@@ -355,14 +361,14 @@ int vxl_volume_upload_regions(vxl_volume* v, const uint8_t* host, const vxl_regi
         p.kind = cudaMemcpyHostToDevice;
         VXL_CUDA(cudaMemcpy3DAsync(&p, v->ctx->stream));
     }
-    if (n > 0) v->dirty = true;
+    if (n > 0) { v->dirty = true; v->dirty_partial = false; }
     return VXL_OK;
 }
 
 int vxl_volume_upload(vxl_volume* v, const uint8_t* host) {
     if (!v || !host) { set_error("vxl_volume_upload: bad argument"); return VXL_ERR_INVALID; }
     VXL_CUDA(cudaMemcpyAsync(v->d_bytes, host, (size_t)v->sx * v->sy * v->sz, cudaMemcpyHostToDevice, v->ctx->stream));
-    v->dirty = true;
+    v->dirty = true; v->dirty_partial = false;
     return VXL_OK;
 }
 
@@ -376,7 +382,7 @@ int vxl_volume_download(vxl_volume* v, uint8_t* host) {
 int vxl_volume_clear(vxl_volume* v) {
     if (!v) { set_error("vxl_volume_clear: vol is NULL"); return VXL_ERR_INVALID; }
     VXL_CUDA(cudaMemsetAsync(v->d_bytes, 0, padded_bytes(v), v->ctx->stream));
-    v->dirty = true;
+    v->dirty = true; v->dirty_partial = false;
     return VXL_OK;
 }
 
@@ -388,7 +394,7 @@ int vxl_volume_device_ptr(vxl_volume* v, uint8_t** out) {
 
 int vxl_volume_mark_dirty(vxl_volume* v) {
     if (!v) { set_error("vxl_volume_mark_dirty: vol is NULL"); return VXL_ERR_INVALID; }
-    v->dirty = true;
+    v->dirty = true; v->dirty_partial = false;
     return VXL_OK;
 }
 
@@ -425,7 +431,7 @@ int vxl_volume_voxelize(vxl_volume* v, const vxl_entity* ents, int n, vxl_region
         max_vox = std::max(max_vox, m.sx * m.sy * m.sz);
     }
     size_t cap = 4096;
-    while (cap < ops * 2) cap <<= 1;
+    while (cap * 2 < ops * 3) cap <<= 1;                 // load factor <= 2/3 if every write hit a different voxel (clear + set mostly overlap)
     if (cap > c->hcap) {
         if (c->d_hkeys) { VXL_CUDA(cudaStreamSynchronize(c->stream)); cudaFree(c->d_hkeys); cudaFree(c->d_hvals); c->d_hkeys = nullptr; c->d_hvals = nullptr; c->hcap = 0; }
         VXL_CUDA(cudaMalloc(&c->d_hkeys, cap * sizeof(unsigned long long)));
@@ -436,7 +442,7 @@ int vxl_volume_voxelize(vxl_volume* v, const vxl_entity* ents, int n, vxl_region
         if (c->d_ents) { VXL_CUDA(cudaStreamSynchronize(c->stream)); cudaFree(c->d_ents); cudaFree(c->d_aabb); c->d_ents = nullptr; c->d_aabb = nullptr; }
         // region/valid outputs live behind the aabb block: [n][6] ints, [n] regions, [n] valid
         VXL_CUDA(cudaMalloc(&c->d_ents, (size_t)n * sizeof(vxl_entity)));
-        VXL_CUDA(cudaMalloc(&c->d_aabb, (size_t)n * (6 * sizeof(int) + sizeof(vxl_region) + sizeof(int))));
+        VXL_CUDA(cudaMalloc(&c->d_aabb, (size_t)n * (12 * sizeof(int) + sizeof(vxl_region) + sizeof(int))));
         c->ents_cap = n;
     }
     if ((int)c->models.size() > c->d_models_cap) {
@@ -452,13 +458,15 @@ int vxl_volume_voxelize(vxl_volume* v, const vxl_entity* ents, int n, vxl_region
     int* d_aabb = c->d_aabb;
     vxl_region* d_regions = (vxl_region*)(d_aabb + (size_t)c->ents_cap * 6);
     int* d_valid = (int*)(d_regions + c->ents_cap);
-    k_vox_init<<<(n + 255) / 256, 256, 0, c->stream>>>(D, n, d_aabb);
+    int* d_tight = d_valid + c->ents_cap;
+    c->aabb_gen++;
+    k_vox_init<<<(n + 255) / 256, 256, 0, c->stream>>>(D, n, d_aabb, d_tight);
     VXL_LAUNCH_CHECK(c);
     const int bx = std::min(std::max((max_vox + 256 * 8 - 1) / (256 * 8), 1), 1024);
     // gridDim.y is limited to 65535: issue the command list in slabs (the sequence tag uses the global index)
     for (int e0 = 0; e0 < n; e0 += 32767) {
         const int ne = std::min(32767, n - e0);
-        k_vox_emit<<<dim3((unsigned)bx, (unsigned)(ne * 2)), 256, 0, c->stream>>>(D, c->d_models, c->d_ents + e0, c->d_hkeys, c->d_hvals, (unsigned long long)cap - 1, d_aabb + (size_t)e0 * 6);
+        k_vox_emit<<<dim3((unsigned)bx, (unsigned)(ne * 2)), 256, 0, c->stream>>>(D, c->d_models, c->d_ents + e0, c->d_hkeys, c->d_hvals, (unsigned long long)cap - 1, d_aabb + (size_t)e0 * 6, d_tight + (size_t)e0 * 6);
         VXL_LAUNCH_CHECK(c);
         if (n > 32767) {
             // sequence tags restart per slab, so resolve each slab before the next one is emitted
@@ -472,6 +480,10 @@ int vxl_volume_voxelize(vxl_volume* v, const vxl_entity* ents, int n, vxl_region
         k_vox_resolve<<<(unsigned)((cap + 255) / 256), 256, 0, c->stream>>>(D, c->d_hkeys, c->d_hvals, cap, (unsigned*)v->d_bytes);
         VXL_LAUNCH_CHECK(c);
     }
+    // levels that were up to date before this call only need the commands' boxes rebuilt (a second call before the rebuild, or a
+    // command list too long for one block row per box, falls back to the full rebuild)
+    v->dirty_partial = !v->dirty && v->occ[0].d_words != nullptr && n <= 16384;
+    v->dirty_boxes = d_tight; v->n_dirty_boxes = n; v->dirty_gen = c->aabb_gen;
     v->dirty = true;
     if (out_regions || out_valid) {
         k_vox_regions<<<(n + 255) / 256, 256, 0, c->stream>>>(D, n, d_aabb, d_regions, d_valid);
@@ -498,7 +510,7 @@ int vxl_volume_gen_terrain(vxl_volume* v) {
     VXL_LAUNCH_CHECK(c);
     VXL_CUDA(cudaStreamSynchronize(c->stream));
     VXL_CUDA(cudaFree(col2));
-    v->dirty = true;
+    v->dirty = true; v->dirty_partial = false;
     return VXL_OK;
 }
 

@@ -269,9 +269,13 @@ class ShadowVoxSystem:
     def build_occupancy(self):
         check(self.lib.vxl_volume_build_occupancy(self.h), "vxl_volume_build_occupancy")
 
+    def mark_dirty(self) -> None:
+        """The next pass rebuilds every occupancy level in full (vxl_volume_mark_dirty)."""
+        check(self.lib.vxl_volume_mark_dirty(self.h), "vxl_volume_mark_dirty")
+
     def occupancy(self, shift: int) -> np.ndarray:
         """Diagnostics: occupancy level as 0/1 uint8 [cz][cy][cx]; 2, 3, 4 = plain (cell = 2^level voxels),
-        13, 14 = 3x3x3-dilated levels 3, 4 including their 1-cell border."""
+        1 = texel level, 13, 14 = 3x3x3-dilated levels 3, 4 including their 1-cell border, 22 = level 2 decoded from its shifted copy."""
         dims = np.zeros(3, np.int32)
         check(self.lib.vxl_volume_debug_occupancy(self.h, int(shift), None, _np_ptr(dims)), "vxl_volume_debug_occupancy")
         out = np.zeros((dims[2], dims[1], dims[0]), np.uint8)
