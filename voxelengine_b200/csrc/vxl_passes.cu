@@ -62,6 +62,9 @@ constexpr size_t smem_bytes() {
 #ifndef VXL_PREPASS_STRIDE
 #define VXL_PREPASS_STRIDE 4
 #endif
+#ifndef VXL_AO_POOL_MIN
+#define VXL_AO_POOL_MIN 2            // fewer AO rays per pixel than this: per-lane scan + resolve (the pool needs rays to fill its passes)
+#endif
 #ifndef VXL_AMB_GH
 #define VXL_AMB_GH 7
 #endif
@@ -473,7 +476,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, VXL_AMBIENT_BLOCKS) k_ambient(c
     unsigned rays = 0, pixels = 0, exact = 0;
     int steps = 0;
     // the AO rays of tile-march launches go through the warp-pooled resolve (all 32 lanes take part, lit or not)
-    const bool POOL = MODE > 0 && G::QCAP > 0 && n_ao <= AO_POOL_MAX_RAYS;
+    const bool POOL = MODE > 0 && G::QCAP > 0 && n_ao <= AO_POOL_MAX_RAYS && n_ao >= VXL_AO_POOL_MIN;
     // ---- the region's 8x4-pixel work items, handed to whichever warp is free ----
     for (int item = STATIC ? warp : next_item(S); item < RG::ITEMS; item = STATIC ? RG::ITEMS : next_item(S)) {
         const PixelCtx p = STATIC ? p0 : item_pixel<RG>(F, K, R, item);
