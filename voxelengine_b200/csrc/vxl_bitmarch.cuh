@@ -25,6 +25,10 @@
 
 namespace vxl {
 
+#ifndef VXL_P1_UNROLL
+#define VXL_P1_UNROLL 2
+#endif
+constexpr int P1_UNROLL = VXL_P1_UNROLL;
 constexpr float BM_MARGIN = 0.125f;          // > accumulated rounding drift of <= 179 additions at |coords| < 8192
 constexpr float BM_MAXCOORD = 8191.0f;
 
@@ -195,12 +199,13 @@ VXL_DI bool warp_any(bool p) {
 // no data-dependent exit; the other lanes of the warp would have kept the issue slots busy anyway.  Every 8
 // probes the warp leaves early if no lane is live.  Use it when `dist` is warp-uniform.
 // COUNT: maintain `fetched` (diagnostic kernels only).
+// GU: unroll factor of the per-probe loop of a group that is not clear (3 divides both group sizes; measured per kernel).
 // GH > 0 (Sparse only): phase 2 runs in groups of 2*GH+1 probes; one test of the dilated level (cell = 2^(SHIFT+1)
 // voxels, tile [DT][DT][DW]) at the group's middle probe clears the whole group when it reads 0, because every probe
 // of the group is then within one dilated cell of the middle one (GH * max|stepDir_a| <= cell, checked per ray).
 // Skipped probes only advance the float recurrence.  Pays off for rays that are coherent across a warp (sun,
 // reflection, point-light shadows); a group that is not clear runs the per-probe loop.
-template <bool SUPER, bool RECORD, bool LOCKSTEP, bool COUNT, int SHIFT, int TY, int TW, int DT = 1, int DW = 1, int GH = 0>
+template <bool SUPER, bool RECORD, bool LOCKSTEP, bool COUNT, int SHIFT, int TY, int TW, int DT = 1, int DW = 1, int GH = 0, int GU = 1>
 VXL_DI float march_bits(const VolView& V, const BitTile& T, float3 origin, float3 dir, float dist, int& steps_out,
                         MarchResult* rec, unsigned& fetched) {
     constexpr float step0 = SUPER ? 2.5f : 0.5f;
@@ -235,7 +240,7 @@ VXL_DI float march_bits(const VolView& V, const BitTile& T, float3 origin, float
     // ---- phase 1 (:138-154): fine steps, position-hashed bit of the texel ----
     int hit1 = -1;
     unsigned hbit = 0u;
-#pragma unroll 2
+#pragma unroll (P1_UNROLL)
     for (int k = 0; k < n1; ++k) {
         if (A.test(pos) & live) {
             if (COUNT) ++fetched;
@@ -306,7 +311,7 @@ VXL_DI float march_bits(const VolView& V, const BitTile& T, float3 origin, float
                 continue;
             }
             pos = p0;
-#pragma unroll 1
+#pragma unroll (GU)
             for (int i = 0; i < G; ++i) {
                 if (probe2(j + i)) { done = true; break; }
                 pos = pos + stepDir;

@@ -42,6 +42,8 @@ constexpr size_t smem_bytes() {
 // Tile geometry per pass.  Plain tile: cells of 2^SHIFT voxels, TW*32 x TY x TY cells.  Dilated tile: cells of
 // 2^(SHIFT+1) voxels, DW*32 x DT x DT cells, covering at least the plain tile.  GH: half width of a probe group of the
 // Sparse march (GH * max|stepDir_a| must stay <= the dilated cell: 7 * 1.0 <= 8, 10 * 1.5 <= 16).
+// GU: unroll factor of the walk through a probe group the dilated level could not clear (reflection 1.23 -> 1.14 ms, point 0.36 -> 0.35 ms
+// with 3; the ambient kernel, whose sun ray is a fraction of its code, gets slower: 4.30 -> 4.37 ms).
 // NEAR: also stage the near tile (texel bits of the 64^3 voxels around the ray origins, 4 KB; vxl_bitmarch.cuh).
 // The plain tile is one TMA box of the level array (vxl_occupancy.cu; it lands ordered [x word][z][y]): TY cells along y starting
 // on a multiple of 4 cells, TY slices, and TW = 3 words (96 cells) along x starting on a word boundary of the array or of its copy
@@ -74,12 +76,18 @@ constexpr size_t smem_bytes() {
 #ifndef VXL_REFL_GH
 #define VXL_REFL_GH 10
 #endif
+#ifndef VXL_LOCAL_GU
+#define VXL_LOCAL_GU 3
+#endif
+#ifndef VXL_REFL_GU
+#define VXL_REFL_GU 3
+#endif
 #ifndef VXL_PASS_TY
 #define VXL_PASS_TY (VXL_PASS_BLOCKS >= 3 ? 68 : 80)
 #endif
-struct AmbientGeom { static constexpr int SHIFT = 2, TY = 76, TW = 3, DT = 39, DW = 2, GH = VXL_AMB_GH, QCAP = VXL_AO_QCAP; static constexpr bool NEAR = true; };     // +-152 voxels in y and z (AO 128, sun 128)
-struct LocalGeom   { static constexpr int SHIFT = 2, TY = VXL_PASS_TY, TW = 3, DT = VXL_PASS_TY / 2 + 1, DW = 2, GH = VXL_LOCAL_GH, QCAP = 0; static constexpr bool NEAR = false; };    // point/spot rays that leave the window take the plain march
-struct ReflGeom    { static constexpr int SHIFT = 3, TY = VXL_PASS_TY, TW = 3, DT = VXL_PASS_TY / 2 + 1, DW = 2, GH = VXL_REFL_GH, QCAP = 0; static constexpr bool NEAR = false; };   // 8-voxel cells (164 steps * |wd| <= 1.5)
+struct AmbientGeom { static constexpr int SHIFT = 2, TY = 76, TW = 3, DT = 39, DW = 2, GH = VXL_AMB_GH, GU = 1, QCAP = VXL_AO_QCAP; static constexpr bool NEAR = true; };     // +-152 voxels in y and z (AO 128, sun 128)
+struct LocalGeom   { static constexpr int SHIFT = 2, TY = VXL_PASS_TY, TW = 3, DT = VXL_PASS_TY / 2 + 1, DW = 2, GH = VXL_LOCAL_GH, GU = VXL_LOCAL_GU, QCAP = 0; static constexpr bool NEAR = false; };    // point/spot rays that leave the window take the plain march
+struct ReflGeom    { static constexpr int SHIFT = 3, TY = VXL_PASS_TY, TW = 3, DT = VXL_PASS_TY / 2 + 1, DW = 2, GH = VXL_REFL_GH, GU = VXL_REFL_GU, QCAP = 0; static constexpr bool NEAR = false; };   // 8-voxel cells (164 steps * |wd| <= 1.5)
 
 // Bounding box of the block's rays -> tile placement -> stage the occupancy tile.
 // [flo, fhi] is (close to) the box the thread's rays stay in, [nlo, nhi] the box of their first 20 voxels, in voxel units; threads
@@ -177,7 +185,7 @@ struct Box3 {
 // MODE: 0 plain march on the bytes, 1 tile march, 2 tile march that also counts the probes that read the volume
 template <int MODE, bool SUPER, bool UNIFORM, typename G>
 __device__ __forceinline__ float ray_march(const VolView& V, const BitTile& T, float3 origin, float3 dir, float dist, int& steps, unsigned& fetched) {
-    if (MODE > 0) return march_bits<SUPER, false, UNIFORM, MODE == 2, G::SHIFT, G::TY, G::TW, G::DT, G::DW, G::GH>(V, T, origin, dir, dist, steps, nullptr, fetched);
+    if (MODE > 0) return march_bits<SUPER, false, UNIFORM, MODE == 2, G::SHIFT, G::TY, G::TW, G::DT, G::DW, G::GH, G::GU>(V, T, origin, dir, dist, steps, nullptr, fetched);
     return march<false>(V, origin, dir, dist, SUPER ? 2.5f : 0.5f, steps, nullptr);
 }
 
