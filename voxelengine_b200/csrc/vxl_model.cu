@@ -123,6 +123,9 @@ struct DrawDev {                     // per draw, derived on the host like Geome
     ModelMips M;
 };
 constexpr int GEOM_MAX_DRAWS = 4096;   // GeometryVoxelPipeline MAX_INSTANCES
+#ifndef VXL_GEOM_BLOCKS
+#define VXL_GEOM_BLOCKS 4            // resident 256-thread blocks per SM k_gbuffer_models' registers are capped for
+#endif
 struct GeomK { float InvView[16], InvProj[16], PV[16], PVlast[16]; float cam[3], jit[2], ires[2], res[2]; int frame; };
 
 __device__ __forceinline__ uint32_t pack_unorm8x4(float a, float b, float c, float d) {
@@ -134,7 +137,7 @@ __device__ __forceinline__ uint32_t pack_snorm8x4(float a, float b, float c, flo
            (((uint32_t)(int)rintf(gclamp(c, -1.0f, 1.0f) * 127.0f) & 0xFFu) << 16) | (((uint32_t)(int)rintf(gclamp(d, -1.0f, 1.0f) * 127.0f) & 0xFFu) << 24);
 }
 
-__global__ void __launch_bounds__(256) k_gbuffer_models(FrameView F, GeomK K, const DrawDev* __restrict__ draws, int n_draws,
+__global__ void __launch_bounds__(256, VXL_GEOM_BLOCKS) k_gbuffer_models(FrameView F, GeomK K, const DrawDev* __restrict__ draws, int n_draws,
                                                         const uint32_t* __restrict__ pal_color, const uint32_t* __restrict__ pal_material,
                                                         uint32_t* __restrict__ depth24, uint32_t* __restrict__ normal, uint32_t* __restrict__ material,
                                                         uint32_t* __restrict__ albedo, float2* __restrict__ motion) {

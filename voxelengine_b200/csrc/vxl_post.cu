@@ -23,6 +23,13 @@
 namespace vxl {
 
 constexpr float NEAR_P = 0.1f;                // Common.frag:12
+#ifndef VXL_TAA_BLOCKS
+#define VXL_TAA_BLOCKS 2
+#endif
+#ifndef VXL_TAA_UNROLL
+#define VXL_TAA_UNROLL 3
+#endif
+constexpr int TAA_UNROLL = VXL_TAA_UNROLL;   // taps in flight per thread (more: spills at 64 registers)
 constexpr int TAA_TAPS = 12;                  // LightTAA.frag:96: radius runs 2..13 while radius <= size (12)
 
 struct FullView {
@@ -90,7 +97,7 @@ __global__ void __launch_bounds__(256) k_decode_depth(const uint32_t* __restrict
     if (i < n) out[i] = unorm24(__ldg(d24 + i));
 }
 
-__global__ void __launch_bounds__(BLOCK_THREADS, 2) k_light_taa(FrameView F, ViewK K, FullView P, const float2* __restrict__ g_cs /* [256][12] */,
+__global__ void __launch_bounds__(BLOCK_THREADS, VXL_TAA_BLOCKS) k_light_taa(FrameView F, ViewK K, FullView P, const float2* __restrict__ g_cs /* [256][12] */,
                                                              float4* __restrict__ out) {
     __shared__ float lut[512];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) { lut[i] = unorm8((uint32_t)i); lut[256 + i] = snorm8((uint32_t)i); }
@@ -129,7 +136,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_light_taa(FrameView F, Vie
     const uint32_t nz = get_noise(F, K, p, -1);
     const float2* cs = g_cs + (nz & 0xFFu) * TAA_TAPS;
     const float k2 = tclamp(0.1f, 0.5f, 1.0f / c.depth);                                      // :99 (sic: clamp(x = 0.1, 0.5, 1/depth))
-#pragma unroll 3
+#pragma unroll (TAA_UNROLL)
     for (int k = 0; k < TAA_TAPS; ++k) {                                                      // :96 radius <= size
         radius += 1.0f;
         const float2 a = __ldg(cs + k);

@@ -12,6 +12,10 @@
 #include "vxl_math.cuh"
 #include "vxl_pixel.cuh"
 
+#ifndef VXL_RESOLVE_BLOCKS
+#define VXL_RESOLVE_BLOCKS 3         // resident 512-thread blocks per SM the resolve kernels' registers are capped for
+#endif
+
 namespace vxl {
 
 constexpr float NEAR_ = 0.1f;                 // Common.frag:12
@@ -55,7 +59,7 @@ __device__ __forceinline__ float screenspace_occlusion(const ViewK& K, const uin
     return 0.0f;
 }
 
-__global__ void __launch_bounds__(BLOCK_THREADS) k_resolve_ambient(FrameView F, ViewK K, const float* __restrict__ g_lut,
+__global__ void __launch_bounds__(BLOCK_THREADS, VXL_RESOLVE_BLOCKS) k_resolve_ambient(FrameView F, ViewK K, const float* __restrict__ g_lut,
                                                                    const uint32_t* __restrict__ albedo, const uint32_t* __restrict__ depth_full,
                                                                    const float* __restrict__ shadow, const float* __restrict__ ao,
                                                                    float4* __restrict__ out) {
@@ -115,7 +119,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_resolve_ambient(FrameView F, 
 }
 
 template <bool SPOT>
-__global__ void __launch_bounds__(BLOCK_THREADS) k_resolve_local(FrameView F, ViewK K, const uint32_t* __restrict__ albedo,
+__global__ void __launch_bounds__(BLOCK_THREADS, VXL_RESOLVE_BLOCKS) k_resolve_local(FrameView F, ViewK K, const uint32_t* __restrict__ albedo,
                                                                  const float* __restrict__ lights, int n_lights,
                                                                  const float* __restrict__ shadow, size_t plane_stride,
                                                                  float4* __restrict__ inout) {
