@@ -476,13 +476,35 @@ static int lighting_host_impl(vxl_ctx* c, vxl_volume* vol, const vxl_lighting_ho
     // bands are ranges of tiles (contiguous in the tile-compact planes).
     const int nt = a->frame.n_tiles;
     const bool by_tiles = a->frame.tile_h < 256 && nt >= 8;
-    // bands of a whole frame: about 1250 thread blocks of the ambient pass each (four waves), at most 16 -- 3 at 1080p, 12 at 4K
-    // (measured at 4K, float / packed planes: 4 bands 7.76 / 7.15 ms, 8: 7.03 / 6.74, 12: 6.86 / 6.71, 16: 6.84 / 6.79, 24: 7.22 / 7.55)
-    int NB = by_tiles ? 4 : (a->frame.tile_h >= 256 ? (int)std::max<size_t>(3, std::min<size_t>(16, px / 640000)) : 1);
+    // bands of a whole frame: one per 800 k pixels, at most 16 -- 3 at 1080p, 10 at 4K
+    // (measured at 4K with equal bands, float / packed planes: 4 bands 7.76 / 7.15 ms, 8: 7.03 / 6.74, 12: 6.86 / 6.71, 16: 6.84 / 6.79, 24: 7.22 / 7.55)
+    int NB = by_tiles ? 4 : (a->frame.tile_h >= 256 ? (int)std::max<size_t>(3, std::min<size_t>(16, px / 800000)) : 1);
     if (const char* nb = getenv("VXL_HOST_BANDS")) { if (*nb) NB = std::max(1, std::min(64, atoi(nb))); }   // tuning knob
     if (by_tiles) NB = std::min(NB, nt);
     const int band_h = ((a->frame.tile_h + NB - 1) / NB + 15) / 16 * 16;          // whole 16-row thread blocks
     const int band_t = (nt + NB - 1) / NB;
+    // Row bands of a whole frame: `starts[b]` .. `starts[b + 1]`, heights 1 : 2 : 4 : ... : 4 : 2 : 1 from six bands on (measured at 4K,
+    // packed / float planes: 12 equal bands 6.60 / 6.77 ms, ten ramped bands 6.46 / 6.72 ms; five or six bands with one large middle
+    // 6.49-6.52 / 7.0-7.5 ms).  VXL_HOST_SCHED="w0,w1,..." overrides the relative heights (tuning knob).
+    std::vector<int> starts;
+    if (!by_tiles) {
+        std::vector<double> w;
+        if (const char* sc = getenv("VXL_HOST_SCHED")) {
+            for (const char* q = sc; *q;) { char* e = nullptr; const double v = strtod(q, &e); if (e == q) break; if (v > 0) w.push_back(v); q = (*e == ',') ? e + 1 : e; }
+        }
+        if (w.empty() && NB >= 6) {                 // 1, 2, 4, ..., 4, 2, 1: a short first band starts the passes early, a short last one ends the read-back early
+            w.assign((size_t)NB, 4.0);
+            w[0] = w[NB - 1] = 1.0; w[1] = w[NB - 2] = 2.0;
+        }
+        if (!w.empty()) {
+            double tot = 0; for (double v : w) tot += v;
+            const int units = (a->frame.tile_h + 15) / 16;
+            double acc = 0; starts.push_back(0);
+            for (size_t i = 0; i + 1 < w.size(); ++i) { acc += w[i]; const int u = std::min(units, std::max(starts.back() / 16 + 1, (int)(acc / tot * units + 0.5))); starts.push_back(u * 16); }
+            starts.push_back(a->frame.tile_h);
+            NB = (int)starts.size() - 1;
+        }
+    }
     const size_t n_ev = 6 + (size_t)NB * 6;
     while (c->ev.size() < n_ev) { cudaEvent_t e; VXL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->ev.push_back(e); }
     cudaEvent_t* ev = c->ev.data();
@@ -510,6 +532,7 @@ static int lighting_host_impl(vxl_ctx* c, vxl_volume* vol, const vxl_lighting_ho
     if (by_tiles) c->light_plane_stride = px;                             // a band's light planes sit inside the shard's
     for (int b = 0; b < NB; ++b) {
         if (by_tiles) { t0 = b * band_t; tn = std::min(band_t, nt - t0); if (tn <= 0) break; }
+        else if (!starts.empty()) { r0 = starts[b]; rows = std::min(starts[b + 1], a->frame.tile_h) - r0; if (rows <= 0) continue; }
         else { r0 = b * band_h; rows = std::min(band_h, a->frame.tile_h - r0); if (rows <= 0) break; }
         const size_t bo = by_tiles ? (size_t)t0 * tile_px : 0;            // where the band starts in every plane
         vxl_frame fd = a->frame;
